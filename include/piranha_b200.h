@@ -1,0 +1,167 @@
+/*
+ * piranha_b200.h -- C ABI of the B200-native sparse polynomial multiplier.
+ *
+ * This is the drop-in boundary for ONE path of bluescarni/piranha:
+ *     series_multiplier<polynomial<Cf, kronecker_monomial<>>>  and the base_series_multiplier machinery.
+ * The reference has no FFI for this path: the plugin mechanism is the class-template protocol of
+ * series_multiplier (include/piranha/series_multiplier.hpp:37-56 -- construct from two series, then
+ * operator()() returns the product).  A specialisation of that template marshals the operands' terms to the
+ * structure-of-arrays form below, calls pk_mul(), and re-inserts the returned terms with
+ * rehash/_unique_insert/_update_size (INTEGRATION.md shows the binding).  Every entry point cites the
+ * reference interface it replaces; paths are relative to /root/reference/include/piranha/.
+ *
+ * Plain pointers and sizes only; no C++ or torch types.  Re-entrant: all mutable state lives in a pk_ctx
+ * (one CUDA device + one stream); different contexts may be used concurrently from different threads
+ * (base_series_multiplier.hpp:404-408: multipliers are built and consumed on one thread).
+ *
+ * Term format (both directions):
+ *   key[i]   int64 Kronecker code of the exponent vector, piranha's kronecker_array<int64_t> codification for
+ *            n_vars components (kronecker_array.hpp:274-307).  The per-component limits M_k the codification
+ *            uses are taken from the library's own restatement of kronecker_array.hpp:128-229, or from
+ *            pk_ctx_set_limits() when the caller's table differs (it depends on the C++ standard library).
+ *   mag[i*limbs .. ]  magnitude of the integer coefficient, `limbs` 64-bit limbs, least significant first
+ *            (the layout of mppp::integer's static storage / GMP's mpz limbs).
+ *   sign[i]  +1 or -1 (0 is accepted for a zero coefficient and contributes nothing).
+ * Results are returned sorted by key (canonical order), with unique keys and no zero coefficients
+ * (series invariants, series.hpp:1312-1320; sanitise_series, base_series_multiplier.hpp:855-949).
+ */
+#ifndef PIRANHA_B200_H
+#define PIRANHA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes and the exception the reference would have thrown (polynomial.hpp:1283, :1315;
+ * base_series_multiplier.hpp:356, :843-846). */
+#define PK_OK 0
+#define PK_E_ARGS 1      /* std::invalid_argument: mismatched n_vars, bad sizes, bad options */
+#define PK_E_KEY_RANGE 2 /* std::overflow_error "Kronecker monomial components are out of bounds"
+                            (check_bounds, polynomial.hpp:1118-1194) */
+#define PK_E_CF_WIDTH 3  /* coefficient bound exceeds the supported fixed accumulator width; never a silent wrap
+                            (the reference promotes to heap mpz instead, integer.hpp:67-85) */
+#define PK_E_NOMEM 4     /* std::bad_alloc */
+#define PK_E_CUDA 5      /* std::runtime_error: CUDA failure, or no sm_100 device present */
+#define PK_E_DEGREE 6    /* std::overflow_error from the checked degree subtraction of the truncation logic
+                            (degree_sub -> safe_int_sub, polynomial.hpp:1243-1252, :1504) */
+
+#define PK_MAX_VARS 40u  /* kronecker_array<int64_t> supports < 40 components */
+
+/* Accumulation strategy (pk_opts.algo). */
+#define PK_ALGO_AUTO 0u
+#define PK_ALGO_DENSE 1u /* dense accumulator in HBM indexed by the re-encoded (tight mixed-radix) code */
+#define PK_ALGO_HASH 2u  /* open-addressing hash table in HBM (replaces hash_set buckets, hash_set.hpp:1251-1327) */
+#define PK_ALGO_ZONE 3u  /* output range cut into zones, each accumulated in one SM's shared memory
+                            (the GPU form of the zone scheme of polynomial.hpp:1783-1966) */
+
+typedef struct pk_ctx pk_ctx;     /* one device + one stream + cached workspaces */
+typedef struct pk_dpoly pk_dpoly; /* a polynomial resident in HBM (sorted by key, with exponent/width metadata) */
+
+/* Host view of a polynomial: what fill_term_pointers (base_series_multiplier.hpp:89-154) walks, flattened. */
+typedef struct pk_poly {
+    uint64_t n;          /* number of terms (series::size()) */
+    uint32_t n_vars;     /* size of the symbol set (m_ss.size()) */
+    uint32_t limbs;      /* 64-bit limbs per coefficient magnitude, 1..2 for operands */
+    const int64_t *key;  /* n Kronecker codes, any order (hash_set order is unspecified) */
+    const uint64_t *mag; /* n * limbs */
+    const int8_t *sign;  /* n */
+} pk_poly;
+
+/* Library-owned result (pinned host memory); release with pk_result_free(). */
+typedef struct pk_result {
+    uint64_t n;
+    uint32_t n_vars;
+    uint32_t limbs;
+    int64_t *key;
+    uint64_t *mag;
+    int8_t *sign;
+    void *owner;
+} pk_result;
+
+/* Options of one multiplication.  Zero-initialise, set struct_size = sizeof(pk_opts). */
+typedef struct pk_opts {
+    uint32_t struct_size;
+    /* Truncation (polynomial::get_auto_truncate_degree(), polynomial.hpp:736-740, :1555-1573):
+     * 0 = none (untruncated_kronecker_mult), 1 = total degree, 2 = partial degree over degree_mask.
+     * A pair (i, j) is multiplied iff deg(t1_i) + deg(t2_j) <= max_degree (polynomial.hpp:1495-1509). */
+    int32_t trunc_mode;
+    int64_t max_degree;
+    const uint8_t *degree_mask; /* n_vars bytes, non-zero = variable counts (mode 2); ignored otherwise */
+    /* Output partition: this call computes only the result terms whose re-encoded code lies in part
+     * `part_index` of `part_count` disjoint, ordered ranges (cut so that pair counts are balanced; the cuts are
+     * a deterministic function of the operands, so every rank derives the same ones).  0/0 or 0/1 = everything. */
+    uint32_t part_index;
+    uint32_t part_count;
+    uint32_t algo;     /* PK_ALGO_* */
+    uint32_t reserved; /* must be 0 */
+} pk_opts;
+
+/* Counters of the most recent pk_mul()/pk_mul_dev() on a context, for benchmarks and tests. */
+typedef struct pk_stats {
+    uint64_t n1, n2;              /* operand sizes after the larger-first swap */
+    uint64_t term_products;       /* W: pairs (i, j) actually multiplied in this call's partition */
+    uint64_t result_terms;        /* R of this call's partition */
+    uint64_t code_range;          /* number of codes in the re-encoded output range */
+    uint64_t table_slots;         /* accumulator slots allocated (dense range, hash capacity, or zone capacity) */
+    uint32_t algo;                /* PK_ALGO_* actually used */
+    uint32_t acc_lanes;           /* 64-bit lanes (dense/hash) or 32-bit words (zone) per accumulator */
+    uint32_t chunk_bits;          /* payload bits per lane (deferred-carry radix), 0 for the zone path */
+    uint32_t result_limbs;        /* limbs per result coefficient */
+    uint32_t kernel_launches;     /* kernels launched by this call */
+    uint32_t retries;             /* hash-capacity / zone-split retries */
+    uint64_t total_launches;      /* kernels launched on this context since creation */
+    float mul_kernel_ms;          /* CUDA-event time of the dominant (pairing + accumulate) kernel */
+    float device_ms;              /* CUDA-event time of all device work of the call */
+} pk_stats;
+
+/* ---- context ---------------------------------------------------------------------------------------------- */
+
+/* Create a context on CUDA device `device`.  `stream` is a cudaStream_t to run on (e.g. the caller's current
+ * stream so its CUDA events see the work) or NULL for a private non-blocking stream.
+ * Fails with PK_E_CUDA when no usable GPU is present: there is no CPU fallback. */
+int pk_ctx_create(int device, void *stream, pk_ctx **out);
+void pk_ctx_destroy(pk_ctx *ctx);
+/* Message of the last error on this context (never NULL). */
+const char *pk_last_error(const pk_ctx *ctx);
+/* Override the Kronecker limits M_0..M_{n_vars-1} for `n_vars` components with the caller's
+ * kronecker_array<int64_t>::get_limits()[n_vars] (kronecker_array.hpp:251-254). */
+int pk_ctx_set_limits(pk_ctx *ctx, uint32_t n_vars, const int64_t *limits);
+/* Read the limits the context uses for `n_vars` components; returns PK_E_ARGS if n_vars is unsupported. */
+int pk_ctx_get_limits(const pk_ctx *ctx, uint32_t n_vars, int64_t *limits_out, int64_t *h_min_out, int64_t *h_max_out);
+int pk_get_stats(pk_ctx *ctx, pk_stats *out);
+
+/* ---- host-to-host product: the call behind series_multiplier::operator()() --------------------------------- */
+
+/* out = a * b.  Replaces series_multiplier<polynomial<Cf, kronecker_monomial<>>>(a, b)()
+ * (polynomial.hpp:1291-1298 ctor incl. check_bounds, :1332-1336 operator(), :1619-1628 execute,
+ * :1632-1672 untruncated_kronecker_mult, :1402-1449 _truncated_multiplication).
+ * Strong guarantee: on failure *out is zeroed (polynomial.hpp:1961-1965). */
+int pk_mul(pk_ctx *ctx, const pk_poly *a, const pk_poly *b, const pk_opts *opts, pk_result *out);
+void pk_result_free(pk_ctx *ctx, pk_result *r);
+
+/* ---- device-resident operands: chained products (f *= tmp, pow) without re-uploading ------------------------ */
+
+/* Copy a host polynomial to HBM, sort it by key and record its per-variable exponent bounds and coefficient
+ * width (the work of fill_term_pointers + the operand half of check_bounds). */
+int pk_upload(pk_ctx *ctx, const pk_poly *p, pk_dpoly **out);
+/* out = a * b with everything staying in HBM (same semantics and errors as pk_mul). */
+int pk_mul_dev(pk_ctx *ctx, const pk_dpoly *a, const pk_dpoly *b, const pk_opts *opts, pk_dpoly **out);
+/* Copy a device polynomial back into library-owned pinned host memory. */
+int pk_download(pk_ctx *ctx, const pk_dpoly *p, pk_result *out);
+void pk_dpoly_free(pk_ctx *ctx, pk_dpoly *p);
+uint64_t pk_dpoly_size(const pk_dpoly *p);
+uint32_t pk_dpoly_limbs(const pk_dpoly *p);
+uint32_t pk_dpoly_nvars(const pk_dpoly *p);
+/* Copy the terms into caller-provided DEVICE buffers (key: n int64, mag: n*limbs uint64 row-major, sign: n int8),
+ * e.g. torch tensors about to be all-gathered over NCCL.  Any pointer may be NULL to skip that array. */
+int pk_dpoly_export(pk_ctx *ctx, const pk_dpoly *p, void *d_key, void *d_mag, void *d_sign);
+/* Order-independent 64-bit digest of (key, coefficient) over all terms, computed on the device.  Digests of
+ * disjoint partitions add up (mod 2^64) to the digest of the whole product. */
+int pk_dpoly_digest(pk_ctx *ctx, const pk_dpoly *p, uint64_t *digest_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIRANHA_B200_H */

@@ -1,0 +1,726 @@
+// Host side of the C ABI (include/piranha_b200.h): context, operand upload, multiplication planning and
+// orchestration, result download.  The CUDA kernels live in pk_kernels.cuh (HBM/L2 accumulators) and
+// pk_zone.cuh (shared-memory zones).  There is no CPU fallback: every product is computed by the kernels.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "../host/kronecker_array.hpp"
+#include "pk_host.cuh"
+#include "pk_kernels.cuh"
+#include "pk_zone.cuh"
+
+using namespace pk;
+
+namespace
+{
+
+void fill_piranha_codec(const pk_ctx *ctx, u32 n_vars, CodecParams &cp)
+{
+    memset(&cp, 0, sizeof(cp));
+    cp.n_vars = n_vars;
+    cp.h_min = n_vars ? ctx->h_min[n_vars] : 0;
+    i64 ps = 1;
+    for (u32 v = 0; v < n_vars; ++v) {
+        const i64 M = ctx->limits[n_vars][v];
+        cp.M[v] = M;
+        cp.radix[v] = 2 * M + 1;
+        cp.pstride[v] = ps;
+        ps = (i64)((u64)ps * (u64)(2 * M + 1));
+        cp.step[v] = 1;
+        cp.tradix[v] = 1;
+    }
+}
+
+void ensure_meta(pk_ctx *ctx, pk_dpoly *p)
+{
+    if (p->has_meta) return;
+    const u32 nv = p->n_vars;
+    p->emin.assign(nv, 0);
+    p->emax.assign(nv, 0);
+    p->egcd.assign(nv, 0);
+    if (p->n == 0) {
+        p->max_bits = 0;
+        p->has_meta = true;
+        return;
+    }
+    MetaDev init;
+    for (u32 v = 0; v < PK_MAX_VARS; ++v) {
+        init.emin[v] = INT64_MAX;
+        init.emax[v] = INT64_MIN;
+        init.egcd[v] = 0;
+    }
+    init.max_bits = 0;
+    init.pad = 0;
+    memcpy(ctx->h_scratch, &init, sizeof(init));
+    CUDA_CHECK(cudaMemcpyAsync(ctx->d_meta, ctx->h_scratch, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    CodecParams cp;
+    fill_piranha_codec(ctx, nv, cp);
+    const u32 grid = std::min<u32>(grid_for(p->n, 256), (u32)ctx->sm_count * 8);
+    PK_LAUNCH(ctx, k_meta, grid, 256, 0, p->key, p->planes, p->n, p->limbs, p->stride, cp, ctx->d_meta);
+    CUDA_CHECK(cudaMemcpyAsync(ctx->h_scratch, ctx->d_meta, sizeof(MetaDev), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    const MetaDev *m = static_cast<const MetaDev *>(ctx->h_scratch);
+    for (u32 v = 0; v < nv; ++v) {
+        p->emin[v] = m->emin[v];
+        p->emax[v] = m->emax[v];
+        p->egcd[v] = m->egcd[v];
+    }
+    p->max_bits = m->max_bits;
+    p->has_meta = true;
+}
+
+template <typename K, typename V>
+void radix_sort_pairs(pk_ctx *ctx, const K *kin, K *kout, const V *vin, V *vout, u64 n, int end_bit)
+{
+    size_t tmp_bytes = 0;
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kin, kout, vin, vout, (int64_t)n, 0, end_bit, ctx->stream));
+    DevBuf tmp(ctx, tmp_bytes);
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, kin, kout, vin, vout, (int64_t)n, 0, end_bit, ctx->stream));
+}
+
+template <typename K>
+void radix_sort_keys(pk_ctx *ctx, const K *kin, K *kout, u64 n, int end_bit)
+{
+    size_t tmp_bytes = 0;
+    CUDA_CHECK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, kin, kout, (int64_t)n, 0, end_bit, ctx->stream));
+    DevBuf tmp(ctx, tmp_bytes);
+    CUDA_CHECK(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, kin, kout, (int64_t)n, 0, end_bit, ctx->stream));
+}
+
+pk_dpoly *upload_impl(pk_ctx *ctx, const pk_poly *p)
+{
+    if (!p) fail(PK_E_ARGS, "null polynomial");
+    if (p->n_vars >= ctx->limits.size()) fail(PK_E_ARGS, "too many variables for the Kronecker codification");
+    if (p->limbs < 1 || p->limbs > 2) fail(PK_E_CF_WIDTH, "operand coefficients must have 1 or 2 limbs");
+    if (p->n >= (1ull << 32)) fail(PK_E_ARGS, "operand too large");
+    if (p->n && (!p->key || !p->mag || !p->sign)) fail(PK_E_ARGS, "null term arrays");
+    const u64 n = p->n;
+    DPolyGuard g{ctx, new_dpoly(ctx, n, p->n_vars, p->limbs)};
+    if (n == 0) {
+        g.p->has_meta = true;
+        g.p->emin.assign(p->n_vars, 0);
+        g.p->emax.assign(p->n_vars, 0);
+        g.p->egcd.assign(p->n_vars, 0);
+        return g.release();
+    }
+    DevBuf raw_key(ctx, n * 8), raw_mag(ctx, n * p->limbs * 8), raw_sign(ctx, n);
+    CUDA_CHECK(cudaMemcpyAsync(raw_key.p, p->key, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(raw_mag.p, p->mag, n * p->limbs * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(raw_sign.p, p->sign, n, cudaMemcpyHostToDevice, ctx->stream));
+    // canonical order: ascending Kronecker code (the role of fill_term_pointers' per-bucket sort,
+    // base_series_multiplier.hpp:126-132; hash_set order itself is unspecified)
+    DevBuf fk(ctx, n * 8), fk2(ctx, n * 8), idx(ctx, n * 4), idx2(ctx, n * 4);
+    PK_LAUNCH(ctx, k_flip_keys, grid_for(n, 256), 256, 0, raw_key.as<i64>(), fk.as<u64>(), n);
+    PK_LAUNCH(ctx, k_iota32, grid_for(n, 256), 256, 0, idx.as<u32>(), n);
+    radix_sort_pairs(ctx, fk.as<u64>(), fk2.as<u64>(), idx.as<u32>(), idx2.as<u32>(), n, 64);
+    PK_LAUNCH(ctx, k_gather_terms, grid_for(n, 256), 256, 0, idx2.as<u32>(), fk2.as<u64>(), raw_mag.as<u64>(),
+              raw_sign.as<signed char>(), g.p->key, g.p->planes, g.p->sign, n, p->limbs, g.p->stride);
+    ensure_meta(ctx, g.p);
+    return g.release();
+}
+
+PinnedBuf *pinned_acquire(pk_ctx *ctx, size_t bytes)
+{
+    PinnedBuf *best = nullptr;
+    for (auto &b : ctx->pinned)
+        if (!b.in_use && b.bytes >= bytes && (!best || b.bytes < best->bytes)) best = &b;
+    if (!best) {
+        for (auto &b : ctx->pinned)
+            if (!b.in_use && b.ptr) { // recycle the slot of a too-small buffer
+                cudaFreeHost(b.ptr);
+                b.ptr = nullptr;
+                b.bytes = 0;
+            }
+        ctx->pinned.erase(std::remove_if(ctx->pinned.begin(), ctx->pinned.end(),
+                                         [](const PinnedBuf &b) { return !b.in_use && !b.ptr; }),
+                          ctx->pinned.end());
+        PinnedBuf nb;
+        nb.bytes = std::max<size_t>(bytes, 4096);
+        nb.bytes += nb.bytes / 8; // headroom so similar-sized results reuse it
+        CUDA_CHECK(cudaMallocHost(&nb.ptr, nb.bytes));
+        ctx->pinned.push_back(nb);
+        best = &ctx->pinned.back();
+    }
+    best->in_use = true;
+    return best;
+}
+
+void download_impl(pk_ctx *ctx, const pk_dpoly *p, pk_result *out)
+{
+    memset(out, 0, sizeof(*out));
+    out->n = p->n;
+    out->n_vars = p->n_vars;
+    out->limbs = p->limbs;
+    if (p->n == 0) return;
+    const u64 n = p->n;
+    const size_t key_b = (n * 8 + 63) & ~63ull, mag_b = (n * p->limbs * 8 + 63) & ~63ull, sign_b = (n + 63) & ~63ull;
+    PinnedBuf *pb = pinned_acquire(ctx, key_b + mag_b + sign_b);
+    char *base = static_cast<char *>(pb->ptr);
+    out->key = reinterpret_cast<int64_t *>(base);
+    out->mag = reinterpret_cast<uint64_t *>(base + key_b);
+    out->sign = reinterpret_cast<int8_t *>(base + key_b + mag_b);
+    out->owner = pb->ptr;
+    try {
+        CUDA_CHECK(cudaMemcpyAsync(out->key, p->key, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (p->limbs == 1) {
+            CUDA_CHECK(cudaMemcpyAsync(out->mag, p->planes, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            DevBuf aos(ctx, n * p->limbs * 8);
+            PK_LAUNCH(ctx, k_planes_to_aos, grid_for(n, 256), 256, 0, p->planes, aos.as<u64>(), n, p->limbs, p->stride);
+            CUDA_CHECK(cudaMemcpyAsync(out->mag, aos.p, n * p->limbs * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CUDA_CHECK(cudaMemcpyAsync(out->sign, p->sign, n, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    } catch (...) {
+        pb->in_use = false;
+        memset(out, 0, sizeof(*out));
+        throw;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ multiply
+
+Plan make_plan(pk_ctx *ctx, const pk_dpoly *A, const pk_dpoly *B, const pk_opts &o)
+{
+    Plan pl;
+    const u32 nv = A->n_vars;
+    pl.n_vars = nv;
+    fill_piranha_codec(ctx, nv, pl.cpA);
+    fill_piranha_codec(ctx, nv, pl.cpB);
+    fill_piranha_codec(ctx, nv, pl.cpR);
+    pl.cpA.trunc_mode = pl.cpB.trunc_mode = (u32)o.trunc_mode;
+    unsigned __int128 range = 1;
+    __int128 base = 0;
+    for (u32 v = 0; v < nv; ++v) {
+        const __int128 lo = (__int128)A->emin[v] + B->emin[v], hi = (__int128)A->emax[v] + B->emax[v];
+        const i64 M = ctx->limits[nv][v];
+        // check_bounds, polynomial.hpp:1189-1193
+        if (lo < -(__int128)M || hi > (__int128)M) fail(PK_E_KEY_RANGE, "Kronecker monomial components are out of bounds");
+        u64 g = gcd64(A->egcd[v], B->egcd[v]);
+        if (g == 0) g = 1;
+        const u64 span = (u64)(A->emax[v] - A->emin[v]) + (u64)(B->emax[v] - B->emin[v]);
+        const u64 tr = span / g + 1;
+        pl.cpA.emin[v] = A->emin[v];
+        pl.cpB.emin[v] = B->emin[v];
+        pl.cpR.emin[v] = (i64)lo;
+        pl.cpA.step[v] = pl.cpB.step[v] = pl.cpR.step[v] = (i64)g;
+        pl.cpA.stride[v] = pl.cpB.stride[v] = pl.cpR.stride[v] = (u64)range;
+        pl.cpA.tradix[v] = pl.cpB.tradix[v] = pl.cpR.tradix[v] = tr;
+        const bool counts = o.trunc_mode == 1 || (o.trunc_mode == 2 && o.degree_mask && o.degree_mask[v]);
+        pl.cpA.mask[v] = pl.cpB.mask[v] = counts ? 1 : 0;
+        range *= tr;
+        if (range >= ((unsigned __int128)1 << 62)) fail(PK_E_KEY_RANGE, "re-encoded code range overflow");
+        base += lo * (__int128)pl.cpR.pstride[v];
+    }
+    pl.base_code = (i64)base;
+    pl.range = (u64)range;
+    pl.code_bits = std::max<u32>(1, bit_length(range));
+    // coefficient widths: |a_i * b_j| < 2^(bitsA + bitsB); at most min(n1, n2) products land on one key
+    pl.LA = std::max<u32>(1, (A->max_bits + 63) / 64);
+    pl.LB = std::max<u32>(1, (B->max_bits + 63) / 64);
+    if (pl.LA > 2 || pl.LB > 2) fail(PK_E_CF_WIDTH, "operand coefficient wider than 2 limbs");
+    pl.prod_bits = std::max<u32>(1, A->max_bits + B->max_bits);
+    pl.cnt_bits = bit_length(std::min(A->n, B->n));
+    if (pl.cnt_bits > 31) fail(PK_E_ARGS, "operands too large");
+    pl.cbits = std::min<u32>(62, 63 - pl.cnt_bits);
+    pl.nl = (pl.prod_bits + pl.cbits - 1) / pl.cbits;
+    pl.out_limbs = (pl.prod_bits + pl.cnt_bits + 63) / 64;
+    if (pl.out_limbs > (u32)kMaxAccLimbs - 1) fail(PK_E_CF_WIDTH, "coefficient bound exceeds the accumulator width");
+    return pl;
+}
+
+template <int MODE, bool FILTER>
+void launch_mul_global(pk_ctx *ctx, const Plan &pl, const MulArgs &args)
+{
+    const u32 R = (pl.LA + pl.LB == 2) ? 8 : 4;
+    const u32 TI = (kMulThreads / 32) * R;
+    const u64 tiles = ((args.nA + TI - 1) / TI) * ((args.nB + kTileJ - 1) / kTileJ);
+    if (tiles >= (1ull << 31)) fail(PK_E_ARGS, "grid too large");
+    const u32 grid = (u32)tiles;
+    if (pl.LA == 1 && pl.LB == 1) PK_LAUNCH(ctx, (k_mul_global<MODE, 1, 1, FILTER>), grid, kMulThreads, 0, args);
+    else if (pl.LA == 2 && pl.LB == 1) PK_LAUNCH(ctx, (k_mul_global<MODE, 2, 1, FILTER>), grid, kMulThreads, 0, args);
+    else if (pl.LA == 1 && pl.LB == 2) PK_LAUNCH(ctx, (k_mul_global<MODE, 1, 2, FILTER>), grid, kMulThreads, 0, args);
+    else PK_LAUNCH(ctx, (k_mul_global<MODE, 2, 2, FILTER>), grid, kMulThreads, 0, args);
+}
+
+pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in)
+{
+    pk_opts o{};
+    if (opts_in) {
+        if (opts_in->struct_size != sizeof(pk_opts)) fail(PK_E_ARGS, "pk_opts.struct_size mismatch");
+        o = *opts_in;
+    }
+    if (!a || !b) fail(PK_E_ARGS, "null operand");
+    // base_series_multiplier.hpp:365-367: "incompatible arguments sets"
+    if (a->n_vars != b->n_vars) fail(PK_E_ARGS, "incompatible arguments sets");
+    if (o.trunc_mode < 0 || o.trunc_mode > 2 || o.reserved != 0 || o.algo > PK_ALGO_ZONE) fail(PK_E_ARGS, "bad options");
+    if (o.trunc_mode == 2 && a->n_vars && !o.degree_mask) fail(PK_E_ARGS, "partial truncation needs degree_mask");
+    u32 P = o.part_count ? o.part_count : 1;
+    if (o.part_index >= P) fail(PK_E_ARGS, "part_index out of range");
+    const u32 nv = a->n_vars;
+
+    ctx->call_launches = 0;
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    ctx->ev_valid = false;
+    // larger series first, base_series_multiplier.hpp:368-372
+    pk_dpoly *A = a, *B = b;
+    if (A->n < B->n) std::swap(A, B);
+    ctx->stats.n1 = A->n;
+    ctx->stats.n2 = B->n;
+    if (A->n == 0 || B->n == 0) { // polynomial.hpp:1654-1656: empty series, symbol set preserved
+        pk_dpoly *r = new_dpoly(ctx, 0, nv, 1);
+        r->has_meta = true;
+        r->emin.assign(nv, 0);
+        r->emax.assign(nv, 0);
+        r->egcd.assign(nv, 0);
+        return r;
+    }
+    ensure_meta(ctx, A);
+    ensure_meta(ctx, B);
+    Plan pl = make_plan(ctx, A, B, o);
+    const bool trunc = o.trunc_mode != 0;
+    const u64 nA = A->n, nB = B->n;
+
+    CUDA_CHECK(cudaEventRecord(ctx->ev_begin, ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(MulCounters), ctx->stream));
+
+    // ---- operand preparation
+    DevBuf keyA(ctx, (nA + 2) * 8), keyB(ctx, (nB + 2) * 8);
+    DevBuf degA(ctx, trunc ? nA * 8 : 0), degB(ctx, trunc ? nB * 8 : 0);
+    PK_LAUNCH(ctx, k_prepare, grid_for(nA, 256), 256, 0, A->key, A->sign, nA, pl.cpA, keyA.as<u64>(),
+              degA.as<i64>());
+    PK_LAUNCH(ctx, k_prepare, grid_for(nB, 256), 256, 0, B->key, B->sign, nB, pl.cpB, keyB.as<u64>(),
+              degB.as<i64>());
+    const u64 *kB = keyB.as<u64>();
+    const u64 *mB = B->planes;
+    u64 strideB = B->stride;
+    std::unique_ptr<DevBuf> keyB2, magB2, slbuf, degBs;
+    if (trunc) {
+        // second operand stable-sorted by degree (polynomial.hpp:1427-1442), then the skip limits
+        DevBuf fd(ctx, nB * 8), idx(ctx, nB * 4), idx2(ctx, nB * 4);
+        degBs.reset(new DevBuf(ctx, nB * 8));
+        PK_LAUNCH(ctx, k_flip_deg, grid_for(nB, 256), 256, 0, degB.as<i64>(), fd.as<u64>(), nB);
+        PK_LAUNCH(ctx, k_iota32, grid_for(nB, 256), 256, 0, idx.as<u32>(), nB);
+        radix_sort_pairs(ctx, fd.as<u64>(), degBs->as<u64>(), idx.as<u32>(), idx2.as<u32>(), nB, 64);
+        keyB2.reset(new DevBuf(ctx, (nB + 2) * 8));
+        const u64 st2 = ((nB + 1) & ~1ull) + 2;
+        magB2.reset(new DevBuf(ctx, st2 * pl.LB * 8));
+        PK_LAUNCH(ctx, k_permute_operand, grid_for(nB, 256), 256, 0, idx2.as<u32>(), keyB.as<u64>(), B->planes,
+                  keyB2->as<u64>(), magB2->as<u64>(), nB, pl.LB, B->stride, st2);
+        kB = keyB2->as<u64>();
+        mB = magB2->as<u64>();
+        strideB = st2;
+        slbuf.reset(new DevBuf(ctx, nA * 4));
+        PK_LAUNCH(ctx, k_skip_limits, grid_for(nA, 256), 256, 0, degA.as<i64>(), nA, degBs->as<u64>(), nB, o.max_degree,
+                  slbuf->as<u32>(), ctx->d_ctr);
+    }
+
+    // ---- output partition [lo, hi) in tight-code space
+    u64 lo = 0, hi = pl.range;
+    if (P > 1) {
+        const u32 SA = (u32)std::min<u64>(nA, 1024), SB = (u32)std::min<u64>(nB, 1024);
+        const u64 S = (u64)SA * SB;
+        DevBuf sums(ctx, S * 8), sorted(ctx, S * 8);
+        // degrees of B in its (possibly degree-sorted) order are needed for the truncation filter of the sample
+        DevBuf degB_perm(ctx, trunc ? nB * 8 : 0);
+        const i64 *dB = degB.as<i64>();
+        if (trunc) { // degBs holds flipped sorted degrees; unflip into degB_perm
+            PK_LAUNCH(ctx, k_flip_deg, grid_for(nB, 256), 256, 0, (const i64 *)degBs->as<u64>(), degB_perm.as<u64>(), nB);
+            dB = degB_perm.as<i64>();
+        }
+        PK_LAUNCH(ctx, k_sample_sums, grid_for(S, 256), 256, 0, keyA.as<u64>(), nA, kB, nB, SA, SB, degA.as<i64>(), dB,
+                  o.max_degree, trunc ? 1 : 0, sums.as<u64>(), ctx->d_ctr);
+        radix_sort_keys(ctx, sums.as<u64>(), sorted.as<u64>(), S, 64);
+        MulCounters *hc = static_cast<MulCounters *>(ctx->h_scratch);
+        CUDA_CHECK(cudaMemcpyAsync(hc, ctx->d_ctr, sizeof(MulCounters), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        const u64 valid = hc->aux;
+        u64 *cuts = reinterpret_cast<u64 *>(static_cast<char *>(ctx->h_scratch) + 1024);
+        cuts[0] = 0;
+        for (u32 p = 1; p < P; ++p) {
+            if (valid == 0) cuts[p] = 0;
+            else
+                CUDA_CHECK(cudaMemcpyAsync(&cuts[p], sorted.as<u64>() + (u64)((unsigned __int128)valid * p / P), 8,
+                                           cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        cuts[P] = pl.range;
+        for (u32 p = 1; p <= P; ++p) cuts[p] = std::max(cuts[p], cuts[p - 1]);
+        lo = cuts[o.part_index];
+        hi = cuts[o.part_index + 1];
+    }
+    const bool filter = trunc || P > 1;
+    const u64 sub_range = hi - lo;
+
+    // ---- strategy
+    const unsigned __int128 w_bound = (unsigned __int128)nA * nB;
+    u32 algo = o.algo;
+    if (algo == PK_ALGO_AUTO) algo = choose_algo(ctx, pl, nA, nB, sub_range, trunc);
+    pk_dpoly *result = nullptr;
+    if (algo == PK_ALGO_ZONE) {
+        result = zone_multiply(ctx, pl, A, B, keyA.as<u64>(), kB, mB, strideB, trunc ? slbuf->as<u32>() : nullptr, lo, hi,
+                               trunc, nv);
+        if (!result) algo = PK_ALGO_AUTO_FALLBACK; // zone path declined (configuration outside its envelope)
+    }
+    if (algo == PK_ALGO_AUTO_FALLBACK) {
+        const unsigned __int128 dense_bytes = (unsigned __int128)sub_range * pl.nl * 8;
+        algo = (sub_range <= 8 * w_bound && dense_bytes <= ((unsigned __int128)16 << 30)) ? PK_ALGO_DENSE : PK_ALGO_HASH;
+    }
+    if (!result) {
+        MulArgs m{};
+        m.keyA = keyA.as<u64>();
+        m.magA = A->planes;
+        m.strideA = A->stride;
+        m.nA = nA;
+        m.keyB = kB;
+        m.magB = mB;
+        m.strideB = strideB;
+        m.nB = nB;
+        m.sl = trunc ? slbuf->as<u32>() : nullptr;
+        m.lo = lo;
+        m.hi = hi;
+        m.nl = pl.nl;
+        m.cbits = pl.cbits;
+        m.keys_sorted = trunc ? 0 : 1;
+        m.ctr = ctx->d_ctr;
+        FinalArgs f{};
+        f.nl = pl.nl;
+        f.cbits = pl.cbits;
+        f.out_limbs = pl.out_limbs;
+        f.cp = pl.cpR;
+        f.base_code = pl.base_code;
+        f.ctr = ctx->d_ctr;
+        size_t free_b = 0, total_b = 0;
+        CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+        MulCounters *hc = static_cast<MulCounters *>(ctx->h_scratch);
+        if (algo == PK_ALGO_DENSE) {
+            const unsigned __int128 bytes = (unsigned __int128)std::max<u64>(sub_range, 1) * pl.nl * 8;
+            if (bytes > (unsigned __int128)total_b) fail(PK_E_NOMEM, "dense accumulator does not fit in device memory");
+            DevBuf acc(ctx, (size_t)bytes);
+            CUDA_CHECK(cudaMemsetAsync(acc.p, 0, (size_t)bytes, ctx->stream));
+            m.acc = acc.as<u64>() - lo * pl.nl; // indexed by absolute code
+            CUDA_CHECK(cudaEventRecord(ctx->ev_mul0, ctx->stream));
+            if (filter) launch_mul_global<0, true>(ctx, pl, m);
+            else launch_mul_global<0, false>(ctx, pl, m);
+            CUDA_CHECK(cudaEventRecord(ctx->ev_mul1, ctx->stream));
+            // normalise + ordered compaction
+            f.acc = m.acc;
+            f.n_slots = sub_range;
+            f.code0 = lo;
+            const u32 nblocks = grid_for(sub_range, kFinThreads * kFinItems);
+            DevBuf counts(ctx, (size_t)nblocks * 4), offsets(ctx, (size_t)nblocks * 8);
+            f.block_counts = counts.as<u32>();
+            f.block_offsets = offsets.as<u64>();
+            PK_LAUNCH(ctx, k_dense_count, nblocks, kFinThreads, 0, f);
+            PK_LAUNCH(ctx, k_scan_counts, 1, 1024, 0, counts.as<u32>(), offsets.as<u64>(), (u64)nblocks, ctx->d_ctr);
+            CUDA_CHECK(cudaMemcpyAsync(hc, ctx->d_ctr, sizeof(MulCounters), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            const u64 n_out = hc->n_out;
+            DPolyGuard g{ctx, new_dpoly(ctx, n_out, nv, pl.out_limbs)};
+            if (n_out) {
+                f.okey = g.p->key;
+                f.oplanes = g.p->planes;
+                f.ostride = g.p->stride;
+                f.osign = g.p->sign;
+                PK_LAUNCH(ctx, k_dense_write, nblocks, kFinThreads, 0, f);
+            }
+            result = g.release();
+            ctx->stats.table_slots = sub_range;
+        } else {
+            unsigned __int128 distinct = std::min<unsigned __int128>(w_bound, sub_range);
+            u64 cap = 1024;
+            while ((unsigned __int128)cap < 2 * distinct) cap <<= 1;
+            u32 rec_words = 2;
+            while (rec_words < pl.nl + 1) rec_words <<= 1;
+            const unsigned __int128 bytes = (unsigned __int128)cap * rec_words * 8;
+            if (bytes > (unsigned __int128)free_b / 10 * 9) fail(PK_E_NOMEM, "hash table does not fit in device memory");
+            if (cap > (1ull << 32)) fail(PK_E_NOMEM, "hash table too large");
+            DevBuf tab(ctx, (size_t)bytes);
+            PK_LAUNCH(ctx, k_hash_init, grid_for((u64)cap * rec_words, 256), 256, 0, tab.as<u64>(), (u64)cap * rec_words,
+                      rec_words);
+            m.acc = tab.as<u64>();
+            m.cap_mask = cap - 1;
+            u32 lg = 0;
+            while ((1ull << lg) < cap) ++lg;
+            m.hash_shift = 64 - lg;
+            m.rec_words = rec_words;
+            CUDA_CHECK(cudaEventRecord(ctx->ev_mul0, ctx->stream));
+            if (filter) launch_mul_global<1, true>(ctx, pl, m);
+            else launch_mul_global<1, false>(ctx, pl, m);
+            CUDA_CHECK(cudaEventRecord(ctx->ev_mul1, ctx->stream));
+            f.acc = tab.as<u64>();
+            f.n_slots = cap;
+            f.rec_words = rec_words;
+            // the number of occupied slots is only known on the device: collect into buffers sized by a first count
+            DevBuf codes(ctx, (size_t)std::min<unsigned __int128>(distinct, cap) * 8),
+                slots(ctx, (size_t)std::min<unsigned __int128>(distinct, cap) * 4);
+            const u32 cgrid = std::min<u32>(grid_for(cap, 256), (u32)ctx->sm_count * 16);
+            PK_LAUNCH(ctx, k_hash_collect, cgrid, 256, 0, f, codes.as<u64>(), slots.as<u32>());
+            CUDA_CHECK(cudaMemcpyAsync(hc, ctx->d_ctr, sizeof(MulCounters), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            const u64 n_out = hc->n_out;
+            DPolyGuard g{ctx, new_dpoly(ctx, n_out, nv, pl.out_limbs)};
+            if (n_out) {
+                DevBuf codes2(ctx, n_out * 8), slots2(ctx, n_out * 4);
+                radix_sort_pairs(ctx, codes.as<u64>(), codes2.as<u64>(), slots.as<u32>(), slots2.as<u32>(), n_out,
+                                 (int)pl.code_bits);
+                f.okey = g.p->key;
+                f.oplanes = g.p->planes;
+                f.ostride = g.p->stride;
+                f.osign = g.p->sign;
+                PK_LAUNCH(ctx, k_hash_write, grid_for(n_out, 256), 256, 0, f, codes2.as<u64>(), slots2.as<u32>(), n_out);
+            }
+            result = g.release();
+            ctx->stats.table_slots = cap;
+        }
+        ctx->stats.acc_lanes = pl.nl;
+        ctx->stats.chunk_bits = pl.cbits;
+    }
+    DPolyGuard rg{ctx, result};
+    CUDA_CHECK(cudaEventRecord(ctx->ev_end, ctx->stream));
+    MulCounters *hc = static_cast<MulCounters *>(ctx->h_scratch);
+    CUDA_CHECK(cudaMemcpyAsync(hc, ctx->d_ctr, sizeof(MulCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->ev_valid = true;
+    if (hc->flags & kFlagDegreeOverflow) fail(PK_E_DEGREE, "overflow in the truncation degree arithmetic");
+    if (hc->flags & kFlagTableFull) fail(PK_E_NOMEM, "accumulator table overflow");
+    if (hc->flags & kFlagWidth) fail(PK_E_CF_WIDTH, "coefficient exceeded the proven bound (internal error)");
+    rg.p->max_bits = hc->max_bits;
+    // trim limbs that the actual coefficients never reach (planes are independent, so this is free)
+    rg.p->limbs = std::max<u32>(1, std::min<u32>(rg.p->limbs, (hc->max_bits + 63) / 64));
+    ctx->stats.term_products = filter ? hc->pairs : (u64)w_bound;
+    ctx->stats.result_terms = rg.p->n;
+    ctx->stats.code_range = pl.range;
+    ctx->stats.algo = algo;
+    ctx->stats.result_limbs = rg.p->limbs;
+    ctx->stats.kernel_launches = ctx->call_launches;
+    return rg.release();
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------ C ABI
+
+#define PK_TRY(ctx_expr, ...)                                    \
+    pk_ctx *ctx__ = (ctx_expr);                                  \
+    try {                                                        \
+        __VA_ARGS__;                                             \
+        return PK_OK;                                            \
+    } catch (const PkError &e) {                                 \
+        if (ctx__) ctx__->err = e.msg;                           \
+        return e.code;                                           \
+    } catch (const std::bad_alloc &) {                           \
+        if (ctx__) ctx__->err = "host allocation failure";       \
+        return PK_E_NOMEM;                                       \
+    } catch (const std::exception &e) {                          \
+        if (ctx__) ctx__->err = e.what();                        \
+        return PK_E_CUDA;                                        \
+    }
+
+extern "C" {
+
+int pk_ctx_create(int device, void *stream, pk_ctx **out)
+{
+    if (!out) return PK_E_ARGS;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return PK_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PK_E_CUDA;
+    if (prop.major < 10) return PK_E_CUDA; // kernels are built for sm_100a only
+    std::unique_ptr<pk_ctx> c(new (std::nothrow) pk_ctx);
+    if (!c) return PK_E_NOMEM;
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) return PK_E_CUDA;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    if (stream) {
+        c->stream = static_cast<cudaStream_t>(stream);
+    } else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return PK_E_CUDA;
+        c->own_stream = true;
+    }
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX; // keep freed blocks cached: no cudaMalloc in steady state
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    bool ok = cudaEventCreate(&c->ev_begin) == cudaSuccess && cudaEventCreate(&c->ev_mul0) == cudaSuccess
+              && cudaEventCreate(&c->ev_mul1) == cudaSuccess && cudaEventCreate(&c->ev_end) == cudaSuccess
+              && cudaMallocHost(&c->h_scratch, kScratchBytes) == cudaSuccess
+              && cudaMalloc((void **)&c->d_ctr, sizeof(MulCounters)) == cudaSuccess
+              && cudaMalloc((void **)&c->d_meta, sizeof(MetaDev)) == cudaSuccess
+              && cudaMalloc((void **)&c->d_digest, 8) == cudaSuccess;
+    if (!ok) {
+        pk_ctx_destroy(c.release());
+        return PK_E_CUDA;
+    }
+    const auto &tab = pb200::kronecker_array<int64_t>::get_limits();
+    c->limits.resize(tab.size());
+    c->h_min.resize(tab.size());
+    c->h_max.resize(tab.size());
+    for (size_t m = 0; m < tab.size(); ++m) {
+        c->limits[m] = std::get<0>(tab[m]);
+        c->h_min[m] = std::get<1>(tab[m]);
+        c->h_max[m] = std::get<2>(tab[m]);
+    }
+    zone_configure(c.get());
+    *out = c.release();
+    return PK_OK;
+}
+
+void pk_ctx_destroy(pk_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &b : ctx->pinned)
+        if (b.ptr) cudaFreeHost(b.ptr);
+    if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+    if (ctx->d_ctr) cudaFree(ctx->d_ctr);
+    if (ctx->d_meta) cudaFree(ctx->d_meta);
+    if (ctx->d_digest) cudaFree(ctx->d_digest);
+    if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->ev_mul0) cudaEventDestroy(ctx->ev_mul0);
+    if (ctx->ev_mul1) cudaEventDestroy(ctx->ev_mul1);
+    if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *pk_last_error(const pk_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int pk_ctx_set_limits(pk_ctx *ctx, uint32_t n_vars, const int64_t *limits)
+{
+    if (!ctx || !limits || n_vars == 0 || n_vars >= PK_MAX_VARS) return PK_E_ARGS;
+    // recompute h_min / h_max the way determine_limit does (kronecker_array.hpp:155-157) and validate the table
+    __int128 c = 1, hmax = 0;
+    for (uint32_t v = 0; v < n_vars; ++v) {
+        if (limits[v] <= 0) return PK_E_ARGS;
+        hmax += c * limits[v];
+        c *= 2 * (__int128)limits[v] + 1;
+        if (c > ((__int128)1 << 64)) return PK_E_ARGS;
+    }
+    if (hmax > (__int128)INT64_MAX || 2 * hmax + 1 > (__int128)INT64_MAX) return PK_E_ARGS;
+    if (ctx->limits.size() <= n_vars) {
+        ctx->limits.resize(n_vars + 1);
+        ctx->h_min.resize(n_vars + 1);
+        ctx->h_max.resize(n_vars + 1);
+    }
+    ctx->limits[n_vars].assign(limits, limits + n_vars);
+    ctx->h_min[n_vars] = (int64_t)-hmax;
+    ctx->h_max[n_vars] = (int64_t)hmax;
+    return PK_OK;
+}
+
+int pk_ctx_get_limits(const pk_ctx *ctx, uint32_t n_vars, int64_t *limits_out, int64_t *h_min_out, int64_t *h_max_out)
+{
+    if (!ctx || n_vars >= ctx->limits.size() || (n_vars && ctx->limits[n_vars].size() != n_vars)) return PK_E_ARGS;
+    if (limits_out)
+        for (uint32_t v = 0; v < n_vars; ++v) limits_out[v] = ctx->limits[n_vars][v];
+    if (h_min_out) *h_min_out = ctx->h_min[n_vars];
+    if (h_max_out) *h_max_out = ctx->h_max[n_vars];
+    return PK_OK;
+}
+
+int pk_get_stats(pk_ctx *ctx, pk_stats *out)
+{
+    if (!ctx || !out) return PK_E_ARGS;
+    if (ctx->ev_valid) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev_mul0, ctx->ev_mul1) == cudaSuccess) ctx->stats.mul_kernel_ms = ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end) == cudaSuccess) ctx->stats.device_ms = ms;
+    }
+    ctx->stats.total_launches = ctx->total_launches;
+    *out = ctx->stats;
+    return PK_OK;
+}
+
+int pk_upload(pk_ctx *ctx, const pk_poly *p, pk_dpoly **out)
+{
+    if (!ctx || !out) return PK_E_ARGS;
+    *out = nullptr;
+    PK_TRY(ctx, { cudaSetDevice(ctx->device); *out = upload_impl(ctx, p); })
+}
+
+int pk_mul_dev(pk_ctx *ctx, const pk_dpoly *a, const pk_dpoly *b, const pk_opts *opts, pk_dpoly **out)
+{
+    if (!ctx || !out) return PK_E_ARGS;
+    *out = nullptr;
+    PK_TRY(ctx, {
+        cudaSetDevice(ctx->device);
+        *out = mul_impl(ctx, const_cast<pk_dpoly *>(a), const_cast<pk_dpoly *>(b), opts);
+    })
+}
+
+int pk_download(pk_ctx *ctx, const pk_dpoly *p, pk_result *out)
+{
+    if (!ctx || !p || !out) return PK_E_ARGS;
+    PK_TRY(ctx, { cudaSetDevice(ctx->device); download_impl(ctx, p, out); })
+}
+
+void pk_dpoly_free(pk_ctx *ctx, pk_dpoly *p)
+{
+    if (!ctx || !p) return;
+    cudaSetDevice(ctx->device);
+    free_dpoly_arrays(ctx, p);
+    delete p;
+}
+
+uint64_t pk_dpoly_size(const pk_dpoly *p) { return p ? p->n : 0; }
+uint32_t pk_dpoly_limbs(const pk_dpoly *p) { return p ? p->limbs : 0; }
+uint32_t pk_dpoly_nvars(const pk_dpoly *p) { return p ? p->n_vars : 0; }
+
+int pk_dpoly_export(pk_ctx *ctx, const pk_dpoly *p, void *d_key, void *d_mag, void *d_sign)
+{
+    if (!ctx || !p) return PK_E_ARGS;
+    PK_TRY(ctx, {
+        cudaSetDevice(ctx->device);
+        if (p->n) {
+            if (d_key) CUDA_CHECK(cudaMemcpyAsync(d_key, p->key, p->n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            if (d_mag)
+                PK_LAUNCH(ctx, k_planes_to_aos, grid_for(p->n, 256), 256, 0, p->planes, static_cast<u64 *>(d_mag), p->n,
+                          p->limbs, p->stride);
+            if (d_sign) CUDA_CHECK(cudaMemcpyAsync(d_sign, p->sign, p->n, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    })
+}
+
+int pk_dpoly_digest(pk_ctx *ctx, const pk_dpoly *p, uint64_t *digest_out)
+{
+    if (!ctx || !p || !digest_out) return PK_E_ARGS;
+    PK_TRY(ctx, {
+        cudaSetDevice(ctx->device);
+        CUDA_CHECK(cudaMemsetAsync(ctx->d_digest, 0, 8, ctx->stream));
+        if (p->n) {
+            const u32 grid = std::min<u32>(grid_for(p->n, 256), (u32)ctx->sm_count * 8);
+            PK_LAUNCH(ctx, k_digest, grid, 256, 0, p->key, p->planes, p->sign, p->n, p->limbs,
+                      p->stride, ctx->d_digest);
+        }
+        CUDA_CHECK(cudaMemcpyAsync(ctx->h_scratch, ctx->d_digest, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        *digest_out = *static_cast<uint64_t *>(ctx->h_scratch);
+    })
+}
+
+int pk_mul(pk_ctx *ctx, const pk_poly *a, const pk_poly *b, const pk_opts *opts, pk_result *out)
+{
+    if (!ctx || !out) return PK_E_ARGS;
+    memset(out, 0, sizeof(*out));
+    PK_TRY(ctx, {
+        cudaSetDevice(ctx->device);
+        DPolyGuard da{ctx, upload_impl(ctx, a)};
+        DPolyGuard db{ctx, (a == b) ? nullptr : upload_impl(ctx, b)};
+        DPolyGuard dr{ctx, mul_impl(ctx, da.p, db.p ? db.p : da.p, opts)};
+        download_impl(ctx, dr.p, out);
+    })
+}
+
+void pk_result_free(pk_ctx *ctx, pk_result *r)
+{
+    if (!ctx || !r) return;
+    for (auto &b : ctx->pinned)
+        if (b.ptr && b.ptr == r->owner) b.in_use = false;
+    memset(r, 0, sizeof(*r));
+}
+
+} // extern "C"

@@ -1,0 +1,184 @@
+// Host-side objects shared by the C ABI implementation (pk_abi.cu) and the zone path (pk_zone.cuh).
+#pragma once
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "pk_device.cuh"
+
+// ------------------------------------------------------------------------------------------------ objects
+
+struct PinnedBuf {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    bool in_use = false;
+};
+
+struct pk_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    std::vector<std::vector<int64_t>> limits; // [n_vars] -> M_k
+    std::vector<int64_t> h_min, h_max;
+    pk_stats stats{};
+    uint64_t total_launches = 0;
+    uint32_t call_launches = 0;
+    cudaEvent_t ev_begin = nullptr, ev_mul0 = nullptr, ev_mul1 = nullptr, ev_end = nullptr;
+    bool ev_valid = false;
+    void *h_scratch = nullptr; // small pinned read-back area
+    pk::MulCounters *d_ctr = nullptr;
+    pk::MetaDev *d_meta = nullptr;
+    pk::u64 *d_digest = nullptr;
+    std::vector<PinnedBuf> pinned;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+};
+
+struct pk_dpoly {
+    uint64_t n = 0, stride = 0;
+    uint32_t n_vars = 0, limbs = 1;
+    pk::i64 *key = nullptr;     // n (+2 padding) piranha codes, ascending
+    pk::u64 *planes = nullptr;  // limbs planes of `stride` words
+    signed char *sign = nullptr;
+    bool has_meta = false;
+    std::vector<int64_t> emin, emax;
+    std::vector<uint64_t> egcd;
+    uint32_t max_bits = 0;
+};
+
+
+namespace pk
+{
+
+constexpr uint32_t PK_ALGO_AUTO_FALLBACK = 100u; // internal: pick dense or hash by size
+
+constexpr size_t kScratchBytes = 1 << 16;
+
+struct PkError {
+    int code;
+    std::string msg;
+};
+
+[[noreturn]] inline void fail(int code, std::string msg) { throw PkError{code, std::move(msg)}; }
+
+#define CUDA_CHECK(expr)                                                                                    \
+    do {                                                                                                    \
+        cudaError_t e__ = (expr);                                                                           \
+        if (e__ != cudaSuccess) {                                                                           \
+            if (e__ == cudaErrorMemoryAllocation) fail(PK_E_NOMEM, std::string("CUDA out of memory: ") + #expr); \
+            fail(PK_E_CUDA, std::string(cudaGetErrorString(e__)) + " at " + #expr);                         \
+        }                                                                                                   \
+    } while (0)
+
+// count a launch of one of OUR kernels (cub's internal launches are library launches and are not counted)
+#define PK_LAUNCH(ctx, kernel, grid, block, smem, ...)                   \
+    do {                                                                 \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
+        ++(ctx)->call_launches;                                          \
+        ++(ctx)->total_launches;                                         \
+        CUDA_CHECK(cudaGetLastError());                                  \
+    } while (0)
+
+struct DevBuf { // stream-ordered allocation with scope lifetime
+    pk_ctx *ctx;
+    void *p = nullptr;
+    DevBuf(pk_ctx *c, size_t bytes) : ctx(c)
+    {
+        if (bytes) CUDA_CHECK(cudaMallocAsync(&p, bytes, c->stream));
+    }
+    ~DevBuf()
+    {
+        if (p) cudaFreeAsync(p, ctx->stream);
+    }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    template <typename T>
+    T *as() const
+    {
+        return static_cast<T *>(p);
+    }
+};
+
+inline u32 grid_for(u64 n, u32 block) { return (u32)std::max<u64>(1, (n + block - 1) / block); }
+
+inline u32 bit_length(unsigned __int128 x)
+{
+    u32 b = 0;
+    while (x) {
+        ++b;
+        x >>= 1;
+    }
+    return b;
+}
+
+inline u64 gcd64(u64 a, u64 b)
+{
+    while (b) {
+        u64 t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+
+struct Plan {
+    u32 n_vars = 0;
+    CodecParams cpA{}, cpB{}, cpR{}; // operand decoders and result encoder
+    i64 base_code = 0;               // piranha code of the exponent vector (emin_a + emin_b)
+    u64 range = 1;                   // number of tight codes
+    u32 code_bits = 1;
+    u32 LA = 1, LB = 1;
+    u32 prod_bits = 0, cnt_bits = 0;
+    u32 cbits = 0, nl = 0, out_limbs = 1;
+};
+
+
+inline void free_dpoly_arrays(pk_ctx *ctx, pk_dpoly *p)
+{
+    if (p->key) cudaFreeAsync(p->key, ctx->stream);
+    if (p->planes) cudaFreeAsync(p->planes, ctx->stream);
+    if (p->sign) cudaFreeAsync(p->sign, ctx->stream);
+    p->key = nullptr;
+    p->planes = nullptr;
+    p->sign = nullptr;
+}
+
+struct DPolyGuard {
+    pk_ctx *ctx;
+    pk_dpoly *p;
+    ~DPolyGuard()
+    {
+        if (p) {
+            free_dpoly_arrays(ctx, p);
+            delete p;
+        }
+    }
+    pk_dpoly *release()
+    {
+        pk_dpoly *r = p;
+        p = nullptr;
+        return r;
+    }
+};
+
+inline pk_dpoly *new_dpoly(pk_ctx *ctx, u64 n, u32 n_vars, u32 limbs)
+{
+    std::unique_ptr<pk_dpoly> p(new pk_dpoly);
+    p->n = n;
+    p->n_vars = n_vars;
+    p->limbs = limbs;
+    p->stride = ((n + 1) & ~1ull) + 2; // even, with slack for the 16-byte TMA granularity
+    DPolyGuard g{ctx, p.release()};
+    CUDA_CHECK(cudaMallocAsync((void **)&g.p->key, (n + 2) * sizeof(int64_t), ctx->stream));
+    CUDA_CHECK(cudaMallocAsync((void **)&g.p->planes, g.p->stride * limbs * sizeof(uint64_t), ctx->stream));
+    CUDA_CHECK(cudaMallocAsync((void **)&g.p->sign, n + 2, ctx->stream));
+    return g.release();
+}
+
+} // namespace pk

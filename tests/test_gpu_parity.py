@@ -1,0 +1,342 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracles, bit-exact.
+
+The cases follow the reference's own tests for this path:
+  tests/polynomial_multiplier_01.cpp:120-174 (bounds), :187-238 (empty, reduced Fateman 10626 / 5786)
+  tests/base_series_multiplier.cpp:517-605     (reduced Fateman and Pearce: 591235 / 591184)
+  tests/polynomial_truncation.cpp:69-177       (total / partial degree truncation)
+  tests/kronecker_monomial_01.cpp:404-461      (term multiply: 2*3 = 6, 2*(-4) = -8 with exponent sums)
+  benchmarks/*.cpp                             (result sizes of fateman1/2, pearce1, monagan1-5, truncated fateman1)
+"""
+import numpy as np
+import pytest
+
+import piranha_b200 as pb
+from oracle import pyoracle as po
+from polyhelper import (P31, assert_sorted_unique, assert_terms_equal, cpu_ref, eval_mod_p, oracle_terms, terms)
+
+pytestmark = pytest.mark.gpu
+
+ALGOS = [pb.PK_ALGO_AUTO, pb.PK_ALGO_DENSE, pb.PK_ALGO_HASH]
+
+
+def gpu_mul(ctx, f, g, nv, **opt):
+    a, b = terms(f, nv, 1), terms(g, nv, 2)
+    out = ctx.mul(a, b, nv, **opt)
+    assert_sorted_unique(out[0])
+    return a, b, out
+
+
+# ---------------------------------------------------------------------------------------------- tiny exact cases
+
+
+def test_term_multiply_fixtures(ctx):
+    # kronecker_monomial_01.cpp:404-461: 2*x * 3*x^2 = 6*x^3 ; 2*x*y^-1 * -4*x^2 = -8*x^3*y^-1
+    r = ctx.mul(terms({(1,): 2}, 1), terms({(2,): 3}, 1), 1)
+    assert_terms_equal(r, oracle_terms({(3,): 6}, 1))
+    r = ctx.mul(terms({(1, -1): 2}, 2), terms({(2, 0): -4}, 2), 2)
+    assert_terms_equal(r, oracle_terms({(3, -1): -8}, 2))
+
+
+def test_empty_and_constants(ctx):
+    # polynomial_multiplier_01.cpp:193-202: empty * x = 0 with the symbol set preserved; pt{2} * pt{3} = 6
+    empty = (np.zeros(0, np.int64), np.zeros((0, 1), np.uint64), np.zeros(0, np.int8))
+    x = terms({(1,): 1}, 1)
+    for a, b in ((empty, x), (x, empty), (empty, empty)):
+        k, m, s = ctx.mul(a, b, 1)
+        assert len(k) == 0
+    r = ctx.mul(terms({(): 2}, 0), terms({(): 3}, 0), 0)
+    assert_terms_equal(r, oracle_terms({(): 6}, 0))
+    r = ctx.mul(terms({(0, 0, 0): 2}, 3), terms({(0, 0, 0): 3}, 3), 3)
+    assert_terms_equal(r, oracle_terms({(0, 0, 0): 6}, 3))
+
+
+def test_square_of_linear(ctx):
+    # polynomial_truncation.cpp:75-77
+    f = {(1, 0, 0, 0): 1, (0, 1, 0, 0): 1, (0, 0, 1, 0): 1, (0, 0, 0, 1): 1}
+    for algo in ALGOS:
+        _, _, r = gpu_mul(ctx, f, f, 4, algo=algo)
+        assert_terms_equal(r, oracle_terms(po.p_mul(f, f), 4))
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_truncation_exact_cases(ctx, algo):
+    # polynomial_truncation.cpp:79-107 (total degree), :141-170 (partial degree); variables t,x,y,z -> indices 0..3
+    nv = 4
+    one = (0, 0, 0, 0)
+    X, Y = (0, 1, 0, 0), (0, 0, 1, 0)
+    f = {one: 1, X: 1, Y: 1}
+    for D in (1, 2, 3, 0, -1):
+        _, _, r = gpu_mul(ctx, f, f, nv, trunc_mode=1, max_degree=D, algo=algo)
+        assert_terms_equal(r, oracle_terms(po.p_mul(f, f, max_degree=D), nv), f"total D={D}")
+    lin = {(1, 0, 0, 0): 1, X: 1, Y: 1, (0, 0, 0, 1): 1}
+    _, _, r = gpu_mul(ctx, lin, lin, nv, trunc_mode=1, max_degree=1, algo=algo)
+    assert len(r[0]) == 0
+    for mask in ([0, 1, 0, 0], [0, 0, 0, 1], [0, 1, 1, 0]):
+        _, _, r = gpu_mul(ctx, f, f, nv, trunc_mode=2, max_degree=1, degree_mask=mask, algo=algo)
+        assert_terms_equal(r, oracle_terms(po.p_mul(f, f, max_degree=1, mask=mask), nv), f"partial {mask}")
+    _, _, r = gpu_mul(ctx, lin, lin, nv, trunc_mode=2, max_degree=1, degree_mask=[0, 1, 0, 0], algo=algo)
+    assert_terms_equal(r, oracle_terms(po.p_mul(lin, lin, max_degree=1, mask=[0, 1, 0, 0]), nv))
+
+
+def test_truncation_degree_overflow(ctx):
+    # degree_sub -> safe_int_sub overflow -> std::overflow_error (polynomial.hpp:1243-1252)
+    f = {(-1,): 1, (0,): 1}
+    with pytest.raises(OverflowError):
+        ctx.mul(terms(f, 1), terms({(1,): 1}, 1), 1, trunc_mode=1, max_degree=(1 << 63) - 1)
+
+
+def test_bounds_fixtures(ctx):
+    # polynomial_multiplier_01.cpp:120-174, 3 variables
+    M = po.kron_limits(3)[0]
+    lim, _, _ = ctx.limits(3)
+    assert tuple(int(x) for x in lim) == M
+    top = {(M[0], M[1], M[2]): 1}
+    for v in range(3):
+        e = [0, 0, 0]
+        e[v] = 1
+        with pytest.raises(OverflowError):
+            ctx.mul(terms(top, 3), terms({tuple(e): 1}, 3), 3)
+        with pytest.raises(OverflowError):  # (x^M0 + 1)(y^M1 + 1)(z^M2 + 1) * (v + 1)
+            big = po.p_mul(po.p_mul({(M[0], 0, 0): 1, (0, 0, 0): 1}, {(0, M[1], 0): 1, (0, 0, 0): 1}),
+                           {(0, 0, M[2]): 1, (0, 0, 0): 1})
+            ctx.mul(terms(big, 3), terms({tuple(e): 1, (0, 0, 0): 1}, 3), 3)
+        neg = [M[0], M[1], M[2]]
+        neg[v] = -neg[v]
+        e[v] = -1
+        with pytest.raises(OverflowError):
+            ctx.mul(terms({tuple(neg): 1}, 3), terms({tuple(e): 1}, 3), 3)
+        # one below the limit succeeds and lands exactly on the limit
+        below = [M[0], M[1], M[2]]
+        below[v] -= 1
+        e[v] = 1
+        r = ctx.mul(terms({tuple(below): 1}, 3), terms({tuple(e): 1}, 3), 3)
+        assert_terms_equal(r, oracle_terms(top, 3))
+    allneg = {(-M[0] + 1, -M[1], -M[2]): 1}
+    r = ctx.mul(terms(allneg, 3), terms({(-1, 0, 0): 1}, 3), 3)
+    assert_terms_equal(r, oracle_terms({(-M[0], -M[1], -M[2]): 1}, 3))
+
+
+def test_argument_errors(ctx):
+    a = terms({(1,): 1}, 1)
+    da, db = ctx.upload(a, 1), ctx.upload(terms({(1, 0): 1}, 2), 2)
+    with pytest.raises(ValueError):  # "incompatible arguments sets", base_series_multiplier.hpp:365-367
+        ctx.mul_dev(da, db)
+    with pytest.raises(ValueError):
+        ctx.mul(a, a, 1, trunc_mode=7)
+    with pytest.raises(ValueError):
+        ctx.mul(a, a, 1, part_index=3, part_count=2)
+
+
+# ---------------------------------------------------------------------------------------------- known answers
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_reduced_fateman(ctx, algo):
+    f, g = po.fateman_operands(10)
+    a, b, r = gpu_mul(ctx, f, g, 4, algo=algo)
+    assert len(r[0]) == 10626  # polynomial_multiplier_01.cpp:214
+    assert_terms_equal(r, cpu_ref(a, b, 4))
+    assert_terms_equal(r, oracle_terms(po.fateman_product_closed_form(10), 4), "closed form")
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_reduced_fateman_cancellations(ctx, algo):
+    f, h = po.fateman_cancel_operands(10)
+    a, b, r = gpu_mul(ctx, f, h, 4, algo=algo)
+    assert len(r[0]) == 5786  # polynomial_multiplier_01.cpp:230
+    assert_terms_equal(r, cpu_ref(a, b, 4))
+
+
+@pytest.mark.parametrize("minus_u,size", [(False, 591235), (True, 591184)])
+@pytest.mark.parametrize("algo", ALGOS)
+def test_reduced_pearce(ctx, algo, minus_u, size):
+    f, g = po.pearce_operands(8, minus_u)
+    a, b, r = gpu_mul(ctx, f, g, 5, algo=algo)
+    assert len(r[0]) == size  # base_series_multiplier.cpp:586, :604
+    assert_terms_equal(r, cpu_ref(a, b, 5, n_threads=4))
+
+
+def test_fateman1_full(ctx):
+    f, g = po.fateman_operands(20)
+    a, b, r = gpu_mul(ctx, f, g, 4)
+    assert len(r[0]) == 135751  # benchmarks/fateman1.cpp:55
+    assert_terms_equal(r, oracle_terms(po.fateman_product_closed_form(20), 4), "closed form")
+    st = ctx.stats()
+    assert st["term_products"] == 10626 * 10626 and st["kernel_launches"] > 0
+
+
+def test_pearce1_full(ctx):
+    f, g = po.pearce_operands(12)
+    a, b, r = gpu_mul(ctx, f, g, 5)
+    assert len(r[0]) == 5821335  # benchmarks/pearce1.cpp:56
+    assert_terms_equal(r, cpu_ref(a, b, 5, n_threads=8))
+    # size-independent property: evaluation homomorphism at a random point mod a prime
+    pt = [3, 5, 7, 11, 13]
+    ea, eb = eval_mod_p(*a, 5, pt), eval_mod_p(*b, 5, pt)
+    assert eval_mod_p(*r, 5, pt) == ea * eb % P31
+
+
+@pytest.mark.parametrize("which,size", [(1, 12341), (2, 12341), (3, 39711), (4, 135751), (5, 417311)])
+def test_monagan(ctx, which, size):
+    f, g = po.monagan_operands(which)
+    nv = len(next(iter(f)))
+    a, b, r = gpu_mul(ctx, f, g, nv)
+    assert len(r[0]) == size  # benchmarks/monagan1-5.cpp
+    assert_terms_equal(r, cpu_ref(a, b, nv, n_threads=8))
+
+
+def test_monagan5_hash_and_dense(ctx):
+    f, g = po.monagan_operands(5)
+    a, b = terms(f, 5, 1), terms(g, 5, 2)
+    ref = cpu_ref(a, b, 5, n_threads=8)
+    for algo in (pb.PK_ALGO_DENSE, pb.PK_ALGO_HASH):
+        assert_terms_equal(ctx.mul(a, b, 5, algo=algo), ref)
+
+
+def test_fateman2_full(ctx):
+    # stresses coefficient width: largest result coefficient is 2^127.96
+    f, g = po.fateman_operands(30)
+    a, b, r = gpu_mul(ctx, f, g, 4)
+    assert len(r[0]) == 635376  # benchmarks/fateman2.cpp:55
+    assert_terms_equal(r, oracle_terms(po.fateman_product_closed_form(30), 4), "closed form")
+    mx = max(abs(c) for c in po.soa_coefficients(r[1], r[2]))
+    assert 127 < mx.bit_length() <= 128
+
+
+@pytest.mark.parametrize("D,size", [(20, 10626), (30, 46376)])
+def test_fateman1_truncated(ctx, D, size):
+    f, g = po.fateman_operands(20)
+    a, b, r = gpu_mul(ctx, f, g, 4, trunc_mode=1, max_degree=D)
+    assert len(r[0]) == size  # benchmarks/fateman1_unpacked_truncation.cpp:57, :59
+    assert_terms_equal(r, cpu_ref(a, b, 4, n_threads=8, trunc_mode=1, max_degree=D))
+    assert ctx.stats()["term_products"] == {20: 3108105, 30: 38970998}[D]  # SURVEY.md section 8 size table
+
+
+# ---------------------------------------------------------------------------------------------- wider coverage
+
+
+def _random_poly(rs, nv, nterms, emin, emax, bits):
+    p = {}
+    while len(p) < nterms:
+        e = tuple(int(x) for x in rs.randint(emin, emax + 1, size=nv))
+        c = int.from_bytes(rs.bytes((bits + 7) // 8), "little") >> ((8 - bits % 8) % 8)
+        c = c or 1
+        p[e] = -c if rs.randint(2) else c
+    return p
+
+
+@pytest.mark.parametrize("bits_a,bits_b", [(64, 64), (100, 40), (40, 128), (128, 128)])
+@pytest.mark.parametrize("algo", ALGOS)
+def test_multi_limb_random(ctx, algo, bits_a, bits_b):
+    rs = np.random.RandomState(bits_a * 1000 + bits_b)
+    f = _random_poly(rs, 3, 300, -4, 9, bits_a)
+    g = _random_poly(rs, 3, 200, -7, 5, bits_b)
+    _, _, r = gpu_mul(ctx, f, g, 3, algo=algo)
+    assert_terms_equal(r, oracle_terms(po.p_mul(f, g), 3))
+
+
+def test_laurent_and_gcd_compaction(ctx):
+    # exponents on a coarse lattice (steps 3 and 5) with negative powers: exercises the re-encoding with gcd steps
+    rs = np.random.RandomState(7)
+    f = {(3 * int(a), -5 * int(b)): int(c) + 1 for a, b, c in rs.randint(0, 30, size=(400, 3))}
+    g = {(-3 * int(a), 5 * int(b) + 2): -(int(c) + 1) for a, b, c in rs.randint(0, 30, size=(400, 3))}
+    for algo in ALGOS:
+        _, _, r = gpu_mul(ctx, f, g, 2, algo=algo)
+        assert_terms_equal(r, oracle_terms(po.p_mul(f, g), 2))
+
+
+def test_many_variables(ctx):
+    rs = np.random.RandomState(11)
+    nv = 12
+    f = _random_poly(rs, nv, 150, 0, 3, 30)
+    g = _random_poly(rs, nv, 150, 0, 3, 30)
+    _, _, r = gpu_mul(ctx, f, g, nv)
+    assert_terms_equal(r, oracle_terms(po.p_mul(f, g), nv))
+
+
+def test_commutative_and_operand_order(ctx):
+    f, g = po.pearce_operands(5)
+    a, b = terms(f, 5, 1), terms(g, 5, 2)
+    assert_terms_equal(ctx.mul(a, b, 5), ctx.mul(b, a, 5))
+    small = terms({(0, 0, 0, 0, 0): 7, (1, 0, 0, 0, 0): -7}, 5)
+    assert_terms_equal(ctx.mul(a, small, 5), ctx.mul(small, a, 5))
+
+
+@pytest.mark.parametrize("parts", [2, 3, 8])
+@pytest.mark.parametrize("case", ["fateman", "pearce", "trunc"])
+def test_output_partitions(ctx, parts, case):
+    """Disjoint output ranges: the concatenation of the parts (in order) is the whole product."""
+    opt = {}
+    if case == "fateman":
+        (f, g), nv = po.fateman_operands(8), 4
+    elif case == "pearce":
+        (f, g), nv = po.pearce_operands(6), 5
+    else:
+        (f, g), nv = po.fateman_operands(8), 4
+        opt = dict(trunc_mode=1, max_degree=9)
+    a, b = terms(f, nv, 1), terms(g, nv, 2)
+    da, db = ctx.upload(a, nv), ctx.upload(b, nv)
+    whole = ctx.mul_dev(da, db, **opt)
+    wk, wm, ws = whole.download()
+    keys, mags, signs, digest, pairs = [], [], [], 0, 0
+    for p in range(parts):
+        part = ctx.mul_dev(da, db, part_index=p, part_count=parts, **opt)
+        pairs += ctx.stats()["term_products"]
+        k, m, s = part.download()
+        digest = (digest + part.digest()) & ((1 << 64) - 1)
+        keys.append(k)
+        mags.append(np.pad(m, ((0, 0), (0, wm.shape[1] - m.shape[1]))) if len(k) else np.zeros((0, wm.shape[1]), np.uint64))
+        signs.append(s)
+    allk = np.concatenate(keys)
+    assert_sorted_unique(allk)  # ordered, disjoint ranges
+    assert_terms_equal((allk, np.concatenate(mags), np.concatenate(signs)), (wk, wm, ws))
+    assert digest == whole.digest() == pb.digest_terms(wk, wm, ws)
+    ctx.mul_dev(da, db, **opt)
+    assert pairs == ctx.stats()["term_products"]  # every term product is done by exactly one partition
+    if case != "trunc":
+        sizes = [len(k) for k in keys]
+        assert min(sizes) > 0
+
+
+def test_device_resident_chain(ctx):
+    # benchmarks/fateman1.hpp:46-48: f *= tmp, nine times, operands never leave HBM
+    nv = 4
+    base = {(0, 0, 0, 0): 1, (1, 0, 0, 0): 1, (0, 1, 0, 0): 1, (0, 0, 1, 0): 1, (0, 0, 0, 1): 1}
+    tmp = ctx.upload(terms(base, nv), nv)
+    f = ctx.upload(terms(base, nv), nv)
+    for _ in range(9):
+        f = ctx.mul_dev(f, tmp)
+    ref, _ = po.fateman_operands(10)
+    assert_terms_equal(f.download(), oracle_terms(ref, nv))
+    sq = ctx.mul_dev(f, f)
+    assert_terms_equal(sq.download(), oracle_terms(po.p_pow_multinomial(po._linear(4, [1, 1, 1, 1]), 20), nv))
+
+
+def test_custom_limits_table(ctx):
+    """pk_ctx_set_limits: a caller whose standard library produced a different Kronecker table."""
+    c2 = pb.Context(0)
+    try:
+        M = [100, 200, 300]
+        c2.set_limits(3, M)
+        lim, hmin, hmax = c2.limits(3)
+        assert list(lim) == M
+
+        def enc(e):
+            code, c = 0, 1
+            for x, m in zip(e, M):
+                code += x * c
+                c *= 2 * m + 1
+            return code
+
+        f = {(1, 2, 3): 5, (0, -7, 4): -2}
+        g = {(10, 20, 30): 3, (-1, 1, 0): 11}
+        mk = lambda p: (np.array([enc(e) for e in p], np.int64), np.array([[abs(c)] for c in p.values()], np.uint64),
+                        np.array([1 if c > 0 else -1 for c in p.values()], np.int8))
+        k, m, s = c2.mul(mk(f), mk(g), 3)
+        ref = po.p_mul(f, g)
+        got = {int(kk): (int(mm[0]) if ss > 0 else -int(mm[0])) for kk, mm, ss in zip(k, m, s)}
+        assert got == {enc(e): c for e, c in ref.items()}
+        with pytest.raises(OverflowError):
+            c2.mul(mk({(100, 0, 0): 1}), mk({(1, 0, 0): 1}), 3)
+    finally:
+        c2.close()
