@@ -22,6 +22,8 @@ def assert_terms_equal(got, ref, what=""):
     assert len(gk) == len(rk), f"{what}: {len(gk)} terms, expected {len(rk)}"
     go, ro = np.argsort(gk, kind="stable"), np.argsort(rk, kind="stable")
     assert np.array_equal(np.asarray(gk)[go], np.asarray(rk)[ro]), f"{what}: key sets differ"
+    if len(gk) == 0:
+        return
     gm = np.asarray(gm).reshape(len(gk), -1)[go]
     rm = np.asarray(rm).reshape(len(rk), -1)[ro]
     L = max(gm.shape[1], rm.shape[1])
