@@ -20,7 +20,7 @@ PK_ALGO_AUTO, PK_ALGO_DENSE, PK_ALGO_HASH, PK_ALGO_ZONE = range(4)
 ALGO_NAMES = {0: "auto", 1: "dense", 2: "hash", 3: "zone"}
 
 EXPORTED_SYMBOLS = [
-    "pk_ctx_create", "pk_ctx_destroy", "pk_last_error", "pk_ctx_set_limits", "pk_ctx_get_limits", "pk_get_stats",
+    "pk_ctx_create", "pk_ctx_destroy", "pk_last_error", "pk_ctx_set_limits", "pk_ctx_get_limits", "pk_get_stats", "pk_ctx_set_tuning",
     "pk_mul", "pk_result_free", "pk_upload", "pk_mul_dev", "pk_download", "pk_dpoly_free", "pk_dpoly_size",
     "pk_dpoly_limbs", "pk_dpoly_nvars", "pk_dpoly_export", "pk_dpoly_digest",
 ]
@@ -91,6 +91,7 @@ def load_library():
     lib.pk_ctx_set_limits.argtypes = [vp, u32, vp]
     lib.pk_ctx_get_limits.argtypes = [vp, u32, vp, C.POINTER(i64), C.POINTER(i64)]
     lib.pk_get_stats.argtypes = [vp, C.POINTER(PkStats)]
+    lib.pk_ctx_set_tuning.argtypes = [vp, C.c_char_p, u64]
     lib.pk_mul.argtypes = [vp, C.POINTER(PkPoly), C.POINTER(PkPoly), C.POINTER(PkOpts), C.POINTER(PkResult)]
     lib.pk_result_free.argtypes = [vp, C.POINTER(PkResult)]
     lib.pk_result_free.restype = None
@@ -215,6 +216,10 @@ class Context:
     def set_limits(self, n_vars: int, limits: Sequence[int]):
         lim = np.ascontiguousarray(limits, dtype=np.int64)
         self._check(self.lib.pk_ctx_set_limits(self.handle, n_vars, lim.ctypes.data))
+
+    def set_tuning(self, **kv):
+        for k, v in kv.items():
+            self._check(self.lib.pk_ctx_set_tuning(self.handle, k.encode(), int(v)))
 
     def stats(self) -> dict:
         s = PkStats()

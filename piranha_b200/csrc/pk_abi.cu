@@ -622,6 +622,22 @@ int pk_ctx_get_limits(const pk_ctx *ctx, uint32_t n_vars, int64_t *limits_out, i
     return PK_OK;
 }
 
+int pk_ctx_set_tuning(pk_ctx *ctx, const char *key, uint64_t value)
+{
+    if (!ctx || !key) return PK_E_ARGS;
+    ZoneTuning &t = ctx->zone_tuning;
+    const std::string k(key);
+    if (k == "zone_target") t.target_zones = (u32)value;
+    else if (k == "zone_chunk") t.zones_per_chunk = std::max<u32>(1, (u32)value);
+    else if (k == "zone_span_log2") t.span_log2_max = std::min<u32>(20, std::max<u32>(10, (u32)value));
+    else if (k == "zone_cap") t.force_cap = (u32)value;
+    else if (k == "zone_mode") t.force_mode = (u32)value;
+    else if (k == "zone_disable") t.disable = (u32)value;
+    else if (k == "zone_cursor_bytes") t.cursor_bytes_max = (u32)value;
+    else return PK_E_ARGS;
+    return PK_OK;
+}
+
 int pk_get_stats(pk_ctx *ctx, pk_stats *out)
 {
     if (!ctx || !out) return PK_E_ARGS;

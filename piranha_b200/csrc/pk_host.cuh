@@ -13,6 +13,21 @@
 
 // ------------------------------------------------------------------------------------------------ objects
 
+namespace pk
+{
+struct ZoneTuning {
+    uint32_t target_zones = 0;    // 0 = 16 per SM
+    uint32_t zones_per_chunk = 4;
+    uint32_t span_log2_max = 18;  // bitmap zones: at most 2^18 codes (32 KB bitmap + 32 KB prefix)
+    uint32_t force_cap = 0;       // tests: force a small accumulator capacity to exercise multi-pass zones
+    uint32_t force_mode = 0;      // 0 auto, 1 dense, 2 bitmap
+    uint32_t max_zones = 1u << 20;
+    uint32_t cursor_bytes_max = 64u << 10;
+    uint32_t disable = 0;
+};
+
+} // namespace pk
+
 struct PinnedBuf {
     void *ptr = nullptr;
     size_t bytes = 0;
@@ -37,6 +52,7 @@ struct pk_ctx {
     pk::u64 *d_digest = nullptr;
     std::vector<PinnedBuf> pinned;
     int sm_count = 148;
+    pk::ZoneTuning zone_tuning;
     size_t smem_optin = 0;
 };
 

@@ -163,12 +163,10 @@ __global__ void k_flip_deg(const i64 *__restrict__ in, u64 *__restrict__ out, u6
 
 // Skip limits: sl[i] = number of terms of the (degree-sorted) second operand with deg2 <= max_degree - deg1[i].
 // The subtraction is checked like safe_int_sub (polynomial.hpp:1248-1252): overflow raises the degree flag.
-// Also accumulates W = sum_i sl[i] for the statistics.
 __global__ void k_skip_limits(const i64 *__restrict__ deg1, u64 n1, const u64 *__restrict__ deg2_sorted_flipped, u64 n2,
                               i64 max_degree, u32 *__restrict__ sl, MulCounters *ctr)
 {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    u64 mine = 0;
     if (i < n1) {
         const i64 d1 = deg1[i];
         const i64 c = (i64)((u64)max_degree - (u64)d1);
@@ -185,12 +183,8 @@ __global__ void k_skip_limits(const i64 *__restrict__ deg1, u64 n1, const u64 *_
                 else lo = mid + 1;
             }
             sl[i] = (u32)lo;
-            mine = lo;
         }
     }
-    // block reduce of W
-    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-    if (lane_id() == 0 && mine) atomicAdd(&ctr->pairs, mine);
 }
 
 // ------------------------------------------------------------------------------------------------ multiply

@@ -16,7 +16,7 @@ from polyhelper import (P31, assert_sorted_unique, assert_terms_equal, cpu_ref, 
 
 pytestmark = pytest.mark.gpu
 
-ALGOS = [pb.PK_ALGO_AUTO, pb.PK_ALGO_DENSE, pb.PK_ALGO_HASH]
+ALGOS = [pb.PK_ALGO_AUTO, pb.PK_ALGO_DENSE, pb.PK_ALGO_HASH, pb.PK_ALGO_ZONE]
 
 
 def gpu_mul(ctx, f, g, nv, **opt):
@@ -185,12 +185,54 @@ def test_monagan(ctx, which, size):
     assert_terms_equal(r, cpu_ref(a, b, nv, n_threads=8))
 
 
-def test_monagan5_hash_and_dense(ctx):
+def test_monagan5_all_strategies(ctx):
     f, g = po.monagan_operands(5)
     a, b = terms(f, 5, 1), terms(g, 5, 2)
     ref = cpu_ref(a, b, 5, n_threads=8)
-    for algo in (pb.PK_ALGO_DENSE, pb.PK_ALGO_HASH):
+    for algo in (pb.PK_ALGO_DENSE, pb.PK_ALGO_HASH, pb.PK_ALGO_ZONE):
         assert_terms_equal(ctx.mul(a, b, 5, algo=algo), ref)
+
+
+@pytest.mark.parametrize("tuning", [
+    dict(zone_mode=1),                               # dense zones
+    dict(zone_mode=2),                               # bitmap zones (perfect hash by rank)
+    dict(zone_mode=2, zone_cap=37),                  # bitmap zones far over capacity: many passes per zone
+    dict(zone_mode=2, zone_span_log2=10, zone_cap=5),
+    dict(zone_mode=1, zone_cap=64),                  # tiny dense zones: long look-back chains
+    dict(zone_mode=2, zone_cursor_bytes=0),          # no row cursors: one binary search per row per zone
+    dict(zone_mode=1, zone_cursor_bytes=0, zone_target=7),
+    dict(zone_mode=2, zone_chunk=1, zone_target=100000),
+    dict(zone_mode=1, zone_chunk=64),
+])
+@pytest.mark.parametrize("case", ["pearce", "cancel", "signed"])
+def test_zone_variants(tuning, case):
+    """Every way the zone kernel can be configured gives the same bits (tuning never changes results)."""
+    if case == "pearce":
+        (f, g), nv = po.pearce_operands(5), 5
+    elif case == "cancel":
+        (f, g), nv = po.fateman_cancel_operands(7), 4
+    else:
+        (f, g), nv = po.monagan_operands(5), 5
+        f = {k: v for i, (k, v) in enumerate(f.items()) if i % 3 == 0}
+        g = {k: -v if i % 2 else v for i, (k, v) in enumerate(g.items()) if i % 5 == 0}
+    c2 = pb.Context(0)
+    try:
+        c2.set_tuning(**tuning)
+        a, b = terms(f, nv, 1), terms(g, nv, 2)
+        r = c2.mul(a, b, nv, algo=pb.PK_ALGO_ZONE)
+        st = c2.stats()
+        assert st["algo"] == pb.PK_ALGO_ZONE
+        assert_sorted_unique(r[0])
+        assert_terms_equal(r, cpu_ref(a, b, nv, n_threads=4))
+        assert st["term_products"] == len(a[0]) * len(b[0])
+    finally:
+        c2.close()
+
+
+def test_zone_is_default_for_benchmark_configs(ctx):
+    for (f, g), nv in ((po.fateman_operands(12), 4), (po.pearce_operands(7), 5)):
+        ctx.mul(terms(f, nv), terms(g, nv, 1), nv)
+        assert ctx.stats()["algo"] == pb.PK_ALGO_ZONE
 
 
 def test_fateman2_full(ctx):
