@@ -17,9 +17,10 @@
 //     runs).  A product is added word by word with ATOMS.ADD; the returned old value gives the carry (borrow) into
 //     the next word.  Each atomic is exact modulo 2^32 and reports its own carry, so the value is exact under any
 //     interleaving.  NW is chosen on the host from a proven bound, so the top word never wraps.
-//   * Zones publish their result counts through a decoupled look-back chain (zone ids are handed out in increasing
-//     order by an atomic counter, so a predecessor is always finished or running), and write their terms straight
-//     into the final, globally sorted arrays: sanitise_series (base_series_multiplier.hpp:855-949) fused in.
+//   * A finished zone claims space in a staging area with one atomicAdd (no inter-block waiting of any kind) and
+//     records (offset, count); an exclusive scan over the zone counts and one gather pass then lay the zones out in
+//     zone order = ascending code order.  Zero coefficients are dropped while emitting: sanitise_series
+//     (base_series_multiplier.hpp:855-949) fused in.
 #pragma once
 
 #include <cstdlib>
@@ -30,7 +31,6 @@ namespace pk
 {
 
 constexpr int kZoneThreads = 1024;
-constexpr u64 kStAgg = 1ull << 62, kStIncl = 2ull << 62, kStMask = (1ull << 62) - 1;
 
 struct ZoneArgs {
     const ulonglong2 *A; // {tight code | sign bit, magnitude limb 0}, ascending code
@@ -55,7 +55,9 @@ struct ZoneArgs {
     CodecParams cp;
     i64 base_code;
     u32 *chunk_counter;
-    u64 *zone_status;
+    u32 *zone_count; // result terms of zone z
+    u64 *zone_off;   // where zone z starts in the staging arrays
+    u64 *bump;       // staging allocation cursor
     MulCounters *ctr;
 };
 
@@ -154,27 +156,6 @@ __device__ __forceinline__ void zone_emit(const ZoneArgs &a, u64 pos, u64 code, 
     a.okey[pos] = zone_code_to_piranha(code, a.cp, a.base_code);
     a.osign[pos] = neg ? (signed char)-1 : (signed char)1;
     maxbits = max(maxbits, bits);
-}
-
-__device__ __forceinline__ void zone_publish(u64 *status, u32 z, u64 flag, u64 value)
-{
-    __threadfence();
-    atomicExch(&status[z], flag | value);
-}
-
-// sum of the result counts of all zones before z (decoupled look-back)
-__device__ __forceinline__ u64 zone_lookback(u64 *status, u32 z)
-{
-    u64 sum = 0;
-    for (u32 p = z; p-- > 0;) {
-        u64 v;
-        do {
-            v = *((volatile u64 *)&status[p]);
-        } while ((v >> 62) == 0);
-        sum += v & kStMask;
-        if ((v >> 62) == 2) break;
-    }
-    return sum;
 }
 
 template <int NW>
@@ -334,13 +315,8 @@ __global__ void __launch_bounds__(kZoneThreads, 1) k_zone(const ZoneArgs a)
                 }
                 u32 total;
                 const u32 excl = block_excl_scan(cnt, s_ws, total);
-                if (!have_base) {
-                    if (tid == 0) {
-                        if (single) zone_publish(a.zone_status, z, z == 0 ? kStIncl : kStAgg, total);
-                        const u64 base = zone_lookback(a.zone_status, z);
-                        if (single && z != 0) zone_publish(a.zone_status, z, kStIncl, base + total);
-                        s_b64[1] = base;
-                    }
+                if (!have_base) { // claim staging space: exact for a single pass, the distinct count otherwise
+                    if (tid == 0) s_b64[1] = atomicAdd(a.bump, single ? (u64)total : (u64)n_entries);
                     __syncthreads();
                     zone_base = s_b64[1];
                     have_base = true;
@@ -389,15 +365,12 @@ __global__ void __launch_bounds__(kZoneThreads, 1) k_zone(const ZoneArgs a)
                 c0 = c1;
                 __syncthreads();
             } while (r0 < n_entries);
-            if (!single) {
-                if (tid == 0) zone_publish(a.zone_status, z, kStIncl, zone_base + zone_written);
+            if (tid == 0) {
+                a.zone_count[z] = (u32)zone_written;
+                a.zone_off[z] = zone_base;
             }
             if (a.mode == 1) { // clear the bitmap for the next zone
                 for (u32 i = tid; i < a.bm_words; i += kZoneThreads) bm[i] = 0;
-            }
-            if (z + 1 == a.n_zones && tid == 0) { // last zone: total number of result terms
-                const u64 base = have_base ? zone_base : zone_lookback(a.zone_status, z);
-                a.ctr->n_out = base + zone_written;
             }
             __syncthreads();
         }
@@ -413,6 +386,47 @@ __global__ void __launch_bounds__(kZoneThreads, 1) k_zone(const ZoneArgs a)
         if (my_maxbits) atomicMax(&a.ctr->max_bits, my_maxbits);
         if (my_flags) atomicOr(&a.ctr->flags, my_flags);
     }
+}
+
+// Lay the zones out in zone order (= ascending code order): one block per zone copies its staged terms to
+// prefix[z] in the final arrays.
+__global__ void __launch_bounds__(256) k_zone_gather(const u32 *__restrict__ zone_count, const u64 *__restrict__ zone_off,
+                                                     const u64 *__restrict__ zone_prefix, u32 n_zones,
+                                                     const i64 *__restrict__ skey, const u64 *__restrict__ splanes,
+                                                     u64 sstride, const signed char *__restrict__ ssign,
+                                                     i64 *__restrict__ okey, u64 *__restrict__ oplanes, u64 ostride,
+                                                     signed char *__restrict__ osign, u32 limbs)
+{
+    for (u32 z = blockIdx.x; z < n_zones; z += gridDim.x) {
+        const u32 n = zone_count[z];
+        const u64 src = zone_off[z], dst = zone_prefix[z];
+        for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
+            okey[dst + i] = skey[src + i];
+            osign[dst + i] = ssign[src + i];
+            for (u32 l = 0; l < limbs; ++l) oplanes[(u64)l * ostride + dst + i] = splanes[(u64)l * sstride + src + i];
+        }
+    }
+}
+
+// exclusive scan of 32-bit counts into 64-bit offsets (single block); total -> *total_out
+__global__ void __launch_bounds__(1024) k_zone_scan(const u32 *__restrict__ counts, u64 *__restrict__ offsets, u32 n,
+                                                    u64 *total_out)
+{
+    __shared__ u32 s_ws[40];
+    __shared__ u64 s_run;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (u32 base = 0; base < n; base += 1024) {
+        const u32 i = base + threadIdx.x;
+        const u32 v = i < n ? counts[i] : 0;
+        u32 total;
+        const u32 ex = block_excl_scan(v, s_ws, total);
+        if (i < n) offsets[i] = s_run + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) s_run += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = s_run;
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -562,9 +576,15 @@ inline pk_dpoly *zone_multiply(pk_ctx *ctx, const Plan &pl, const pk_dpoly *A, c
     DevBuf pa(ctx, (nA + 1) * 16), pb(ctx, (nB + 1) * 16);
     PK_LAUNCH(ctx, k_pack_operand, grid_for(nA, 256), 256, 0, keyA, A->planes, pa.as<ulonglong2>(), nA);
     PK_LAUNCH(ctx, k_pack_operand, grid_for(nB, 256), 256, 0, keyB, magB, pb.as<ulonglong2>(), nB);
-    DevBuf status(ctx, (size_t)zp.n_zones * 8 + 16);
-    CUDA_CHECK(cudaMemsetAsync(status.p, 0, (size_t)zp.n_zones * 8 + 16, ctx->stream));
-    u32 *chunk_counter = reinterpret_cast<u32 *>(status.as<u64>() + zp.n_zones);
+    // per-zone bookkeeping: offsets (u64), prefix (u64), counts (u32), then the bump cursor and the chunk counter
+    const size_t nz = zp.n_zones;
+    DevBuf book(ctx, nz * 20 + 64);
+    u64 *zone_off = book.as<u64>();
+    u64 *zone_prefix = zone_off + nz;
+    u64 *bump = zone_prefix + nz;
+    u32 *chunk_counter = reinterpret_cast<u32 *>(bump + 1);
+    u32 *zone_count = chunk_counter + 2;
+    CUDA_CHECK(cudaMemsetAsync(bump, 0, 16, ctx->stream));
 
     DPolyGuard g{ctx, new_dpoly(ctx, out_cap, nv, pl.out_limbs)};
     ZoneArgs za{};
@@ -596,7 +616,9 @@ inline pk_dpoly *zone_multiply(pk_ctx *ctx, const Plan &pl, const pk_dpoly *A, c
     za.cp = pl.cpR;
     za.base_code = pl.base_code;
     za.chunk_counter = chunk_counter;
-    za.zone_status = status.as<u64>();
+    za.zone_count = zone_count;
+    za.zone_off = zone_off;
+    za.bump = bump;
     za.ctr = ctx->d_ctr;
     const u32 grid = std::min<u32>((u32)ctx->sm_count, zp.n_chunks);
     CUDA_CHECK(cudaEventRecord(ctx->ev_mul0, ctx->stream));
@@ -608,28 +630,23 @@ inline pk_dpoly *zone_multiply(pk_ctx *ctx, const Plan &pl, const pk_dpoly *A, c
     default: zone_launch<6>(ctx, za, grid, zp.smem); break;
     }
     CUDA_CHECK(cudaEventRecord(ctx->ev_mul1, ctx->stream));
+    PK_LAUNCH(ctx, k_zone_scan, 1, 1024, 0, zone_count, zone_prefix, zp.n_zones, &ctx->d_ctr->n_out);
     MulCounters *hc = static_cast<MulCounters *>(ctx->h_scratch);
     CUDA_CHECK(cudaMemcpyAsync(hc, ctx->d_ctr, sizeof(MulCounters), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     const u64 n_out = hc->n_out;
-    if (n_out > out_cap) fail(PK_E_CUDA, "zone path: result count exceeds its bound (internal error)");
+    if (n_out > out_cap || (hc->flags & kFlagTableFull)) fail(PK_E_CUDA, "zone path: result count exceeds its bound (internal error)");
     ctx->stats.table_slots = (u64)zp.cap;
     ctx->stats.acc_lanes = zp.NW;
     ctx->stats.chunk_bits = 0;
     ctx->stats.retries = zp.mode; // 0 dense zones, 1 bitmap zones (reported through the spare counter)
-    if (out_cap > n_out + n_out / 4 + 1024) { // give the slack back: exact-size arrays, device-to-device copy
-        DPolyGuard e{ctx, new_dpoly(ctx, n_out, nv, pl.out_limbs)};
-        if (n_out) {
-            CUDA_CHECK(cudaMemcpyAsync(e.p->key, g.p->key, n_out * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-            for (u32 l = 0; l < pl.out_limbs; ++l)
-                CUDA_CHECK(cudaMemcpyAsync(e.p->planes + l * e.p->stride, g.p->planes + l * g.p->stride, n_out * 8,
-                                           cudaMemcpyDeviceToDevice, ctx->stream));
-            CUDA_CHECK(cudaMemcpyAsync(e.p->sign, g.p->sign, n_out, cudaMemcpyDeviceToDevice, ctx->stream));
-        }
-        return e.release();
+    DPolyGuard e{ctx, new_dpoly(ctx, n_out, nv, pl.out_limbs)};
+    if (n_out) {
+        const u32 ggrid = std::min<u32>(zp.n_zones, (u32)ctx->sm_count * 16);
+        PK_LAUNCH(ctx, k_zone_gather, ggrid, 256, 0, zone_count, zone_off, zone_prefix, zp.n_zones, g.p->key, g.p->planes,
+                  g.p->stride, g.p->sign, e.p->key, e.p->planes, e.p->stride, e.p->sign, pl.out_limbs);
     }
-    g.p->n = n_out;
-    return g.release();
+    return e.release();
 }
 
 } // namespace pk
