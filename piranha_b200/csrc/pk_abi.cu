@@ -49,13 +49,13 @@ void ensure_meta(pk_ctx *ctx, pk_dpoly *p)
         init.egcd[v] = 0;
     }
     init.max_bits = 0;
-    init.pad = 0;
+    init.any_neg = 0;
     memcpy(ctx->h_scratch, &init, sizeof(init));
     CUDA_CHECK(cudaMemcpyAsync(ctx->d_meta, ctx->h_scratch, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
     CodecParams cp;
     fill_piranha_codec(ctx, nv, cp);
     const u32 grid = std::min<u32>(grid_for(p->n, 256), (u32)ctx->sm_count * 8);
-    PK_LAUNCH(ctx, k_meta, grid, 256, 0, p->key, p->planes, p->n, p->limbs, p->stride, cp, ctx->d_meta);
+    PK_LAUNCH(ctx, k_meta, grid, 256, 0, p->key, p->planes, p->sign, p->n, p->limbs, p->stride, cp, ctx->d_meta);
     CUDA_CHECK(cudaMemcpyAsync(ctx->h_scratch, ctx->d_meta, sizeof(MetaDev), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     const MetaDev *m = static_cast<const MetaDev *>(ctx->h_scratch);
@@ -65,6 +65,7 @@ void ensure_meta(pk_ctx *ctx, pk_dpoly *p)
         p->egcd[v] = m->egcd[v];
     }
     p->max_bits = m->max_bits;
+    p->any_neg = m->any_neg != 0;
     p->has_meta = true;
 }
 

@@ -42,7 +42,7 @@ struct MetaDev {
     i64 emax[PK_MAX_VARS];
     u64 egcd[PK_MAX_VARS]; // gcd over terms of (e - e_first)
     u32 max_bits;          // bit length of the largest coefficient magnitude
-    u32 pad;
+    u32 any_neg;           // some coefficient is negative
 };
 
 // Device-side counters of one multiplication (read back once at the end).

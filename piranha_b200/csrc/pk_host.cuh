@@ -66,6 +66,7 @@ struct pk_dpoly {
     std::vector<int64_t> emin, emax;
     std::vector<uint64_t> egcd;
     uint32_t max_bits = 0;
+    bool any_neg = false;
 };
 
 

@@ -73,8 +73,8 @@ __device__ __forceinline__ void atomic_gcd(u64 *p, u64 v)
 
 // One pass over a polynomial: decode every key, reduce per-variable min / max / gcd(e - e_first) and the widest
 // coefficient.  meta must be initialised (emin=+inf, emax=-inf, egcd=0, max_bits=0).
-__global__ void k_meta(const i64 *__restrict__ key, const u64 *__restrict__ planes, u64 n, u32 limbs, u64 stride,
-                       CodecParams cp, MetaDev *meta)
+__global__ void k_meta(const i64 *__restrict__ key, const u64 *__restrict__ planes, const signed char *__restrict__ sign,
+                       u64 n, u32 limbs, u64 stride, CodecParams cp, MetaDev *meta)
 {
     __shared__ i64 s_min[PK_MAX_VARS], s_max[PK_MAX_VARS];
     __shared__ u64 s_gcd[PK_MAX_VARS];
@@ -110,6 +110,7 @@ __global__ void k_meta(const i64 *__restrict__ key, const u64 *__restrict__ plan
             if (m) bits = 64u * l + bitlen64(m);
         }
         if (bits > s_bits) atomicMax(&s_bits, bits);
+        if (sign[i] < 0 && bits && !*((volatile u32 *)&meta->any_neg)) atomicOr(&meta->any_neg, 1u);
     }
     __syncthreads();
     for (u32 v = threadIdx.x; v < cp.n_vars; v += blockDim.x) {

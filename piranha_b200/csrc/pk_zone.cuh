@@ -32,28 +32,37 @@ namespace pk
 
 constexpr int kZoneThreads = 1024;
 
+// Result key codec, slimmed for the kernel parameter space: tight code -> piranha code by repeated division with
+// precomputed 64-bit magic multipliers (exact for 32-bit codes), digit * (step * piranha stride) summed up.
+struct ZoneCodec {
+    u32 n_vars;
+    u32 pad;
+    i64 base_code;
+    u32 tradix[PK_MAX_VARS];
+    u64 magic[PK_MAX_VARS];     // floor(2^64 / tradix) + 1
+    i64 spstride[PK_MAX_VARS];  // step * piranha stride
+};
+
 struct ZoneArgs {
-    const ulonglong2 *A; // {tight code | sign bit, magnitude limb 0}, ascending code
-    u64 nA;
-    const ulonglong2 *B;
-    u64 nB;
-    u64 lo, hi; // output partition of this call
-    u64 span;   // codes per zone
+    const uint4 *A; // {tight code (32 bit), sign flag, magnitude lo, magnitude hi}, ascending code
+    u32 nA;
+    const uint4 *B;
+    u32 nB;
+    u32 lo, hi; // output partition of this call (tight codes, < 2^32)
+    u32 span;   // codes per zone
     u32 n_zones, zones_per_chunk, n_chunks;
-    u32 mode; // 0 dense, 1 bitmap
-    u32 cap;  // accumulator entries per zone pass
+    u32 cap; // accumulator entries per zone pass
     u32 use_cursors;
     u32 pw; // 32-bit words of a product magnitude
     u32 bm_words;
-    u32 off_cursor, off_acc, off_bm, off_pre; // byte offsets into dynamic shared memory
+    u32 off_cursor, off_acc, off_bm, off_pre, off_list; // byte offsets into dynamic shared memory
     i64 *okey;
     u64 *oplanes;
     u64 ostride;
     signed char *osign;
     u32 out_limbs;
     u64 out_cap;
-    CodecParams cp;
-    i64 base_code;
+    ZoneCodec cd;
     u32 *chunk_counter;
     u32 *zone_count; // result terms of zone z
     u64 *zone_off;   // where zone z starts in the staging arrays
@@ -61,70 +70,90 @@ struct ZoneArgs {
     MulCounters *ctr;
 };
 
-__global__ void k_pack_operand(const u64 *__restrict__ key, const u64 *__restrict__ m0, ulonglong2 *__restrict__ out, u64 n)
+// prepared key (tight | sign bit) + magnitude -> packed 16-byte operand record
+__global__ void k_pack_operand(const u64 *__restrict__ key, const u64 *__restrict__ m0, uint4 *__restrict__ out, u64 n)
 {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = make_ulonglong2(key[i], m0[i]);
+    if (i < n) {
+        const u64 k = key[i], m = m0[i];
+        out[i] = make_uint4((u32)(k & 0xFFFFFFFFull), (u32)(k >> 63), (u32)m, (u32)(m >> 32));
+    }
 }
 
-// first index with (T[idx].x & mask) >= x
-__device__ __forceinline__ u32 zone_lower_bound(const ulonglong2 *__restrict__ T, u32 n, u64 x)
+// first index with T[idx].x >= x
+__device__ __forceinline__ u32 zone_lower_bound(const uint4 *__restrict__ T, u32 n, u32 x)
 {
     u32 lo = 0, hi = n;
     while (lo < hi) {
         const u32 mid = (lo + hi) >> 1;
-        if ((__ldg(&T[mid].x) & kKeyMask) < x) lo = mid + 1;
+        if (__ldg(&T[mid].x) < x) lo = mid + 1;
         else hi = mid;
     }
     return lo;
 }
 
-// acc[w * cap + slot] += / -= the 128-bit magnitude (p0..p3), eager carry through the returned old values.
-template <int NW>
-__device__ __forceinline__ void zone_accumulate(u32 *acc, u32 cap, u32 slot, u64 plo, u64 phi, u32 pw, bool neg)
+__device__ __forceinline__ u32 atoms_add(u32 saddr, u32 v)
 {
-    const u32 p[4] = {(u32)plo, (u32)(plo >> 32), (u32)phi, (u32)(phi >> 32)};
+    u32 old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void reds_add(u32 saddr, u32 v)
+{
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void reds_or(u32 saddr, u32 v)
+{
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
+// Accumulator word w of entry e lives at saddr0 + w * wstride (word planes).  The 128-bit magnitude p0..p3 is
+// added (subtracted when neg) word by word; the value returned by each ATOMS gives the carry (borrow) into the
+// next word.  Words below pw always issue their atomic (branch-free); above pw only a pending carry travels on.
+template <int NW, bool SIGNED>
+__device__ __forceinline__ void zone_accumulate(u32 saddr0, u32 wstride, u32 p0, u32 p1, u32 p2, u32 p3, u32 pw, bool neg)
+{
+    const u32 p[4] = {p0, p1, p2, p3};
     u32 c = 0;
+    u32 addr = saddr0;
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
+        const u32 pv = (w < 4) ? p[w < 4 ? w : 0] : 0u;
         if ((u32)w >= pw && c == 0) break;
-        const u64 t = (u64)((w < 4) ? p[w < 4 ? w : 0] : 0u) + c;
-        if (t == 0) {
-            c = 0;
-        } else if (t >> 32) {
-            c = 1; // exactly 2^32: this word is unchanged, the carry (borrow) moves on
+        const u32 x = pv + c;
+        const u32 ovf = (x < c) ? 1u : 0u; // pv == 0xffffffff and c == 1: the word is unchanged, the carry moves on
+        if (w == NW - 1) {
+            reds_add(addr, (SIGNED && neg) ? 0u - x : x); // top word: its carry-out is the proven-impossible overflow
+        } else if (SIGNED && neg) {
+            const u32 old = atoms_add(addr, 0u - x);
+            c = ((old < x) ? 1u : 0u) | ovf;
         } else {
-            const u32 x = (u32)t;
-            if (!neg) {
-                const u32 old = atomicAdd(&acc[w * cap + slot], x);
-                c = (old + x) < x;
-            } else {
-                const u32 old = atomicAdd(&acc[w * cap + slot], 0u - x);
-                c = old < x;
-            }
+            const u32 old = atoms_add(addr, x);
+            c = ((old + x < x) ? 1u : 0u) | ovf;
         }
+        addr += wstride;
     }
 }
 
-__device__ __forceinline__ i64 zone_code_to_piranha(u64 code, const CodecParams &cp, i64 base_code)
+__device__ __forceinline__ i64 zone_code_to_piranha(u32 code, const ZoneCodec &cd)
 {
-    i64 out = base_code;
-    if (code <= 0xFFFFFFFFull) { // 32-bit divisions are ~5x cheaper than 64-bit ones
-        u32 c = (u32)code;
-        for (u32 v = 0; v < cp.n_vars; ++v) {
-            const u32 r = (u32)cp.tradix[v];
-            const u32 q = c / r, d = c - q * r;
+    i64 out = cd.base_code;
+    u32 c = code;
+    for (u32 v = 0; v < cd.n_vars; ++v) {
+        const u32 r = cd.tradix[v];
+        if (r > 1) {
+            const u32 q = (u32)__umul64hi((u64)c, cd.magic[v]);
+            const u32 d = c - q * r;
             c = q;
-            out += (i64)d * cp.step[v] * cp.pstride[v];
+            out += (i64)d * cd.spstride[v];
         }
-        return out;
     }
-    return tight_to_piranha(code, cp, base_code);
+    return out;
 }
 
 // Two's complement NW words -> sign, magnitude; writes the term at `pos`.
 template <int NW>
-__device__ __forceinline__ void zone_emit(const ZoneArgs &a, u64 pos, u64 code, const u32 (&wd)[NW], u32 &maxbits, u32 &flags)
+__device__ __forceinline__ void zone_emit(const ZoneArgs &a, u64 pos, u32 code, const u32 (&wd)[NW], u32 &maxbits, u32 &flags)
 {
     u32 m[NW];
     const bool neg = (wd[NW - 1] >> 31) != 0;
@@ -153,12 +182,13 @@ __device__ __forceinline__ void zone_emit(const ZoneArgs &a, u64 pos, u64 code, 
         if (limb) bits = 64u * l + bitlen64(limb);
     }
     for (u32 l = (NW + 1) / 2; l < a.out_limbs; ++l) a.oplanes[(u64)l * a.ostride + pos] = 0;
-    a.okey[pos] = zone_code_to_piranha(code, a.cp, a.base_code);
+    a.okey[pos] = zone_code_to_piranha(code, a.cd);
     a.osign[pos] = neg ? (signed char)-1 : (signed char)1;
     maxbits = max(maxbits, bits);
 }
 
-template <int NW>
+// MODE 0: dense zones (slot = code - zlo).  MODE 1: bitmap zones (slot = rank of the code among the codes that occur).
+template <int NW, int MODE, bool SIGNED>
 __global__ void __launch_bounds__(kZoneThreads, 1) k_zone(const ZoneArgs a)
 {
     extern __shared__ __align__(16) unsigned char zsmem[];
@@ -166,19 +196,23 @@ __global__ void __launch_bounds__(kZoneThreads, 1) k_zone(const ZoneArgs a)
     u32 *acc = reinterpret_cast<u32 *>(zsmem + a.off_acc);
     u32 *bm = reinterpret_cast<u32 *>(zsmem + a.off_bm);
     u32 *pre = reinterpret_cast<u32 *>(zsmem + a.off_pre);
+    u32 *list = reinterpret_cast<u32 *>(zsmem + a.off_list);
     __shared__ u32 s_ws[40];
     __shared__ u64 s_b64[2];
     __shared__ u32 s_b32[4];
+    __shared__ u32 s_next; // dynamic row-batch counter
 
-    const u32 tid = threadIdx.x;
-    const u32 nA = (u32)a.nA, nB = (u32)a.nB;
-    const u64 kb0 = __ldg(&a.B[0].x) & kKeyMask, kbmax = __ldg(&a.B[nB - 1].x) & kKeyMask;
+    const u32 tid = threadIdx.x, lane = tid & 31u;
+    const u32 nA = a.nA, nB = a.nB;
+    const u32 kb0 = __ldg(&a.B[0].x), kbmax = __ldg(&a.B[nB - 1].x);
+    const u32 acc_s = smem_u32(acc), bm_s = smem_u32(bm);
+    const u32 wstride = a.cap * 4u;
     u64 my_pairs = 0;
     u32 my_maxbits = 0, my_flags = 0;
 
-    // accumulators (and bitmap) start cleared; every finalisation leaves them cleared again
+    // accumulators (and bitmap) start cleared; every pass leaves them cleared again
     for (u32 i = tid; i < a.cap * NW; i += kZoneThreads) acc[i] = 0;
-    if (a.mode == 1)
+    if (MODE == 1)
         for (u32 i = tid; i < a.bm_words; i += kZoneThreads) bm[i] = 0;
     __syncthreads();
 
@@ -190,32 +224,41 @@ __global__ void __launch_bounds__(kZoneThreads, 1) k_zone(const ZoneArgs a)
         if (chunk >= a.n_chunks) break;
         const u32 z0 = chunk * a.zones_per_chunk, z1 = min(a.n_zones, z0 + a.zones_per_chunk);
         if (a.use_cursors) { // one binary search per row per chunk
-            const u64 clo = a.lo + (u64)z0 * a.span;
+            const u32 clo = a.lo + z0 * a.span;
             for (u32 i = tid; i < nA; i += kZoneThreads) {
-                const u64 ka = __ldg(&a.A[i].x) & kKeyMask;
+                const u32 ka = __ldg(&a.A[i].x);
                 cursor[i] = (ka >= clo) ? 0u : zone_lower_bound(a.B, nB, clo - ka);
             }
             __syncthreads();
         }
         for (u32 z = z0; z < z1; ++z) {
-            const u64 zlo = a.lo + (u64)z * a.span;
-            const u64 zhi = min(a.hi, zlo + a.span);
+            const u32 zlo = a.lo + z * a.span;
+            const u32 zhi = (a.hi - zlo > a.span) ? zlo + a.span : a.hi;
             // rows that can reach the zone: a_i + b_max >= zlo and a_i + b_0 < zhi
             const u32 i_beg = (zlo > kbmax) ? zone_lower_bound(a.A, nA, zlo - kbmax) : 0u;
             const u32 i_end = (zhi > kb0) ? zone_lower_bound(a.A, nA, zhi - kb0) : 0u;
 
             // ---------------- walk 1 (bitmap zones): mark the codes that occur
-            u32 zone_count = 0; // distinct codes of the zone (bitmap mode)
-            if (a.mode == 1) {
-                for (u32 i = i_beg + tid; i < i_end; i += kZoneThreads) {
-                    const u64 ka = __ldg(&a.A[i].x) & kKeyMask;
-                    u32 j = a.use_cursors ? cursor[i] : ((ka >= zlo) ? 0u : zone_lower_bound(a.B, nB, zlo - ka));
-                    while (j < nB) {
-                        const u64 code = ka + (__ldg(&a.B[j].x) & kKeyMask);
-                        if (code >= zhi) break;
-                        const u32 slot = (u32)(code - zlo);
-                        atomicOr(&bm[slot >> 5], 1u << (slot & 31u));
-                        ++j;
+            u32 zone_count = 0;
+            if (MODE == 1) {
+                if (tid == 0) s_next = i_beg;
+                __syncthreads();
+                for (;;) {
+                    u32 r = 0;
+                    if (lane == 0) r = atomicAdd(&s_next, 32u);
+                    r = __shfl_sync(0xffffffffu, r, 0);
+                    if (r >= i_end) break;
+                    const u32 i = r + lane;
+                    if (i < i_end) {
+                        const u32 ka = __ldg(&a.A[i].x);
+                        u32 j = a.use_cursors ? cursor[i] : ((ka >= zlo) ? 0u : zone_lower_bound(a.B, nB, zlo - ka));
+                        while (j < nB) {
+                            const u32 code = ka + __ldg(&a.B[j].x);
+                            if (code >= zhi) break;
+                            const u32 slot = code - zlo;
+                            reds_or(bm_s + (slot >> 5) * 4u, 1u << (slot & 31u));
+                            ++j;
+                        }
                     }
                 }
                 __syncthreads();
@@ -235,132 +278,106 @@ __global__ void __launch_bounds__(kZoneThreads, 1) k_zone(const ZoneArgs a)
             }
 
             // ---------------- accumulate + emit, in passes of at most `cap` entries
-            const u32 n_entries = (a.mode == 1) ? zone_count : (u32)(zhi - zlo);
+            const u32 n_entries = (MODE == 1) ? zone_count : (zhi - zlo);
             const bool single = n_entries <= a.cap;
             u64 zone_base = 0, zone_written = 0;
             bool have_base = false;
-            u32 r0 = 0;      // first rank (bitmap) / slot (dense) of this pass
-            u64 c0 = zlo;    // first code of this pass
+            u32 r0 = 0;   // first rank (bitmap) / slot (dense) of this pass
+            u32 c0 = zlo; // first code of this pass
             do {
                 const u32 r1 = min(n_entries, r0 + a.cap);
-                u64 c1 = zhi;
-                if (r1 < n_entries) { // code of rank r1 bounds this pass (bitmap zones with more entries than cap)
-                    if (tid == 0) {
-                        u32 lo_w = 0, hi_w = a.bm_words; // last word with pre[w] <= r1
-                        while (hi_w - lo_w > 1) {
-                            const u32 mid = (lo_w + hi_w) >> 1;
-                            if (pre[mid] <= r1) lo_w = mid;
-                            else hi_w = mid;
-                        }
-                        while (__popc(bm[lo_w]) <= (int)(r1 - pre[lo_w])) ++lo_w; // skip empty words
-                        const u32 bit = __fns(bm[lo_w], 0, (int)(r1 - pre[lo_w]) + 1);
-                        s_b64[0] = zlo + (u64)lo_w * 32u + bit;
-                    }
-                    __syncthreads();
-                    c1 = s_b64[0];
-                    __syncthreads();
-                }
-                for (u32 i = i_beg + tid; i < i_end; i += kZoneThreads) {
-                    const ulonglong2 av = __ldg(&a.A[i]);
-                    const u64 ka = av.x & kKeyMask;
-                    u32 j = a.use_cursors ? cursor[i] : ((ka >= c0) ? 0u : zone_lower_bound(a.B, nB, c0 - ka));
-                    while (j < nB) {
-                        const ulonglong2 bv = __ldg(&a.B[j]);
-                        const u64 code = ka + (bv.x & kKeyMask);
-                        if (code >= c1) break;
-                        const u32 slot = (u32)(code - zlo);
-                        u32 e;
-                        if (a.mode == 1) e = pre[slot >> 5] + __popc(bm[slot >> 5] & ((1u << (slot & 31u)) - 1u)) - r0;
-                        else e = slot - r0;
-                        const u64 plo = av.y * bv.y, phi = __umul64hi(av.y, bv.y);
-                        zone_accumulate<NW>(acc, a.cap, e, plo, phi, a.pw, ((av.x ^ bv.x) >> 63) != 0);
-                        ++j;
-                        ++my_pairs;
-                    }
-                    if (a.use_cursors) cursor[i] = j;
-                }
-                __syncthreads();
-
-                // ---- emit the entries [r0, r1) in ascending code order; threads own contiguous pieces
-                const u32 n_pass = r1 - r0;
-                u32 cnt = 0;
-                u32 u0, u1; // unit range of this thread: slots (dense) or bitmap words (bitmap)
-                if (a.mode == 1) {
-                    const u32 wpt = (a.bm_words + kZoneThreads - 1) / kZoneThreads;
-                    u0 = min(a.bm_words, tid * wpt);
-                    u1 = min(a.bm_words, u0 + wpt);
-                    for (u32 w = u0; w < u1; ++w) {
-                        u32 bits = bm[w], rank = pre[w];
-                        while (bits) {
-                            bits &= bits - 1;
-                            if (rank >= r0 && rank < r1) {
-                                u32 any = 0;
-#pragma unroll
-                                for (int q = 0; q < NW; ++q) any |= acc[q * a.cap + (rank - r0)];
-                                cnt += any != 0;
+                u32 c1 = zhi;
+                if (MODE == 1) {
+                    if (r1 < n_entries) { // the code of rank r1 bounds this pass (zone with more entries than cap)
+                        if (tid == 0) {
+                            u32 lo_w = 0, hi_w = a.bm_words; // last word with pre[w] <= r1
+                            while (hi_w - lo_w > 1) {
+                                const u32 mid = (lo_w + hi_w) >> 1;
+                                if (pre[mid] <= r1) lo_w = mid;
+                                else hi_w = mid;
                             }
-                            ++rank;
+                            const u32 bit = __fns(bm[lo_w], 0, (int)(r1 - pre[lo_w]) + 1);
+                            s_b32[1] = zlo + lo_w * 32u + bit;
                         }
+                        __syncthreads();
+                        c1 = s_b32[1];
                     }
-                } else {
-                    const u32 spt = (n_pass + kZoneThreads - 1) / kZoneThreads;
-                    u0 = min(n_pass, tid * spt);
-                    u1 = min(n_pass, u0 + spt);
-                    for (u32 s = u0; s < u1; ++s) {
-                        u32 any = 0;
-#pragma unroll
-                        for (int q = 0; q < NW; ++q) any |= acc[q * a.cap + s];
-                        cnt += any != 0;
-                    }
-                }
-                u32 total;
-                const u32 excl = block_excl_scan(cnt, s_ws, total);
-                if (!have_base) { // claim staging space: exact for a single pass, the distinct count otherwise
-                    if (tid == 0) s_b64[1] = atomicAdd(a.bump, single ? (u64)total : (u64)n_entries);
-                    __syncthreads();
-                    zone_base = s_b64[1];
-                    have_base = true;
-                    __syncthreads();
-                }
-                u64 pos = zone_base + zone_written + excl;
-                if (a.mode == 1) {
-                    for (u32 w = u0; w < u1; ++w) {
+                    // rank -> slot list of this pass, so that emission runs with full warps
+                    const u32 wpt = (a.bm_words + kZoneThreads - 1) / kZoneThreads;
+                    const u32 w0 = min(a.bm_words, tid * wpt), w1 = min(a.bm_words, w0 + wpt);
+                    for (u32 w = w0; w < w1; ++w) {
                         u32 bits = bm[w], rank = pre[w];
                         while (bits) {
                             const u32 b = __ffs(bits) - 1;
                             bits &= bits - 1;
-                            if (rank >= r0 && rank < r1) {
-                                u32 wd[NW], any = 0;
-#pragma unroll
-                                for (int q = 0; q < NW; ++q) {
-                                    wd[q] = acc[q * a.cap + (rank - r0)];
-                                    acc[q * a.cap + (rank - r0)] = 0;
-                                    any |= wd[q];
-                                }
-                                if (any) {
-                                    zone_emit<NW>(a, pos, zlo + (u64)w * 32u + b, wd, my_maxbits, my_flags);
-                                    ++pos;
-                                }
-                            }
+                            if (rank >= r0 && rank < r1) list[rank - r0] = w * 32u + b;
                             ++rank;
                         }
                     }
-                } else {
-                    for (u32 s = u0; s < u1; ++s) {
-                        u32 wd[NW], any = 0;
-#pragma unroll
-                        for (int q = 0; q < NW; ++q) {
-                            wd[q] = acc[q * a.cap + s];
-                            acc[q * a.cap + s] = 0;
-                            any |= wd[q];
+                }
+                if (tid == 0) s_next = i_beg;
+                __syncthreads();
+                for (;;) {
+                    u32 r = 0;
+                    if (lane == 0) r = atomicAdd(&s_next, 32u);
+                    r = __shfl_sync(0xffffffffu, r, 0);
+                    if (r >= i_end) break;
+                    const u32 i = r + lane;
+                    if (i < i_end) {
+                        const uint4 av = __ldg(&a.A[i]);
+                        const u32 ka = av.x;
+                        const u64 ma = (u64)av.z | ((u64)av.w << 32);
+                        u32 j = a.use_cursors ? cursor[i] : ((ka >= c0) ? 0u : zone_lower_bound(a.B, nB, c0 - ka));
+                        u32 done = 0;
+                        while (j < nB) {
+                            const uint4 bv = __ldg(&a.B[j]);
+                            const u32 code = ka + bv.x;
+                            if (code >= c1) break;
+                            const u32 slot = code - zlo;
+                            u32 e;
+                            if (MODE == 1) e = pre[slot >> 5] + __popc(bm[slot >> 5] & ((1u << (slot & 31u)) - 1u)) - r0;
+                            else e = slot - r0;
+                            const u64 mb = (u64)bv.z | ((u64)bv.w << 32);
+                            const u64 plo = ma * mb, phi = __umul64hi(ma, mb);
+                            zone_accumulate<NW, SIGNED>(acc_s + e * 4u, wstride, (u32)plo, (u32)(plo >> 32), (u32)phi,
+                                                        (u32)(phi >> 32), a.pw, SIGNED && ((av.y ^ bv.y) != 0));
+                            ++j;
+                            ++done;
                         }
-                        if (any) {
-                            zone_emit<NW>(a, pos, zlo + r0 + s, wd, my_maxbits, my_flags);
-                            ++pos;
-                        }
+                        my_pairs += done;
+                        if (a.use_cursors) cursor[i] = j;
                     }
                 }
-                zone_written += total;
+                __syncthreads();
+
+                // ---- emit the entries [0, n_pass) of this pass in ascending code order, 1024 at a time
+                const u32 n_pass = r1 - r0;
+                for (u32 base = 0; base < n_pass; base += kZoneThreads) {
+                    const u32 e = base + tid;
+                    u32 wd[NW], any = 0;
+                    if (e < n_pass) {
+#pragma unroll
+                        for (int q = 0; q < NW; ++q) {
+                            wd[q] = acc[q * a.cap + e];
+                            acc[q * a.cap + e] = 0;
+                            any |= wd[q];
+                        }
+                    }
+                    u32 total;
+                    const u32 excl = block_excl_scan(any != 0 ? 1u : 0u, s_ws, total);
+                    if (!have_base) { // claim staging space: exact when one batch is the whole zone, else the entry count
+                        const bool exact = single && n_pass <= kZoneThreads;
+                        if (tid == 0) s_b64[1] = atomicAdd(a.bump, exact ? (u64)total : (u64)n_entries);
+                        __syncthreads();
+                        zone_base = s_b64[1];
+                        have_base = true;
+                    }
+                    if (any) {
+                        const u32 slot = (MODE == 1) ? list[e] : (r0 + e);
+                        zone_emit<NW>(a, zone_base + zone_written + excl, zlo + slot, wd, my_maxbits, my_flags);
+                    }
+                    zone_written += total;
+                }
                 r0 = r1;
                 c0 = c1;
                 __syncthreads();
@@ -369,7 +386,7 @@ __global__ void __launch_bounds__(kZoneThreads, 1) k_zone(const ZoneArgs a)
                 a.zone_count[z] = (u32)zone_written;
                 a.zone_off[z] = zone_base;
             }
-            if (a.mode == 1) { // clear the bitmap for the next zone
+            if (MODE == 1) { // clear the bitmap for the next zone
                 for (u32 i = tid; i < a.bm_words; i += kZoneThreads) bm[i] = 0;
             }
             __syncthreads();
@@ -381,7 +398,7 @@ __global__ void __launch_bounds__(kZoneThreads, 1) k_zone(const ZoneArgs a)
         my_maxbits = max(my_maxbits, __shfl_xor_sync(0xffffffffu, my_maxbits, o));
         my_flags |= __shfl_xor_sync(0xffffffffu, my_flags, o);
     }
-    if (lane_id() == 0) {
+    if (lane == 0) {
         if (my_pairs) atomicAdd(&a.ctr->pairs, my_pairs);
         if (my_maxbits) atomicMax(&a.ctr->max_bits, my_maxbits);
         if (my_flags) atomicOr(&a.ctr->flags, my_flags);
@@ -437,10 +454,37 @@ inline u32 env_u32(const char *name, u32 dflt)
     return v ? (u32)strtoul(v, nullptr, 10) : dflt;
 }
 
+template <int NW, int MODE, bool SIGNED>
+struct ZoneKernel {
+    static void set_smem(size_t bytes)
+    {
+        cudaFuncSetAttribute(k_zone<NW, MODE, SIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    }
+    static void launch(pk_ctx *ctx, const ZoneArgs &za, u32 grid, size_t smem)
+    {
+        PK_LAUNCH(ctx, (k_zone<NW, MODE, SIGNED>), grid, kZoneThreads, smem, za);
+    }
+};
+
 template <int NW>
-void zone_set_smem(size_t bytes)
+void zone_set_smem_nw(size_t b)
 {
-    cudaFuncSetAttribute(k_zone<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    ZoneKernel<NW, 0, false>::set_smem(b);
+    ZoneKernel<NW, 0, true>::set_smem(b);
+    ZoneKernel<NW, 1, false>::set_smem(b);
+    ZoneKernel<NW, 1, true>::set_smem(b);
+}
+
+template <int NW>
+void zone_launch_nw(pk_ctx *ctx, const ZoneArgs &za, u32 grid, size_t smem, u32 mode, bool is_signed)
+{
+    if (mode == 0) {
+        if (is_signed) ZoneKernel<NW, 0, true>::launch(ctx, za, grid, smem);
+        else ZoneKernel<NW, 0, false>::launch(ctx, za, grid, smem);
+    } else {
+        if (is_signed) ZoneKernel<NW, 1, true>::launch(ctx, za, grid, smem);
+        else ZoneKernel<NW, 1, false>::launch(ctx, za, grid, smem);
+    }
 }
 
 inline void zone_configure(pk_ctx *ctx)
@@ -453,18 +497,18 @@ inline void zone_configure(pk_ctx *ctx)
     t.force_mode = env_u32("PK_ZONE_MODE", t.force_mode);
     t.disable = env_u32("PK_ZONE_DISABLE", t.disable);
     const size_t dyn = ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0;
-    zone_set_smem<2>(dyn);
-    zone_set_smem<3>(dyn);
-    zone_set_smem<4>(dyn);
-    zone_set_smem<5>(dyn);
-    zone_set_smem<6>(dyn);
+    zone_set_smem_nw<2>(dyn);
+    zone_set_smem_nw<3>(dyn);
+    zone_set_smem_nw<4>(dyn);
+    zone_set_smem_nw<5>(dyn);
+    zone_set_smem_nw<6>(dyn);
 }
 
 struct ZonePlan {
     bool ok = false;
     u32 NW = 0, mode = 0, cap = 0, use_cursors = 0, bm_words = 0, n_zones = 0, zones_per_chunk = 1, n_chunks = 0;
-    u64 span = 0;
-    u32 off_cursor = 0, off_acc = 0, off_bm = 0, off_pre = 0;
+    u32 span = 0;
+    u32 off_cursor = 0, off_acc = 0, off_bm = 0, off_pre = 0, off_list = 0;
     size_t smem = 0;
 };
 
@@ -473,6 +517,7 @@ inline ZonePlan zone_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB, u64 sub_r
     const ZoneTuning &t = ctx->zone_tuning;
     ZonePlan zp;
     if (t.disable || pl.LA != 1 || pl.LB != 1 || sub_range == 0) return zp;
+    if (pl.range > 0xFFFFFFFFull) return zp; // the kernel works on 32-bit tight codes
     u32 NW = (pl.prod_bits + pl.cnt_bits + 1 + 31) / 32;
     NW = std::max<u32>(NW, 2);
     if (NW > 6) return zp;
@@ -494,7 +539,7 @@ inline ZonePlan zone_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB, u64 sub_r
     while (span_b > 1024 && (sub_range + span_b - 1) / span_b < target) span_b >>= 1;
     const size_t bm_bytes = span_b / 8, pre_bytes = span_b / 8;
     const u64 zones_b = (sub_range + span_b - 1) / span_b;
-    const bool bitmap_fits = avail > bm_bytes + pre_bytes + (size_t)NW * 4 * 256;
+    const bool bitmap_fits = avail > bm_bytes + pre_bytes + (size_t)(NW + 1) * 4 * 256;
     // cost model: a row visit costs about half a product; bitmap zones walk twice
     const double W = (double)nA * (double)nB;
     const double cost_d = (double)zones_d * (double)nA * 0.5 + W;
@@ -507,35 +552,36 @@ inline ZonePlan zone_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB, u64 sub_r
     zp.off_cursor = 0;
     off += zp.use_cursors ? cursor_bytes : 0;
     if (mode == 0) {
-        zp.span = span_d;
+        zp.span = (u32)span_d;
         zp.cap = (u32)span_d;
-        zp.n_zones = (u32)zones_d;
         if (zones_d > t.max_zones) return zp;
+        zp.n_zones = (u32)zones_d;
+        if (t.force_cap) { // tests: tiny dense zones
+            zp.cap = std::max<u32>(32, std::min<u32>(zp.cap, t.force_cap & ~31u));
+            zp.span = zp.cap;
+            const u64 nz = (sub_range + zp.span - 1) / zp.span;
+            if (nz > t.max_zones) return zp;
+            zp.n_zones = (u32)nz;
+        }
         zp.off_acc = (u32)off;
         off += (size_t)zp.cap * NW * 4;
     } else {
-        zp.span = span_b;
+        zp.span = (u32)span_b;
         zp.bm_words = (u32)(span_b / 32);
-        zp.n_zones = (u32)zones_b;
         if (zones_b > t.max_zones) return zp;
+        zp.n_zones = (u32)zones_b;
         zp.off_bm = (u32)off;
         off += bm_bytes;
         zp.off_pre = (u32)off;
         off += pre_bytes;
-        zp.off_acc = (u32)off;
-        u64 cap = ((budget - off) / (NW * 4)) & ~31ull;
+        u64 cap = ((budget - off) / ((NW + 1) * 4)) & ~31ull; // NW accumulator words + one list word per entry
         cap = std::min<u64>(cap, span_b);
+        if (t.force_cap) cap = std::max<u64>(1, std::min<u64>(cap, t.force_cap));
         zp.cap = (u32)cap;
+        zp.off_list = (u32)off;
+        off += ((size_t)zp.cap * 4 + 15) & ~15ull;
+        zp.off_acc = (u32)off;
         off += (size_t)zp.cap * NW * 4;
-    }
-    if (t.force_cap) {
-        if (mode == 0) { // dense: shrinking the capacity means shrinking the zone
-            zp.cap = std::max<u32>(32, t.force_cap & ~31u);
-            zp.span = zp.cap;
-            zp.n_zones = (u32)((sub_range + zp.span - 1) / zp.span);
-        } else {
-            zp.cap = std::max<u32>(1, std::min<u32>(zp.cap, t.force_cap));
-        }
     }
     zp.smem = off;
     zp.zones_per_chunk = zp.use_cursors ? t.zones_per_chunk : 1;
@@ -549,12 +595,6 @@ inline u32 choose_algo(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB, u64 sub_rang
     if (trunc) return PK_ALGO_AUTO_FALLBACK;
     if ((unsigned __int128)nA * nB < (1u << 16)) return PK_ALGO_AUTO_FALLBACK; // launch-bound anyway
     return zone_plan(ctx, pl, nA, nB, sub_range).ok ? PK_ALGO_ZONE : PK_ALGO_AUTO_FALLBACK;
-}
-
-template <int NW>
-void zone_launch(pk_ctx *ctx, const ZoneArgs &za, u32 grid, size_t smem)
-{
-    PK_LAUNCH(ctx, k_zone<NW>, grid, kZoneThreads, smem, za);
 }
 
 // Returns the product restricted to [lo, hi), or nullptr when the configuration is outside the zone path's envelope.
@@ -574,8 +614,8 @@ inline pk_dpoly *zone_multiply(pk_ctx *ctx, const Plan &pl, const pk_dpoly *A, c
     if ((unsigned __int128)out_cap * (9 + 8 * pl.out_limbs) > (unsigned __int128)total_b / 2) return nullptr;
 
     DevBuf pa(ctx, (nA + 1) * 16), pb(ctx, (nB + 1) * 16);
-    PK_LAUNCH(ctx, k_pack_operand, grid_for(nA, 256), 256, 0, keyA, A->planes, pa.as<ulonglong2>(), nA);
-    PK_LAUNCH(ctx, k_pack_operand, grid_for(nB, 256), 256, 0, keyB, magB, pb.as<ulonglong2>(), nB);
+    PK_LAUNCH(ctx, k_pack_operand, grid_for(nA, 256), 256, 0, keyA, A->planes, pa.as<uint4>(), nA);
+    PK_LAUNCH(ctx, k_pack_operand, grid_for(nB, 256), 256, 0, keyB, magB, pb.as<uint4>(), nB);
     // per-zone bookkeeping: offsets (u64), prefix (u64), counts (u32), then the bump cursor and the chunk counter
     const size_t nz = zp.n_zones;
     DevBuf book(ctx, nz * 20 + 64);
@@ -588,46 +628,53 @@ inline pk_dpoly *zone_multiply(pk_ctx *ctx, const Plan &pl, const pk_dpoly *A, c
 
     DPolyGuard g{ctx, new_dpoly(ctx, out_cap, nv, pl.out_limbs)};
     ZoneArgs za{};
-    za.A = pa.as<ulonglong2>();
-    za.nA = nA;
-    za.B = pb.as<ulonglong2>();
-    za.nB = nB;
-    za.lo = lo;
-    za.hi = hi;
+    za.A = pa.as<uint4>();
+    za.nA = (u32)nA;
+    za.B = pb.as<uint4>();
+    za.nB = (u32)nB;
+    za.lo = (u32)lo;
+    za.hi = (u32)hi;
     za.span = zp.span;
     za.n_zones = zp.n_zones;
     za.zones_per_chunk = zp.zones_per_chunk;
     za.n_chunks = zp.n_chunks;
-    za.mode = zp.mode;
     za.cap = zp.cap;
     za.use_cursors = zp.use_cursors;
-    za.pw = (pl.prod_bits + 31) / 32;
+    za.pw = std::min<u32>(4, (pl.prod_bits + 31) / 32);
     za.bm_words = zp.bm_words;
     za.off_cursor = zp.off_cursor;
     za.off_acc = zp.off_acc;
     za.off_bm = zp.off_bm;
     za.off_pre = zp.off_pre;
+    za.off_list = zp.off_list;
     za.okey = g.p->key;
     za.oplanes = g.p->planes;
     za.ostride = g.p->stride;
     za.osign = g.p->sign;
     za.out_limbs = pl.out_limbs;
     za.out_cap = out_cap;
-    za.cp = pl.cpR;
-    za.base_code = pl.base_code;
+    za.cd.n_vars = pl.cpR.n_vars;
+    za.cd.base_code = pl.base_code;
+    for (u32 v = 0; v < pl.cpR.n_vars; ++v) {
+        const u64 r = pl.cpR.tradix[v];
+        za.cd.tradix[v] = (u32)r;
+        za.cd.magic[v] = r > 1 ? (u64)((((unsigned __int128)1) << 64) / r) + 1 : 0;
+        za.cd.spstride[v] = (i64)((u64)pl.cpR.step[v] * (u64)pl.cpR.pstride[v]);
+    }
     za.chunk_counter = chunk_counter;
     za.zone_count = zone_count;
     za.zone_off = zone_off;
     za.bump = bump;
     za.ctr = ctx->d_ctr;
+    const bool is_signed = A->any_neg || B->any_neg;
     const u32 grid = std::min<u32>((u32)ctx->sm_count, zp.n_chunks);
     CUDA_CHECK(cudaEventRecord(ctx->ev_mul0, ctx->stream));
     switch (zp.NW) {
-    case 2: zone_launch<2>(ctx, za, grid, zp.smem); break;
-    case 3: zone_launch<3>(ctx, za, grid, zp.smem); break;
-    case 4: zone_launch<4>(ctx, za, grid, zp.smem); break;
-    case 5: zone_launch<5>(ctx, za, grid, zp.smem); break;
-    default: zone_launch<6>(ctx, za, grid, zp.smem); break;
+    case 2: zone_launch_nw<2>(ctx, za, grid, zp.smem, zp.mode, is_signed); break;
+    case 3: zone_launch_nw<3>(ctx, za, grid, zp.smem, zp.mode, is_signed); break;
+    case 4: zone_launch_nw<4>(ctx, za, grid, zp.smem, zp.mode, is_signed); break;
+    case 5: zone_launch_nw<5>(ctx, za, grid, zp.smem, zp.mode, is_signed); break;
+    default: zone_launch_nw<6>(ctx, za, grid, zp.smem, zp.mode, is_signed); break;
     }
     CUDA_CHECK(cudaEventRecord(ctx->ev_mul1, ctx->stream));
     PK_LAUNCH(ctx, k_zone_scan, 1, 1024, 0, zone_count, zone_prefix, zp.n_zones, &ctx->d_ctr->n_out);
