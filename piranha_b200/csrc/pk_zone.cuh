@@ -352,6 +352,23 @@ __global__ void __launch_bounds__(kZoneThreads, 1) k_zone(const ZoneArgs a)
 
                 // ---- emit the entries [0, n_pass) of this pass in ascending code order, 1024 at a time
                 const u32 n_pass = r1 - r0;
+                if (!have_base) { // claim staging space: the exact count of a single-pass zone, else the entry count
+                    u32 nz = 0;
+                    if (single) {
+                        for (u32 e = tid; e < n_pass; e += kZoneThreads) {
+                            u32 any = 0;
+#pragma unroll
+                            for (int q = 0; q < NW; ++q) any |= acc[q * a.cap + e];
+                            nz += any != 0;
+                        }
+                    }
+                    u32 total_nz;
+                    block_excl_scan(nz, s_ws, total_nz);
+                    if (tid == 0) s_b64[1] = atomicAdd(a.bump, single ? (u64)total_nz : (u64)n_entries);
+                    __syncthreads();
+                    zone_base = s_b64[1];
+                    have_base = true;
+                }
                 for (u32 base = 0; base < n_pass; base += kZoneThreads) {
                     const u32 e = base + tid;
                     u32 wd[NW], any = 0;
@@ -365,13 +382,6 @@ __global__ void __launch_bounds__(kZoneThreads, 1) k_zone(const ZoneArgs a)
                     }
                     u32 total;
                     const u32 excl = block_excl_scan(any != 0 ? 1u : 0u, s_ws, total);
-                    if (!have_base) { // claim staging space: exact when one batch is the whole zone, else the entry count
-                        const bool exact = single && n_pass <= kZoneThreads;
-                        if (tid == 0) s_b64[1] = atomicAdd(a.bump, exact ? (u64)total : (u64)n_entries);
-                        __syncthreads();
-                        zone_base = s_b64[1];
-                        have_base = true;
-                    }
                     if (any) {
                         const u32 slot = (MODE == 1) ? list[e] : (r0 + e);
                         zone_emit<NW>(a, zone_base + zone_written + excl, zlo + slot, wd, my_maxbits, my_flags);
