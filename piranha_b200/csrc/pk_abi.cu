@@ -534,6 +534,7 @@ int pk_ctx_create(int device, void *stream, pk_ctx **out)
     if (cudaSetDevice(device) != cudaSuccess) return PK_E_CUDA;
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
+    c->smem_per_sm = prop.sharedMemPerMultiprocessor;
     if (stream) {
         c->stream = static_cast<cudaStream_t>(stream);
     } else {
@@ -635,6 +636,7 @@ int pk_ctx_set_tuning(pk_ctx *ctx, const char *key, uint64_t value)
     else if (k == "zone_mode") t.force_mode = (u32)value;
     else if (k == "zone_disable") t.disable = (u32)value;
     else if (k == "zone_cursor_bytes") t.cursor_bytes_max = (u32)value;
+    else if (k == "zone_tpb") t.tpb = (value == 256 || value == 512 || value == 1024) ? (u32)value : 0;
     else return PK_E_ARGS;
     return PK_OK;
 }

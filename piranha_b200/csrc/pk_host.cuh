@@ -22,8 +22,9 @@ struct ZoneTuning {
     uint32_t force_cap = 0;       // tests: force a small accumulator capacity to exercise multi-pass zones
     uint32_t force_mode = 0;      // 0 auto, 1 dense, 2 bitmap
     uint32_t max_zones = 1u << 20;
-    uint32_t cursor_bytes_max = 64u << 10;
+    uint32_t cursor_bytes_max = 64u << 20; // row cursors live in global memory; 0 disables them
     uint32_t disable = 0;
+    uint32_t tpb = 0;              // threads per block: 0 auto, 256 / 512 / 1024
 };
 
 } // namespace pk
@@ -54,6 +55,7 @@ struct pk_ctx {
     int sm_count = 148;
     pk::ZoneTuning zone_tuning;
     size_t smem_optin = 0;
+    size_t smem_per_sm = 0;
 };
 
 struct pk_dpoly {

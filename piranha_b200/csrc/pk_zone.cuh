@@ -30,7 +30,6 @@
 namespace pk
 {
 
-constexpr int kZoneThreads = 1024;
 
 // Result key codec, slimmed for the kernel parameter space: tight code -> piranha code by repeated division with
 // precomputed 64-bit magic multipliers (exact for 32-bit codes), digit * (step * piranha stride) summed up.
@@ -55,7 +54,9 @@ struct ZoneArgs {
     u32 use_cursors;
     u32 pw; // 32-bit words of a product magnitude
     u32 bm_words;
-    u32 off_cursor, off_acc, off_bm, off_pre, off_list; // byte offsets into dynamic shared memory
+    u32 *cursors;      // use_cursors: nA row cursors per block, in global memory (L1/L2 resident, coalesced per batch)
+    u32 cursor_stride; // words per block
+    u32 off_acc, off_bm, off_pre, off_list; // byte offsets into dynamic shared memory
     i64 *okey;
     u64 *oplanes;
     u64 ostride;
@@ -188,11 +189,14 @@ __device__ __forceinline__ void zone_emit(const ZoneArgs &a, u64 pos, u32 code, 
 }
 
 // MODE 0: dense zones (slot = code - zlo).  MODE 1: bitmap zones (slot = rank of the code among the codes that occur).
-template <int NW, int MODE, bool SIGNED>
-__global__ void __launch_bounds__(kZoneThreads, 1) k_zone(const ZoneArgs a)
+// TPB threads per block, 1024 / TPB blocks per SM: while one block sits in a barrier phase (prefix, emit, walk tail)
+// the others keep the issue slots busy.
+template <int NW, int MODE, bool SIGNED, int TPB>
+__global__ void __launch_bounds__(TPB, 1024 / TPB) k_zone(const ZoneArgs a)
 {
+    constexpr u32 kZoneThreads = TPB;
     extern __shared__ __align__(16) unsigned char zsmem[];
-    u32 *cursor = reinterpret_cast<u32 *>(zsmem + a.off_cursor);
+    u32 *cursor = a.cursors + (size_t)blockIdx.x * a.cursor_stride;
     u32 *acc = reinterpret_cast<u32 *>(zsmem + a.off_acc);
     u32 *bm = reinterpret_cast<u32 *>(zsmem + a.off_bm);
     u32 *pre = reinterpret_cast<u32 *>(zsmem + a.off_pre);
@@ -262,16 +266,22 @@ __global__ void __launch_bounds__(kZoneThreads, 1) k_zone(const ZoneArgs a)
                     }
                 }
                 __syncthreads();
-                // exclusive popcount prefix per bitmap word: rank(code) = pre[word] + popc(bits below)
-                const u32 wpt = (a.bm_words + kZoneThreads - 1) / kZoneThreads;
-                const u32 w0 = min(a.bm_words, tid * wpt), w1 = min(a.bm_words, w0 + wpt);
+                // exclusive popcount prefix per group of 4 bitmap words (128 codes):
+                // rank(code) = pre[group] + popc(words of the group below) + popc(bits below in its word)
+                const u32 n_groups = a.bm_words >> 2;
+                const u32 gpt = (n_groups + kZoneThreads - 1) / kZoneThreads;
+                const u32 g0 = min(n_groups, tid * gpt), g1 = min(n_groups, g0 + gpt);
                 u32 local = 0;
-                for (u32 w = w0; w < w1; ++w) local += __popc(bm[w]);
+                for (u32 g = g0; g < g1; ++g) {
+                    const uint4 w4 = reinterpret_cast<const uint4 *>(bm)[g];
+                    local += __popc(w4.x) + __popc(w4.y) + __popc(w4.z) + __popc(w4.w);
+                }
                 u32 total;
                 u32 run = block_excl_scan(local, s_ws, total);
-                for (u32 w = w0; w < w1; ++w) {
-                    pre[w] = run;
-                    run += __popc(bm[w]);
+                for (u32 g = g0; g < g1; ++g) {
+                    const uint4 w4 = reinterpret_cast<const uint4 *>(bm)[g];
+                    pre[g] = run;
+                    run += __popc(w4.x) + __popc(w4.y) + __popc(w4.z) + __popc(w4.w);
                 }
                 zone_count = total;
                 __syncthreads();
@@ -288,30 +298,38 @@ __global__ void __launch_bounds__(kZoneThreads, 1) k_zone(const ZoneArgs a)
                 const u32 r1 = min(n_entries, r0 + a.cap);
                 u32 c1 = zhi;
                 if (MODE == 1) {
+                    const u32 n_groups = a.bm_words >> 2;
                     if (r1 < n_entries) { // the code of rank r1 bounds this pass (zone with more entries than cap)
                         if (tid == 0) {
-                            u32 lo_w = 0, hi_w = a.bm_words; // last word with pre[w] <= r1
-                            while (hi_w - lo_w > 1) {
-                                const u32 mid = (lo_w + hi_w) >> 1;
-                                if (pre[mid] <= r1) lo_w = mid;
-                                else hi_w = mid;
+                            u32 lo_g = 0, hi_g = n_groups; // last group with pre[g] <= r1
+                            while (hi_g - lo_g > 1) {
+                                const u32 mid = (lo_g + hi_g) >> 1;
+                                if (pre[mid] <= r1) lo_g = mid;
+                                else hi_g = mid;
                             }
-                            const u32 bit = __fns(bm[lo_w], 0, (int)(r1 - pre[lo_w]) + 1);
-                            s_b32[1] = zlo + lo_w * 32u + bit;
+                            u32 rem = r1 - pre[lo_g], w = lo_g * 4;
+                            while (rem >= (u32)__popc(bm[w])) {
+                                rem -= __popc(bm[w]);
+                                ++w;
+                            }
+                            s_b32[1] = zlo + w * 32u + __fns(bm[w], 0, (int)rem + 1);
                         }
                         __syncthreads();
                         c1 = s_b32[1];
                     }
                     // rank -> slot list of this pass, so that emission runs with full warps
-                    const u32 wpt = (a.bm_words + kZoneThreads - 1) / kZoneThreads;
-                    const u32 w0 = min(a.bm_words, tid * wpt), w1 = min(a.bm_words, w0 + wpt);
-                    for (u32 w = w0; w < w1; ++w) {
-                        u32 bits = bm[w], rank = pre[w];
-                        while (bits) {
-                            const u32 b = __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            if (rank >= r0 && rank < r1) list[rank - r0] = w * 32u + b;
-                            ++rank;
+                    const u32 gpt = (n_groups + kZoneThreads - 1) / kZoneThreads;
+                    const u32 g0 = min(n_groups, tid * gpt), g1 = min(n_groups, g0 + gpt);
+                    for (u32 g = g0; g < g1; ++g) {
+                        u32 rank = pre[g];
+                        for (u32 q = 0; q < 4; ++q) {
+                            u32 bits = bm[g * 4 + q];
+                            while (bits) {
+                                const u32 b = __ffs(bits) - 1;
+                                bits &= bits - 1;
+                                if (rank >= r0 && rank < r1) list[rank - r0] = (g * 4 + q) * 32u + b;
+                                ++rank;
+                            }
                         }
                     }
                 }
@@ -335,8 +353,16 @@ __global__ void __launch_bounds__(kZoneThreads, 1) k_zone(const ZoneArgs a)
                             if (code >= c1) break;
                             const u32 slot = code - zlo;
                             u32 e;
-                            if (MODE == 1) e = pre[slot >> 5] + __popc(bm[slot >> 5] & ((1u << (slot & 31u)) - 1u)) - r0;
-                            else e = slot - r0;
+                            if (MODE == 1) {
+                                const u32 g = slot >> 7, q = (slot >> 5) & 3u;
+                                const uint4 w4 = reinterpret_cast<const uint4 *>(bm)[g];
+                                const u32 wq = q == 0 ? w4.x : (q == 1 ? w4.y : (q == 2 ? w4.z : w4.w));
+                                u32 rk = pre[g] + __popc(wq & ((1u << (slot & 31u)) - 1u));
+                                rk += (q > 0 ? __popc(w4.x) : 0) + (q > 1 ? __popc(w4.y) : 0) + (q > 2 ? __popc(w4.z) : 0);
+                                e = rk - r0;
+                            } else {
+                                e = slot - r0;
+                            }
                             const u64 mb = (u64)bv.z | ((u64)bv.w << 32);
                             const u64 plo = ma * mb, phi = __umul64hi(ma, mb);
                             zone_accumulate<NW, SIGNED>(acc_s + e * 4u, wstride, (u32)plo, (u32)(plo >> 32), (u32)phi,
@@ -464,37 +490,53 @@ inline u32 env_u32(const char *name, u32 dflt)
     return v ? (u32)strtoul(v, nullptr, 10) : dflt;
 }
 
-template <int NW, int MODE, bool SIGNED>
+template <int NW, int MODE, bool SIGNED, int TPB>
 struct ZoneKernel {
     static void set_smem(size_t bytes)
     {
-        cudaFuncSetAttribute(k_zone<NW, MODE, SIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaFuncSetAttribute(k_zone<NW, MODE, SIGNED, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     }
     static void launch(pk_ctx *ctx, const ZoneArgs &za, u32 grid, size_t smem)
     {
-        PK_LAUNCH(ctx, (k_zone<NW, MODE, SIGNED>), grid, kZoneThreads, smem, za);
+        PK_LAUNCH(ctx, (k_zone<NW, MODE, SIGNED, TPB>), grid, TPB, smem, za);
     }
 };
 
-template <int NW>
-void zone_set_smem_nw(size_t b)
+template <int NW, int TPB>
+void zone_set_smem_nt(size_t b)
 {
-    ZoneKernel<NW, 0, false>::set_smem(b);
-    ZoneKernel<NW, 0, true>::set_smem(b);
-    ZoneKernel<NW, 1, false>::set_smem(b);
-    ZoneKernel<NW, 1, true>::set_smem(b);
+    ZoneKernel<NW, 0, false, TPB>::set_smem(b);
+    ZoneKernel<NW, 0, true, TPB>::set_smem(b);
+    ZoneKernel<NW, 1, false, TPB>::set_smem(b);
+    ZoneKernel<NW, 1, true, TPB>::set_smem(b);
 }
 
 template <int NW>
-void zone_launch_nw(pk_ctx *ctx, const ZoneArgs &za, u32 grid, size_t smem, u32 mode, bool is_signed)
+void zone_set_smem_nw(size_t optin)
+{
+    zone_set_smem_nt<NW, 1024>(optin);
+    zone_set_smem_nt<NW, 512>(optin);
+    zone_set_smem_nt<NW, 256>(optin);
+}
+
+template <int NW, int TPB>
+void zone_launch_nt(pk_ctx *ctx, const ZoneArgs &za, u32 grid, size_t smem, u32 mode, bool is_signed)
 {
     if (mode == 0) {
-        if (is_signed) ZoneKernel<NW, 0, true>::launch(ctx, za, grid, smem);
-        else ZoneKernel<NW, 0, false>::launch(ctx, za, grid, smem);
+        if (is_signed) ZoneKernel<NW, 0, true, TPB>::launch(ctx, za, grid, smem);
+        else ZoneKernel<NW, 0, false, TPB>::launch(ctx, za, grid, smem);
     } else {
-        if (is_signed) ZoneKernel<NW, 1, true>::launch(ctx, za, grid, smem);
-        else ZoneKernel<NW, 1, false>::launch(ctx, za, grid, smem);
+        if (is_signed) ZoneKernel<NW, 1, true, TPB>::launch(ctx, za, grid, smem);
+        else ZoneKernel<NW, 1, false, TPB>::launch(ctx, za, grid, smem);
     }
+}
+
+template <int NW>
+void zone_launch_nw(pk_ctx *ctx, const ZoneArgs &za, u32 grid, size_t smem, u32 mode, bool is_signed, u32 tpb)
+{
+    if (tpb == 256) zone_launch_nt<NW, 256>(ctx, za, grid, smem, mode, is_signed);
+    else if (tpb == 512) zone_launch_nt<NW, 512>(ctx, za, grid, smem, mode, is_signed);
+    else zone_launch_nt<NW, 1024>(ctx, za, grid, smem, mode, is_signed);
 }
 
 inline void zone_configure(pk_ctx *ctx)
@@ -506,6 +548,7 @@ inline void zone_configure(pk_ctx *ctx)
     t.force_cap = env_u32("PK_ZONE_CAP", t.force_cap);
     t.force_mode = env_u32("PK_ZONE_MODE", t.force_mode);
     t.disable = env_u32("PK_ZONE_DISABLE", t.disable);
+    t.tpb = env_u32("PK_ZONE_TPB", t.tpb);
     const size_t dyn = ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0;
     zone_set_smem_nw<2>(dyn);
     zone_set_smem_nw<3>(dyn);
@@ -517,8 +560,8 @@ inline void zone_configure(pk_ctx *ctx)
 struct ZonePlan {
     bool ok = false;
     u32 NW = 0, mode = 0, cap = 0, use_cursors = 0, bm_words = 0, n_zones = 0, zones_per_chunk = 1, n_chunks = 0;
-    u32 span = 0;
-    u32 off_cursor = 0, off_acc = 0, off_bm = 0, off_pre = 0, off_list = 0;
+    u32 span = 0, tpb = 1024, grid = 0;
+    u32 off_acc = 0, off_bm = 0, off_pre = 0, off_list = 0;
     size_t smem = 0;
 };
 
@@ -532,71 +575,85 @@ inline ZonePlan zone_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB, u64 sub_r
     NW = std::max<u32>(NW, 2);
     if (NW > 6) return zp;
     zp.NW = NW;
-    const size_t budget = (ctx->smem_optin > 4096 ? ctx->smem_optin - 2048 : 0);
-    if (budget < (64u << 10)) return zp;
-    const size_t cursor_bytes = ((nA * 4 + 15) & ~15ull);
-    zp.use_cursors = cursor_bytes <= t.cursor_bytes_max ? 1 : 0;
-    const size_t avail = budget - (zp.use_cursors ? cursor_bytes : 0);
+    zp.use_cursors = (nA * 4 <= (u64)t.cursor_bytes_max) ? 1 : 0;
     const u32 target = t.target_zones ? t.target_zones : (u32)ctx->sm_count * 16;
-    const u64 dense_cap_max = (avail / (NW * 4)) & ~31ull;
-    // dense zones sized for the target zone count, but never beyond what shared memory holds
-    u64 span_d = std::max<u64>(64, (sub_range + target - 1) / target);
-    span_d = (span_d + 31) & ~31ull;
-    if (span_d > dense_cap_max) span_d = dense_cap_max;
-    const u64 zones_d = (sub_range + span_d - 1) / span_d;
-    // bitmap zones
-    u64 span_b = 1ull << t.span_log2_max;
-    while (span_b > 1024 && (sub_range + span_b - 1) / span_b < target) span_b >>= 1;
-    const size_t bm_bytes = span_b / 8, pre_bytes = span_b / 8;
-    const u64 zones_b = (sub_range + span_b - 1) / span_b;
-    const bool bitmap_fits = avail > bm_bytes + pre_bytes + (size_t)(NW + 1) * 4 * 256;
-    // cost model: a row visit costs about half a product; bitmap zones walk twice
     const double W = (double)nA * (double)nB;
-    const double cost_d = (double)zones_d * (double)nA * 0.5 + W;
-    const double cost_b = bitmap_fits ? (double)zones_b * (double)nA * 1.0 + W * 1.6 : 1e300;
-    u32 mode = cost_d <= cost_b ? 0 : 1;
-    if (t.force_mode == 1) mode = 0;
-    if (t.force_mode == 2 && bitmap_fits) mode = 1;
-    zp.mode = mode;
-    size_t off = 0;
-    zp.off_cursor = 0;
-    off += zp.use_cursors ? cursor_bytes : 0;
-    if (mode == 0) {
-        zp.span = (u32)span_d;
-        zp.cap = (u32)span_d;
-        if (zones_d > t.max_zones) return zp;
-        zp.n_zones = (u32)zones_d;
-        if (t.force_cap) { // tests: tiny dense zones
-            zp.cap = std::max<u32>(32, std::min<u32>(zp.cap, t.force_cap & ~31u));
-            zp.span = zp.cap;
-            const u64 nz = (sub_range + zp.span - 1) / zp.span;
-            if (nz > t.max_zones) return zp;
-            zp.n_zones = (u32)nz;
+    // cost of one candidate (mode, threads per block): a row visit costs about half a product, bitmap zones walk twice
+    double best_cost = 1e300;
+    for (u32 tpb : {1024u, 512u, 256u}) {
+        if (t.tpb && t.tpb != tpb) continue;
+        const u32 ctas = 1024 / tpb;
+        size_t budget = (ctx->smem_per_sm > ctas * 1024 ? (ctx->smem_per_sm - ctas * 1024) / ctas : 0);
+        budget = std::min(budget, ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0);
+        budget = budget > 1024 ? (budget - 512) & ~255ull : 0; // static shared memory + alignment slack
+        if (budget < (16u << 10)) continue;
+        for (u32 mode = 0; mode < 2; ++mode) {
+            if (t.force_mode == 1 && mode != 0) continue;
+            if (t.force_mode == 2 && mode != 1) continue;
+            ZonePlan c;
+            c.NW = NW;
+            c.use_cursors = zp.use_cursors;
+            c.mode = mode;
+            c.tpb = tpb;
+            size_t off = 0;
+            double cost;
+            if (mode == 0) {
+                const u64 cap_max = (budget / (NW * 4)) & ~31ull;
+                if (cap_max < 32) continue;
+                u64 span = std::max<u64>(64, (sub_range + target - 1) / target);
+                span = (span + 31) & ~31ull;
+                span = std::min(span, cap_max);
+                if (t.force_cap) span = std::max<u64>(32, std::min<u64>(span, t.force_cap & ~31u));
+                const u64 nz = (sub_range + span - 1) / span;
+                if (nz > t.max_zones) continue;
+                c.span = (u32)span;
+                c.cap = (u32)span;
+                c.n_zones = (u32)nz;
+                c.off_acc = 0;
+                off = (size_t)c.cap * NW * 4;
+                cost = (double)nz * (double)nA * 0.5 + W;
+            } else {
+                u64 span = 1ull << t.span_log2_max;
+                while (span > 1024 && (sub_range + span - 1) / span < target) span >>= 1;
+                // bitmap (span / 8 bytes) + prefix per 128 codes (span / 32 bytes) must leave room for entries
+                while (span > 1024 && span / 8 + span / 32 + (size_t)(NW + 1) * 4 * 512 > budget) span >>= 1;
+                const size_t bm_bytes = span / 8, pre_bytes = span / 32;
+                if (bm_bytes + pre_bytes + (size_t)(NW + 1) * 4 * 64 > budget) continue;
+                const u64 nz = (sub_range + span - 1) / span;
+                if (nz > t.max_zones) continue;
+                c.span = (u32)span;
+                c.bm_words = (u32)(span / 32);
+                c.n_zones = (u32)nz;
+                c.off_bm = 0;
+                off = bm_bytes;
+                c.off_pre = (u32)off;
+                off += (pre_bytes + 15) & ~15ull;
+                u64 cap = ((budget - off - 16) / ((NW + 1) * 4)) & ~31ull; // NW accumulator words + one list word
+                cap = std::min<u64>(cap, span);
+                if (t.force_cap) cap = std::max<u64>(1, std::min<u64>(cap, t.force_cap));
+                c.cap = (u32)cap;
+                c.off_list = (u32)off;
+                off += ((size_t)c.cap * 4 + 15) & ~15ull;
+                c.off_acc = (u32)off;
+                off += (size_t)c.cap * NW * 4;
+                // expected passes per zone when zones are denser than the capacity
+                const double dens = std::min(1.0, W / (double)sub_range);
+                const double passes = std::max(1.0, dens * (double)span / (double)cap);
+                cost = (double)nz * (double)nA * (0.5 + 0.5 * passes) + W * 1.6;
+            }
+            cost *= (tpb == 1024 ? 1.15 : (tpb == 512 ? 1.0 : 1.02)); // measured preference (profiles/)
+            c.smem = off;
+            if (cost < best_cost) {
+                best_cost = cost;
+                zp = c;
+                zp.ok = true;
+            }
         }
-        zp.off_acc = (u32)off;
-        off += (size_t)zp.cap * NW * 4;
-    } else {
-        zp.span = (u32)span_b;
-        zp.bm_words = (u32)(span_b / 32);
-        if (zones_b > t.max_zones) return zp;
-        zp.n_zones = (u32)zones_b;
-        zp.off_bm = (u32)off;
-        off += bm_bytes;
-        zp.off_pre = (u32)off;
-        off += pre_bytes;
-        u64 cap = ((budget - off) / ((NW + 1) * 4)) & ~31ull; // NW accumulator words + one list word per entry
-        cap = std::min<u64>(cap, span_b);
-        if (t.force_cap) cap = std::max<u64>(1, std::min<u64>(cap, t.force_cap));
-        zp.cap = (u32)cap;
-        zp.off_list = (u32)off;
-        off += ((size_t)zp.cap * 4 + 15) & ~15ull;
-        zp.off_acc = (u32)off;
-        off += (size_t)zp.cap * NW * 4;
     }
-    zp.smem = off;
+    if (!zp.ok) return zp;
     zp.zones_per_chunk = zp.use_cursors ? t.zones_per_chunk : 1;
     zp.n_chunks = (zp.n_zones + zp.zones_per_chunk - 1) / zp.zones_per_chunk;
-    zp.ok = true;
+    zp.grid = std::min<u32>((u32)ctx->sm_count * (1024 / zp.tpb), zp.n_chunks);
     return zp;
 }
 
@@ -636,6 +693,9 @@ inline pk_dpoly *zone_multiply(pk_ctx *ctx, const Plan &pl, const pk_dpoly *A, c
     u32 *zone_count = chunk_counter + 2;
     CUDA_CHECK(cudaMemsetAsync(bump, 0, 16, ctx->stream));
 
+    const u32 cursor_stride = (u32)((nA + 31) & ~31ull);
+    DevBuf cursors(ctx, zp.use_cursors ? (size_t)zp.grid * cursor_stride * 4 : 0);
+
     DPolyGuard g{ctx, new_dpoly(ctx, out_cap, nv, pl.out_limbs)};
     ZoneArgs za{};
     za.A = pa.as<uint4>();
@@ -652,7 +712,8 @@ inline pk_dpoly *zone_multiply(pk_ctx *ctx, const Plan &pl, const pk_dpoly *A, c
     za.use_cursors = zp.use_cursors;
     za.pw = std::min<u32>(4, (pl.prod_bits + 31) / 32);
     za.bm_words = zp.bm_words;
-    za.off_cursor = zp.off_cursor;
+    za.cursors = cursors.as<u32>();
+    za.cursor_stride = cursor_stride;
     za.off_acc = zp.off_acc;
     za.off_bm = zp.off_bm;
     za.off_pre = zp.off_pre;
@@ -677,14 +738,14 @@ inline pk_dpoly *zone_multiply(pk_ctx *ctx, const Plan &pl, const pk_dpoly *A, c
     za.bump = bump;
     za.ctr = ctx->d_ctr;
     const bool is_signed = A->any_neg || B->any_neg;
-    const u32 grid = std::min<u32>((u32)ctx->sm_count, zp.n_chunks);
+    const u32 grid = zp.grid;
     CUDA_CHECK(cudaEventRecord(ctx->ev_mul0, ctx->stream));
     switch (zp.NW) {
-    case 2: zone_launch_nw<2>(ctx, za, grid, zp.smem, zp.mode, is_signed); break;
-    case 3: zone_launch_nw<3>(ctx, za, grid, zp.smem, zp.mode, is_signed); break;
-    case 4: zone_launch_nw<4>(ctx, za, grid, zp.smem, zp.mode, is_signed); break;
-    case 5: zone_launch_nw<5>(ctx, za, grid, zp.smem, zp.mode, is_signed); break;
-    default: zone_launch_nw<6>(ctx, za, grid, zp.smem, zp.mode, is_signed); break;
+    case 2: zone_launch_nw<2>(ctx, za, grid, zp.smem, zp.mode, is_signed, zp.tpb); break;
+    case 3: zone_launch_nw<3>(ctx, za, grid, zp.smem, zp.mode, is_signed, zp.tpb); break;
+    case 4: zone_launch_nw<4>(ctx, za, grid, zp.smem, zp.mode, is_signed, zp.tpb); break;
+    case 5: zone_launch_nw<5>(ctx, za, grid, zp.smem, zp.mode, is_signed, zp.tpb); break;
+    default: zone_launch_nw<6>(ctx, za, grid, zp.smem, zp.mode, is_signed, zp.tpb); break;
     }
     CUDA_CHECK(cudaEventRecord(ctx->ev_mul1, ctx->stream));
     PK_LAUNCH(ctx, k_zone_scan, 1, 1024, 0, zone_count, zone_prefix, zp.n_zones, &ctx->d_ctr->n_out);
@@ -696,7 +757,7 @@ inline pk_dpoly *zone_multiply(pk_ctx *ctx, const Plan &pl, const pk_dpoly *A, c
     ctx->stats.table_slots = (u64)zp.cap;
     ctx->stats.acc_lanes = zp.NW;
     ctx->stats.chunk_bits = 0;
-    ctx->stats.retries = zp.mode; // 0 dense zones, 1 bitmap zones (reported through the spare counter)
+    ctx->stats.retries = zp.mode | (zp.tpb << 8); // bit 0: bitmap zones; bits 8..: threads per block (spare counter)
     DPolyGuard e{ctx, new_dpoly(ctx, n_out, nv, pl.out_limbs)};
     if (n_out) {
         const u32 ggrid = std::min<u32>(zp.n_zones, (u32)ctx->sm_count * 16);
