@@ -132,7 +132,7 @@ int pk_ctx_set_limits(pk_ctx *ctx, uint32_t n_vars, const int64_t *limits);
 int pk_ctx_get_limits(const pk_ctx *ctx, uint32_t n_vars, int64_t *limits_out, int64_t *h_min_out, int64_t *h_max_out);
 int pk_get_stats(pk_ctx *ctx, pk_stats *out);
 /* Kernel tuning knobs (the analogue of piranha::tuning, tuning.hpp:54-60).  Keys: "zone_target" (zones per product,
- * 0 = 16 per SM), "zone_chunk" (consecutive zones per work unit), "zone_span_log2" (max log2 codes per bitmap zone),
+ * 0 = 12 per SM), "zone_chunk" (consecutive zones per work unit), "zone_span_log2" (max log2 codes per bitmap zone),
  * "zone_cap" (force a small accumulator capacity; tests), "zone_mode" (0 auto, 1 dense, 2 bitmap), "zone_disable",
  * "zone_cursor_bytes" (memory allowed for row cursors, 0 = binary search per row per zone), "zone_tpb" (threads per
  * block: 0 auto, 256, 512, 1024).  Never changes results, only how they are computed. */

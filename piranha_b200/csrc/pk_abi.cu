@@ -390,8 +390,7 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
         f.cp = pl.cpR;
         f.base_code = pl.base_code;
         f.ctr = ctx->d_ctr;
-        size_t free_b = 0, total_b = 0;
-        CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+        const size_t total_b = ctx->total_mem; // allocation failures surface as PK_E_NOMEM from cudaMallocAsync
         MulCounters *hc = static_cast<MulCounters *>(ctx->h_scratch);
         if (algo == PK_ALGO_DENSE) {
             const unsigned __int128 bytes = (unsigned __int128)std::max<u64>(sub_range, 1) * pl.nl * 8;
@@ -433,7 +432,7 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
             u32 rec_words = 2;
             while (rec_words < pl.nl + 1) rec_words <<= 1;
             const unsigned __int128 bytes = (unsigned __int128)cap * rec_words * 8;
-            if (bytes > (unsigned __int128)free_b / 10 * 9) fail(PK_E_NOMEM, "hash table does not fit in device memory");
+            if (bytes > (unsigned __int128)total_b / 10 * 9) fail(PK_E_NOMEM, "hash table does not fit in device memory");
             if (cap > (1ull << 32)) fail(PK_E_NOMEM, "hash table too large");
             DevBuf tab(ctx, (size_t)bytes);
             PK_LAUNCH(ctx, k_hash_init, grid_for((u64)cap * rec_words, 256), 256, 0, tab.as<u64>(), (u64)cap * rec_words,
@@ -535,6 +534,7 @@ int pk_ctx_create(int device, void *stream, pk_ctx **out)
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
     c->smem_per_sm = prop.sharedMemPerMultiprocessor;
+    c->total_mem = prop.totalGlobalMem;
     if (stream) {
         c->stream = static_cast<cudaStream_t>(stream);
     } else {

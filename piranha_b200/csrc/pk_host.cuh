@@ -16,8 +16,8 @@
 namespace pk
 {
 struct ZoneTuning {
-    uint32_t target_zones = 0;    // 0 = 16 per SM
-    uint32_t zones_per_chunk = 4;
+    uint32_t target_zones = 0;    // 0 = 12 per SM
+    uint32_t zones_per_chunk = 2;
     uint32_t span_log2_max = 18;  // bitmap zones: at most 2^18 codes (32 KB bitmap + 32 KB prefix)
     uint32_t force_cap = 0;       // tests: force a small accumulator capacity to exercise multi-pass zones
     uint32_t force_mode = 0;      // 0 auto, 1 dense, 2 bitmap
@@ -56,6 +56,7 @@ struct pk_ctx {
     pk::ZoneTuning zone_tuning;
     size_t smem_optin = 0;
     size_t smem_per_sm = 0;
+    size_t total_mem = 0;
 };
 
 struct pk_dpoly {

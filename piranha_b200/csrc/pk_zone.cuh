@@ -576,7 +576,7 @@ inline ZonePlan zone_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB, u64 sub_r
     if (NW > 6) return zp;
     zp.NW = NW;
     zp.use_cursors = (nA * 4 <= (u64)t.cursor_bytes_max) ? 1 : 0;
-    const u32 target = t.target_zones ? t.target_zones : (u32)ctx->sm_count * 16;
+    const u32 target = t.target_zones ? t.target_zones : (u32)ctx->sm_count * 12;
     const double W = (double)nA * (double)nB;
     // cost of one candidate (mode, threads per block): a row visit costs about half a product, bitmap zones walk twice
     double best_cost = 1e300;
@@ -676,9 +676,8 @@ inline pk_dpoly *zone_multiply(pk_ctx *ctx, const Plan &pl, const pk_dpoly *A, c
     if (!zp.ok) return nullptr;
     const unsigned __int128 w_bound = (unsigned __int128)nA * nB;
     const u64 out_cap = (u64)std::min<unsigned __int128>(w_bound, hi - lo);
-    size_t free_b = 0, total_b = 0;
-    CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-    if ((unsigned __int128)out_cap * (9 + 8 * pl.out_limbs) > (unsigned __int128)total_b / 2) return nullptr;
+    // (cudaMemGetInfo is a multi-millisecond host call on this driver: the device size is cached at context creation)
+    if ((unsigned __int128)out_cap * (9 + 8 * pl.out_limbs) > (unsigned __int128)ctx->total_mem / 2) return nullptr;
 
     DevBuf pa(ctx, (nA + 1) * 16), pb(ctx, (nB + 1) * 16);
     PK_LAUNCH(ctx, k_pack_operand, grid_for(nA, 256), 256, 0, keyA, A->planes, pa.as<uint4>(), nA);

@@ -9,11 +9,10 @@ from bench import build_operands
 
 def main():
     wl = sys.argv[1:] or ["fateman1", "pearce1"]
-    combos = []
-    for tpb in (256, 512, 1024):
-        for chunk in (2, 4, 8):
-            for target in (1184, 2368, 4736):
-                combos.append(dict(zone_tpb=tpb, zone_chunk=chunk, zone_target=target))
+    grid = {"zone_tpb": (256, 512, 1024), "zone_chunk": (2, 4, 8), "zone_target": (1184, 2368, 4736)}
+    if os.environ.get("SWEEP_GRID"):  # e.g. "zone_tpb=1024;zone_chunk=1,2,3;zone_target=2368,3552"
+        grid = {k: tuple(int(x) for x in v.split(",")) for k, v in (kv.split("=") for kv in os.environ["SWEEP_GRID"].split(";"))}
+    combos = [dict(zip(grid, vals)) for vals in itertools.product(*grid.values())]
     extra = os.environ.get("SWEEP_EXTRA")
     for w in wl:
         a, b, nv, L = build_operands(w)
