@@ -65,6 +65,7 @@ struct ZoneArgs {
     u64 out_cap;
     ZoneCodec cd;
     u32 *chunk_counter;
+    const u32 *chunk_order; // heaviest-first schedule (nullptr = natural order)
     u32 *zone_count; // result terms of zone z
     u64 *zone_off;   // where zone z starts in the staging arrays
     u64 *bump;       // staging allocation cursor
@@ -223,9 +224,10 @@ __global__ void __launch_bounds__(TPB, 1024 / TPB) k_zone(const ZoneArgs a)
     for (;;) {
         if (tid == 0) s_b32[0] = atomicAdd(a.chunk_counter, 1u);
         __syncthreads();
-        const u32 chunk = s_b32[0];
+        const u32 claimed = s_b32[0];
         __syncthreads();
-        if (chunk >= a.n_chunks) break;
+        if (claimed >= a.n_chunks) break;
+        const u32 chunk = a.chunk_order ? __ldg(&a.chunk_order[claimed]) : claimed;
         const u32 z0 = chunk * a.zones_per_chunk, z1 = min(a.n_zones, z0 + a.zones_per_chunk);
         if (a.use_cursors) { // one binary search per row per chunk
             const u32 clo = a.lo + z0 * a.span;
@@ -441,6 +443,50 @@ __global__ void __launch_bounds__(TPB, 1024 / TPB) k_zone(const ZoneArgs a)
     }
 }
 
+// Work estimate per chunk of zones: a stratified sample of pair sums (every (nA/SA)-th row against every
+// (nB/SB)-th column) is histogrammed by chunk.  Zone work is bell-shaped over the code range (multinomial
+// coefficients), so blocks claim chunks heaviest-first: the role of piranha's task sorting + zone claiming
+// (polynomial.hpp:1863, :1921-1947), with longest-processing-time-first instead of first-bucket order.
+__global__ void k_zone_work(const uint4 *__restrict__ A, u32 nA, const uint4 *__restrict__ B, u32 nB, u32 SA, u32 SB, u32 lo,
+                            u32 hi, u32 span, u32 zones_per_chunk, u32 *__restrict__ work)
+{
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= SA * SB) return;
+    const u32 ia = (u32)((u64)(t / SB) * nA / SA), jb = (u32)((u64)(t % SB) * nB / SB);
+    const u32 code = __ldg(&A[ia].x) + __ldg(&B[jb].x);
+    if (code >= lo && code < hi) atomicAdd(&work[(code - lo) / span / zones_per_chunk], 1u);
+}
+
+constexpr u32 kMaxOrderedChunks = 4096;
+
+// Sort chunk ids by descending sampled work (bitonic sort of packed (work, ~id) keys in shared memory).
+__global__ void __launch_bounds__(1024) k_zone_order(const u32 *__restrict__ work, u32 n_chunks, u32 *__restrict__ order)
+{
+    __shared__ u64 keys[kMaxOrderedChunks];
+    u32 n2 = 1;
+    while (n2 < n_chunks) n2 <<= 1;
+    for (u32 i = threadIdx.x; i < n2; i += blockDim.x)
+        keys[i] = i < n_chunks ? (((u64)work[i] << 32) | (u64)(0xFFFFFFFFu - i)) : 0ull;
+    __syncthreads();
+    for (u32 k = 2; k <= n2; k <<= 1) {
+        for (u32 j = k >> 1; j > 0; j >>= 1) {
+            for (u32 i = threadIdx.x; i < n2; i += blockDim.x) {
+                const u32 l = i ^ j;
+                if (l > i) {
+                    const u64 x = keys[i], y = keys[l];
+                    const bool desc = (i & k) == 0; // descending overall
+                    if (desc ? (x < y) : (x > y)) {
+                        keys[i] = y;
+                        keys[l] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (u32 i = threadIdx.x; i < n_chunks; i += blockDim.x) order[i] = 0xFFFFFFFFu - (u32)(keys[i] & 0xFFFFFFFFull);
+}
+
 // Lay the zones out in zone order (= ascending code order): one block per zone copies its staged terms to
 // prefix[z] in the final arrays.
 __global__ void __launch_bounds__(256) k_zone_gather(const u32 *__restrict__ zone_count, const u64 *__restrict__ zone_off,
@@ -549,6 +595,7 @@ inline void zone_configure(pk_ctx *ctx)
     t.force_mode = env_u32("PK_ZONE_MODE", t.force_mode);
     t.disable = env_u32("PK_ZONE_DISABLE", t.disable);
     t.tpb = env_u32("PK_ZONE_TPB", t.tpb);
+    t.no_lpt = env_u32("PK_ZONE_NO_LPT", t.no_lpt);
     const size_t dyn = ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0;
     zone_set_smem_nw<2>(dyn);
     zone_set_smem_nw<3>(dyn);
@@ -684,13 +731,22 @@ inline pk_dpoly *zone_multiply(pk_ctx *ctx, const Plan &pl, const pk_dpoly *A, c
     PK_LAUNCH(ctx, k_pack_operand, grid_for(nB, 256), 256, 0, keyB, magB, pb.as<uint4>(), nB);
     // per-zone bookkeeping: offsets (u64), prefix (u64), counts (u32), then the bump cursor and the chunk counter
     const size_t nz = zp.n_zones;
-    DevBuf book(ctx, nz * 20 + 64);
+    const bool ordered = zp.n_chunks > 1 && zp.n_chunks <= kMaxOrderedChunks && !ctx->zone_tuning.no_lpt;
+    DevBuf book(ctx, nz * 20 + 64 + (ordered ? (size_t)zp.n_chunks * 8 : 0));
     u64 *zone_off = book.as<u64>();
     u64 *zone_prefix = zone_off + nz;
     u64 *bump = zone_prefix + nz;
     u32 *chunk_counter = reinterpret_cast<u32 *>(bump + 1);
     u32 *zone_count = chunk_counter + 2;
+    u32 *chunk_work = zone_count + nz, *chunk_order = chunk_work + zp.n_chunks;
     CUDA_CHECK(cudaMemsetAsync(bump, 0, 16, ctx->stream));
+    if (ordered) {
+        CUDA_CHECK(cudaMemsetAsync(chunk_work, 0, (size_t)zp.n_chunks * 4, ctx->stream));
+        const u32 SA = (u32)std::min<u64>(nA, 512), SB = (u32)std::min<u64>(nB, 512);
+        PK_LAUNCH(ctx, k_zone_work, grid_for((u64)SA * SB, 256), 256, 0, pa.as<uint4>(), (u32)nA, pb.as<uint4>(), (u32)nB, SA,
+                  SB, (u32)lo, (u32)hi, zp.span, zp.zones_per_chunk, chunk_work);
+        PK_LAUNCH(ctx, k_zone_order, 1, 1024, 0, chunk_work, zp.n_chunks, chunk_order);
+    }
 
     const u32 cursor_stride = (u32)((nA + 31) & ~31ull);
     DevBuf cursors(ctx, zp.use_cursors ? (size_t)zp.grid * cursor_stride * 4 : 0);
@@ -732,6 +788,7 @@ inline pk_dpoly *zone_multiply(pk_ctx *ctx, const Plan &pl, const pk_dpoly *A, c
         za.cd.spstride[v] = (i64)((u64)pl.cpR.step[v] * (u64)pl.cpR.pstride[v]);
     }
     za.chunk_counter = chunk_counter;
+    za.chunk_order = ordered ? chunk_order : nullptr;
     za.zone_count = zone_count;
     za.zone_off = zone_off;
     za.bump = bump;
