@@ -135,7 +135,7 @@ int pk_get_stats(pk_ctx *ctx, pk_stats *out);
  * 0 = 12 per SM), "zone_chunk" (consecutive zones per work unit), "zone_span_log2" (max log2 codes per bitmap zone),
  * "zone_cap" (force a small accumulator capacity; tests), "zone_mode" (0 auto, 1 dense, 2 bitmap), "zone_disable",
  * "zone_cursor_bytes" (memory allowed for row cursors, 0 = binary search per row per zone), "zone_tpb" (threads per
- * block: 0 auto, 256, 512, 1024).  Never changes results, only how they are computed. */
+ * block: 0 auto, 256, 512, 1024), "zone_uniform" (1 = equal-span zones instead of equal-work zones).  Never changes results, only how they are computed. */
 int pk_ctx_set_tuning(pk_ctx *ctx, const char *key, uint64_t value);
 
 /* ---- host-to-host product: the call behind series_multiplier::operator()() --------------------------------- */

@@ -636,7 +636,7 @@ int pk_ctx_set_tuning(pk_ctx *ctx, const char *key, uint64_t value)
     else if (k == "zone_mode") t.force_mode = (u32)value;
     else if (k == "zone_disable") t.disable = (u32)value;
     else if (k == "zone_cursor_bytes") t.cursor_bytes_max = (u32)value;
-    else if (k == "zone_no_lpt") t.no_lpt = (u32)value;
+    else if (k == "zone_uniform") t.uniform = (u32)value;
     else if (k == "zone_tpb") t.tpb = (value == 256 || value == 512 || value == 1024) ? (u32)value : 0;
     else return PK_E_ARGS;
     return PK_OK;

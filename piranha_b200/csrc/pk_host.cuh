@@ -25,7 +25,7 @@ struct ZoneTuning {
     uint32_t cursor_bytes_max = 64u << 20; // row cursors live in global memory; 0 disables them
     uint32_t disable = 0;
     uint32_t tpb = 0;              // threads per block: 0 auto, 256 / 512 / 1024
-    uint32_t no_lpt = 0;           // 1 = claim chunks in code order instead of heaviest-first
+    uint32_t uniform = 0;          // 1 = equal-span zones instead of equal-work (quantile) zones
 };
 
 } // namespace pk

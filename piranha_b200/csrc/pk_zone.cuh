@@ -48,8 +48,9 @@ struct ZoneArgs {
     const uint4 *B;
     u32 nB;
     u32 lo, hi; // output partition of this call (tight codes, < 2^32)
-    u32 span;   // codes per zone
-    u32 n_zones, zones_per_chunk, n_chunks;
+    const u32 *cuts;        // zone z covers codes [cuts[z], cuts[z+1]): equal-work cuts built on the device
+    const u32 *n_zones_dev; // number of zones (device-side value, decided by k_zone_cuts)
+    u32 zones_per_chunk;
     u32 cap; // accumulator entries per zone pass
     u32 use_cursors;
     u32 pw; // 32-bit words of a product magnitude
@@ -65,7 +66,7 @@ struct ZoneArgs {
     u64 out_cap;
     ZoneCodec cd;
     u32 *chunk_counter;
-    const u32 *chunk_order; // heaviest-first schedule (nullptr = natural order)
+    u64 *trace;             // optional: per chunk {start ns, end ns, smid, products} (PK_ZONE_TRACE)
     u32 *zone_count; // result terms of zone z
     u64 *zone_off;   // where zone z starts in the staging arrays
     u64 *bump;       // staging allocation cursor
@@ -214,6 +215,8 @@ __global__ void __launch_bounds__(TPB, 1024 / TPB) k_zone(const ZoneArgs a)
     const u32 wstride = a.cap * 4u;
     u64 my_pairs = 0;
     u32 my_maxbits = 0, my_flags = 0;
+    const u32 n_zones = __ldg(a.n_zones_dev);
+    const u32 n_chunks = (n_zones + a.zones_per_chunk - 1) / a.zones_per_chunk;
 
     // accumulators (and bitmap) start cleared; every pass leaves them cleared again
     for (u32 i = tid; i < a.cap * NW; i += kZoneThreads) acc[i] = 0;
@@ -226,11 +229,14 @@ __global__ void __launch_bounds__(TPB, 1024 / TPB) k_zone(const ZoneArgs a)
         __syncthreads();
         const u32 claimed = s_b32[0];
         __syncthreads();
-        if (claimed >= a.n_chunks) break;
-        const u32 chunk = a.chunk_order ? __ldg(&a.chunk_order[claimed]) : claimed;
-        const u32 z0 = chunk * a.zones_per_chunk, z1 = min(a.n_zones, z0 + a.zones_per_chunk);
+        if (claimed >= n_chunks) break;
+        const u32 chunk = claimed;
+        u64 t_start = 0;
+        if (a.trace && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
+        const u64 pairs_before = my_pairs;
+        const u32 z0 = chunk * a.zones_per_chunk, z1 = min(n_zones, z0 + a.zones_per_chunk);
         if (a.use_cursors) { // one binary search per row per chunk
-            const u32 clo = a.lo + z0 * a.span;
+            const u32 clo = __ldg(&a.cuts[z0]);
             for (u32 i = tid; i < nA; i += kZoneThreads) {
                 const u32 ka = __ldg(&a.A[i].x);
                 cursor[i] = (ka >= clo) ? 0u : zone_lower_bound(a.B, nB, clo - ka);
@@ -238,8 +244,8 @@ __global__ void __launch_bounds__(TPB, 1024 / TPB) k_zone(const ZoneArgs a)
             __syncthreads();
         }
         for (u32 z = z0; z < z1; ++z) {
-            const u32 zlo = a.lo + z * a.span;
-            const u32 zhi = (a.hi - zlo > a.span) ? zlo + a.span : a.hi;
+            const u32 zlo = __ldg(&a.cuts[z]), zhi = __ldg(&a.cuts[z + 1]);
+            const u32 zwords = (MODE == 1) ? min(a.bm_words, ((zhi - zlo + 127u) >> 7) << 2) : 0u; // bitmap words in use
             // rows that can reach the zone: a_i + b_max >= zlo and a_i + b_0 < zhi
             const u32 i_beg = (zlo > kbmax) ? zone_lower_bound(a.A, nA, zlo - kbmax) : 0u;
             const u32 i_end = (zhi > kb0) ? zone_lower_bound(a.A, nA, zhi - kb0) : 0u;
@@ -270,7 +276,7 @@ __global__ void __launch_bounds__(TPB, 1024 / TPB) k_zone(const ZoneArgs a)
                 __syncthreads();
                 // exclusive popcount prefix per group of 4 bitmap words (128 codes):
                 // rank(code) = pre[group] + popc(words of the group below) + popc(bits below in its word)
-                const u32 n_groups = a.bm_words >> 2;
+                const u32 n_groups = zwords >> 2;
                 const u32 gpt = (n_groups + kZoneThreads - 1) / kZoneThreads;
                 const u32 g0 = min(n_groups, tid * gpt), g1 = min(n_groups, g0 + gpt);
                 u32 local = 0;
@@ -300,7 +306,7 @@ __global__ void __launch_bounds__(TPB, 1024 / TPB) k_zone(const ZoneArgs a)
                 const u32 r1 = min(n_entries, r0 + a.cap);
                 u32 c1 = zhi;
                 if (MODE == 1) {
-                    const u32 n_groups = a.bm_words >> 2;
+                    const u32 n_groups = zwords >> 2;
                     if (r1 < n_entries) { // the code of rank r1 bounds this pass (zone with more entries than cap)
                         if (tid == 0) {
                             u32 lo_g = 0, hi_g = n_groups; // last group with pre[g] <= r1
@@ -425,9 +431,21 @@ __global__ void __launch_bounds__(TPB, 1024 / TPB) k_zone(const ZoneArgs a)
                 a.zone_off[z] = zone_base;
             }
             if (MODE == 1) { // clear the bitmap for the next zone
-                for (u32 i = tid; i < a.bm_words; i += kZoneThreads) bm[i] = 0;
+                for (u32 i = tid; i < zwords; i += kZoneThreads) bm[i] = 0;
             }
             __syncthreads();
+        }
+        if (a.trace) {
+            if (tid == 0) {
+                u64 t_end;
+                u32 smid;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
+                asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+                a.trace[4 * (size_t)chunk + 0] = t_start;
+                a.trace[4 * (size_t)chunk + 1] = t_end;
+                a.trace[4 * (size_t)chunk + 2] = ((u64)claimed << 32) | smid;
+            }
+            if (tid == 32) a.trace[4 * (size_t)chunk + 3] = my_pairs - pairs_before; // one thread's share: relative weight
         }
     }
     // per-thread statistics
@@ -443,59 +461,83 @@ __global__ void __launch_bounds__(TPB, 1024 / TPB) k_zone(const ZoneArgs a)
     }
 }
 
-// Work estimate per chunk of zones: a stratified sample of pair sums (every (nA/SA)-th row against every
-// (nB/SB)-th column) is histogrammed by chunk.  Zone work is bell-shaped over the code range (multinomial
-// coefficients), so blocks claim chunks heaviest-first: the role of piranha's task sorting + zone claiming
-// (polynomial.hpp:1863, :1921-1947), with longest-processing-time-first instead of first-bucket order.
-__global__ void k_zone_work(const uint4 *__restrict__ A, u32 nA, const uint4 *__restrict__ B, u32 nB, u32 SA, u32 SB, u32 lo,
-                            u32 hi, u32 span, u32 zones_per_chunk, u32 *__restrict__ work)
+// Zone work is very uneven over the code range (multinomial coefficients pile up products in the middle: measured
+// max/median chunk time 13x with equal-span zones, profiles/), so zones are cut at WORK quantiles: a hashed sample
+// of pair sums is radix-sorted and every (S/Z)-th sample becomes a zone boundary; intervals wider than what the
+// accumulator holds are split evenly.  This is the role of piranha's zone table (polynomial.hpp:1788-1867), with
+// zones equalised by pair count instead of bucket count.
+__global__ void k_zone_sample(const uint4 *__restrict__ A, u32 nA, const uint4 *__restrict__ B, u32 nB, u32 S, u32 lo, u32 hi,
+                              u32 *__restrict__ out)
 {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= SA * SB) return;
-    const u32 ia = (u32)((u64)(t / SB) * nA / SA), jb = (u32)((u64)(t % SB) * nB / SB);
+    if (t >= S) return;
+    const u64 h = mix64(0x9E3779B97F4A7C15ull * (t + 1));
+    const u32 ia = (u32)((h & 0xFFFFFFFFull) * nA >> 32), jb = (u32)((h >> 32) * nB >> 32);
     const u32 code = __ldg(&A[ia].x) + __ldg(&B[jb].x);
-    if (code >= lo && code < hi) atomicAdd(&work[(code - lo) / span / zones_per_chunk], 1u);
+    out[t] = (code >= lo && code < hi) ? code : 0xFFFFFFFFu;
 }
 
-constexpr u32 kMaxOrderedChunks = 4096;
-
-// Sort chunk ids by descending sampled work (bitonic sort of packed (work, ~id) keys in shared memory).
-__global__ void __launch_bounds__(1024) k_zone_order(const u32 *__restrict__ work, u32 n_chunks, u32 *__restrict__ order)
+// One block: boundaries b_k (k = 0..Z) = lo, the work quantiles, hi; interval k is split into ceil(len / max_span)
+// zones.  Writes cuts[0..n] and n.  `uniform` != 0 replaces the quantiles by equal spans (tests, comparison).
+__global__ void __launch_bounds__(1024) k_zone_cuts(const u32 *__restrict__ sorted, u32 S, u32 lo, u32 hi, u32 Z, u32 max_span,
+                                                    u32 uniform, u32 max_zones, u32 *__restrict__ cuts, u32 *__restrict__ n_zones)
 {
-    __shared__ u64 keys[kMaxOrderedChunks];
-    u32 n2 = 1;
-    while (n2 < n_chunks) n2 <<= 1;
-    for (u32 i = threadIdx.x; i < n2; i += blockDim.x)
-        keys[i] = i < n_chunks ? (((u64)work[i] << 32) | (u64)(0xFFFFFFFFu - i)) : 0ull;
-    __syncthreads();
-    for (u32 k = 2; k <= n2; k <<= 1) {
-        for (u32 j = k >> 1; j > 0; j >>= 1) {
-            for (u32 i = threadIdx.x; i < n2; i += blockDim.x) {
-                const u32 l = i ^ j;
-                if (l > i) {
-                    const u64 x = keys[i], y = keys[l];
-                    const bool desc = (i & k) == 0; // descending overall
-                    if (desc ? (x < y) : (x > y)) {
-                        keys[i] = y;
-                        keys[l] = x;
-                    }
-                }
-            }
-            __syncthreads();
+    __shared__ u32 s_ws[40];
+    __shared__ u32 s_valid;
+    if (threadIdx.x == 0) { // number of in-range samples (the rest sorted to the end as 0xFFFFFFFF)
+        u32 l = 0, h = S;
+        while (l < h) {
+            const u32 m = (l + h) >> 1;
+            if (sorted[m] < 0xFFFFFFFFu) l = m + 1;
+            else h = m;
         }
+        s_valid = l;
     }
-    for (u32 i = threadIdx.x; i < n_chunks; i += blockDim.x) order[i] = 0xFFFFFFFFu - (u32)(keys[i] & 0xFFFFFFFFull);
+    __syncthreads();
+    const u32 V = s_valid;
+    const u32 ustep = (u32)(((u64)(hi - lo) + Z - 1) / Z);
+    auto boundary = [&](u32 k) -> u32 {
+        if (k == 0) return lo;
+        if (k >= Z) return hi;
+        if (uniform || V == 0) return (u32)min((u64)hi, (u64)lo + (u64)k * ustep);
+        return min(hi, max(lo, sorted[(u32)((u64)k * V / Z)]));
+    };
+    u32 run = 0;
+    for (u32 base = 0; base < Z; base += 1024) {
+        const u32 k = base + threadIdx.x;
+        u32 b0 = 0, len = 0, pieces = 0;
+        if (k < Z) {
+            b0 = boundary(k);
+            const u32 b1 = boundary(k + 1);
+            len = b1 > b0 ? b1 - b0 : 0;
+            pieces = len ? (len + max_span - 1) / max_span : 0;
+        }
+        u32 total;
+        const u32 excl = block_excl_scan(pieces, s_ws, total);
+        if (pieces) {
+            const u32 step = (len + pieces - 1) / pieces;
+            for (u32 q = 0; q < pieces; ++q)
+                if (run + excl + q < max_zones) cuts[run + excl + q] = b0 + q * step;
+        }
+        run += total;
+    }
+    if (threadIdx.x == 0) {
+        const u32 n = min(run, max_zones);
+        cuts[n] = hi;
+        *n_zones = n;
+    }
 }
 
 // Lay the zones out in zone order (= ascending code order): one block per zone copies its staged terms to
 // prefix[z] in the final arrays.
 __global__ void __launch_bounds__(256) k_zone_gather(const u32 *__restrict__ zone_count, const u64 *__restrict__ zone_off,
-                                                     const u64 *__restrict__ zone_prefix, u32 n_zones,
+                                                     const u64 *__restrict__ zone_prefix, const u32 *__restrict__ n_zones_dev,
                                                      const i64 *__restrict__ skey, const u64 *__restrict__ splanes,
                                                      u64 sstride, const signed char *__restrict__ ssign,
                                                      i64 *__restrict__ okey, u64 *__restrict__ oplanes, u64 ostride,
                                                      signed char *__restrict__ osign, u32 limbs)
 {
+    const u32 n_zones = __ldg(n_zones_dev);
     for (u32 z = blockIdx.x; z < n_zones; z += gridDim.x) {
         const u32 n = zone_count[z];
         const u64 src = zone_off[z], dst = zone_prefix[z];
@@ -508,9 +550,10 @@ __global__ void __launch_bounds__(256) k_zone_gather(const u32 *__restrict__ zon
 }
 
 // exclusive scan of 32-bit counts into 64-bit offsets (single block); total -> *total_out
-__global__ void __launch_bounds__(1024) k_zone_scan(const u32 *__restrict__ counts, u64 *__restrict__ offsets, u32 n,
-                                                    u64 *total_out)
+__global__ void __launch_bounds__(1024) k_zone_scan(const u32 *__restrict__ counts, u64 *__restrict__ offsets,
+                                                    const u32 *__restrict__ n_dev, u64 *total_out)
 {
+    const u32 n = __ldg(n_dev);
     __shared__ u32 s_ws[40];
     __shared__ u64 s_run;
     if (threadIdx.x == 0) s_run = 0;
@@ -595,7 +638,7 @@ inline void zone_configure(pk_ctx *ctx)
     t.force_mode = env_u32("PK_ZONE_MODE", t.force_mode);
     t.disable = env_u32("PK_ZONE_DISABLE", t.disable);
     t.tpb = env_u32("PK_ZONE_TPB", t.tpb);
-    t.no_lpt = env_u32("PK_ZONE_NO_LPT", t.no_lpt);
+    t.uniform = env_u32("PK_ZONE_UNIFORM", t.uniform);
     const size_t dyn = ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0;
     zone_set_smem_nw<2>(dyn);
     zone_set_smem_nw<3>(dyn);
@@ -606,25 +649,35 @@ inline void zone_configure(pk_ctx *ctx)
 
 struct ZonePlan {
     bool ok = false;
-    u32 NW = 0, mode = 0, cap = 0, use_cursors = 0, bm_words = 0, n_zones = 0, zones_per_chunk = 1, n_chunks = 0;
-    u32 span = 0, tpb = 1024, grid = 0;
+    u32 NW = 0, mode = 0, cap = 0, use_cursors = 0, bm_words = 0, zones_per_chunk = 1;
+    u32 max_span = 0;   // widest zone (dense: = cap; bitmap: codes covered by the bitmap)
+    u32 target = 0;     // number of work quantiles
+    u32 max_zones = 0;  // upper bound on the zone count (device decides the exact number)
+    u32 tpb = 1024, grid = 0;
     u32 off_acc = 0, off_bm = 0, off_pre = 0, off_list = 0;
     size_t smem = 0;
 };
+
+inline u64 pow2_ceil(u64 x)
+{
+    u64 p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
 
 inline ZonePlan zone_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB, u64 sub_range)
 {
     const ZoneTuning &t = ctx->zone_tuning;
     ZonePlan zp;
     if (t.disable || pl.LA != 1 || pl.LB != 1 || sub_range == 0) return zp;
-    if (pl.range > 0xFFFFFFFFull) return zp; // the kernel works on 32-bit tight codes
+    if (pl.range > 0xFFFFFFFEull) return zp; // the kernel works on 32-bit tight codes
     u32 NW = (pl.prod_bits + pl.cnt_bits + 1 + 31) / 32;
     NW = std::max<u32>(NW, 2);
     if (NW > 6) return zp;
-    zp.NW = NW;
-    zp.use_cursors = (nA * 4 <= (u64)t.cursor_bytes_max) ? 1 : 0;
-    const u32 target = t.target_zones ? t.target_zones : (u32)ctx->sm_count * 12;
+    const u32 use_cursors = (nA * 4 <= (u64)t.cursor_bytes_max) ? 1 : 0;
+    const u32 target = std::max<u32>(1, t.target_zones ? t.target_zones : (u32)ctx->sm_count * 12);
     const double W = (double)nA * (double)nB;
+    const u64 avg_span = (sub_range + target - 1) / target;
     // cost of one candidate (mode, threads per block): a row visit costs about half a product, bitmap zones walk twice
     double best_cost = 1e300;
     for (u32 tpb : {1024u, 512u, 256u}) {
@@ -639,38 +692,39 @@ inline ZonePlan zone_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB, u64 sub_r
             if (t.force_mode == 2 && mode != 1) continue;
             ZonePlan c;
             c.NW = NW;
-            c.use_cursors = zp.use_cursors;
+            c.use_cursors = use_cursors;
             c.mode = mode;
             c.tpb = tpb;
+            c.target = target;
             size_t off = 0;
             double cost;
             if (mode == 0) {
+                // light regions may use zones up to 4x the average span, bounded by what shared memory holds
                 const u64 cap_max = (budget / (NW * 4)) & ~31ull;
                 if (cap_max < 32) continue;
-                u64 span = std::max<u64>(64, (sub_range + target - 1) / target);
-                span = (span + 31) & ~31ull;
-                span = std::min(span, cap_max);
-                if (t.force_cap) span = std::max<u64>(32, std::min<u64>(span, t.force_cap & ~31u));
-                const u64 nz = (sub_range + span - 1) / span;
-                if (nz > t.max_zones) continue;
-                c.span = (u32)span;
-                c.cap = (u32)span;
-                c.n_zones = (u32)nz;
+                u64 cap = std::max<u64>(64, (4 * avg_span + 31) & ~31ull);
+                cap = std::min(cap, cap_max);
+                if (t.force_cap) cap = std::max<u64>(32, std::min<u64>(cap, t.force_cap & ~31u));
+                const u64 nz_max = (u64)target + (sub_range + cap - 1) / cap + 2;
+                if (nz_max > t.max_zones) continue;
+                c.max_span = (u32)cap;
+                c.cap = (u32)cap;
+                c.max_zones = (u32)nz_max;
                 c.off_acc = 0;
                 off = (size_t)c.cap * NW * 4;
-                cost = (double)nz * (double)nA * 0.5 + W;
+                const double nz_est = std::max<double>((double)target, (double)sub_range / (double)cap);
+                cost = nz_est * (double)nA * 0.5 + W;
             } else {
-                u64 span = 1ull << t.span_log2_max;
-                while (span > 1024 && (sub_range + span - 1) / span < target) span >>= 1;
+                u64 span = std::min<u64>(1ull << t.span_log2_max, std::max<u64>(1024, pow2_ceil(4 * avg_span)));
                 // bitmap (span / 8 bytes) + prefix per 128 codes (span / 32 bytes) must leave room for entries
                 while (span > 1024 && span / 8 + span / 32 + (size_t)(NW + 1) * 4 * 512 > budget) span >>= 1;
                 const size_t bm_bytes = span / 8, pre_bytes = span / 32;
                 if (bm_bytes + pre_bytes + (size_t)(NW + 1) * 4 * 64 > budget) continue;
-                const u64 nz = (sub_range + span - 1) / span;
-                if (nz > t.max_zones) continue;
-                c.span = (u32)span;
+                const u64 nz_max = (u64)target + (sub_range + span - 1) / span + 2;
+                if (nz_max > t.max_zones) continue;
+                c.max_span = (u32)span;
                 c.bm_words = (u32)(span / 32);
-                c.n_zones = (u32)nz;
+                c.max_zones = (u32)nz_max;
                 c.off_bm = 0;
                 off = bm_bytes;
                 c.off_pre = (u32)off;
@@ -683,12 +737,12 @@ inline ZonePlan zone_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB, u64 sub_r
                 off += ((size_t)c.cap * 4 + 15) & ~15ull;
                 c.off_acc = (u32)off;
                 off += (size_t)c.cap * NW * 4;
-                // expected passes per zone when zones are denser than the capacity
+                const double nz_est = std::max<double>((double)target, (double)sub_range / (double)span);
                 const double dens = std::min(1.0, W / (double)sub_range);
-                const double passes = std::max(1.0, dens * (double)span / (double)cap);
-                cost = (double)nz * (double)nA * (0.5 + 0.5 * passes) + W * 1.6;
+                const double passes = std::max(1.0, dens * (double)sub_range / nz_est / (double)cap);
+                cost = nz_est * (double)nA * (0.5 + 0.5 * passes) + W * 1.6;
             }
-            cost *= (tpb == 1024 ? 1.15 : (tpb == 512 ? 1.0 : 1.02)); // measured preference (profiles/)
+            cost *= (tpb == 1024 ? 1.0 : (tpb == 512 ? 1.15 : 1.4)); // measured preference (profiles/sweeps)
             c.smem = off;
             if (cost < best_cost) {
                 best_cost = cost;
@@ -699,8 +753,7 @@ inline ZonePlan zone_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB, u64 sub_r
     }
     if (!zp.ok) return zp;
     zp.zones_per_chunk = zp.use_cursors ? t.zones_per_chunk : 1;
-    zp.n_chunks = (zp.n_zones + zp.zones_per_chunk - 1) / zp.zones_per_chunk;
-    zp.grid = std::min<u32>((u32)ctx->sm_count * (1024 / zp.tpb), zp.n_chunks);
+    zp.grid = (u32)ctx->sm_count * (1024 / zp.tpb);
     return zp;
 }
 
@@ -729,23 +782,30 @@ inline pk_dpoly *zone_multiply(pk_ctx *ctx, const Plan &pl, const pk_dpoly *A, c
     DevBuf pa(ctx, (nA + 1) * 16), pb(ctx, (nB + 1) * 16);
     PK_LAUNCH(ctx, k_pack_operand, grid_for(nA, 256), 256, 0, keyA, A->planes, pa.as<uint4>(), nA);
     PK_LAUNCH(ctx, k_pack_operand, grid_for(nB, 256), 256, 0, keyB, magB, pb.as<uint4>(), nB);
-    // per-zone bookkeeping: offsets (u64), prefix (u64), counts (u32), then the bump cursor and the chunk counter
-    const size_t nz = zp.n_zones;
-    const bool ordered = zp.n_chunks > 1 && zp.n_chunks <= kMaxOrderedChunks && !ctx->zone_tuning.no_lpt;
-    DevBuf book(ctx, nz * 20 + 64 + (ordered ? (size_t)zp.n_chunks * 8 : 0));
+
+    // ---- zone cuts at work quantiles (sample -> sort -> cut builder), all on the device
+    const u32 S = (u32)std::min<unsigned __int128>(w_bound, 1u << 18);
+    const size_t nz = zp.max_zones;
+    // bookkeeping: offsets (u64), prefix (u64) per zone; bump cursor; chunk counter; zone count; counts + cuts (u32)
+    DevBuf book(ctx, nz * 24 + 128);
     u64 *zone_off = book.as<u64>();
     u64 *zone_prefix = zone_off + nz;
     u64 *bump = zone_prefix + nz;
     u32 *chunk_counter = reinterpret_cast<u32 *>(bump + 1);
+    u32 *n_zones_dev = chunk_counter + 1;
     u32 *zone_count = chunk_counter + 2;
-    u32 *chunk_work = zone_count + nz, *chunk_order = chunk_work + zp.n_chunks;
+    u32 *cuts = zone_count + nz; // nz + 1 entries
     CUDA_CHECK(cudaMemsetAsync(bump, 0, 16, ctx->stream));
-    if (ordered) {
-        CUDA_CHECK(cudaMemsetAsync(chunk_work, 0, (size_t)zp.n_chunks * 4, ctx->stream));
-        const u32 SA = (u32)std::min<u64>(nA, 512), SB = (u32)std::min<u64>(nB, 512);
-        PK_LAUNCH(ctx, k_zone_work, grid_for((u64)SA * SB, 256), 256, 0, pa.as<uint4>(), (u32)nA, pb.as<uint4>(), (u32)nB, SA,
-                  SB, (u32)lo, (u32)hi, zp.span, zp.zones_per_chunk, chunk_work);
-        PK_LAUNCH(ctx, k_zone_order, 1, 1024, 0, chunk_work, zp.n_chunks, chunk_order);
+    {
+        DevBuf samp(ctx, (size_t)S * 4), sorted(ctx, (size_t)S * 4);
+        PK_LAUNCH(ctx, k_zone_sample, grid_for(S, 256), 256, 0, pa.as<uint4>(), (u32)nA, pb.as<uint4>(), (u32)nB, S, (u32)lo,
+                  (u32)hi, samp.as<u32>());
+        size_t tmp_bytes = 0;
+        CUDA_CHECK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, samp.as<u32>(), sorted.as<u32>(), (int)S, 0, 32, ctx->stream));
+        DevBuf tmp(ctx, tmp_bytes);
+        CUDA_CHECK(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, samp.as<u32>(), sorted.as<u32>(), (int)S, 0, 32, ctx->stream));
+        PK_LAUNCH(ctx, k_zone_cuts, 1, 1024, 0, sorted.as<u32>(), S, (u32)lo, (u32)hi, zp.target, zp.max_span,
+                  ctx->zone_tuning.uniform, zp.max_zones, cuts, n_zones_dev);
     }
 
     const u32 cursor_stride = (u32)((nA + 31) & ~31ull);
@@ -759,10 +819,9 @@ inline pk_dpoly *zone_multiply(pk_ctx *ctx, const Plan &pl, const pk_dpoly *A, c
     za.nB = (u32)nB;
     za.lo = (u32)lo;
     za.hi = (u32)hi;
-    za.span = zp.span;
-    za.n_zones = zp.n_zones;
+    za.cuts = cuts;
+    za.n_zones_dev = n_zones_dev;
     za.zones_per_chunk = zp.zones_per_chunk;
-    za.n_chunks = zp.n_chunks;
     za.cap = zp.cap;
     za.use_cursors = zp.use_cursors;
     za.pw = std::min<u32>(4, (pl.prod_bits + 31) / 32);
@@ -788,11 +847,15 @@ inline pk_dpoly *zone_multiply(pk_ctx *ctx, const Plan &pl, const pk_dpoly *A, c
         za.cd.spstride[v] = (i64)((u64)pl.cpR.step[v] * (u64)pl.cpR.pstride[v]);
     }
     za.chunk_counter = chunk_counter;
-    za.chunk_order = ordered ? chunk_order : nullptr;
     za.zone_count = zone_count;
     za.zone_off = zone_off;
     za.bump = bump;
     za.ctr = ctx->d_ctr;
+    const char *trace_path = getenv("PK_ZONE_TRACE");
+    const size_t max_chunks = (nz + zp.zones_per_chunk - 1) / zp.zones_per_chunk;
+    DevBuf trace(ctx, trace_path ? max_chunks * 32 : 0);
+    if (trace_path) CUDA_CHECK(cudaMemsetAsync(trace.p, 0, max_chunks * 32, ctx->stream));
+    za.trace = trace.as<u64>();
     const bool is_signed = A->any_neg || B->any_neg;
     const u32 grid = zp.grid;
     CUDA_CHECK(cudaEventRecord(ctx->ev_mul0, ctx->stream));
@@ -804,10 +867,18 @@ inline pk_dpoly *zone_multiply(pk_ctx *ctx, const Plan &pl, const pk_dpoly *A, c
     default: zone_launch_nw<6>(ctx, za, grid, zp.smem, zp.mode, is_signed, zp.tpb); break;
     }
     CUDA_CHECK(cudaEventRecord(ctx->ev_mul1, ctx->stream));
-    PK_LAUNCH(ctx, k_zone_scan, 1, 1024, 0, zone_count, zone_prefix, zp.n_zones, &ctx->d_ctr->n_out);
+    PK_LAUNCH(ctx, k_zone_scan, 1, 1024, 0, zone_count, zone_prefix, n_zones_dev, &ctx->d_ctr->n_out);
     MulCounters *hc = static_cast<MulCounters *>(ctx->h_scratch);
     CUDA_CHECK(cudaMemcpyAsync(hc, ctx->d_ctr, sizeof(MulCounters), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (trace_path) {
+        std::vector<u64> tr(max_chunks * 4);
+        CUDA_CHECK(cudaMemcpy(tr.data(), trace.p, tr.size() * 8, cudaMemcpyDeviceToHost));
+        if (FILE *f = fopen(trace_path, "wb")) {
+            fwrite(tr.data(), 8, tr.size(), f);
+            fclose(f);
+        }
+    }
     const u64 n_out = hc->n_out;
     if (n_out > out_cap || (hc->flags & kFlagTableFull)) fail(PK_E_CUDA, "zone path: result count exceeds its bound (internal error)");
     ctx->stats.table_slots = (u64)zp.cap;
@@ -816,8 +887,8 @@ inline pk_dpoly *zone_multiply(pk_ctx *ctx, const Plan &pl, const pk_dpoly *A, c
     ctx->stats.retries = zp.mode | (zp.tpb << 8); // bit 0: bitmap zones; bits 8..: threads per block (spare counter)
     DPolyGuard e{ctx, new_dpoly(ctx, n_out, nv, pl.out_limbs)};
     if (n_out) {
-        const u32 ggrid = std::min<u32>(zp.n_zones, (u32)ctx->sm_count * 16);
-        PK_LAUNCH(ctx, k_zone_gather, ggrid, 256, 0, zone_count, zone_off, zone_prefix, zp.n_zones, g.p->key, g.p->planes,
+        const u32 ggrid = std::min<u32>(zp.max_zones, (u32)ctx->sm_count * 16);
+        PK_LAUNCH(ctx, k_zone_gather, ggrid, 256, 0, zone_count, zone_off, zone_prefix, n_zones_dev, g.p->key, g.p->planes,
                   g.p->stride, g.p->sign, e.p->key, e.p->planes, e.p->stride, e.p->sign, pl.out_limbs);
     }
     return e.release();

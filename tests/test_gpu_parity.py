@@ -204,8 +204,8 @@ def test_monagan5_all_strategies(ctx):
     dict(zone_mode=2, zone_chunk=1, zone_target=100000),
     dict(zone_mode=1, zone_chunk=64),
     dict(zone_mode=1, zone_tpb=256),
-    dict(zone_mode=2, zone_no_lpt=1),
-    dict(zone_mode=1, zone_no_lpt=1, zone_chunk=3),
+    dict(zone_mode=2, zone_uniform=1),
+    dict(zone_mode=1, zone_uniform=1, zone_chunk=3),
     dict(zone_mode=2, zone_tpb=256, zone_cap=100),
     dict(zone_mode=2, zone_tpb=512),
     dict(zone_mode=1, zone_tpb=1024, zone_target=3),
