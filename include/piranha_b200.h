@@ -55,6 +55,8 @@ extern "C" {
 #define PK_ALGO_HASH 2u  /* open-addressing hash table in HBM (replaces hash_set buckets, hash_set.hpp:1251-1327) */
 #define PK_ALGO_ZONE 3u  /* output range cut into zones, each accumulated in one SM's shared memory
                             (the GPU form of the zone scheme of polynomial.hpp:1783-1966) */
+#define PK_ALGO_BLOCK 4u /* zones aligned to the digits of the re-encoded code: the double loop becomes a list of dense
+                            tiles (blocked_multiplication, base_series_multiplier.hpp:449-504, inside the zone scheme) */
 
 typedef struct pk_ctx pk_ctx;     /* one device + one stream + cached workspaces */
 typedef struct pk_dpoly pk_dpoly; /* a polynomial resident in HBM (sorted by key, with exponent/width metadata) */
@@ -135,7 +137,11 @@ int pk_get_stats(pk_ctx *ctx, pk_stats *out);
  * 0 = 12 per SM), "zone_chunk" (consecutive zones per work unit), "zone_span_log2" (max log2 codes per bitmap zone),
  * "zone_cap" (force a small accumulator capacity; tests), "zone_mode" (0 auto, 1 dense, 2 bitmap), "zone_disable",
  * "zone_cursor_bytes" (memory allowed for row cursors, 0 = binary search per row per zone), "zone_tpb" (threads per
- * block: 0 auto, 256, 512, 1024), "zone_uniform" (1 = equal-span zones instead of equal-work zones).  Never changes results, only how they are computed. */
+ * block: 0 auto, 256, 512, 1024), "zone_uniform" (1 = equal-span zones instead of equal-work zones); for the block
+ * path "block_disable", "block_target" (products per tile), "block_zone_work" (products per zone aimed at),
+ * "block_min_tile", "block_mode" (0 auto, 1 dense, 2 bitmap), "block_hz" (blocks per zone), "block_tpb" (0 = 1024, 512),
+ * "block_natural" (1 = zones claimed in code order instead of heaviest first).
+ * Never changes results, only how they are computed. */
 int pk_ctx_set_tuning(pk_ctx *ctx, const char *key, uint64_t value);
 
 /* ---- host-to-host product: the call behind series_multiplier::operator()() --------------------------------- */

@@ -8,8 +8,8 @@ Layout:
 
 There is no CPU implementation in this package; without the CUDA library and a B200 every call raises.
 """
-from .abi import (ALGO_NAMES, PK_ALGO_AUTO, PK_ALGO_DENSE, PK_ALGO_HASH, PK_ALGO_ZONE, Context, DevicePoly, PkError,
+from .abi import (ALGO_NAMES, PK_ALGO_AUTO, PK_ALGO_DENSE, PK_ALGO_HASH, PK_ALGO_ZONE, PK_ALGO_BLOCK, Context, DevicePoly, PkError,
                   digest_terms, load_library)
 
 __all__ = ["Context", "DevicePoly", "PkError", "load_library", "digest_terms", "PK_ALGO_AUTO", "PK_ALGO_DENSE",
-           "PK_ALGO_HASH", "PK_ALGO_ZONE", "ALGO_NAMES"]
+           "PK_ALGO_HASH", "PK_ALGO_ZONE", "PK_ALGO_BLOCK", "ALGO_NAMES"]

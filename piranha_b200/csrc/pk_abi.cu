@@ -7,6 +7,7 @@
 #include "pk_host.cuh"
 #include "pk_kernels.cuh"
 #include "pk_zone.cuh"
+#include "pk_block.cuh"
 
 using namespace pk;
 
@@ -253,7 +254,7 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
     if (!a || !b) fail(PK_E_ARGS, "null operand");
     // base_series_multiplier.hpp:365-367: "incompatible arguments sets"
     if (a->n_vars != b->n_vars) fail(PK_E_ARGS, "incompatible arguments sets");
-    if (o.trunc_mode < 0 || o.trunc_mode > 2 || o.reserved != 0 || o.algo > PK_ALGO_ZONE) fail(PK_E_ARGS, "bad options");
+    if (o.trunc_mode < 0 || o.trunc_mode > 2 || o.reserved != 0 || o.algo > PK_ALGO_BLOCK) fail(PK_E_ARGS, "bad options");
     if (o.trunc_mode == 2 && a->n_vars && !o.degree_mask) fail(PK_E_ARGS, "partial truncation needs degree_mask");
     u32 P = o.part_count ? o.part_count : 1;
     if (o.part_index >= P) fail(PK_E_ARGS, "part_index out of range");
@@ -316,6 +317,10 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
     }
 
     // ---- output partition [lo, hi) in tight-code space
+    BlockPlan bp = trunc ? BlockPlan{} : block_plan(ctx, pl, nA, nB);
+    // a partitioned product uses the block geometry only when every part gets many whole blocks (else the rounding
+    // of the cuts would unbalance the parts); a function of the operands and P only, so all ranks agree
+    if (bp.ok && P > 1 && pl.range / bp.S < 256ull * P) bp.ok = false;
     u64 lo = 0, hi = pl.range;
     if (P > 1) {
         const u32 SA = (u32)std::min<u64>(nA, 1024), SB = (u32)std::min<u64>(nB, 1024);
@@ -345,6 +350,10 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
         }
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         cuts[P] = pl.range;
+        // whole blocks per rank when the operands have a block geometry (a function of the operands only, so every
+        // rank rounds the same way and the partitions stay disjoint and exhaustive)
+        if (bp.ok)
+            for (u32 p = 1; p < P; ++p) cuts[p] -= cuts[p] % bp.S;
         for (u32 p = 1; p <= P; ++p) cuts[p] = std::max(cuts[p], cuts[p - 1]);
         lo = cuts[o.part_index];
         hi = cuts[o.part_index + 1];
@@ -355,8 +364,15 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
     // ---- strategy
     const unsigned __int128 w_bound = (unsigned __int128)nA * nB;
     u32 algo = o.algo;
-    if (algo == PK_ALGO_AUTO) algo = choose_algo(ctx, pl, nA, nB, sub_range, trunc);
+    if (algo == PK_ALGO_AUTO) {
+        algo = choose_algo(ctx, pl, nA, nB, sub_range, trunc);
+        if (algo == PK_ALGO_ZONE && bp.ok && sub_range) algo = PK_ALGO_BLOCK;
+    }
     pk_dpoly *result = nullptr;
+    if (algo == PK_ALGO_BLOCK) {
+        if (bp.ok && sub_range) result = block_multiply(ctx, pl, bp, A, B, keyA.as<u64>(), kB, lo, hi, nv);
+        if (!result) algo = PK_ALGO_ZONE; // no block geometry for these operands (or tiny groups): generic zones
+    }
     if (algo == PK_ALGO_ZONE) {
         result = zone_multiply(ctx, pl, A, B, keyA.as<u64>(), kB, mB, strideB, trunc ? slbuf->as<u32>() : nullptr, lo, hi,
                                trunc, nv);
@@ -566,6 +582,7 @@ int pk_ctx_create(int device, void *stream, pk_ctx **out)
         c->h_max[m] = std::get<2>(tab[m]);
     }
     zone_configure(c.get());
+    block_configure(c.get());
     *out = c.release();
     return PK_OK;
 }
@@ -638,6 +655,14 @@ int pk_ctx_set_tuning(pk_ctx *ctx, const char *key, uint64_t value)
     else if (k == "zone_cursor_bytes") t.cursor_bytes_max = (u32)value;
     else if (k == "zone_uniform") t.uniform = (u32)value;
     else if (k == "zone_tpb") t.tpb = (value == 256 || value == 512 || value == 1024) ? (u32)value : 0;
+    else if (k == "block_disable") ctx->block_tuning.disable = (u32)value;
+    else if (k == "block_target") ctx->block_tuning.tile_target = std::max<u32>(32, (u32)value);
+    else if (k == "block_zone_work") ctx->block_tuning.zone_work = std::max<u32>(1, (u32)value);
+    else if (k == "block_min_tile") ctx->block_tuning.min_tile = (u32)value;
+    else if (k == "block_mode") ctx->block_tuning.force_mode = (u32)value;
+    else if (k == "block_hz") ctx->block_tuning.force_hz = (u32)value;
+    else if (k == "block_tpb") ctx->block_tuning.tpb = (value == 512) ? 512u : 0u;
+    else if (k == "block_natural") ctx->block_tuning.natural = (u32)value;
     else return PK_E_ARGS;
     return PK_OK;
 }

@@ -28,6 +28,17 @@ struct ZoneTuning {
     uint32_t uniform = 0;          // 1 = equal-span zones instead of equal-work (quantile) zones
 };
 
+struct BlockTuning {
+    uint32_t disable = 0;
+    uint32_t tile_target = 512;   // products per tile of the block path
+    uint32_t zone_work = 1u << 16; // aim for about this many products per zone (more blocks per zone when blocks are light)
+    uint32_t min_tile = 8;        // decline the block path when the average pair of groups has fewer products
+    uint32_t force_mode = 0;      // 0 auto, 1 dense, 2 bitmap
+    uint32_t force_hz = 0;        // tests: blocks per zone
+    uint32_t tpb = 0;             // 0 = 1024, or 512
+    uint32_t natural = 0;         // 1 = claim zones in code order instead of heaviest first
+};
+
 } // namespace pk
 
 struct PinnedBuf {
@@ -55,6 +66,7 @@ struct pk_ctx {
     std::vector<PinnedBuf> pinned;
     int sm_count = 148;
     pk::ZoneTuning zone_tuning;
+    pk::BlockTuning block_tuning;
     size_t smem_optin = 0;
     size_t smem_per_sm = 0;
     size_t total_mem = 0;

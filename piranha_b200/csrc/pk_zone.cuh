@@ -757,6 +757,18 @@ inline ZonePlan zone_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB, u64 sub_r
     return zp;
 }
 
+inline void zone_fill_codec(const Plan &pl, ZoneCodec &cd)
+{
+    cd.n_vars = pl.cpR.n_vars;
+    cd.base_code = pl.base_code;
+    for (u32 v = 0; v < pl.cpR.n_vars; ++v) {
+        const u64 r = pl.cpR.tradix[v];
+        cd.tradix[v] = (u32)r;
+        cd.magic[v] = r > 1 ? (u64)((((unsigned __int128)1) << 64) / r) + 1 : 0;
+        cd.spstride[v] = (i64)((u64)pl.cpR.step[v] * (u64)pl.cpR.pstride[v]);
+    }
+}
+
 inline u32 choose_algo(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB, u64 sub_range, bool trunc)
 {
     if (trunc) return PK_ALGO_AUTO_FALLBACK;
@@ -838,14 +850,7 @@ inline pk_dpoly *zone_multiply(pk_ctx *ctx, const Plan &pl, const pk_dpoly *A, c
     za.osign = g.p->sign;
     za.out_limbs = pl.out_limbs;
     za.out_cap = out_cap;
-    za.cd.n_vars = pl.cpR.n_vars;
-    za.cd.base_code = pl.base_code;
-    for (u32 v = 0; v < pl.cpR.n_vars; ++v) {
-        const u64 r = pl.cpR.tradix[v];
-        za.cd.tradix[v] = (u32)r;
-        za.cd.magic[v] = r > 1 ? (u64)((((unsigned __int128)1) << 64) / r) + 1 : 0;
-        za.cd.spstride[v] = (i64)((u64)pl.cpR.step[v] * (u64)pl.cpR.pstride[v]);
-    }
+    zone_fill_codec(pl, za.cd);
     za.chunk_counter = chunk_counter;
     za.zone_count = zone_count;
     za.zone_off = zone_off;

@@ -45,12 +45,14 @@ def gather_terms(key: torch.Tensor, mag: torch.Tensor, sign: torch.Tensor, count
         mag = mag.view(-1, 1)
     if mag.shape[1] < limbs:
         mag = torch.nn.functional.pad(mag, (0, limbs - mag.shape[1]))
-    k_all = torch.empty((world, nmax), dtype=torch.int64, device=device)
-    m_all = torch.empty((world, nmax, limbs), dtype=torch.int64, device=device)
-    s_all = torch.empty((world, nmax), dtype=torch.int8, device=device)
+    # flat outputs (rank-major concatenation): the one layout both NCCL and gloo accept
+    k_all = torch.empty(world * nmax, dtype=torch.int64, device=device)
+    m_all = torch.empty(world * nmax * limbs, dtype=torch.int64, device=device)
+    s_all = torch.empty(world * nmax, dtype=torch.int8, device=device)
     dist.all_gather_into_tensor(k_all, padded(key, (nmax,), torch.int64), group=group)
-    dist.all_gather_into_tensor(m_all, padded(mag, (nmax, limbs), torch.int64), group=group)
+    dist.all_gather_into_tensor(m_all, padded(mag, (nmax, limbs), torch.int64).view(-1), group=group)
     dist.all_gather_into_tensor(s_all, padded(sign, (nmax,), torch.int8), group=group)
+    k_all, m_all, s_all = k_all.view(world, nmax), m_all.view(world, nmax, limbs), s_all.view(world, nmax)
     keys = torch.cat([k_all[r, :counts[r]] for r in range(world)])
     mags = torch.cat([m_all[r, :counts[r]] for r in range(world)])
     signs = torch.cat([s_all[r, :counts[r]] for r in range(world)])

@@ -16,7 +16,7 @@ from polyhelper import (P31, assert_sorted_unique, assert_terms_equal, cpu_ref, 
 
 pytestmark = pytest.mark.gpu
 
-ALGOS = [pb.PK_ALGO_AUTO, pb.PK_ALGO_DENSE, pb.PK_ALGO_HASH, pb.PK_ALGO_ZONE]
+ALGOS = [pb.PK_ALGO_AUTO, pb.PK_ALGO_DENSE, pb.PK_ALGO_HASH, pb.PK_ALGO_ZONE, pb.PK_ALGO_BLOCK]
 
 
 def gpu_mul(ctx, f, g, nv, **opt):
@@ -189,7 +189,7 @@ def test_monagan5_all_strategies(ctx):
     f, g = po.monagan_operands(5)
     a, b = terms(f, 5, 1), terms(g, 5, 2)
     ref = cpu_ref(a, b, 5, n_threads=8)
-    for algo in (pb.PK_ALGO_DENSE, pb.PK_ALGO_HASH, pb.PK_ALGO_ZONE):
+    for algo in (pb.PK_ALGO_DENSE, pb.PK_ALGO_HASH, pb.PK_ALGO_ZONE, pb.PK_ALGO_BLOCK):
         assert_terms_equal(ctx.mul(a, b, 5, algo=algo), ref)
 
 
@@ -236,10 +236,65 @@ def test_zone_variants(tuning, case):
         c2.close()
 
 
-def test_zone_is_default_for_benchmark_configs(ctx):
+def _variant_case(case):
+    if case == "pearce":
+        (f, g), nv = po.pearce_operands(5), 5
+    elif case == "cancel":
+        (f, g), nv = po.fateman_cancel_operands(7), 4
+    else:
+        (f, g), nv = po.monagan_operands(5), 5
+        f = {k: v for i, (k, v) in enumerate(f.items()) if i % 3 == 0}
+        g = {k: -v if i % 2 else v for i, (k, v) in enumerate(g.items()) if i % 5 == 0}
+    return f, g, nv
+
+
+@pytest.mark.parametrize("tuning", [
+    dict(block_mode=1),                                   # dense blocks
+    dict(block_mode=2),                                   # bitmap blocks
+    dict(block_mode=1, block_hz=1),
+    dict(block_mode=1, block_hz=7, block_natural=1),
+    dict(block_mode=2, block_hz=3, zone_cap=37),          # bitmap zones far over capacity: many passes per zone
+    dict(block_mode=2, block_hz=1000000, zone_cap=5),
+    dict(block_mode=1, block_target=32),                  # many tiny tiles
+    dict(block_mode=2, block_target=100000),              # whole group pairs as single tiles
+    dict(block_mode=1, block_tpb=512),
+    dict(block_mode=2, block_tpb=512, block_natural=1),
+    dict(block_mode=1, block_zone_work=1),
+    dict(block_mode=2, block_zone_work=100000000, zone_span_log2=12),
+    dict(block_mode=2, zone_span_log2=20),
+])
+@pytest.mark.parametrize("case", ["pearce", "cancel", "signed"])
+def test_block_variants(tuning, case):
+    """Every way the block kernel can be configured gives the same bits."""
+    f, g, nv = _variant_case(case)
+    c2 = pb.Context(0)
+    try:
+        c2.set_tuning(block_min_tile=0, **tuning)
+        a, b = terms(f, nv, 1), terms(g, nv, 2)
+        r = c2.mul(a, b, nv, algo=pb.PK_ALGO_BLOCK)
+        st = c2.stats()
+        assert st["algo"] == pb.PK_ALGO_BLOCK
+        assert_sorted_unique(r[0])
+        assert_terms_equal(r, cpu_ref(a, b, nv, n_threads=4))
+        assert st["term_products"] == len(a[0]) * len(b[0])
+    finally:
+        c2.close()
+
+
+def test_block_declines_without_a_digit_split(ctx):
+    # one variable: there is no hi digit, the generic zone path takes over
+    f = {(i,): i + 1 for i in range(0, 3000, 3)}
+    g = {(i,): 2 * i + 1 for i in range(0, 2000, 2)}
+    a, b = terms(f, 1, 1), terms(g, 1, 2)
+    r = ctx.mul(a, b, 1, algo=pb.PK_ALGO_BLOCK)
+    assert ctx.stats()["algo"] == pb.PK_ALGO_ZONE
+    assert_terms_equal(r, cpu_ref(a, b, 1))
+
+
+def test_block_is_default_for_benchmark_configs(ctx):
     for (f, g), nv in ((po.fateman_operands(12), 4), (po.pearce_operands(7), 5)):
         ctx.mul(terms(f, nv), terms(g, nv, 1), nv)
-        assert ctx.stats()["algo"] == pb.PK_ALGO_ZONE
+        assert ctx.stats()["algo"] == pb.PK_ALGO_BLOCK
 
 
 def test_fateman2_full(ctx):
