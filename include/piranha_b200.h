@@ -139,7 +139,7 @@ int pk_get_stats(pk_ctx *ctx, pk_stats *out);
  * "zone_cursor_bytes" (memory allowed for row cursors, 0 = binary search per row per zone), "zone_tpb" (threads per
  * block: 0 auto, 256, 512, 1024), "zone_uniform" (1 = equal-span zones instead of equal-work zones); for the block
  * path "block_disable", "block_target" (products per tile), "block_zone_work" (products per zone aimed at),
- * "block_min_tile", "block_mode" (0 auto, 1 dense, 2 bitmap), "block_hz" (blocks per zone), "block_tpb" (0 = 1024, 512),
+ * "block_min_tile", "block_mode" (0 auto, 1 dense, 2 bitmap), "block_hz" (blocks per zone),
  * "block_natural" (1 = zones claimed in code order instead of heaviest first).
  * Never changes results, only how they are computed. */
 int pk_ctx_set_tuning(pk_ctx *ctx, const char *key, uint64_t value);

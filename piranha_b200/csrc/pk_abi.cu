@@ -200,7 +200,9 @@ Plan make_plan(pk_ctx *ctx, const pk_dpoly *A, const pk_dpoly *B, const pk_opts 
         u64 g = gcd64(A->egcd[v], B->egcd[v]);
         if (g == 0) g = 1;
         const u64 span = (u64)(A->emax[v] - A->emin[v]) + (u64)(B->emax[v] - B->emin[v]);
-        const u64 tr = span / g + 1;
+        u64 tr = span / g + 1;
+        if (v == 0 && nv >= 2 && ctx->block_tuning.radix0_residue) // (bank-conflict experiment: any radix >= tr is exact)
+            tr += (ctx->block_tuning.radix0_residue + 32 - tr % 32) % 32;
         pl.cpA.emin[v] = A->emin[v];
         pl.cpB.emin[v] = B->emin[v];
         pl.cpR.emin[v] = (i64)lo;
@@ -661,8 +663,9 @@ int pk_ctx_set_tuning(pk_ctx *ctx, const char *key, uint64_t value)
     else if (k == "block_min_tile") ctx->block_tuning.min_tile = (u32)value;
     else if (k == "block_mode") ctx->block_tuning.force_mode = (u32)value;
     else if (k == "block_hz") ctx->block_tuning.force_hz = (u32)value;
-    else if (k == "block_tpb") ctx->block_tuning.tpb = (value == 512) ? 512u : 0u;
     else if (k == "block_natural") ctx->block_tuning.natural = (u32)value;
+    else if (k == "block_wide") ctx->block_tuning.wide = (u32)value;
+    else if (k == "block_radix0") ctx->block_tuning.radix0_residue = std::min<u32>(32, (u32)value);
     else return PK_E_ARGS;
     return PK_OK;
 }

@@ -56,7 +56,7 @@ __global__ void k_block_groups(const uint4 *__restrict__ rec, u32 n, u64 magicS,
     if (hi != next) tab[hi].y = i + 1;
 }
 
-constexpr u32 kTileCols = 64; // widest tile, in terms of gb
+constexpr u32 kTileCols = 32; // a full tile holds exactly one term of gb per lane
 
 struct TileArgs {
     const u32 *glistA, *glistB;
@@ -65,6 +65,7 @@ struct TileArgs {
     u32 h_base, n_h; // partition, in blocks
     u32 Hz;
     u32 target;      // products per tile
+    u32 wide;        // 1 = use 64-term chunks of gb (two terms per lane)
     u32 *cnt;        // tiles per block (count pass) / cursor per block (scatter pass)
     u64 *zwork;      // products per zone
     const u32 *tstart;
@@ -75,6 +76,9 @@ struct TileArgs {
 
 // One thread per pair of groups (ga, gb).  PASS 0: count the tiles of block h = hi(ga) + hi(gb) and add the pair's
 // products to its zone.  PASS 1: write the tiles at the block's scanned offset.
+// Tile shapes: gb is cut into chunks of exactly 32 terms (FULL tiles: lane = term of gb, held in registers over the
+// rows of the tile) plus one ragged chunk of nb mod 32 terms (FLAT tiles: rows x terms flattened over the lanes); rows
+// are cut so that a tile has about `target` products.
 template <int PASS>
 __global__ void k_block_tiles(const TileArgs t)
 {
@@ -87,13 +91,14 @@ __global__ void k_block_tiles(const TileArgs t)
     const u32 hr = h - t.h_base;
     const uint2 ra = __ldg(&t.tabA[ha]), rb = __ldg(&t.tabB[hb]);
     const u32 na = ra.y - ra.x, nb = rb.y - rb.x;
-    // tile shape: at most kTileCols terms of gb (balanced column chunks) x as many rows as reach `target` products,
-    // so that a lane keeps its term of gb in registers over the rows of the tile
-    const u32 ncol = (nb + kTileCols - 1) / kTileCols;
-    const u32 cw = (nb + ncol - 1) / ncol;
-    const u32 rpt = min(1023u, max(1u, t.target / cw)); // rows per tile
-    const u32 nrow = (na + rpt - 1) / rpt;
-    const u32 nt = nrow * ncol;
+    // gb = n64 chunks of 64 terms (two per lane) + at most one chunk of 32 (one per lane) + a ragged rest (flat)
+    const u32 n64 = t.wide ? nb / 64u : 0u;
+    const u32 n32 = (nb - n64 * 64u) / kTileCols, rem = nb - n64 * 64u - n32 * kTileCols;
+    const u32 rpt_w = min(1023u, max(1u, t.target / 64u));
+    const u32 rpt_f = min(1023u, max(1u, t.target / kTileCols));
+    const u32 rpt_r = rem ? min(1023u, max(1u, t.target / rem)) : 1u;
+    const u32 nrow_w = (na + rpt_w - 1) / rpt_w, nrow_f = (na + rpt_f - 1) / rpt_f, nrow_r = rem ? (na + rpt_r - 1) / rpt_r : 0u;
+    const u32 nt = n64 * nrow_w + n32 * nrow_f + nrow_r;
     if (PASS == 0) {
         atomicAdd(&t.cnt[hr], nt);
         atomicAdd(&t.zwork[hr / t.Hz], (u64)na * nb);
@@ -103,14 +108,15 @@ __global__ void k_block_tiles(const TileArgs t)
             atomicOr(&t.ctr->flags, kFlagTableFull);
             return;
         }
-        u32 k = pos;
-        for (u32 c = 0; c < ncol; ++c) {
-            const u32 c0 = c * cw, cn = min(cw, nb - c0);
-            for (u32 r = 0; r < nrow; ++r, ++k) {
-                const u32 r0 = r * rpt;
-                t.tiles[k] = make_uint4(ra.x + r0, rb.x + c0, min(rpt, na - r0) | (cn << 10), hr);
-            }
-        }
+        u32 k = pos, c0 = rb.x;
+        for (u32 c = 0; c < n64; ++c, c0 += 64u)
+            for (u32 r = 0; r < nrow_w; ++r, ++k)
+                t.tiles[k] = make_uint4(ra.x + r * rpt_w, c0, min(rpt_w, na - r * rpt_w) | (64u << 10), hr);
+        for (u32 c = 0; c < n32; ++c, c0 += kTileCols)
+            for (u32 r = 0; r < nrow_f; ++r, ++k)
+                t.tiles[k] = make_uint4(ra.x + r * rpt_f, c0, min(rpt_f, na - r * rpt_f) | (kTileCols << 10), hr);
+        for (u32 r = 0; r < nrow_r; ++r, ++k)
+            t.tiles[k] = make_uint4(ra.x + r * rpt_r, c0, min(rpt_r, na - r * rpt_r) | (rem << 10), hr);
     }
 }
 
@@ -162,19 +168,23 @@ __device__ __forceinline__ void block_tile_loop(const uint4 *__restrict__ A, con
                                                 u32 lane, F &&f)
 {
     const u32 a0 = t.x, b0 = t.y, an = t.z & 1023u, bn = t.z >> 10;
-    if (bn >= 32u) {
-        // wide: lane = term of gb (held in registers), loop over the rows (one broadcast load per row)
-        for (u32 j0 = 0; j0 < bn; j0 += 32u) {
-            const u32 j = j0 + lane;
-            const bool ok = j < bn;
-            const uint4 bv = block_load<FULL>(&B[b0 + (ok ? j : 0u)]);
-            for (u32 i = 0; i < an; ++i) {
-                const uint4 av = block_load<FULL>(&A[a0 + i]);
-                if (ok) f(av, bv);
-            }
+    if (bn == 64u) {
+        // two terms of gb per lane: one broadcast load of a row feeds 64 products
+        const uint4 bv0 = block_load<FULL>(&B[b0 + lane]), bv1 = block_load<FULL>(&B[b0 + 32u + lane]);
+        for (u32 i = 0; i < an; ++i) {
+            const uint4 av = block_load<FULL>(&A[a0 + i]);
+            f(av, bv0);
+            f(av, bv1);
+        }
+    } else if (bn == kTileCols) {
+        // full tile: lane = term of gb (held in registers), loop over the rows (one broadcast load per row)
+        const uint4 bv = block_load<FULL>(&B[b0 + lane]);
+        for (u32 i = 0; i < an; ++i) {
+            const uint4 av = block_load<FULL>(&A[a0 + i]);
+            f(av, bv);
         }
     } else {
-        // narrow: the an x bn products are flattened over the lanes; (i, j) advance by 32 without a division
+        // flat tile: the an x bn products are flattened over the lanes; (i, j) advance by 32 without a division
         const u32 total = an * bn;
         const u32 q = 32u / bn, r = 32u - q * bn;
         u32 i = lane / bn, j = lane - i * bn;
@@ -192,17 +202,66 @@ __device__ __forceinline__ void block_tile_loop(const uint4 *__restrict__ A, con
     }
 }
 
-// MODE 0: dense zones (slot = code - zlo; the plan guarantees Hz * S <= cap, so one pass).
-// MODE 1: bitmap zones (slot = rank of the code among the codes that occur; passes of at most cap entries).
-template <int NW, int MODE, bool SIGNED, int TPB>
-__global__ void __launch_bounds__(TPB, 1024 / TPB) k_block(const BlockArgs ba)
+// Add (subtract when neg) the magnitude p0..p3 -- PW significant 32-bit words -- into the NW-word two's complement
+// accumulator whose word w lives at saddr0 + w * wstride.  Words below PW always issue their atomic; the value an
+// ATOMS returns gives the carry into the next word (one add.cc / addc chain per word, no branches); above PW only a
+// pending carry travels on.  The top word's carry-out is the overflow the host's width bound proves impossible.
+template <int NW, int PW, bool SIGNED>
+__device__ __forceinline__ void block_accumulate(u32 saddr0, u32 wstride, u32 p0, u32 p1, u32 p2, u32 p3, bool neg)
 {
-    constexpr u32 kThreads = TPB;
+    const u32 p[5] = {p0, p1, p2, p3, 0u};
+    u32 addr = saddr0;
+    if (SIGNED && neg) {
+        u32 x = p[0], ovf = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            if (w >= PW && x == 0 && ovf == 0) return;
+            if (w == NW - 1) {
+                reds_add(addr, 0u - x);
+                return;
+            }
+            const u32 old = atoms_add(addr, 0u - x);
+            const u32 borrow = ((old < x) ? 1u : 0u) | ovf; // x == 0 with ovf set: the word is unchanged, the borrow moves on
+            const u32 pn = (w + 1 < PW) ? p[(w + 1 < 4) ? w + 1 : 4] : 0u;
+            x = pn + borrow;
+            ovf = (x < borrow) ? 1u : 0u;
+            addr += wstride;
+        }
+    } else {
+        u32 x = p[0], ovf = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            if (w >= PW && x == 0) return; // (ovf needs x == 0xffffffff + 1, impossible above PW where the word is just the carry)
+            if (w == NW - 1) {
+                reds_add(addr, x);
+                return;
+            }
+            const u32 old = atoms_add(addr, x);
+            const u32 pn = (w + 1 < PW) ? p[(w + 1 < 4) ? w + 1 : 4] : 0u;
+            u32 xn, ovfn;
+            // xn = pn + ovf + carry(old + x);  ovfn = carry of that sum (ovf and the carry are never both set)
+            asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %2, %3;\n\taddc.cc.u32 %0, %4, %5;\n\taddc.u32 %1, 0, 0;\n\t}"
+                : "=r"(xn), "=r"(ovfn)
+                : "r"(old), "r"(x), "r"(pn), "r"(ovf));
+            x = xn;
+            ovf = (w + 1 < PW) ? ovfn : 0u;
+            addr += wstride;
+        }
+    }
+}
+
+// MODE 0: dense zones (slot = code - zlo; the plan guarantees Hz * S <= cap, so one pass).
+// MODE 1: bitmap zones (slot = rank of the code among the codes that occur; passes of at most cap entries).  The
+//         bitmap is an array of {bits, rank of the word's first bit} pairs, so a rank is one 8-byte shared load, one
+//         mask and one popcount.
+template <int NW, int PW, int MODE, bool SIGNED>
+__global__ void __launch_bounds__(1024, 1) k_block(const BlockArgs ba)
+{
+    constexpr u32 kThreads = 1024;
     const ZoneArgs &a = ba.z;
     extern __shared__ __align__(16) unsigned char zsmem[];
     u32 *acc = reinterpret_cast<u32 *>(zsmem + a.off_acc);
-    u32 *bm = reinterpret_cast<u32 *>(zsmem + a.off_bm);
-    u32 *pre = reinterpret_cast<u32 *>(zsmem + a.off_pre);
+    uint2 *bm = reinterpret_cast<uint2 *>(zsmem + a.off_bm); // MODE 1: {bits, prefix}
     u32 *list = reinterpret_cast<u32 *>(zsmem + a.off_list);
     __shared__ u32 s_ws[40];
     __shared__ u64 s_b64[2];
@@ -218,7 +277,7 @@ __global__ void __launch_bounds__(TPB, 1024 / TPB) k_block(const BlockArgs ba)
 
     for (u32 i = tid; i < a.cap * NW; i += kThreads) acc[i] = 0;
     if (MODE == 1)
-        for (u32 i = tid; i < a.bm_words; i += kThreads) bm[i] = 0;
+        for (u32 i = tid; i < a.bm_words; i += kThreads) bm[i] = make_uint2(0u, 0u);
     __syncthreads();
 
     for (;;) {
@@ -232,7 +291,7 @@ __global__ void __launch_bounds__(TPB, 1024 / TPB) k_block(const BlockArgs ba)
         const u32 zlo = (ba.h_base + hr0) * ba.S, zhi = (ba.h_base + hr1) * ba.S;
         const u32 t0 = __ldg(&ba.tstart[hr0]), t1 = __ldg(&ba.tstart[hr1]);
         if (t0 == t1) continue; // (only in natural order: a zone without tiles)
-        const u32 zwords = (MODE == 1) ? min(a.bm_words, ((zhi - zlo + 127u) >> 7) << 2) : 0u;
+        const u32 zwords = (MODE == 1) ? min(a.bm_words, (zhi - zlo + 31u) >> 5) : 0u; // bitmap words in use
 
         // ---------------- walk 1 (bitmap zones): mark the codes that occur
         u32 zone_count = 0;
@@ -245,26 +304,23 @@ __global__ void __launch_bounds__(TPB, 1024 / TPB) k_block(const BlockArgs ba)
                 k = __shfl_sync(0xffffffffu, k, 0);
                 if (k >= t1) break;
                 const uint4 t = __ldg(&ba.tiles[k]);
+                if (lane == 0) my_pairs += (u64)(t.z & 1023u) * (t.z >> 10);
                 block_tile_loop<false>(a.A, a.B, t, lane, [&](const uint4 &av, const uint4 &bv) {
                     const u32 slot = av.x + bv.x - zlo;
-                    reds_or(bm_s + (slot >> 5) * 4u, 1u << (slot & 31u));
+                    reds_or(bm_s + (slot >> 5) * 8u, 1u << (slot & 31u));
                 });
             }
             __syncthreads();
-            const u32 n_groups = zwords >> 2;
-            const u32 gpt = (n_groups + kThreads - 1) / kThreads;
-            const u32 g0 = min(n_groups, tid * gpt), g1 = min(n_groups, g0 + gpt);
+            // exclusive popcount prefix per bitmap word
+            const u32 wpt = (zwords + kThreads - 1) / kThreads;
+            const u32 w0 = min(zwords, tid * wpt), w1 = min(zwords, w0 + wpt);
             u32 local = 0;
-            for (u32 g = g0; g < g1; ++g) {
-                const uint4 w4 = reinterpret_cast<const uint4 *>(bm)[g];
-                local += __popc(w4.x) + __popc(w4.y) + __popc(w4.z) + __popc(w4.w);
-            }
+            for (u32 w = w0; w < w1; ++w) local += __popc(bm[w].x);
             u32 total;
             u32 run = block_excl_scan(local, s_ws, total);
-            for (u32 g = g0; g < g1; ++g) {
-                const uint4 w4 = reinterpret_cast<const uint4 *>(bm)[g];
-                pre[g] = run;
-                run += __popc(w4.x) + __popc(w4.y) + __popc(w4.z) + __popc(w4.w);
+            for (u32 w = w0; w < w1; ++w) {
+                bm[w].y = run;
+                run += __popc(bm[w].x);
             }
             zone_count = total;
             __syncthreads();
@@ -272,7 +328,7 @@ __global__ void __launch_bounds__(TPB, 1024 / TPB) k_block(const BlockArgs ba)
 
         // ---------------- accumulate + emit, in passes of at most `cap` entries
         const u32 n_entries = (MODE == 1) ? zone_count : (zhi - zlo);
-        const bool single = n_entries <= a.cap;
+        const bool single = (MODE == 0) || n_entries <= a.cap;
         u64 zone_base = 0, zone_written = 0;
         bool have_base = false;
         u32 r0 = 0;   // first rank (bitmap) / slot (dense) of this pass
@@ -280,69 +336,69 @@ __global__ void __launch_bounds__(TPB, 1024 / TPB) k_block(const BlockArgs ba)
         do {
             const u32 r1 = min(n_entries, r0 + a.cap);
             u32 c1 = zhi;
+            u32 tp0 = t0, tp1 = t1; // tiles of this pass
             if (MODE == 1) {
-                const u32 n_groups = zwords >> 2;
                 if (r1 < n_entries) { // the code of rank r1 bounds this pass
                     if (tid == 0) {
-                        u32 lo_g = 0, hi_g = n_groups;
-                        while (hi_g - lo_g > 1) {
-                            const u32 mid = (lo_g + hi_g) >> 1;
-                            if (pre[mid] <= r1) lo_g = mid;
-                            else hi_g = mid;
+                        u32 lo_w = 0, hi_w = zwords; // last word with prefix <= r1
+                        while (hi_w - lo_w > 1) {
+                            const u32 mid = (lo_w + hi_w) >> 1;
+                            if (bm[mid].y <= r1) lo_w = mid;
+                            else hi_w = mid;
                         }
-                        u32 rem = r1 - pre[lo_g], w = lo_g * 4;
-                        while (rem >= (u32)__popc(bm[w])) {
-                            rem -= __popc(bm[w]);
+                        u32 rem = r1 - bm[lo_w].y, w = lo_w;
+                        while (rem >= (u32)__popc(bm[w].x)) {
+                            rem -= __popc(bm[w].x);
                             ++w;
                         }
-                        s_b32[1] = zlo + w * 32u + __fns(bm[w], 0, (int)rem + 1);
+                        s_b32[1] = zlo + w * 32u + __fns(bm[w].x, 0, (int)rem + 1);
                     }
                     __syncthreads();
                     c1 = s_b32[1];
                 }
-                const u32 gpt = (n_groups + kThreads - 1) / kThreads;
-                const u32 g0 = min(n_groups, tid * gpt), g1 = min(n_groups, g0 + gpt);
-                for (u32 g = g0; g < g1; ++g) {
-                    u32 rank = pre[g];
-                    for (u32 q = 0; q < 4; ++q) {
-                        u32 bits = bm[g * 4 + q];
-                        while (bits) {
-                            const u32 b = __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            if (rank >= r0 && rank < r1) list[rank - r0] = (g * 4 + q) * 32u + b;
-                            ++rank;
-                        }
+                if (!single) { // the codes of a pass are consecutive, so only the tiles of its blocks are walked
+                    tp0 = __ldg(&ba.tstart[hr0 + (c0 - zlo) / ba.S]);
+                    tp1 = __ldg(&ba.tstart[hr0 + (c1 - 1u - zlo) / ba.S + 1u]);
+                }
+                // rank -> slot list of this pass, so that emission runs with full warps
+                const u32 wpt = (zwords + kThreads - 1) / kThreads;
+                const u32 w0 = min(zwords, tid * wpt), w1 = min(zwords, w0 + wpt);
+                for (u32 w = w0; w < w1; ++w) {
+                    const uint2 bw = bm[w];
+                    u32 rank = bw.y, bits = bw.x;
+                    if (rank >= r1 || rank + (u32)__popc(bits) <= r0) continue;
+                    while (bits) {
+                        const u32 b = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        if (rank >= r0 && rank < r1) list[rank - r0] = w * 32u + b;
+                        ++rank;
                     }
                 }
             }
-            if (tid == 0) s_next = t0;
+            if (tid == 0) s_next = tp0;
             __syncthreads();
             for (;;) {
                 u32 k = 0;
                 if (lane == 0) k = atomicAdd(&s_next, 1u);
                 k = __shfl_sync(0xffffffffu, k, 0);
-                if (k >= t1) break;
+                if (k >= tp1) break;
                 const uint4 t = __ldg(&ba.tiles[k]);
-                if (lane == 0 && r0 == 0) my_pairs += (u64)(t.z & 1023u) * (t.z >> 10);
+                if (MODE == 0 && lane == 0) my_pairs += (u64)(t.z & 1023u) * (t.z >> 10);
                 block_tile_loop<true>(a.A, a.B, t, lane, [&](const uint4 &av, const uint4 &bv) {
                     const u32 code = av.x + bv.x;
-                    if (!single && (code < c0 || code >= c1)) return;
+                    if (MODE == 1 && !single && (code < c0 || code >= c1)) return;
                     const u32 slot = code - zlo;
                     u32 e;
                     if (MODE == 1) {
-                        const u32 g = slot >> 7, q = (slot >> 5) & 3u;
-                        const uint4 w4 = reinterpret_cast<const uint4 *>(bm)[g];
-                        const u32 wq = q == 0 ? w4.x : (q == 1 ? w4.y : (q == 2 ? w4.z : w4.w));
-                        u32 rk = pre[g] + __popc(wq & ((1u << (slot & 31u)) - 1u));
-                        rk += (q > 0 ? __popc(w4.x) : 0) + (q > 1 ? __popc(w4.y) : 0) + (q > 2 ? __popc(w4.z) : 0);
-                        e = rk - r0;
+                        const uint2 bw = bm[slot >> 5];
+                        e = bw.y + __popc(bw.x & ((1u << (slot & 31u)) - 1u)) - r0;
                     } else {
-                        e = slot - r0;
+                        e = slot;
                     }
                     const u64 ma = (u64)av.z | ((u64)av.w << 32), mb = (u64)bv.z | ((u64)bv.w << 32);
                     const u64 plo = ma * mb, phi = __umul64hi(ma, mb);
-                    zone_accumulate<NW, SIGNED>(acc_s + e * 4u, wstride, (u32)plo, (u32)(plo >> 32), (u32)phi,
-                                                (u32)(phi >> 32), a.pw, SIGNED && ((av.y ^ bv.y) != 0));
+                    block_accumulate<NW, PW, SIGNED>(acc_s + e * 4u, wstride, (u32)plo, (u32)(plo >> 32), (u32)phi,
+                                                     (u32)(phi >> 32), SIGNED && ((av.y ^ bv.y) != 0));
                 });
             }
             __syncthreads();
@@ -380,7 +436,7 @@ __global__ void __launch_bounds__(TPB, 1024 / TPB) k_block(const BlockArgs ba)
                 u32 total;
                 const u32 excl = block_excl_scan(any != 0 ? 1u : 0u, s_ws, total);
                 if (any) {
-                    const u32 slot = (MODE == 1) ? list[e] : (r0 + e);
+                    const u32 slot = (MODE == 1) ? list[e] : e;
                     zone_emit<NW>(a, zone_base + zone_written + excl, zlo + slot, wd, my_maxbits, my_flags);
                 }
                 zone_written += total;
@@ -394,7 +450,7 @@ __global__ void __launch_bounds__(TPB, 1024 / TPB) k_block(const BlockArgs ba)
             a.zone_off[z] = zone_base;
         }
         if (MODE == 1) {
-            for (u32 i = tid; i < zwords; i += kThreads) bm[i] = 0;
+            for (u32 i = tid; i < zwords; i += kThreads) bm[i].x = 0;
         }
         __syncthreads();
     }
@@ -412,51 +468,49 @@ __global__ void __launch_bounds__(TPB, 1024 / TPB) k_block(const BlockArgs ba)
 
 // ------------------------------------------------------------------------------------------------ host side
 
-template <int NW, int MODE, bool SIGNED, int TPB>
+template <int NW, int PW, int MODE, bool SIGNED>
 struct BlockKernel {
     static void set_smem(size_t bytes)
     {
-        cudaFuncSetAttribute(k_block<NW, MODE, SIGNED, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaFuncSetAttribute(k_block<NW, PW, MODE, SIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     }
     static void launch(pk_ctx *ctx, const BlockArgs &ba, u32 grid, size_t smem)
     {
-        PK_LAUNCH(ctx, (k_block<NW, MODE, SIGNED, TPB>), grid, TPB, smem, ba);
+        PK_LAUNCH(ctx, (k_block<NW, PW, MODE, SIGNED>), grid, 1024, smem, ba);
     }
 };
 
-template <int NW, int TPB>
-void block_set_smem_nt(size_t b)
+// The (accumulator words, product words) pairs the width bound can ask for: NW = ceil((prod_bits + cnt_bits + 1) / 32)
+// with cnt_bits <= 31, PW = min(4, ceil(prod_bits / 32)).
+#define PK_BLOCK_WIDTHS(X) X(2, 1) X(2, 2) X(3, 2) X(3, 3) X(4, 3) X(4, 4) X(5, 4) X(6, 4)
+
+template <int NW, int PW>
+void block_set_smem_w(size_t b)
 {
-    BlockKernel<NW, 0, false, TPB>::set_smem(b);
-    BlockKernel<NW, 0, true, TPB>::set_smem(b);
-    BlockKernel<NW, 1, false, TPB>::set_smem(b);
-    BlockKernel<NW, 1, true, TPB>::set_smem(b);
+    BlockKernel<NW, PW, 0, false>::set_smem(b);
+    BlockKernel<NW, PW, 0, true>::set_smem(b);
+    BlockKernel<NW, PW, 1, false>::set_smem(b);
+    BlockKernel<NW, PW, 1, true>::set_smem(b);
 }
 
-template <int NW>
-void block_set_smem_nw(size_t optin)
-{
-    block_set_smem_nt<NW, 1024>(optin);
-    block_set_smem_nt<NW, 512>(optin);
-}
-
-template <int NW, int TPB>
-void block_launch_nt(pk_ctx *ctx, const BlockArgs &ba, u32 grid, size_t smem, u32 mode, bool is_signed)
+template <int NW, int PW>
+void block_launch_w(pk_ctx *ctx, const BlockArgs &ba, u32 grid, size_t smem, u32 mode, bool is_signed)
 {
     if (mode == 0) {
-        if (is_signed) BlockKernel<NW, 0, true, TPB>::launch(ctx, ba, grid, smem);
-        else BlockKernel<NW, 0, false, TPB>::launch(ctx, ba, grid, smem);
+        if (is_signed) BlockKernel<NW, PW, 0, true>::launch(ctx, ba, grid, smem);
+        else BlockKernel<NW, PW, 0, false>::launch(ctx, ba, grid, smem);
     } else {
-        if (is_signed) BlockKernel<NW, 1, true, TPB>::launch(ctx, ba, grid, smem);
-        else BlockKernel<NW, 1, false, TPB>::launch(ctx, ba, grid, smem);
+        if (is_signed) BlockKernel<NW, PW, 1, true>::launch(ctx, ba, grid, smem);
+        else BlockKernel<NW, PW, 1, false>::launch(ctx, ba, grid, smem);
     }
 }
 
-template <int NW>
-void block_launch_nw(pk_ctx *ctx, const BlockArgs &ba, u32 grid, size_t smem, u32 mode, bool is_signed, u32 tpb)
+inline bool block_width_supported(u32 NW, u32 PW)
 {
-    if (tpb == 512) block_launch_nt<NW, 512>(ctx, ba, grid, smem, mode, is_signed);
-    else block_launch_nt<NW, 1024>(ctx, ba, grid, smem, mode, is_signed);
+#define X(nw, pw) if (NW == nw && PW == pw) return true;
+    PK_BLOCK_WIDTHS(X)
+#undef X
+    return false;
 }
 
 inline void block_configure(pk_ctx *ctx)
@@ -466,26 +520,32 @@ inline void block_configure(pk_ctx *ctx)
     t.tile_target = std::max<u32>(32, env_u32("PK_BLOCK_TARGET", t.tile_target));
     t.zone_work = std::max<u32>(1, env_u32("PK_BLOCK_ZONE_WORK", t.zone_work));
     t.force_mode = env_u32("PK_BLOCK_MODE", t.force_mode);
-    t.tpb = env_u32("PK_BLOCK_TPB", t.tpb);
     t.natural = env_u32("PK_BLOCK_NATURAL", t.natural);
+    t.wide = env_u32("PK_BLOCK_WIDE", t.wide);
+    t.radix0_residue = env_u32("PK_BLOCK_RADIX0", t.radix0_residue);
     const size_t dyn = ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0;
-    block_set_smem_nw<2>(dyn);
-    block_set_smem_nw<3>(dyn);
-    block_set_smem_nw<4>(dyn);
-    block_set_smem_nw<5>(dyn);
-    block_set_smem_nw<6>(dyn);
+#define X(nw, pw) block_set_smem_w<nw, pw>(dyn);
+    PK_BLOCK_WIDTHS(X)
+#undef X
 }
 
 struct BlockPlan {
     bool ok = false;
-    u32 NW = 0, mode = 0, tpb = 1024, grid = 0;
+    u32 NW = 0, PW = 0, mode = 0, grid = 0;
     u32 split = 0; // digits [0, split) form `lo`
     u32 S = 0;     // codes per block
     u32 Hz_max = 1;
     u32 cap = 0, bm_words = 0;
-    u32 off_acc = 0, off_bm = 0, off_pre = 0, off_list = 0;
+    u32 off_acc = 0, off_bm = 0, off_list = 0;
     size_t smem = 0;
 };
+
+inline size_t block_smem_budget(pk_ctx *ctx)
+{
+    size_t budget = ctx->smem_per_sm > 1024 ? ctx->smem_per_sm - 1024 : 0;
+    budget = std::min(budget, ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0);
+    return budget > 1024 ? (budget - 512) & ~255ull : 0; // static shared memory + alignment slack
+}
 
 // The geometry of the block path for a pair of operands.  A function of the operands (tight radices, widths) and of
 // the device only -- NOT of the output partition -- so every rank of a partitioned product derives the same S and
@@ -497,14 +557,10 @@ inline BlockPlan block_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB)
     if (t.disable || pl.LA != 1 || pl.LB != 1 || pl.n_vars < 2) return bp;
     if (nA >= (1u << 22) || nB >= (1u << 22)) return bp; // tile records pack the column count in 22 bits
     if (pl.range > 0xFFFFFFFEull) return bp;
-    u32 NW = (pl.prod_bits + pl.cnt_bits + 1 + 31) / 32;
-    NW = std::max<u32>(NW, 2);
-    if (NW > 6) return bp;
-    const u32 tpb = (t.tpb == 512) ? 512 : 1024;
-    const u32 ctas = 1024 / tpb;
-    size_t budget = (ctx->smem_per_sm > ctas * 1024 ? (ctx->smem_per_sm - ctas * 1024) / ctas : 0);
-    budget = std::min(budget, ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0);
-    budget = budget > 1024 ? (budget - 512) & ~255ull : 0;
+    const u32 NW = std::max<u32>(2, (pl.prod_bits + pl.cnt_bits + 1 + 31) / 32);
+    const u32 PW = std::min<u32>(4, (pl.prod_bits + 31) / 32);
+    if (!block_width_supported(NW, PW)) return bp;
+    const size_t budget = block_smem_budget(ctx);
     if (budget < (16u << 10)) return bp;
     const double W = (double)nA * (double)nB;
     // dense zones when there is at least about one product per three codes, else bitmap zones
@@ -512,7 +568,9 @@ inline BlockPlan block_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB)
     if (t.force_mode == 1) mode = 0;
     if (t.force_mode == 2) mode = 1;
     const u64 cap_dense = (budget / (NW * 4)) & ~31ull;
-    const u64 span_bitmap = 1ull << ctx->zone_tuning.span_log2_max;
+    // bitmap zones: 8 bytes of {bits, prefix} per 32 codes, and room for at least 2048 entries
+    u64 span_bitmap = 1ull << ctx->zone_tuning.span_log2_max;
+    while (span_bitmap > 1024 && span_bitmap / 4 + (size_t)(NW + 1) * 4 * 2048 > budget) span_bitmap >>= 1;
     const u64 limit = mode == 0 ? cap_dense : span_bitmap;
     // the largest split whose block still fits; at least one digit must stay in `hi`
     u64 S = 1;
@@ -527,18 +585,12 @@ inline BlockPlan block_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB)
     if (pl.range / S > (8u << 20)) return bp;                  // group tables are indexed by hi
     if (pl.range + 2 * S >= 0xFFFFFFFFull) return bp;          // zone bounds are 32-bit
     bp.NW = NW;
+    bp.PW = PW;
     bp.mode = mode;
-    bp.tpb = tpb;
     bp.split = split;
     bp.S = (u32)S;
-    if (mode == 0) {
-        bp.Hz_max = (u32)std::max<u64>(1, cap_dense / S);
-        bp.cap = (u32)cap_dense; // trimmed to Hz * S at launch
-        bp.off_acc = 0;
-    } else {
-        bp.Hz_max = (u32)std::max<u64>(1, span_bitmap / S);
-    }
-    bp.grid = (u32)ctx->sm_count * ctas;
+    bp.Hz_max = (u32)std::max<u64>(1, limit / S);
+    bp.grid = (u32)ctx->sm_count;
     bp.ok = true;
     return bp;
 }
@@ -546,10 +598,7 @@ inline BlockPlan block_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB)
 // Shared-memory layout once Hz is known.  Returns false when the zone does not fit.
 inline bool block_layout(pk_ctx *ctx, BlockPlan &bp, u32 Hz)
 {
-    const u32 ctas = 1024 / bp.tpb;
-    size_t budget = (ctx->smem_per_sm > ctas * 1024 ? (ctx->smem_per_sm - ctas * 1024) / ctas : 0);
-    budget = std::min(budget, ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0);
-    budget = budget > 1024 ? (budget - 512) & ~255ull : 0;
+    const size_t budget = block_smem_budget(ctx);
     const u64 span = (u64)Hz * bp.S;
     const u32 NW = bp.NW;
     size_t off = 0;
@@ -559,16 +608,14 @@ inline bool block_layout(pk_ctx *ctx, BlockPlan &bp, u32 Hz)
         off = (size_t)bp.cap * NW * 4;
         bp.bm_words = 0;
     } else {
-        const u64 span128 = (span + 127) & ~127ull;
-        const size_t bm_bytes = span128 / 8, pre_bytes = span128 / 32;
-        if (bm_bytes + pre_bytes + (size_t)(NW + 1) * 4 * 64 + 64 > budget) return false;
-        bp.bm_words = (u32)(span128 / 32);
+        const u64 words = (span + 31) / 32;
+        const size_t bm_bytes = (words * 8 + 15) & ~15ull;
+        if (bm_bytes + (size_t)(NW + 1) * 4 * 64 + 64 > budget) return false;
+        bp.bm_words = (u32)words;
         bp.off_bm = 0;
         off = bm_bytes;
-        bp.off_pre = (u32)off;
-        off += (pre_bytes + 15) & ~15ull;
-        u64 cap = ((budget - off - 16) / ((NW + 1) * 4)) & ~31ull;
-        cap = std::min<u64>(cap, span128);
+        u64 cap = ((budget - off - 16) / ((NW + 1) * 4)) & ~31ull; // NW accumulator words + one list word per entry
+        cap = std::min<u64>(cap, (span + 31) & ~31ull);
         if (ctx->zone_tuning.force_cap) cap = std::max<u64>(1, std::min<u64>(cap, ctx->zone_tuning.force_cap));
         bp.cap = (u32)cap;
         bp.off_list = (u32)off;
@@ -629,9 +676,15 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
         Hz = (Hz + 1) / 2;
     }
     const u32 nz = (u32)((n_h + Hz - 1) / Hz);
+    if (getenv("PK_BLOCK_DEBUG"))
+        fprintf(stderr, "block path: S=%u split=%u n_h=%u Hz=%llu (max %u) zones=%u mode=%u NW=%u PW=%u cap=%u bm_words=%u smem=%zu GA=%u GB=%u\n",
+                S, bp.split, n_h, (unsigned long long)Hz, bp.Hz_max, nz, bp.mode, bp.NW, bp.PW, bp.cap, bp.bm_words, bp.smem, GA, GB);
 
     // ---- tile list: count -> scan -> scatter
-    const u64 max_tiles64 = 4 * (u64)(w_bound / bt.tile_target) + 2 * pairs + 2 * ((u64)GA * nB) / kTileCols + 64;
+    // every chunk of gb (at most nb / 32 + 2 per pair) gives at most 2 * na * width / target + 1 tiles (+ na / 1023 when the
+    // row count per tile hits its 10-bit cap)
+    const u64 max_tiles64 = 2 * (u64)(w_bound / bt.tile_target) + ((u64)GA * nB) / kTileCols + 2 * pairs
+                            + (nB / kTileCols + 2 * (u64)GB) * (nA / 1023 + 1) + 64;
     if (max_tiles64 >= (1ull << 31)) return nullptr;
     const u32 max_tiles = (u32)max_tiles64;
     DevBuf cnt(ctx, ((size_t)n_h + 1) * 4), tstart(ctx, ((size_t)n_h + 1) * 4), tiles(ctx, (size_t)max_tiles * 16);
@@ -659,6 +712,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     ta.n_h = n_h;
     ta.Hz = (u32)Hz;
     ta.target = bt.tile_target;
+    ta.wide = bt.wide;
     ta.cnt = cnt.as<u32>();
     ta.zwork = zwork;
     ta.tstart = tstart.as<u32>();
@@ -693,7 +747,6 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     za.bm_words = bp.bm_words;
     za.off_acc = bp.off_acc;
     za.off_bm = bp.off_bm;
-    za.off_pre = bp.off_pre;
     za.off_list = bp.off_list;
     za.okey = g.p->key;
     za.oplanes = g.p->planes;
@@ -718,13 +771,10 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     const bool is_signed = A->any_neg || B->any_neg;
     const u32 grid = std::min<u32>(bp.grid, nz);
     CUDA_CHECK(cudaEventRecord(ctx->ev_mul0, ctx->stream));
-    switch (bp.NW) {
-    case 2: block_launch_nw<2>(ctx, ba, grid, bp.smem, bp.mode, is_signed, bp.tpb); break;
-    case 3: block_launch_nw<3>(ctx, ba, grid, bp.smem, bp.mode, is_signed, bp.tpb); break;
-    case 4: block_launch_nw<4>(ctx, ba, grid, bp.smem, bp.mode, is_signed, bp.tpb); break;
-    case 5: block_launch_nw<5>(ctx, ba, grid, bp.smem, bp.mode, is_signed, bp.tpb); break;
-    default: block_launch_nw<6>(ctx, ba, grid, bp.smem, bp.mode, is_signed, bp.tpb); break;
-    }
+#define X(nw, pw) \
+    if (bp.NW == nw && bp.PW == pw) block_launch_w<nw, pw>(ctx, ba, grid, bp.smem, bp.mode, is_signed);
+    PK_BLOCK_WIDTHS(X)
+#undef X
     CUDA_CHECK(cudaEventRecord(ctx->ev_mul1, ctx->stream));
     PK_LAUNCH(ctx, k_zone_scan, 1, 1024, 0, zone_count, zone_prefix, n_zones_dev, &ctx->d_ctr->n_out);
     MulCounters *hc = static_cast<MulCounters *>(ctx->h_scratch);
@@ -735,7 +785,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     ctx->stats.table_slots = (u64)bp.cap;
     ctx->stats.acc_lanes = bp.NW;
     ctx->stats.chunk_bits = 0;
-    ctx->stats.retries = bp.mode | (bp.tpb << 8);
+    ctx->stats.retries = bp.mode | (1024u << 8);
     DPolyGuard e{ctx, new_dpoly(ctx, n_out, nv, pl.out_limbs)};
     if (n_out) {
         const u32 ggrid = std::min<u32>(nz, (u32)ctx->sm_count * 16);

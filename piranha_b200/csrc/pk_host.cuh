@@ -35,8 +35,9 @@ struct BlockTuning {
     uint32_t min_tile = 8;        // decline the block path when the average pair of groups has fewer products
     uint32_t force_mode = 0;      // 0 auto, 1 dense, 2 bitmap
     uint32_t force_hz = 0;        // tests: blocks per zone
-    uint32_t tpb = 0;             // 0 = 1024, or 512
     uint32_t natural = 0;         // 1 = claim zones in code order instead of heaviest first
+    uint32_t wide = 1;            // 1 = 64-term chunks of gb (two terms per lane) where the group is large enough
+    uint32_t radix0_residue = 0;  // experiment: pad the radix of digit 0 so that radix mod 32 == this (1..32); 0 = off
 };
 
 } // namespace pk

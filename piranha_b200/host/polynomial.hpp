@@ -1,0 +1,573 @@
+// Host mirror of the reference's operator interface for the multiplier path:
+//
+//   term<Cf, Key>                      include/piranha/term.hpp (mutable coefficient, hash/equality on the key only)
+//   polynomial<Cf, Key>                the part of include/piranha/polynomial.hpp + series.hpp that operator* needs:
+//                                      construction from a symbol name or a constant, + - *, pow, size, equality,
+//                                      get_symbol_set, _container, the auto-truncation statics (:646-740) and
+//                                      truncated_multiplication / untruncated_multiplication (:813-893)
+//   series_multiplier<polynomial<integer, kronecker_monomial<int64_t>>>
+//                                      THE DROP-IN: the class-template protocol of series_multiplier.hpp:37-56 --
+//                                      construct from two series, operator()() returns the product -- implemented
+//                                      by marshalling the terms to the C ABI (include/piranha_b200.h) and filling
+//                                      the result container with rehash / _unique_insert / _update_size exactly as
+//                                      sparse_kronecker_multiplication does (polynomial.hpp:1666-1667, :1750-1754,
+//                                      base_series_multiplier.hpp:934).
+//
+// The arithmetic of the product runs ONLY on the GPU (libpiranha_b200.so); this header contains no multiplication
+// loop.  Series addition/subtraction and symbol merging are host code, as in the reference.
+#ifndef PB200_POLYNOMIAL_HPP
+#define PB200_POLYNOMIAL_HPP
+
+#include <algorithm>
+#include <cstddef>
+#include <cstdint>
+#include <cstdlib>
+#include <iostream>
+#include <mutex>
+#include <new>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "../../include/piranha_b200.h"
+#include "hash_set.hpp"
+#include "integer.hpp"
+#include "kronecker_monomial.hpp"
+#include "series_multiplier.hpp"
+
+namespace pb200
+{
+
+template <typename Cf, typename Key>
+struct term {
+    using cf_type = Cf;
+    using key_type = Key;
+    term() = default;
+    term(Cf cf, Key key) : m_cf(std::move(cf)), m_key(std::move(key)) {}
+    bool operator==(const term &o) const { return m_key == o.m_key; }
+    std::size_t hash() const { return m_key.hash(); }
+    bool is_zero(const symbol_fset &) const { return math::is_zero(m_cf); }
+    bool is_compatible(const symbol_fset &args) const { return m_key.is_compatible(args); }
+    mutable Cf m_cf{};
+    Key m_key{};
+};
+
+struct term_hasher {
+    template <typename Term>
+    std::size_t operator()(const Term &t) const
+    {
+        return t.hash();
+    }
+};
+
+// One pk_ctx per host thread: multipliers are built and consumed on one thread, and operator* may be called
+// concurrently from different threads on different operands (base_series_multiplier.hpp:404-408).
+class gpu
+{
+public:
+    static pk_ctx *context()
+    {
+        thread_local holder h;
+        if (!h.ctx) {
+            const char *dev = std::getenv("PB200_DEVICE");
+            const int rc = pk_ctx_create(dev ? std::atoi(dev) : 0, nullptr, &h.ctx);
+            if (rc != PK_OK) throw std::runtime_error("piranha_b200: no usable sm_100 GPU (pk_ctx_create failed); there is no CPU fallback");
+        }
+        return h.ctx;
+    }
+    // status code -> the exception the reference throws (include/piranha_b200.h)
+    static void check(pk_ctx *ctx, int rc)
+    {
+        if (rc == PK_OK) return;
+        const std::string msg = pk_last_error(ctx);
+        switch (rc) {
+        case PK_E_ARGS: throw std::invalid_argument(msg);
+        case PK_E_KEY_RANGE:
+        case PK_E_DEGREE:
+        case PK_E_CF_WIDTH: throw std::overflow_error(msg);
+        case PK_E_NOMEM: throw std::bad_alloc();
+        default: throw std::runtime_error(msg);
+        }
+    }
+
+private:
+    struct holder {
+        pk_ctx *ctx = nullptr;
+        ~holder()
+        {
+            if (ctx) pk_ctx_destroy(ctx);
+        }
+    };
+};
+
+template <typename Cf, typename Key>
+class polynomial
+{
+public:
+    using term_type = term<Cf, Key>;
+    using container_type = hash_set<term_type, term_hasher>;
+    using size_type = typename container_type::size_type;
+    using degree_type = typename Key::value_type;
+
+    polynomial() = default;
+    // pt{"x"}: the symbol x with unit coefficient
+    explicit polynomial(const std::string &name) : m_symbol_set{name} { insert(term_type(Cf(1), Key{degree_type(1)})); }
+    explicit polynomial(const char *name) : polynomial(std::string(name)) {}
+    // pt{3}: a constant
+    template <typename T, typename std::enable_if<std::is_integral<T>::value || std::is_same<T, Cf>::value, int>::type = 0>
+    polynomial(const T &c)
+    {
+        insert(term_type(Cf(c), Key{}));
+    }
+
+    size_type size() const { return m_container.size(); }
+    bool empty() const { return m_container.empty(); }
+    const symbol_fset &get_symbol_set() const { return m_symbol_set; }
+    void set_symbol_set(const symbol_fset &s)
+    {
+        if (!empty()) throw std::invalid_argument("cannot set arguments on a non-empty series");
+        m_symbol_set = s;
+    }
+    container_type &_container() { return m_container; }
+    const container_type &_container() const { return m_container; }
+
+    // series::insert: add to an existing term or create it, drop zeros (series.hpp:2190)
+    template <bool Sign = true>
+    void insert(term_type t)
+    {
+        if (!t.is_compatible(m_symbol_set)) throw std::invalid_argument("cannot insert incompatible term");
+        if (t.is_zero(m_symbol_set)) return;
+        auto it = m_container.find(t);
+        if (it == m_container.end()) {
+            if (!Sign) t.m_cf = -t.m_cf;
+            m_container.insert(std::move(t));
+        } else {
+            if (Sign) it->m_cf += t.m_cf;
+            else it->m_cf -= t.m_cf;
+            if (math::is_zero(it->m_cf)) m_container.erase(it);
+        }
+    }
+
+    // ---- arithmetic
+    polynomial operator-() const
+    {
+        polynomial r(*this);
+        for (const auto &t : r.m_container) t.m_cf = -t.m_cf;
+        return r;
+    }
+    polynomial &operator+=(const polynomial &o) { return *this = merged_binary(*this, o, true); }
+    polynomial &operator-=(const polynomial &o) { return *this = merged_binary(*this, o, false); }
+    // x *= y  is  x = x * y  (series.hpp:799-805)
+    polynomial &operator*=(const polynomial &o) { return *this = *this * o; }
+    friend polynomial operator+(const polynomial &a, const polynomial &b) { return merged_binary(a, b, true); }
+    friend polynomial operator-(const polynomial &a, const polynomial &b) { return merged_binary(a, b, false); }
+    // dispatch_binary_mul -> series_merge_f -> series_multiplier<Series>(x, y)()   (series.hpp:738-752, :2855-2893)
+    friend polynomial operator*(const polynomial &a, const polynomial &b)
+    {
+        if (a.m_symbol_set == b.m_symbol_set) return series_multiplier<polynomial>(a, b)();
+        symbol_fset merged(a.m_symbol_set);
+        merged.insert(b.m_symbol_set.begin(), b.m_symbol_set.end());
+        const polynomial a2 = a.extend_symbol_set(merged), b2 = b.extend_symbol_set(merged);
+        return series_multiplier<polynomial>(a2, b2)();
+    }
+    template <typename T, typename std::enable_if<std::is_integral<T>::value, int>::type = 0>
+    friend polynomial operator+(const polynomial &a, T n) { return a + polynomial(n); }
+    template <typename T, typename std::enable_if<std::is_integral<T>::value, int>::type = 0>
+    friend polynomial operator+(T n, const polynomial &a) { return polynomial(n) + a; }
+    template <typename T, typename std::enable_if<std::is_integral<T>::value, int>::type = 0>
+    friend polynomial operator-(const polynomial &a, T n) { return a - polynomial(n); }
+    template <typename T, typename std::enable_if<std::is_integral<T>::value, int>::type = 0>
+    friend polynomial operator-(T n, const polynomial &a) { return polynomial(n) - a; }
+    template <typename T, typename std::enable_if<std::is_integral<T>::value, int>::type = 0>
+    friend polynomial operator*(const polynomial &a, T n) { return a.scaled(Cf(n)); }
+    template <typename T, typename std::enable_if<std::is_integral<T>::value, int>::type = 0>
+    friend polynomial operator*(T n, const polynomial &a) { return a.scaled(Cf(n)); }
+
+    friend bool operator==(const polynomial &a, const polynomial &b)
+    {
+        if (a.m_symbol_set != b.m_symbol_set) {
+            symbol_fset merged(a.m_symbol_set);
+            merged.insert(b.m_symbol_set.begin(), b.m_symbol_set.end());
+            return a.extend_symbol_set(merged).same_terms(b.extend_symbol_set(merged));
+        }
+        return a.same_terms(b);
+    }
+    friend bool operator!=(const polynomial &a, const polynomial &b) { return !(a == b); }
+    template <typename T, typename std::enable_if<std::is_integral<T>::value, int>::type = 0>
+    friend bool operator==(const polynomial &a, T n) { return a == polynomial(n); }
+    template <typename T, typename std::enable_if<std::is_integral<T>::value, int>::type = 0>
+    friend bool operator==(T n, const polynomial &a) { return a == polynomial(n); }
+
+    // Exponentiation: single-term series go through the key (so x.pow(-1) and x.pow(limit) work as in the reference,
+    // series.hpp:2333-2403), everything else by repeated multiplication through operator*.
+    polynomial pow(long long n) const
+    {
+        if (size() == 1u) {
+            const term_type &t = *m_container.begin();
+            if (n >= 0 || t.m_cf == Cf(1) || t.m_cf == Cf(-1)) {
+                polynomial r;
+                r.m_symbol_set = m_symbol_set;
+                Cf c = n >= 0 ? t.m_cf.pow(static_cast<unsigned>(n)) : ((n % 2) ? t.m_cf : Cf(1));
+                r.insert(term_type(std::move(c), t.m_key.pow(n, m_symbol_set)));
+                return r;
+            }
+        }
+        if (n < 0) throw std::invalid_argument("negative powers are supported only for single-term series with unit coefficient");
+        polynomial r(1), b(*this);
+        r.m_symbol_set = m_symbol_set;
+        r.m_container.clear();
+        r.insert(term_type(Cf(1), Key(std::vector<degree_type>(m_symbol_set.size(), 0))));
+        unsigned long long e = static_cast<unsigned long long>(n);
+        while (e) {
+            if (e & 1u) r = r * b;
+            e >>= 1;
+            if (e) b = b * b;
+        }
+        return r;
+    }
+
+    degree_type degree() const
+    {
+        if (empty()) return degree_type(0);
+        bool first = true;
+        degree_type d = 0;
+        for (const auto &t : m_container) {
+            const degree_type td = t.m_key.degree(m_symbol_set);
+            if (first || td > d) d = td;
+            first = false;
+        }
+        return d;
+    }
+    // coefficient of the monomial with the given exponents (find_cf)
+    Cf find_cf(const std::vector<degree_type> &exponents) const
+    {
+        if (exponents.size() != m_symbol_set.size()) throw std::invalid_argument("invalid number of exponents");
+        const auto it = m_container.find(term_type(Cf(0), Key(exponents)));
+        return it == m_container.end() ? Cf(0) : it->m_cf;
+    }
+
+    // ---- auto-truncation (polynomial.hpp:646-740): per-type static state under a mutex
+    static void set_auto_truncate_degree(const degree_type &max_degree)
+    {
+        std::lock_guard<std::mutex> lock(s_at_mutex());
+        s_at_mode() = 1;
+        s_at_degree() = max_degree;
+        s_at_names().clear();
+    }
+    static void set_auto_truncate_degree(const degree_type &max_degree, const std::vector<std::string> &names)
+    {
+        std::lock_guard<std::mutex> lock(s_at_mutex());
+        s_at_mode() = 2;
+        s_at_degree() = max_degree;
+        s_at_names() = symbol_fset(names.begin(), names.end());
+    }
+    static void unset_auto_truncate_degree()
+    {
+        std::lock_guard<std::mutex> lock(s_at_mutex());
+        s_at_mode() = 0;
+        s_at_degree() = degree_type(0);
+        s_at_names().clear();
+    }
+    static std::tuple<int, degree_type, symbol_fset> get_auto_truncate_degree()
+    {
+        std::lock_guard<std::mutex> lock(s_at_mutex());
+        return std::make_tuple(s_at_mode(), s_at_degree(), s_at_names());
+    }
+    // explicit (non-automatic) forms, polynomial.hpp:813-893
+    static polynomial untruncated_multiplication(const polynomial &p1, const polynomial &p2)
+    {
+        return with_merged(p1, p2, [](const polynomial &a, const polynomial &b) { return series_multiplier<polynomial>(a, b)._untruncated_multiplication(); });
+    }
+    static polynomial truncated_multiplication(const polynomial &p1, const polynomial &p2, const degree_type &max_degree)
+    {
+        return with_merged(p1, p2, [&](const polynomial &a, const polynomial &b) { return series_multiplier<polynomial>(a, b)._truncated_multiplication(max_degree); });
+    }
+    static polynomial truncated_multiplication(const polynomial &p1, const polynomial &p2, const degree_type &max_degree,
+                                               const std::vector<std::string> &names)
+    {
+        return with_merged(p1, p2, [&](const polynomial &a, const polynomial &b) {
+            std::vector<std::size_t> idx;
+            for (const auto &n : symbol_fset(names.begin(), names.end())) {
+                const std::size_t i = symbol_index(a.get_symbol_set(), n);
+                if (i < a.get_symbol_set().size()) idx.push_back(i);
+            }
+            return series_multiplier<polynomial>(a, b)._truncated_multiplication(max_degree, names, idx);
+        });
+    }
+
+    // canonical printing (sorted by key) for test diagnostics
+    friend std::ostream &operator<<(std::ostream &os, const polynomial &p)
+    {
+        std::vector<const term_type *> v;
+        for (const auto &t : p.m_container) v.push_back(&t);
+        std::sort(v.begin(), v.end(), [](const term_type *a, const term_type *b) { return a->m_key < b->m_key; });
+        if (v.empty()) return os << "0";
+        bool first = true;
+        for (const term_type *t : v) {
+            if (!first) os << " + ";
+            first = false;
+            os << t->m_cf;
+            const auto e = t->m_key.unpack(p.m_symbol_set);
+            std::size_t i = 0;
+            for (const auto &n : p.m_symbol_set) {
+                if (e[i]) os << "*" << n << "**" << e[i];
+                ++i;
+            }
+        }
+        return os;
+    }
+
+    polynomial extend_symbol_set(const symbol_fset &merged) const
+    {
+        if (merged == m_symbol_set) return *this;
+        polynomial r;
+        r.m_symbol_set = merged;
+        r.m_container.rehash(m_container.bucket_count());
+        for (const auto &t : m_container) r.m_container.insert(term_type(t.m_cf, t.m_key.merge_symbols(m_symbol_set, merged)));
+        return r;
+    }
+
+private:
+    template <typename F>
+    static polynomial with_merged(const polynomial &a, const polynomial &b, F &&f)
+    {
+        if (a.m_symbol_set == b.m_symbol_set) return f(a, b);
+        symbol_fset merged(a.m_symbol_set);
+        merged.insert(b.m_symbol_set.begin(), b.m_symbol_set.end());
+        return f(a.extend_symbol_set(merged), b.extend_symbol_set(merged));
+    }
+    static polynomial merged_binary(const polynomial &a, const polynomial &b, bool plus)
+    {
+        symbol_fset merged(a.m_symbol_set);
+        merged.insert(b.m_symbol_set.begin(), b.m_symbol_set.end());
+        polynomial r = a.extend_symbol_set(merged);
+        const polynomial b2 = b.extend_symbol_set(merged);
+        for (const auto &t : b2.m_container) {
+            if (plus) r.template insert<true>(t);
+            else r.template insert<false>(t);
+        }
+        return r;
+    }
+    polynomial scaled(const Cf &c) const
+    {
+        polynomial r;
+        r.m_symbol_set = m_symbol_set;
+        if (math::is_zero(c)) return r;
+        r.m_container.rehash(m_container.bucket_count());
+        for (const auto &t : m_container) r.m_container.insert(term_type(t.m_cf * c, t.m_key));
+        return r;
+    }
+    bool same_terms(const polynomial &o) const
+    {
+        if (size() != o.size()) return false;
+        for (const auto &t : m_container) {
+            const auto it = o.m_container.find(t);
+            if (it == o.m_container.end() || it->m_cf != t.m_cf) return false;
+        }
+        return true;
+    }
+    static std::mutex &s_at_mutex()
+    {
+        static std::mutex m;
+        return m;
+    }
+    static int &s_at_mode()
+    {
+        static int v = 0;
+        return v;
+    }
+    static degree_type &s_at_degree()
+    {
+        static degree_type v = 0;
+        return v;
+    }
+    static symbol_fset &s_at_names()
+    {
+        static symbol_fset v;
+        return v;
+    }
+
+    symbol_fset m_symbol_set;
+    container_type m_container;
+};
+
+namespace math
+{
+template <typename Cf, typename Key>
+inline polynomial<Cf, Key> pow(const polynomial<Cf, Key> &p, long long n)
+{
+    return p.pow(n);
+}
+} // namespace math
+
+// ------------------------------------------------------------------------------------------------ the drop-in
+
+// series_multiplier<polynomial<integer, kronecker_monomial<int64_t>>>: same protocol and member names as
+// polynomial.hpp:991-1968, with the work done by pk_mul().
+template <>
+class series_multiplier<polynomial<integer, kronecker_monomial<std::int64_t>>, void>
+{
+public:
+    using series_type = polynomial<integer, kronecker_monomial<std::int64_t>>;
+    using key_type = kronecker_monomial<std::int64_t>;
+    using term_type = series_type::term_type;
+    using degree_type = series_type::degree_type;
+
+    // base_series_multiplier ctor (base_series_multiplier.hpp:363-401) + check_bounds (polynomial.hpp:1118-1194):
+    // throws std::invalid_argument on mismatching symbol sets and std::overflow_error when an exponent of the
+    // product could leave the Kronecker limits -- from the constructor, like the reference.
+    explicit series_multiplier(const series_type &s1, const series_type &s2) : m_ss(s1.get_symbol_set())
+    {
+        if (s1.get_symbol_set() != s2.get_symbol_set()) throw std::invalid_argument("incompatible arguments sets");
+        const series_type *p1 = &s1, *p2 = &s2;
+        if (p1->size() < p2->size()) std::swap(p1, p2); // larger series first
+        flatten(*p1, m_key1, m_mag1, m_sign1, m_limbs1);
+        flatten(*p2, m_key2, m_mag2, m_sign2, m_limbs2);
+        check_bounds();
+    }
+    series_multiplier(const series_multiplier &) = delete;
+    series_multiplier &operator=(const series_multiplier &) = delete;
+
+    // execute(): the auto-truncation state of the series type selects the path (polynomial.hpp:1596-1628)
+    series_type operator()() const
+    {
+        const auto t = series_type::get_auto_truncate_degree();
+        if (std::get<0>(t) == 0) return _untruncated_multiplication();
+        if (std::get<0>(t) == 1) return _truncated_multiplication(std::get<1>(t));
+        std::vector<std::string> names(std::get<2>(t).begin(), std::get<2>(t).end());
+        std::vector<std::size_t> idx;
+        for (const auto &n : names) {
+            const std::size_t i = symbol_index(m_ss, n);
+            if (i < m_ss.size()) idx.push_back(i);
+        }
+        return _truncated_multiplication(std::get<1>(t), names, idx);
+    }
+    series_type _untruncated_multiplication() const
+    {
+        pk_opts o = make_opts();
+        return run(o);
+    }
+    series_type _truncated_multiplication(const degree_type &max_degree) const
+    {
+        pk_opts o = make_opts();
+        o.trunc_mode = 1;
+        o.max_degree = max_degree;
+        return run(o);
+    }
+    series_type _truncated_multiplication(const degree_type &max_degree, const std::vector<std::string> &,
+                                          const std::vector<std::size_t> &idx) const
+    {
+        std::vector<std::uint8_t> mask(std::max<std::size_t>(1, m_ss.size()), 0);
+        for (const std::size_t i : idx) {
+            if (i >= m_ss.size()) throw std::invalid_argument("invalid symbol position in a truncated multiplication");
+            mask[i] = 1;
+        }
+        pk_opts o = make_opts();
+        o.trunc_mode = 2;
+        o.max_degree = max_degree;
+        o.degree_mask = mask.data();
+        return run(o);
+    }
+    // statistics of the last product on this thread's context (benchmarks)
+    static pk_stats last_stats()
+    {
+        pk_stats st{};
+        pk_get_stats(gpu::context(), &st);
+        return st;
+    }
+
+private:
+    static pk_opts make_opts()
+    {
+        pk_opts o{};
+        o.struct_size = sizeof(pk_opts);
+        return o;
+    }
+    static void flatten(const series_type &s, std::vector<std::int64_t> &key, std::vector<std::uint64_t> &mag,
+                        std::vector<std::int8_t> &sign, std::uint32_t &limbs)
+    {
+        const std::size_t n = s.size();
+        std::size_t L = 1;
+        for (const auto &t : s._container()) L = std::max(L, t.m_cf.size());
+        // wider operands than the C ABI takes are reported by pk_mul as PK_E_CF_WIDTH -> std::overflow_error
+        limbs = static_cast<std::uint32_t>(L);
+        key.resize(n);
+        mag.assign(n * L, 0);
+        sign.resize(n);
+        std::size_t i = 0;
+        for (const auto &t : s._container()) {
+            key[i] = t.m_key.get_int();
+            for (std::size_t l = 0; l < t.m_cf.size(); ++l) mag[i * L + l] = t.m_cf.limb(l);
+            sign[i] = static_cast<std::int8_t>(t.m_cf.sign());
+            ++i;
+        }
+    }
+    void minmax(const std::vector<std::int64_t> &key, std::vector<std::int64_t> &lo, std::vector<std::int64_t> &hi) const
+    {
+        const std::size_t nv = m_ss.size();
+        std::vector<std::int64_t> e(nv);
+        lo.assign(nv, 0);
+        hi.assign(nv, 0);
+        for (std::size_t i = 0; i < key.size(); ++i) {
+            kronecker_array<std::int64_t>::decode(e, key[i]);
+            for (std::size_t v = 0; v < nv; ++v) {
+                if (i == 0 || e[v] < lo[v]) lo[v] = e[v];
+                if (i == 0 || e[v] > hi[v]) hi[v] = e[v];
+            }
+        }
+    }
+    void check_bounds() const
+    {
+        const std::size_t nv = m_ss.size();
+        if (!nv || m_key1.empty() || m_key2.empty()) return;
+        std::vector<std::int64_t> lo1, hi1, lo2, hi2;
+        minmax(m_key1, lo1, hi1);
+        minmax(m_key2, lo2, hi2);
+        const auto &M = std::get<0>(kronecker_array<std::int64_t>::get_limits()[nv]);
+        for (std::size_t v = 0; v < nv; ++v) {
+            const __int128 lo = static_cast<__int128>(lo1[v]) + lo2[v], hi = static_cast<__int128>(hi1[v]) + hi2[v];
+            if (lo < -static_cast<__int128>(M[v]) || hi > static_cast<__int128>(M[v]))
+                throw std::overflow_error("Kronecker monomial components are out of bounds");
+        }
+    }
+    series_type run(const pk_opts &o) const
+    {
+        series_type retval;
+        retval.set_symbol_set(m_ss); // polynomial.hpp:1651-1652
+        if (m_key1.empty() || m_key2.empty()) return retval; // :1654-1656
+        pk_ctx *ctx = gpu::context();
+        const std::uint32_t nv = static_cast<std::uint32_t>(m_ss.size());
+        const pk_poly a{m_key1.size(), nv, m_limbs1, m_key1.data(), m_mag1.data(), m_sign1.data()};
+        const pk_poly b{m_key2.size(), nv, m_limbs2, m_key2.data(), m_mag2.data(), m_sign2.data()};
+        pk_result r{};
+        gpu::check(ctx, pk_mul(ctx, &a, &b, &o, &r));
+        try {
+            auto &c = retval._container();
+            c.rehash(std::max<std::size_t>(1, r.n));
+            for (std::uint64_t i = 0; i < r.n; ++i) {
+                term_type t(integer::from_limbs(r.sign[i], r.mag + i * r.limbs, r.limbs), key_type::from_int(r.key[i]));
+                c._unique_insert(std::move(t), c._bucket_from_hash(static_cast<std::size_t>(r.key[i])));
+            }
+            c._update_size(r.n);
+        } catch (...) {
+            pk_result_free(ctx, &r);
+            retval._container().clear(); // strong guarantee, polynomial.hpp:1961-1965
+            throw;
+        }
+        pk_result_free(ctx, &r);
+        return retval;
+    }
+
+    symbol_fset m_ss;
+    std::vector<std::int64_t> m_key1, m_key2;
+    std::vector<std::uint64_t> m_mag1, m_mag2;
+    std::vector<std::int8_t> m_sign1, m_sign2;
+    std::uint32_t m_limbs1 = 1, m_limbs2 = 1;
+};
+
+} // namespace pb200
+
+#endif

@@ -1,0 +1,196 @@
+// CPU-only tests of the host mirror (no GPU, no product): integer arithmetic, Kronecker codification, hash_set,
+// series addition and symbol merging.  Follows the reference's tests/integer_01.cpp:149-175 (multiply_accumulate),
+// tests/kronecker_array.cpp:52-160 (limits structure, encode/decode round trips), tests/kronecker_monomial_01.cpp:404-461
+// (key multiply) and tests/hash_set_01.cpp (low-level interface).
+#include <cstdint>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../piranha_b200/host/polynomial.hpp"
+#include "check.hpp"
+
+using namespace pb200;
+
+static void integer_test()
+{
+    CHECK_EQUAL(integer(0).sign(), 0);
+    CHECK_EQUAL(integer(-5).to_string(), "-5");
+    CHECK_EQUAL(integer("123456789012345678901234567890").to_string(), "123456789012345678901234567890");
+    CHECK_EQUAL((integer("-99999999999999999999") + integer("99999999999999999999")).is_zero(), true);
+    CHECK_EQUAL(integer(std::numeric_limits<long long>::min()).to_string(), "-9223372036854775808");
+    std::mt19937_64 rng(42);
+    for (int it = 0; it < 20000; ++it) {
+        const long long a = static_cast<long long>(rng()) >> (rng() % 40), b = static_cast<long long>(rng()) >> (rng() % 40);
+        const __int128 p = static_cast<__int128>(a) * b, s = static_cast<__int128>(a) + b, d = static_cast<__int128>(a) - b;
+        auto to128 = [](const integer &n) {
+            unsigned __int128 m = (static_cast<unsigned __int128>(n.limb(1)) << 64) | n.limb(0);
+            return n.sign() < 0 ? -static_cast<__int128>(m) : static_cast<__int128>(m);
+        };
+        CHECK(to128(integer(a) * integer(b)) == p);
+        CHECK(to128(integer(a) + integer(b)) == s);
+        CHECK(to128(integer(a) - integer(b)) == d);
+        // multiply_accumulate against ordinary operators (integer_01.cpp:149-175)
+        integer x(a), y(b), z(a ^ b);
+        integer acc = x;
+        math::multiply_accumulate(acc, y, z);
+        CHECK(acc == x + y * z);
+        CHECK((integer(a) < integer(b)) == (a < b));
+    }
+    // wide values: (2^64 - 1)^4 and string round trip
+    integer w("18446744073709551615");
+    integer w4 = w * w * w * w;
+    CHECK_EQUAL(w4.to_string(), "115792089237316195398462578067141184799968521174335529155754622898352762650625");
+    CHECK_EQUAL(w4.bits(), 256u);
+    CHECK(integer(w4.to_string()) == w4);
+    CHECK_THROW(w4 * w4 * w4, std::overflow_error); // beyond the static capacity: reported, never wrapped
+    CHECK_EQUAL(integer(3).pow(40).to_string(), "12157665459056928801");
+    CHECK_THROW(integer("12x"), std::invalid_argument);
+}
+
+static void kronecker_array_test()
+{
+    using ka = kronecker_array<std::int64_t>;
+    const auto &l = ka::get_limits();
+    CHECK(l.size() > 1u);
+    CHECK(std::get<0>(l[0]).empty());
+    for (std::size_t m = 1; m < l.size(); ++m) { // kronecker_array.cpp:52-83
+        CHECK_EQUAL(std::get<0>(l[m]).size(), m);
+        for (auto v : std::get<0>(l[m])) CHECK(v > 0);
+        CHECK(std::get<1>(l[m]) < 0);
+        CHECK(std::get<2>(l[m]) > 0);
+        CHECK(std::get<3>(l[m]) > 0);
+    }
+    std::mt19937 rng(7);
+    for (std::size_t m = 1; m < std::min<std::size_t>(l.size(), 12); ++m) { // round trips, :100-160
+        const auto &M = std::get<0>(l[m]);
+        std::vector<std::int64_t> v(m), out(m);
+        for (int it = 0; it < 200; ++it) {
+            for (std::size_t i = 0; i < m; ++i) v[i] = it == 0 ? -M[i] : (it == 1 ? M[i] : std::uniform_int_distribution<std::int64_t>(-M[i], M[i])(rng));
+            ka::decode(out, ka::encode(v));
+            CHECK(out == v);
+        }
+        v[0] = M[0] + 1;
+        CHECK_THROW(ka::encode(v), std::invalid_argument);
+    }
+    std::vector<std::int64_t> empty;
+    CHECK_EQUAL(ka::encode(empty), 0);
+    CHECK_THROW(ka::encode(std::vector<std::int64_t>(l.size(), 0)), std::invalid_argument);
+}
+
+static void kronecker_monomial_test()
+{
+    using k_type = kronecker_monomial<std::int64_t>;
+    using term_type = term<integer, k_type>;
+    // kronecker_monomial_01.cpp:404-461
+    symbol_fset ed{"x"};
+    term_type t1(integer(2), k_type{1}), t2(integer(3), k_type{2}), res;
+    k_type::multiply(res, t1, t2, ed);
+    CHECK_EQUAL(res.m_cf, integer(6));
+    CHECK_EQUAL(res.m_key.get_int(), 3);
+    symbol_fset xy{"x", "y"};
+    term_type t3(integer(2), k_type{1, -1}), t4(integer(-4), k_type{2, 0});
+    k_type::multiply(res, t3, t4, xy);
+    CHECK_EQUAL(res.m_cf, integer(-8));
+    CHECK((res.m_key.unpack(xy) == std::vector<std::int64_t>{3, -1}));
+    CHECK_EQUAL((k_type{1, 2}.degree(xy)), 3);
+    CHECK_EQUAL((k_type{1, 2}.degree({1}, xy)), 2);
+    CHECK((k_type{1, 2}.pow(3, xy).unpack(xy) == std::vector<std::int64_t>{3, 6}));
+    CHECK((k_type{5}.merge_symbols(symbol_fset{"y"}, symbol_fset{"x", "y", "z"}).unpack(symbol_fset{"x", "y", "z"})
+           == std::vector<std::int64_t>{0, 5, 0}));
+    CHECK(k_type{}.is_compatible(symbol_fset{}));
+    CHECK(!k_type::from_int(1).is_compatible(symbol_fset{}));
+}
+
+static void hash_set_test()
+{
+    struct H {
+        std::size_t operator()(int v) const { return static_cast<std::size_t>(v); }
+    };
+    hash_set<int, H> h;
+    CHECK(h.empty());
+    CHECK_EQUAL(h.bucket_count(), 0u);
+    for (int i = 0; i < 1000; ++i) CHECK(h.insert(i * 7).second);
+    CHECK(!h.insert(7).second);
+    CHECK_EQUAL(h.size(), 1000u);
+    CHECK((h.bucket_count() & (h.bucket_count() - 1)) == 0u);
+    CHECK(h.load_factor() <= 1.0);
+    for (int i = 0; i < 1000; ++i) CHECK(h.find(i * 7) != h.end());
+    CHECK(h.find(3) == h.end());
+    for (int i = 0; i < 1000; i += 2) h.erase(h.find(i * 7));
+    CHECK_EQUAL(h.size(), 500u);
+    std::size_t n = 0;
+    for (auto it = h.begin(); it != h.end(); ++it) ++n;
+    CHECK_EQUAL(n, 500u);
+    // low-level interface: rehash, _bucket, _unique_insert, _update_size (base_series_multiplier.cpp:448-515 uses it the same way)
+    hash_set<int, H> g;
+    g.rehash(100);
+    CHECK_EQUAL(g.bucket_count(), 128u);
+    for (int i = 0; i < 100; ++i) g._unique_insert(i, g._bucket(i));
+    CHECK_EQUAL(g.size(), 0u);
+    g._update_size(100);
+    CHECK_EQUAL(g.size(), 100u);
+    for (int i = 0; i < 100; ++i) CHECK(g._find(i, g._bucket(i)) != g.end());
+    g.rehash(1); // would exceed the maximum load factor: refused
+    CHECK_EQUAL(g.bucket_count(), 128u);
+    g.rehash(1000);
+    CHECK_EQUAL(g.bucket_count(), 1024u);
+    for (int i = 0; i < 100; ++i) CHECK(g.find(i) != g.end());
+}
+
+static void series_test()
+{
+    using pt = polynomial<integer, kronecker_monomial<std::int64_t>>;
+    pt x{"x"}, y{"y"};
+    CHECK_EQUAL(x.size(), 1u);
+    CHECK((x.get_symbol_set() == symbol_fset{"x"}));
+    auto s = x + y + 1;
+    CHECK_EQUAL(s.size(), 3u);
+    CHECK((s.get_symbol_set() == symbol_fset{"x", "y"}));
+    CHECK_EQUAL(s - s, 0);
+    CHECK_EQUAL((s - y - x), 1);
+    CHECK_EQUAL((x + x).find_cf({1}), integer(2));
+    CHECK_EQUAL((2 * x * 3).find_cf({1}), integer(6));
+    CHECK_EQUAL((x * 0).size(), 0u);
+    CHECK((x.pow(-3).get_symbol_set() == symbol_fset{"x"}));
+    CHECK_EQUAL(x.pow(-3).find_cf({-3}), integer(1));
+    CHECK_EQUAL(x.pow(5).degree(), 5);
+    CHECK(x + y == y + x);
+    CHECK(x + y != y - x);
+    // the primary template has no call operator: only the specialised series type is multipliable
+    static_assert(std::is_empty<series_multiplier<int>>::value, "primary template must be empty");
+    // auto-truncation state (polynomial_truncation.cpp:69-80, :170-177)
+    auto tup = pt::get_auto_truncate_degree();
+    CHECK_EQUAL(std::get<0>(tup), 0);
+    pt::set_auto_truncate_degree(3);
+    tup = pt::get_auto_truncate_degree();
+    CHECK_EQUAL(std::get<0>(tup), 1);
+    CHECK_EQUAL(std::get<1>(tup), 3);
+    pt::set_auto_truncate_degree(1, {"x", "z"});
+    tup = pt::get_auto_truncate_degree();
+    CHECK_EQUAL(std::get<0>(tup), 2);
+    CHECK((std::get<2>(tup) == symbol_fset{"x", "z"}));
+    pt::unset_auto_truncate_degree();
+    tup = pt::get_auto_truncate_degree();
+    CHECK_EQUAL(std::get<0>(tup), 0);
+    CHECK(std::get<2>(tup).empty());
+}
+
+int main(int argc, char **argv)
+{
+    if (argc > 1 && std::string(argv[1]) == "--limits") { // the table the library codifies with, for tests/test_cpp_host.py
+        const auto &l = kronecker_array<std::int64_t>::get_limits();
+        for (std::size_t m = 0; m < l.size(); ++m) {
+            std::printf("%zu %lld", m, static_cast<long long>(std::get<1>(l[m])));
+            for (auto v : std::get<0>(l[m])) std::printf(" %lld", static_cast<long long>(v));
+            std::printf("\n");
+        }
+        return 0;
+    }
+    RUN_TEST(integer_test);
+    RUN_TEST(kronecker_array_test);
+    RUN_TEST(kronecker_monomial_test);
+    RUN_TEST(hash_set_test);
+    RUN_TEST(series_test);
+    return test_summary();
+}

@@ -1,0 +1,203 @@
+// GPU tests of the drop-in through the reference's own operator interface: every product below goes
+// polynomial::operator* -> series_multiplier<polynomial<integer, kronecker_monomial<>>> -> pk_mul (CUDA).
+// The cases restate the reference's tests for this path:
+//   tests/polynomial_multiplier_01.cpp:120-174  bounds (std::overflow_error from the constructor; one below the limit is fine)
+//   tests/polynomial_multiplier_01.cpp:187-238  empty series, reduced Fateman 10626, cancellations 5786
+//   tests/base_series_multiplier.cpp:517-605    reduced Pearce 591235 / 591184
+//   tests/polynomial_truncation.cpp:69-177      total and partial degree auto-truncation
+//   tests/polynomial_multiplier_03.cpp:75-127   untruncated_multiplication / truncated_multiplication statics
+//   tests/polynomial_01.cpp:321-422             differential test against an independent multiplier (here: a plain
+//                                               host double loop used only as the checker inside this test)
+#include <cstdint>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../piranha_b200/host/polynomial.hpp"
+#include "check.hpp"
+
+using namespace pb200;
+using k_type = kronecker_monomial<std::int64_t>;
+using pt = polynomial<integer, k_type>;
+
+// checker only: schoolbook product on the host through series::insert (the role of polynomial_alt's plain multiplier)
+static pt plain_product(const pt &a, const pt &b)
+{
+    symbol_fset ss(a.get_symbol_set());
+    ss.insert(b.get_symbol_set().begin(), b.get_symbol_set().end());
+    const pt a2 = a.extend_symbol_set(ss), b2 = b.extend_symbol_set(ss);
+    pt r;
+    r.set_symbol_set(ss);
+    for (const auto &t1 : a2._container())
+        for (const auto &t2 : b2._container()) {
+            pt::term_type t;
+            k_type::multiply(t, t1, t2, ss);
+            r.insert(t);
+        }
+    return r;
+}
+
+static void bounds_test()
+{
+    using ka = kronecker_array<std::int64_t>;
+    const auto &limits = std::get<0>(ka::get_limits()[3]);
+    pt x{"x"}, y{"y"}, z{"z"};
+    CHECK_THROW(x.pow(limits[0]) * y.pow(limits[1]) * z.pow(limits[2]) * x, std::overflow_error);
+    CHECK_THROW((x.pow(limits[0]) + 1) * (y.pow(limits[1]) + 1) * (z.pow(limits[2]) + 1) * (x + 1), std::overflow_error);
+    CHECK_THROW(x.pow(limits[0]) * y.pow(limits[1]) * z.pow(limits[2]) * y, std::overflow_error);
+    CHECK_THROW(x.pow(limits[0]) * y.pow(limits[1]) * z.pow(limits[2]) * z, std::overflow_error);
+    CHECK_THROW(x.pow(-limits[0]) * y.pow(limits[1]) * z.pow(limits[2]) * x.pow(-1), std::overflow_error);
+    CHECK_THROW((x.pow(limits[0]) + 1) * (y.pow(-limits[1]) + 1) * (z.pow(limits[2]) + 1) * (y.pow(-1) + 1), std::overflow_error);
+    CHECK_THROW(x.pow(limits[0]) * y.pow(limits[1]) * z.pow(-limits[2]) * z.pow(-1), std::overflow_error);
+    CHECK_EQUAL(x.pow(limits[0] - 1) * y.pow(limits[1]) * z.pow(limits[2]) * x, x.pow(limits[0]) * y.pow(limits[1]) * z.pow(limits[2]));
+    CHECK_EQUAL(x.pow(limits[0]) * y.pow(limits[1] - 1) * z.pow(limits[2]) * y, x.pow(limits[0]) * y.pow(limits[1]) * z.pow(limits[2]));
+    CHECK_EQUAL(x.pow(limits[0]) * y.pow(limits[1]) * z.pow(limits[2] - 1) * z, x.pow(limits[0]) * y.pow(limits[1]) * z.pow(limits[2]));
+    CHECK_EQUAL(x.pow(-limits[0] + 1) * y.pow(-limits[1]) * z.pow(-limits[2]) * x.pow(-1),
+                x.pow(-limits[0]) * y.pow(-limits[1]) * z.pow(-limits[2]));
+    CHECK_EQUAL(pt{2} * pt{3}, 6);
+    // the exception comes from the constructor of the multiplier, before anything is computed
+    const pt big = x.pow(limits[0]) * y.pow(limits[1]) * z.pow(limits[2]);
+    const pt xx = x.extend_symbol_set(big.get_symbol_set());
+    CHECK_THROW((series_multiplier<pt>(big, xx)), std::overflow_error);
+    // mismatching symbol sets reach the multiplier only through direct use
+    CHECK_THROW((series_multiplier<pt>(x, y)), std::invalid_argument);
+}
+
+static void multiplication_test()
+{
+    pt e1, e2;
+    CHECK_EQUAL(e1 * e2, 0);
+    CHECK_EQUAL((e1 * e2).get_symbol_set().size(), 0u);
+    pt x{"x"};
+    CHECK_EQUAL(e1 * x, 0);
+    CHECK_EQUAL(x * e1, 0);
+    CHECK(((x * e1).get_symbol_set() == symbol_fset{"x"}));
+    CHECK(((e1 * x).get_symbol_set() == symbol_fset{"x"}));
+    // a reduced Fateman benchmark
+    pt y{"y"}, z{"z"}, t{"t"};
+    auto f = 1 + x + y + z + t;
+    auto tmp2 = f;
+    for (int i = 1; i < 10; ++i) f *= tmp2;
+    auto g = f + 1;
+    auto retval = f * g;
+    CHECK_EQUAL(retval.size(), 10626u);
+    // every coefficient of f*(f+1) has the closed form multinomial(20; a,b,c,d,.) + [deg <= 10] multinomial(10; ...)
+    CHECK_EQUAL(retval.find_cf({0, 0, 0, 0}), integer(2));
+    CHECK_EQUAL(retval.find_cf({20, 0, 0, 0}), integer(1));
+    CHECK_EQUAL(retval.find_cf({1, 0, 0, 0}), integer(30));
+    CHECK_EQUAL(retval.find_cf({5, 5, 5, 5}), integer("11732745024"));
+    // with cancellations
+    auto h = 1 - x + y + z + t;
+    f = 1 + x + y + z + t;
+    tmp2 = h;
+    auto tmp3 = f;
+    for (int i = 1; i < 10; ++i) {
+        h *= tmp2;
+        f *= tmp3;
+    }
+    retval = f * h;
+    CHECK_EQUAL(retval.size(), 5786u);
+    // differential check on a smaller pair against the host schoolbook product
+    auto f5 = (1 + x + y + z + t).pow(5), h5 = (1 - x + y + z + t).pow(5);
+    CHECK(f5 * h5 == plain_product(f5, h5));
+    CHECK(f5 * h5 == h5 * f5);
+}
+
+static void pearce_test()
+{
+    pt x{"x"}, y{"y"}, z{"z"}, t{"t"}, u{"u"};
+    auto f = (x + y + z * z * 2 + t * t * t * 3 + u * u * u * u * u * 5 + 1);
+    auto g = (u + t + z * z * 2 + y * y * y * 3 + x * x * x * x * x * 5 + 1);
+    const auto tmp_f(f), tmp_g(g);
+    for (int i = 1; i < 8; ++i) {
+        f *= tmp_f;
+        g *= tmp_g;
+    }
+    CHECK_EQUAL((f * g).size(), 591235u);
+    auto f2 = (x + y + z * z * 2 + t * t * t * 3 + u * u * u * u * u * 5 + 1);
+    auto g2 = (-1 * u + t + z * z * 2 + y * y * y * 3 + x * x * x * x * x * 5 + 1);
+    const auto tmp_f2(f2), tmp_g2(g2);
+    for (int i = 1; i < 8; ++i) {
+        f2 *= tmp_f2;
+        g2 *= tmp_g2;
+    }
+    CHECK_EQUAL((f2 * g2).size(), 591184u);
+}
+
+static void truncation_test()
+{
+    pt x{"x"}, y{"y"}, z{"z"}, t{"t"};
+    auto tup = pt::get_auto_truncate_degree();
+    CHECK_EQUAL(std::get<0>(tup), 0);
+    CHECK_EQUAL((x + y + z + t) * (x + y + z + t),
+                t * t + 2 * t * x + 2 * t * y + 2 * t * z + x * x + 2 * x * y + 2 * x * z + y * y + 2 * y * z + z * z);
+    // total degree
+    pt::set_auto_truncate_degree(1);
+    CHECK_EQUAL((x + y + 1) * (x + y + 1), 2 * x + 2 * y + 1);
+    pt::set_auto_truncate_degree(2);
+    pt::unset_auto_truncate_degree(); // build the expected value untruncated
+    const pt full = 2 * x + 2 * y + 1 + 2 * x * y + x * x + y * y;
+    pt::set_auto_truncate_degree(2);
+    CHECK_EQUAL((x + y + 1) * (x + y + 1), full);
+    pt::set_auto_truncate_degree(3);
+    CHECK_EQUAL((x + y + 1) * (x + y + 1), full);
+    pt::set_auto_truncate_degree(0);
+    CHECK_EQUAL((x + y + 1) * (x + y + 1), 1);
+    pt::set_auto_truncate_degree(-1);
+    CHECK_EQUAL((x + y + 1) * (x + y + 1), 0);
+    pt::set_auto_truncate_degree(1);
+    CHECK_EQUAL((x + y + z + t) * (x + y + z + t), 0);
+    // partial degree
+    pt::unset_auto_truncate_degree();
+    const pt e_x = 2 * x * y + 2 * x + y * y + 2 * y + 1, e_z = x * x + 2 * x * y + 2 * x + y * y + 2 * y + 1;
+    const pt e_4 = t * t + 2 * t * x + 2 * t * y + 2 * t * z + 2 * x * y + 2 * x * z + y * y + 2 * y * z + z * z;
+    pt::set_auto_truncate_degree(1, {"x"});
+    CHECK_EQUAL((x + y + 1) * (x + y + 1), e_x);
+    pt::set_auto_truncate_degree(1, {"z"});
+    CHECK_EQUAL((x + y + 1) * (x + y + 1), e_z);
+    pt::set_auto_truncate_degree(1, {"x", "y"});
+    CHECK_EQUAL((x + y + 1) * (x + y + 1), 2 * x + 2 * y + 1);
+    pt::set_auto_truncate_degree(1, {"x"});
+    CHECK_EQUAL((x + y + z + t) * (x + y + z + t), e_4);
+    pt::unset_auto_truncate_degree();
+    // the explicit static forms (polynomial_multiplier_03.cpp:75-127)
+    CHECK_EQUAL(pt::untruncated_multiplication(x + y, x - y), x * x - y * y);
+    CHECK_EQUAL(pt::truncated_multiplication(x + y + 1, x + y + 1, 1), 2 * x + 2 * y + 1);
+    CHECK_EQUAL(pt::truncated_multiplication(x + y + 1, x + y + 1, 1, {"x"}), e_x);
+    CHECK_EQUAL(pt::truncated_multiplication(x + y + 1, x + y + 1, -1), 0);
+    // degree-limit arithmetic is checked: max - d1 overflowing throws (polynomial.hpp:1243-1252)
+    CHECK_THROW(pt::truncated_multiplication(1 + x.pow(-1), x, std::numeric_limits<std::int64_t>::max()), std::overflow_error);
+    // truncated Fateman: degree 20 keeps exactly the terms of f (benchmarks/fateman1_unpacked_truncation.cpp:56-59, power 10 here)
+    auto f = (1 + x + y + z + t).pow(10);
+    CHECK_EQUAL(pt::truncated_multiplication(f, f + 1, 10).size(), 1001u);
+    CHECK_EQUAL(pt::truncated_multiplication(f, f + 1, 20).size(), 10626u);
+}
+
+static void threads_test()
+{
+    // operator* may be called concurrently from different user threads on different operands
+    std::vector<std::size_t> sizes(4, 0);
+    std::vector<std::thread> th;
+    for (int k = 0; k < 4; ++k)
+        th.emplace_back([k, &sizes]() {
+            pt x{"x"}, y{"y"}, z{"z"};
+            auto f = (1 + x + y + z).pow(6 + k);
+            sizes[k] = (f * (f + 1)).size();
+        });
+    for (auto &t : th) t.join();
+    for (int k = 0; k < 4; ++k) {
+        const std::size_t n = 2 * (6 + k); // (1+x+y+z)^(2n'): C(n+3, 3) terms
+        CHECK_EQUAL(sizes[k], (n + 1) * (n + 2) * (n + 3) / 6);
+    }
+}
+
+int main()
+{
+    RUN_TEST(bounds_test);
+    RUN_TEST(multiplication_test);
+    RUN_TEST(pearce_test);
+    RUN_TEST(truncation_test);
+    RUN_TEST(threads_test);
+    return test_summary();
+}

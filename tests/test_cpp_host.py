@@ -1,0 +1,64 @@
+"""The C++ host mirror of the reference's operator interface (piranha_b200/host/): polynomial, kronecker_monomial,
+hash_set, integer and the series_multiplier specialisation that calls the C ABI.
+
+  host_logic_test   CPU only: arithmetic, codification, container, series addition (no product is computed)
+  multiplier_test   GPU: the reference's own multiplier tests restated against operator* (tests/cpp/multiplier_test.cpp)
+"""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "build", "bin")
+
+
+def _build():
+    subprocess.check_call(["make", "-s", "-C", ROOT, "host"], stdout=subprocess.DEVNULL)
+
+
+def _run(name, timeout):
+    _build()
+    p = subprocess.run([os.path.join(BIN, name)], capture_output=True, text=True, timeout=timeout)
+    assert p.returncode == 0, p.stdout[-4000:] + p.stderr[-2000:]
+    assert " 0 failures" in p.stdout
+    return p.stdout
+
+
+def test_host_logic():
+    out = _run("host_logic_test", 300)
+    for t in ("integer_test", "kronecker_array_test", "kronecker_monomial_test", "hash_set_test", "series_test"):
+        assert f"[  OK  ] {t}" in out
+
+
+def test_host_kronecker_limits_match_the_golden_table():
+    """The C++ kronecker_array the library codifies with (piranha_b200/host/kronecker_array.hpp: the perturbed-prime
+    search of the reference's kronecker_array.hpp:128-229) yields the table recorded in tests/golden/."""
+    import json
+
+    _build()
+    out = subprocess.check_output([os.path.join(BIN, "host_logic_test"), "--limits"], text=True)
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "kronecker_limits.json")))
+    rows = [list(map(int, line.split())) for line in out.splitlines()]
+    assert len(rows) == len(golden["limits"])
+    for m, hmin, *M in rows:
+        assert M == golden["limits"][m], m
+        assert hmin == golden["h_min"][m], m
+
+
+@pytest.mark.gpu
+def test_reference_multiplier_tests_through_operator_star():
+    out = _run("multiplier_test", 900)
+    for t in ("bounds_test", "multiplication_test", "pearce_test", "truncation_test", "threads_test"):
+        assert f"[  OK  ] {t}" in out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prog,size", [("fateman1", 135751), ("pearce1", 5821335)])
+def test_cpp_benchmarks(prog, size):
+    """benchmarks/*.cpp: operands built by repeated operator*=, the final product timed, the result size checked
+    against the reference's known answer (benchmarks/fateman1.cpp:55, pearce1.cpp:56)."""
+    _build()
+    p = subprocess.run([os.path.join(BIN, prog), "2"], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert f"-> {size} terms" in p.stdout

@@ -257,8 +257,8 @@ def _variant_case(case):
     dict(block_mode=2, block_hz=1000000, zone_cap=5),
     dict(block_mode=1, block_target=32),                  # many tiny tiles
     dict(block_mode=2, block_target=100000),              # whole group pairs as single tiles
-    dict(block_mode=1, block_tpb=512),
-    dict(block_mode=2, block_tpb=512, block_natural=1),
+    dict(block_mode=1, block_hz=2, block_target=64),
+    dict(block_mode=2, block_natural=1, block_hz=5),
     dict(block_mode=1, block_zone_work=1),
     dict(block_mode=2, block_zone_work=100000000, zone_span_log2=12),
     dict(block_mode=2, zone_span_log2=20),
