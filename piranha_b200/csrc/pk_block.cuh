@@ -186,8 +186,10 @@ __device__ __forceinline__ void block_tile_loop(const uint4 *__restrict__ A, con
     } else {
         // flat tile: the an x bn products are flattened over the lanes; (i, j) advance by 32 without a division
         const u32 total = an * bn;
-        const u32 q = 32u / bn, r = 32u - q * bn;
-        u32 i = lane / bn, j = lane - i * bn;
+        // lane / bn and 32 / bn for bn < 32 through one float reciprocal (the +0.5 keeps the quotient far from an integer boundary)
+        const float rbn = __frcp_rn((float)bn);
+        const u32 q = (u32)(32.5f * rbn), r = 32u - q * bn;
+        u32 i = (u32)(((float)lane + 0.5f) * rbn), j = lane - i * bn;
         for (u32 idx = lane; idx < total; idx += 32u) {
             const uint4 av = block_load<FULL>(&A[a0 + i]);
             const uint4 bv = block_load<FULL>(&B[b0 + j]);
@@ -250,6 +252,29 @@ __device__ __forceinline__ void block_accumulate(u32 saddr0, u32 wstride, u32 p0
     }
 }
 
+// Dynamic tile claiming for one walk over the tiles [*, tend) of a zone: a warp claims its next tile (shared-memory
+// counter) and loads that tile's record BEFORE it processes the current one, so the claim and the record's L2 latency
+// hide behind useful work.  The counter must have been set to the first tile before the block-wide barrier.
+template <typename F>
+__device__ __forceinline__ void block_for_each_tile(const uint4 *__restrict__ tiles, u32 *s_next, u32 tend, u32 lane, F &&body)
+{
+    u32 k = 0;
+    if (lane == 0) k = atomicAdd(s_next, 1u);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    if (k >= tend) return;
+    uint4 t = __ldg(&tiles[k]);
+    for (;;) {
+        u32 kn = 0;
+        if (lane == 0) kn = atomicAdd(s_next, 1u);
+        kn = __shfl_sync(0xffffffffu, kn, 0);
+        uint4 tn = make_uint4(0u, 0u, 0u, 0u);
+        if (kn < tend) tn = __ldg(&tiles[kn]);
+        body(t);
+        if (kn >= tend) return;
+        t = tn;
+    }
+}
+
 // MODE 0: dense zones (slot = code - zlo; the plan guarantees Hz * S <= cap, so one pass).
 // MODE 1: bitmap zones (slot = rank of the code among the codes that occur; passes of at most cap entries).  The
 //         bitmap is an array of {bits, rank of the word's first bit} pairs, so a rank is one 8-byte shared load, one
@@ -298,18 +323,13 @@ __global__ void __launch_bounds__(1024, 1) k_block(const BlockArgs ba)
         if (MODE == 1) {
             if (tid == 0) s_next = t0;
             __syncthreads();
-            for (;;) {
-                u32 k = 0;
-                if (lane == 0) k = atomicAdd(&s_next, 1u);
-                k = __shfl_sync(0xffffffffu, k, 0);
-                if (k >= t1) break;
-                const uint4 t = __ldg(&ba.tiles[k]);
+            block_for_each_tile(ba.tiles, &s_next, t1, lane, [&](const uint4 &t) {
                 if (lane == 0) my_pairs += (u64)(t.z & 1023u) * (t.z >> 10);
                 block_tile_loop<false>(a.A, a.B, t, lane, [&](const uint4 &av, const uint4 &bv) {
                     const u32 slot = av.x + bv.x - zlo;
                     reds_or(bm_s + (slot >> 5) * 8u, 1u << (slot & 31u));
                 });
-            }
+            });
             __syncthreads();
             // exclusive popcount prefix per bitmap word
             const u32 wpt = (zwords + kThreads - 1) / kThreads;
@@ -377,12 +397,7 @@ __global__ void __launch_bounds__(1024, 1) k_block(const BlockArgs ba)
             }
             if (tid == 0) s_next = tp0;
             __syncthreads();
-            for (;;) {
-                u32 k = 0;
-                if (lane == 0) k = atomicAdd(&s_next, 1u);
-                k = __shfl_sync(0xffffffffu, k, 0);
-                if (k >= tp1) break;
-                const uint4 t = __ldg(&ba.tiles[k]);
+            block_for_each_tile(ba.tiles, &s_next, tp1, lane, [&](const uint4 &t) {
                 if (MODE == 0 && lane == 0) my_pairs += (u64)(t.z & 1023u) * (t.z >> 10);
                 block_tile_loop<true>(a.A, a.B, t, lane, [&](const uint4 &av, const uint4 &bv) {
                     const u32 code = av.x + bv.x;
@@ -400,7 +415,7 @@ __global__ void __launch_bounds__(1024, 1) k_block(const BlockArgs ba)
                     block_accumulate<NW, PW, SIGNED>(acc_s + e * 4u, wstride, (u32)plo, (u32)(plo >> 32), (u32)phi,
                                                      (u32)(phi >> 32), SIGNED && ((av.y ^ bv.y) != 0));
                 });
-            }
+            });
             __syncthreads();
 
             // ---- emit the entries [0, n_pass) of this pass in ascending code order
@@ -573,11 +588,15 @@ inline BlockPlan block_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB)
     while (span_bitmap > 1024 && span_bitmap / 4 + (size_t)(NW + 1) * 4 * 2048 > budget) span_bitmap >>= 1;
     const u64 limit = mode == 0 ? cap_dense : span_bitmap;
     // the largest split whose block still fits; at least one digit must stay in `hi`
+    // (bitmap zones: a block should also hold its entries in one pass -- the products of a block bound its entries --
+    // because only multi-block zones can restrict a pass to the tiles of the blocks it covers)
+    const u64 cap_bitmap = (budget / 2 / ((NW + 1) * 4)) & ~31ull;
     u64 S = 1;
     u32 split = 0;
     for (u32 v = 0; v + 1 < pl.n_vars; ++v) {
         const u64 next = S * pl.cpR.tradix[v];
         if (next > limit) break;
+        if (mode == 1 && split >= 1 && W / ((double)pl.range / (double)next) > (double)cap_bitmap) break;
         S = next;
         split = v + 1;
     }
@@ -788,9 +807,8 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     ctx->stats.retries = bp.mode | (1024u << 8);
     DPolyGuard e{ctx, new_dpoly(ctx, n_out, nv, pl.out_limbs)};
     if (n_out) {
-        const u32 ggrid = std::min<u32>(nz, (u32)ctx->sm_count * 16);
-        PK_LAUNCH(ctx, k_zone_gather, ggrid, 256, 0, zone_count, zone_off, zone_prefix, n_zones_dev, g.p->key, g.p->planes,
-                  g.p->stride, g.p->sign, e.p->key, e.p->planes, e.p->stride, e.p->sign, pl.out_limbs);
+        PK_LAUNCH(ctx, k_zone_gather, grid_for(n_out, kGatherPerBlock), 256, 0, zone_count, zone_off, zone_prefix, n_zones_dev,
+                  g.p->key, g.p->planes, g.p->stride, g.p->sign, e.p->key, e.p->planes, e.p->stride, e.p->sign, pl.out_limbs, n_out);
     }
     return e.release();
 }

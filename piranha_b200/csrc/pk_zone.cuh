@@ -528,24 +528,36 @@ __global__ void __launch_bounds__(1024) k_zone_cuts(const u32 *__restrict__ sort
     }
 }
 
-// Lay the zones out in zone order (= ascending code order): one block per zone copies its staged terms to
-// prefix[z] in the final arrays.
+// Lay the zones out in zone order (= ascending code order).  One thread per OUTPUT term (so every write is coalesced
+// and the grid covers the whole result whatever the zone sizes): a block finds the zone of its first term by binary
+// search over the scanned zone offsets, then every thread walks forward from there.
+constexpr u32 kGatherPerBlock = 1024;
 __global__ void __launch_bounds__(256) k_zone_gather(const u32 *__restrict__ zone_count, const u64 *__restrict__ zone_off,
                                                      const u64 *__restrict__ zone_prefix, const u32 *__restrict__ n_zones_dev,
                                                      const i64 *__restrict__ skey, const u64 *__restrict__ splanes,
                                                      u64 sstride, const signed char *__restrict__ ssign,
                                                      i64 *__restrict__ okey, u64 *__restrict__ oplanes, u64 ostride,
-                                                     signed char *__restrict__ osign, u32 limbs)
+                                                     signed char *__restrict__ osign, u32 limbs, u64 n_out)
 {
+    (void)zone_count;
     const u32 n_zones = __ldg(n_zones_dev);
-    for (u32 z = blockIdx.x; z < n_zones; z += gridDim.x) {
-        const u32 n = zone_count[z];
-        const u64 src = zone_off[z], dst = zone_prefix[z];
-        for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
-            okey[dst + i] = skey[src + i];
-            osign[dst + i] = ssign[src + i];
-            for (u32 l = 0; l < limbs; ++l) oplanes[(u64)l * ostride + dst + i] = splanes[(u64)l * sstride + src + i];
-        }
+    const u64 base = (u64)blockIdx.x * kGatherPerBlock;
+    if (base >= n_out || n_zones == 0) return;
+    u32 lo = 0, hi = n_zones; // last zone whose first output position is <= base
+    while (hi - lo > 1) {
+        const u32 mid = (lo + hi) >> 1;
+        if (__ldg(&zone_prefix[mid]) <= base) lo = mid;
+        else hi = mid;
+    }
+    u32 z = lo;
+    for (u32 k = 0; k < kGatherPerBlock / 256; ++k) {
+        const u64 i = base + k * 256u + threadIdx.x;
+        if (i >= n_out) break;
+        while (z + 1 < n_zones && __ldg(&zone_prefix[z + 1]) <= i) ++z;
+        const u64 src = __ldg(&zone_off[z]) + (i - __ldg(&zone_prefix[z]));
+        okey[i] = skey[src];
+        osign[i] = ssign[src];
+        for (u32 l = 0; l < limbs; ++l) oplanes[(u64)l * ostride + i] = splanes[(u64)l * sstride + src];
     }
 }
 
@@ -892,9 +904,8 @@ inline pk_dpoly *zone_multiply(pk_ctx *ctx, const Plan &pl, const pk_dpoly *A, c
     ctx->stats.retries = zp.mode | (zp.tpb << 8); // bit 0: bitmap zones; bits 8..: threads per block (spare counter)
     DPolyGuard e{ctx, new_dpoly(ctx, n_out, nv, pl.out_limbs)};
     if (n_out) {
-        const u32 ggrid = std::min<u32>(zp.max_zones, (u32)ctx->sm_count * 16);
-        PK_LAUNCH(ctx, k_zone_gather, ggrid, 256, 0, zone_count, zone_off, zone_prefix, n_zones_dev, g.p->key, g.p->planes,
-                  g.p->stride, g.p->sign, e.p->key, e.p->planes, e.p->stride, e.p->sign, pl.out_limbs);
+        PK_LAUNCH(ctx, k_zone_gather, grid_for(n_out, kGatherPerBlock), 256, 0, zone_count, zone_off, zone_prefix, n_zones_dev,
+                  g.p->key, g.p->planes, g.p->stride, g.p->sign, e.p->key, e.p->planes, e.p->stride, e.p->sign, pl.out_limbs, n_out);
     }
     return e.release();
 }
