@@ -169,6 +169,9 @@ uint32_t pk_dpoly_nvars(const pk_dpoly *p);
 /* Copy the terms into caller-provided DEVICE buffers (key: n int64, mag: n*limbs uint64 row-major, sign: n int8),
  * e.g. torch tensors about to be all-gathered over NCCL.  Any pointer may be NULL to skip that array. */
 int pk_dpoly_export(pk_ctx *ctx, const pk_dpoly *p, void *d_key, void *d_mag, void *d_sign);
+/* Same, with magnitude rows of mag_limbs >= pk_dpoly_limbs(p) words (high limbs zero): lets every rank of a
+ * partitioned product write its terms straight into its slice of one common result buffer. */
+int pk_dpoly_export_padded(pk_ctx *ctx, const pk_dpoly *p, void *d_key, void *d_mag, void *d_sign, uint32_t mag_limbs);
 /* Order-independent 64-bit digest of (key, coefficient) over all terms, computed on the device.  Digests of
  * disjoint partitions add up (mod 2^64) to the digest of the whole product. */
 int pk_dpoly_digest(pk_ctx *ctx, const pk_dpoly *p, uint64_t *digest_out);

@@ -22,7 +22,7 @@ ALGO_NAMES = {0: "auto", 1: "dense", 2: "hash", 3: "zone", 4: "block"}
 EXPORTED_SYMBOLS = [
     "pk_ctx_create", "pk_ctx_destroy", "pk_last_error", "pk_ctx_set_limits", "pk_ctx_get_limits", "pk_get_stats", "pk_ctx_set_tuning",
     "pk_mul", "pk_result_free", "pk_upload", "pk_mul_dev", "pk_download", "pk_dpoly_free", "pk_dpoly_size",
-    "pk_dpoly_limbs", "pk_dpoly_nvars", "pk_dpoly_export", "pk_dpoly_digest",
+    "pk_dpoly_limbs", "pk_dpoly_nvars", "pk_dpoly_export", "pk_dpoly_export_padded", "pk_dpoly_digest",
 ]
 
 
@@ -107,6 +107,7 @@ def load_library():
     lib.pk_dpoly_nvars.argtypes = [vp]
     lib.pk_dpoly_nvars.restype = u32
     lib.pk_dpoly_export.argtypes = [vp, vp, vp, vp, vp]
+    lib.pk_dpoly_export_padded.argtypes = [vp, vp, vp, vp, vp, u32]
     lib.pk_dpoly_digest.argtypes = [vp, vp, C.POINTER(u64)]
     _lib = lib
     return lib
@@ -164,9 +165,11 @@ class DevicePoly:
         self.ctx._check(self.ctx.lib.pk_dpoly_digest(self.ctx.handle, self.handle, C.byref(d)))
         return int(d.value)
 
-    def export_to(self, key_ptr: int, mag_ptr: int, sign_ptr: int):
-        """Copy the terms into caller-owned DEVICE buffers (e.g. torch tensors' data_ptr())."""
-        self.ctx._check(self.ctx.lib.pk_dpoly_export(self.ctx.handle, self.handle, key_ptr, mag_ptr, sign_ptr))
+    def export_to(self, key_ptr: int, mag_ptr: int, sign_ptr: int, mag_limbs: int = 0):
+        """Copy the terms into caller-owned DEVICE buffers (e.g. torch tensors' data_ptr()); mag rows of `mag_limbs`
+        words (default: this polynomial's own limb count)."""
+        self.ctx._check(self.ctx.lib.pk_dpoly_export_padded(self.ctx.handle, self.handle, key_ptr, mag_ptr, sign_ptr,
+                                                            mag_limbs or self.limbs))
 
     def free(self):
         if self.handle:

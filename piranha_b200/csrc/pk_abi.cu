@@ -167,7 +167,7 @@ void download_impl(pk_ctx *ctx, const pk_dpoly *p, pk_result *out)
             CUDA_CHECK(cudaMemcpyAsync(out->mag, p->planes, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
         } else {
             DevBuf aos(ctx, n * p->limbs * 8);
-            PK_LAUNCH(ctx, k_planes_to_aos, grid_for(n, 256), 256, 0, p->planes, aos.as<u64>(), n, p->limbs, p->stride);
+            PK_LAUNCH(ctx, k_planes_to_aos, grid_for(n, 256), 256, 0, p->planes, aos.as<u64>(), n, p->limbs, p->stride, p->limbs);
             CUDA_CHECK(cudaMemcpyAsync(out->mag, aos.p, n * p->limbs * 8, cudaMemcpyDeviceToHost, ctx->stream));
         }
         CUDA_CHECK(cudaMemcpyAsync(out->sign, p->sign, n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -259,7 +259,7 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
     if (o.trunc_mode < 0 || o.trunc_mode > 2 || o.reserved != 0 || o.algo > PK_ALGO_BLOCK) fail(PK_E_ARGS, "bad options");
     if (o.trunc_mode == 2 && a->n_vars && !o.degree_mask) fail(PK_E_ARGS, "partial truncation needs degree_mask");
     u32 P = o.part_count ? o.part_count : 1;
-    if (o.part_index >= P) fail(PK_E_ARGS, "part_index out of range");
+    if (o.part_index >= P || P > 4096) fail(PK_E_ARGS, "part_index / part_count out of range");
     const u32 nv = a->n_vars;
 
     ctx->call_launches = 0;
@@ -325,9 +325,10 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
     if (bp.ok && P > 1 && pl.range / bp.S < 256ull * P) bp.ok = false;
     u64 lo = 0, hi = pl.range;
     if (P > 1) {
-        const u32 SA = (u32)std::min<u64>(nA, 1024), SB = (u32)std::min<u64>(nB, 1024);
+        // stratified sample of pair sums: 512 x 512 pairs resolve the cuts to ~0.2 % of the work for any P <= 64
+        const u32 SA = (u32)std::min<u64>(nA, 512), SB = (u32)std::min<u64>(nB, 512);
         const u64 S = (u64)SA * SB;
-        DevBuf sums(ctx, S * 8), sorted(ctx, S * 8);
+        DevBuf sums(ctx, S * 8), sorted(ctx, S * 8), dcuts(ctx, ((size_t)P + 1) * 8);
         // degrees of B in its (possibly degree-sorted) order are needed for the truncation filter of the sample
         DevBuf degB_perm(ctx, trunc ? nB * 8 : 0);
         const i64 *dB = degB.as<i64>();
@@ -337,20 +338,13 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
         }
         PK_LAUNCH(ctx, k_sample_sums, grid_for(S, 256), 256, 0, keyA.as<u64>(), nA, kB, nB, SA, SB, degA.as<i64>(), dB,
                   o.max_degree, trunc ? 1 : 0, sums.as<u64>(), ctx->d_ctr);
+        // (excluded pairs carry the all-ones sentinel and sort last: every bit of the key takes part)
         radix_sort_keys(ctx, sums.as<u64>(), sorted.as<u64>(), S, 64);
-        MulCounters *hc = static_cast<MulCounters *>(ctx->h_scratch);
-        CUDA_CHECK(cudaMemcpyAsync(hc, ctx->d_ctr, sizeof(MulCounters), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        const u64 valid = hc->aux;
+        PK_LAUNCH(ctx, k_pick_cuts, 1, 64, 0, sorted.as<u64>(), ctx->d_ctr, P, dcuts.as<u64>());
         u64 *cuts = reinterpret_cast<u64 *>(static_cast<char *>(ctx->h_scratch) + 1024);
-        cuts[0] = 0;
-        for (u32 p = 1; p < P; ++p) {
-            if (valid == 0) cuts[p] = 0;
-            else
-                CUDA_CHECK(cudaMemcpyAsync(&cuts[p], sorted.as<u64>() + (u64)((unsigned __int128)valid * p / P), 8,
-                                           cudaMemcpyDeviceToHost, ctx->stream));
-        }
+        CUDA_CHECK(cudaMemcpyAsync(cuts, dcuts.p, ((size_t)P + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        cuts[0] = 0;
         cuts[P] = pl.range;
         // whole blocks per rank when the operands have a block geometry (a function of the operands only, so every
         // rank rounds the same way and the partitions stay disjoint and exhaustive)
@@ -718,19 +712,24 @@ uint64_t pk_dpoly_size(const pk_dpoly *p) { return p ? p->n : 0; }
 uint32_t pk_dpoly_limbs(const pk_dpoly *p) { return p ? p->limbs : 0; }
 uint32_t pk_dpoly_nvars(const pk_dpoly *p) { return p ? p->n_vars : 0; }
 
-int pk_dpoly_export(pk_ctx *ctx, const pk_dpoly *p, void *d_key, void *d_mag, void *d_sign)
+int pk_dpoly_export_padded(pk_ctx *ctx, const pk_dpoly *p, void *d_key, void *d_mag, void *d_sign, uint32_t mag_limbs)
 {
-    if (!ctx || !p) return PK_E_ARGS;
+    if (!ctx || !p || mag_limbs < p->limbs) return PK_E_ARGS;
     PK_TRY(ctx, {
         cudaSetDevice(ctx->device);
         if (p->n) {
             if (d_key) CUDA_CHECK(cudaMemcpyAsync(d_key, p->key, p->n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
             if (d_mag)
                 PK_LAUNCH(ctx, k_planes_to_aos, grid_for(p->n, 256), 256, 0, p->planes, static_cast<u64 *>(d_mag), p->n,
-                          p->limbs, p->stride);
+                          p->limbs, p->stride, mag_limbs);
             if (d_sign) CUDA_CHECK(cudaMemcpyAsync(d_sign, p->sign, p->n, cudaMemcpyDeviceToDevice, ctx->stream));
         }
     })
+}
+
+int pk_dpoly_export(pk_ctx *ctx, const pk_dpoly *p, void *d_key, void *d_mag, void *d_sign)
+{
+    return pk_dpoly_export_padded(ctx, p, d_key, d_mag, d_sign, p ? p->limbs : 0);
 }
 
 int pk_dpoly_digest(pk_ctx *ctx, const pk_dpoly *p, uint64_t *digest_out)

@@ -25,11 +25,13 @@ __global__ void k_aos_to_planes(const u64 *__restrict__ aos, u64 *__restrict__ p
     for (u32 l = 0; l < limbs; ++l) planes[l * stride + i] = aos[i * limbs + l];
 }
 
-__global__ void k_planes_to_aos(const u64 *__restrict__ planes, u64 *__restrict__ aos, u64 n, u32 limbs, u64 stride)
+// limb planes -> AoS rows of out_limbs >= limbs words (missing high limbs are zero)
+__global__ void k_planes_to_aos(const u64 *__restrict__ planes, u64 *__restrict__ aos, u64 n, u32 limbs, u64 stride,
+                                u32 out_limbs)
 {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    for (u32 l = 0; l < limbs; ++l) aos[i * limbs + l] = planes[l * stride + i];
+    for (u32 l = 0; l < out_limbs; ++l) aos[i * out_limbs + l] = l < limbs ? planes[l * stride + i] : 0ull;
 }
 
 __global__ void k_iota32(u32 *out, u64 n)
@@ -516,6 +518,14 @@ __global__ void k_sample_sums(const u64 *__restrict__ keyA, u64 nA, const u64 *_
     }
     if (v != kEmptyKey) atomicAdd(&ctr->aux, 1ull);
     out[t] = v;
+}
+
+// cuts[p] = the (valid * p / P)-th smallest sampled pair sum, p = 1 .. P-1 (valid = number of admissible samples)
+__global__ void k_pick_cuts(const u64 *__restrict__ sorted, const MulCounters *__restrict__ ctr, u32 P, u64 *__restrict__ cuts)
+{
+    const u64 valid = ctr->aux;
+    for (u32 p = threadIdx.x; p <= P; p += blockDim.x)
+        cuts[p] = (p == 0 || p == P || valid == 0) ? 0ull : sorted[(u64)((unsigned __int128)valid * p / P)];
 }
 
 // ------------------------------------------------------------------------------------------------ digest

@@ -3,8 +3,12 @@
 Both operands are replicated (they are at most a few MB); rank r calls pk_mul_dev with part_index=r and
 part_count=world_size, so every term product is performed by exactly one rank and no reduction is needed.
 The only exchange is the final gather of result sizes and terms (torch.distributed: NCCL over NVLink on GPUs,
-gloo in the CPU tests).  Ranges are ordered, so concatenating the per-rank sorted outputs in rank order gives the
+gloo in the CPU tests).  Ranges are ordered, so laying the per-rank sorted outputs out in rank order gives the
 globally sorted result.  This is the GPU form of the zone scheme of polynomial.hpp:1783-1966 lifted to ranks.
+
+The term gather moves every byte once: the sizes are all-gathered first, every rank then writes its own terms
+straight into its slice of the common result buffers (device-to-device, pk_dpoly_export_padded) and each slice is
+broadcast in place from its owner -- no padding to the largest rank, no staging copies, no concatenation.
 """
 from __future__ import annotations
 
@@ -24,39 +28,48 @@ def gather_sizes(n_local: int, limbs_local: int, device, group=None) -> Tuple[Li
     return [int(x) for x in allv[:, 0]], int(allv[:, 1].max())
 
 
-def gather_terms(key: torch.Tensor, mag: torch.Tensor, sign: torch.Tensor, counts: List[int], limbs: int, group=None):
-    """Gather variable-size per-rank term arrays into the global (rank-ordered) arrays on every rank.
+def _offsets(counts: List[int]) -> List[int]:
+    off = [0]
+    for c in counts:
+        off.append(off[-1] + c)
+    return off
 
-    key int64[n_r], mag int64[n_r, limbs] (bit pattern of the uint64 limbs), sign int8[n_r].  Buffers are padded to
-    the largest count so that one all_gather_into_tensor per array suffices (three collectives in total)."""
+
+def exchange_slices(keys: torch.Tensor, mags: torch.Tensor, signs: torch.Tensor, counts: List[int], group=None):
+    """In-place exchange: rank r owns rows [off_r, off_r + counts[r]) of the three result buffers (already filled
+    locally) and broadcasts them to everyone.  3 * world collectives, all asynchronous, each moving its bytes once."""
     world = dist.get_world_size(group)
+    off = _offsets(counts)
+    work = []
+    for r in range(world):
+        if counts[r] == 0:
+            continue
+        src = dist.get_global_rank(group, r) if group is not None else r
+        for buf in (keys, mags, signs):
+            work.append(dist.broadcast(buf[off[r]:off[r + 1]], src=src, group=group, async_op=True))
+    for w in work:
+        w.wait()
+    return keys, mags, signs
+
+
+def gather_terms(key: torch.Tensor, mag: torch.Tensor, sign: torch.Tensor, counts: List[int], limbs: int, group=None):
+    """Gather variable-size per-rank term arrays (torch tensors) into the global rank-ordered arrays on every rank.
+
+    key int64[n_r], mag int64[n_r, limbs_r] (bit pattern of the uint64 limbs), sign int8[n_r]."""
     rank = dist.get_rank(group)
     device = key.device
-    nmax = max(max(counts), 1)
+    off = _offsets(counts)
     n = counts[rank]
-
-    def padded(t, shape, dtype):
-        buf = torch.zeros(shape, dtype=dtype, device=device)
-        if n:
-            buf[:n] = t[:n]
-        return buf
-
-    if mag.dim() == 1:
-        mag = mag.view(-1, 1)
-    if mag.shape[1] < limbs:
-        mag = torch.nn.functional.pad(mag, (0, limbs - mag.shape[1]))
-    # flat outputs (rank-major concatenation): the one layout both NCCL and gloo accept
-    k_all = torch.empty(world * nmax, dtype=torch.int64, device=device)
-    m_all = torch.empty(world * nmax * limbs, dtype=torch.int64, device=device)
-    s_all = torch.empty(world * nmax, dtype=torch.int8, device=device)
-    dist.all_gather_into_tensor(k_all, padded(key, (nmax,), torch.int64), group=group)
-    dist.all_gather_into_tensor(m_all, padded(mag, (nmax, limbs), torch.int64).view(-1), group=group)
-    dist.all_gather_into_tensor(s_all, padded(sign, (nmax,), torch.int8), group=group)
-    k_all, m_all, s_all = k_all.view(world, nmax), m_all.view(world, nmax, limbs), s_all.view(world, nmax)
-    keys = torch.cat([k_all[r, :counts[r]] for r in range(world)])
-    mags = torch.cat([m_all[r, :counts[r]] for r in range(world)])
-    signs = torch.cat([s_all[r, :counts[r]] for r in range(world)])
-    return keys, mags, signs
+    keys = torch.empty(off[-1], dtype=torch.int64, device=device)
+    mags = torch.zeros((off[-1], limbs), dtype=torch.int64, device=device) if mag.dim() == 1 or mag.shape[-1] < limbs \
+        else torch.empty((off[-1], limbs), dtype=torch.int64, device=device)
+    signs = torch.empty(off[-1], dtype=torch.int8, device=device)
+    if n:
+        keys[off[rank]:off[rank + 1]] = key[:n]
+        m = mag.view(n, -1) if mag.dim() == 1 else mag[:n]
+        mags[off[rank]:off[rank + 1], :m.shape[1]] = m
+        signs[off[rank]:off[rank + 1]] = sign[:n]
+    return exchange_slices(keys, mags, signs, counts, group)
 
 
 def export_local(dpoly, device) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -77,6 +90,12 @@ def multiply_partitioned(ctx, da, db, device, group=None, gather: bool = True, *
     part = ctx.mul_dev(da, db, part_index=rank, part_count=world, **opt)
     if not gather:
         return part, None
-    key, mag, sign = export_local(part, device)
     counts, limbs = gather_sizes(len(part), max(1, part.limbs), device, group)
-    return part, gather_terms(key, mag, sign, counts, limbs, group)
+    off = _offsets(counts)
+    keys = torch.empty(off[-1], dtype=torch.int64, device=device)
+    mags = torch.empty((off[-1], limbs), dtype=torch.int64, device=device)
+    signs = torch.empty(off[-1], dtype=torch.int8, device=device)
+    if counts[rank]:  # this rank's terms go straight into its slice of the result
+        lo = off[rank]
+        part.export_to(keys[lo:].data_ptr(), mags[lo:].data_ptr(), signs[lo:].data_ptr(), mag_limbs=limbs)
+    return part, exchange_slices(keys, mags, signs, counts, group)
