@@ -83,19 +83,60 @@ def export_local(dpoly, device) -> Tuple[torch.Tensor, torch.Tensor, torch.Tenso
     return key, mag, sign
 
 
-def multiply_partitioned(ctx, da, db, device, group=None, gather: bool = True, **opt):
-    """One multi-GPU product: this rank's partition through the C ABI, then the size + term gather."""
+class GatherWorkspace:
+    """Result buffers reused across products (grow-only).  Tensors that took part in an NCCL collective are released
+    lazily by the caching allocator (they are recorded on NCCL's stream), so allocating 100+ MB of fresh result buffers
+    per product costs milliseconds; a workspace owned by the caller avoids it."""
+
+    def __init__(self):
+        self.keys = self.mags = self.signs = None
+
+    def get(self, n: int, limbs: int, device):
+        if self.keys is None or self.keys.numel() < n or self.mags.numel() < n * limbs:
+            cap = max(n + n // 8, 1)
+            self.keys = torch.empty(cap, dtype=torch.int64, device=device)
+            self.mags = torch.empty(cap * limbs, dtype=torch.int64, device=device)
+            self.signs = torch.empty(cap, dtype=torch.int8, device=device)
+        return self.keys[:n], self.mags[:n * limbs].view(n, limbs), self.signs[:n]
+
+
+def multiply_partitioned(ctx, da, db, device, group=None, gather: bool = True, workspace: "GatherWorkspace" = None, **opt):
+    """One multi-GPU product: this rank's partition through the C ABI, then the size + term gather (into `workspace`
+    when given: the returned tensors are then views that the next product overwrites)."""
+    import os
+    import time
+
+    trace = os.environ.get("PK_DIST_TRACE") and dist.get_rank(group) == 0
+    t = [time.perf_counter()]
+
+    def mark():
+        if trace:
+            torch.cuda.synchronize(device)
+            t.append(time.perf_counter())
+
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     part = ctx.mul_dev(da, db, part_index=rank, part_count=world, **opt)
+    mark()
     if not gather:
         return part, None
     counts, limbs = gather_sizes(len(part), max(1, part.limbs), device, group)
+    mark()
     off = _offsets(counts)
-    keys = torch.empty(off[-1], dtype=torch.int64, device=device)
-    mags = torch.empty((off[-1], limbs), dtype=torch.int64, device=device)
-    signs = torch.empty(off[-1], dtype=torch.int8, device=device)
+    if workspace is not None:
+        keys, mags, signs = workspace.get(off[-1], limbs, device)
+    else:
+        keys = torch.empty(off[-1], dtype=torch.int64, device=device)
+        mags = torch.empty((off[-1], limbs), dtype=torch.int64, device=device)
+        signs = torch.empty(off[-1], dtype=torch.int8, device=device)
+    mark()
     if counts[rank]:  # this rank's terms go straight into its slice of the result
         lo = off[rank]
         part.export_to(keys[lo:].data_ptr(), mags[lo:].data_ptr(), signs[lo:].data_ptr(), mag_limbs=limbs)
-    return part, exchange_slices(keys, mags, signs, counts, group)
+    mark()
+    out = exchange_slices(keys, mags, signs, counts, group)
+    mark()
+    if trace:
+        names = ("mul_dev", "sizes", "alloc", "export", "exchange")
+        print("[pk dist] " + "  ".join(f"{n} {1e3 * (b - a):.3f} ms" for n, a, b in zip(names, t, t[1:])), flush=True)
+    return part, out
