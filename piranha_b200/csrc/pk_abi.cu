@@ -298,8 +298,9 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
     const u64 *mB = B->planes;
     u64 strideB = B->stride;
     std::unique_ptr<DevBuf> keyB2, magB2, slbuf, degBs;
-    if (trunc) {
-        // second operand stable-sorted by degree (polynomial.hpp:1427-1442), then the skip limits
+    // The HBM-accumulator kernels truncate per row: second operand stable-sorted by degree (polynomial.hpp:1427-1442),
+    // then the skip limits.  Only built when those kernels run (the block path prunes per tile instead).
+    auto prepare_degree_sorted = [&]() {
         DevBuf fd(ctx, nB * 8), idx(ctx, nB * 4), idx2(ctx, nB * 4);
         degBs.reset(new DevBuf(ctx, nB * 8));
         PK_LAUNCH(ctx, k_flip_deg, grid_for(nB, 256), 256, 0, degB.as<i64>(), fd.as<u64>(), nB);
@@ -316,10 +317,10 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
         slbuf.reset(new DevBuf(ctx, nA * 4));
         PK_LAUNCH(ctx, k_skip_limits, grid_for(nA, 256), 256, 0, degA.as<i64>(), nA, degBs->as<u64>(), nB, o.max_degree,
                   slbuf->as<u32>(), ctx->d_ctr);
-    }
+    };
 
     // ---- output partition [lo, hi) in tight-code space
-    BlockPlan bp = trunc ? BlockPlan{} : block_plan(ctx, pl, nA, nB);
+    BlockPlan bp = block_plan(ctx, pl, nA, nB);
     // a partitioned product uses the block geometry only when every part gets many whole blocks (else the rounding
     // of the cuts would unbalance the parts); a function of the operands and P only, so all ranks agree
     if (bp.ok && P > 1 && pl.range / bp.S < 256ull * P) bp.ok = false;
@@ -329,13 +330,7 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
         const u32 SA = (u32)std::min<u64>(nA, 512), SB = (u32)std::min<u64>(nB, 512);
         const u64 S = (u64)SA * SB;
         DevBuf sums(ctx, S * 8), sorted(ctx, S * 8), dcuts(ctx, ((size_t)P + 1) * 8);
-        // degrees of B in its (possibly degree-sorted) order are needed for the truncation filter of the sample
-        DevBuf degB_perm(ctx, trunc ? nB * 8 : 0);
-        const i64 *dB = degB.as<i64>();
-        if (trunc) { // degBs holds flipped sorted degrees; unflip into degB_perm
-            PK_LAUNCH(ctx, k_flip_deg, grid_for(nB, 256), 256, 0, (const i64 *)degBs->as<u64>(), degB_perm.as<u64>(), nB);
-            dB = degB_perm.as<i64>();
-        }
+        const i64 *dB = degB.as<i64>(); // (both operands are still in code order here: keys and degrees match)
         PK_LAUNCH(ctx, k_sample_sums, grid_for(S, 256), 256, 0, keyA.as<u64>(), nA, kB, nB, SA, SB, degA.as<i64>(), dB,
                   o.max_degree, trunc ? 1 : 0, sums.as<u64>(), ctx->d_ctr);
         // (excluded pairs carry the all-ones sentinel and sort last: every bit of the key takes part)
@@ -361,14 +356,17 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
     const unsigned __int128 w_bound = (unsigned __int128)nA * nB;
     u32 algo = o.algo;
     if (algo == PK_ALGO_AUTO) {
-        algo = choose_algo(ctx, pl, nA, nB, sub_range, trunc);
-        if (algo == PK_ALGO_ZONE && bp.ok && sub_range) algo = PK_ALGO_BLOCK;
+        if (w_bound >= (1u << 16) && bp.ok && sub_range) algo = PK_ALGO_BLOCK;
+        else algo = choose_algo(ctx, pl, nA, nB, sub_range, trunc);
     }
     pk_dpoly *result = nullptr;
     if (algo == PK_ALGO_BLOCK) {
-        if (bp.ok && sub_range) result = block_multiply(ctx, pl, bp, A, B, keyA.as<u64>(), kB, lo, hi, nv);
+        if (bp.ok && sub_range)
+            result = block_multiply(ctx, pl, bp, A, B, keyA.as<u64>(), keyB.as<u64>(), lo, hi, nv, trunc ? degA.as<i64>() : nullptr,
+                                    trunc ? degB.as<i64>() : nullptr, o.max_degree, filter);
         if (!result) algo = PK_ALGO_ZONE; // no block geometry for these operands (or tiny groups): generic zones
     }
+    if (trunc && !result) prepare_degree_sorted();
     if (algo == PK_ALGO_ZONE) {
         result = zone_multiply(ctx, pl, A, B, keyA.as<u64>(), kB, mB, strideB, trunc ? slbuf->as<u32>() : nullptr, lo, hi,
                                trunc, nv);

@@ -26,6 +26,8 @@
 namespace pk
 {
 
+struct TruncDev;
+
 struct BlockArgs {
     ZoneArgs z;           // operands, accumulator geometry, output staging (shared with the zone path)
     const uint4 *tiles;   // {a0, b0, an | bn << 10, block index relative to h_base}, grouped by block
@@ -35,18 +37,90 @@ struct BlockArgs {
     u32 h_base, n_h;      // blocks [h_base, h_base + n_h) belong to this call's partition
     u32 Hz;               // blocks per zone
     u32 S;                // codes per block
+    const TruncDev *trunc; // degree truncation (nullptr = none)
 };
+
+// Degree truncation in the block path (polynomial.hpp:1402-1531 restated per tile).  Records carry the term's degree as
+// an offset from its operand's smallest degree; a pair (i, j) is multiplied iff off_a + off_b <= dlim, where
+// dlim = max_degree - min_deg_a - min_deg_b.  Groups record their smallest and largest offset, so a pair of groups is
+// dropped (no tile) when even its smallest degrees exceed the limit and walked without any test when its largest fit.
+struct TruncDev {
+    i64 min_a, max_a, min_b, max_b; // degree extremes of the operands
+    u32 dlim;                       // limit on the sum of offsets
+    u32 none;                       // 1 = no pair can pass (the limit is below the smallest degree sum)
+};
+
+__global__ void k_trunc_init(TruncDev *t)
+{
+    t->min_a = t->min_b = INT64_MAX;
+    t->max_a = t->max_b = INT64_MIN;
+    t->dlim = 0;
+    t->none = 0;
+}
+
+__global__ void k_deg_minmax(const i64 *__restrict__ deg, u32 n, i64 *mn, i64 *mx)
+{
+    i64 lo = INT64_MAX, hi = INT64_MIN;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const i64 d = deg[i];
+        lo = min(lo, d);
+        hi = max(hi, d);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31u) == 0) {
+        atomicMin(mn, lo);
+        atomicMax(mx, hi);
+    }
+}
+
+// dlim, and the reference's checked subtraction max_degree - d1 over the first operand (degree_sub -> safe_int_sub,
+// polynomial.hpp:1243-1252, :1504): it overflows for some term iff it overflows at one of the two extremes.
+__global__ void k_trunc_limits(TruncDev *t, i64 max_degree, MulCounters *ctr)
+{
+    const i64 ext[2] = {t->min_a, t->max_a};
+    for (int k = 0; k < 2; ++k) {
+        const i64 c = (i64)((u64)max_degree - (u64)ext[k]);
+        if (((max_degree ^ ext[k]) & (max_degree ^ c)) < 0) atomicOr(&ctr->flags, kFlagDegreeOverflow);
+    }
+    const __int128 lim = (__int128)max_degree - t->min_a - t->min_b;
+    if (lim < 0) {
+        t->none = 1;
+        t->dlim = 0;
+    } else {
+        t->dlim = lim > (__int128)0xFFFFFFFEu ? 0xFFFFFFFEu : (u32)lim;
+    }
+}
+
+// packed record with the degree offset: y = sign | offset << 1
+__global__ void k_pack_operand_deg(const u64 *__restrict__ key, const u64 *__restrict__ m0, const i64 *__restrict__ deg,
+                                   const i64 *__restrict__ deg_min, uint4 *__restrict__ out, u64 n)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const u64 k = key[i], m = m0[i];
+        const u32 off = (u32)(deg[i] - *deg_min); // < 2^31: checked on the host from the exponent bounds
+        out[i] = make_uint4((u32)(k & 0xFFFFFFFFull), (u32)(k >> 63) | (off << 1), (u32)m, (u32)(m >> 32));
+    }
+}
 
 // code / S for 32-bit codes with magic = floor(2^64 / S) + 1
 __device__ __forceinline__ u32 div_magic(u32 x, u64 magic) { return (u32)__umul64hi((u64)x, magic); }
 
 // Group table of one operand: tab[hi] = {first term, one past the last term}; glist = the hi values that occur.
 __global__ void k_block_groups(const uint4 *__restrict__ rec, u32 n, u64 magicS, uint2 *__restrict__ tab,
-                               u32 *__restrict__ glist, u32 *__restrict__ gcount)
+                               u32 *__restrict__ glist, u32 *__restrict__ gcount, uint2 *__restrict__ gdeg)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const u32 hi = div_magic(__ldg(&rec[i].x), magicS);
+    if (gdeg) { // truncation: {smallest, ~largest} degree offset of the group (both by atomicMin from an all-ones fill)
+        const u32 off = __ldg(&rec[i].y) >> 1;
+        atomicMin(&gdeg[hi].x, off);
+        atomicMin(&gdeg[hi].y, ~off);
+    }
     const u32 prev = i ? div_magic(__ldg(&rec[i - 1].x), magicS) : 0xFFFFFFFFu;
     const u32 next = (i + 1 < n) ? div_magic(__ldg(&rec[i + 1].x), magicS) : 0xFFFFFFFFu;
     if (hi != prev) {
@@ -66,6 +140,8 @@ struct TileArgs {
     u32 Hz;
     u32 target;      // products per tile
     u32 wide;        // 1 = use 64-term chunks of gb (two terms per lane)
+    const uint2 *gdegA, *gdegB; // truncation: degree offset extremes per group (nullptr = untruncated)
+    const TruncDev *trunc;
     u32 *cnt;        // tiles per block (count pass) / cursor per block (scatter pass)
     u64 *zwork;      // products per zone
     const u32 *tstart;
@@ -91,6 +167,14 @@ __global__ void k_block_tiles(const TileArgs t)
     const u32 hr = h - t.h_base;
     const uint2 ra = __ldg(&t.tabA[ha]), rb = __ldg(&t.tabB[hb]);
     const u32 na = ra.y - ra.x, nb = rb.y - rb.x;
+    u32 filt = 0; // bit 31 of the tile word: products of the tile need the degree test
+    if (t.trunc) {
+        if (t.trunc->none) return;
+        const uint2 da = __ldg(&t.gdegA[ha]), db = __ldg(&t.gdegB[hb]);
+        const u32 dlim = t.trunc->dlim;
+        if ((u64)da.x + db.x > dlim) return; // degree pruning at tile level: not even the smallest degrees fit
+        if ((u64)(~da.y) + (~db.y) > dlim) filt = 0x80000000u;
+    }
     // gb = n64 chunks of 64 terms (two per lane) + at most one chunk of 32 (one per lane) + a ragged rest (flat)
     const u32 n64 = t.wide ? nb / 64u : 0u;
     const u32 n32 = (nb - n64 * 64u) / kTileCols, rem = nb - n64 * 64u - n32 * kTileCols;
@@ -111,12 +195,12 @@ __global__ void k_block_tiles(const TileArgs t)
         u32 k = pos, c0 = rb.x;
         for (u32 c = 0; c < n64; ++c, c0 += 64u)
             for (u32 r = 0; r < nrow_w; ++r, ++k)
-                t.tiles[k] = make_uint4(ra.x + r * rpt_w, c0, min(rpt_w, na - r * rpt_w) | (64u << 10), hr);
+                t.tiles[k] = make_uint4(ra.x + r * rpt_w, c0, min(rpt_w, na - r * rpt_w) | (64u << 10) | filt, hr);
         for (u32 c = 0; c < n32; ++c, c0 += kTileCols)
             for (u32 r = 0; r < nrow_f; ++r, ++k)
-                t.tiles[k] = make_uint4(ra.x + r * rpt_f, c0, min(rpt_f, na - r * rpt_f) | (kTileCols << 10), hr);
+                t.tiles[k] = make_uint4(ra.x + r * rpt_f, c0, min(rpt_f, na - r * rpt_f) | (kTileCols << 10) | filt, hr);
         for (u32 r = 0; r < nrow_r; ++r, ++k)
-            t.tiles[k] = make_uint4(ra.x + r * rpt_r, c0, min(rpt_r, na - r * rpt_r) | (rem << 10), hr);
+            t.tiles[k] = make_uint4(ra.x + r * rpt_r, c0, min(rpt_r, na - r * rpt_r) | (rem << 10) | filt, hr);
     }
 }
 
@@ -155,19 +239,24 @@ __global__ void k_block_natural_order(u32 nz, u32 *__restrict__ n_active, u32 *_
     *n_zones = nz;
 }
 
-template <bool FULL>
+// LOAD 0: the code only (bitmap marking), 1: code + sign/degree word (marking with the degree test), 2: whole record
+template <int LOAD>
 __device__ __forceinline__ uint4 block_load(const uint4 *p)
 {
-    if (FULL) return __ldg(p);
+    if (LOAD == 2) return __ldg(p);
+    if (LOAD == 1) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+        return make_uint4(v.x, v.y, 0u, 0u);
+    }
     return make_uint4(__ldg(&p->x), 0u, 0u, 0u);
 }
 
-// Visit every product of one tile: f(a_record, b_record).  FULL = false loads only the codes (bitmap marking).
-template <bool FULL, typename F>
+// Visit every product of one tile: f(a_record, b_record).  FULL selects how much of a record is loaded (block_load).
+template <int FULL, typename F>
 __device__ __forceinline__ void block_tile_loop(const uint4 *__restrict__ A, const uint4 *__restrict__ B, const uint4 t,
                                                 u32 lane, F &&f)
 {
-    const u32 a0 = t.x, b0 = t.y, an = t.z & 1023u, bn = t.z >> 10;
+    const u32 a0 = t.x, b0 = t.y, an = t.z & 1023u, bn = (t.z >> 10) & 127u;
     if (bn == 64u) {
         // two terms of gb per lane: one broadcast load of a row feeds 64 products
         const uint4 bv0 = block_load<FULL>(&B[b0 + lane]), bv1 = block_load<FULL>(&B[b0 + 32u + lane]);
@@ -299,6 +388,7 @@ __global__ void __launch_bounds__(1024, 1) k_block(const BlockArgs ba)
     u64 my_pairs = 0;
     u32 my_maxbits = 0, my_flags = 0;
     const u32 n_active = __ldg(ba.n_active);
+    const u32 dlim = ba.trunc ? __ldg(&ba.trunc->dlim) : 0xFFFFFFFFu;
 
     for (u32 i = tid; i < a.cap * NW; i += kThreads) acc[i] = 0;
     if (MODE == 1)
@@ -324,11 +414,20 @@ __global__ void __launch_bounds__(1024, 1) k_block(const BlockArgs ba)
             if (tid == 0) s_next = t0;
             __syncthreads();
             block_for_each_tile(ba.tiles, &s_next, t1, lane, [&](const uint4 &t) {
-                if (lane == 0) my_pairs += (u64)(t.z & 1023u) * (t.z >> 10);
-                block_tile_loop<false>(a.A, a.B, t, lane, [&](const uint4 &av, const uint4 &bv) {
-                    const u32 slot = av.x + bv.x - zlo;
-                    reds_or(bm_s + (slot >> 5) * 8u, 1u << (slot & 31u));
-                });
+                if (t.z >> 31) { // truncation: some products of this tile exceed the degree limit
+                    block_tile_loop<1>(a.A, a.B, t, lane, [&](const uint4 &av, const uint4 &bv) {
+                        if ((av.y >> 1) + (bv.y >> 1) > dlim) return;
+                        ++my_pairs;
+                        const u32 slot = av.x + bv.x - zlo;
+                        reds_or(bm_s + (slot >> 5) * 8u, 1u << (slot & 31u));
+                    });
+                } else {
+                    if (lane == 0) my_pairs += (u64)(t.z & 1023u) * ((t.z >> 10) & 127u);
+                    block_tile_loop<0>(a.A, a.B, t, lane, [&](const uint4 &av, const uint4 &bv) {
+                        const u32 slot = av.x + bv.x - zlo;
+                        reds_or(bm_s + (slot >> 5) * 8u, 1u << (slot & 31u));
+                    });
+                }
             });
             __syncthreads();
             // exclusive popcount prefix per bitmap word
@@ -397,24 +496,33 @@ __global__ void __launch_bounds__(1024, 1) k_block(const BlockArgs ba)
             }
             if (tid == 0) s_next = tp0;
             __syncthreads();
+            auto accumulate = [&](const uint4 &av, const uint4 &bv) {
+                const u32 code = av.x + bv.x;
+                if (MODE == 1 && !single && (code < c0 || code >= c1)) return;
+                const u32 slot = code - zlo;
+                u32 e;
+                if (MODE == 1) {
+                    const uint2 bw = bm[slot >> 5];
+                    e = bw.y + __popc(bw.x & ((1u << (slot & 31u)) - 1u)) - r0;
+                } else {
+                    e = slot;
+                }
+                const u64 ma = (u64)av.z | ((u64)av.w << 32), mb = (u64)bv.z | ((u64)bv.w << 32);
+                const u64 plo = ma * mb, phi = __umul64hi(ma, mb);
+                block_accumulate<NW, PW, SIGNED>(acc_s + e * 4u, wstride, (u32)plo, (u32)(plo >> 32), (u32)phi,
+                                                 (u32)(phi >> 32), SIGNED && (((av.y ^ bv.y) & 1u) != 0));
+            };
             block_for_each_tile(ba.tiles, &s_next, tp1, lane, [&](const uint4 &t) {
-                if (MODE == 0 && lane == 0) my_pairs += (u64)(t.z & 1023u) * (t.z >> 10);
-                block_tile_loop<true>(a.A, a.B, t, lane, [&](const uint4 &av, const uint4 &bv) {
-                    const u32 code = av.x + bv.x;
-                    if (MODE == 1 && !single && (code < c0 || code >= c1)) return;
-                    const u32 slot = code - zlo;
-                    u32 e;
-                    if (MODE == 1) {
-                        const uint2 bw = bm[slot >> 5];
-                        e = bw.y + __popc(bw.x & ((1u << (slot & 31u)) - 1u)) - r0;
-                    } else {
-                        e = slot;
-                    }
-                    const u64 ma = (u64)av.z | ((u64)av.w << 32), mb = (u64)bv.z | ((u64)bv.w << 32);
-                    const u64 plo = ma * mb, phi = __umul64hi(ma, mb);
-                    block_accumulate<NW, PW, SIGNED>(acc_s + e * 4u, wstride, (u32)plo, (u32)(plo >> 32), (u32)phi,
-                                                     (u32)(phi >> 32), SIGNED && ((av.y ^ bv.y) != 0));
-                });
+                if (t.z >> 31) { // truncation: test the degree of every product of this tile
+                    block_tile_loop<2>(a.A, a.B, t, lane, [&](const uint4 &av, const uint4 &bv) {
+                        if ((av.y >> 1) + (bv.y >> 1) > dlim) return;
+                        if (MODE == 0) ++my_pairs;
+                        accumulate(av, bv);
+                    });
+                } else {
+                    if (MODE == 0 && lane == 0) my_pairs += (u64)(t.z & 1023u) * ((t.z >> 10) & 127u);
+                    block_tile_loop<2>(a.A, a.B, t, lane, accumulate);
+                }
             });
             __syncthreads();
 
@@ -649,9 +757,20 @@ inline bool block_layout(pk_ctx *ctx, BlockPlan &bp, u32 Hz)
 // Returns the product restricted to [lo, hi) (both multiples of S), or nullptr when the operands do not suit the
 // block path (tiny groups); the caller then uses the generic zone path.
 inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const pk_dpoly *A, const pk_dpoly *B,
-                                const u64 *keyA, const u64 *keyB, u64 lo, u64 hi, u32 nv)
+                                const u64 *keyA, const u64 *keyB, u64 lo, u64 hi, u32 nv, const i64 *degA, const i64 *degB,
+                                i64 max_degree, bool count_pairs)
 {
+    (void)count_pairs;
     const u64 nA = A->n, nB = B->n;
+    const bool trunc = degA != nullptr;
+    if (trunc) { // degree offsets are 31-bit: bound the degree span of each operand by its exponent spans
+        for (const pk_dpoly *P : {A, B}) {
+            unsigned __int128 span = 0;
+            for (u32 v = 0; v < nv; ++v)
+                if (pl.cpA.mask[v]) span += (unsigned __int128)((__int128)P->emax[v] - P->emin[v]);
+            if (span >= ((unsigned __int128)1 << 31)) return nullptr;
+        }
+    }
     const BlockTuning &bt = ctx->block_tuning;
     const u32 S = bp.S;
     if (lo % S != 0 || (hi % S != 0 && hi != pl.range) || hi <= lo) return nullptr;
@@ -661,21 +780,35 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     const u64 out_cap = (u64)std::min<unsigned __int128>(w_bound, hi - lo);
     if ((unsigned __int128)out_cap * (9 + 8 * pl.out_limbs) > (unsigned __int128)ctx->total_mem / 2) return nullptr;
 
-    DevBuf pa(ctx, (nA + 1) * 16), pb(ctx, (nB + 1) * 16);
-    PK_LAUNCH(ctx, k_pack_operand, grid_for(nA, 256), 256, 0, keyA, A->planes, pa.as<uint4>(), nA);
-    PK_LAUNCH(ctx, k_pack_operand, grid_for(nB, 256), 256, 0, keyB, B->planes, pb.as<uint4>(), nB);
+    const u64 HR = pl.range / S + 2;
+    DevBuf pa(ctx, (nA + 1) * 16), pb(ctx, (nB + 1) * 16), tdev(ctx, trunc ? sizeof(TruncDev) : 0);
+    DevBuf gdegA(ctx, trunc ? HR * 8 : 0), gdegB(ctx, trunc ? HR * 8 : 0);
+    TruncDev *td = tdev.as<TruncDev>();
+    if (trunc) {
+        PK_LAUNCH(ctx, k_trunc_init, 1, 1, 0, td);
+        const u32 rg = std::min<u32>(grid_for(std::max(nA, nB), 256), (u32)ctx->sm_count * 4);
+        PK_LAUNCH(ctx, k_deg_minmax, rg, 256, 0, degA, (u32)nA, &td->min_a, &td->max_a);
+        PK_LAUNCH(ctx, k_deg_minmax, rg, 256, 0, degB, (u32)nB, &td->min_b, &td->max_b);
+        PK_LAUNCH(ctx, k_trunc_limits, 1, 1, 0, td, max_degree, ctx->d_ctr);
+        PK_LAUNCH(ctx, k_pack_operand_deg, grid_for(nA, 256), 256, 0, keyA, A->planes, degA, &td->min_a, pa.as<uint4>(), nA);
+        PK_LAUNCH(ctx, k_pack_operand_deg, grid_for(nB, 256), 256, 0, keyB, B->planes, degB, &td->min_b, pb.as<uint4>(), nB);
+        CUDA_CHECK(cudaMemsetAsync(gdegA.p, 0xFF, HR * 8, ctx->stream));
+        CUDA_CHECK(cudaMemsetAsync(gdegB.p, 0xFF, HR * 8, ctx->stream));
+    } else {
+        PK_LAUNCH(ctx, k_pack_operand, grid_for(nA, 256), 256, 0, keyA, A->planes, pa.as<uint4>(), nA);
+        PK_LAUNCH(ctx, k_pack_operand, grid_for(nB, 256), 256, 0, keyB, B->planes, pb.as<uint4>(), nB);
+    }
 
     // ---- groups of equal hi
     const u64 magicS = (u64)((((unsigned __int128)1) << 64) / S) + 1;
-    const u64 HR = pl.range / S + 2;
     DevBuf tabA(ctx, HR * 8), tabB(ctx, HR * 8), glA(ctx, nA * 4), glB(ctx, nB * 4), gcnt(ctx, 16);
     CUDA_CHECK(cudaMemsetAsync(tabA.p, 0, HR * 8, ctx->stream));
     CUDA_CHECK(cudaMemsetAsync(tabB.p, 0, HR * 8, ctx->stream));
     CUDA_CHECK(cudaMemsetAsync(gcnt.p, 0, 16, ctx->stream));
     PK_LAUNCH(ctx, k_block_groups, grid_for(nA, 256), 256, 0, pa.as<uint4>(), (u32)nA, magicS, tabA.as<uint2>(), glA.as<u32>(),
-              gcnt.as<u32>());
+              gcnt.as<u32>(), trunc ? gdegA.as<uint2>() : nullptr);
     PK_LAUNCH(ctx, k_block_groups, grid_for(nB, 256), 256, 0, pb.as<uint4>(), (u32)nB, magicS, tabB.as<uint2>(), glB.as<u32>(),
-              gcnt.as<u32>() + 1);
+              gcnt.as<u32>() + 1, trunc ? gdegB.as<uint2>() : nullptr);
     u32 *hg = reinterpret_cast<u32 *>(static_cast<char *>(ctx->h_scratch) + 2048);
     CUDA_CHECK(cudaMemcpyAsync(hg, gcnt.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -736,6 +869,9 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     ta.Hz = (u32)Hz;
     ta.target = bt.tile_target;
     ta.wide = bt.wide;
+    ta.gdegA = trunc ? gdegA.as<uint2>() : nullptr;
+    ta.gdegB = trunc ? gdegB.as<uint2>() : nullptr;
+    ta.trunc = trunc ? td : nullptr;
     ta.cnt = cnt.as<u32>();
     ta.zwork = zwork;
     ta.tstart = tstart.as<u32>();
@@ -791,6 +927,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     ba.n_h = n_h;
     ba.Hz = (u32)Hz;
     ba.S = S;
+    ba.trunc = trunc ? td : nullptr;
     const bool is_signed = A->any_neg || B->any_neg;
     const u32 grid = std::min<u32>(bp.grid, nz);
     CUDA_CHECK(cudaEventRecord(ctx->ev_mul0, ctx->stream));

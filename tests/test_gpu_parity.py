@@ -281,6 +281,55 @@ def test_block_variants(tuning, case):
         c2.close()
 
 
+@pytest.mark.parametrize("tuning", [
+    dict(block_mode=1),
+    dict(block_mode=2),
+    dict(block_mode=2, block_hz=4, zone_cap=41),     # multi-pass bitmap zones with the degree test
+    dict(block_mode=1, block_target=32, block_wide=0),
+])
+@pytest.mark.parametrize("case", ["total", "partial", "laurent", "none_pass", "all_pass"])
+def test_block_truncation(tuning, case):
+    """Degree truncation inside the block kernel (tile-level pruning + per-product test on straddling tiles)."""
+    rs = np.random.RandomState(5)
+    nv = 4
+    if case == "laurent":
+        f = {(int(a) - 6, int(b), int(c) - 3, int(d)): int(v) - 50 or 1 for a, b, c, d, v in rs.randint(0, 12, size=(900, 5)) * [1, 1, 1, 1, 9]}
+        g = {(int(a), int(b) - 5, int(c), int(d) - 2): int(v) + 1 for a, b, c, d, v in rs.randint(0, 12, size=(700, 5))}
+        opt = dict(trunc_mode=1, max_degree=7)
+    else:
+        f, g = po.fateman_operands(7)
+        g = {k: (-v if sum(k) % 3 == 0 else v) for k, v in g.items()}
+        opt = {"total": dict(trunc_mode=1, max_degree=9), "partial": dict(trunc_mode=2, max_degree=5, degree_mask=[1, 0, 1, 0]),
+               "none_pass": dict(trunc_mode=1, max_degree=-1), "all_pass": dict(trunc_mode=1, max_degree=1000)}[case]
+    c2 = pb.Context(0)
+    try:
+        c2.set_tuning(block_min_tile=0, **tuning)
+        a, b = terms(f, nv, 1), terms(g, nv, 2)
+        r = c2.mul(a, b, nv, algo=pb.PK_ALGO_BLOCK, **opt)
+        st = c2.stats()
+        assert st["algo"] == pb.PK_ALGO_BLOCK
+        assert_sorted_unique(r[0])
+        kw = dict(trunc_mode=opt["trunc_mode"], max_degree=opt["max_degree"])
+        if "degree_mask" in opt:
+            kw["deg_mask"] = opt["degree_mask"]
+        assert_terms_equal(r, cpu_ref(a, b, nv, n_threads=4, **kw))
+        # the pairs actually multiplied are exactly those within the degree limit
+        mask = opt.get("degree_mask", [1] * nv)
+        da = np.array([sum(e for e, m in zip(k, mask) if m) for k in f])
+        db = np.array([sum(e for e, m in zip(k, mask) if m) for k in g])
+        assert st["term_products"] == int((da[:, None] + db[None, :] <= opt["max_degree"]).sum())
+    finally:
+        c2.close()
+
+
+def test_block_truncation_degree_overflow(ctx):
+    # the checked subtraction max_degree - d1 (polynomial.hpp:1243-1252) also guards the block path
+    f, g = po.fateman_operands(6)
+    f = {(k[0] - 3, k[1], k[2], k[3]): v for k, v in f.items()}
+    with pytest.raises(OverflowError):
+        ctx.mul(terms(f, 4, 1), terms(g, 4, 2), 4, trunc_mode=1, max_degree=2 ** 63 - 1, algo=pb.PK_ALGO_BLOCK)
+
+
 def test_block_declines_without_a_digit_split(ctx):
     # one variable: there is no hi digit, the generic zone path takes over
     f = {(i,): i + 1 for i in range(0, 3000, 3)}

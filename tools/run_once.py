@@ -8,11 +8,12 @@ from bench import build_operands
 
 def main():
     args = sys.argv[1:]
-    iters, algo, tuning, wl = 3, pb.PK_ALGO_AUTO, {}, []
+    iters, algo, tuning, wl, trunc = 3, pb.PK_ALGO_AUTO, {}, [], None
     i = 0
     while i < len(args):
         a = args[i]
         if a == "--iters": iters = int(args[i + 1]); i += 2; continue
+        if a == "--trunc": trunc = int(args[i + 1]); i += 2; continue
         if a == "--algo": algo = {v: k for k, v in pb.ALGO_NAMES.items()}[args[i + 1]]; i += 2; continue
         if "=" in a: k, v = a.split("="); tuning[k] = int(v)
         else: wl.append(a)
@@ -24,7 +25,7 @@ def main():
         da, db = ctx.upload(a, nv), ctx.upload(b, nv)
         ks, ds = [], []
         for it in range(iters):
-            r = ctx.mul_dev(da, db, algo=algo)
+            r = ctx.mul_dev(da, db, algo=algo, **(dict(trunc_mode=1, max_degree=trunc) if trunc is not None else {}))
             st = ctx.stats()
             ks.append(st["mul_kernel_ms"]); ds.append(st["device_ms"])
         W = st["term_products"]
