@@ -140,7 +140,9 @@ int pk_get_stats(pk_ctx *ctx, pk_stats *out);
  * block: 0 auto, 256, 512, 1024), "zone_uniform" (1 = equal-span zones instead of equal-work zones); for the block
  * path "block_disable", "block_target" (products per tile), "block_zone_work" (products per zone aimed at),
  * "block_min_tile", "block_mode" (0 auto, 1 dense, 2 bitmap), "block_hz" (blocks per zone),
- * "block_natural" (1 = zones claimed in code order instead of heaviest first).
+ * "block_natural" (1 = zones claimed in code order instead of heaviest first); for pk_mul "pipe_parts" (output parts
+ * of a pipelined product whose device-to-host copy overlaps the computation of the next part; 0 = off, the default) and
+ * "pipe_min_products".
  * Never changes results, only how they are computed. */
 int pk_ctx_set_tuning(pk_ctx *ctx, const char *key, uint64_t value);
 

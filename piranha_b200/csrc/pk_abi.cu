@@ -57,7 +57,7 @@ void ensure_meta(pk_ctx *ctx, pk_dpoly *p)
     fill_piranha_codec(ctx, nv, cp);
     const u32 grid = std::min<u32>(grid_for(p->n, 256), (u32)ctx->sm_count * 8);
     PK_LAUNCH(ctx, k_meta, grid, 256, 0, p->key, p->planes, p->sign, p->n, p->limbs, p->stride, cp, ctx->d_meta);
-    CUDA_CHECK(cudaMemcpyAsync(ctx->h_scratch, ctx->d_meta, sizeof(MetaDev), cudaMemcpyDeviceToHost, ctx->stream));
+    readback(ctx, ctx->h_scratch, ctx->d_meta, sizeof(MetaDev));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     const MetaDev *m = static_cast<const MetaDev *>(ctx->h_scratch);
     for (u32 v = 0; v < nv; ++v) {
@@ -337,7 +337,7 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
         radix_sort_keys(ctx, sums.as<u64>(), sorted.as<u64>(), S, 64);
         PK_LAUNCH(ctx, k_pick_cuts, 1, 64, 0, sorted.as<u64>(), ctx->d_ctr, P, dcuts.as<u64>());
         u64 *cuts = reinterpret_cast<u64 *>(static_cast<char *>(ctx->h_scratch) + 1024);
-        CUDA_CHECK(cudaMemcpyAsync(cuts, dcuts.p, ((size_t)P + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        readback(ctx, cuts, dcuts.p, ((size_t)P + 1) * 8);
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         cuts[0] = 0;
         cuts[P] = pl.range;
@@ -422,7 +422,7 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
             f.block_offsets = offsets.as<u64>();
             PK_LAUNCH(ctx, k_dense_count, nblocks, kFinThreads, 0, f);
             PK_LAUNCH(ctx, k_scan_counts, 1, 1024, 0, counts.as<u32>(), offsets.as<u64>(), (u64)nblocks, ctx->d_ctr);
-            CUDA_CHECK(cudaMemcpyAsync(hc, ctx->d_ctr, sizeof(MulCounters), cudaMemcpyDeviceToHost, ctx->stream));
+            readback(ctx, hc, ctx->d_ctr, sizeof(MulCounters));
             CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
             const u64 n_out = hc->n_out;
             DPolyGuard g{ctx, new_dpoly(ctx, n_out, nv, pl.out_limbs)};
@@ -465,7 +465,7 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
                 slots(ctx, (size_t)std::min<unsigned __int128>(distinct, cap) * 4);
             const u32 cgrid = std::min<u32>(grid_for(cap, 256), (u32)ctx->sm_count * 16);
             PK_LAUNCH(ctx, k_hash_collect, cgrid, 256, 0, f, codes.as<u64>(), slots.as<u32>());
-            CUDA_CHECK(cudaMemcpyAsync(hc, ctx->d_ctr, sizeof(MulCounters), cudaMemcpyDeviceToHost, ctx->stream));
+            readback(ctx, hc, ctx->d_ctr, sizeof(MulCounters));
             CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
             const u64 n_out = hc->n_out;
             DPolyGuard g{ctx, new_dpoly(ctx, n_out, nv, pl.out_limbs)};
@@ -488,7 +488,7 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
     DPolyGuard rg{ctx, result};
     CUDA_CHECK(cudaEventRecord(ctx->ev_end, ctx->stream));
     MulCounters *hc = static_cast<MulCounters *>(ctx->h_scratch);
-    CUDA_CHECK(cudaMemcpyAsync(hc, ctx->d_ctr, sizeof(MulCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    readback(ctx, hc, ctx->d_ctr, sizeof(MulCounters));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     ctx->ev_valid = true;
     if (hc->flags & kFlagDegreeOverflow) fail(PK_E_DEGREE, "overflow in the truncation degree arithmetic");
@@ -577,6 +577,7 @@ int pk_ctx_create(int device, void *stream, pk_ctx **out)
     }
     zone_configure(c.get());
     block_configure(c.get());
+    c->pipe_parts = env_u32("PK_PIPE_PARTS", c->pipe_parts);
     *out = c.release();
     return PK_OK;
 }
@@ -596,6 +597,8 @@ void pk_ctx_destroy(pk_ctx *ctx)
     if (ctx->ev_mul0) cudaEventDestroy(ctx->ev_mul0);
     if (ctx->ev_mul1) cudaEventDestroy(ctx->ev_mul1);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->ev_part) cudaEventDestroy(ctx->ev_part);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -656,6 +659,9 @@ int pk_ctx_set_tuning(pk_ctx *ctx, const char *key, uint64_t value)
     else if (k == "block_mode") ctx->block_tuning.force_mode = (u32)value;
     else if (k == "block_hz") ctx->block_tuning.force_hz = (u32)value;
     else if (k == "block_natural") ctx->block_tuning.natural = (u32)value;
+    else if (k == "pipe_parts") ctx->pipe_parts = (u32)std::min<uint64_t>(value, 64);
+    else if (k == "pipe_min_products") ctx->pipe_min_products = value;
+    else if (k == "pipe_test_small") ctx->pipe_test_small = (u32)value;
     else if (k == "block_wide") ctx->block_tuning.wide = (u32)value;
     else if (k == "block_radix0") ctx->block_tuning.radix0_residue = std::min<u32>(32, (u32)value);
     else return PK_E_ARGS;
@@ -741,11 +747,152 @@ int pk_dpoly_digest(pk_ctx *ctx, const pk_dpoly *p, uint64_t *digest_out)
             PK_LAUNCH(ctx, k_digest, grid, 256, 0, p->key, p->planes, p->sign, p->n, p->limbs,
                       p->stride, ctx->d_digest);
         }
-        CUDA_CHECK(cudaMemcpyAsync(ctx->h_scratch, ctx->d_digest, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        readback(ctx, ctx->h_scratch, ctx->d_digest, 8);
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         *digest_out = *static_cast<uint64_t *>(ctx->h_scratch);
     })
 }
+
+namespace
+{
+
+// A product whose result is large next to its work (sparse output range) is bound by the device-to-host copy of the
+// result.  Such a product is computed in `pipe_parts` consecutive output ranges (the same partition mechanism the
+// ranks of a multi-GPU product use), and the terms of part p travel to the host on a second stream while part p+1 is
+// being computed.  Parts are ordered ranges, so they land back to back in the host arrays and the result is sorted.
+bool should_pipeline(pk_ctx *ctx, const pk_dpoly *a, const pk_dpoly *b, const pk_opts *opts)
+{
+    if (ctx->pipe_parts < 2 || !a->n || !b->n || a->n_vars != b->n_vars) return false;
+    if (opts && (opts->part_count > 1 || opts->trunc_mode != 0)) return false;
+    const unsigned __int128 W = (unsigned __int128)a->n * b->n;
+    if (W < ctx->pipe_min_products) return false;
+    unsigned __int128 range = 1; // tight code range of the product (as in make_plan)
+    for (u32 v = 0; v < a->n_vars; ++v) {
+        u64 g = gcd64(a->egcd[v], b->egcd[v]);
+        if (!g) g = 1;
+        range *= ((u64)(a->emax[v] - a->emin[v]) + (u64)(b->emax[v] - b->emin[v])) / g + 1;
+        if (range >= ((unsigned __int128)1 << 62)) break;
+    }
+    return range > 3 * W; // same test that selects bitmap zones: the result has about as many terms as products allow
+}
+
+void collect_part_stats(pk_ctx *ctx, pk_stats &acc)
+{
+    float ms = 0.f;
+    if (ctx->ev_valid) {
+        if (cudaEventElapsedTime(&ms, ctx->ev_mul0, ctx->ev_mul1) == cudaSuccess) acc.mul_kernel_ms += ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end) == cudaSuccess) acc.device_ms += ms;
+    }
+    const pk_stats &s = ctx->stats;
+    acc.n1 = s.n1;
+    acc.n2 = s.n2;
+    acc.term_products += s.term_products;
+    acc.result_terms += s.result_terms;
+    acc.code_range = s.code_range;
+    acc.table_slots = s.table_slots;
+    acc.algo = s.algo;
+    acc.acc_lanes = s.acc_lanes;
+    acc.chunk_bits = s.chunk_bits;
+    acc.result_limbs = std::max(acc.result_limbs, s.result_limbs);
+    acc.kernel_launches += s.kernel_launches;
+    acc.retries = s.retries;
+}
+
+void mul_pipelined(pk_ctx *ctx, pk_dpoly *da, pk_dpoly *db, const pk_opts *opts, pk_result *out)
+{
+    const u32 P = ctx->pipe_parts;
+    if (!ctx->copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!ctx->ev_part) CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_part, cudaEventDisableTiming));
+    struct Parts {
+        pk_ctx *ctx;
+        std::vector<pk_dpoly *> v;
+        std::vector<void *> aos; // magnitude rows staged for the copies; released only after the copies are done (a
+                                 // stream-ordered free on the copy stream would make the next part's allocations wait
+                                 // for the copy)
+        ~Parts()
+        {
+            cudaStreamSynchronize(ctx->copy_stream); // copies may still read the parts
+            for (void *q : aos) cudaFreeAsync(q, ctx->stream);
+            for (pk_dpoly *p : v)
+                if (p) {
+                    free_dpoly_arrays(ctx, p);
+                    delete p;
+                }
+        }
+    } parts{ctx, {}};
+    pk_stats acc{};
+    PinnedBuf *pb = nullptr;
+    u64 cap = 0, off = 0;
+    u32 L = 1;
+    bool overflow = false;
+    char *base = nullptr;
+    auto copy_part = [&](const pk_dpoly *p, u64 at, cudaStream_t after) {
+        if (!p->n) return;
+        void *aos = nullptr;
+        CUDA_CHECK(cudaMallocAsync(&aos, p->n * L * 8, ctx->stream));
+        parts.aos.push_back(aos);
+        PK_LAUNCH(ctx, k_planes_to_aos, grid_for(p->n, 256), 256, 0, p->planes, static_cast<u64 *>(aos), p->n, p->limbs, p->stride, L);
+        CUDA_CHECK(cudaEventRecord(ctx->ev_part, ctx->stream));
+        CUDA_CHECK(cudaStreamWaitEvent(after, ctx->ev_part, 0));
+        CUDA_CHECK(cudaMemcpyAsync(base + at * 8, p->key, p->n * 8, cudaMemcpyDeviceToHost, after));
+        CUDA_CHECK(cudaMemcpyAsync(base + cap * 8 + at * L * 8, aos, p->n * L * 8, cudaMemcpyDeviceToHost, after));
+        CUDA_CHECK(cudaMemcpyAsync(base + cap * 8 + cap * L * 8 + at, p->sign, p->n, cudaMemcpyDeviceToHost, after));
+    };
+    try {
+        for (u32 p = 0; p < P; ++p) {
+            pk_opts o{};
+            if (opts) o = *opts;
+            o.struct_size = sizeof(pk_opts);
+            o.part_index = p;
+            o.part_count = P;
+            parts.v.push_back(mul_impl(ctx, da, db, &o));
+            pk_dpoly *part = parts.v.back();
+            collect_part_stats(ctx, acc);
+            if (p == 0) { // size the host arrays from the first part (parts are balanced by work, not by terms)
+                L = part->alloc_limbs;
+                cap = std::max<u64>(4096, (part->n * P) + (part->n * P) / 4 + 4096);
+                if (ctx->pipe_test_small) cap = std::max<u64>(1, part->n);
+                cap = (cap + 63) & ~63ull;
+                pb = pinned_acquire(ctx, cap * (9 + 8 * (size_t)L));
+                base = static_cast<char *>(pb->ptr);
+            }
+            if (off + part->n > cap) overflow = true;
+            if (!overflow) copy_part(part, off, ctx->copy_stream);
+            off += part->n;
+        }
+        CUDA_CHECK(cudaStreamSynchronize(ctx->copy_stream));
+        if (overflow) { // the estimate was too small: exact allocation, copy everything again
+            pb->in_use = false;
+            cap = (off + 63) & ~63ull;
+            pb = pinned_acquire(ctx, cap * (9 + 8 * (size_t)L));
+            base = static_cast<char *>(pb->ptr);
+            u64 at = 0;
+            for (pk_dpoly *part : parts.v) {
+                copy_part(part, at, ctx->stream);
+                at += part->n;
+            }
+            CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        }
+    } catch (...) {
+        if (pb) pb->in_use = false;
+        throw;
+    }
+    out->n = off;
+    out->n_vars = da->n_vars;
+    out->limbs = L;
+    if (off) {
+        out->key = reinterpret_cast<int64_t *>(base);
+        out->mag = reinterpret_cast<uint64_t *>(base + cap * 8);
+        out->sign = reinterpret_cast<int8_t *>(base + cap * 8 + cap * L * 8);
+        out->owner = pb->ptr;
+    } else if (pb) {
+        pb->in_use = false;
+    }
+    ctx->stats = acc;
+    ctx->ev_valid = false; // the per-part event times were summed above
+}
+
+} // namespace
 
 int pk_mul(pk_ctx *ctx, const pk_poly *a, const pk_poly *b, const pk_opts *opts, pk_result *out)
 {
@@ -755,8 +902,14 @@ int pk_mul(pk_ctx *ctx, const pk_poly *a, const pk_poly *b, const pk_opts *opts,
         cudaSetDevice(ctx->device);
         DPolyGuard da{ctx, upload_impl(ctx, a)};
         DPolyGuard db{ctx, (a == b) ? nullptr : upload_impl(ctx, b)};
-        DPolyGuard dr{ctx, mul_impl(ctx, da.p, db.p ? db.p : da.p, opts)};
-        download_impl(ctx, dr.p, out);
+        pk_dpoly *pa = da.p;
+        pk_dpoly *pb2 = db.p ? db.p : da.p;
+        if (should_pipeline(ctx, pa, pb2, opts)) {
+            mul_pipelined(ctx, pa, pb2, opts, out);
+        } else {
+            DPolyGuard dr{ctx, mul_impl(ctx, pa, pb2, opts)};
+            download_impl(ctx, dr.p, out);
+        }
     })
 }
 

@@ -810,7 +810,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     PK_LAUNCH(ctx, k_block_groups, grid_for(nB, 256), 256, 0, pb.as<uint4>(), (u32)nB, magicS, tabB.as<uint2>(), glB.as<u32>(),
               gcnt.as<u32>() + 1, trunc ? gdegB.as<uint2>() : nullptr);
     u32 *hg = reinterpret_cast<u32 *>(static_cast<char *>(ctx->h_scratch) + 2048);
-    CUDA_CHECK(cudaMemcpyAsync(hg, gcnt.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    readback(ctx, hg, gcnt.p, 8);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     const u32 GA = hg[0], GB = hg[1];
     const u64 pairs = (u64)GA * GB;
@@ -938,7 +938,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     CUDA_CHECK(cudaEventRecord(ctx->ev_mul1, ctx->stream));
     PK_LAUNCH(ctx, k_zone_scan, 1, 1024, 0, zone_count, zone_prefix, n_zones_dev, &ctx->d_ctr->n_out);
     MulCounters *hc = static_cast<MulCounters *>(ctx->h_scratch);
-    CUDA_CHECK(cudaMemcpyAsync(hc, ctx->d_ctr, sizeof(MulCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    readback(ctx, hc, ctx->d_ctr, sizeof(MulCounters));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     const u64 n_out = hc->n_out;
     if (n_out > out_cap || (hc->flags & kFlagTableFull)) fail(PK_E_CUDA, "block path: a count exceeds its bound (internal error)");

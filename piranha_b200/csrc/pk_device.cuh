@@ -219,6 +219,15 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
                  : "memory");
 }
 
+// Small read-backs (counters, cut points) are written to mapped pinned host memory by a kernel instead of going through
+// a copy engine: a DMA read-back queues behind any bulk device-to-host copy in flight (the pipelined pk_mul keeps one
+// running on a second stream), which stalled every such read-back for the length of that copy.
+__global__ void k_readback(u32 *__restrict__ host_dst, const u32 *__restrict__ dev_src, u32 n_words)
+{
+    for (u32 i = threadIdx.x; i < n_words; i += blockDim.x) host_dst[i] = dev_src[i];
+    __threadfence_system();
+}
+
 // ---- warp scans ---------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ u32 warp_incl_scan(u32 v)

@@ -52,6 +52,13 @@ struct pk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr; // device-to-host copies of a pipelined pk_mul (created on first use)
+    cudaEvent_t ev_part = nullptr;
+    uint32_t pipe_parts = 0;           // output parts of a pipelined pk_mul; 0 or 1 = off (the default: measured on
+                                       // pearce1 the copy is 2.9 ms of a 3.9 ms call and the product only 0.65 ms, so
+                                       // overlapping them gains under 10 % and costs the per-part fixed work)
+    uint64_t pipe_min_products = 1ull << 23;
+    uint32_t pipe_test_small = 0;      // tests: undersize the host arrays so that the re-copy path runs
     std::string err;
     std::vector<std::vector<int64_t>> limits; // [n_vars] -> M_k
     std::vector<int64_t> h_min, h_max;
@@ -76,6 +83,7 @@ struct pk_ctx {
 struct pk_dpoly {
     uint64_t n = 0, stride = 0;
     uint32_t n_vars = 0, limbs = 1;
+    uint32_t alloc_limbs = 1;   // planes allocated (limbs may be trimmed below it)
     pk::i64 *key = nullptr;     // n (+2 padding) piranha codes, ascending
     pk::u64 *planes = nullptr;  // limbs planes of `stride` words
     signed char *sign = nullptr;
@@ -138,6 +146,14 @@ struct DevBuf { // stream-ordered allocation with scope lifetime
         return static_cast<T *>(p);
     }
 };
+
+// dev -> pinned host, `bytes` a multiple of 4, without a copy engine (see k_readback); the caller synchronises the stream
+inline void readback(pk_ctx *ctx, void *host_pinned, const void *dev, size_t bytes)
+{
+    PK_LAUNCH(ctx, k_readback, 1, 64, 0, static_cast<u32 *>(host_pinned), static_cast<const u32 *>(dev), (u32)(bytes / 4));
+    --ctx->call_launches; // plumbing, not part of the product's kernel count
+    --ctx->total_launches;
+}
 
 inline u32 grid_for(u64 n, u32 block) { return (u32)std::max<u64>(1, (n + block - 1) / block); }
 
@@ -207,6 +223,7 @@ inline pk_dpoly *new_dpoly(pk_ctx *ctx, u64 n, u32 n_vars, u32 limbs)
     p->n = n;
     p->n_vars = n_vars;
     p->limbs = limbs;
+    p->alloc_limbs = limbs;
     p->stride = ((n + 1) & ~1ull) + 2; // even, with slack for the 16-byte TMA granularity
     DPolyGuard g{ctx, p.release()};
     CUDA_CHECK(cudaMallocAsync((void **)&g.p->key, (n + 2) * sizeof(int64_t), ctx->stream));

@@ -330,6 +330,32 @@ def test_block_truncation_degree_overflow(ctx):
         ctx.mul(terms(f, 4, 1), terms(g, 4, 2), 4, trunc_mode=1, max_degree=2 ** 63 - 1, algo=pb.PK_ALGO_BLOCK)
 
 
+@pytest.mark.parametrize("small", [0, 1])
+@pytest.mark.parametrize("parts", [2, 4, 7])
+def test_pipelined_host_product(parts, small):
+    """pk_mul of a sparse product computes output ranges one after the other and copies each to the host while the next
+    is computed; the result is the same bits as the one-shot product (small=1 undersizes the host arrays on purpose so
+    that the exact re-copy path runs)."""
+    (f, g), nv = po.pearce_operands(6), 5
+    a, b = terms(f, nv, 1), terms(g, nv, 2)
+    c2 = pb.Context(0)
+    try:
+        c2.set_tuning(pipe_parts=0)
+        ref = c2.mul(a, b, nv)
+        st0 = c2.stats()
+        c2.set_tuning(pipe_parts=parts, pipe_min_products=1, pipe_test_small=small)
+        r = c2.mul(a, b, nv)
+        st = c2.stats()
+        assert_sorted_unique(r[0])
+        assert_terms_equal(r, ref)
+        assert st["term_products"] == st0["term_products"] == len(a[0]) * len(b[0])
+        assert st["result_terms"] == len(ref[0])
+        assert st["kernel_launches"] > st0["kernel_launches"]  # it really ran in parts
+        assert_terms_equal(r, cpu_ref(a, b, nv, n_threads=4))
+    finally:
+        c2.close()
+
+
 def test_block_declines_without_a_digit_split(ctx):
     # one variable: there is no hi digit, the generic zone path takes over
     f = {(i,): i + 1 for i in range(0, 3000, 3)}
