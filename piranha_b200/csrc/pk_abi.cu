@@ -290,10 +290,15 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
     // ---- operand preparation
     DevBuf keyA(ctx, (nA + 2) * 8), keyB(ctx, (nB + 2) * 8);
     DevBuf degA(ctx, trunc ? nA * 8 : 0), degB(ctx, trunc ? nB * 8 : 0);
-    PK_LAUNCH(ctx, k_prepare, grid_for(nA, 256), 256, 0, A->key, A->sign, nA, pl.cpA, keyA.as<u64>(),
-              degA.as<i64>());
-    PK_LAUNCH(ctx, k_prepare, grid_for(nB, 256), 256, 0, B->key, B->sign, nB, pl.cpB, keyB.as<u64>(),
-              degB.as<i64>());
+    // the block path's packed operand records are written by the same pass (untruncated products; the truncated
+    // form of the record needs the operand's smallest degree first)
+    BlockPlan bp = block_plan(ctx, pl, nA, nB);
+    const bool prepack = bp.ok && !trunc && (o.algo == PK_ALGO_AUTO || o.algo == PK_ALGO_BLOCK);
+    DevBuf packA(ctx, prepack ? (nA + 1) * 16 : 0), packB(ctx, prepack ? (nB + 1) * 16 : 0);
+    PK_LAUNCH(ctx, k_prepare, grid_for(nA, 256), 256, 0, A->key, A->sign, nA, pl.cpA, keyA.as<u64>(), degA.as<i64>(), A->planes,
+              packA.as<uint4>());
+    PK_LAUNCH(ctx, k_prepare, grid_for(nB, 256), 256, 0, B->key, B->sign, nB, pl.cpB, keyB.as<u64>(), degB.as<i64>(), B->planes,
+              packB.as<uint4>());
     const u64 *kB = keyB.as<u64>();
     const u64 *mB = B->planes;
     u64 strideB = B->stride;
@@ -320,7 +325,6 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
     };
 
     // ---- output partition [lo, hi) in tight-code space
-    BlockPlan bp = block_plan(ctx, pl, nA, nB);
     // a partitioned product uses the block geometry only when every part gets many whole blocks (else the rounding
     // of the cuts would unbalance the parts); a function of the operands and P only, so all ranks agree
     if (bp.ok && P > 1 && pl.range / bp.S < 256ull * P) bp.ok = false;
@@ -363,7 +367,8 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
     if (algo == PK_ALGO_BLOCK) {
         if (bp.ok && sub_range)
             result = block_multiply(ctx, pl, bp, A, B, keyA.as<u64>(), keyB.as<u64>(), lo, hi, nv, trunc ? degA.as<i64>() : nullptr,
-                                    trunc ? degB.as<i64>() : nullptr, o.max_degree, filter);
+                                    trunc ? degB.as<i64>() : nullptr, o.max_degree, prepack ? packA.as<uint4>() : nullptr,
+                                    prepack ? packB.as<uint4>() : nullptr);
         if (!result) algo = PK_ALGO_ZONE; // no block geometry for these operands (or tiny groups): generic zones
     }
     if (trunc && !result) prepare_degree_sorted();
@@ -488,6 +493,8 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
     DPolyGuard rg{ctx, result};
     CUDA_CHECK(cudaEventRecord(ctx->ev_end, ctx->stream));
     MulCounters *hc = static_cast<MulCounters *>(ctx->h_scratch);
+    // (the product returns only when the stream is idle: measured, a product that returned with its last copy kernel in
+    // flight made the next product's stream-ordered allocations of ~1 GB take 16 ms instead of reusing the freed blocks)
     readback(ctx, hc, ctx->d_ctr, sizeof(MulCounters));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     ctx->ev_valid = true;
@@ -673,6 +680,7 @@ int pk_get_stats(pk_ctx *ctx, pk_stats *out)
     if (!ctx || !out) return PK_E_ARGS;
     if (ctx->ev_valid) {
         float ms = 0.f;
+        cudaEventSynchronize(ctx->ev_end); // the last copy of a product may still be running
         if (cudaEventElapsedTime(&ms, ctx->ev_mul0, ctx->ev_mul1) == cudaSuccess) ctx->stats.mul_kernel_ms = ms;
         if (cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end) == cudaSuccess) ctx->stats.device_ms = ms;
     }
@@ -780,6 +788,7 @@ void collect_part_stats(pk_ctx *ctx, pk_stats &acc)
 {
     float ms = 0.f;
     if (ctx->ev_valid) {
+        cudaEventSynchronize(ctx->ev_end);
         if (cudaEventElapsedTime(&ms, ctx->ev_mul0, ctx->ev_mul1) == cudaSuccess) acc.mul_kernel_ms += ms;
         if (cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end) == cudaSuccess) acc.device_ms += ms;
     }

@@ -143,7 +143,6 @@ struct TileArgs {
     const uint2 *gdegA, *gdegB; // truncation: degree offset extremes per group (nullptr = untruncated)
     const TruncDev *trunc;
     u32 *cnt;        // tiles per block (count pass) / cursor per block (scatter pass)
-    u64 *zwork;      // products per zone
     const u32 *tstart;
     uint4 *tiles;
     u32 max_tiles;
@@ -185,7 +184,6 @@ __global__ void k_block_tiles(const TileArgs t)
     const u32 nt = n64 * nrow_w + n32 * nrow_f + nrow_r;
     if (PASS == 0) {
         atomicAdd(&t.cnt[hr], nt);
-        atomicAdd(&t.zwork[hr / t.Hz], (u64)na * nb);
     } else {
         const u32 pos = __ldg(&t.tstart[hr]) + atomicAdd(&t.cnt[hr], nt);
         if (pos + nt > t.max_tiles) { // cannot happen: max_tiles is a proven bound
@@ -206,9 +204,12 @@ __global__ void k_block_tiles(const TileArgs t)
 
 // Zone order for the dynamic claiming: heaviest first (LPT), by a counting sort over 256 logarithmic work classes.
 // One block.  Zones without work sort last and are never claimed (n_active).
-__global__ void __launch_bounds__(1024) k_block_order(const u64 *__restrict__ zwork, u32 nz, u32 *__restrict__ order,
-                                                      u32 *__restrict__ n_active, u32 *__restrict__ n_zones)
+__global__ void __launch_bounds__(1024) k_block_order(const u32 *__restrict__ tstart, u32 n_h, u32 Hz, u32 nz,
+                                                      u32 *__restrict__ order, u32 *__restrict__ n_active,
+                                                      u32 *__restrict__ n_zones)
 {
+    // work of a zone = its number of tiles (every tile holds about the same number of products)
+    auto zwork_of = [&](u32 z) -> u64 { return (u64)(tstart[min(n_h, (z + 1) * Hz)] - tstart[z * Hz]); };
     __shared__ u32 s_hist[256], s_start[256];
     for (u32 i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(1024) k_block_order(const u64 *__restrict__ zw
         const u32 m = e >= 2 ? (u32)(w >> (e - 2)) & 3u : 0u;
         return min(255u, 4u * e + m + 1u);
     };
-    for (u32 z = threadIdx.x; z < nz; z += blockDim.x) atomicAdd(&s_hist[cls(zwork[z])], 1u);
+    for (u32 z = threadIdx.x; z < nz; z += blockDim.x) atomicAdd(&s_hist[cls(zwork_of(z))], 1u);
     __syncthreads();
     if (threadIdx.x == 0) {
         u32 run = 0;
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(1024) k_block_order(const u64 *__restrict__ zw
         *n_zones = nz;
     }
     __syncthreads();
-    for (u32 z = threadIdx.x; z < nz; z += blockDim.x) order[atomicAdd(&s_start[cls(zwork[z])], 1u)] = z;
+    for (u32 z = threadIdx.x; z < nz; z += blockDim.x) order[atomicAdd(&s_start[cls(zwork_of(z))], 1u)] = z;
 }
 
 __global__ void k_block_natural_order(u32 nz, u32 *__restrict__ n_active, u32 *__restrict__ n_zones)
@@ -758,9 +759,8 @@ inline bool block_layout(pk_ctx *ctx, BlockPlan &bp, u32 Hz)
 // block path (tiny groups); the caller then uses the generic zone path.
 inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const pk_dpoly *A, const pk_dpoly *B,
                                 const u64 *keyA, const u64 *keyB, u64 lo, u64 hi, u32 nv, const i64 *degA, const i64 *degB,
-                                i64 max_degree, bool count_pairs)
+                                i64 max_degree, const uint4 *prepackA, const uint4 *prepackB)
 {
-    (void)count_pairs;
     const u64 nA = A->n, nB = B->n;
     const bool trunc = degA != nullptr;
     if (trunc) { // degree offsets are 31-bit: bound the degree span of each operand by its exponent spans
@@ -781,7 +781,10 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     if ((unsigned __int128)out_cap * (9 + 8 * pl.out_limbs) > (unsigned __int128)ctx->total_mem / 2) return nullptr;
 
     const u64 HR = pl.range / S + 2;
-    DevBuf pa(ctx, (nA + 1) * 16), pb(ctx, (nB + 1) * 16), tdev(ctx, trunc ? sizeof(TruncDev) : 0);
+    const bool packed = prepackA && prepackB && !trunc;
+    DevBuf pa_own(ctx, packed ? 0 : (nA + 1) * 16), pb_own(ctx, packed ? 0 : (nB + 1) * 16), tdev(ctx, trunc ? sizeof(TruncDev) : 0);
+    uint4 *const pa_p = packed ? const_cast<uint4 *>(prepackA) : pa_own.as<uint4>();
+    uint4 *const pb_p = packed ? const_cast<uint4 *>(prepackB) : pb_own.as<uint4>();
     DevBuf gdegA(ctx, trunc ? HR * 8 : 0), gdegB(ctx, trunc ? HR * 8 : 0);
     TruncDev *td = tdev.as<TruncDev>();
     if (trunc) {
@@ -790,13 +793,13 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
         PK_LAUNCH(ctx, k_deg_minmax, rg, 256, 0, degA, (u32)nA, &td->min_a, &td->max_a);
         PK_LAUNCH(ctx, k_deg_minmax, rg, 256, 0, degB, (u32)nB, &td->min_b, &td->max_b);
         PK_LAUNCH(ctx, k_trunc_limits, 1, 1, 0, td, max_degree, ctx->d_ctr);
-        PK_LAUNCH(ctx, k_pack_operand_deg, grid_for(nA, 256), 256, 0, keyA, A->planes, degA, &td->min_a, pa.as<uint4>(), nA);
-        PK_LAUNCH(ctx, k_pack_operand_deg, grid_for(nB, 256), 256, 0, keyB, B->planes, degB, &td->min_b, pb.as<uint4>(), nB);
+        PK_LAUNCH(ctx, k_pack_operand_deg, grid_for(nA, 256), 256, 0, keyA, A->planes, degA, &td->min_a, pa_p, nA);
+        PK_LAUNCH(ctx, k_pack_operand_deg, grid_for(nB, 256), 256, 0, keyB, B->planes, degB, &td->min_b, pb_p, nB);
         CUDA_CHECK(cudaMemsetAsync(gdegA.p, 0xFF, HR * 8, ctx->stream));
         CUDA_CHECK(cudaMemsetAsync(gdegB.p, 0xFF, HR * 8, ctx->stream));
-    } else {
-        PK_LAUNCH(ctx, k_pack_operand, grid_for(nA, 256), 256, 0, keyA, A->planes, pa.as<uint4>(), nA);
-        PK_LAUNCH(ctx, k_pack_operand, grid_for(nB, 256), 256, 0, keyB, B->planes, pb.as<uint4>(), nB);
+    } else if (!packed) {
+        PK_LAUNCH(ctx, k_pack_operand, grid_for(nA, 256), 256, 0, keyA, A->planes, pa_p, nA);
+        PK_LAUNCH(ctx, k_pack_operand, grid_for(nB, 256), 256, 0, keyB, B->planes, pb_p, nB);
     }
 
     // ---- groups of equal hi
@@ -805,9 +808,9 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     CUDA_CHECK(cudaMemsetAsync(tabA.p, 0, HR * 8, ctx->stream));
     CUDA_CHECK(cudaMemsetAsync(tabB.p, 0, HR * 8, ctx->stream));
     CUDA_CHECK(cudaMemsetAsync(gcnt.p, 0, 16, ctx->stream));
-    PK_LAUNCH(ctx, k_block_groups, grid_for(nA, 256), 256, 0, pa.as<uint4>(), (u32)nA, magicS, tabA.as<uint2>(), glA.as<u32>(),
+    PK_LAUNCH(ctx, k_block_groups, grid_for(nA, 256), 256, 0, pa_p, (u32)nA, magicS, tabA.as<uint2>(), glA.as<u32>(),
               gcnt.as<u32>(), trunc ? gdegA.as<uint2>() : nullptr);
-    PK_LAUNCH(ctx, k_block_groups, grid_for(nB, 256), 256, 0, pb.as<uint4>(), (u32)nB, magicS, tabB.as<uint2>(), glB.as<u32>(),
+    PK_LAUNCH(ctx, k_block_groups, grid_for(nB, 256), 256, 0, pb_p, (u32)nB, magicS, tabB.as<uint2>(), glB.as<u32>(),
               gcnt.as<u32>() + 1, trunc ? gdegB.as<uint2>() : nullptr);
     u32 *hg = reinterpret_cast<u32 *>(static_cast<char *>(ctx->h_scratch) + 2048);
     readback(ctx, hg, gcnt.p, 8);
@@ -873,7 +876,6 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     ta.gdegB = trunc ? gdegB.as<uint2>() : nullptr;
     ta.trunc = trunc ? td : nullptr;
     ta.cnt = cnt.as<u32>();
-    ta.zwork = zwork;
     ta.tstart = tstart.as<u32>();
     ta.tiles = tiles.as<uint4>();
     ta.max_tiles = max_tiles;
@@ -889,15 +891,15 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, ((size_t)n_h + 1) * 4, ctx->stream));
     PK_LAUNCH(ctx, (k_block_tiles<1>), pgrid, 256, 0, ta);
     const bool lpt = !bt.natural && nz <= (1u << 17);
-    if (lpt) PK_LAUNCH(ctx, k_block_order, 1, 1024, 0, zwork, nz, order, n_active_dev, n_zones_dev);
+    if (lpt) PK_LAUNCH(ctx, k_block_order, 1, 1024, 0, tstart.as<u32>(), n_h, (u32)Hz, nz, order, n_active_dev, n_zones_dev);
     else PK_LAUNCH(ctx, k_block_natural_order, 1, 1, 0, nz, n_active_dev, n_zones_dev);
 
     DPolyGuard g{ctx, new_dpoly(ctx, out_cap, nv, pl.out_limbs)};
     BlockArgs ba{};
     ZoneArgs &za = ba.z;
-    za.A = pa.as<uint4>();
+    za.A = pa_p;
     za.nA = (u32)nA;
-    za.B = pb.as<uint4>();
+    za.B = pb_p;
     za.nB = (u32)nB;
     za.lo = (u32)lo;
     za.hi = (u32)hi;

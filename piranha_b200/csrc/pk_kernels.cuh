@@ -126,7 +126,7 @@ __global__ void k_meta(const i64 *__restrict__ key, const u64 *__restrict__ plan
 // Per-multiplication operand preparation: tight code | sign bit, degree (total or partial), coefficient limbs
 // are read straight from the operand's planes by the multiply kernel.
 __global__ void k_prepare(const i64 *__restrict__ key, const signed char *__restrict__ sign, u64 n, CodecParams cp,
-                          u64 *__restrict__ okey, i64 *__restrict__ odeg)
+                          u64 *__restrict__ okey, i64 *__restrict__ odeg, const u64 *__restrict__ m0, uint4 *__restrict__ opack)
 {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -144,6 +144,10 @@ __global__ void k_prepare(const i64 *__restrict__ key, const signed char *__rest
     // a zero coefficient contributes nothing: its magnitude limbs are zero, the sign bit is irrelevant
     okey[i] = tight | (s < 0 ? kSignBit : 0ull);
     if (odeg) odeg[i] = deg;
+    if (opack) { // packed 16-byte record of the shared-memory paths: {tight code (32 bit), sign, magnitude (one limb)}
+        const u64 m = m0[i];
+        opack[i] = make_uint4((u32)tight, s < 0 ? 1u : 0u, (u32)m, (u32)(m >> 32));
+    }
 }
 
 // permute prepared operand arrays (after sorting the second operand by degree, polynomial.hpp:1427-1442)
