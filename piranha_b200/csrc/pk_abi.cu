@@ -594,6 +594,10 @@ void pk_ctx_destroy(pk_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->staging) {
+        free_dpoly_arrays(ctx, ctx->staging);
+        delete ctx->staging;
+    }
     for (auto &b : ctx->pinned)
         if (b.ptr) cudaFreeHost(b.ptr);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);

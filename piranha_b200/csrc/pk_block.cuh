@@ -894,7 +894,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     if (lpt) PK_LAUNCH(ctx, k_block_order, 1, 1024, 0, tstart.as<u32>(), n_h, (u32)Hz, nz, order, n_active_dev, n_zones_dev);
     else PK_LAUNCH(ctx, k_block_natural_order, 1, 1, 0, nz, n_active_dev, n_zones_dev);
 
-    DPolyGuard g{ctx, new_dpoly(ctx, out_cap, nv, pl.out_limbs)};
+    const StagingView g = staging_acquire(ctx, out_cap, nv, pl.out_limbs);
     BlockArgs ba{};
     ZoneArgs &za = ba.z;
     za.A = pa_p;

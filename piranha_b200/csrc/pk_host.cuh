@@ -78,6 +78,8 @@ struct pk_ctx {
     size_t smem_optin = 0;
     size_t smem_per_sm = 0;
     size_t total_mem = 0;
+    pk_dpoly *staging = nullptr; // unordered per-zone output of the shared-memory paths, kept across products (grow-only)
+    uint64_t staging_cap = 0;
 };
 
 struct pk_dpoly {
@@ -230,6 +232,33 @@ inline pk_dpoly *new_dpoly(pk_ctx *ctx, u64 n, u32 n_vars, u32 limbs)
     CUDA_CHECK(cudaMallocAsync((void **)&g.p->planes, g.p->stride * limbs * sizeof(uint64_t), ctx->stream));
     CUDA_CHECK(cudaMallocAsync((void **)&g.p->sign, n + 2, ctx->stream));
     return g.release();
+}
+
+// The staging arrays of the zone / block paths are bounded by min(term products, code range) terms (~1 GB for
+// pearce1) although only the result's size is ever written.  They are kept in the context and reused: allocating and
+// freeing blocks of that size per product through the stream-ordered pool made the pool re-map memory every few
+// products (measured: 16 ms stalls inside the timed region of bench.py).
+struct StagingView {
+    pk_dpoly *p;
+};
+inline StagingView staging_acquire(pk_ctx *ctx, u64 n, u32 n_vars, u32 limbs)
+{
+    pk_dpoly *s = ctx->staging;
+    if (!s || ctx->staging_cap < n || s->alloc_limbs < limbs) {
+        if (s) {
+            free_dpoly_arrays(ctx, s);
+            delete s;
+            ctx->staging = nullptr;
+            ctx->staging_cap = 0;
+        }
+        const u64 cap = n + n / 8 + 1024;
+        ctx->staging = new_dpoly(ctx, cap, n_vars, limbs);
+        ctx->staging_cap = cap;
+        s = ctx->staging;
+    }
+    s->n = n;
+    s->n_vars = n_vars;
+    return StagingView{s};
 }
 
 } // namespace pk

@@ -835,7 +835,7 @@ inline pk_dpoly *zone_multiply(pk_ctx *ctx, const Plan &pl, const pk_dpoly *A, c
     const u32 cursor_stride = (u32)((nA + 31) & ~31ull);
     DevBuf cursors(ctx, zp.use_cursors ? (size_t)zp.grid * cursor_stride * 4 : 0);
 
-    DPolyGuard g{ctx, new_dpoly(ctx, out_cap, nv, pl.out_limbs)};
+    const StagingView g = staging_acquire(ctx, out_cap, nv, pl.out_limbs);
     ZoneArgs za{};
     za.A = pa.as<uint4>();
     za.nA = (u32)nA;
