@@ -31,9 +31,10 @@ void fill_piranha_codec(const pk_ctx *ctx, u32 n_vars, CodecParams &cp)
     }
 }
 
-void ensure_meta(pk_ctx *ctx, pk_dpoly *p)
+// Exponent bounds, gcd steps and coefficient width of a polynomial whose terms are in the given arrays (any order;
+// `aos`: magnitudes row-major as the caller passed them, else limb planes).
+void compute_meta(pk_ctx *ctx, pk_dpoly *p, const i64 *key, const u64 *mag, const signed char *sign, u64 stride, bool aos)
 {
-    if (p->has_meta) return;
     const u32 nv = p->n_vars;
     p->emin.assign(nv, 0);
     p->emax.assign(nv, 0);
@@ -56,7 +57,7 @@ void ensure_meta(pk_ctx *ctx, pk_dpoly *p)
     CodecParams cp;
     fill_piranha_codec(ctx, nv, cp);
     const u32 grid = std::min<u32>(grid_for(p->n, 256), (u32)ctx->sm_count * 8);
-    PK_LAUNCH(ctx, k_meta, grid, 256, 0, p->key, p->planes, p->sign, p->n, p->limbs, p->stride, cp, ctx->d_meta);
+    PK_LAUNCH(ctx, k_meta, grid, 256, 0, key, mag, sign, p->n, p->limbs, stride, cp, ctx->d_meta, aos ? 1u : 0u);
     readback(ctx, ctx->h_scratch, ctx->d_meta, sizeof(MetaDev));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     const MetaDev *m = static_cast<const MetaDev *>(ctx->h_scratch);
@@ -68,6 +69,11 @@ void ensure_meta(pk_ctx *ctx, pk_dpoly *p)
     p->max_bits = m->max_bits;
     p->any_neg = m->any_neg != 0;
     p->has_meta = true;
+}
+
+void ensure_meta(pk_ctx *ctx, pk_dpoly *p)
+{
+    if (!p->has_meta) compute_meta(ctx, p, p->key, p->planes, p->sign, p->stride, false);
 }
 
 template <typename K, typename V>
@@ -108,13 +114,28 @@ pk_dpoly *upload_impl(pk_ctx *ctx, const pk_poly *p)
     CUDA_CHECK(cudaMemcpyAsync(raw_key.p, p->key, n * 8, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(raw_mag.p, p->mag, n * p->limbs * 8, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(raw_sign.p, p->sign, n, cudaMemcpyHostToDevice, ctx->stream));
-    // canonical order: ascending Kronecker code (the role of fill_term_pointers' per-bucket sort,
-    // base_series_multiplier.hpp:126-132; hash_set order itself is unspecified)
+    // exponent bounds first (on the caller's order), then the canonical order: ascending Kronecker code (the role of
+    // fill_term_pointers' per-bucket sort, base_series_multiplier.hpp:126-132; hash_set order itself is unspecified).
+    // The sort key is the polynomial's own tight code -- monotone in the Kronecker code and only as wide as the
+    // exponent spans need (18 bits for fateman1's operands instead of 64), so the radix sort runs 3 passes, not 8.
+    compute_meta(ctx, g.p, raw_key.as<i64>(), raw_mag.as<u64>(), raw_sign.as<signed char>(), 0, true);
+    CodecParams cp;
+    fill_piranha_codec(ctx, p->n_vars, cp);
+    unsigned __int128 range = 1;
+    for (u32 v = 0; v < p->n_vars; ++v) {
+        const u64 gs = g.p->egcd[v] ? g.p->egcd[v] : 1;
+        cp.emin[v] = g.p->emin[v];
+        cp.step[v] = (i64)gs;
+        cp.stride[v] = (u64)range;
+        range *= (u64)(g.p->emax[v] - g.p->emin[v]) / gs + 1;
+        if (range >= ((unsigned __int128)1 << 62)) fail(PK_E_KEY_RANGE, "exponent spans too wide to re-encode");
+    }
     DevBuf fk(ctx, n * 8), fk2(ctx, n * 8), idx(ctx, n * 4), idx2(ctx, n * 4);
-    PK_LAUNCH(ctx, k_flip_keys, grid_for(n, 256), 256, 0, raw_key.as<i64>(), fk.as<u64>(), n);
+    PK_LAUNCH(ctx, k_prepare, grid_for(n, 256), 256, 0, raw_key.as<i64>(), raw_sign.as<signed char>(), n, cp, fk.as<u64>(),
+              (i64 *)nullptr, (const u64 *)nullptr, (uint4 *)nullptr);
     PK_LAUNCH(ctx, k_iota32, grid_for(n, 256), 256, 0, idx.as<u32>(), n);
-    radix_sort_pairs(ctx, fk.as<u64>(), fk2.as<u64>(), idx.as<u32>(), idx2.as<u32>(), n, 64);
-    PK_LAUNCH(ctx, k_gather_terms, grid_for(n, 256), 256, 0, idx2.as<u32>(), fk2.as<u64>(), raw_mag.as<u64>(),
+    radix_sort_pairs(ctx, fk.as<u64>(), fk2.as<u64>(), idx.as<u32>(), idx2.as<u32>(), n, (int)std::max<u32>(1, bit_length(range)));
+    PK_LAUNCH(ctx, k_gather_terms, grid_for(n, 256), 256, 0, idx2.as<u32>(), raw_key.as<i64>(), raw_mag.as<u64>(),
               raw_sign.as<signed char>(), g.p->key, g.p->planes, g.p->sign, n, p->limbs, g.p->stride);
     ensure_meta(ctx, g.p);
     return g.release();

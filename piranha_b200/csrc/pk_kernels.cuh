@@ -48,14 +48,14 @@ __global__ void k_flip_keys(const i64 *__restrict__ in, u64 *__restrict__ out, u
 }
 
 // gather terms through a permutation (after sorting by key)
-__global__ void k_gather_terms(const u32 *__restrict__ perm, const u64 *__restrict__ skey_flipped,
+__global__ void k_gather_terms(const u32 *__restrict__ perm, const i64 *__restrict__ raw_key,
                                const u64 *__restrict__ mag_aos, const signed char *__restrict__ sign, i64 *__restrict__ okey,
                                u64 *__restrict__ oplanes, signed char *__restrict__ osign, u64 n, u32 limbs, u64 stride)
 {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const u32 s = perm[i];
-    okey[i] = (i64)(skey_flipped[i] ^ kSignBit);
+    okey[i] = raw_key[s];
     for (u32 l = 0; l < limbs; ++l) oplanes[l * stride + i] = mag_aos[(u64)s * limbs + l];
     osign[i] = sign[s];
 }
@@ -76,7 +76,7 @@ __device__ __forceinline__ void atomic_gcd(u64 *p, u64 v)
 // One pass over a polynomial: decode every key, reduce per-variable min / max / gcd(e - e_first) and the widest
 // coefficient.  meta must be initialised (emin=+inf, emax=-inf, egcd=0, max_bits=0).
 __global__ void k_meta(const i64 *__restrict__ key, const u64 *__restrict__ planes, const signed char *__restrict__ sign,
-                       u64 n, u32 limbs, u64 stride, CodecParams cp, MetaDev *meta)
+                       u64 n, u32 limbs, u64 stride, CodecParams cp, MetaDev *meta, u32 aos)
 {
     __shared__ i64 s_min[PK_MAX_VARS], s_max[PK_MAX_VARS];
     __shared__ u64 s_gcd[PK_MAX_VARS];
@@ -108,7 +108,7 @@ __global__ void k_meta(const i64 *__restrict__ key, const u64 *__restrict__ plan
         }
         u32 bits = 0;
         for (u32 l = 0; l < limbs; ++l) {
-            const u64 m = planes[l * stride + i];
+            const u64 m = aos ? planes[i * limbs + l] : planes[l * stride + i]; // (aos: the caller's row-major limbs)
             if (m) bits = 64u * l + bitlen64(m);
         }
         if (bits > s_bits) atomicMax(&s_bits, bits);
