@@ -646,6 +646,7 @@ inline void block_configure(pk_ctx *ctx)
     t.force_mode = env_u32("PK_BLOCK_MODE", t.force_mode);
     t.natural = env_u32("PK_BLOCK_NATURAL", t.natural);
     t.wide = env_u32("PK_BLOCK_WIDE", t.wide);
+    t.smem_limit = env_u32("PK_BLOCK_SMEM", t.smem_limit);
     t.radix0_residue = env_u32("PK_BLOCK_RADIX0", t.radix0_residue);
     const size_t dyn = ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0;
 #define X(nw, pw) block_set_smem_w<nw, pw>(dyn);
@@ -668,6 +669,7 @@ inline size_t block_smem_budget(pk_ctx *ctx)
 {
     size_t budget = ctx->smem_per_sm > 1024 ? ctx->smem_per_sm - 1024 : 0;
     budget = std::min(budget, ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0);
+    if (ctx->block_tuning.smem_limit) budget = std::min<size_t>(budget, ctx->block_tuning.smem_limit);
     return budget > 1024 ? (budget - 512) & ~255ull : 0; // static shared memory + alignment slack
 }
 
@@ -697,7 +699,7 @@ inline BlockPlan block_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB)
     while (span_bitmap > 1024 && span_bitmap / 4 + (size_t)(NW + 1) * 4 * 2048 > budget) span_bitmap >>= 1;
     const u64 limit = mode == 0 ? cap_dense : span_bitmap;
     // the largest split whose block still fits; at least one digit must stay in `hi`
-    // (bitmap zones: a block should also hold its entries in one pass -- the products of a block bound its entries --
+    // (bitmap zones: a block should also hold its entries in one pass -- the products and the codes of a block bound them --
     // because only multi-block zones can restrict a pass to the tiles of the blocks it covers)
     const u64 cap_bitmap = (budget / 2 / ((NW + 1) * 4)) & ~31ull;
     u64 S = 1;
@@ -705,7 +707,7 @@ inline BlockPlan block_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB)
     for (u32 v = 0; v + 1 < pl.n_vars; ++v) {
         const u64 next = S * pl.cpR.tradix[v];
         if (next > limit) break;
-        if (mode == 1 && split >= 1 && W / ((double)pl.range / (double)next) > (double)cap_bitmap) break;
+        if (mode == 1 && split >= 1 && std::min(W / ((double)pl.range / (double)next), (double)next) > (double)cap_bitmap) break;
         S = next;
         split = v + 1;
     }
@@ -842,7 +844,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     // ---- tile list: count -> scan -> scatter
     // every chunk of gb (at most nb / 32 + 2 per pair) gives at most 2 * na * width / target + 1 tiles (+ na / 1023 when the
     // row count per tile hits its 10-bit cap)
-    const u64 max_tiles64 = 2 * (u64)(w_bound / bt.tile_target) + ((u64)GA * nB) / kTileCols + 2 * pairs
+    const u64 max_tiles64 = 2 * (u64)(w_bound / std::min<u32>(bt.tile_target, 512)) + ((u64)GA * nB) / kTileCols + 2 * pairs
                             + (nB / kTileCols + 2 * (u64)GB) * (nA / 1023 + 1) + 64;
     if (max_tiles64 >= (1ull << 31)) return nullptr;
     const u32 max_tiles = (u32)max_tiles64;
@@ -870,7 +872,9 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     ta.h_base = h_base;
     ta.n_h = n_h;
     ta.Hz = (u32)Hz;
-    ta.target = bt.tile_target;
+    // (measured: dense zones like 1024-2048 products per tile, bitmap zones 512 -- their tiles are walked twice and the
+    // zones are smaller, so finer tiles balance the warps better)
+    ta.target = bp.mode == 1 ? std::min<u32>(bt.tile_target, 512) : bt.tile_target;
     ta.wide = bt.wide;
     ta.gdegA = trunc ? gdegA.as<uint2>() : nullptr;
     ta.gdegB = trunc ? gdegB.as<uint2>() : nullptr;

@@ -30,13 +30,14 @@ struct ZoneTuning {
 
 struct BlockTuning {
     uint32_t disable = 0;
-    uint32_t tile_target = 512;   // products per tile of the block path
+    uint32_t tile_target = 1024;  // products per tile of the block path (sweep: 256 is 8 % slower, 1024-2048 best)
     uint32_t zone_work = 1u << 16; // aim for about this many products per zone (more blocks per zone when blocks are light)
     uint32_t min_tile = 8;        // decline the block path when the average pair of groups has fewer products
     uint32_t force_mode = 0;      // 0 auto, 1 dense, 2 bitmap
     uint32_t force_hz = 0;        // tests: blocks per zone
     uint32_t natural = 0;         // 1 = claim zones in code order instead of heaviest first
     uint32_t wide = 1;            // 1 = 64-term chunks of gb (two terms per lane) where the group is large enough
+    uint32_t smem_limit = 0;      // bytes of shared memory a zone may use (0 = all): what is left over serves as L1
     uint32_t radix0_residue = 0;  // experiment: pad the radix of digit 0 so that radix mod 32 == this (1..32); 0 = off
 };
 

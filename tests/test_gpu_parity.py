@@ -391,6 +391,31 @@ def test_fateman1_truncated(ctx, D, size):
     assert ctx.stats()["term_products"] == {20: 3108105, 30: 38970998}[D]  # SURVEY.md section 8 size table
 
 
+@pytest.mark.parametrize("which", ["fateman1_dynamic", "pearce_dynamic_reduced"])
+def test_dynamic_benchmarks(ctx, which):
+    """benchmarks/fateman1_dynamic.cpp, pearce1_dynamic.cpp: the first operand scaled by 2^64 - 1, so operands need two
+    limbs and the result four (mp++ would leave its static storage; here the width bound selects wider accumulators)."""
+    factor = 2 ** 64 - 1
+    if which == "fateman1_dynamic":
+        (f, g), nv, size = po.fateman_operands(20), 4, 135751
+        f = {k: v * factor for k, v in f.items()}
+        g = dict(f)
+        one = (0,) * nv
+        g[one] = g.get(one, 0) + 1  # f * (f + 1) with the scaled f (benchmarks/fateman1.hpp:49-55)
+    else:
+        (f, g), nv, size = po.pearce_operands(6), 5, None
+        f = {k: v * factor for k, v in f.items()}
+        g = {k: v * factor for k, v in g.items()}
+    a, b = terms(f, nv, 1), terms(g, nv, 2)
+    assert a[1].shape[1] == 2
+    r = ctx.mul(a, b, nv)
+    assert_sorted_unique(r[0])
+    if size is not None:
+        assert len(r[0]) == size
+    assert r[1].shape[1] >= 3
+    assert_terms_equal(r, cpu_ref(a, b, nv, n_threads=8))
+
+
 # ---------------------------------------------------------------------------------------------- wider coverage
 
 
@@ -412,6 +437,68 @@ def test_multi_limb_random(ctx, algo, bits_a, bits_b):
     g = _random_poly(rs, 3, 200, -7, 5, bits_b)
     _, _, r = gpu_mul(ctx, f, g, 3, algo=algo)
     assert_terms_equal(r, oracle_terms(po.p_mul(f, g), 3))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_products_every_strategy(ctx, seed):
+    """Random shapes against the exact Python oracle through every accumulation strategy: variable counts 2..6,
+    exponent boxes that put 31/32/33/64/65 terms in a group, lattice steps, negative exponents, mixed signs, widths up to
+    64 bits, truncation on some seeds."""
+    rs = np.random.RandomState(1000 + seed)
+    nv = int(rs.randint(2, 7))
+    lo = [int(x) for x in rs.randint(-3, 2, size=nv)]
+    span = [int(x) for x in rs.choice([1, 2, 3, 5, 8, 31, 32, 33, 64, 65], size=nv)]
+    span[0] = int(rs.choice([31, 32, 33, 64, 65, 96, 7]))  # digit 0 decides the tile shapes
+    step = [int(x) for x in rs.choice([1, 1, 1, 2, 3], size=nv)]
+    bits = int(rs.choice([3, 20, 40, 64]))
+
+    def poly(nterms, sgn):
+        p = {}
+        for _ in range(nterms):
+            e = tuple(lo[v] + step[v] * int(rs.randint(0, span[v])) for v in range(nv))
+            c = int(rs.randint(1, 2 ** 31)) ** 3 % (2 ** bits - 1) + 1
+            p[e] = -c if (sgn and rs.rand() < 0.4) else c
+        return p
+
+    f, g = poly(int(rs.randint(40, 1500)), seed % 2), poly(int(rs.randint(40, 1500)), seed % 3 == 0)
+    opt, kw = {}, {}
+    if seed % 4 == 3:
+        D = int(np.median([sum(k) for k in f]) + np.median([sum(k) for k in g]))
+        opt, kw = dict(trunc_mode=1, max_degree=D), dict(max_degree=D)
+    expect = oracle_terms(po.p_mul(f, g, **kw), nv)
+    ctx.set_tuning(block_min_tile=0)
+    try:
+        for algo in ALGOS:
+            try:
+                _, _, r = gpu_mul(ctx, f, g, nv, algo=algo, **opt)
+            except MemoryError:
+                assert algo == pb.PK_ALGO_DENSE  # a forced dense accumulator over a sparse 2^40 range is refused, not faked
+                continue
+            assert_terms_equal(r, expect, f"seed {seed} algo {algo}")
+    finally:
+        ctx.set_tuning(block_min_tile=8)
+
+
+@pytest.mark.parametrize("w0,w1", [(31, 3), (32, 2), (33, 4), (64, 2), (65, 3), (96, 2), (1, 70), (130, 1)])
+def test_full_boxes_every_strategy(ctx, w0, w1):
+    """Operands that fill an exponent box: groups of exactly 31 / 32 / 33 / 64 / 65 / 96 terms hit every tile shape of the
+    block kernel (64-term, 32-term and ragged chunks) with every lane occupied."""
+    rs = np.random.RandomState(w0 * 100 + w1)
+    f = {(a, b, c): int(rs.randint(1, 2 ** 40)) * (1 if (a + b) % 3 else -1) for a in range(w0) for b in range(w1) for c in range(5)}
+    g = {(a, b, c): int(rs.randint(1, 2 ** 38)) for a in range(w0) for b in range(w1) for c in range(0, 9, 2)}
+    expect = oracle_terms(po.p_mul(f, g), 3)
+    ctx.set_tuning(block_min_tile=0)
+    try:
+        for algo in ALGOS:
+            _, _, r = gpu_mul(ctx, f, g, 3, algo=algo)
+            assert_terms_equal(r, expect, f"box {w0}x{w1} algo {algo}")
+        for mode in (1, 2):
+            ctx.set_tuning(block_mode=mode, block_target=64)
+            _, _, r = gpu_mul(ctx, f, g, 3, algo=pb.PK_ALGO_BLOCK)
+            assert ctx.stats()["algo"] == pb.PK_ALGO_BLOCK
+            assert_terms_equal(r, expect, f"box {w0}x{w1} block mode {mode}")
+    finally:
+        ctx.set_tuning(block_min_tile=8, block_mode=0, block_target=1024)
 
 
 def test_laurent_and_gcd_compaction(ctx):
