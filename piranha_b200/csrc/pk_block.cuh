@@ -252,26 +252,41 @@ __device__ __forceinline__ uint4 block_load(const uint4 *p)
     return make_uint4(__ldg(&p->x), 0u, 0u, 0u);
 }
 
-// Visit every product of one tile: f(a_record, b_record).  FULL selects how much of a record is loaded (block_load).
-template <int FULL, typename F>
-__device__ __forceinline__ void block_tile_loop(const uint4 *__restrict__ A, const uint4 *__restrict__ B, const uint4 t,
+// second limb of a magnitude (operands of up to two limbs keep it in a parallel 8-byte array): loaded only by the
+// accumulating walk of the two-limb kernels
+template <int LOAD, int LW>
+__device__ __forceinline__ uint2 block_load_hi(const uint2 *p, u32 idx)
+{
+    if (LOAD == 2 && LW == 2) return __ldg(&p[idx]);
+    return make_uint2(0u, 0u);
+}
+
+// Visit every product of one tile: f(a_record, b_record, a_high_limb, b_high_limb).  FULL selects how much of a record
+// is loaded (block_load); LW = limbs per operand magnitude (1 or 2).
+template <int FULL, int LW, typename F>
+__device__ __forceinline__ void block_tile_loop(const uint4 *__restrict__ A, const uint4 *__restrict__ B,
+                                                const uint2 *__restrict__ A1, const uint2 *__restrict__ B1, const uint4 t,
                                                 u32 lane, F &&f)
 {
     const u32 a0 = t.x, b0 = t.y, an = t.z & 1023u, bn = (t.z >> 10) & 127u;
     if (bn == 64u) {
         // two terms of gb per lane: one broadcast load of a row feeds 64 products
         const uint4 bv0 = block_load<FULL>(&B[b0 + lane]), bv1 = block_load<FULL>(&B[b0 + 32u + lane]);
+        const uint2 bh0 = block_load_hi<FULL, LW>(B1, b0 + lane), bh1 = block_load_hi<FULL, LW>(B1, b0 + 32u + lane);
         for (u32 i = 0; i < an; ++i) {
             const uint4 av = block_load<FULL>(&A[a0 + i]);
-            f(av, bv0);
-            f(av, bv1);
+            const uint2 ah = block_load_hi<FULL, LW>(A1, a0 + i);
+            f(av, bv0, ah, bh0);
+            f(av, bv1, ah, bh1);
         }
     } else if (bn == kTileCols) {
         // full tile: lane = term of gb (held in registers), loop over the rows (one broadcast load per row)
         const uint4 bv = block_load<FULL>(&B[b0 + lane]);
+        const uint2 bh = block_load_hi<FULL, LW>(B1, b0 + lane);
         for (u32 i = 0; i < an; ++i) {
             const uint4 av = block_load<FULL>(&A[a0 + i]);
-            f(av, bv);
+            const uint2 ah = block_load_hi<FULL, LW>(A1, a0 + i);
+            f(av, bv, ah, bh);
         }
     } else {
         // flat tile: the an x bn products are flattened over the lanes; (i, j) advance by 32 without a division
@@ -283,7 +298,7 @@ __device__ __forceinline__ void block_tile_loop(const uint4 *__restrict__ A, con
         for (u32 idx = lane; idx < total; idx += 32u) {
             const uint4 av = block_load<FULL>(&A[a0 + i]);
             const uint4 bv = block_load<FULL>(&B[b0 + j]);
-            f(av, bv);
+            f(av, bv, block_load_hi<FULL, LW>(A1, a0 + i), block_load_hi<FULL, LW>(B1, b0 + j));
             i += q;
             j += r;
             if (j >= bn) {
@@ -294,14 +309,13 @@ __device__ __forceinline__ void block_tile_loop(const uint4 *__restrict__ A, con
     }
 }
 
-// Add (subtract when neg) the magnitude p0..p3 -- PW significant 32-bit words -- into the NW-word two's complement
-// accumulator whose word w lives at saddr0 + w * wstride.  Words below PW always issue their atomic; the value an
-// ATOMS returns gives the carry into the next word (one add.cc / addc chain per word, no branches); above PW only a
-// pending carry travels on.  The top word's carry-out is the overflow the host's width bound proves impossible.
+// Add (subtract when neg) the magnitude p[0..PW) -- PW significant 32-bit words, PW <= 8 -- into the NW-word two's
+// complement accumulator whose word w lives at saddr0 + w * wstride.  Words below PW always issue their atomic; the
+// value an ATOMS returns gives the carry into the next word (one add.cc / addc chain per word, no branches); above PW
+// only a pending carry travels on.  The top word's carry-out is the overflow the host's width bound proves impossible.
 template <int NW, int PW, bool SIGNED>
-__device__ __forceinline__ void block_accumulate(u32 saddr0, u32 wstride, u32 p0, u32 p1, u32 p2, u32 p3, bool neg)
+__device__ __forceinline__ void block_accumulate(u32 saddr0, u32 wstride, const u32 (&p)[8], bool neg)
 {
-    const u32 p[5] = {p0, p1, p2, p3, 0u};
     u32 addr = saddr0;
     if (SIGNED && neg) {
         u32 x = p[0], ovf = 0;
@@ -314,7 +328,7 @@ __device__ __forceinline__ void block_accumulate(u32 saddr0, u32 wstride, u32 p0
             }
             const u32 old = atoms_add(addr, 0u - x);
             const u32 borrow = ((old < x) ? 1u : 0u) | ovf; // x == 0 with ovf set: the word is unchanged, the borrow moves on
-            const u32 pn = (w + 1 < PW) ? p[(w + 1 < 4) ? w + 1 : 4] : 0u;
+            const u32 pn = (w + 1 < PW) ? p[(w + 1 < 8) ? w + 1 : 7] : 0u;
             x = pn + borrow;
             ovf = (x < borrow) ? 1u : 0u;
             addr += wstride;
@@ -329,7 +343,7 @@ __device__ __forceinline__ void block_accumulate(u32 saddr0, u32 wstride, u32 p0
                 return;
             }
             const u32 old = atoms_add(addr, x);
-            const u32 pn = (w + 1 < PW) ? p[(w + 1 < 4) ? w + 1 : 4] : 0u;
+            const u32 pn = (w + 1 < PW) ? p[(w + 1 < 8) ? w + 1 : 7] : 0u;
             u32 xn, ovfn;
             // xn = pn + ovf + carry(old + x);  ovfn = carry of that sum (ovf and the carry are never both set)
             asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %2, %3;\n\taddc.cc.u32 %0, %4, %5;\n\taddc.u32 %1, 0, 0;\n\t}"
@@ -369,7 +383,7 @@ __device__ __forceinline__ void block_for_each_tile(const uint4 *__restrict__ ti
 // MODE 1: bitmap zones (slot = rank of the code among the codes that occur; passes of at most cap entries).  The
 //         bitmap is an array of {bits, rank of the word's first bit} pairs, so a rank is one 8-byte shared load, one
 //         mask and one popcount.
-template <int NW, int PW, int MODE, bool SIGNED>
+template <int NW, int PW, int MODE, bool SIGNED, int LW>
 __global__ void __launch_bounds__(1024, 1) k_block(const BlockArgs ba)
 {
     constexpr u32 kThreads = 1024;
@@ -416,7 +430,7 @@ __global__ void __launch_bounds__(1024, 1) k_block(const BlockArgs ba)
             __syncthreads();
             block_for_each_tile(ba.tiles, &s_next, t1, lane, [&](const uint4 &t) {
                 if (t.z >> 31) { // truncation: some products of this tile exceed the degree limit
-                    block_tile_loop<1>(a.A, a.B, t, lane, [&](const uint4 &av, const uint4 &bv) {
+                    block_tile_loop<1, LW>(a.A, a.B, a.A1, a.B1, t, lane, [&](const uint4 &av, const uint4 &bv, const uint2 &, const uint2 &) {
                         if ((av.y >> 1) + (bv.y >> 1) > dlim) return;
                         ++my_pairs;
                         const u32 slot = av.x + bv.x - zlo;
@@ -424,7 +438,7 @@ __global__ void __launch_bounds__(1024, 1) k_block(const BlockArgs ba)
                     });
                 } else {
                     if (lane == 0) my_pairs += (u64)(t.z & 1023u) * ((t.z >> 10) & 127u);
-                    block_tile_loop<0>(a.A, a.B, t, lane, [&](const uint4 &av, const uint4 &bv) {
+                    block_tile_loop<0, LW>(a.A, a.B, a.A1, a.B1, t, lane, [&](const uint4 &av, const uint4 &bv, const uint2 &, const uint2 &) {
                         const u32 slot = av.x + bv.x - zlo;
                         reds_or(bm_s + (slot >> 5) * 8u, 1u << (slot & 31u));
                     });
@@ -497,7 +511,7 @@ __global__ void __launch_bounds__(1024, 1) k_block(const BlockArgs ba)
             }
             if (tid == 0) s_next = tp0;
             __syncthreads();
-            auto accumulate = [&](const uint4 &av, const uint4 &bv) {
+            auto accumulate = [&](const uint4 &av, const uint4 &bv, const uint2 &ah, const uint2 &bh) {
                 const u32 code = av.x + bv.x;
                 if (MODE == 1 && !single && (code < c0 || code >= c1)) return;
                 const u32 slot = code - zlo;
@@ -509,20 +523,30 @@ __global__ void __launch_bounds__(1024, 1) k_block(const BlockArgs ba)
                     e = slot;
                 }
                 const u64 ma = (u64)av.z | ((u64)av.w << 32), mb = (u64)bv.z | ((u64)bv.w << 32);
-                const u64 plo = ma * mb, phi = __umul64hi(ma, mb);
-                block_accumulate<NW, PW, SIGNED>(acc_s + e * 4u, wstride, (u32)plo, (u32)(plo >> 32), (u32)phi,
-                                                 (u32)(phi >> 32), SIGNED && (((av.y ^ bv.y) & 1u) != 0));
+                u32 pw[8];
+                if (LW == 1) {
+                    const u64 plo = ma * mb, phi = __umul64hi(ma, mb);
+                    pw[0] = (u32)plo, pw[1] = (u32)(plo >> 32), pw[2] = (u32)phi, pw[3] = (u32)(phi >> 32);
+                    pw[4] = pw[5] = pw[6] = pw[7] = 0u;
+                } else {
+                    const u64 xa[2] = {ma, (u64)ah.x | ((u64)ah.y << 32)}, xb[2] = {mb, (u64)bh.x | ((u64)bh.y << 32)};
+                    u64 pr[4];
+                    mag_mul<2, 2>(xa, xb, pr);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) pw[2 * q] = (u32)pr[q], pw[2 * q + 1] = (u32)(pr[q] >> 32);
+                }
+                block_accumulate<NW, PW, SIGNED>(acc_s + e * 4u, wstride, pw, SIGNED && (((av.y ^ bv.y) & 1u) != 0));
             };
             block_for_each_tile(ba.tiles, &s_next, tp1, lane, [&](const uint4 &t) {
                 if (t.z >> 31) { // truncation: test the degree of every product of this tile
-                    block_tile_loop<2>(a.A, a.B, t, lane, [&](const uint4 &av, const uint4 &bv) {
+                    block_tile_loop<2, LW>(a.A, a.B, a.A1, a.B1, t, lane, [&](const uint4 &av, const uint4 &bv, const uint2 &ah, const uint2 &bh) {
                         if ((av.y >> 1) + (bv.y >> 1) > dlim) return;
                         if (MODE == 0) ++my_pairs;
-                        accumulate(av, bv);
+                        accumulate(av, bv, ah, bh);
                     });
                 } else {
                     if (MODE == 0 && lane == 0) my_pairs += (u64)(t.z & 1023u) * ((t.z >> 10) & 127u);
-                    block_tile_loop<2>(a.A, a.B, t, lane, accumulate);
+                    block_tile_loop<2, LW>(a.A, a.B, a.A1, a.B1, t, lane, accumulate);
                 }
             });
             __syncthreads();
@@ -592,47 +616,67 @@ __global__ void __launch_bounds__(1024, 1) k_block(const BlockArgs ba)
 
 // ------------------------------------------------------------------------------------------------ host side
 
-template <int NW, int PW, int MODE, bool SIGNED>
+template <int NW, int PW, int MODE, bool SIGNED, int LW>
 struct BlockKernel {
     static void set_smem(size_t bytes)
     {
-        cudaFuncSetAttribute(k_block<NW, PW, MODE, SIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaFuncSetAttribute(k_block<NW, PW, MODE, SIGNED, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     }
     static void launch(pk_ctx *ctx, const BlockArgs &ba, u32 grid, size_t smem)
     {
-        PK_LAUNCH(ctx, (k_block<NW, PW, MODE, SIGNED>), grid, 1024, smem, ba);
+        PK_LAUNCH(ctx, (k_block<NW, PW, MODE, SIGNED, LW>), grid, 1024, smem, ba);
     }
 };
 
-// The (accumulator words, product words) pairs the width bound can ask for: NW = ceil((prod_bits + cnt_bits + 1) / 32)
-// with cnt_bits <= 31, PW = min(4, ceil(prod_bits / 32)).
+// One-limb operands: the (accumulator words, product words) pairs the width bound can ask for:
+// NW = ceil((prod_bits + cnt_bits + 1) / 32) with cnt_bits <= 31, PW = min(4, ceil(prod_bits / 32)).
 #define PK_BLOCK_WIDTHS(X) X(2, 1) X(2, 2) X(3, 2) X(3, 3) X(4, 3) X(4, 4) X(5, 4) X(6, 4)
+// Two-limb operands (products of 65 .. 256 bits): PW = ceil(prod_bits / 32) and always one more accumulator word (the
+// count bits fit in it), signed accumulation for every sign mix -- fewer instances for the rarer case.
+#define PK_BLOCK_WIDTHS2(X) X(4, 3) X(5, 4) X(6, 5) X(7, 6) X(8, 7) X(9, 8)
 
 template <int NW, int PW>
 void block_set_smem_w(size_t b)
 {
-    BlockKernel<NW, PW, 0, false>::set_smem(b);
-    BlockKernel<NW, PW, 0, true>::set_smem(b);
-    BlockKernel<NW, PW, 1, false>::set_smem(b);
-    BlockKernel<NW, PW, 1, true>::set_smem(b);
+    BlockKernel<NW, PW, 0, false, 1>::set_smem(b);
+    BlockKernel<NW, PW, 0, true, 1>::set_smem(b);
+    BlockKernel<NW, PW, 1, false, 1>::set_smem(b);
+    BlockKernel<NW, PW, 1, true, 1>::set_smem(b);
+}
+
+template <int NW, int PW>
+void block_set_smem_w2(size_t b)
+{
+    BlockKernel<NW, PW, 0, true, 2>::set_smem(b);
+    BlockKernel<NW, PW, 1, true, 2>::set_smem(b);
 }
 
 template <int NW, int PW>
 void block_launch_w(pk_ctx *ctx, const BlockArgs &ba, u32 grid, size_t smem, u32 mode, bool is_signed)
 {
     if (mode == 0) {
-        if (is_signed) BlockKernel<NW, PW, 0, true>::launch(ctx, ba, grid, smem);
-        else BlockKernel<NW, PW, 0, false>::launch(ctx, ba, grid, smem);
+        if (is_signed) BlockKernel<NW, PW, 0, true, 1>::launch(ctx, ba, grid, smem);
+        else BlockKernel<NW, PW, 0, false, 1>::launch(ctx, ba, grid, smem);
     } else {
-        if (is_signed) BlockKernel<NW, PW, 1, true>::launch(ctx, ba, grid, smem);
-        else BlockKernel<NW, PW, 1, false>::launch(ctx, ba, grid, smem);
+        if (is_signed) BlockKernel<NW, PW, 1, true, 1>::launch(ctx, ba, grid, smem);
+        else BlockKernel<NW, PW, 1, false, 1>::launch(ctx, ba, grid, smem);
     }
 }
 
-inline bool block_width_supported(u32 NW, u32 PW)
+template <int NW, int PW>
+void block_launch_w2(pk_ctx *ctx, const BlockArgs &ba, u32 grid, size_t smem, u32 mode)
 {
-#define X(nw, pw) if (NW == nw && PW == pw) return true;
+    if (mode == 0) BlockKernel<NW, PW, 0, true, 2>::launch(ctx, ba, grid, smem);
+    else BlockKernel<NW, PW, 1, true, 2>::launch(ctx, ba, grid, smem);
+}
+
+inline bool block_width_supported(u32 NW, u32 PW, u32 LW)
+{
+#define X(nw, pw) if (LW == 1 && NW == nw && PW == pw) return true;
     PK_BLOCK_WIDTHS(X)
+#undef X
+#define X(nw, pw) if (LW == 2 && NW == nw && PW == pw) return true;
+    PK_BLOCK_WIDTHS2(X)
 #undef X
     return false;
 }
@@ -652,11 +696,14 @@ inline void block_configure(pk_ctx *ctx)
 #define X(nw, pw) block_set_smem_w<nw, pw>(dyn);
     PK_BLOCK_WIDTHS(X)
 #undef X
+#define X(nw, pw) block_set_smem_w2<nw, pw>(dyn);
+    PK_BLOCK_WIDTHS2(X)
+#undef X
 }
 
 struct BlockPlan {
     bool ok = false;
-    u32 NW = 0, PW = 0, mode = 0, grid = 0;
+    u32 NW = 0, PW = 0, LW = 1, mode = 0, grid = 0;
     u32 split = 0; // digits [0, split) form `lo`
     u32 S = 0;     // codes per block
     u32 Hz_max = 1;
@@ -680,12 +727,17 @@ inline BlockPlan block_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB)
 {
     const BlockTuning &t = ctx->block_tuning;
     BlockPlan bp;
-    if (t.disable || pl.LA != 1 || pl.LB != 1 || pl.n_vars < 2) return bp;
+    if (t.disable || pl.LA > 2 || pl.LB > 2 || pl.n_vars < 2) return bp;
     if (nA >= (1u << 22) || nB >= (1u << 22)) return bp; // tile records pack the column count in 22 bits
     if (pl.range > 0xFFFFFFFEull) return bp;
-    const u32 NW = std::max<u32>(2, (pl.prod_bits + pl.cnt_bits + 1 + 31) / 32);
-    const u32 PW = std::min<u32>(4, (pl.prod_bits + 31) / 32);
-    if (!block_width_supported(NW, PW)) return bp;
+    const u32 LW = std::max(pl.LA, pl.LB);
+    u32 NW = std::max<u32>(2, (pl.prod_bits + pl.cnt_bits + 1 + 31) / 32);
+    u32 PW = std::min<u32>(4, (pl.prod_bits + 31) / 32);
+    if (LW == 2) { // (two-limb operands whose product still fits 64 bits are rare: they take PW = 3 like the rest)
+        PW = std::max<u32>(3, (pl.prod_bits + 31) / 32);
+        NW = PW + 1;
+    }
+    if (!block_width_supported(NW, PW, LW)) return bp;
     const size_t budget = block_smem_budget(ctx);
     if (budget < (16u << 10)) return bp;
     const double W = (double)nA * (double)nB;
@@ -716,6 +768,7 @@ inline BlockPlan block_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB)
     if (pl.range + 2 * S >= 0xFFFFFFFFull) return bp;          // zone bounds are 32-bit
     bp.NW = NW;
     bp.PW = PW;
+    bp.LW = LW;
     bp.mode = mode;
     bp.split = split;
     bp.S = (u32)S;
@@ -901,6 +954,14 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     const StagingView g = staging_acquire(ctx, out_cap, nv, pl.out_limbs);
     BlockArgs ba{};
     ZoneArgs &za = ba.z;
+    // second limbs: a limb plane of u64 is bit-identical to the {lo, hi} word pairs the kernel loads; an operand that
+    // needs only one limb gets a zero plane
+    DevBuf zero1(ctx, bp.LW == 2 ? std::max(nA, nB) * 8 + 16 : 0);
+    if (bp.LW == 2) {
+        if (pl.LA < 2 || pl.LB < 2) CUDA_CHECK(cudaMemsetAsync(zero1.p, 0, std::max(nA, nB) * 8 + 16, ctx->stream));
+        za.A1 = (pl.LA == 2 && A->limbs >= 2) ? reinterpret_cast<const uint2 *>(A->planes + A->stride) : zero1.as<uint2>();
+        za.B1 = (pl.LB == 2 && B->limbs >= 2) ? reinterpret_cast<const uint2 *>(B->planes + B->stride) : zero1.as<uint2>();
+    }
     za.A = pa_p;
     za.nA = (u32)nA;
     za.B = pb_p;
@@ -938,8 +999,12 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     const u32 grid = std::min<u32>(bp.grid, nz);
     CUDA_CHECK(cudaEventRecord(ctx->ev_mul0, ctx->stream));
 #define X(nw, pw) \
-    if (bp.NW == nw && bp.PW == pw) block_launch_w<nw, pw>(ctx, ba, grid, bp.smem, bp.mode, is_signed);
+    if (bp.LW == 1 && bp.NW == nw && bp.PW == pw) block_launch_w<nw, pw>(ctx, ba, grid, bp.smem, bp.mode, is_signed);
     PK_BLOCK_WIDTHS(X)
+#undef X
+#define X(nw, pw) \
+    if (bp.LW == 2 && bp.NW == nw && bp.PW == pw) block_launch_w2<nw, pw>(ctx, ba, grid, bp.smem, bp.mode);
+    PK_BLOCK_WIDTHS2(X)
 #undef X
     CUDA_CHECK(cudaEventRecord(ctx->ev_mul1, ctx->stream));
     PK_LAUNCH(ctx, k_zone_scan, 1, 1024, 0, zone_count, zone_prefix, n_zones_dev, &ctx->d_ctr->n_out);

@@ -47,6 +47,7 @@ struct ZoneArgs {
     u32 nA;
     const uint4 *B;
     u32 nB;
+    const uint2 *A1, *B1; // block path, two-limb operands: the second limb of every magnitude (else unused)
     u32 lo, hi; // output partition of this call (tight codes, < 2^32)
     const u32 *cuts;        // zone z covers codes [cuts[z], cuts[z+1]): equal-work cuts built on the device
     const u32 *n_zones_dev; // number of zones (device-side value, decided by k_zone_cuts)

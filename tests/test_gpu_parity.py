@@ -416,6 +416,34 @@ def test_dynamic_benchmarks(ctx, which):
     assert_terms_equal(r, cpu_ref(a, b, nv, n_threads=8))
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("case", ["both_wide", "a_wide", "b_wide", "wide_trunc", "max_width"])
+def test_block_two_limb_operands(ctx, mode, case):
+    """The block kernel with operands of up to two limbs (products of up to 256 bits, accumulators of up to 9 words)."""
+    (f, g), nv = po.fateman_cancel_operands(7), 4
+    big, huge = 2 ** 64 - 1, 2 ** 100 + 12345
+    opt, kw = {}, {}
+    if case in ("both_wide", "wide_trunc"):
+        f = {k: v * big for k, v in f.items()}
+        g = {k: v * huge for k, v in g.items()}
+    elif case == "a_wide":
+        f = {k: v * huge for k, v in f.items()}
+    elif case == "b_wide":
+        g = {k: v * big * 3 for k, v in g.items()}
+    else:  # magnitudes just below 2^128 on both sides
+        f = {k: (2 ** 128 - 1 - i) * (1 if v > 0 else -1) for i, (k, v) in enumerate(f.items())}
+        g = {k: (2 ** 128 - 159 - 7 * i) * (1 if v > 0 else -1) for i, (k, v) in enumerate(g.items())}
+    if case == "wide_trunc":
+        opt, kw = dict(trunc_mode=1, max_degree=9), dict(max_degree=9)
+    ctx.set_tuning(block_mode=mode, block_min_tile=0)
+    try:
+        _, _, r = gpu_mul(ctx, f, g, nv, algo=pb.PK_ALGO_BLOCK, **opt)
+        assert ctx.stats()["algo"] == pb.PK_ALGO_BLOCK
+        assert_terms_equal(r, oracle_terms(po.p_mul(f, g, **kw), nv), f"{case} mode {mode}")
+    finally:
+        ctx.set_tuning(block_mode=0, block_min_tile=8)
+
+
 # ---------------------------------------------------------------------------------------------- wider coverage
 
 
