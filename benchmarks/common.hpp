@@ -52,22 +52,29 @@ inline pt pearce(int n, pt *g_out)
     return f;
 }
 
-// time `reps` products a * b through operator* (host series in, host series out), report the best and the GPU share
+// time `reps` products a * b through operator*.  The product is left where it is computed (HBM); reading its terms
+// brings it into the host hash_set once.  Both times are reported: the reference's benchmark times operator* alone, and
+// its result is a host container, so the comparable figure is the sum.
 inline int run(const char *name, const pt &a, const pt &b, std::size_t expected_size, int reps)
 {
     std::size_t size = 0;
-    double best = 1e300;
+    double best_mul = 1e300, best_host = 1e300;
     for (int r = 0; r < reps; ++r) {
         simple_timer timer(name);
         const pt res = a * b;
         size = res.size();
-        best = std::min(best, timer.elapsed_ms());
+        const double t_mul = timer.elapsed_ms();
+        res.materialise();
+        const double t_all = timer.elapsed_ms();
+        best_mul = std::min(best_mul, t_mul);
+        best_host = std::min(best_host, t_all - t_mul);
     }
     const pk_stats st = pb200::series_multiplier<pt>::last_stats();
-    std::printf("%s: %zu x %zu terms -> %zu terms, best operator* %.3f ms (device %.3f ms, pairing kernel %.3f ms), "
-                "%.1f G term-products/s end to end\n",
-                name, a.size(), b.size(), size, best, st.device_ms, st.mul_kernel_ms,
-                static_cast<double>(a.size()) * static_cast<double>(b.size()) / best / 1e6);
+    const double W = static_cast<double>(a.size()) * static_cast<double>(b.size());
+    std::printf("%s: %zu x %zu terms -> %zu terms; operator* %.3f ms with the result resident in HBM (device %.3f ms, pairing "
+                "kernel %.3f ms), + %.3f ms to fill the host hash_set; %.1f / %.2f G term-products/s\n",
+                name, a.size(), b.size(), size, best_mul, st.device_ms, st.mul_kernel_ms, best_host, W / best_mul / 1e6,
+                W / (best_mul + best_host) / 1e6);
     if (size != expected_size) {
         std::printf("FAILED: expected %zu terms\n", expected_size);
         return 1;

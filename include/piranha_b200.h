@@ -162,6 +162,10 @@ void pk_result_free(pk_ctx *ctx, pk_result *r);
 int pk_upload(pk_ctx *ctx, const pk_poly *p, pk_dpoly **out);
 /* out = a * b with everything staying in HBM (same semantics and errors as pk_mul). */
 int pk_mul_dev(pk_ctx *ctx, const pk_dpoly *a, const pk_dpoly *b, const pk_opts *opts, pk_dpoly **out);
+/* The bounds check of the multiplier's constructor alone (check_bounds, polynomial.hpp:1118-1194, :1291-1298): PK_OK, or
+ * PK_E_KEY_RANGE when an exponent of a * b could leave the Kronecker limits, PK_E_ARGS for mismatching symbol sets.
+ * Host arithmetic on the exponent bounds recorded at upload; nothing is computed on the device. */
+int pk_check_bounds(pk_ctx *ctx, const pk_dpoly *a, const pk_dpoly *b);
 /* Copy a device polynomial back into library-owned pinned host memory. */
 int pk_download(pk_ctx *ctx, const pk_dpoly *p, pk_result *out);
 void pk_dpoly_free(pk_ctx *ctx, pk_dpoly *p);

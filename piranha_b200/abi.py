@@ -21,7 +21,7 @@ ALGO_NAMES = {0: "auto", 1: "dense", 2: "hash", 3: "zone", 4: "block"}
 
 EXPORTED_SYMBOLS = [
     "pk_ctx_create", "pk_ctx_destroy", "pk_last_error", "pk_ctx_set_limits", "pk_ctx_get_limits", "pk_get_stats", "pk_ctx_set_tuning",
-    "pk_mul", "pk_result_free", "pk_upload", "pk_mul_dev", "pk_download", "pk_dpoly_free", "pk_dpoly_size",
+    "pk_mul", "pk_result_free", "pk_upload", "pk_mul_dev", "pk_check_bounds", "pk_download", "pk_dpoly_free", "pk_dpoly_size",
     "pk_dpoly_limbs", "pk_dpoly_nvars", "pk_dpoly_export", "pk_dpoly_export_padded", "pk_dpoly_digest",
 ]
 
@@ -97,6 +97,7 @@ def load_library():
     lib.pk_result_free.restype = None
     lib.pk_upload.argtypes = [vp, C.POINTER(PkPoly), C.POINTER(vp)]
     lib.pk_mul_dev.argtypes = [vp, vp, vp, C.POINTER(PkOpts), C.POINTER(vp)]
+    lib.pk_check_bounds.argtypes = [vp, vp, vp]
     lib.pk_download.argtypes = [vp, vp, C.POINTER(PkResult)]
     lib.pk_dpoly_free.argtypes = [vp, vp]
     lib.pk_dpoly_free.restype = None

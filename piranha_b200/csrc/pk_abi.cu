@@ -732,6 +732,25 @@ int pk_mul_dev(pk_ctx *ctx, const pk_dpoly *a, const pk_dpoly *b, const pk_opts 
     })
 }
 
+int pk_check_bounds(pk_ctx *ctx, const pk_dpoly *a, const pk_dpoly *b)
+{
+    if (!ctx || !a || !b) return PK_E_ARGS;
+    PK_TRY(ctx, {
+        if (a->n_vars != b->n_vars) fail(PK_E_ARGS, "incompatible arguments sets");
+        if (a->n_vars >= ctx->limits.size()) fail(PK_E_ARGS, "too many variables for the Kronecker codification");
+        if (a->n && b->n) {
+            cudaSetDevice(ctx->device);
+            ensure_meta(ctx, const_cast<pk_dpoly *>(a));
+            ensure_meta(ctx, const_cast<pk_dpoly *>(b));
+            for (u32 v = 0; v < a->n_vars; ++v) {
+                const __int128 lo = (__int128)a->emin[v] + b->emin[v], hi = (__int128)a->emax[v] + b->emax[v];
+                const i64 M = ctx->limits[a->n_vars][v];
+                if (lo < -(__int128)M || hi > (__int128)M) fail(PK_E_KEY_RANGE, "Kronecker monomial components are out of bounds");
+            }
+        }
+    })
+}
+
 int pk_download(pk_ctx *ctx, const pk_dpoly *p, pk_result *out)
 {
     if (!ctx || !p || !out) return PK_E_ARGS;

@@ -23,6 +23,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <iostream>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <stdexcept>
@@ -123,16 +124,25 @@ public:
         insert(term_type(Cf(c), Key{}));
     }
 
-    size_type size() const { return m_container.size(); }
-    bool empty() const { return m_container.empty(); }
+    // number of terms; a device-resident product answers without touching the host
+    size_type size() const { return m_host_valid ? m_container.size() : static_cast<size_type>(pk_dpoly_size(m_dev->p)); }
+    bool empty() const { return size() == 0; }
     const symbol_fset &get_symbol_set() const { return m_symbol_set; }
     void set_symbol_set(const symbol_fset &s)
     {
         if (!empty()) throw std::invalid_argument("cannot set arguments on a non-empty series");
         m_symbol_set = s;
     }
-    container_type &_container() { return m_container; }
-    const container_type &_container() const { return m_container; }
+    // the term container (series.hpp:2817-2828).  Reading it brings a device-resident result to the host (once);
+    // the non-const form also drops the device copy, because the caller may change the terms.
+    container_type &_container() { return host_mut(); }
+    const container_type &_container() const { return host(); }
+    // ---- device residency: a product stays in HBM until its terms are asked for, and
+    // an operand keeps the device copy made for its first product, so chains like f *= tmp (series.hpp:799-805) and pow
+    // never re-upload f nor download intermediate results
+    bool is_device_resident() const { return static_cast<bool>(m_dev); }
+    bool is_host_resident() const { return m_host_valid; }
+    void materialise() const { (void)host(); }
 
     // series::insert: add to an existing term or create it, drop zeros (series.hpp:2190)
     template <bool Sign = true>
@@ -140,14 +150,15 @@ public:
     {
         if (!t.is_compatible(m_symbol_set)) throw std::invalid_argument("cannot insert incompatible term");
         if (t.is_zero(m_symbol_set)) return;
-        auto it = m_container.find(t);
-        if (it == m_container.end()) {
+        container_type &c = host_mut();
+        auto it = c.find(t);
+        if (it == c.end()) {
             if (!Sign) t.m_cf = -t.m_cf;
-            m_container.insert(std::move(t));
+            c.insert(std::move(t));
         } else {
             if (Sign) it->m_cf += t.m_cf;
             else it->m_cf -= t.m_cf;
-            if (math::is_zero(it->m_cf)) m_container.erase(it);
+            if (math::is_zero(it->m_cf)) c.erase(it);
         }
     }
 
@@ -155,7 +166,7 @@ public:
     polynomial operator-() const
     {
         polynomial r(*this);
-        for (const auto &t : r.m_container) t.m_cf = -t.m_cf;
+        for (const auto &t : r.host_mut()) t.m_cf = -t.m_cf;
         return r;
     }
     polynomial &operator+=(const polynomial &o) { return *this = merged_binary(*this, o, true); }
@@ -206,7 +217,7 @@ public:
     polynomial pow(long long n) const
     {
         if (size() == 1u) {
-            const term_type &t = *m_container.begin();
+            const term_type &t = *host().begin();
             if (n >= 0 || t.m_cf == Cf(1) || t.m_cf == Cf(-1)) {
                 polynomial r;
                 r.m_symbol_set = m_symbol_set;
@@ -218,7 +229,7 @@ public:
         if (n < 0) throw std::invalid_argument("negative powers are supported only for single-term series with unit coefficient");
         polynomial r(1), b(*this);
         r.m_symbol_set = m_symbol_set;
-        r.m_container.clear();
+        r.host_mut().clear();
         r.insert(term_type(Cf(1), Key(std::vector<degree_type>(m_symbol_set.size(), 0))));
         unsigned long long e = static_cast<unsigned long long>(n);
         while (e) {
@@ -234,7 +245,7 @@ public:
         if (empty()) return degree_type(0);
         bool first = true;
         degree_type d = 0;
-        for (const auto &t : m_container) {
+        for (const auto &t : host()) {
             const degree_type td = t.m_key.degree(m_symbol_set);
             if (first || td > d) d = td;
             first = false;
@@ -245,8 +256,8 @@ public:
     Cf find_cf(const std::vector<degree_type> &exponents) const
     {
         if (exponents.size() != m_symbol_set.size()) throw std::invalid_argument("invalid number of exponents");
-        const auto it = m_container.find(term_type(Cf(0), Key(exponents)));
-        return it == m_container.end() ? Cf(0) : it->m_cf;
+        const auto it = host().find(term_type(Cf(0), Key(exponents)));
+        return it == host().end() ? Cf(0) : it->m_cf;
     }
 
     // ---- auto-truncation (polynomial.hpp:646-740): per-type static state under a mutex
@@ -302,7 +313,7 @@ public:
     friend std::ostream &operator<<(std::ostream &os, const polynomial &p)
     {
         std::vector<const term_type *> v;
-        for (const auto &t : p.m_container) v.push_back(&t);
+        for (const auto &t : p.host()) v.push_back(&t);
         std::sort(v.begin(), v.end(), [](const term_type *a, const term_type *b) { return a->m_key < b->m_key; });
         if (v.empty()) return os << "0";
         bool first = true;
@@ -325,8 +336,8 @@ public:
         if (merged == m_symbol_set) return *this;
         polynomial r;
         r.m_symbol_set = merged;
-        r.m_container.rehash(m_container.bucket_count());
-        for (const auto &t : m_container) r.m_container.insert(term_type(t.m_cf, t.m_key.merge_symbols(m_symbol_set, merged)));
+        r.m_container.rehash(host().bucket_count());
+        for (const auto &t : host()) r.m_container.insert(term_type(t.m_cf, t.m_key.merge_symbols(m_symbol_set, merged)));
         return r;
     }
 
@@ -345,7 +356,7 @@ private:
         merged.insert(b.m_symbol_set.begin(), b.m_symbol_set.end());
         polynomial r = a.extend_symbol_set(merged);
         const polynomial b2 = b.extend_symbol_set(merged);
-        for (const auto &t : b2.m_container) {
+        for (const auto &t : b2.host()) {
             if (plus) r.template insert<true>(t);
             else r.template insert<false>(t);
         }
@@ -356,16 +367,16 @@ private:
         polynomial r;
         r.m_symbol_set = m_symbol_set;
         if (math::is_zero(c)) return r;
-        r.m_container.rehash(m_container.bucket_count());
-        for (const auto &t : m_container) r.m_container.insert(term_type(t.m_cf * c, t.m_key));
+        r.m_container.rehash(host().bucket_count());
+        for (const auto &t : host()) r.m_container.insert(term_type(t.m_cf * c, t.m_key));
         return r;
     }
     bool same_terms(const polynomial &o) const
     {
         if (size() != o.size()) return false;
-        for (const auto &t : m_container) {
-            const auto it = o.m_container.find(t);
-            if (it == o.m_container.end() || it->m_cf != t.m_cf) return false;
+        for (const auto &t : host()) {
+            const auto it = o.host().find(t);
+            if (it == o.host().end() || it->m_cf != t.m_cf) return false;
         }
         return true;
     }
@@ -390,8 +401,63 @@ private:
         return v;
     }
 
+    // ---- host / device state
+    struct device_terms { // owns one pk_dpoly (immutable once created, so copies of the series share it)
+        pk_dpoly *p = nullptr;
+        ~device_terms()
+        {
+            if (p) {
+                try {
+                    pk_dpoly_free(gpu::context(), p);
+                } catch (...) {
+                }
+            }
+        }
+    };
+    static constexpr bool gpu_type = std::is_same<Cf, integer>::value && std::is_same<Key, kronecker_monomial<std::int64_t>>::value;
+    const container_type &host() const
+    {
+        if (!m_host_valid) download();
+        return m_container;
+    }
+    container_type &host_mut()
+    {
+        if (!m_host_valid) download();
+        m_dev.reset();
+        return m_container;
+    }
+    // device terms -> host container: rehash + _unique_insert + _update_size, as sparse_kronecker_multiplication fills its
+    // result (polynomial.hpp:1666-1667, :1750-1754, base_series_multiplier.hpp:934)
+    void download() const
+    {
+        if constexpr (gpu_type) {
+            pk_ctx *ctx = gpu::context();
+            pk_result r{};
+            gpu::check(ctx, pk_download(ctx, m_dev->p, &r));
+            try {
+                m_container.clear();
+                m_container.rehash(std::max<std::size_t>(1, r.n));
+                for (std::uint64_t i = 0; i < r.n; ++i) {
+                    term_type t(integer::from_limbs(r.sign[i], r.mag + i * r.limbs, r.limbs), Key::from_int(r.key[i]));
+                    m_container._unique_insert(std::move(t), m_container._bucket_from_hash(static_cast<std::size_t>(r.key[i])));
+                }
+                m_container._update_size(r.n);
+            } catch (...) {
+                pk_result_free(ctx, &r);
+                m_container.clear();
+                throw;
+            }
+            pk_result_free(ctx, &r);
+            m_host_valid = true;
+        }
+    }
+    template <typename, typename>
+    friend class series_multiplier;
+
     symbol_fset m_symbol_set;
-    container_type m_container;
+    mutable container_type m_container;
+    mutable bool m_host_valid = true;
+    mutable std::shared_ptr<device_terms> m_dev;
 };
 
 namespace math
@@ -406,7 +472,8 @@ inline polynomial<Cf, Key> pow(const polynomial<Cf, Key> &p, long long n)
 // ------------------------------------------------------------------------------------------------ the drop-in
 
 // series_multiplier<polynomial<integer, kronecker_monomial<int64_t>>>: same protocol and member names as
-// polynomial.hpp:991-1968, with the work done by pk_mul().
+// polynomial.hpp:991-1968, with the work done by the C ABI.  Operands are brought to the device once (the copy stays
+// with the series), the product is pk_mul_dev and stays on the device until the caller reads its terms.
 template <>
 class series_multiplier<polynomial<integer, kronecker_monomial<std::int64_t>>, void>
 {
@@ -422,11 +489,12 @@ public:
     explicit series_multiplier(const series_type &s1, const series_type &s2) : m_ss(s1.get_symbol_set())
     {
         if (s1.get_symbol_set() != s2.get_symbol_set()) throw std::invalid_argument("incompatible arguments sets");
-        const series_type *p1 = &s1, *p2 = &s2;
-        if (p1->size() < p2->size()) std::swap(p1, p2); // larger series first
-        flatten(*p1, m_key1, m_mag1, m_sign1, m_limbs1);
-        flatten(*p2, m_key2, m_mag2, m_sign2, m_limbs2);
-        check_bounds();
+        m_s1 = &s1;
+        m_s2 = &s2;
+        if (m_s1->size() < m_s2->size()) std::swap(m_s1, m_s2); // larger series first
+        if (m_s1->empty() || m_s2->empty()) return;
+        pk_ctx *ctx = gpu::context();
+        gpu::check(ctx, pk_check_bounds(ctx, device(*m_s1), device(*m_s2)));
     }
     series_multiplier(const series_multiplier &) = delete;
     series_multiplier &operator=(const series_multiplier &) = delete;
@@ -486,86 +554,50 @@ private:
         o.struct_size = sizeof(pk_opts);
         return o;
     }
-    static void flatten(const series_type &s, std::vector<std::int64_t> &key, std::vector<std::uint64_t> &mag,
-                        std::vector<std::int8_t> &sign, std::uint32_t &limbs)
+    // The series' terms in HBM: uploaded on first use (the role of fill_term_pointers, base_series_multiplier.hpp:89-154:
+    // walk the container once, here into the structure-of-arrays form of the C ABI) and kept with the series.
+    static pk_dpoly *device(const series_type &s)
     {
-        const std::size_t n = s.size();
+        if (s.m_dev) return s.m_dev->p;
+        const auto &c = s.host();
+        const std::size_t n = c.size();
         std::size_t L = 1;
-        for (const auto &t : s._container()) L = std::max(L, t.m_cf.size());
-        // wider operands than the C ABI takes are reported by pk_mul as PK_E_CF_WIDTH -> std::overflow_error
-        limbs = static_cast<std::uint32_t>(L);
-        key.resize(n);
-        mag.assign(n * L, 0);
-        sign.resize(n);
+        for (const auto &t : c) L = std::max(L, t.m_cf.size());
+        // wider operands than the C ABI takes are reported by pk_upload as PK_E_CF_WIDTH -> std::overflow_error
+        std::vector<std::int64_t> key(n);
+        std::vector<std::uint64_t> mag(n * L, 0);
+        std::vector<std::int8_t> sign(n);
         std::size_t i = 0;
-        for (const auto &t : s._container()) {
+        for (const auto &t : c) {
             key[i] = t.m_key.get_int();
             for (std::size_t l = 0; l < t.m_cf.size(); ++l) mag[i * L + l] = t.m_cf.limb(l);
             sign[i] = static_cast<std::int8_t>(t.m_cf.sign());
             ++i;
         }
-    }
-    void minmax(const std::vector<std::int64_t> &key, std::vector<std::int64_t> &lo, std::vector<std::int64_t> &hi) const
-    {
-        const std::size_t nv = m_ss.size();
-        std::vector<std::int64_t> e(nv);
-        lo.assign(nv, 0);
-        hi.assign(nv, 0);
-        for (std::size_t i = 0; i < key.size(); ++i) {
-            kronecker_array<std::int64_t>::decode(e, key[i]);
-            for (std::size_t v = 0; v < nv; ++v) {
-                if (i == 0 || e[v] < lo[v]) lo[v] = e[v];
-                if (i == 0 || e[v] > hi[v]) hi[v] = e[v];
-            }
-        }
-    }
-    void check_bounds() const
-    {
-        const std::size_t nv = m_ss.size();
-        if (!nv || m_key1.empty() || m_key2.empty()) return;
-        std::vector<std::int64_t> lo1, hi1, lo2, hi2;
-        minmax(m_key1, lo1, hi1);
-        minmax(m_key2, lo2, hi2);
-        const auto &M = std::get<0>(kronecker_array<std::int64_t>::get_limits()[nv]);
-        for (std::size_t v = 0; v < nv; ++v) {
-            const __int128 lo = static_cast<__int128>(lo1[v]) + lo2[v], hi = static_cast<__int128>(hi1[v]) + hi2[v];
-            if (lo < -static_cast<__int128>(M[v]) || hi > static_cast<__int128>(M[v]))
-                throw std::overflow_error("Kronecker monomial components are out of bounds");
-        }
+        pk_ctx *ctx = gpu::context();
+        const pk_poly hp{n, static_cast<std::uint32_t>(s.get_symbol_set().size()), static_cast<std::uint32_t>(L), key.data(),
+                         mag.data(), sign.data()};
+        auto dev = std::make_shared<series_type::device_terms>();
+        gpu::check(ctx, pk_upload(ctx, &hp, &dev->p));
+        s.m_dev = std::move(dev);
+        return s.m_dev->p;
     }
     series_type run(const pk_opts &o) const
     {
         series_type retval;
         retval.set_symbol_set(m_ss); // polynomial.hpp:1651-1652
-        if (m_key1.empty() || m_key2.empty()) return retval; // :1654-1656
+        if (m_s1->empty() || m_s2->empty()) return retval; // :1654-1656
         pk_ctx *ctx = gpu::context();
-        const std::uint32_t nv = static_cast<std::uint32_t>(m_ss.size());
-        const pk_poly a{m_key1.size(), nv, m_limbs1, m_key1.data(), m_mag1.data(), m_sign1.data()};
-        const pk_poly b{m_key2.size(), nv, m_limbs2, m_key2.data(), m_mag2.data(), m_sign2.data()};
-        pk_result r{};
-        gpu::check(ctx, pk_mul(ctx, &a, &b, &o, &r));
-        try {
-            auto &c = retval._container();
-            c.rehash(std::max<std::size_t>(1, r.n));
-            for (std::uint64_t i = 0; i < r.n; ++i) {
-                term_type t(integer::from_limbs(r.sign[i], r.mag + i * r.limbs, r.limbs), key_type::from_int(r.key[i]));
-                c._unique_insert(std::move(t), c._bucket_from_hash(static_cast<std::size_t>(r.key[i])));
-            }
-            c._update_size(r.n);
-        } catch (...) {
-            pk_result_free(ctx, &r);
-            retval._container().clear(); // strong guarantee, polynomial.hpp:1961-1965
-            throw;
-        }
-        pk_result_free(ctx, &r);
+        auto dev = std::make_shared<series_type::device_terms>();
+        gpu::check(ctx, pk_mul_dev(ctx, device(*m_s1), device(*m_s2), &o, &dev->p));
+        // the result stays in HBM; reading its terms (or _container()) downloads it once into the hash_set
+        retval.m_dev = std::move(dev);
+        retval.m_host_valid = false;
         return retval;
     }
 
     symbol_fset m_ss;
-    std::vector<std::int64_t> m_key1, m_key2;
-    std::vector<std::uint64_t> m_mag1, m_mag2;
-    std::vector<std::int8_t> m_sign1, m_sign2;
-    std::uint32_t m_limbs1 = 1, m_limbs2 = 1;
+    const series_type *m_s1 = nullptr, *m_s2 = nullptr;
 };
 
 } // namespace pb200

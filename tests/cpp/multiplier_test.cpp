@@ -192,8 +192,49 @@ static void threads_test()
     }
 }
 
+static void residency_test()
+{
+    // a product stays on the device until its terms are read; operands keep the device copy of their first product, so
+    // chained products (f *= tmp, pow; series.hpp:799-805, :2333-2403) neither re-upload nor download in between
+    pt x{"x"}, y{"y"}, z{"z"};
+    const pt base = 1 + x + y + z;
+    CHECK(base.is_host_resident());
+    CHECK(!base.is_device_resident());
+    pt f = base * base;
+    CHECK(f.is_device_resident());
+    CHECK(!f.is_host_resident());
+    CHECK(base.is_device_resident()); // uploaded once, kept
+    CHECK_EQUAL(f.size(), 10u);       // answered from the device
+    CHECK(!f.is_host_resident());
+    pt g = f;
+    for (int i = 0; i < 6; ++i) g *= base; // (1+x+y+z)^8 without touching the host
+    CHECK(!g.is_host_resident());
+    CHECK_EQUAL(g.size(), 165u);
+    CHECK_EQUAL(g.find_cf({0, 0, 0}), integer(1)); // first read: materialised
+    CHECK(g.is_host_resident());
+    CHECK(g.is_device_resident());
+    CHECK_EQUAL(g.find_cf({2, 3, 3}), integer(560)); // 8! / (2! 3! 3! 0!)
+    g += 1; // a host-side change drops the device copy
+    CHECK(!g.is_device_resident());
+    CHECK_EQUAL(g.find_cf({0, 0, 0}), integer(2));
+    CHECK_EQUAL((g * base).find_cf({0, 0, 0}), integer(2));
+    // copies share the device terms; changing one does not change the other
+    pt h = f;
+    h -= x * x;
+    CHECK_EQUAL(f.find_cf({2, 0, 0}), integer(1));
+    CHECK_EQUAL(h.find_cf({2, 0, 0}), integer(0));
+    // an empty product is an empty series with the symbol set kept
+    pt::set_auto_truncate_degree(-1);
+    const pt e = base * base;
+    pt::unset_auto_truncate_degree();
+    CHECK_EQUAL(e.size(), 0u);
+    CHECK_EQUAL(e, 0);
+    CHECK((e.get_symbol_set() == symbol_fset{"x", "y", "z"}));
+}
+
 int main()
 {
+    RUN_TEST(residency_test);
     RUN_TEST(bounds_test);
     RUN_TEST(multiplication_test);
     RUN_TEST(pearce_test);
