@@ -19,6 +19,8 @@
 // built: pairs of groups outside the partition never become tiles.
 #pragma once
 
+#include <chrono>
+
 #include <cub/device/device_scan.cuh>
 
 #include "pk_zone.cuh"
@@ -818,6 +820,15 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
 {
     const u64 nA = A->n, nB = B->n;
     const bool trunc = degA != nullptr;
+    const bool timing = getenv("PK_TIMING") != nullptr; // debug: host wall time of every phase (adds stream syncs)
+    auto t_prev = std::chrono::steady_clock::now();
+    auto phase = [&](const char *what) {
+        if (!timing) return;
+        cudaStreamSynchronize(ctx->stream);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[pk block] %-18s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     if (trunc) { // degree offsets are 31-bit: bound the degree span of each operand by its exponent spans
         for (const pk_dpoly *P : {A, B}) {
             unsigned __int128 span = 0;
@@ -857,6 +868,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
         PK_LAUNCH(ctx, k_pack_operand, grid_for(nB, 256), 256, 0, keyB, B->planes, pb_p, nB);
     }
 
+    phase("pack");
     // ---- groups of equal hi
     const u64 magicS = (u64)((((unsigned __int128)1) << 64) / S) + 1;
     DevBuf tabA(ctx, HR * 8), tabB(ctx, HR * 8), glA(ctx, nA * 4), glB(ctx, nB * 4), gcnt(ctx, 16);
@@ -871,6 +883,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     readback(ctx, hg, gcnt.p, 8);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     const u32 GA = hg[0], GB = hg[1];
+    phase("groups");
     const u64 pairs = (u64)GA * GB;
     // tiny groups: the tile list would be as long as the product itself
     if ((unsigned __int128)pairs * bt.min_tile > w_bound || pairs >= (1ull << 31)) return nullptr;
@@ -951,7 +964,9 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     if (lpt) PK_LAUNCH(ctx, k_block_order, 1, 1024, 0, tstart.as<u32>(), n_h, (u32)Hz, nz, order, n_active_dev, n_zones_dev);
     else PK_LAUNCH(ctx, k_block_natural_order, 1, 1, 0, nz, n_active_dev, n_zones_dev);
 
+    phase("tile list");
     const StagingView g = staging_acquire(ctx, out_cap, nv, pl.out_limbs);
+    phase("staging");
     BlockArgs ba{};
     ZoneArgs &za = ba.z;
     // second limbs: a limb plane of u64 is bit-identical to the {lo, hi} word pairs the kernel loads; an operand that
@@ -1007,6 +1022,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     PK_BLOCK_WIDTHS2(X)
 #undef X
     CUDA_CHECK(cudaEventRecord(ctx->ev_mul1, ctx->stream));
+    phase("k_block");
     PK_LAUNCH(ctx, k_zone_scan, 1, 1024, 0, zone_count, zone_prefix, n_zones_dev, &ctx->d_ctr->n_out);
     MulCounters *hc = static_cast<MulCounters *>(ctx->h_scratch);
     readback(ctx, hc, ctx->d_ctr, sizeof(MulCounters));
@@ -1017,11 +1033,14 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     ctx->stats.acc_lanes = bp.NW;
     ctx->stats.chunk_bits = 0;
     ctx->stats.retries = bp.mode | (1024u << 8);
+    phase("scan + count");
     DPolyGuard e{ctx, new_dpoly(ctx, n_out, nv, pl.out_limbs)};
+    phase("result alloc");
     if (n_out) {
         PK_LAUNCH(ctx, k_zone_gather, grid_for(n_out, kGatherPerBlock), 256, 0, zone_count, zone_off, zone_prefix, n_zones_dev,
                   g.p->key, g.p->planes, g.p->stride, g.p->sign, e.p->key, e.p->planes, e.p->stride, e.p->sign, pl.out_limbs, n_out);
     }
+    phase("gather");
     return e.release();
 }
 

@@ -7,6 +7,8 @@ The cases follow the reference's own tests for this path:
   tests/kronecker_monomial_01.cpp:404-461      (term multiply: 2*3 = 6, 2*(-4) = -8 with exponent sums)
   benchmarks/*.cpp                             (result sizes of fateman1/2, pearce1, monagan1-5, truncated fateman1)
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -442,6 +444,27 @@ def test_block_two_limb_operands(ctx, mode, case):
         assert_terms_equal(r, oracle_terms(po.p_mul(f, g, **kw), nv), f"{case} mode {mode}")
     finally:
         ctx.set_tuning(block_mode=0, block_min_tile=8)
+
+
+def test_pearce2_full(ctx):
+    """benchmarks/pearce2.cpp:57 -- the largest configuration with a known answer that one GPU call and the CPU oracle
+    both finish in seconds: 20349^2 = 414 M products, 28 398 035 result terms (710 MB of result, ~10 GB of staging)."""
+    (f, g), nv = po.pearce_operands(16), 5
+    a, b = terms(f, nv, 1), terms(g, nv, 2)
+    da, db = ctx.upload(a, nv), ctx.upload(b, nv)
+    r = ctx.mul_dev(da, db)
+    st = ctx.stats()
+    assert len(r) == 28398035
+    assert st["algo"] == pb.PK_ALGO_BLOCK and st["term_products"] == 20349 ** 2
+    # the parts of a 4-way partition add up to the same digest (checksum of checksums)
+    parts = sum(ctx.mul_dev(da, db, part_index=p, part_count=4).digest() for p in range(4)) & ((1 << 64) - 1)
+    assert parts == r.digest()
+    key, mag, sign = r.download()
+    del r
+    assert_sorted_unique(key)
+    ref = cpu_ref(a, b, nv, n_threads=os.cpu_count() or 8)
+    assert_terms_equal((key, mag, sign), ref)
+    assert pb.digest_terms(*ref) == parts
 
 
 # ---------------------------------------------------------------------------------------------- wider coverage
