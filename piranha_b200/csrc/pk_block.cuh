@@ -132,6 +132,44 @@ __global__ void k_block_groups(const uint4 *__restrict__ rec, u32 n, u64 magicS,
     if (hi != next) tab[hi].y = i + 1;
 }
 
+// Bank-conflict-free lanes.  In a 32- or 64-term tile lane j holds term j of a chunk of gb and every lane adds into slot
+// lo_a + lo_b(j), so the bank of an ATOMS is (const + code_b(j)) mod 32: distinct banks for the 32 lanes iff their codes are
+// distinct mod 32.  Terms of a group in code order put 2-3 short rows of the lowest digit on a warp, which overlap by a
+// few banks (measured: 2.4 wavefronts per ATOMS).  The order of the terms INSIDE a group is free (a tile is any set of
+// terms of gb), so every group of B can be re-ordered by (rank within its residue class, residue class): positions
+// 32k .. 32k+31 then hold one term of each class as long as every class has more than k terms.  One warp per group.
+// Measured effect on the pairing kernel: -3 % (fateman1), -2 % (fateman2): the shared-memory atomic unit retires about
+// 11.4 lane-atomics per clock whether or not the lanes conflict (tools/microbench.cu), so the extra wavefronts that ncu
+// counts are not the bound.  Optional (tuning key "block_permute").
+__global__ void __launch_bounds__(256) k_block_permute(const uint4 *__restrict__ rec, const uint2 *__restrict__ hi_limb,
+                                                       const uint2 *__restrict__ tab, const u32 *__restrict__ glist,
+                                                       const u32 *__restrict__ gcount, u32 *__restrict__ rank_tmp,
+                                                       uint4 *__restrict__ out, uint2 *__restrict__ out_hi)
+{
+    __shared__ u32 s_cnt[8][32];
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const u32 G = __ldg(gcount);
+    for (u32 g = blockIdx.x * 8u + warp; g < G; g += gridDim.x * 8u) {
+        const uint2 r = __ldg(&tab[__ldg(&glist[g])]);
+        const u32 s = r.x, n = r.y - r.x;
+        s_cnt[warp][lane] = 0;
+        __syncwarp();
+        for (u32 i = lane; i < n; i += 32u) rank_tmp[s + i] = atomicAdd(&s_cnt[warp][__ldg(&rec[s + i].x) & 31u], 1u);
+        __syncwarp();
+        for (u32 i = lane; i < n; i += 32u) {
+            const u32 c = __ldg(&rec[s + i].x) & 31u, rk = rank_tmp[s + i];
+            u32 pos = 0; // terms before (rk, c) in (rank, class) order
+            for (u32 q = 0; q < 32u; ++q) {
+                const u32 cq = s_cnt[warp][q];
+                pos += min(cq, rk) + ((q < c && cq > rk) ? 1u : 0u);
+            }
+            out[s + pos] = __ldg(&rec[s + i]);
+            if (hi_limb) out_hi[s + pos] = __ldg(&hi_limb[s + i]);
+        }
+        __syncwarp();
+    }
+}
+
 constexpr u32 kTileCols = 32; // a full tile holds exactly one term of gb per lane
 
 struct TileArgs {
@@ -692,6 +730,7 @@ inline void block_configure(pk_ctx *ctx)
     t.force_mode = env_u32("PK_BLOCK_MODE", t.force_mode);
     t.natural = env_u32("PK_BLOCK_NATURAL", t.natural);
     t.wide = env_u32("PK_BLOCK_WIDE", t.wide);
+    t.permute = env_u32("PK_BLOCK_PERMUTE", t.permute);
     t.smem_limit = env_u32("PK_BLOCK_SMEM", t.smem_limit);
     t.radix0_residue = env_u32("PK_BLOCK_RADIX0", t.radix0_residue);
     const size_t dyn = ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0;
@@ -879,6 +918,26 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
               gcnt.as<u32>(), trunc ? gdegA.as<uint2>() : nullptr);
     PK_LAUNCH(ctx, k_block_groups, grid_for(nB, 256), 256, 0, pb_p, (u32)nB, magicS, tabB.as<uint2>(), glB.as<u32>(),
               gcnt.as<u32>() + 1, trunc ? gdegB.as<uint2>() : nullptr);
+    // lanes of a tile on distinct banks: re-order the terms inside every group of B (k_block_permute)
+    const bool permute = bt.permute != 0;
+    DevBuf pb_perm(ctx, permute ? (nB + 1) * 16 : 0), hi_perm(ctx, permute && bp.LW == 2 ? (nB + 1) * 8 : 0), rank_tmp(ctx, permute ? nB * 4 : 0);
+    DevBuf zero1(ctx, bp.LW == 2 ? std::max(nA, nB) * 8 + 16 : 0);
+    const uint2 *hiA = nullptr, *hiB = nullptr;
+    if (bp.LW == 2) {
+        // second limbs: a limb plane of u64 is bit-identical to the {lo, hi} word pairs the kernel loads; an operand that
+        // needs only one limb gets a zero plane
+        if (pl.LA < 2 || pl.LB < 2) CUDA_CHECK(cudaMemsetAsync(zero1.p, 0, std::max(nA, nB) * 8 + 16, ctx->stream));
+        hiA = (pl.LA == 2 && A->limbs >= 2) ? reinterpret_cast<const uint2 *>(A->planes + A->stride) : zero1.as<uint2>();
+        hiB = (pl.LB == 2 && B->limbs >= 2) ? reinterpret_cast<const uint2 *>(B->planes + B->stride) : zero1.as<uint2>();
+    }
+    const uint4 *pb_use = pb_p;
+    if (permute) {
+        const u32 pgrid = std::min<u32>(grid_for(nB, 64), (u32)ctx->sm_count * 8);
+        PK_LAUNCH(ctx, k_block_permute, pgrid, 256, 0, pb_p, hiB, tabB.as<uint2>(), glB.as<u32>(), gcnt.as<u32>() + 1,
+                  rank_tmp.as<u32>(), pb_perm.as<uint4>(), hi_perm.as<uint2>());
+        pb_use = pb_perm.as<uint4>();
+        if (bp.LW == 2) hiB = hi_perm.as<uint2>();
+    }
     u32 *hg = reinterpret_cast<u32 *>(static_cast<char *>(ctx->h_scratch) + 2048);
     readback(ctx, hg, gcnt.p, 8);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -969,17 +1028,11 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     phase("staging");
     BlockArgs ba{};
     ZoneArgs &za = ba.z;
-    // second limbs: a limb plane of u64 is bit-identical to the {lo, hi} word pairs the kernel loads; an operand that
-    // needs only one limb gets a zero plane
-    DevBuf zero1(ctx, bp.LW == 2 ? std::max(nA, nB) * 8 + 16 : 0);
-    if (bp.LW == 2) {
-        if (pl.LA < 2 || pl.LB < 2) CUDA_CHECK(cudaMemsetAsync(zero1.p, 0, std::max(nA, nB) * 8 + 16, ctx->stream));
-        za.A1 = (pl.LA == 2 && A->limbs >= 2) ? reinterpret_cast<const uint2 *>(A->planes + A->stride) : zero1.as<uint2>();
-        za.B1 = (pl.LB == 2 && B->limbs >= 2) ? reinterpret_cast<const uint2 *>(B->planes + B->stride) : zero1.as<uint2>();
-    }
+    za.A1 = hiA;
+    za.B1 = hiB;
     za.A = pa_p;
     za.nA = (u32)nA;
-    za.B = pb_p;
+    za.B = pb_use;
     za.nB = (u32)nB;
     za.lo = (u32)lo;
     za.hi = (u32)hi;

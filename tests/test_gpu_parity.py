@@ -264,6 +264,8 @@ def _variant_case(case):
     dict(block_mode=1, block_zone_work=1),
     dict(block_mode=2, block_zone_work=100000000, zone_span_log2=12),
     dict(block_mode=2, zone_span_log2=20),
+    dict(block_mode=1, block_permute=1),
+    dict(block_mode=2, block_permute=1, block_hz=2),
 ])
 @pytest.mark.parametrize("case", ["pearce", "cancel", "signed"])
 def test_block_variants(tuning, case):
@@ -544,12 +546,12 @@ def test_full_boxes_every_strategy(ctx, w0, w1):
             _, _, r = gpu_mul(ctx, f, g, 3, algo=algo)
             assert_terms_equal(r, expect, f"box {w0}x{w1} algo {algo}")
         for mode in (1, 2):
-            ctx.set_tuning(block_mode=mode, block_target=64)
+            ctx.set_tuning(block_mode=mode, block_target=64, block_permute=mode - 1)
             _, _, r = gpu_mul(ctx, f, g, 3, algo=pb.PK_ALGO_BLOCK)
             assert ctx.stats()["algo"] == pb.PK_ALGO_BLOCK
             assert_terms_equal(r, expect, f"box {w0}x{w1} block mode {mode}")
     finally:
-        ctx.set_tuning(block_min_tile=8, block_mode=0, block_target=1024)
+        ctx.set_tuning(block_min_tile=8, block_mode=0, block_target=1024, block_permute=0)
 
 
 def test_laurent_and_gcd_compaction(ctx):
