@@ -39,6 +39,8 @@ struct BlockTuning {
     uint32_t wide = 1;            // 1 = 64-term chunks of gb (two terms per lane) where the group is large enough
     uint32_t permute = 0;         // 1 = re-order the terms inside B's groups so that the lanes of a tile hit distinct banks
                                   // (measured: 2-3 % on the pairing kernel, the price of one more launch; off)
+    uint32_t hash = 0;            // sparse zones: 1 = try a one-walk shared-memory hash accumulation before the two-walk
+                                  // bitmap scheme (measured slower on pearce1: 0.60 vs 0.39 ms; experiment, off)
     uint32_t smem_limit = 0;      // bytes of shared memory a zone may use (0 = all): what is left over serves as L1
     uint32_t radix0_residue = 0;  // experiment: pad the radix of digit 0 so that radix mod 32 == this (1..32); 0 = off
 };

@@ -266,6 +266,10 @@ def _variant_case(case):
     dict(block_mode=2, zone_span_log2=20),
     dict(block_mode=1, block_permute=1),
     dict(block_mode=2, block_permute=1, block_hz=2),
+    dict(block_mode=2, block_hash=0),                     # two-walk bitmap scheme only
+    dict(block_mode=2, block_hash=0, block_hz=3, zone_cap=37),
+    dict(block_mode=2, block_hash=1, zone_cap=64),         # hash attempts that run out of probes and fall back
+    dict(block_mode=2, block_hash=1, block_hz=1000000),
 ])
 @pytest.mark.parametrize("case", ["pearce", "cancel", "signed"])
 def test_block_variants(tuning, case):
