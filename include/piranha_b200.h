@@ -65,7 +65,7 @@ typedef struct pk_dpoly pk_dpoly; /* a polynomial resident in HBM (sorted by key
 typedef struct pk_poly {
     uint64_t n;          /* number of terms (series::size()) */
     uint32_t n_vars;     /* size of the symbol set (m_ss.size()) */
-    uint32_t limbs;      /* 64-bit limbs per coefficient magnitude, 1..2 for operands */
+    uint32_t limbs;      /* 64-bit limbs per coefficient magnitude, 1..2 for operands (results: up to 5) */
     const int64_t *key;  /* n Kronecker codes, any order (hash_set order is unspecified) */
     const uint64_t *mag; /* n * limbs */
     const int8_t *sign;  /* n */
@@ -133,17 +133,21 @@ int pk_ctx_set_limits(pk_ctx *ctx, uint32_t n_vars, const int64_t *limits);
 /* Read the limits the context uses for `n_vars` components; returns PK_E_ARGS if n_vars is unsupported. */
 int pk_ctx_get_limits(const pk_ctx *ctx, uint32_t n_vars, int64_t *limits_out, int64_t *h_min_out, int64_t *h_max_out);
 int pk_get_stats(pk_ctx *ctx, pk_stats *out);
-/* Kernel tuning knobs (the analogue of piranha::tuning, tuning.hpp:54-60).  Keys: "zone_target" (zones per product,
- * 0 = 12 per SM), "zone_chunk" (consecutive zones per work unit), "zone_span_log2" (max log2 codes per bitmap zone),
- * "zone_cap" (force a small accumulator capacity; tests), "zone_mode" (0 auto, 1 dense, 2 bitmap), "zone_disable",
- * "zone_cursor_bytes" (memory allowed for row cursors, 0 = binary search per row per zone), "zone_tpb" (threads per
- * block: 0 auto, 256, 512, 1024), "zone_uniform" (1 = equal-span zones instead of equal-work zones); for the block
- * path "block_disable", "block_target" (products per tile), "block_zone_work" (products per zone aimed at),
- * "block_min_tile", "block_mode" (0 auto, 1 dense, 2 bitmap), "block_hz" (blocks per zone),
- * "block_natural" (1 = zones claimed in code order instead of heaviest first); for pk_mul "pipe_parts" (output parts
- * of a pipelined product whose device-to-host copy overlaps the computation of the next part; 0 = off, the default) and
- * "pipe_min_products".
- * Never changes results, only how they are computed. */
+/* Kernel tuning knobs (the analogue of piranha::tuning, tuning.hpp:54-60).  Never change results, only how they are
+ * computed.  Keys:
+ *   zone path   "zone_target" (zones per product, 0 = 12 per SM), "zone_chunk" (consecutive zones per work unit),
+ *               "zone_span_log2" (max log2 codes per bitmap zone), "zone_cap" (force a small accumulator capacity; tests),
+ *               "zone_mode" (0 auto, 1 dense, 2 bitmap), "zone_disable", "zone_cursor_bytes" (memory for row cursors,
+ *               0 = binary search per row per zone), "zone_tpb" (0 auto, 256, 512, 1024), "zone_uniform" (1 = equal-span zones)
+ *   block path  "block_disable", "block_target" (products per tile), "block_zone_work" (products per zone aimed at),
+ *               "block_min_tile" (decline when the average pair of groups is smaller), "block_mode" (0 auto, 1 dense,
+ *               2 bitmap), "block_hz" (blocks per zone), "block_natural" (1 = zones claimed in code order instead of
+ *               heaviest first), "block_wide" (64-term tiles), "block_smem" (bytes of shared memory per zone, 0 = all)
+ *               and the measured-and-rejected experiments, all off: "block_permute" (bank-conflict-free order inside
+ *               groups), "block_hash" (one-walk hash accumulation for sparse zones), "block_radix0" (pad the radix of
+ *               digit 0 to a residue mod 32)
+ *   pk_mul      "pipe_parts" (output parts of a pipelined product whose device-to-host copy overlaps the computation of
+ *               the next part; 0 = off, the default), "pipe_min_products", "pipe_test_small" (tests) */
 int pk_ctx_set_tuning(pk_ctx *ctx, const char *key, uint64_t value);
 
 /* ---- host-to-host product: the call behind series_multiplier::operator()() --------------------------------- */

@@ -17,14 +17,6 @@ namespace pk
 
 // ------------------------------------------------------------------------------------------------ plumbing
 
-// AoS magnitudes [n][limbs] -> limb planes [limbs][stride]
-__global__ void k_aos_to_planes(const u64 *__restrict__ aos, u64 *__restrict__ planes, u64 n, u32 limbs, u64 stride)
-{
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    for (u32 l = 0; l < limbs; ++l) planes[l * stride + i] = aos[i * limbs + l];
-}
-
 // limb planes -> AoS rows of out_limbs >= limbs words (missing high limbs are zero)
 __global__ void k_planes_to_aos(const u64 *__restrict__ planes, u64 *__restrict__ aos, u64 n, u32 limbs, u64 stride,
                                 u32 out_limbs)
@@ -38,13 +30,6 @@ __global__ void k_iota32(u32 *out, u64 n)
 {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (u32)i;
-}
-
-// keys with the sign bit flipped sort as signed integers under an unsigned radix sort
-__global__ void k_flip_keys(const i64 *__restrict__ in, u64 *__restrict__ out, u64 n)
-{
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (u64)in[i] ^ kSignBit;
 }
 
 // gather terms through a permutation (after sorting by key)
