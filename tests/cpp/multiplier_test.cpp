@@ -14,6 +14,7 @@
 #include <thread>
 #include <vector>
 
+#include "../../piranha_b200/host/monomial.hpp"
 #include "../../piranha_b200/host/polynomial.hpp"
 #include "check.hpp"
 
@@ -35,6 +36,21 @@ static pt plain_product(const pt &a, const pt &b)
             k_type::multiply(t, t1, t2, ss);
             r.insert(t);
         }
+    return r;
+}
+
+// (x + y + 1)^3 * (x + 1) truncated to partial degree 3 in x: the untruncated product with the terms of higher x-degree dropped
+template <typename S>
+static S pt_partial_reference()
+{
+    S x{"x"}, y{"y"};
+    S::unset_auto_truncate_degree();
+    const S full = (x + y + 1).pow(3) * (x + 1);
+    S r;
+    r.set_symbol_set(full.get_symbol_set());
+    for (const auto &t : full._container())
+        if (t.m_key.unpack(full.get_symbol_set())[0] <= 3) r.insert(t);
+    S::set_auto_truncate_degree(3, {"x"});
     return r;
 }
 
@@ -232,9 +248,45 @@ static void residency_test()
     CHECK((e.get_symbol_set() == symbol_fset{"x", "y", "z"}));
 }
 
+static void unpacked_test()
+{
+    // unpacked exponent-vector keys go through the same GPU product (packed on the fly): benchmarks/fateman1_unpacked.cpp
+    // (reduced to power 10: 10626 terms) and fateman1_unpacked_truncation.cpp:56-59 (degree 20 keeps exactly the terms of f)
+    using ut = polynomial<integer, monomial<int>>;
+    ut x{"x"}, y{"y"}, z{"z"}, t{"t"};
+    auto f = 1 + x + y + z + t;
+    const auto base(f);
+    for (int i = 1; i < 10; ++i) f *= base;
+    const auto g = f + 1;
+    const auto r = f * g;
+    CHECK_EQUAL(r.size(), 10626u);
+    CHECK_EQUAL(r.find_cf({5, 5, 5, 5}), integer("11732745024"));
+    CHECK_EQUAL(r.find_cf({0, 0, 0, 0}), integer(2));
+    CHECK_EQUAL(ut::truncated_multiplication(f, g, 10).size(), 1001u);
+    ut::set_auto_truncate_degree(10);
+    CHECK_EQUAL((f * g).size(), 1001u);
+    ut::set_auto_truncate_degree(3, {"x"});
+    {
+        const ut expect = pt_partial_reference<ut>(); // (leaves the partial truncation set)
+        CHECK_EQUAL((x + y + 1).pow(3) * (x + 1), expect);
+    }
+    ut::unset_auto_truncate_degree();
+    // same answer as the Kronecker-keyed series
+    pt kx{"x"}, ky{"y"};
+    const auto kr = (1 + kx + ky).pow(7) * (1 - kx + ky).pow(5);
+    const auto ur = (1 + x + y).pow(7) * (1 - x + y).pow(5);
+    CHECK_EQUAL(kr.size(), ur.size());
+    for (const auto &term : ur._container()) {
+        const auto e = term.m_key.unpack(ur.get_symbol_set());
+        CHECK_EQUAL(kr.find_cf({e[0], e[1]}), term.m_cf);
+    }
+    CHECK_THROW((series_multiplier<ut>(x, y)), std::invalid_argument);
+}
+
 int main()
 {
     RUN_TEST(residency_test);
+    RUN_TEST(unpacked_test);
     RUN_TEST(bounds_test);
     RUN_TEST(multiplication_test);
     RUN_TEST(pearce_test);
