@@ -1044,6 +1044,32 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     if ((unsigned __int128)out_cap * (9 + 8 * pl.out_limbs) > (unsigned __int128)ctx->total_mem / 2) return nullptr;
 
     const u64 HR = pl.range / S + 2;
+    // ---- zone geometry: about zone_work products per zone, at least 4 zones per thread block when possible
+    const double avg_h = (double)w_bound / (double)n_h;
+    u64 Hz = (u64)std::max(1.0, (double)bt.zone_work / std::max(1.0, avg_h));
+    Hz = std::min<u64>(Hz, std::max<u64>(1, n_h / (4ull * bp.grid)));
+    if (bp.mode == 1) { // bitmap zones: keep the products of a zone near what one pass of entries holds (measured: pearce1)
+        const double cap_est = (double)(block_smem_budget(ctx) / ((bp.NW + 1) * 4));
+        Hz = std::min<u64>(Hz, (u64)std::max(1.0, cap_est / std::max(1.0, avg_h)));
+    }
+    Hz = std::max<u64>(1, std::min<u64>(Hz, bp.Hz_max));
+    if (bt.force_hz) Hz = std::max<u64>(1, std::min<u64>(bt.force_hz, bp.Hz_max));
+    while (!block_layout(ctx, bp, (u32)Hz)) {
+        if (Hz == 1) return nullptr;
+        Hz = (Hz + 1) / 2;
+    }
+    const u32 nz = (u32)((n_h + Hz - 1) / Hz);
+    // every array that must start at zero lives in ONE allocation cleared by ONE memset: group tables, group counters,
+    // zone bookkeeping, the tile counters of the count pass and the tile cursors of the scatter pass
+    const size_t z_tab = (size_t)HR * 8, z_book = (size_t)nz * 32 + 128, z_cnt = (((size_t)n_h + 1) * 4 + 15) & ~15ull;
+    const size_t zo_tabA = 0, zo_tabB = z_tab, zo_gcnt = 2 * z_tab, zo_book = zo_gcnt + 16, zo_cnt = zo_book + z_book,
+                 zo_cur = zo_cnt + z_cnt, z_total = zo_cur + z_cnt;
+    DevBuf zeroed(ctx, z_total);
+    CUDA_CHECK(cudaMemsetAsync(zeroed.p, 0, z_total, ctx->stream));
+    char *const zbase = zeroed.as<char>();
+    uint2 *const tabA_p = reinterpret_cast<uint2 *>(zbase + zo_tabA), *const tabB_p = reinterpret_cast<uint2 *>(zbase + zo_tabB);
+    u32 *const gcnt_p = reinterpret_cast<u32 *>(zbase + zo_gcnt);
+    u32 *const cnt_p = reinterpret_cast<u32 *>(zbase + zo_cnt), *const cur_p = reinterpret_cast<u32 *>(zbase + zo_cur);
     const bool packed = prepackA && prepackB && !trunc;
     DevBuf pa_own(ctx, packed ? 0 : (nA + 1) * 16), pb_own(ctx, packed ? 0 : (nB + 1) * 16), tdev(ctx, trunc ? sizeof(TruncDev) : 0);
     uint4 *const pa_p = packed ? const_cast<uint4 *>(prepackA) : pa_own.as<uint4>();
@@ -1068,14 +1094,11 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     phase("pack");
     // ---- groups of equal hi
     const u64 magicS = (u64)((((unsigned __int128)1) << 64) / S) + 1;
-    DevBuf tabA(ctx, HR * 8), tabB(ctx, HR * 8), glA(ctx, nA * 4), glB(ctx, nB * 4), gcnt(ctx, 16);
-    CUDA_CHECK(cudaMemsetAsync(tabA.p, 0, HR * 8, ctx->stream));
-    CUDA_CHECK(cudaMemsetAsync(tabB.p, 0, HR * 8, ctx->stream));
-    CUDA_CHECK(cudaMemsetAsync(gcnt.p, 0, 16, ctx->stream));
-    PK_LAUNCH(ctx, k_block_groups, grid_for(nA, 256), 256, 0, pa_p, (u32)nA, magicS, tabA.as<uint2>(), glA.as<u32>(),
-              gcnt.as<u32>(), trunc ? gdegA.as<uint2>() : nullptr);
-    PK_LAUNCH(ctx, k_block_groups, grid_for(nB, 256), 256, 0, pb_p, (u32)nB, magicS, tabB.as<uint2>(), glB.as<u32>(),
-              gcnt.as<u32>() + 1, trunc ? gdegB.as<uint2>() : nullptr);
+    DevBuf glA(ctx, nA * 4), glB(ctx, nB * 4);
+    PK_LAUNCH(ctx, k_block_groups, grid_for(nA, 256), 256, 0, pa_p, (u32)nA, magicS, tabA_p, glA.as<u32>(),
+              gcnt_p, trunc ? gdegA.as<uint2>() : nullptr);
+    PK_LAUNCH(ctx, k_block_groups, grid_for(nB, 256), 256, 0, pb_p, (u32)nB, magicS, tabB_p, glB.as<u32>(),
+              gcnt_p + 1, trunc ? gdegB.as<uint2>() : nullptr);
     // lanes of a tile on distinct banks: re-order the terms inside every group of B (k_block_permute)
     const bool permute = bt.permute != 0;
     DevBuf pb_perm(ctx, permute ? (nB + 1) * 16 : 0), hi_perm(ctx, permute && bp.LW == 2 ? (nB + 1) * 8 : 0), rank_tmp(ctx, permute ? nB * 4 : 0);
@@ -1091,13 +1114,13 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     const uint4 *pb_use = pb_p;
     if (permute) {
         const u32 pgrid = std::min<u32>(grid_for(nB, 64), (u32)ctx->sm_count * 8);
-        PK_LAUNCH(ctx, k_block_permute, pgrid, 256, 0, pb_p, hiB, tabB.as<uint2>(), glB.as<u32>(), gcnt.as<u32>() + 1,
+        PK_LAUNCH(ctx, k_block_permute, pgrid, 256, 0, pb_p, hiB, tabB_p, glB.as<u32>(), gcnt_p + 1,
                   rank_tmp.as<u32>(), pb_perm.as<uint4>(), hi_perm.as<uint2>());
         pb_use = pb_perm.as<uint4>();
         if (bp.LW == 2) hiB = hi_perm.as<uint2>();
     }
     u32 *hg = reinterpret_cast<u32 *>(static_cast<char *>(ctx->h_scratch) + 2048);
-    readback(ctx, hg, gcnt.p, 8);
+    readback(ctx, hg, gcnt_p, 8);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     const u32 GA = hg[0], GB = hg[1];
     phase("groups");
@@ -1105,21 +1128,6 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     // tiny groups: the tile list would be as long as the product itself
     if ((unsigned __int128)pairs * bt.min_tile > w_bound || pairs >= (1ull << 31)) return nullptr;
 
-    // ---- zone geometry: about zone_work products per zone, at least 4 zones per thread block when possible
-    const double avg_h = (double)w_bound / (double)n_h;
-    u64 Hz = (u64)std::max(1.0, (double)bt.zone_work / std::max(1.0, avg_h));
-    Hz = std::min<u64>(Hz, std::max<u64>(1, n_h / (4ull * bp.grid)));
-    if (bp.mode == 1) { // bitmap zones: keep the products of a zone near what one pass of entries holds (measured: pearce1)
-        const double cap_est = (double)(block_smem_budget(ctx) / ((bp.NW + 1) * 4));
-        Hz = std::min<u64>(Hz, (u64)std::max(1.0, cap_est / std::max(1.0, avg_h)));
-    }
-    Hz = std::max<u64>(1, std::min<u64>(Hz, bp.Hz_max));
-    if (bt.force_hz) Hz = std::max<u64>(1, std::min<u64>(bt.force_hz, bp.Hz_max));
-    while (!block_layout(ctx, bp, (u32)Hz)) {
-        if (Hz == 1) return nullptr;
-        Hz = (Hz + 1) / 2;
-    }
-    const u32 nz = (u32)((n_h + Hz - 1) / Hz);
     if (getenv("PK_BLOCK_DEBUG"))
         fprintf(stderr, "block path: S=%u split=%u n_h=%u Hz=%llu (max %u) zones=%u mode=%u NW=%u PW=%u cap=%u bm_words=%u smem=%zu GA=%u GB=%u\n",
                 S, bp.split, n_h, (unsigned long long)Hz, bp.Hz_max, nz, bp.mode, bp.NW, bp.PW, bp.cap, bp.bm_words, bp.smem, GA, GB);
@@ -1131,10 +1139,9 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
                             + (nB / kTileCols + 2 * (u64)GB) * (nA / 1023 + 1) + 64;
     if (max_tiles64 >= (1ull << 31)) return nullptr;
     const u32 max_tiles = (u32)max_tiles64;
-    DevBuf cnt(ctx, ((size_t)n_h + 1) * 4), tstart(ctx, ((size_t)n_h + 1) * 4), tiles(ctx, (size_t)max_tiles * 16);
-    // bookkeeping: zone work (u64), offsets (u64), prefix (u64) per zone; bump; counters; zone count + order (u32)
-    DevBuf book(ctx, (size_t)nz * 32 + 128);
-    u64 *zwork = book.as<u64>();
+    DevBuf tstart(ctx, ((size_t)n_h + 1) * 4), tiles(ctx, (size_t)max_tiles * 16);
+    // bookkeeping: (spare u64), offsets (u64), prefix (u64) per zone; bump; counters; zone count + order (u32)
+    u64 *zwork = reinterpret_cast<u64 *>(zbase + zo_book);
     u64 *zone_off = zwork + nz;
     u64 *zone_prefix = zone_off + nz;
     u64 *bump = zone_prefix + nz;
@@ -1143,13 +1150,11 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     u32 *n_active_dev = chunk_counter + 2;
     u32 *zone_count = chunk_counter + 4;
     u32 *order = zone_count + nz;
-    CUDA_CHECK(cudaMemsetAsync(book.p, 0, (size_t)nz * 32 + 128, ctx->stream));
-    CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, ((size_t)n_h + 1) * 4, ctx->stream));
     TileArgs ta{};
     ta.glistA = glA.as<u32>();
     ta.glistB = glB.as<u32>();
-    ta.tabA = tabA.as<uint2>();
-    ta.tabB = tabB.as<uint2>();
+    ta.tabA = tabA_p;
+    ta.tabB = tabB_p;
     ta.GA = GA;
     ta.GB = GB;
     ta.h_base = h_base;
@@ -1162,7 +1167,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     ta.gdegA = trunc ? gdegA.as<uint2>() : nullptr;
     ta.gdegB = trunc ? gdegB.as<uint2>() : nullptr;
     ta.trunc = trunc ? td : nullptr;
-    ta.cnt = cnt.as<u32>();
+    ta.cnt = cnt_p;
     ta.tstart = tstart.as<u32>();
     ta.tiles = tiles.as<uint4>();
     ta.max_tiles = max_tiles;
@@ -1171,11 +1176,11 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     PK_LAUNCH(ctx, (k_block_tiles<0>), pgrid, 256, 0, ta);
     {
         size_t tmp_bytes = 0;
-        CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt.as<u32>(), tstart.as<u32>(), (int)(n_h + 1), ctx->stream));
+        CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt_p, tstart.as<u32>(), (int)(n_h + 1), ctx->stream));
         DevBuf tmp(ctx, tmp_bytes);
-        CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, cnt.as<u32>(), tstart.as<u32>(), (int)(n_h + 1), ctx->stream));
+        CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, cnt_p, tstart.as<u32>(), (int)(n_h + 1), ctx->stream));
     }
-    CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, ((size_t)n_h + 1) * 4, ctx->stream));
+    ta.cnt = cur_p; // the scatter pass counts again, into its own zeroed cursors
     PK_LAUNCH(ctx, (k_block_tiles<1>), pgrid, 256, 0, ta);
     const bool lpt = !bt.natural && nz <= (1u << 17);
     if (lpt) PK_LAUNCH(ctx, k_block_order, 1, 1024, 0, tstart.as<u32>(), n_h, (u32)Hz, nz, order, n_active_dev, n_zones_dev);
