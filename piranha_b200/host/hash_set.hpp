@@ -196,6 +196,9 @@ public:
         return iterator(this, idx);
     }
     void _update_size(size_type n) { m_n_elements = n; }
+    // hint that `bucket` is about to receive an element (bulk fills touch the buckets in random order: one cache miss
+    // per element unless the bucket heads are requested a few elements ahead)
+    void _prefetch_bucket(size_type bucket) const { __builtin_prefetch(&m_heads[bucket], 1, 1); }
 
 private:
     std::vector<node> m_nodes;

@@ -438,6 +438,7 @@ private:
                 m_container.clear();
                 m_container.rehash(std::max<std::size_t>(1, r.n));
                 for (std::uint64_t i = 0; i < r.n; ++i) {
+                    if (i + 24 < r.n) m_container._prefetch_bucket(m_container._bucket_from_hash(static_cast<std::size_t>(r.key[i + 24])));
                     term_type t(integer::from_limbs(r.sign[i], r.mag + i * r.limbs, r.limbs), Key::from_int(r.key[i]));
                     m_container._unique_insert(std::move(t), m_container._bucket_from_hash(static_cast<std::size_t>(r.key[i])));
                 }
