@@ -109,7 +109,8 @@ typedef struct pk_stats {
     uint64_t table_slots;         /* accumulator slots allocated (dense range, hash capacity, or zone capacity) */
     uint32_t algo;                /* PK_ALGO_* actually used */
     uint32_t acc_lanes;           /* 64-bit lanes (dense/hash) or 32-bit words (zone) per accumulator */
-    uint32_t chunk_bits;          /* payload bits per lane (deferred-carry radix), 0 for the zone path */
+    uint32_t chunk_bits;          /* dense/hash: payload bits per lane (deferred-carry radix); block path: 32-bit words
+                                     of a product (= shared-memory atomics per term product); 0 for the zone path */
     uint32_t result_limbs;        /* limbs per result coefficient */
     uint32_t kernel_launches;     /* kernels launched by this call */
     uint32_t retries;             /* hash-capacity / zone-split retries */

@@ -1250,7 +1250,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     if (n_out > out_cap || (hc->flags & kFlagTableFull)) fail(PK_E_CUDA, "block path: a count exceeds its bound (internal error)");
     ctx->stats.table_slots = (u64)bp.cap;
     ctx->stats.acc_lanes = bp.NW;
-    ctx->stats.chunk_bits = 0;
+    ctx->stats.chunk_bits = bp.PW; // (block path: 32-bit words of a product = unconditional ATOMS per term product)
     ctx->stats.retries = bp.mode | (1024u << 8);
     phase("scan + count");
     DPolyGuard e{ctx, new_dpoly(ctx, n_out, nv, pl.out_limbs)};
