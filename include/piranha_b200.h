@@ -126,6 +126,10 @@ typedef struct pk_stats {
  * Fails with PK_E_CUDA when no usable GPU is present: there is no CPU fallback. */
 int pk_ctx_create(int device, void *stream, pk_ctx **out);
 void pk_ctx_destroy(pk_ctx *ctx);
+/* Release what the context keeps between products to make them cheap: the staging arrays of the shared-memory paths
+ * (up to min(term products, code range) terms, ~1 GB after a pearce1-sized product), idle pinned result buffers and the
+ * cached blocks of the device's stream-ordered memory pool.  The next product re-creates what it needs. */
+int pk_ctx_trim(pk_ctx *ctx);
 /* Message of the last error on this context (never NULL). */
 const char *pk_last_error(const pk_ctx *ctx);
 /* Override the Kronecker limits M_0..M_{n_vars-1} for `n_vars` components with the caller's

@@ -20,7 +20,7 @@ PK_ALGO_AUTO, PK_ALGO_DENSE, PK_ALGO_HASH, PK_ALGO_ZONE, PK_ALGO_BLOCK = range(5
 ALGO_NAMES = {0: "auto", 1: "dense", 2: "hash", 3: "zone", 4: "block"}
 
 EXPORTED_SYMBOLS = [
-    "pk_ctx_create", "pk_ctx_destroy", "pk_last_error", "pk_ctx_set_limits", "pk_ctx_get_limits", "pk_get_stats", "pk_ctx_set_tuning",
+    "pk_ctx_create", "pk_ctx_destroy", "pk_ctx_trim", "pk_last_error", "pk_ctx_set_limits", "pk_ctx_get_limits", "pk_get_stats", "pk_ctx_set_tuning",
     "pk_mul", "pk_result_free", "pk_upload", "pk_mul_dev", "pk_check_bounds", "pk_download", "pk_dpoly_free", "pk_dpoly_size",
     "pk_dpoly_limbs", "pk_dpoly_nvars", "pk_dpoly_export", "pk_dpoly_export_padded", "pk_dpoly_digest",
 ]
@@ -86,6 +86,7 @@ def load_library():
     lib.pk_ctx_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
     lib.pk_ctx_destroy.argtypes = [vp]
     lib.pk_ctx_destroy.restype = None
+    lib.pk_ctx_trim.argtypes = [vp]
     lib.pk_last_error.argtypes = [vp]
     lib.pk_last_error.restype = C.c_char_p
     lib.pk_ctx_set_limits.argtypes = [vp, u32, vp]
@@ -206,6 +207,10 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def trim(self):
+        """Release cached workspaces (staging arrays, idle pinned buffers, pooled device memory)."""
+        self._check(self.lib.pk_ctx_trim(self.handle))
 
     def _check(self, rc: int):
         if rc != PK_OK:

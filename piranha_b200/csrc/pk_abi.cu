@@ -635,6 +635,32 @@ void pk_ctx_destroy(pk_ctx *ctx)
     delete ctx;
 }
 
+int pk_ctx_trim(pk_ctx *ctx)
+{
+    if (!ctx) return PK_E_ARGS;
+    PK_TRY(ctx, {
+        cudaSetDevice(ctx->device);
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->staging) {
+            free_dpoly_arrays(ctx, ctx->staging);
+            delete ctx->staging;
+            ctx->staging = nullptr;
+            ctx->staging_cap = 0;
+        }
+        for (auto &b : ctx->pinned)
+            if (!b.in_use && b.ptr) {
+                cudaFreeHost(b.ptr);
+                b.ptr = nullptr;
+                b.bytes = 0;
+            }
+        ctx->pinned.erase(std::remove_if(ctx->pinned.begin(), ctx->pinned.end(), [](const PinnedBuf &b) { return !b.in_use && !b.ptr; }),
+                          ctx->pinned.end());
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    })
+}
+
 const char *pk_last_error(const pk_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 int pk_ctx_set_limits(pk_ctx *ctx, uint32_t n_vars, const int64_t *limits)

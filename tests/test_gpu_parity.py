@@ -635,6 +635,23 @@ def test_device_resident_chain(ctx):
     assert_terms_equal(sq.download(), oracle_terms(po.p_pow_multinomial(po._linear(4, [1, 1, 1, 1]), 20), nv))
 
 
+def test_trim_releases_and_products_still_work():
+    import torch
+
+    c2 = pb.Context(0)
+    try:
+        (f, g), nv = po.pearce_operands(6), 5
+        a, b = terms(f, nv, 1), terms(g, nv, 2)
+        r1 = c2.mul(a, b, nv)
+        free_before = torch.cuda.mem_get_info(0)[0]
+        c2.trim()
+        free_after = torch.cuda.mem_get_info(0)[0]
+        assert free_after >= free_before  # the staging arrays went back to the driver
+        assert_terms_equal(c2.mul(a, b, nv), r1)
+    finally:
+        c2.close()
+
+
 def test_custom_limits_table(ctx):
     """pk_ctx_set_limits: a caller whose standard library produced a different Kronecker table."""
     c2 = pb.Context(0)
