@@ -143,7 +143,8 @@ int pk_get_stats(pk_ctx *ctx, pk_stats *out);
  *   zone path   "zone_target" (zones per product, 0 = 12 per SM), "zone_chunk" (consecutive zones per work unit),
  *               "zone_span_log2" (max log2 codes per bitmap zone), "zone_cap" (force a small accumulator capacity; tests),
  *               "zone_mode" (0 auto, 1 dense, 2 bitmap), "zone_disable", "zone_cursor_bytes" (memory for row cursors,
- *               0 = binary search per row per zone), "zone_tpb" (0 auto, 256, 512, 1024), "zone_uniform" (1 = equal-span zones)
+ *               0 = binary search per row per zone), "zone_tpb" (accepted, no effect: 1024 threads per block), "zone_uniform" (1 =
+ *               equal-span zones)
  *   block path  "block_disable", "block_target" (products per tile), "block_zone_work" (products per zone aimed at),
  *               "block_min_tile" (decline when the average pair of groups is smaller), "block_mode" (0 auto, 1 dense,
  *               2 bitmap), "block_hz" (blocks per zone), "block_natural" (1 = zones claimed in code order instead of

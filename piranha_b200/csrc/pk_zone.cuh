@@ -616,9 +616,7 @@ void zone_set_smem_nt(size_t b)
 template <int NW>
 void zone_set_smem_nw(size_t optin)
 {
-    zone_set_smem_nt<NW, 1024>(optin);
-    zone_set_smem_nt<NW, 512>(optin);
-    zone_set_smem_nt<NW, 256>(optin);
+    zone_set_smem_nt<NW, 1024>(optin); // (256- and 512-thread variants were measured slower and are no longer instantiated)
 }
 
 template <int NW, int TPB>
@@ -636,9 +634,8 @@ void zone_launch_nt(pk_ctx *ctx, const ZoneArgs &za, u32 grid, size_t smem, u32 
 template <int NW>
 void zone_launch_nw(pk_ctx *ctx, const ZoneArgs &za, u32 grid, size_t smem, u32 mode, bool is_signed, u32 tpb)
 {
-    if (tpb == 256) zone_launch_nt<NW, 256>(ctx, za, grid, smem, mode, is_signed);
-    else if (tpb == 512) zone_launch_nt<NW, 512>(ctx, za, grid, smem, mode, is_signed);
-    else zone_launch_nt<NW, 1024>(ctx, za, grid, smem, mode, is_signed);
+    (void)tpb;
+    zone_launch_nt<NW, 1024>(ctx, za, grid, smem, mode, is_signed);
 }
 
 inline void zone_configure(pk_ctx *ctx)
@@ -693,8 +690,7 @@ inline ZonePlan zone_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB, u64 sub_r
     const u64 avg_span = (sub_range + target - 1) / target;
     // cost of one candidate (mode, threads per block): a row visit costs about half a product, bitmap zones walk twice
     double best_cost = 1e300;
-    for (u32 tpb : {1024u, 512u, 256u}) {
-        if (t.tpb && t.tpb != tpb) continue;
+    for (u32 tpb : {1024u}) { // (one block of 1024 threads per SM: the smaller variants lost every sweep)
         const u32 ctas = 1024 / tpb;
         size_t budget = (ctx->smem_per_sm > ctas * 1024 ? (ctx->smem_per_sm - ctas * 1024) / ctas : 0);
         budget = std::min(budget, ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0);
