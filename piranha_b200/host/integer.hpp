@@ -140,6 +140,67 @@ public:
     friend bool operator<=(const integer &a, const integer &b) { return !(b < a); }
     friend bool operator>=(const integer &a, const integer &b) { return !(a < b); }
 
+    // truncating division (quotient rounded towards zero, remainder with the sign of the dividend), by binary long division:
+    // only the rational coefficient path uses it (lcm / gcd of denominators), never the product itself
+    static void divmod(const integer &a, const integer &b, integer &q, integer &r)
+    {
+        if (!b.m_size) throw std::domain_error("integer division by zero");
+        integer quo, rem;
+        const unsigned nb = a.bits();
+        for (unsigned i = nb; i-- > 0;) {
+            rem.shl1((a.m_mag[i / 64] >> (i % 64)) & 1u);
+            if (cmp_mag(rem, b) >= 0) {
+                integer d(b);
+                d.m_neg = false;
+                rem.m_neg = false;
+                rem -= d;
+                quo.m_mag[i / 64] |= limb_t(1) << (i % 64);
+                if (i / 64 + 1 > quo.m_size) quo.m_size = i / 64 + 1;
+            }
+        }
+        quo.m_neg = quo.m_size && (a.m_neg != b.m_neg);
+        rem.m_neg = rem.m_size && a.m_neg;
+        q = quo;
+        r = rem;
+    }
+    friend integer operator/(const integer &a, const integer &b)
+    {
+        integer q, r;
+        divmod(a, b, q, r);
+        return q;
+    }
+    friend integer operator%(const integer &a, const integer &b)
+    {
+        integer q, r;
+        divmod(a, b, q, r);
+        return r;
+    }
+    integer abs() const
+    {
+        integer r(*this);
+        r.m_neg = false;
+        return r;
+    }
+    static integer gcd(integer a, integer b)
+    {
+        a.m_neg = b.m_neg = false;
+        while (b.m_size) {
+            if (a.m_size <= 1 && b.m_size <= 1) { // both fit one limb: finish in machine arithmetic
+                limb_t x = a.m_mag[0], y = b.m_mag[0];
+                while (y) {
+                    const limb_t t = x % y;
+                    x = y;
+                    y = t;
+                }
+                return integer(x);
+            }
+            integer t = a % b;
+            a = b;
+            b = t;
+        }
+        return a;
+    }
+
     integer pow(unsigned n) const
     {
         integer r(1), b(*this);
@@ -220,6 +281,19 @@ private:
             m_neg = neg;
         }
     }
+    void shl1(limb_t low_bit) // magnitude = magnitude * 2 + low_bit
+    {
+        limb_t carry = low_bit;
+        for (unsigned i = 0; i < m_size; ++i) {
+            const limb_t nc = m_mag[i] >> 63;
+            m_mag[i] = (m_mag[i] << 1) | carry;
+            carry = nc;
+        }
+        if (carry) {
+            if (m_size == max_limbs) throw std::overflow_error("integer: value exceeds the static capacity");
+            m_mag[m_size++] = carry;
+        }
+    }
     void mul_small(limb_t m)
     {
         limb_t carry = 0;
@@ -263,7 +337,12 @@ private:
 
 namespace math
 {
-inline bool is_zero(const integer &n) { return n.is_zero(); }
+// any coefficient type with an is_zero() member (integer, rational)
+template <typename T>
+inline auto is_zero(const T &n) -> decltype(n.is_zero())
+{
+    return n.is_zero();
+}
 inline void multiply_accumulate(integer &x, const integer &y, const integer &z) { x.multiply_accumulate(y, z); }
 inline void mul3(integer &r, const integer &a, const integer &b) { r = a * b; }
 inline integer pow(const integer &b, unsigned n) { return b.pow(n); }

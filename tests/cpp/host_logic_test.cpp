@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../piranha_b200/host/polynomial.hpp"
+#include "../../piranha_b200/host/rational.hpp"
 #include "check.hpp"
 
 using namespace pb200;
@@ -46,6 +47,47 @@ static void integer_test()
     CHECK_THROW(w4 * w4 * w4, std::overflow_error); // beyond the static capacity: reported, never wrapped
     CHECK_EQUAL(integer(3).pow(40).to_string(), "12157665459056928801");
     CHECK_THROW(integer("12x"), std::invalid_argument);
+}
+
+static void rational_test()
+{
+    // division against __int128 on random operands, then the identities a = q * b + r, |r| < |b|, sign(r) = sign(a)
+    std::mt19937_64 rng(7);
+    for (int i = 0; i < 2000; ++i) {
+        const std::int64_t a = static_cast<std::int64_t>(rng()) >> (rng() % 40), b = static_cast<std::int64_t>(rng()) >> (rng() % 60);
+        if (!b) continue;
+        const integer A(a), B(b);
+        const integer W = A * integer(static_cast<std::int64_t>(rng())) * integer(static_cast<std::int64_t>(rng())) + integer(a);
+        CHECK_EQUAL(A / B, integer(a / b));
+        CHECK_EQUAL(A % B, integer(a % b));
+        integer q, r;
+        integer::divmod(W, B, q, r);
+        CHECK_EQUAL(q * B + r, W);
+        CHECK(r.abs() < B.abs());
+        CHECK(r.is_zero() || r.sign() == W.sign());
+        const integer g = integer::gcd(W, B);
+        CHECK((W % g).is_zero() && (B % g).is_zero());
+        CHECK_EQUAL(integer::gcd(W / g, B / g), integer(1));
+    }
+    CHECK_THROW(integer(1) / integer(0), std::domain_error);
+    CHECK_EQUAL(integer::gcd(integer(0), integer(-12)), integer(12));
+    // canonical form, arithmetic
+    CHECK_EQUAL(rational(6, -4), rational(-3, 2));
+    CHECK_EQUAL(rational(0, -5), rational(0));
+    CHECK_EQUAL(rational(0, -5).den(), integer(1));
+    CHECK_THROW(rational(1, 0), std::domain_error);
+    CHECK_EQUAL(rational(1, 2) + rational(1, 3), rational(5, 6));
+    CHECK_EQUAL(rational(1, 2) - rational(1, 2), rational(0));
+    CHECK_EQUAL(rational(4, 3) * rational(5, 2), rational(10, 3));
+    CHECK_EQUAL(rational(4, 3) / rational(-2, 9), rational(-6));
+    CHECK_THROW(rational(1) / rational(0), std::domain_error);
+    CHECK_EQUAL(rational(-2, 3).pow(3), rational(-8, 27));
+    // rational series: linear operations stay on the host
+    using qt = polynomial<rational, kronecker_monomial<std::int64_t>>;
+    qt x{"x"}, y{"y"};
+    const qt s = x + y - x;
+    CHECK_EQUAL(s, y);
+    CHECK_EQUAL((x + x).size(), 1u);
 }
 
 static void kronecker_array_test()
@@ -188,6 +230,7 @@ int main(int argc, char **argv)
         return 0;
     }
     RUN_TEST(integer_test);
+    RUN_TEST(rational_test);
     RUN_TEST(kronecker_array_test);
     RUN_TEST(kronecker_monomial_test);
     RUN_TEST(hash_set_test);

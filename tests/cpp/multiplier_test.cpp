@@ -16,6 +16,7 @@
 
 #include "../../piranha_b200/host/monomial.hpp"
 #include "../../piranha_b200/host/polynomial.hpp"
+#include "../../piranha_b200/host/rational.hpp"
 #include "check.hpp"
 
 using namespace pb200;
@@ -283,9 +284,54 @@ static void unpacked_test()
     CHECK_THROW((series_multiplier<ut>(x, y)), std::invalid_argument);
 }
 
+static void rational_test()
+{
+    // tests/polynomial_multiplier_02.cpp:114-154 (polynomial_multiplier_multiplier_finalise_test): rational coefficients
+    // are brought to a common denominator, multiplied as integers (on the GPU) and divided back
+    using qt = polynomial<rational, k_type>;
+    {
+        qt x{"x"}, y{"y"};
+        CHECK_EQUAL(x * 4 / rational(3) * y * 5 / rational(2), rational(10, 3) * x * y);
+        CHECK_EQUAL((x * 4 / rational(3) + y * 5 / rational(2)) * (x.pow(2) * 4 / rational(13) - y * 5 / rational(17)),
+                    16 * x.pow(3) / 39 + rational(10, 13) * y * x * x - 20 * x * y / 51 - 25 * y * y / 34);
+    }
+    pt cmp;
+    {
+        pt x("x"), y("y"), z("z"), t("t");
+        auto f = 1 + x + y + z + t;
+        const auto tmp2 = f;
+        for (int i = 1; i < 10; ++i) f *= tmp2;
+        cmp = f * (f + 1);
+    }
+    qt res;
+    {
+        qt x("x"), y("y"), z("z"), t("t");
+        auto f = 1 + x + y + z + t;
+        const auto tmp2 = f;
+        for (int i = 1; i < 10; ++i) f *= tmp2;
+        const auto g = f + 1;
+        res = f / 2 * g / 3;
+    }
+    const qt res6 = res * 6;
+    CHECK_EQUAL(res6.size(), cmp.size());
+    CHECK_EQUAL(cmp.size(), 10626u);
+    std::size_t same = 0;
+    for (const auto &t : cmp._container()) {
+        const auto it = res6._container().find(qt::term_type(rational(0), t.m_key));
+        if (it != res6._container().end() && it->m_cf == rational(t.m_cf)) ++same;
+    }
+    CHECK_EQUAL(same, cmp.size());
+    // integer helpers behind the lcm / gcd passes
+    CHECK_EQUAL(integer::gcd(integer("123456789012345678901234567890"), integer("987654321098765432109876543210")), integer("9000000000900000000090"));
+    CHECK_EQUAL(integer("-1000000000000000000000000000007") / integer("1000000000000"), integer("-1000000000000000000"));
+    CHECK_EQUAL(integer("-1000000000000000000000000000007") % integer("1000000000000"), integer(-7));
+    CHECK_EQUAL(rational(6, -4), rational(-3, 2));
+}
+
 int main()
 {
     RUN_TEST(residency_test);
+    RUN_TEST(rational_test);
     RUN_TEST(unpacked_test);
     RUN_TEST(bounds_test);
     RUN_TEST(multiplication_test);
