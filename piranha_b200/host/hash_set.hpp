@@ -12,14 +12,91 @@
 #include <algorithm>
 #include <cstddef>
 #include <cstdint>
+#include <exception>
 #include <functional>
 #include <iterator>
+#include <new>
 #include <stdexcept>
+#include <thread>
 #include <utility>
 #include <vector>
 
 namespace pb200
 {
+
+namespace detail
+{
+// Contiguous pool of constructed nodes over raw storage: what hash_set needs from std::vector, plus the one thing
+// std::vector cannot do -- hand out uninitialised storage for n nodes so that several threads construct (and first-touch
+// the pages of) disjoint ranges at once.
+template <typename Node>
+class node_pool
+{
+public:
+    node_pool() = default;
+    node_pool(const node_pool &o)
+    {
+        reserve(o.m_size);
+        for (; m_size < o.m_size; ++m_size) ::new (static_cast<void *>(m_p + m_size)) Node(o.m_p[m_size]);
+    }
+    node_pool(node_pool &&o) noexcept : m_p(o.m_p), m_size(o.m_size), m_cap(o.m_cap) { o.m_p = nullptr, o.m_size = o.m_cap = 0; }
+    node_pool &operator=(node_pool o) noexcept
+    {
+        swap(o);
+        return *this;
+    }
+    ~node_pool() { release(); }
+    void swap(node_pool &o) noexcept
+    {
+        std::swap(m_p, o.m_p);
+        std::swap(m_size, o.m_size);
+        std::swap(m_cap, o.m_cap);
+    }
+    std::size_t size() const { return m_size; }
+    Node &operator[](std::size_t i) { return m_p[i]; }
+    const Node &operator[](std::size_t i) const { return m_p[i]; }
+    void clear() { release(); }
+    void reserve(std::size_t n)
+    {
+        if (n <= m_cap) return;
+        Node *np = static_cast<Node *>(::operator new(n * sizeof(Node)));
+        for (std::size_t i = 0; i < m_size; ++i) {
+            ::new (static_cast<void *>(np + i)) Node(std::move(m_p[i]));
+            m_p[i].~Node();
+        }
+        ::operator delete(m_p);
+        m_p = np;
+        m_cap = n;
+    }
+    void push_back(Node &&v)
+    {
+        if (m_size == m_cap) reserve(m_cap ? 2 * m_cap : 8);
+        ::new (static_cast<void *>(m_p + m_size)) Node(std::move(v));
+        ++m_size;
+    }
+    // raw storage for n nodes in an EMPTY pool; the caller constructs nodes and then calls commit(n) (all constructed) or
+    // abandon() (none left constructed)
+    Node *raw(std::size_t n)
+    {
+        release();
+        reserve(n);
+        return m_p;
+    }
+    void commit(std::size_t n) { m_size = n; }
+    void abandon() { m_size = 0; }
+
+private:
+    void release()
+    {
+        for (std::size_t i = 0; i < m_size; ++i) m_p[i].~Node();
+        ::operator delete(m_p);
+        m_p = nullptr;
+        m_size = m_cap = 0;
+    }
+    Node *m_p = nullptr;
+    std::size_t m_size = 0, m_cap = 0;
+};
+} // namespace detail
 
 template <typename T, typename Hash = std::hash<T>, typename Pred = std::equal_to<T>>
 class hash_set
@@ -196,12 +273,70 @@ public:
         return iterator(this, idx);
     }
     void _update_size(size_type n) { m_n_elements = n; }
+    // Replace the contents with n elements known to be distinct: make(i) builds element i and hash_of(i) is its hash.
+    // n_threads threads construct disjoint node ranges in place and push them on their buckets with an atomic exchange
+    // of the bucket head (insert-only, no readers: lock-free and exact).  The thread-parallel counterpart of
+    // rehash + n x _unique_insert + _update_size; the reference fills results from several threads by bucket ranges
+    // (base_series_multiplier.hpp:885-948).  Node order is i, so iteration order does not depend on the thread count.
+    template <typename Make, typename HashOf>
+    void _bulk_unique_fill(size_type n, Make make, HashOf hash_of, unsigned n_threads)
+    {
+        if (n >= npos) throw std::overflow_error("hash_set: too many elements");
+        clear();
+        if (!n) return;
+        size_type nb = 1;
+        while (nb < n) nb <<= 1;
+        n_threads = static_cast<unsigned>(std::max<size_type>(1, std::min<size_type>(n_threads, n / 4096 + 1)));
+        node *pool = m_nodes.raw(n);
+        m_heads.resize(nb); // value-initialised once; the slices are set to npos by the threads below
+        std::uint32_t *heads = m_heads.data();
+        std::vector<size_type> built(n_threads, 0);
+        std::vector<std::exception_ptr> err(n_threads);
+        auto clear_heads = [&](unsigned t) {
+            const size_type lo = nb * t / n_threads, hi = nb * (t + 1) / n_threads;
+            std::fill(heads + lo, heads + hi, npos);
+        };
+        auto build = [&](unsigned t) {
+            const size_type lo = n * t / n_threads, hi = n * (t + 1) / n_threads;
+            size_type i = lo;
+            try {
+                for (; i < hi; ++i) {
+                    if (i + 16 < hi) __builtin_prefetch(heads + (hash_of(i + 16) & (nb - 1)), 1, 1);
+                    ::new (static_cast<void *>(pool + i)) node{make(i), npos, true};
+                    pool[i].next = __atomic_exchange_n(heads + (hash_of(i) & (nb - 1)), static_cast<std::uint32_t>(i), __ATOMIC_RELAXED);
+                }
+            } catch (...) {
+                err[t] = std::current_exception();
+            }
+            built[t] = i - lo;
+        };
+        auto run = [&](auto &&f) {
+            std::vector<std::thread> th;
+            for (unsigned t = 1; t < n_threads; ++t) th.emplace_back(f, t);
+            f(0u);
+            for (auto &x : th) x.join();
+        };
+        run(clear_heads);
+        run(build);
+        for (unsigned t = 0; t < n_threads; ++t) {
+            if (!err[t]) continue;
+            for (unsigned u = 0; u < n_threads; ++u) {
+                const size_type lo = n * u / n_threads;
+                for (size_type i = lo; i < lo + built[u]; ++i) pool[i].~node();
+            }
+            m_nodes.abandon();
+            clear();
+            std::rethrow_exception(err[t]);
+        }
+        m_nodes.commit(n);
+        m_n_elements = n;
+    }
     // hint that `bucket` is about to receive an element (bulk fills touch the buckets in random order: one cache miss
     // per element unless the bucket heads are requested a few elements ahead)
     void _prefetch_bucket(size_type bucket) const { __builtin_prefetch(&m_heads[bucket], 1, 1); }
 
 private:
-    std::vector<node> m_nodes;
+    detail::node_pool<node> m_nodes;
     std::vector<std::uint32_t> m_heads;
     std::uint32_t m_free = npos;
     size_type m_n_elements = 0;

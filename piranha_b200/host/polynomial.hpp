@@ -36,6 +36,7 @@
 #include "../../include/piranha_b200.h"
 #include "hash_set.hpp"
 #include "integer.hpp"
+#include "settings.hpp"
 #include "kronecker_monomial.hpp"
 #include "series_multiplier.hpp"
 
@@ -436,6 +437,15 @@ private:
             gpu::check(ctx, pk_download(ctx, m_dev->p, &r));
             try {
                 m_container.clear();
+                const unsigned nt = settings::get_n_threads();
+                if (nt > 1u && r.n >= (1u << 16)) { // large results: thread-parallel fill
+                    m_container._bulk_unique_fill(
+                        r.n, [&r](std::size_t i) { return term_type(integer::from_limbs(r.sign[i], r.mag + i * r.limbs, r.limbs), Key::from_int(r.key[i])); },
+                        [&r](std::size_t i) { return static_cast<std::size_t>(r.key[i]); }, nt);
+                    pk_result_free(ctx, &r);
+                    m_host_valid = true;
+                    return;
+                }
                 m_container.rehash(std::max<std::size_t>(1, r.n));
                 for (std::uint64_t i = 0; i < r.n; ++i) {
                     if (i + 24 < r.n) m_container._prefetch_bucket(m_container._bucket_from_hash(static_cast<std::size_t>(r.key[i + 24])));

@@ -187,18 +187,18 @@ private:
         series_type r;
         r.set_symbol_set(m_ss);
         auto &c = r._container();
-        c.rehash(std::max<std::size_t>(1, p.size()));
         if (!p.m_host_valid) { // product still in HBM: fill the rational container straight from the downloaded terms
             pk_ctx *ctx = gpu::context();
             pk_result res{};
             gpu::check(ctx, pk_download(ctx, p.m_dev->p, &res));
             try {
-                for (std::uint64_t i = 0; i < res.n; ++i) {
-                    series_type::term_type t(rational(integer::from_limbs(res.sign[i], res.mag + i * res.limbs, res.limbs), den),
-                                             key_type::from_int(res.key[i]));
-                    c._unique_insert(std::move(t), c._bucket_from_hash(static_cast<std::size_t>(res.key[i])));
-                }
-                c._update_size(res.n);
+                c._bulk_unique_fill(
+                    res.n,
+                    [&res, &den](std::size_t i) {
+                        return series_type::term_type(rational(integer::from_limbs(res.sign[i], res.mag + i * res.limbs, res.limbs), den),
+                                                      key_type::from_int(res.key[i]));
+                    },
+                    [&res](std::size_t i) { return static_cast<std::size_t>(res.key[i]); }, settings::get_n_threads());
             } catch (...) {
                 pk_result_free(ctx, &res);
                 throw;
@@ -206,6 +206,7 @@ private:
             pk_result_free(ctx, &res);
             return r;
         }
+        c.rehash(std::max<std::size_t>(1, p.size()));
         for (const auto &t : p._container()) c.insert(series_type::term_type(rational(t.m_cf, den), t.m_key));
         return r;
     }

@@ -178,6 +178,51 @@ static void hash_set_test()
     g.rehash(1000);
     CHECK_EQUAL(g.bucket_count(), 1024u);
     for (int i = 0; i < 100; ++i) CHECK(g.find(i) != g.end());
+    // thread-parallel bulk fill: same contents, same iteration order whatever the thread count; the set stays usable
+    const std::size_t nbulk = 50000;
+    std::vector<int> order1;
+    for (unsigned nt : {1u, 2u, 5u, 8u}) {
+        hash_set<int, H> b;
+        b.insert(-1); // replaced by the fill
+        b._bulk_unique_fill(nbulk, [](std::size_t i) { return static_cast<int>(i * 3); }, [](std::size_t i) { return i * 3; }, nt);
+        CHECK_EQUAL(b.size(), nbulk);
+        CHECK_EQUAL(b.bucket_count(), 65536u);
+        CHECK(b.find(-1) == b.end());
+        std::size_t found = 0;
+        for (std::size_t i = 0; i < nbulk; ++i) found += b.find(static_cast<int>(i * 3)) != b.end();
+        CHECK_EQUAL(found, nbulk);
+        CHECK(b.find(1) == b.end());
+        std::vector<int> order(b.begin(), b.end());
+        if (nt == 1u) order1 = order;
+        CHECK(order == order1);
+        b.erase(b.find(3));
+        CHECK(b.insert(1).second);
+        CHECK(!b.insert(6).second);
+        CHECK_EQUAL(b.size(), nbulk);
+        hash_set<int, H> c(b); // copies and moves of the node pool
+        CHECK_EQUAL(c.size(), nbulk);
+        CHECK(c.find(1) != c.end() && c.find(3) == c.end());
+        hash_set<int, H> d(std::move(c));
+        CHECK_EQUAL(d.size(), nbulk);
+        CHECK(d.find(9) != d.end());
+        // an element constructor that throws leaves an empty, reusable set
+        bool thrown = false;
+        try {
+            b._bulk_unique_fill(nbulk, [](std::size_t i) { if (i == 31234) throw std::overflow_error("x"); return static_cast<int>(i); },
+                                [](std::size_t i) { return i; }, nt);
+        } catch (const std::overflow_error &) {
+            thrown = true;
+        }
+        CHECK(thrown);
+        CHECK(b.empty());
+        CHECK(b.insert(5).second);
+    }
+    CHECK(settings::get_n_threads() >= 1u);
+    settings::set_n_threads(3u);
+    CHECK_EQUAL(settings::get_n_threads(), 3u);
+    CHECK_THROW(settings::set_n_threads(0u), std::invalid_argument);
+    settings::reset_n_threads();
+    CHECK(settings::get_n_threads() >= 1u);
 }
 
 static void series_test()
