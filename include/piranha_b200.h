@@ -188,6 +188,20 @@ int pk_dpoly_export(pk_ctx *ctx, const pk_dpoly *p, void *d_key, void *d_mag, vo
 /* Same, with magnitude rows of mag_limbs >= pk_dpoly_limbs(p) words (high limbs zero): lets every rank of a
  * partitioned product write its terms straight into its slice of one common result buffer. */
 int pk_dpoly_export_padded(pk_ctx *ctx, const pk_dpoly *p, void *d_key, void *d_mag, void *d_sign, uint32_t mag_limbs);
+/* Term exchange of a partitioned product over peer-mapped device memory (NVLink / NVSwitch; e.g. the buffers of a torch
+ * symmetric-memory allocation), the "gather result sizes and terms" step of the multi-GPU path without a collective
+ * library on the data path.  All pointer tables are host arrays of n_peers <= 16 DEVICE addresses, valid on this
+ * context's GPU, index = rank (own rank included).
+ *   pk_dpoly_publish_size: writes {term count, limbs} of p to slot_ptrs[j] (2 x uint64 each) on every peer j.
+ *   pk_dpoly_export_peers: after a barrier across the ranks, d_sizes (this rank's own table: n_peers x {count, limbs}) is
+ *     complete; the kernel derives this rank's term offset (sum of the counts of lower ranks) and the common row width
+ *     (max limbs) from it and stores its terms into key_ptrs[j] / mag_ptrs[j] / sign_ptrs[j] of every peer j.  Nothing is
+ *     written when the whole result exceeds cap_terms terms or cap_limbs <= 8 limbs: every rank sees the same table, so
+ *     every rank skips; the caller grows the buffers and repeats.  A second barrier completes the exchange. */
+int pk_dpoly_publish_size(pk_ctx *ctx, const pk_dpoly *p, uint32_t n_peers, const uint64_t *slot_ptrs);
+int pk_dpoly_export_peers(pk_ctx *ctx, const pk_dpoly *p, uint32_t n_peers, uint32_t rank, const void *d_sizes,
+                          const uint64_t *key_ptrs, const uint64_t *mag_ptrs, const uint64_t *sign_ptrs, uint64_t cap_terms,
+                          uint32_t cap_limbs);
 /* Order-independent 64-bit digest of (key, coefficient) over all terms, computed on the device.  Digests of
  * disjoint partitions add up (mod 2^64) to the digest of the whole product. */
 int pk_dpoly_digest(pk_ctx *ctx, const pk_dpoly *p, uint64_t *digest_out);

@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = [
     "pk_ctx_create", "pk_ctx_destroy", "pk_ctx_trim", "pk_last_error", "pk_ctx_set_limits", "pk_ctx_get_limits", "pk_get_stats", "pk_ctx_set_tuning",
     "pk_mul", "pk_result_free", "pk_upload", "pk_mul_dev", "pk_check_bounds", "pk_download", "pk_dpoly_free", "pk_dpoly_size",
     "pk_dpoly_limbs", "pk_dpoly_nvars", "pk_dpoly_export", "pk_dpoly_export_padded", "pk_dpoly_digest",
+    "pk_dpoly_publish_size", "pk_dpoly_export_peers",
 ]
 
 
@@ -110,6 +111,8 @@ def load_library():
     lib.pk_dpoly_nvars.restype = u32
     lib.pk_dpoly_export.argtypes = [vp, vp, vp, vp, vp]
     lib.pk_dpoly_export_padded.argtypes = [vp, vp, vp, vp, vp, u32]
+    lib.pk_dpoly_publish_size.argtypes = [vp, vp, u32, vp]
+    lib.pk_dpoly_export_peers.argtypes = [vp, vp, u32, u32, vp, vp, vp, vp, u64, u32]
     lib.pk_dpoly_digest.argtypes = [vp, vp, C.POINTER(u64)]
     _lib = lib
     return lib
@@ -172,6 +175,20 @@ class DevicePoly:
         words (default: this polynomial's own limb count)."""
         self.ctx._check(self.ctx.lib.pk_dpoly_export_padded(self.ctx.handle, self.handle, key_ptr, mag_ptr, sign_ptr,
                                                             mag_limbs or self.limbs))
+
+    def publish_size(self, slot_ptrs: Sequence[int]):
+        """Write {term count, limbs} into slot_ptrs[j] (peer-mapped device address, 2 x uint64) on every peer j."""
+        tab = (C.c_uint64 * len(slot_ptrs))(*slot_ptrs)
+        self.ctx._check(self.ctx.lib.pk_dpoly_publish_size(self.ctx.handle, self.handle, len(slot_ptrs), tab))
+
+    def export_peers(self, rank: int, sizes_ptr: int, key_ptrs: Sequence[int], mag_ptrs: Sequence[int],
+                     sign_ptrs: Sequence[int], cap_terms: int, cap_limbs: int):
+        """Push the terms into the result arrays of every peer (peer-mapped device addresses, index = rank) at the term
+        offset the kernel derives from the size table at sizes_ptr (pk_dpoly_export_peers)."""
+        n = len(key_ptrs)
+        k, m, g = (C.c_uint64 * n)(*key_ptrs), (C.c_uint64 * n)(*mag_ptrs), (C.c_uint64 * n)(*sign_ptrs)
+        self.ctx._check(self.ctx.lib.pk_dpoly_export_peers(self.ctx.handle, self.handle, n, rank, sizes_ptr, k, m, g,
+                                                           cap_terms, cap_limbs))
 
     def free(self):
         if self.handle:

@@ -817,6 +817,48 @@ int pk_dpoly_export(pk_ctx *ctx, const pk_dpoly *p, void *d_key, void *d_mag, vo
     return pk_dpoly_export_padded(ctx, p, d_key, d_mag, d_sign, p ? p->limbs : 0);
 }
 
+namespace
+{
+bool fill_peer_table(PeerTable &t, uint32_t n_peers, const uint64_t *slots, const uint64_t *keys, const uint64_t *mags,
+                     const uint64_t *signs)
+{
+    if (!n_peers || n_peers > kMaxPeers) return false;
+    for (uint32_t j = 0; j < n_peers; ++j) {
+        t.slot[j] = slots ? reinterpret_cast<u64 *>(slots[j]) : nullptr;
+        t.key[j] = keys ? reinterpret_cast<i64 *>(keys[j]) : nullptr;
+        t.mag[j] = mags ? reinterpret_cast<u64 *>(mags[j]) : nullptr;
+        t.sign[j] = signs ? reinterpret_cast<signed char *>(signs[j]) : nullptr;
+    }
+    return true;
+}
+} // namespace
+
+int pk_dpoly_publish_size(pk_ctx *ctx, const pk_dpoly *p, uint32_t n_peers, const uint64_t *slot_ptrs)
+{
+    PeerTable t{};
+    if (!ctx || !p || !slot_ptrs || !fill_peer_table(t, n_peers, slot_ptrs, nullptr, nullptr, nullptr)) return PK_E_ARGS;
+    PK_TRY(ctx, {
+        cudaSetDevice(ctx->device);
+        PK_LAUNCH(ctx, k_peer_publish, 1, 32, 0, t, n_peers, p->n, (u64)std::max<u32>(1, p->limbs));
+    })
+}
+
+int pk_dpoly_export_peers(pk_ctx *ctx, const pk_dpoly *p, uint32_t n_peers, uint32_t rank, const void *d_sizes,
+                          const uint64_t *key_ptrs, const uint64_t *mag_ptrs, const uint64_t *sign_ptrs, uint64_t cap_terms,
+                          uint32_t cap_limbs)
+{
+    PeerTable t{};
+    if (!ctx || !p || !d_sizes || !key_ptrs || !mag_ptrs || !sign_ptrs || rank >= n_peers || p->limbs > 8 || cap_limbs > 8
+        || !fill_peer_table(t, n_peers, nullptr, key_ptrs, mag_ptrs, sign_ptrs))
+        return PK_E_ARGS;
+    PK_TRY(ctx, {
+        cudaSetDevice(ctx->device);
+        if (p->n)
+            PK_LAUNCH(ctx, k_peer_push, grid_for(p->n, 256), 256, 0, t, n_peers, rank, static_cast<const u64 *>(d_sizes), p->key,
+                      p->planes, p->stride, p->sign, p->n, p->limbs, cap_terms, cap_limbs);
+    })
+}
+
 int pk_dpoly_digest(pk_ctx *ctx, const pk_dpoly *p, uint64_t *digest_out)
 {
     if (!ctx || !p || !digest_out) return PK_E_ARGS;

@@ -26,6 +26,63 @@ __global__ void k_planes_to_aos(const u64 *__restrict__ planes, u64 *__restrict_
     for (u32 l = 0; l < out_limbs; ++l) aos[i * out_limbs + l] = l < limbs ? planes[l * stride + i] : 0ull;
 }
 
+// ---- multi-GPU term exchange over peer-mapped memory (NVLink / NVSwitch): every rank of a partitioned product pushes
+// its terms straight into the result arrays of ALL ranks with plain stores.
+constexpr u32 kMaxPeers = 16;
+struct PeerTable {
+    u64 *slot[kMaxPeers];          // where this rank's {n, limbs} goes on peer j
+    i64 *key[kMaxPeers];           // result arrays of peer j
+    u64 *mag[kMaxPeers];
+    signed char *sign[kMaxPeers];
+};
+
+// publish {n, limbs} of this rank's part in every peer's size table
+__global__ void k_peer_publish(const PeerTable t, u32 n_peers, u64 n, u64 limbs)
+{
+    const u32 j = threadIdx.x;
+    if (j < n_peers) {
+        t.slot[j][0] = n;
+        t.slot[j][1] = limbs;
+    }
+}
+
+// sizes: {n, limbs} of every rank (local copy of the size table, complete after the barrier that follows
+// k_peer_publish).  Rank `rank` writes its terms at term offset sum(n of lower ranks), magnitude rows of
+// max(limbs of all ranks) words.  A result that does not fit (cap_terms, cap_limbs) is not written at all: every rank
+// takes the same decision from the same table and the host grows the buffers.
+__global__ void __launch_bounds__(256) k_peer_push(const PeerTable t, u32 n_peers, u32 rank, const u64 *__restrict__ sizes,
+                                                  const i64 *__restrict__ key, const u64 *__restrict__ planes, u64 stride,
+                                                  const signed char *__restrict__ sign, u64 n, u32 limbs, u64 cap_terms,
+                                                  u32 cap_limbs)
+{
+    u64 off = 0, total = 0;
+    u32 out_limbs = 1;
+    for (u32 r = 0; r < n_peers; ++r) {
+        const u64 nr = __ldg(&sizes[2 * r]);
+        if (r < rank) off += nr;
+        total += nr;
+        if (nr) out_limbs = max(out_limbs, (u32)__ldg(&sizes[2 * r + 1]));
+    }
+    if (total > cap_terms || out_limbs > cap_limbs) return;
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const i64 k = key[i];
+    const signed char sg = sign[i];
+    u64 m[8];
+#pragma unroll
+    for (u32 l = 0; l < 8; ++l) m[l] = (l < limbs) ? planes[l * stride + i] : 0ull;
+    const u64 o = off + i;
+    for (u32 j = 0; j < n_peers; ++j) {
+        const u32 p = (rank + j) % n_peers; // start with the own copy, spread the peers over the links
+        t.key[p][o] = k;
+        t.sign[p][o] = sg;
+        u64 *row = t.mag[p] + o * out_limbs;
+#pragma unroll
+        for (u32 l = 0; l < 8; ++l)
+            if (l < out_limbs) row[l] = m[l];
+    }
+}
+
 __global__ void k_iota32(u32 *out, u64 n)
 {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;

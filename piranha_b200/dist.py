@@ -2,8 +2,9 @@
 
 Both operands are replicated (they are at most a few MB); rank r calls pk_mul_dev with part_index=r and
 part_count=world_size, so every term product is performed by exactly one rank and no reduction is needed.
-The only exchange is the final gather of result sizes and terms (torch.distributed: NCCL over NVLink on GPUs,
-gloo in the CPU tests).  Ranges are ordered, so laying the per-rank sorted outputs out in rank order gives the
+The only exchange is the final gather of result sizes and terms: on GPUs PeerExchange (stores over NVLink into
+peer-mapped result arrays by a kernel of this library, torch symmetric memory for the mapping and the barriers), or
+torch.distributed collectives (NCCL; gloo in the CPU tests).  Ranges are ordered, so laying the per-rank sorted outputs out in rank order gives the
 globally sorted result.  This is the GPU form of the zone scheme of polynomial.hpp:1783-1966 lifted to ranks.
 
 The term gather is two collectives: the sizes are all-gathered first; every rank then writes its own terms straight
@@ -121,9 +122,78 @@ def export_local(dpoly, device) -> Tuple[torch.Tensor, torch.Tensor, torch.Tenso
     return key, mag, sign
 
 
-def multiply_partitioned(ctx, da, db, device, group=None, gather: bool = True, workspace: "GatherWorkspace" = None, **opt):
-    """One multi-GPU product: this rank's partition through the C ABI, then the size + term gather (into `workspace`
-    when given: the returned tensors are then views that the next product overwrites)."""
+class PeerExchange:
+    """Term exchange of a partitioned product over peer-mapped memory (NVLink / NVSwitch), without a collective on the
+    data path: the result arrays of every rank live in one torch symmetric-memory allocation, every rank publishes the
+    size of its part in all size tables, and after a barrier ONE kernel of this library (pk_dpoly_export_peers) stores
+    the rank's terms straight into the result arrays of all ranks at the offset it derives from the size table.  A second
+    barrier completes the product; only then does the host read the size table (the single host round trip).
+
+    Layout of the symmetric buffer (bytes): [2 size tables of world x {count, limbs} uint64, alternating between
+    products | keys cap x 8 | magnitudes cap x cap_limbs x 8 | signs cap].  Buffers grow collectively: every rank sees the
+    same size table, so every rank takes the same decision."""
+
+    HEADER = 1024
+
+    def __init__(self, device, group=None, capacity: int = 1 << 16, limbs: int = 2):
+        self.device, self.group = device, group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if 2 * self.world * 16 > self.HEADER:
+            raise ValueError("too many ranks for the size tables")
+        self.parity = 0
+        self.buf = self.hdl = None
+        self._allocate(capacity, limbs)
+
+    def _allocate(self, capacity: int, limbs: int):
+        import torch.distributed._symmetric_memory as symm
+
+        self.cap, self.cap_limbs = int(capacity), int(limbs)
+        self.key_off = self.HEADER
+        self.mag_off = self.key_off + self.cap * 8
+        self.sign_off = self.mag_off + self.cap * self.cap_limbs * 8
+        nbytes = (self.sign_off + self.cap + 255) // 256 * 256
+        self.buf = self.hdl = None  # release the old allocation on every rank before the new rendezvous
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.buf[:self.HEADER].zero_()
+        self.base = [int(p) for p in self.hdl.buffer_ptrs]
+        self.hdl.barrier()
+
+    def _slots(self, parity: int):
+        off = parity * self.world * 16 + self.rank * 16
+        return [b + off for b in self.base]
+
+    def exchange(self, part):
+        """All ranks call this with their part of one product; returns (keys, mags, signs) views of the complete result
+        in rank (= code) order, valid until the next exchange."""
+        w = self.world
+        while True:
+            par = self.parity
+            self.parity ^= 1
+            part.publish_size(self._slots(par))
+            self.hdl.barrier()
+            sizes_ptr = self.base[self.rank] + par * w * 16
+            part.export_peers(self.rank, sizes_ptr, [b + self.key_off for b in self.base], [b + self.mag_off for b in self.base],
+                              [b + self.sign_off for b in self.base], self.cap, self.cap_limbs)
+            self.hdl.barrier()
+            sizes = self.buf[par * w * 16:(par + 1) * w * 16].view(torch.int64).cpu().view(w, 2)  # the host round trip
+            counts = [int(x) for x in sizes[:, 0]]
+            total = sum(counts)
+            limbs = max([int(sizes[r, 1]) for r in range(w) if counts[r]] or [1])
+            if total <= self.cap and limbs <= self.cap_limbs:
+                break
+            self._allocate(max(total + total // 8, self.cap), max(limbs, self.cap_limbs))  # nothing was written: grow, repeat
+        keys = self.buf[self.key_off:self.key_off + total * 8].view(torch.int64)
+        mags = self.buf[self.mag_off:self.mag_off + total * limbs * 8].view(torch.int64).view(total, limbs)
+        signs = self.buf[self.sign_off:self.sign_off + total].view(torch.int8)
+        return counts, (keys, mags, signs)
+
+
+def multiply_partitioned(ctx, da, db, device, group=None, gather: bool = True, workspace: "GatherWorkspace" = None,
+                         peers: "PeerExchange" = None, **opt):
+    """One multi-GPU product: this rank's partition through the C ABI, then the size + term gather -- over peer memory
+    when a PeerExchange is given, else two collectives (into `workspace` when given).  The returned tensors are views
+    that the next product overwrites."""
     import os
     import time
 
@@ -141,6 +211,12 @@ def multiply_partitioned(ctx, da, db, device, group=None, gather: bool = True, w
     mark()
     if not gather:
         return part, None
+    if peers is not None:  # peer-memory exchange (NVLink stores by this library's kernel, no collective on the data path)
+        _, out = peers.exchange(part)
+        mark()
+        if trace:
+            print("[pk dist] " + "  ".join(f"{n} {1e3 * (b - a):.3f} ms" for n, a, b in zip(("mul_dev", "peer exchange"), t, t[1:])), flush=True)
+        return part, out
     counts, limbs = gather_sizes(len(part), max(1, part.limbs), device, group)
     mark()
     workspace = workspace or GatherWorkspace()

@@ -621,6 +621,59 @@ def test_output_partitions(ctx, parts, case):
         assert min(sizes) > 0
 
 
+@pytest.mark.parametrize("parts", [2, 5])
+def test_peer_exchange_kernels_one_gpu(ctx, parts):
+    """pk_dpoly_publish_size / pk_dpoly_export_peers with every 'peer' on this GPU: each part pushes its terms into the
+    result arrays of all peers at the offset derived from the size table; every peer ends up with the whole product."""
+    import torch
+
+    (f, g), nv = po.pearce_operands(6), 5
+    a, b = terms(f, nv, 1), terms(g, nv, 2)
+    da, db = ctx.upload(a, nv), ctx.upload(b, nv)
+    wk, wm, ws = ctx.mul_dev(da, db).download()
+    n, L = len(wk), wm.shape[1]
+    dev = torch.device("cuda", 0)
+    tables = [torch.zeros(parts * 2, dtype=torch.int64, device=dev) for _ in range(parts)]
+    keys = [torch.full((n + 8,), -1, dtype=torch.int64, device=dev) for _ in range(parts)]
+    mags = [torch.full(((n + 8) * (L + 1),), -1, dtype=torch.int64, device=dev) for _ in range(parts)]
+    signs = [torch.zeros(n + 8, dtype=torch.int8, device=dev) for _ in range(parts)]
+    torch.cuda.synchronize()
+    ps = [ctx.mul_dev(da, db, part_index=r, part_count=parts) for r in range(parts)]
+    for r, part in enumerate(ps):
+        part.publish_size([t.data_ptr() + 16 * r for t in tables])
+    for cap_terms, cap_limbs, written in ((n - 1, L + 1, False), (n + 8, L - 1 if L > 1 else 0, False), (n + 8, L + 1, True)):
+        for r, part in enumerate(ps):
+            part.export_peers(r, tables[r].data_ptr(), [k.data_ptr() for k in keys], [m.data_ptr() for m in mags],
+                              [x.data_ptr() for x in signs], cap_terms, cap_limbs)
+        ctx.download(ps[0])  # synchronises the context's stream
+        for j in range(parts):
+            if not written:  # a result that does not fit is not written at all
+                assert int(keys[j].max()) == -1 and int(signs[j].abs().sum()) == 0
+                continue
+            assert tables[j].cpu().view(parts, 2)[:, 0].tolist() == [len(x) for x in ps]
+            got = (keys[j][:n].cpu().numpy(), mags[j][:n * L].cpu().numpy().view(np.uint64).reshape(n, L), signs[j][:n].cpu().numpy())
+            assert_terms_equal(got, (wk, wm, ws))
+            assert int(keys[j][n:].max()) == -1
+
+
+def test_peer_exchange_two_gpus():
+    """The peer-memory exchange between two processes / two GPUs (torch symmetric memory + this library's push kernel)
+    against the whole product and against the NCCL exchange.  Needs two GPUs."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(here, "dist_peer_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("PEER-EXCHANGE-OK") == 2, out.stdout[-3000:]
+
+
 def test_device_resident_chain(ctx):
     # benchmarks/fateman1.hpp:46-48: f *= tmp, nine times, operands never leave HBM
     nv = 4
