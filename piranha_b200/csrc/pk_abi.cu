@@ -389,7 +389,7 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
         if (bp.ok && sub_range)
             result = block_multiply(ctx, pl, bp, A, B, keyA.as<u64>(), keyB.as<u64>(), lo, hi, nv, trunc ? degA.as<i64>() : nullptr,
                                     trunc ? degB.as<i64>() : nullptr, o.max_degree, prepack ? packA.as<uint4>() : nullptr,
-                                    prepack ? packB.as<uint4>() : nullptr);
+                                    prepack ? packB.as<uint4>() : nullptr, P);
         if (!result) algo = PK_ALGO_ZONE; // no block geometry for these operands (or tiny groups): generic zones
     }
     if (trunc && !result) prepare_degree_sorted();
@@ -717,6 +717,8 @@ int pk_ctx_set_tuning(pk_ctx *ctx, const char *key, uint64_t value)
     else if (k == "block_mode") ctx->block_tuning.force_mode = (u32)value;
     else if (k == "block_hz") ctx->block_tuning.force_hz = (u32)value;
     else if (k == "block_natural") ctx->block_tuning.natural = (u32)value;
+    else if (k == "block_equal_zones") ctx->block_tuning.equal_zones = (u32)value;
+    else if (k == "block_zone_products") ctx->block_tuning.zone_products = (u32)value;
     else if (k == "pipe_parts") ctx->pipe_parts = (u32)std::min<uint64_t>(value, 64);
     else if (k == "pipe_min_products") ctx->pipe_min_products = value;
     else if (k == "pipe_test_small") ctx->pipe_test_small = (u32)value;

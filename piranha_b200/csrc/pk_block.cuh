@@ -37,7 +37,7 @@ struct BlockArgs {
     const u32 *order;     // zones, heaviest first (nullptr = natural order)
     const u32 *n_active;  // zones with at least one tile (device value)
     u32 h_base, n_h;      // blocks [h_base, h_base + n_h) belong to this call's partition
-    u32 Hz;               // blocks per zone
+    const u32 *zstart;    // first block of every zone (n_zones + 1 entries, ascending)
     u32 S;                // codes per block
     const TruncDev *trunc; // degree truncation (nullptr = none)
     u32 off_keys;          // MODE 1: byte offset of the hash keys (cap words) in dynamic shared memory
@@ -179,7 +179,6 @@ struct TileArgs {
     const uint2 *tabA, *tabB;
     u32 GA, GB;
     u32 h_base, n_h; // partition, in blocks
-    u32 Hz;
     u32 target;      // products per tile
     u32 wide;        // 1 = use 64-term chunks of gb (two terms per lane)
     const uint2 *gdegA, *gdegB; // truncation: degree offset extremes per group (nullptr = untruncated)
@@ -244,14 +243,75 @@ __global__ void k_block_tiles(const TileArgs t)
     }
 }
 
+// Zones of Hz consecutive blocks each (dense zones: the slots of Hz blocks are what shared memory holds).
+__global__ void k_block_uniform_zones(u32 n_h, u32 Hz, u32 nz, u32 *__restrict__ zstart, u32 *__restrict__ n_zones)
+{
+    const u32 z = blockIdx.x * blockDim.x + threadIdx.x;
+    if (z <= nz) zstart[z] = min(n_h, z * Hz);
+    if (z == 0) *n_zones = nz;
+}
+
+// Zones of about equal work (bitmap zones): the blocks are cut at the quantiles of the tile count (nq of them), and a
+// quantile longer than span_max blocks (the bitmap of a zone covers span_max blocks) is cut into equal pieces.  Where
+// blocks are heavy a zone is a few blocks, in the sparse tail it is span_max blocks -- every zone costs a thread block
+// about the same time, whatever part of the code range (or which output partition) it comes from.  One block.
+__global__ void __launch_bounds__(1024) k_block_equal_zones(const u32 *__restrict__ tstart, u32 n_h, u32 span_max, u32 nq,
+                                                            u32 max_zones, u32 *__restrict__ zstart, u32 *__restrict__ n_zones)
+{
+    __shared__ u32 s_ws[40];
+    __shared__ u32 s_run;
+    const u32 total = tstart[n_h];
+    const u32 per = max(1u, (total + nq - 1) / nq);
+    auto bound = [&](u32 q) -> u32 { // first block whose tiles start at or after tile q * per
+        if (q == 0) return 0u;
+        if (q >= nq) return n_h;
+        const u64 want = (u64)q * per;
+        u32 lo = 0, hi = n_h;
+        while (lo < hi) {
+            const u32 mid = (lo + hi) >> 1;
+            if (tstart[mid] < want) lo = mid + 1;
+            else hi = mid;
+        }
+        return lo;
+    };
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (u32 base = 0; base < nq; base += blockDim.x) {
+        const u32 q = base + threadIdx.x;
+        u32 b0 = 0, len = 0, pieces = 0;
+        if (q < nq) {
+            b0 = bound(q);
+            len = bound(q + 1) - b0;
+            pieces = (len + span_max - 1) / span_max;
+        }
+        u32 tot;
+        const u32 excl = block_excl_scan(pieces, s_ws, tot);
+        const u32 run = s_run;
+        if (pieces) {
+            const u32 step = (len + pieces - 1) / pieces;
+            for (u32 j = 0; j < pieces; ++j)
+                if (run + excl + j < max_zones) zstart[run + excl + j] = b0 + j * step;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_run = run + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const u32 nz = min(s_run, max_zones); // (max_zones is a proven bound: nq + n_h / span_max + 1)
+        zstart[nz] = n_h;
+        *n_zones = nz;
+    }
+}
+
 // Zone order for the dynamic claiming: heaviest first (LPT), by a counting sort over 256 logarithmic work classes.
 // One block.  Zones without work sort last and are never claimed (n_active).
-__global__ void __launch_bounds__(1024) k_block_order(const u32 *__restrict__ tstart, u32 n_h, u32 Hz, u32 nz,
-                                                      u32 *__restrict__ order, u32 *__restrict__ n_active,
-                                                      u32 *__restrict__ n_zones)
+__global__ void __launch_bounds__(1024) k_block_order(const u32 *__restrict__ tstart, const u32 *__restrict__ zstart,
+                                                      const u32 *__restrict__ n_zones, u32 *__restrict__ order,
+                                                      u32 *__restrict__ n_active)
 {
+    const u32 nz = *n_zones;
     // work of a zone = its number of tiles (every tile holds about the same number of products)
-    auto zwork_of = [&](u32 z) -> u64 { return (u64)(tstart[min(n_h, (z + 1) * Hz)] - tstart[z * Hz]); };
+    auto zwork_of = [&](u32 z) -> u64 { return (u64)(tstart[zstart[z + 1]] - tstart[zstart[z]]); };
     __shared__ u32 s_hist[256], s_start[256];
     for (u32 i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
@@ -270,16 +330,14 @@ __global__ void __launch_bounds__(1024) k_block_order(const u32 *__restrict__ ts
             run += s_hist[c];
         }
         *n_active = nz - s_hist[0];
-        *n_zones = nz;
     }
     __syncthreads();
     for (u32 z = threadIdx.x; z < nz; z += blockDim.x) order[atomicAdd(&s_start[cls(zwork_of(z))], 1u)] = z;
 }
 
-__global__ void k_block_natural_order(u32 nz, u32 *__restrict__ n_active, u32 *__restrict__ n_zones)
+__global__ void k_block_natural_order(const u32 *__restrict__ n_zones, u32 *__restrict__ n_active)
 {
-    *n_active = nz;
-    *n_zones = nz;
+    *n_active = *n_zones;
 }
 
 // LOAD 0: the code only (bitmap marking), 1: code + sign/degree word (marking with the degree test), 2: whole record
@@ -486,7 +544,7 @@ __global__ void __launch_bounds__(1024, 1) k_block(const BlockArgs ba)
         __syncthreads();
         if (claimed >= n_active) break;
         const u32 z = ba.order ? __ldg(&ba.order[claimed]) : claimed;
-        const u32 hr0 = z * ba.Hz, hr1 = min(ba.n_h, hr0 + ba.Hz);
+        const u32 hr0 = __ldg(&ba.zstart[z]), hr1 = __ldg(&ba.zstart[z + 1]);
         const u32 zlo = (ba.h_base + hr0) * ba.S, zhi = (ba.h_base + hr1) * ba.S;
         const u32 t0 = __ldg(&ba.tstart[hr0]), t1 = __ldg(&ba.tstart[hr1]);
         if (t0 == t1) continue; // (only in natural order: a zone without tiles)
@@ -1010,10 +1068,11 @@ inline bool block_layout(pk_ctx *ctx, BlockPlan &bp, u32 Hz)
 }
 
 // Returns the product restricted to [lo, hi) (both multiples of S), or nullptr when the operands do not suit the
-// block path (tiny groups); the caller then uses the generic zone path.
+// block path (tiny groups); the caller then uses the generic zone path.  parts = number of output partitions the
+// whole product is cut into (this call computes one of them).
 inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const pk_dpoly *A, const pk_dpoly *B,
                                 const u64 *keyA, const u64 *keyB, u64 lo, u64 hi, u32 nv, const i64 *degA, const i64 *degB,
-                                i64 max_degree, const uint4 *prepackA, const uint4 *prepackB)
+                                i64 max_degree, const uint4 *prepackA, const uint4 *prepackB, u32 parts)
 {
     const u64 nA = A->n, nB = B->n;
     const bool trunc = degA != nullptr;
@@ -1045,7 +1104,8 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
 
     const u64 HR = pl.range / S + 2;
     // ---- zone geometry: about zone_work products per zone, at least 4 zones per thread block when possible
-    const double avg_h = (double)w_bound / (double)n_h;
+    // (an output partition holds about 1 / parts of the products: the cuts are quantiles of sampled pair sums)
+    const double avg_h = (double)w_bound / (double)std::max<u32>(1, parts) / (double)n_h;
     u64 Hz = (u64)std::max(1.0, (double)bt.zone_work / std::max(1.0, avg_h));
     Hz = std::min<u64>(Hz, std::max<u64>(1, n_h / (4ull * bp.grid)));
     if (bp.mode == 1) { // bitmap zones: keep the products of a zone near what one pass of entries holds (measured: pearce1)
@@ -1058,10 +1118,25 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
         if (Hz == 1) return nullptr;
         Hz = (Hz + 1) / 2;
     }
-    const u32 nz = (u32)((n_h + Hz - 1) / Hz);
+    // bitmap zones are cut at equal work (k_block_equal_zones): nq quantiles of at most zone_work products each, at least
+    // 4 per thread block, no zone longer than Hz blocks; dense zones are Hz blocks each.  nz = bound on the zone count.
+    // (measured on pearce1: zones of ~one pass of entries (14 k products) are 20 % SLOWER than zones of 65 k -- a walk
+    // hands out one 512-product tile per warp and round, so a zone needs several rounds to keep 32 warps busy.)
+    // By default only the output partitions of a multi-GPU product use them: a partition starts or ends in the dense
+    // middle of the code range, where zones of Hz blocks are several times heavier than the average zone and the
+    // heaviest-first schedule cannot balance them (pearce1, halves: 0.228 / 0.314 ms with zones of Hz blocks,
+    // 0.210 / 0.232 ms cut at equal work; whole products are within 1 % (pearce1) or 5 % slower (pearce2) and keep Hz).
+    const bool equal_zones = bp.mode == 1 && (bt.equal_zones == 2 || (bt.equal_zones == 1 && parts > 1));
+    u32 nq = 0;
+    if (equal_zones) {
+        const double per_zone = bt.zone_products ? (double)bt.zone_products : (double)bt.zone_work;
+        const double want = (double)w_bound / (double)std::max<u32>(1, parts) / std::max(1.0, per_zone);
+        nq = (u32)std::min<double>(1u << 16, std::max<double>(4.0 * bp.grid, want));
+    }
+    const u32 nz = equal_zones ? nq + (u32)(n_h / Hz) + 2 : (u32)((n_h + Hz - 1) / Hz);
     // every array that must start at zero lives in ONE allocation cleared by ONE memset: group tables, group counters,
     // zone bookkeeping, the tile counters of the count pass and the tile cursors of the scatter pass
-    const size_t z_tab = (size_t)HR * 8, z_book = (size_t)nz * 32 + 128, z_cnt = (((size_t)n_h + 1) * 4 + 15) & ~15ull;
+    const size_t z_tab = (size_t)HR * 8, z_book = (size_t)nz * 36 + 160, z_cnt = (((size_t)n_h + 1) * 4 + 15) & ~15ull;
     const size_t zo_tabA = 0, zo_tabB = z_tab, zo_gcnt = 2 * z_tab, zo_book = zo_gcnt + 16, zo_cnt = zo_book + z_book,
                  zo_cur = zo_cnt + z_cnt, z_total = zo_cur + z_cnt;
     DevBuf zeroed(ctx, z_total);
@@ -1129,7 +1204,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     if ((unsigned __int128)pairs * bt.min_tile > w_bound || pairs >= (1ull << 31)) return nullptr;
 
     if (getenv("PK_BLOCK_DEBUG"))
-        fprintf(stderr, "block path: S=%u split=%u n_h=%u Hz=%llu (max %u) zones=%u mode=%u NW=%u PW=%u cap=%u bm_words=%u smem=%zu GA=%u GB=%u\n",
+        fprintf(stderr, "block path: S=%u split=%u n_h=%u Hz=%llu (max %u) zones<=%u mode=%u NW=%u PW=%u cap=%u bm_words=%u smem=%zu GA=%u GB=%u\n",
                 S, bp.split, n_h, (unsigned long long)Hz, bp.Hz_max, nz, bp.mode, bp.NW, bp.PW, bp.cap, bp.bm_words, bp.smem, GA, GB);
 
     // ---- tile list: count -> scan -> scatter
@@ -1150,6 +1225,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     u32 *n_active_dev = chunk_counter + 2;
     u32 *zone_count = chunk_counter + 4;
     u32 *order = zone_count + nz;
+    u32 *zstart = order + nz; // nz + 1 entries
     TileArgs ta{};
     ta.glistA = glA.as<u32>();
     ta.glistB = glB.as<u32>();
@@ -1159,7 +1235,6 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     ta.GB = GB;
     ta.h_base = h_base;
     ta.n_h = n_h;
-    ta.Hz = (u32)Hz;
     // (measured: dense zones like 1024-2048 products per tile, bitmap zones 512 -- their tiles are walked twice and the
     // zones are smaller, so finer tiles balance the warps better)
     ta.target = bp.mode == 1 ? std::min<u32>(bt.tile_target, 512) : bt.tile_target;
@@ -1182,9 +1257,11 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     }
     ta.cnt = cur_p; // the scatter pass counts again, into its own zeroed cursors
     PK_LAUNCH(ctx, (k_block_tiles<1>), pgrid, 256, 0, ta);
+    if (equal_zones) PK_LAUNCH(ctx, k_block_equal_zones, 1, 1024, 0, tstart.as<u32>(), n_h, (u32)Hz, nq, nz, zstart, n_zones_dev);
+    else PK_LAUNCH(ctx, k_block_uniform_zones, grid_for((u64)nz + 1, 256), 256, 0, n_h, (u32)Hz, nz, zstart, n_zones_dev);
     const bool lpt = !bt.natural && nz <= (1u << 17);
-    if (lpt) PK_LAUNCH(ctx, k_block_order, 1, 1024, 0, tstart.as<u32>(), n_h, (u32)Hz, nz, order, n_active_dev, n_zones_dev);
-    else PK_LAUNCH(ctx, k_block_natural_order, 1, 1, 0, nz, n_active_dev, n_zones_dev);
+    if (lpt) PK_LAUNCH(ctx, k_block_order, 1, 1024, 0, tstart.as<u32>(), zstart, n_zones_dev, order, n_active_dev);
+    else PK_LAUNCH(ctx, k_block_natural_order, 1, 1, 0, n_zones_dev, n_active_dev);
 
     phase("tile list");
     const StagingView g = staging_acquire(ctx, out_cap, nv, pl.out_limbs);
@@ -1223,7 +1300,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     ba.n_active = n_active_dev;
     ba.h_base = h_base;
     ba.n_h = n_h;
-    ba.Hz = (u32)Hz;
+    ba.zstart = zstart;
     ba.S = S;
     ba.trunc = trunc ? td : nullptr;
     ba.off_keys = bp.off_keys;

@@ -36,6 +36,9 @@ struct BlockTuning {
     uint32_t force_mode = 0;      // 0 auto, 1 dense, 2 bitmap
     uint32_t force_hz = 0;        // tests: blocks per zone
     uint32_t natural = 0;         // 1 = claim zones in code order instead of heaviest first
+    uint32_t equal_zones = 1;     // bitmap mode: zones cut at equal work (tile-count quantiles) instead of Hz blocks each:
+                                  // 0 never, 1 output partitions only (default), 2 always
+    uint32_t zone_products = 0;   // equal-work zones: products per zone (0 = zone_work)
     uint32_t wide = 1;            // 1 = 64-term chunks of gb (two terms per lane) where the group is large enough
     uint32_t permute = 0;         // 1 = re-order the terms inside B's groups so that the lanes of a tile hit distinct banks
                                   // (measured: 2-3 % on the pairing kernel, the price of one more launch; off)

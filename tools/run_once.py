@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Run the device-resident product of one or more workloads a few times and print the stats of the last call.
-Short command for ncu:  python tools/run_once.py fateman1 [--iters 3] [--algo block] [key=value tuning ...]"""
+Short command for ncu:  python tools/run_once.py fateman1 [--iters 3] [--algo block] [--part i/n] [key=value tuning ...]"""
 import os, sys, statistics
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import piranha_b200 as pb
@@ -8,12 +8,13 @@ from bench import build_operands
 
 def main():
     args = sys.argv[1:]
-    iters, algo, tuning, wl, trunc = 3, pb.PK_ALGO_AUTO, {}, [], None
+    iters, algo, tuning, wl, trunc, part = 3, pb.PK_ALGO_AUTO, {}, [], None, None
     i = 0
     while i < len(args):
         a = args[i]
         if a == "--iters": iters = int(args[i + 1]); i += 2; continue
         if a == "--trunc": trunc = int(args[i + 1]); i += 2; continue
+        if a == "--part": part = tuple(int(x) for x in args[i + 1].split("/")); i += 2; continue
         if a == "--algo": algo = {v: k for k, v in pb.ALGO_NAMES.items()}[args[i + 1]]; i += 2; continue
         if "=" in a: k, v = a.split("="); tuning[k] = int(v)
         else: wl.append(a)
@@ -25,7 +26,9 @@ def main():
         da, db = ctx.upload(a, nv), ctx.upload(b, nv)
         ks, ds = [], []
         for it in range(iters):
-            r = ctx.mul_dev(da, db, algo=algo, **(dict(trunc_mode=1, max_degree=trunc) if trunc is not None else {}))
+            opt = dict(trunc_mode=1, max_degree=trunc) if trunc is not None else {}
+            if part: opt.update(part_index=part[0], part_count=part[1])
+            r = ctx.mul_dev(da, db, algo=algo, **opt)
             st = ctx.stats()
             ks.append(st["mul_kernel_ms"]); ds.append(st["device_ms"])
         W = st["term_products"]
