@@ -551,14 +551,40 @@ __global__ void __launch_bounds__(256) k_zone_gather(const u32 *__restrict__ zon
         else hi = mid;
     }
     u32 z = lo;
-    for (u32 k = 0; k < kGatherPerBlock / 256; ++k) {
+    constexpr u32 kPer = kGatherPerBlock / 256;
+    u64 src[kPer];
+#pragma unroll
+    for (u32 k = 0; k < kPer; ++k) { // source positions first, then all loads of the thread in flight at once
         const u64 i = base + k * 256u + threadIdx.x;
-        if (i >= n_out) break;
-        while (z + 1 < n_zones && __ldg(&zone_prefix[z + 1]) <= i) ++z;
-        const u64 src = __ldg(&zone_off[z]) + (i - __ldg(&zone_prefix[z]));
-        okey[i] = skey[src];
-        osign[i] = ssign[src];
-        for (u32 l = 0; l < limbs; ++l) oplanes[(u64)l * ostride + i] = splanes[(u64)l * sstride + src];
+        src[k] = ~0ull;
+        if (i < n_out) {
+            while (z + 1 < n_zones && __ldg(&zone_prefix[z + 1]) <= i) ++z;
+            src[k] = __ldg(&zone_off[z]) + (i - __ldg(&zone_prefix[z]));
+        }
+    }
+    i64 kk[kPer];
+    signed char sg[kPer];
+#pragma unroll
+    for (u32 k = 0; k < kPer; ++k)
+        if (src[k] != ~0ull) {
+            kk[k] = __ldcs(&skey[src[k]]);
+            sg[k] = __ldcs(&ssign[src[k]]);
+        }
+#pragma unroll
+    for (u32 k = 0; k < kPer; ++k)
+        if (src[k] != ~0ull) {
+            const u64 i = base + k * 256u + threadIdx.x;
+            okey[i] = kk[k];
+            osign[i] = sg[k];
+        }
+    for (u32 l = 0; l < limbs; ++l) {
+        u64 m[kPer];
+#pragma unroll
+        for (u32 k = 0; k < kPer; ++k)
+            if (src[k] != ~0ull) m[k] = __ldcs(&splanes[(u64)l * sstride + src[k]]);
+#pragma unroll
+        for (u32 k = 0; k < kPer; ++k)
+            if (src[k] != ~0ull) oplanes[(u64)l * ostride + base + k * 256u + threadIdx.x] = m[k];
     }
 }
 
