@@ -358,8 +358,9 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
         const i64 *dB = degB.as<i64>(); // (both operands are still in code order here: keys and degrees match)
         PK_LAUNCH(ctx, k_sample_sums, grid_for(S, 256), 256, 0, keyA.as<u64>(), nA, kB, nB, SA, SB, degA.as<i64>(), dB,
                   o.max_degree, trunc ? 1 : 0, sums.as<u64>(), ctx->d_ctr);
-        // (excluded pairs carry the all-ones sentinel and sort last: every bit of the key takes part)
-        radix_sort_keys(ctx, sums.as<u64>(), sorted.as<u64>(), S, 64);
+        // (excluded pairs carry the all-ones sentinel; sums are below the code range, so sorting on one bit more than
+        // the range has still puts the sentinels last -- 4 radix passes instead of 8 for a 2^30 range)
+        radix_sort_keys(ctx, sums.as<u64>(), sorted.as<u64>(), S, (int)std::min<u32>(64, bit_length(pl.range) + 1));
         PK_LAUNCH(ctx, k_pick_cuts, 1, 64, 0, sorted.as<u64>(), ctx->d_ctr, P, dcuts.as<u64>());
         u64 *cuts = reinterpret_cast<u64 *>(static_cast<char *>(ctx->h_scratch) + 1024);
         readback(ctx, cuts, dcuts.p, ((size_t)P + 1) * 8);

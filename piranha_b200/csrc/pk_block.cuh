@@ -305,10 +305,17 @@ __global__ void __launch_bounds__(1024) k_block_equal_zones(const u32 *__restric
 
 // Zone order for the dynamic claiming: heaviest first (LPT), by a counting sort over 256 logarithmic work classes.
 // One block.  Zones without work sort last and are never claimed (n_active).
-__global__ void __launch_bounds__(1024) k_block_order(const u32 *__restrict__ tstart, const u32 *__restrict__ zstart,
-                                                      const u32 *__restrict__ n_zones, u32 *__restrict__ order,
-                                                      u32 *__restrict__ n_active)
+// uniform_hz != 0: the zones are uniform_nz zones of uniform_hz blocks each and this kernel writes zstart / n_zones itself
+// (saves the launch of k_block_uniform_zones).
+__global__ void __launch_bounds__(1024) k_block_order(const u32 *__restrict__ tstart, u32 *__restrict__ zstart,
+                                                      u32 *__restrict__ n_zones, u32 *__restrict__ order,
+                                                      u32 *__restrict__ n_active, u32 n_h, u32 uniform_hz, u32 uniform_nz)
 {
+    if (uniform_hz) {
+        for (u32 z = threadIdx.x; z <= uniform_nz; z += blockDim.x) zstart[z] = min(n_h, z * uniform_hz);
+        if (threadIdx.x == 0) *n_zones = uniform_nz;
+        __syncthreads();
+    }
     const u32 nz = *n_zones;
     // work of a zone = its number of tiles (every tile holds about the same number of products)
     auto zwork_of = [&](u32 z) -> u64 { return (u64)(tstart[zstart[z + 1]] - tstart[zstart[z]]); };
@@ -1257,10 +1264,12 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     }
     ta.cnt = cur_p; // the scatter pass counts again, into its own zeroed cursors
     PK_LAUNCH(ctx, (k_block_tiles<1>), pgrid, 256, 0, ta);
-    if (equal_zones) PK_LAUNCH(ctx, k_block_equal_zones, 1, 1024, 0, tstart.as<u32>(), n_h, (u32)Hz, nq, nz, zstart, n_zones_dev);
-    else PK_LAUNCH(ctx, k_block_uniform_zones, grid_for((u64)nz + 1, 256), 256, 0, n_h, (u32)Hz, nz, zstart, n_zones_dev);
     const bool lpt = !bt.natural && nz <= (1u << 17);
-    if (lpt) PK_LAUNCH(ctx, k_block_order, 1, 1024, 0, tstart.as<u32>(), zstart, n_zones_dev, order, n_active_dev);
+    if (equal_zones) PK_LAUNCH(ctx, k_block_equal_zones, 1, 1024, 0, tstart.as<u32>(), n_h, (u32)Hz, nq, nz, zstart, n_zones_dev);
+    else if (!lpt) PK_LAUNCH(ctx, k_block_uniform_zones, grid_for((u64)nz + 1, 256), 256, 0, n_h, (u32)Hz, nz, zstart, n_zones_dev);
+    if (lpt)
+        PK_LAUNCH(ctx, k_block_order, 1, 1024, 0, tstart.as<u32>(), zstart, n_zones_dev, order, n_active_dev, n_h,
+                  equal_zones ? 0u : (u32)Hz, equal_zones ? 0u : nz);
     else PK_LAUNCH(ctx, k_block_natural_order, 1, 1, 0, n_zones_dev, n_active_dev);
 
     phase("tile list");
