@@ -517,7 +517,8 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
     MulCounters *hc = static_cast<MulCounters *>(ctx->h_scratch);
     // (the product returns only when the stream is idle: measured, a product that returned with its last copy kernel in
     // flight made the next product's stream-ordered allocations of ~1 GB take 16 ms instead of reusing the freed blocks)
-    readback(ctx, hc, ctx->d_ctr, sizeof(MulCounters));
+    // (the block path read the counters after its pairing kernel, into the same host words; only the gather follows it)
+    if (algo != PK_ALGO_BLOCK) readback(ctx, hc, ctx->d_ctr, sizeof(MulCounters));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     ctx->ev_valid = true;
     if (hc->flags & kFlagDegreeOverflow) fail(PK_E_DEGREE, "overflow in the truncation degree arithmetic");
