@@ -149,7 +149,7 @@ int pk_get_stats(pk_ctx *ctx, pk_stats *out);
  *               "block_min_tile" (decline when the average pair of groups is smaller), "block_mode" (0 auto, 1 dense,
  *               2 bitmap), "block_hz" (blocks per zone), "block_natural" (1 = zones claimed in code order instead of
  *               heaviest first), "block_equal_zones" (bitmap mode, zones cut at equal work instead of block_hz blocks each: 0 never,
- *               1 = for output partitions only, the default, 2 always), "block_zone_products" (products per equal-work zone, 0 = auto), "block_wide" (64-term tiles), "block_smem" (bytes of shared memory per zone, 0 = all)
+ *               1 = for output partitions only, the default, 2 always), "block_zone_products" (products per equal-work zone, 0 = auto), "block_wide" (64-term tiles), "block_pair_walk" (1 = the accumulating walk takes two products at a time, default), "block_smem" (bytes of shared memory per zone, 0 = all)
  *               and the measured-and-rejected experiments, all off: "block_permute" (bank-conflict-free order inside
  *               groups), "block_hash" (one-walk hash accumulation for sparse zones), "block_radix0" (pad the radix of
  *               digit 0 to a residue mod 32)

@@ -725,6 +725,7 @@ int pk_ctx_set_tuning(pk_ctx *ctx, const char *key, uint64_t value)
     else if (k == "pipe_min_products") ctx->pipe_min_products = value;
     else if (k == "pipe_test_small") ctx->pipe_test_small = (u32)value;
     else if (k == "block_wide") ctx->block_tuning.wide = (u32)value;
+    else if (k == "block_pair_walk") ctx->block_tuning.pair_walk = (u32)value;
     else if (k == "block_hash") ctx->block_tuning.hash = (u32)value;
     else if (k == "block_permute") ctx->block_tuning.permute = (u32)value;
     else if (k == "block_smem") ctx->block_tuning.smem_limit = (u32)value;

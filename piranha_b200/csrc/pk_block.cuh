@@ -42,6 +42,7 @@ struct BlockArgs {
     const TruncDev *trunc; // degree truncation (nullptr = none)
     u32 off_keys;          // MODE 1: byte offset of the hash keys (cap words) in dynamic shared memory
     u32 hash;              // MODE 1: 1 = try the one-walk hash accumulation first
+    u32 pair_walk;         // one-limb operands: 1 = the accumulating walk takes two products at a time
 };
 
 // Degree truncation in the block path (polynomial.hpp:1402-1531 restated per tile).  Records carry the term's degree as
@@ -413,6 +414,112 @@ __device__ __forceinline__ void block_tile_loop(const uint4 *__restrict__ A, con
                 ++i;
             }
         }
+    }
+}
+
+// The accumulating walk of one-limb operands visits the products of a tile TWO at a time:
+// f2(a0, b0, a1, b1, on1) -- product 0 is always valid, product 1 iff on1.  The two multiply-accumulate chains are
+// independent, so their shared-memory atomics (whose returned values feed the carries) are in flight together; one
+// product at a time leaves a warp waiting on the ATOMS round trip of every word (the `memory` clobber of the atomics
+// also keeps the next product's operand loads behind them).  Used by the dense zones only (see the walk).
+template <typename F2>
+__device__ __forceinline__ void block_tile_loop2(const uint4 *__restrict__ A, const uint4 *__restrict__ B, const uint4 t, u32 lane,
+                                                 F2 &&f2)
+{
+    const u32 a0 = t.x, b0 = t.y, an = t.z & 1023u, bn = (t.z >> 10) & 127u;
+    if (bn == 64u) {
+        const uint4 bv0 = __ldg(&B[b0 + lane]), bv1 = __ldg(&B[b0 + 32u + lane]);
+        for (u32 i = 0; i < an; ++i) {
+            const uint4 av = __ldg(&A[a0 + i]);
+            f2(av, bv0, av, bv1, true);
+        }
+    } else if (bn == kTileCols) {
+        const uint4 bv = __ldg(&B[b0 + lane]);
+        u32 i = 0;
+        for (; i + 1 < an; i += 2) {
+            const uint4 av0 = __ldg(&A[a0 + i]), av1 = __ldg(&A[a0 + i + 1]);
+            f2(av0, bv, av1, bv, true);
+        }
+        if (i < an) {
+            const uint4 av = __ldg(&A[a0 + i]);
+            f2(av, bv, av, bv, false);
+        }
+    } else {
+        // flat tile: positions lane + 32 k of the an x bn products; two consecutive positions of a lane per iteration
+        const u32 total = an * bn;
+        const float rbn = __frcp_rn((float)bn);
+        const u32 q = (u32)(32.5f * rbn), r = 32u - q * bn;
+        u32 i = (u32)(((float)lane + 0.5f) * rbn), j = lane - i * bn;
+        for (u32 idx = lane; idx < total; idx += 64u) {
+            const uint4 av0 = __ldg(&A[a0 + i]), bv0 = __ldg(&B[b0 + j]);
+            i += q;
+            j += r;
+            if (j >= bn) {
+                j -= bn;
+                ++i;
+            }
+            const bool on1 = idx + 32u < total;
+            const uint4 av1 = on1 ? __ldg(&A[a0 + i]) : av0, bv1 = on1 ? __ldg(&B[b0 + j]) : bv0;
+            f2(av0, bv0, av1, bv1, on1);
+            i += q;
+            j += r;
+            if (j >= bn) {
+                j -= bn;
+                ++i;
+            }
+        }
+    }
+}
+
+// One word of an accumulation chain after its atomic returned `old`: x = the word that was added (subtracted when neg),
+// ovf = the overflow that came with it, pn = the next word of the product (0 above it).  Leaves the next word to add in x
+// and its overflow in ovf.  keep_ovf: the add chain drops the overflow above the product (it cannot occur there).
+template <bool SIGNED>
+__device__ __forceinline__ void block_chain_next(u32 old, u32 &x, u32 &ovf, bool neg, u32 pn, bool below_pw)
+{
+    if (SIGNED && neg) {
+        const u32 borrow = ((old < x) ? 1u : 0u) | ovf; // x == 0 with ovf set: the word is unchanged, the borrow moves on
+        x = pn + borrow;
+        ovf = (x < borrow) ? 1u : 0u;
+    } else {
+        u32 xn, ovfn;
+        // xn = pn + ovf + carry(old + x);  ovfn = carry of that sum (ovf and the carry are never both set)
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %2, %3;\n\taddc.cc.u32 %0, %4, %5;\n\taddc.u32 %1, 0, 0;\n\t}"
+            : "=r"(xn), "=r"(ovfn)
+            : "r"(old), "r"(x), "r"(pn), "r"(ovf));
+        x = xn;
+        ovf = below_pw ? ovfn : 0u;
+    }
+}
+
+// block_accumulate for two independent products: the atomics of word w of both chains are issued back to back, then
+// both carries are formed, so the two ATOMS round trips overlap.  on0 / on1 switch a chain off (filtered product).
+template <int NW, int PW, bool SIGNED>
+__device__ __forceinline__ void block_accumulate2(u32 addr0, const u32 (&p0)[4], bool neg0, bool on0, u32 addr1,
+                                                  const u32 (&p1)[4], bool neg1, bool on1, u32 wstride)
+{
+    u32 x0 = p0[0], x1 = p1[0], o0 = 0, o1 = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        if (w >= PW) { // above the product only a pending carry / borrow travels on
+            on0 = on0 && ((x0 | o0) != 0u);
+            on1 = on1 && ((x1 | o1) != 0u);
+            if (!on0 && !on1) return;
+        }
+        const u32 v0 = (SIGNED && neg0) ? 0u - x0 : x0, v1 = (SIGNED && neg1) ? 0u - x1 : x1;
+        if (w == NW - 1) {
+            if (on0) reds_add(addr0, v0);
+            if (on1) reds_add(addr1, v1);
+            return;
+        }
+        u32 old0 = 0, old1 = 0;
+        if (on0) old0 = atoms_add(addr0, v0);
+        if (on1) old1 = atoms_add(addr1, v1);
+        const u32 pn0 = (w + 1 < PW) ? p0[(w + 1 < 4) ? w + 1 : 3] : 0u, pn1 = (w + 1 < PW) ? p1[(w + 1 < 4) ? w + 1 : 3] : 0u;
+        block_chain_next<SIGNED>(old0, x0, o0, neg0, pn0, w + 1 < PW);
+        block_chain_next<SIGNED>(old1, x1, o1, neg1, pn1, w + 1 < PW);
+        addr0 += wstride;
+        addr1 += wstride;
     }
 }
 
@@ -795,7 +902,40 @@ __global__ void __launch_bounds__(1024, 1) k_block(const BlockArgs ba)
                 }
                 block_accumulate<NW, PW, SIGNED>(acc_s + e * 4u, wstride, pw, SIGNED && (((av.y ^ bv.y) & 1u) != 0));
             };
+            // the same for two products at a time (one-limb operands): slots and products of both first, then the two
+            // accumulation chains interleaved word by word
+            auto accumulate2 = [&](const uint4 &av0, const uint4 &bv0, bool on0, const uint4 &av1, const uint4 &bv1, bool on1) {
+                const u32 code0 = av0.x + bv0.x, code1 = av1.x + bv1.x;
+                if (MODE == 1 && !single) {
+                    on0 = on0 && code0 >= c0 && code0 < c1;
+                    on1 = on1 && code1 >= c0 && code1 < c1;
+                }
+                const u32 slot0 = on0 ? code0 - zlo : 0u, slot1 = on1 ? code1 - zlo : 0u;
+                u32 e0 = slot0, e1 = slot1;
+                if (MODE == 1) {
+                    const uint2 bw0 = bm[slot0 >> 5], bw1 = bm[slot1 >> 5];
+                    e0 = on0 ? bw0.y + __popc(bw0.x & ((1u << (slot0 & 31u)) - 1u)) - r0 : 0u;
+                    e1 = on1 ? bw1.y + __popc(bw1.x & ((1u << (slot1 & 31u)) - 1u)) - r0 : 0u;
+                }
+                const u64 ma0 = (u64)av0.z | ((u64)av0.w << 32), mb0 = (u64)bv0.z | ((u64)bv0.w << 32);
+                const u64 ma1 = (u64)av1.z | ((u64)av1.w << 32), mb1 = (u64)bv1.z | ((u64)bv1.w << 32);
+                const u64 lo0 = ma0 * mb0, hi0 = __umul64hi(ma0, mb0), lo1 = ma1 * mb1, hi1 = __umul64hi(ma1, mb1);
+                const u32 p0[4] = {(u32)lo0, (u32)(lo0 >> 32), (u32)hi0, (u32)(hi0 >> 32)};
+                const u32 p1[4] = {(u32)lo1, (u32)(lo1 >> 32), (u32)hi1, (u32)(hi1 >> 32)};
+                block_accumulate2<NW, (PW < 4 ? PW : 4), SIGNED>(acc_s + e0 * 4u, p0, SIGNED && (((av0.y ^ bv0.y) & 1u) != 0), on0,
+                                                                 acc_s + e1 * 4u, p1, SIGNED && (((av1.y ^ bv1.y) & 1u) != 0), on1, wstride);
+            };
             block_for_each_tile(ba.tiles, &s_next, tp1, lane, [&](const uint4 &t) {
+                // (measured: fateman2, five-word chains, 3.63 -> 3.43 ms; fateman1 unchanged; bitmap zones 5 % SLOWER --
+                // their rank look-ups and range tests double too -- and degree-tested tiles 30 % slower, so only the
+                // untested tiles of dense zones take the pair walk)
+                if (LW == 1 && MODE == 0 && ba.pair_walk && !(t.z >> 31)) {
+                    if (lane == 0) my_pairs += (u64)(t.z & 1023u) * ((t.z >> 10) & 127u);
+                    block_tile_loop2(a.A, a.B, t, lane, [&](const uint4 &av0, const uint4 &bv0, const uint4 &av1, const uint4 &bv1, bool on1) {
+                        accumulate2(av0, bv0, true, av1, bv1, on1);
+                    });
+                    return;
+                }
                 if (t.z >> 31) { // truncation: test the degree of every product of this tile
                     block_tile_loop<2, LW>(a.A, a.B, a.A1, a.B1, t, lane, [&](const uint4 &av, const uint4 &bv, const uint2 &ah, const uint2 &bh) {
                         if ((av.y >> 1) + (bv.y >> 1) > dlim) return;
@@ -947,6 +1087,7 @@ inline void block_configure(pk_ctx *ctx)
     t.zone_work = std::max<u32>(1, env_u32("PK_BLOCK_ZONE_WORK", t.zone_work));
     t.force_mode = env_u32("PK_BLOCK_MODE", t.force_mode);
     t.natural = env_u32("PK_BLOCK_NATURAL", t.natural);
+    t.pair_walk = env_u32("PK_BLOCK_PAIR_WALK", t.pair_walk);
     t.wide = env_u32("PK_BLOCK_WIDE", t.wide);
     t.permute = env_u32("PK_BLOCK_PERMUTE", t.permute);
     t.hash = env_u32("PK_BLOCK_HASH", t.hash);
@@ -1314,6 +1455,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     ba.trunc = trunc ? td : nullptr;
     ba.off_keys = bp.off_keys;
     ba.hash = (bp.mode == 1 && bt.hash) ? 1u : 0u;
+    ba.pair_walk = bt.pair_walk;
     const bool is_signed = A->any_neg || B->any_neg;
     const u32 grid = std::min<u32>(bp.grid, nz);
     CUDA_CHECK(cudaEventRecord(ctx->ev_mul0, ctx->stream));

@@ -40,6 +40,7 @@ struct BlockTuning {
                                   // 0 never, 1 output partitions only (default), 2 always
     uint32_t zone_products = 0;   // equal-work zones: products per zone (0 = zone_work)
     uint32_t wide = 1;            // 1 = 64-term chunks of gb (two terms per lane) where the group is large enough
+    uint32_t pair_walk = 1;       // one-limb operands: the accumulating walk takes two products at a time (two ATOMS chains in flight)
     uint32_t permute = 0;         // 1 = re-order the terms inside B's groups so that the lanes of a tile hit distinct banks
                                   // (measured: 2-3 % on the pairing kernel, the price of one more launch; off)
     uint32_t hash = 0;            // sparse zones: 1 = try a one-walk shared-memory hash accumulation before the two-walk
