@@ -36,6 +36,7 @@
 #include <pthread.h>
 #include <stdatomic.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -703,6 +704,24 @@ static int plain_multiplication(mult_t *m)
     return rc;
 }
 
+/* ---------------------------------------------------------------- sanitise (count pass) */
+
+typedef struct {
+    const table_t *tab;
+    uint64_t b0, b1, count;
+} sanitise_t;
+
+static void *sanitise_worker(void *p)
+{
+    sanitise_t *w = (sanitise_t *)p;
+    uint64_t cnt = 0;
+    for (uint64_t b = w->b0; b < w->b1; ++b)
+        for (const node_t *c = &w->tab->b[b]; c && c->used; c = c->next)
+            if (!acc_is_zero(&c->cf)) ++cnt;
+    w->count = cnt;
+    return NULL;
+}
+
 /* ---------------------------------------------------------------- public entry point */
 
 static uint32_t use_threads(uint64_t n1, uint64_t n2, uint32_t n_threads, uint64_t min_work)
@@ -827,19 +846,42 @@ int pc_mul(uint64_t n1, const int64_t *key1, const uint64_t *mag1, uint32_t limb
         rc = plain_multiplication(&m); /* polynomial.hpp:1640-1649 */
     } else {
         const uint64_t est = estimate_final_series_size(&m);
+        if (getenv("PC_TIMING")) fprintf(stderr, "[pc] estimate done at %.1f ms\n", (now_s() - t0) * 1e3);
         rc = table_rehash(&m.tab, est, m.n_threads);
         if (!rc) rc = sparse_kronecker_multiplication(&m);
     }
     if (rc) goto done;
-    /* sanitise_series: count the non-zero terms (zeros are dropped at extraction below) */
+    if (getenv("PC_TIMING")) fprintf(stderr, "[pc] multiplication done at %.1f ms\n", (now_s() - t0) * 1e3);
+    /* sanitise_series: count the non-zero terms (zeros are dropped at extraction below); one bucket range per thread,
+     * base_series_multiplier.hpp:885-948 */
     {
-        uint64_t cnt = 0;
-        for (uint64_t b = 0; b < m.tab.nb; ++b)
-            for (node_t *c = &m.tab.b[b]; c && c->used; c = c->next)
-                if (!acc_is_zero(&c->cf)) ++cnt;
+        const uint32_t nt = (m.n_threads > 1 && m.tab.nb >= 4096) ? m.n_threads : 1;
+        sanitise_t *sw = (sanitise_t *)calloc(nt, sizeof(sanitise_t));
+        pthread_t *sth = (pthread_t *)calloc(nt, sizeof(pthread_t));
+        if (!sw || !sth) {
+            free(sw);
+            free(sth);
+            rc = PC_E_NOMEM;
+            goto done;
+        }
+        for (uint32_t t = 0; t < nt; ++t) {
+            sw[t].tab = &m.tab;
+            sw[t].b0 = m.tab.nb / nt * t;
+            sw[t].b1 = (t + 1 == nt) ? m.tab.nb : m.tab.nb / nt * (t + 1);
+        }
+        for (uint32_t t = 1; t < nt; ++t) pthread_create(&sth[t], NULL, sanitise_worker, &sw[t]);
+        sanitise_worker(&sw[0]);
+        uint64_t cnt = sw[0].count;
+        for (uint32_t t = 1; t < nt; ++t) {
+            pthread_join(sth[t], NULL);
+            cnt += sw[t].count;
+        }
+        free(sw);
+        free(sth);
         out->n = cnt;
         out->buckets = m.tab.nb;
     }
+    if (getenv("PC_TIMING")) fprintf(stderr, "[pc] sanitise done at %.1f ms\n", (now_s() - t0) * 1e3);
 done:
     out->seconds = now_s() - t0;
     if (!rc && out->n) { /* extraction to SoA: outside the timed region */
