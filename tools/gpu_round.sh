@@ -13,5 +13,5 @@ for w in fateman1 pearce1; do
 done
 timeout 200 python tools/run_once.py fateman1 pearce1 fateman2 monagan1 monagan2 monagan3 monagan4 monagan5 pearce2 fateman1_dynamic pearce1_dynamic --iters 8 > gpurun_out/once_all.log 2>&1
 timeout 100 python tools/run_once.py fateman1 --iters 6 --trunc 20 >> gpurun_out/once_all.log 2>&1; timeout 100 python tools/run_once.py fateman1 --iters 6 --trunc 30 >> gpurun_out/once_all.log 2>&1
-(timeout 100 build/bin/fateman1 5 | tail -n 1; timeout 100 build/bin/fateman2 3 | tail -n 1; timeout 100 build/bin/pearce1 5 | tail -n 1; timeout 100 build/bin/fateman1_rational 5 | tail -n 1) > gpurun_out/cpp_bench.txt 2>&1
+(timeout 100 build/bin/fateman1 5 | tail -n 1; timeout 100 build/bin/fateman2 3 | tail -n 1; timeout 100 build/bin/pearce1 5 | tail -n 1; timeout 100 build/bin/fateman1_rational 5 | tail -n 1; timeout 100 build/bin/pearce1_rational 3 | tail -n 1) > gpurun_out/cpp_bench.txt 2>&1
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -n 2 gpurun_out/smoke.log
