@@ -598,11 +598,13 @@ static int sparse_kronecker_multiplication(mult_t *m)
         ws[t].bpz = m->tab.nb / n_zones;
     }
     for (int phase = 0; phase < 2 && !rc; ++phase) {
+        const double tp = now_s();
         for (uint32_t t = 0; t < m->n_threads; ++t) pthread_create(&th[t], NULL, phase ? zone_worker : zone_builder, &ws[t]);
         for (uint32_t t = 0; t < m->n_threads; ++t) {
             pthread_join(th[t], NULL);
             if (ws[t].rc) rc = ws[t].rc;
         }
+        if (getenv("PC_TIMING")) fprintf(stderr, "[pc] %s %.1f ms\n", phase ? "zone workers" : "zone builders", (now_s() - tp) * 1e3);
     }
     for (uint64_t z = 0; z < n_zones; ++z) free(zones[z].t);
     free(zones);
