@@ -274,6 +274,29 @@ int main(int argc, char **argv)
         }
         return 0;
     }
+    if (argc > 1 && std::string(argv[1]) == "--calc") { // exact arithmetic on request, for tests/test_cpp_host.py
+        // lines "op a b" (integers: add sub mul div mod gcd) or "qop an ad bn bd" (rationals: qadd qsub qmul qdiv), decimal
+        std::string op, x[4];
+        while (std::cin >> op) {
+            try {
+                if (op[0] == 'q') {
+                    std::cin >> x[0] >> x[1] >> x[2] >> x[3];
+                    const rational a{integer{x[0]}, integer{x[1]}}, b{integer{x[2]}, integer{x[3]}};
+                    const rational r = op == "qadd" ? a + b : op == "qsub" ? a - b : op == "qmul" ? a * b : a / b;
+                    std::cout << r.num() << ' ' << r.den() << '\n';
+                } else {
+                    std::cin >> x[0] >> x[1];
+                    const integer a{x[0]}, b{x[1]};
+                    const integer r = op == "add" ? a + b : op == "sub" ? a - b : op == "mul" ? a * b : op == "div" ? a / b
+                                      : op == "mod" ? a % b : integer::gcd(a, b);
+                    std::cout << r << '\n';
+                }
+            } catch (const std::exception &e) {
+                std::cout << "error " << e.what() << '\n';
+            }
+        }
+        return 0;
+    }
     RUN_TEST(integer_test);
     RUN_TEST(rational_test);
     RUN_TEST(kronecker_array_test);

@@ -46,6 +46,54 @@ def test_host_kronecker_limits_match_the_golden_table():
         assert hmin == golden["h_min"][m], m
 
 
+def test_host_integer_and_rational_against_python():
+    """The mirror's exact arithmetic (integer +, -, *, truncating / and %, gcd; rational +, -, *, / in canonical form) on
+    random operands of up to ~180 bits against Python's int and fractions.Fraction (C semantics for / and %)."""
+    import random
+    from fractions import Fraction
+
+    _build()
+    rng = random.Random(20240607)
+
+    def big(bits, nonzero=False):
+        while True:
+            v = rng.getrandbits(rng.randrange(1, bits)) * rng.choice((-1, 1))
+            if v or not nonzero:
+                return v
+
+    lines, want = [], []
+    for _ in range(1500):
+        op = rng.choice(("add", "sub", "mul", "div", "mod", "gcd"))
+        a, b = big(180), big(180, nonzero=op in ("div", "mod"))
+        if op == "div":
+            r = abs(a) // abs(b) * (1 if (a < 0) == (b < 0) else -1)
+        elif op == "mod":
+            r = abs(a) % abs(b) * (-1 if a < 0 else 1)
+        elif op == "gcd":
+            import math
+            r = math.gcd(a, b)
+        else:
+            r = {"add": a + b, "sub": a - b, "mul": a * b}[op]
+        lines.append(f"{op} {a} {b}")
+        want.append(str(r))
+    for _ in range(1500):
+        op = rng.choice(("qadd", "qsub", "qmul", "qdiv"))
+        an, ad, bn, bd = big(90), big(90, True), big(90, nonzero=op == "qdiv"), big(90, True)
+        fa, fb = Fraction(an, ad), Fraction(bn, bd)
+        r = {"qadd": fa + fb, "qsub": fa - fb, "qmul": fa * fb, "qdiv": (fa / fb) if bn else None}[op]
+        lines.append(f"{op} {an} {ad} {bn} {bd}")
+        want.append(f"{r.numerator} {r.denominator}")
+    lines += ["div 5 0", "qdiv 1 2 0 3", "mul " + str(1 << 200) + " " + str(1 << 200)]
+    p = subprocess.run([os.path.join(BIN, "host_logic_test"), "--calc"], input="\n".join(lines) + "\n", capture_output=True,
+                       text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    got = p.stdout.splitlines()
+    assert len(got) == len(lines)
+    bad = [(l, g, w) for l, g, w in zip(lines, got, want) if g != w]
+    assert not bad, bad[:5]
+    assert all(g.startswith("error") for g in got[len(want):])  # division by zero, capacity overflow: reported, never wrapped
+
+
 @pytest.mark.gpu
 def test_reference_multiplier_tests_through_operator_star():
     out = _run("multiplier_test", 900)
