@@ -178,6 +178,31 @@ def test_pearce1_full(ctx):
     assert eval_mod_p(*r, 5, pt) == ea * eb % P31
 
 
+@pytest.mark.parametrize("parts", [2, 8])
+def test_pearce1_full_partitions(ctx, parts):
+    """BASELINE-size pearce1 cut into output partitions (the per-rank work of a multi-GPU product; bitmap zones cut at
+    equal work): ordered, disjoint, and together the whole product -- checksum of checksums and term counts."""
+    f, g = po.pearce_operands(12)
+    a, b = terms(f, 5, 1), terms(g, 5, 2)
+    da, db = ctx.upload(a, 5), ctx.upload(b, 5)
+    whole = ctx.mul_dev(da, db)
+    digest, n, pairs, last_key = 0, 0, 0, None
+    for p in range(parts):
+        part = ctx.mul_dev(da, db, part_index=p, part_count=parts)
+        st = ctx.stats()
+        pairs += st["term_products"]
+        digest = (digest + part.digest()) & ((1 << 64) - 1)
+        n += len(part)
+        assert len(part) > 0
+        k = part.download()[0]
+        assert_sorted_unique(k)
+        assert last_key is None or k[0] > last_key
+        last_key = k[-1]
+    assert n == len(whole) == 5821335
+    assert digest == whole.digest()
+    assert pairs == 6188 * 6188
+
+
 @pytest.mark.parametrize("which,size", [(1, 12341), (2, 12341), (3, 39711), (4, 135751), (5, 417311)])
 def test_monagan(ctx, which, size):
     f, g = po.monagan_operands(which)
