@@ -11,8 +11,10 @@
  * reference interface it replaces; paths are relative to /root/reference/include/piranha/.
  *
  * Plain pointers and sizes only; no C++ or torch types.  Re-entrant: all mutable state lives in a pk_ctx
- * (one CUDA device + one stream); different contexts may be used concurrently from different threads
- * (base_series_multiplier.hpp:404-408: multipliers are built and consumed on one thread).
+ * (one CUDA device + one stream, or -- pk_ctx_create_multi -- several devices driven from the one calling thread);
+ * different contexts may be used concurrently from different threads (base_series_multiplier.hpp:404-408: multipliers
+ * are built and consumed on one thread).  No call changes the calling thread's current CUDA device, and device memory
+ * comes from a pool private to the context (the device's default memory pool is not touched).
  *
  * Term format (both directions):
  *   key[i]   int64 Kronecker code of the exponent vector, piranha's kronecker_array<int64_t> codification for
@@ -125,6 +127,20 @@ typedef struct pk_stats {
  * stream so its CUDA events see the work) or NULL for a private non-blocking stream.
  * Fails with PK_E_CUDA when no usable GPU is present: there is no CPU fallback. */
 int pk_ctx_create(int device, void *stream, pk_ctx **out);
+/* Create a context that spreads every product over `n_devices` <= 16 GPUs of this box (device_ids = NULL: devices
+ * 0..n-1; a device may be listed more than once, its parts then share it -- how the tests run the N-part path on one GPU).
+ * This is the multiplier's own parallelism -- the zones that the reference's thread pool claims inside ONE call of
+ * series_multiplier::operator()() (polynomial.hpp:1783-1966, settings::set_n_threads) -- lifted to devices: the output
+ * Kronecker-code range is cut into n_devices ordered parts balanced by work, device r computes part r from its own
+ * replica of the operands, and pk_mul() / pk_download() copy the parts over n_devices PCIe links at once, each straight
+ * to its offset of ONE pinned host result (ordered ranges: no merge, no device-to-device traffic).  Products of
+ * pk_mul_dev() stay partitioned in HBM and are replicated peer-to-peer only when they become operands.  One worker thread
+ * per device; the handle is used from one thread at a time like any other context.  All entry points accept the handle
+ * except the single-device exports (pk_dpoly_export*, pk_dpoly_publish_size, pk_dpoly_export_peers) and pk_opts.part_count
+ * > 1, which return PK_E_ARGS; polynomials belong to the context that created them. */
+int pk_ctx_create_multi(uint32_t n_devices, const int *device_ids, pk_ctx **out);
+/* Number of devices behind the handle (1 for pk_ctx_create). */
+uint32_t pk_ctx_device_count(const pk_ctx *ctx);
 void pk_ctx_destroy(pk_ctx *ctx);
 /* Release what the context keeps between products to make them cheap: the staging arrays of the shared-memory paths
  * (up to min(term products, code range) terms, ~1 GB after a pearce1-sized product), idle pinned result buffers and the

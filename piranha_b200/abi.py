@@ -20,7 +20,7 @@ PK_ALGO_AUTO, PK_ALGO_DENSE, PK_ALGO_HASH, PK_ALGO_ZONE, PK_ALGO_BLOCK = range(5
 ALGO_NAMES = {0: "auto", 1: "dense", 2: "hash", 3: "zone", 4: "block"}
 
 EXPORTED_SYMBOLS = [
-    "pk_ctx_create", "pk_ctx_destroy", "pk_ctx_trim", "pk_last_error", "pk_ctx_set_limits", "pk_ctx_get_limits", "pk_get_stats", "pk_ctx_set_tuning",
+    "pk_ctx_create", "pk_ctx_create_multi", "pk_ctx_device_count", "pk_ctx_destroy", "pk_ctx_trim", "pk_last_error", "pk_ctx_set_limits", "pk_ctx_get_limits", "pk_get_stats", "pk_ctx_set_tuning",
     "pk_mul", "pk_result_free", "pk_upload", "pk_mul_dev", "pk_check_bounds", "pk_download", "pk_dpoly_free", "pk_dpoly_size",
     "pk_dpoly_limbs", "pk_dpoly_nvars", "pk_dpoly_export", "pk_dpoly_export_padded", "pk_dpoly_digest",
     "pk_dpoly_publish_size", "pk_dpoly_export_peers",
@@ -64,8 +64,8 @@ def _raise(code: int, msg: str):
     """Map status codes to the exception types the reference throws."""
     if code == PK_E_ARGS:
         raise ValueError(msg)  # std::invalid_argument
-    if code in (PK_E_KEY_RANGE, PK_E_DEGREE):
-        raise OverflowError(msg)  # std::overflow_error
+    if code in (PK_E_KEY_RANGE, PK_E_DEGREE, PK_E_CF_WIDTH):
+        raise OverflowError(msg)  # std::overflow_error (the C++ mirror maps PK_E_CF_WIDTH the same way)
     if code == PK_E_NOMEM:
         raise MemoryError(msg)  # std::bad_alloc
     raise PkError(code, msg)
@@ -85,6 +85,9 @@ def load_library():
     lib = C.CDLL(LIB_PATH)
     vp, u32, u64, i64 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int64
     lib.pk_ctx_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    lib.pk_ctx_create_multi.argtypes = [u32, C.POINTER(C.c_int), C.POINTER(vp)]
+    lib.pk_ctx_device_count.argtypes = [vp]
+    lib.pk_ctx_device_count.restype = u32
     lib.pk_ctx_destroy.argtypes = [vp]
     lib.pk_ctx_destroy.restype = None
     lib.pk_ctx_trim.argtypes = [vp]
@@ -204,15 +207,28 @@ class DevicePoly:
 
 
 class Context:
-    """pk_ctx: one device, one stream."""
+    """pk_ctx: one device and one stream, or (Context.multi) several devices behind one handle."""
 
-    def __init__(self, device: int = 0, stream: int = 0):
+    def __init__(self, device: int = 0, stream: int = 0, devices: Optional[Sequence[int]] = None):
         self.lib = load_library()
         h = C.c_void_p()
-        rc = self.lib.pk_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h))
+        if devices is not None:
+            ids = (C.c_int * len(devices))(*devices)
+            rc = self.lib.pk_ctx_create_multi(len(devices), ids, C.byref(h))
+        else:
+            rc = self.lib.pk_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h))
         if rc != PK_OK:
             raise PkError(rc, "pk_ctx_create failed: no usable sm_100 GPU (there is no CPU fallback)")
         self.handle = h
+
+    @classmethod
+    def multi(cls, devices: Sequence[int]) -> "Context":
+        """pk_ctx_create_multi: every product is cut into len(devices) output-code ranges, one per device."""
+        return cls(devices=list(devices))
+
+    @property
+    def device_count(self) -> int:
+        return int(self.lib.pk_ctx_device_count(self.handle))
 
     def close(self):
         if self.handle:

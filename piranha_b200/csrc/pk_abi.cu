@@ -73,6 +73,9 @@ void compute_meta(pk_ctx *ctx, pk_dpoly *p, const i64 *key, const u64 *mag, cons
 
 void ensure_meta(pk_ctx *ctx, pk_dpoly *p)
 {
+    // results of pk_mul_dev get their exponent bounds on first use as an operand; two threads (contexts) may share the
+    // polynomial, so the lazy fill is serialised
+    std::lock_guard<std::mutex> lock(p->meta_mutex);
     if (!p->has_meta) compute_meta(ctx, p, p->key, p->planes, p->sign, p->stride, false);
 }
 
@@ -159,7 +162,7 @@ PinnedBuf *pinned_acquire(pk_ctx *ctx, size_t bytes)
         PinnedBuf nb;
         nb.bytes = std::max<size_t>(bytes, 4096);
         nb.bytes += nb.bytes / 8; // headroom so similar-sized results reuse it
-        CUDA_CHECK(cudaMallocHost(&nb.ptr, nb.bytes));
+        CUDA_CHECK(cudaHostAlloc(&nb.ptr, nb.bytes, cudaHostAllocPortable)); // any device may copy into it
         ctx->pinned.push_back(nb);
         best = &ctx->pinned.back();
     }
@@ -538,6 +541,8 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
 
 } // namespace
 
+#include "pk_multi.cuh"
+
 // ------------------------------------------------------------------------------------------------ C ABI
 
 #define PK_TRY(ctx_expr, ...)                                    \
@@ -570,7 +575,7 @@ int pk_ctx_create(int device, void *stream, pk_ctx **out)
     std::unique_ptr<pk_ctx> c(new (std::nothrow) pk_ctx);
     if (!c) return PK_E_NOMEM;
     c->device = device;
-    if (cudaSetDevice(device) != cudaSuccess) return PK_E_CUDA;
+    DeviceScope ds(device); // the caller's current device is restored on return
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
     c->smem_per_sm = prop.sharedMemPerMultiprocessor;
@@ -581,17 +586,24 @@ int pk_ctx_create(int device, void *stream, pk_ctx **out)
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return PK_E_CUDA;
         c->own_stream = true;
     }
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX; // keep freed blocks cached: no cudaMalloc in steady state
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    // a private stream-ordered pool that keeps freed blocks cached (no cudaMalloc in steady state); the device's
+    // default pool and its attributes belong to the host application and are left alone
+    cudaMemPoolProps pp{};
+    pp.allocType = cudaMemAllocationTypePinned;
+    pp.handleTypes = cudaMemHandleTypeNone;
+    pp.location.type = cudaMemLocationTypeDevice;
+    pp.location.id = device;
+    bool ok = cudaMemPoolCreate(&c->pool, &pp) == cudaSuccess;
+    if (ok) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
-    bool ok = cudaEventCreate(&c->ev_begin) == cudaSuccess && cudaEventCreate(&c->ev_mul0) == cudaSuccess
-              && cudaEventCreate(&c->ev_mul1) == cudaSuccess && cudaEventCreate(&c->ev_end) == cudaSuccess
-              && cudaMallocHost(&c->h_scratch, kScratchBytes) == cudaSuccess
-              && cudaMalloc((void **)&c->d_ctr, sizeof(MulCounters)) == cudaSuccess
-              && cudaMalloc((void **)&c->d_meta, sizeof(MetaDev)) == cudaSuccess
-              && cudaMalloc((void **)&c->d_digest, 8) == cudaSuccess;
+    ok = ok && cudaEventCreate(&c->ev_begin) == cudaSuccess && cudaEventCreate(&c->ev_mul0) == cudaSuccess
+         && cudaEventCreate(&c->ev_mul1) == cudaSuccess && cudaEventCreate(&c->ev_end) == cudaSuccess
+         && cudaHostAlloc(&c->h_scratch, kScratchBytes, cudaHostAllocPortable) == cudaSuccess
+         && cudaMalloc((void **)&c->d_ctr, sizeof(MulCounters)) == cudaSuccess
+         && cudaMalloc((void **)&c->d_meta, sizeof(MetaDev)) == cudaSuccess
+         && cudaMalloc((void **)&c->d_digest, 8) == cudaSuccess;
     if (!ok) {
         pk_ctx_destroy(c.release());
         return PK_E_CUDA;
@@ -612,10 +624,60 @@ int pk_ctx_create(int device, void *stream, pk_ctx **out)
     return PK_OK;
 }
 
+int pk_ctx_create_multi(uint32_t n_devices, const int *device_ids, pk_ctx **out)
+{
+    if (!out) return PK_E_ARGS;
+    *out = nullptr;
+    if (n_devices == 0 || n_devices > kMaxPeers) return PK_E_ARGS;
+    std::unique_ptr<pk_ctx> M(new (std::nothrow) pk_ctx);
+    if (!M) return PK_E_NOMEM;
+    int rc = PK_OK;
+    for (uint32_t i = 0; i < n_devices && rc == PK_OK; ++i) {
+        pk_ctx *sub = nullptr;
+        rc = pk_ctx_create(device_ids ? device_ids[i] : (int)i, nullptr, &sub);
+        if (rc == PK_OK) M->subs.push_back(sub);
+    }
+    if (rc != PK_OK) {
+        for (pk_ctx *sub : M->subs) pk_ctx_destroy(sub);
+        return rc;
+    }
+    M->device = M->subs[0]->device;
+    M->limits = M->subs[0]->limits;
+    M->h_min = M->subs[0]->h_min;
+    M->h_max = M->subs[0]->h_max;
+    // direct peer copies between the devices (parts of a device-resident product are replicated over NVLink when the
+    // product becomes an operand); without peer access cudaMemcpyPeerAsync stages through the host, still correct
+    for (pk_ctx *x : M->subs) {
+        DeviceScope ds(x->device);
+        for (pk_ctx *y : M->subs) {
+            int can = 0;
+            if (x != y && cudaDeviceCanAccessPeer(&can, x->device, y->device) == cudaSuccess && can)
+                if (cudaDeviceEnablePeerAccess(y->device, 0) == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        }
+    }
+    try {
+        M->multi = new pk_multi_state;
+        M->multi->w.resize(n_devices);
+        pk_ctx *Mp = M.get();
+        for (uint32_t r = 0; r < n_devices; ++r) M->multi->w[r].th = std::thread(multi_worker_main, Mp, r);
+    } catch (...) {
+        multi_destroy(M.release());
+        return PK_E_NOMEM;
+    }
+    *out = M.release();
+    return PK_OK;
+}
+
+uint32_t pk_ctx_device_count(const pk_ctx *ctx) { return ctx ? (ctx->subs.empty() ? 1u : (uint32_t)ctx->subs.size()) : 0u; }
+
 void pk_ctx_destroy(pk_ctx *ctx)
 {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    if (!ctx->subs.empty() || ctx->multi) {
+        multi_destroy(ctx);
+        return;
+    }
+    DeviceScope ds(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->staging) {
         free_dpoly_arrays(ctx, ctx->staging);
@@ -633,6 +695,7 @@ void pk_ctx_destroy(pk_ctx *ctx)
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->ev_part) cudaEventDestroy(ctx->ev_part);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool); // (blocks still owned by live polynomials are released with them)
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -640,8 +703,26 @@ void pk_ctx_destroy(pk_ctx *ctx)
 int pk_ctx_trim(pk_ctx *ctx)
 {
     if (!ctx) return PK_E_ARGS;
+    if (!ctx->subs.empty()) {
+        for (pk_ctx *sub : ctx->subs) {
+            const int rc = pk_ctx_trim(sub);
+            if (rc != PK_OK) {
+                ctx->err = sub->err;
+                return rc;
+            }
+        }
+        for (auto &b : ctx->pinned)
+            if (!b.in_use && b.ptr) {
+                cudaFreeHost(b.ptr);
+                b.ptr = nullptr;
+                b.bytes = 0;
+            }
+        ctx->pinned.erase(std::remove_if(ctx->pinned.begin(), ctx->pinned.end(), [](const PinnedBuf &b) { return !b.in_use && !b.ptr; }),
+                          ctx->pinned.end());
+        return PK_OK;
+    }
     PK_TRY(ctx, {
-        cudaSetDevice(ctx->device);
+        DeviceScope ds(ctx->device);
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         if (ctx->staging) {
             free_dpoly_arrays(ctx, ctx->staging);
@@ -658,8 +739,7 @@ int pk_ctx_trim(pk_ctx *ctx)
         ctx->pinned.erase(std::remove_if(ctx->pinned.begin(), ctx->pinned.end(), [](const PinnedBuf &b) { return !b.in_use && !b.ptr; }),
                           ctx->pinned.end());
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        if (ctx->pool) cudaMemPoolTrimTo(ctx->pool, 0);
     })
 }
 
@@ -685,6 +765,7 @@ int pk_ctx_set_limits(pk_ctx *ctx, uint32_t n_vars, const int64_t *limits)
     ctx->limits[n_vars].assign(limits, limits + n_vars);
     ctx->h_min[n_vars] = (int64_t)-hmax;
     ctx->h_max[n_vars] = (int64_t)hmax;
+    for (pk_ctx *sub : ctx->subs) pk_ctx_set_limits(sub, n_vars, limits);
     return PK_OK;
 }
 
@@ -701,6 +782,13 @@ int pk_ctx_get_limits(const pk_ctx *ctx, uint32_t n_vars, int64_t *limits_out, i
 int pk_ctx_set_tuning(pk_ctx *ctx, const char *key, uint64_t value)
 {
     if (!ctx || !key) return PK_E_ARGS;
+    if (!ctx->subs.empty()) {
+        for (pk_ctx *sub : ctx->subs) {
+            const int rc = pk_ctx_set_tuning(sub, key, value);
+            if (rc != PK_OK) return rc;
+        }
+        return PK_OK;
+    }
     ZoneTuning &t = ctx->zone_tuning;
     const std::string k(key);
     if (k == "zone_target") t.target_zones = (u32)value;
@@ -737,6 +825,10 @@ int pk_ctx_set_tuning(pk_ctx *ctx, const char *key, uint64_t value)
 int pk_get_stats(pk_ctx *ctx, pk_stats *out)
 {
     if (!ctx || !out) return PK_E_ARGS;
+    if (!ctx->subs.empty()) { // aggregated by the last product (sums over the parts, times = the slowest device)
+        *out = ctx->stats;
+        return PK_OK;
+    }
     if (ctx->ev_valid) {
         float ms = 0.f;
         cudaEventSynchronize(ctx->ev_end); // the last copy of a product may still be running
@@ -752,7 +844,14 @@ int pk_upload(pk_ctx *ctx, const pk_poly *p, pk_dpoly **out)
 {
     if (!ctx || !out) return PK_E_ARGS;
     *out = nullptr;
-    PK_TRY(ctx, { cudaSetDevice(ctx->device); *out = upload_impl(ctx, p); })
+    PK_TRY(ctx, {
+        if (!ctx->subs.empty()) {
+            *out = multi_upload(ctx, p);
+        } else {
+            DeviceScope ds(ctx->device);
+            *out = upload_impl(ctx, p);
+        }
+    })
 }
 
 int pk_mul_dev(pk_ctx *ctx, const pk_dpoly *a, const pk_dpoly *b, const pk_opts *opts, pk_dpoly **out)
@@ -760,19 +859,35 @@ int pk_mul_dev(pk_ctx *ctx, const pk_dpoly *a, const pk_dpoly *b, const pk_opts 
     if (!ctx || !out) return PK_E_ARGS;
     *out = nullptr;
     PK_TRY(ctx, {
-        cudaSetDevice(ctx->device);
-        *out = mul_impl(ctx, const_cast<pk_dpoly *>(a), const_cast<pk_dpoly *>(b), opts);
+        if (!ctx->subs.empty()) {
+            *out = multi_mul_dev(ctx, const_cast<pk_dpoly *>(a), const_cast<pk_dpoly *>(b), opts);
+        } else {
+            if ((a && a->is_multi) || (b && b->is_multi)) fail(PK_E_ARGS, "operand belongs to a multi-device context");
+            DeviceScope ds(ctx->device);
+            *out = mul_impl(ctx, const_cast<pk_dpoly *>(a), const_cast<pk_dpoly *>(b), opts);
+        }
     })
 }
 
 int pk_check_bounds(pk_ctx *ctx, const pk_dpoly *a, const pk_dpoly *b)
 {
     if (!ctx || !a || !b) return PK_E_ARGS;
+    if (!ctx->subs.empty()) { // the exponent bounds of the replicas on the first device
+        PK_TRY(ctx, {
+            multi_require(ctx, a);
+            multi_require(ctx, b);
+            multi_replicate(ctx, const_cast<pk_dpoly *>(a));
+            multi_replicate(ctx, const_cast<pk_dpoly *>(b));
+            const int rc = pk_check_bounds(ctx->subs[0], a->rep[0], b->rep[0]);
+            if (rc != PK_OK) fail(rc, ctx->subs[0]->err);
+        })
+    }
     PK_TRY(ctx, {
+        if (a->is_multi || b->is_multi) fail(PK_E_ARGS, "operand belongs to a multi-device context");
         if (a->n_vars != b->n_vars) fail(PK_E_ARGS, "incompatible arguments sets");
         if (a->n_vars >= ctx->limits.size()) fail(PK_E_ARGS, "too many variables for the Kronecker codification");
         if (a->n && b->n) {
-            cudaSetDevice(ctx->device);
+            DeviceScope ds(ctx->device);
             ensure_meta(ctx, const_cast<pk_dpoly *>(a));
             ensure_meta(ctx, const_cast<pk_dpoly *>(b));
             for (u32 v = 0; v < a->n_vars; ++v) {
@@ -787,13 +902,25 @@ int pk_check_bounds(pk_ctx *ctx, const pk_dpoly *a, const pk_dpoly *b)
 int pk_download(pk_ctx *ctx, const pk_dpoly *p, pk_result *out)
 {
     if (!ctx || !p || !out) return PK_E_ARGS;
-    PK_TRY(ctx, { cudaSetDevice(ctx->device); download_impl(ctx, p, out); })
+    PK_TRY(ctx, {
+        if (!ctx->subs.empty()) {
+            multi_download(ctx, p, out);
+        } else {
+            if (p->is_multi) fail(PK_E_ARGS, "polynomial belongs to a multi-device context");
+            DeviceScope ds(ctx->device);
+            download_impl(ctx, p, out);
+        }
+    })
 }
 
 void pk_dpoly_free(pk_ctx *ctx, pk_dpoly *p)
 {
     if (!ctx || !p) return;
-    cudaSetDevice(ctx->device);
+    if (p->is_multi) {
+        if (!ctx->subs.empty()) multi_free(ctx, p);
+        return;
+    }
+    DeviceScope ds(ctx->device);
     free_dpoly_arrays(ctx, p);
     delete p;
 }
@@ -804,9 +931,9 @@ uint32_t pk_dpoly_nvars(const pk_dpoly *p) { return p ? p->n_vars : 0; }
 
 int pk_dpoly_export_padded(pk_ctx *ctx, const pk_dpoly *p, void *d_key, void *d_mag, void *d_sign, uint32_t mag_limbs)
 {
-    if (!ctx || !p || mag_limbs < p->limbs) return PK_E_ARGS;
+    if (!ctx || !p || mag_limbs < p->limbs || p->is_multi || !ctx->subs.empty()) return PK_E_ARGS;
     PK_TRY(ctx, {
-        cudaSetDevice(ctx->device);
+        DeviceScope ds(ctx->device);
         if (p->n) {
             if (d_key) CUDA_CHECK(cudaMemcpyAsync(d_key, p->key, p->n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
             if (d_mag)
@@ -841,9 +968,10 @@ bool fill_peer_table(PeerTable &t, uint32_t n_peers, const uint64_t *slots, cons
 int pk_dpoly_publish_size(pk_ctx *ctx, const pk_dpoly *p, uint32_t n_peers, const uint64_t *slot_ptrs)
 {
     PeerTable t{};
-    if (!ctx || !p || !slot_ptrs || !fill_peer_table(t, n_peers, slot_ptrs, nullptr, nullptr, nullptr)) return PK_E_ARGS;
+    if (!ctx || !p || p->is_multi || !ctx->subs.empty() || !slot_ptrs || !fill_peer_table(t, n_peers, slot_ptrs, nullptr, nullptr, nullptr))
+        return PK_E_ARGS;
     PK_TRY(ctx, {
-        cudaSetDevice(ctx->device);
+        DeviceScope ds(ctx->device);
         PK_LAUNCH(ctx, k_peer_publish, 1, 32, 0, t, n_peers, p->n, (u64)std::max<u32>(1, p->limbs));
     })
 }
@@ -854,10 +982,10 @@ int pk_dpoly_export_peers(pk_ctx *ctx, const pk_dpoly *p, uint32_t n_peers, uint
 {
     PeerTable t{};
     if (!ctx || !p || !d_sizes || !key_ptrs || !mag_ptrs || !sign_ptrs || rank >= n_peers || p->limbs > 8 || cap_limbs > 8
-        || !fill_peer_table(t, n_peers, nullptr, key_ptrs, mag_ptrs, sign_ptrs))
+        || p->is_multi || !ctx->subs.empty() || !fill_peer_table(t, n_peers, nullptr, key_ptrs, mag_ptrs, sign_ptrs))
         return PK_E_ARGS;
     PK_TRY(ctx, {
-        cudaSetDevice(ctx->device);
+        DeviceScope ds(ctx->device);
         if (p->n)
             PK_LAUNCH(ctx, k_peer_push, grid_for(p->n, 256), 256, 0, t, n_peers, rank, static_cast<const u64 *>(d_sizes), p->key,
                       p->planes, p->stride, p->sign, p->n, p->limbs, cap_terms, cap_limbs);
@@ -867,8 +995,12 @@ int pk_dpoly_export_peers(pk_ctx *ctx, const pk_dpoly *p, uint32_t n_peers, uint
 int pk_dpoly_digest(pk_ctx *ctx, const pk_dpoly *p, uint64_t *digest_out)
 {
     if (!ctx || !p || !digest_out) return PK_E_ARGS;
+    if (!ctx->subs.empty()) {
+        PK_TRY(ctx, { *digest_out = multi_digest(ctx, p); })
+    }
+    if (p->is_multi) return PK_E_ARGS;
     PK_TRY(ctx, {
-        cudaSetDevice(ctx->device);
+        DeviceScope ds(ctx->device);
         CUDA_CHECK(cudaMemsetAsync(ctx->d_digest, 0, 8, ctx->stream));
         if (p->n) {
             const u32 grid = std::min<u32>(grid_for(p->n, 256), (u32)ctx->sm_count * 8);
@@ -958,7 +1090,7 @@ void mul_pipelined(pk_ctx *ctx, pk_dpoly *da, pk_dpoly *db, const pk_opts *opts,
     auto copy_part = [&](const pk_dpoly *p, u64 at, cudaStream_t after) {
         if (!p->n) return;
         void *aos = nullptr;
-        CUDA_CHECK(cudaMallocAsync(&aos, p->n * L * 8, ctx->stream));
+        CUDA_CHECK(cudaMallocFromPoolAsync(&aos, p->n * L * 8, ctx->pool, ctx->stream));
         parts.aos.push_back(aos);
         PK_LAUNCH(ctx, k_planes_to_aos, grid_for(p->n, 256), 256, 0, p->planes, static_cast<u64 *>(aos), p->n, p->limbs, p->stride, L);
         CUDA_CHECK(cudaEventRecord(ctx->ev_part, ctx->stream));
@@ -1027,8 +1159,11 @@ int pk_mul(pk_ctx *ctx, const pk_poly *a, const pk_poly *b, const pk_opts *opts,
 {
     if (!ctx || !out) return PK_E_ARGS;
     memset(out, 0, sizeof(*out));
+    if (!ctx->subs.empty()) {
+        PK_TRY(ctx, { multi_mul(ctx, a, b, opts, out); })
+    }
     PK_TRY(ctx, {
-        cudaSetDevice(ctx->device);
+        DeviceScope ds(ctx->device);
         DPolyGuard da{ctx, upload_impl(ctx, a)};
         DPolyGuard db{ctx, (a == b) ? nullptr : upload_impl(ctx, b)};
         pk_dpoly *pa = da.p;

@@ -4,9 +4,13 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "pk_device.cuh"
@@ -89,6 +93,11 @@ struct pk_ctx {
     size_t total_mem = 0;
     pk_dpoly *staging = nullptr; // unordered per-zone output of the shared-memory paths, kept across products (grow-only)
     uint64_t staging_cap = 0;
+    cudaMemPool_t pool = nullptr; // private stream-ordered pool: freed blocks stay cached, the device's default pool is untouched
+    // multi-device context (pk_ctx_create_multi): one sub-context + one worker thread per device; the master owns the
+    // pinned result buffers and no device state of its own
+    std::vector<pk_ctx *> subs;
+    struct pk_multi_state *multi = nullptr;
 };
 
 struct pk_dpoly {
@@ -103,6 +112,11 @@ struct pk_dpoly {
     std::vector<uint64_t> egcd;
     uint32_t max_bits = 0;
     bool any_neg = false;
+    std::mutex meta_mutex; // has_meta and the fields above are filled lazily (results of pk_mul_dev): guarded
+    // multi-device polynomial (created through a multi-device context): rep[d] = full replica on device d (nullptr = not
+    // materialised), part[r] = the ordered parts of a partitioned product (part r lives on device r); n = total terms
+    bool is_multi = false;
+    std::vector<pk_dpoly *> rep, part;
 };
 
 
@@ -143,7 +157,7 @@ struct DevBuf { // stream-ordered allocation with scope lifetime
     void *p = nullptr;
     DevBuf(pk_ctx *c, size_t bytes) : ctx(c)
     {
-        if (bytes) CUDA_CHECK(cudaMallocAsync(&p, bytes, c->stream));
+        if (bytes) CUDA_CHECK(cudaMallocFromPoolAsync(&p, bytes, c->pool, c->stream));
     }
     ~DevBuf()
     {
@@ -237,9 +251,9 @@ inline pk_dpoly *new_dpoly(pk_ctx *ctx, u64 n, u32 n_vars, u32 limbs)
     p->alloc_limbs = limbs;
     p->stride = ((n + 1) & ~1ull) + 2; // even, with slack for the 16-byte TMA granularity
     DPolyGuard g{ctx, p.release()};
-    CUDA_CHECK(cudaMallocAsync((void **)&g.p->key, (n + 2) * sizeof(int64_t), ctx->stream));
-    CUDA_CHECK(cudaMallocAsync((void **)&g.p->planes, g.p->stride * limbs * sizeof(uint64_t), ctx->stream));
-    CUDA_CHECK(cudaMallocAsync((void **)&g.p->sign, n + 2, ctx->stream));
+    CUDA_CHECK(cudaMallocFromPoolAsync((void **)&g.p->key, (n + 2) * sizeof(int64_t), ctx->pool, ctx->stream));
+    CUDA_CHECK(cudaMallocFromPoolAsync((void **)&g.p->planes, g.p->stride * limbs * sizeof(uint64_t), ctx->pool, ctx->stream));
+    CUDA_CHECK(cudaMallocFromPoolAsync((void **)&g.p->sign, n + 2, ctx->pool, ctx->stream));
     return g.release();
 }
 

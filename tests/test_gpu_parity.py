@@ -758,3 +758,96 @@ def test_custom_limits_table(ctx):
             c2.mul(mk({(100, 0, 0): 1}), mk({(1, 0, 0): 1}), 3)
     finally:
         c2.close()
+
+
+# ---------------------------------------------------------------------------------------------- multi-device context
+
+
+def _multi_devices(n):
+    """n sub-contexts: real GPUs when the box has them, else all on GPU 0 (same code path, parts share the device)."""
+    import torch
+
+    have = torch.cuda.device_count()
+    return [i % have for i in range(n)]
+
+
+@pytest.mark.parametrize("n_dev", [1, 2, 3, 8])
+def test_multi_ctx_host_product(ctx, n_dev):
+    """pk_ctx_create_multi + pk_mul: N ordered parts land in ONE host result that equals the single-device product and the
+    oracle, term by term (reduced Pearce 591235, reduced Fateman with cancellation 5786, truncated Fateman)."""
+    m = pb.Context.multi(_multi_devices(n_dev))
+    try:
+        assert m.device_count == n_dev
+        (f, g), nv = po.pearce_operands(8), 5
+        a, b = terms(f, nv, 1), terms(g, nv, 2)
+        out = m.mul(a, b, nv)
+        assert_sorted_unique(out[0])
+        assert len(out[0]) == 591235  # tests/base_series_multiplier.cpp:571-605
+        assert_terms_equal(out, cpu_ref(a, b, nv))
+        st = m.stats()
+        assert st["term_products"] == len(a[0]) * len(b[0]) and st["result_terms"] == 591235
+        # cancellation: (1+x+y+z+t)^10 * ((1-x+y+z+t)^10) has 5786 terms (polynomial_multiplier_01.cpp:218-231)
+        f2, g2 = po.fateman_cancel_operands(10)
+        a2, b2 = terms(f2, 4, 3), terms(g2, 4, 4)
+        out2 = m.mul(a2, b2, 4)
+        assert_terms_equal(out2, ctx.mul(a2, b2, 4))
+        assert_terms_equal(out2, oracle_terms(po.p_mul(f2, g2), 4))
+        # truncation through the partitioned path
+        ff, gg = po.fateman_operands(10)
+        a3, b3 = terms(ff, 4, 5), terms(gg, 4, 6)
+        out3 = m.mul(a3, b3, 4, trunc_mode=1, max_degree=12)
+        assert_terms_equal(out3, cpu_ref(a3, b3, 4, trunc_mode=1, max_degree=12))
+        # empty operand: empty product
+        empty = (np.zeros(0, np.int64), np.zeros((0, 1), np.uint64), np.zeros(0, np.int8))
+        assert len(m.mul(empty, a3, 4)[0]) == 0
+    finally:
+        m.close()
+
+
+def test_multi_ctx_device_resident_chain(ctx):
+    """Products of a multi-device context stay partitioned in HBM and are replicated peer-to-peer when they become
+    operands: f *= tmp nine times (benchmarks/fateman1.hpp:46-48), then a square, against the closed forms."""
+    m = pb.Context.multi(_multi_devices(3))
+    try:
+        nv = 4
+        base = {(0, 0, 0, 0): 1, (1, 0, 0, 0): 1, (0, 1, 0, 0): 1, (0, 0, 1, 0): 1, (0, 0, 0, 1): 1}
+        tmp = m.upload(terms(base, nv), nv)
+        f = m.upload(terms(base, nv), nv)
+        for _ in range(9):
+            f = m.mul_dev(f, tmp)
+        ref, _ = po.fateman_operands(10)
+        assert len(f) == len(ref)
+        assert_terms_equal(f.download(), oracle_terms(ref, nv))
+        sq = m.mul_dev(f, f)
+        want = oracle_terms(po.p_pow_multinomial(po._linear(4, [1, 1, 1, 1]), 20), nv)
+        got = sq.download()
+        assert_sorted_unique(got[0])
+        assert_terms_equal(got, want)
+        assert sq.digest() == pb.digest_terms(*want)
+        # the same product on the single-device context has the same digest
+        sf = ctx.upload(oracle_terms(ref, nv), nv)
+        assert ctx.mul_dev(sf, sf).digest() == sq.digest()
+    finally:
+        m.close()
+
+
+def test_multi_ctx_argument_errors(ctx):
+    m = pb.Context.multi(_multi_devices(2))
+    try:
+        (f, g), nv = po.pearce_operands(4), 5
+        a, b = terms(f, nv, 1), terms(g, nv, 2)
+        with pytest.raises(ValueError):
+            m.mul(a, b, nv, part_index=0, part_count=2)  # the context partitions the product itself
+        da_single = ctx.upload(a, nv)
+        da_multi, db_multi = m.upload(a, nv), m.upload(b, nv)
+        with pytest.raises(ValueError):
+            m.mul_dev(da_single, db_multi)  # polynomials belong to the context that created them
+        with pytest.raises(ValueError):
+            ctx.mul_dev(da_multi, da_single)
+        with pytest.raises(OverflowError):  # check_bounds through the multi-device handle (polynomial_multiplier_01.cpp:120-174)
+            lim, _, _ = m.limits(1)
+            big = terms({(int(lim[0]),): 1}, 1)
+            m.mul(big, terms({(1,): 1}, 1), 1)
+        assert_terms_equal(m.mul_dev(da_multi, db_multi).download(), ctx.mul(a, b, nv))
+    finally:
+        m.close()
