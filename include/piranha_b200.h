@@ -139,6 +139,11 @@ int pk_ctx_create(int device, void *stream, pk_ctx **out);
  * except the single-device exports (pk_dpoly_export*, pk_dpoly_publish_size, pk_dpoly_export_peers) and pk_opts.part_count
  * > 1, which return PK_E_ARGS; polynomials belong to the context that created them. */
 int pk_ctx_create_multi(uint32_t n_devices, const int *device_ids, pk_ctx **out);
+/* Number of usable (sm_100) CUDA devices on this box; 0 when there is none (no context can be created then). */
+int pk_device_count(void);
+/* Block until everything the context has queued on its stream(s) has finished (cudaStreamSynchronize).  A caller that
+ * mixes its own streams with a context on a private stream orders the two with this. */
+int pk_ctx_synchronize(pk_ctx *ctx);
 /* Number of devices behind the handle (1 for pk_ctx_create). */
 uint32_t pk_ctx_device_count(const pk_ctx *ctx);
 void pk_ctx_destroy(pk_ctx *ctx);

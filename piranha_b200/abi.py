@@ -20,7 +20,7 @@ PK_ALGO_AUTO, PK_ALGO_DENSE, PK_ALGO_HASH, PK_ALGO_ZONE, PK_ALGO_BLOCK = range(5
 ALGO_NAMES = {0: "auto", 1: "dense", 2: "hash", 3: "zone", 4: "block"}
 
 EXPORTED_SYMBOLS = [
-    "pk_ctx_create", "pk_ctx_create_multi", "pk_ctx_device_count", "pk_ctx_destroy", "pk_ctx_trim", "pk_last_error", "pk_ctx_set_limits", "pk_ctx_get_limits", "pk_get_stats", "pk_ctx_set_tuning",
+    "pk_ctx_create", "pk_ctx_create_multi", "pk_ctx_device_count", "pk_device_count", "pk_ctx_synchronize", "pk_ctx_destroy", "pk_ctx_trim", "pk_last_error", "pk_ctx_set_limits", "pk_ctx_get_limits", "pk_get_stats", "pk_ctx_set_tuning",
     "pk_mul", "pk_result_free", "pk_upload", "pk_mul_dev", "pk_check_bounds", "pk_download", "pk_dpoly_free", "pk_dpoly_size",
     "pk_dpoly_limbs", "pk_dpoly_nvars", "pk_dpoly_export", "pk_dpoly_export_padded", "pk_dpoly_digest",
     "pk_dpoly_publish_size", "pk_dpoly_export_peers",
@@ -86,6 +86,8 @@ def load_library():
     vp, u32, u64, i64 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int64
     lib.pk_ctx_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
     lib.pk_ctx_create_multi.argtypes = [u32, C.POINTER(C.c_int), C.POINTER(vp)]
+    lib.pk_device_count.argtypes = []
+    lib.pk_ctx_synchronize.argtypes = [vp]
     lib.pk_ctx_device_count.argtypes = [vp]
     lib.pk_ctx_device_count.restype = u32
     lib.pk_ctx_destroy.argtypes = [vp]
@@ -220,6 +222,11 @@ class Context:
         if rc != PK_OK:
             raise PkError(rc, "pk_ctx_create failed: no usable sm_100 GPU (there is no CPU fallback)")
         self.handle = h
+        self.stream = int(stream) if (stream and devices is None) else None  # None: streams private to the context
+
+    def synchronize(self):
+        """Wait for everything queued on the context's stream(s)."""
+        self._check(self.lib.pk_ctx_synchronize(self.handle))
 
     @classmethod
     def multi(cls, devices: Sequence[int]) -> "Context":

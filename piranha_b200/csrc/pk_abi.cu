@@ -668,6 +668,32 @@ int pk_ctx_create_multi(uint32_t n_devices, const int *device_ids, pk_ctx **out)
     return PK_OK;
 }
 
+int pk_device_count(void)
+{
+    int count = 0, usable = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    for (int d = 0; d < count; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major >= 10) ++usable;
+    }
+    return usable;
+}
+
+int pk_ctx_synchronize(pk_ctx *ctx)
+{
+    if (!ctx) return PK_E_ARGS;
+    PK_TRY(ctx, {
+        if (!ctx->subs.empty()) {
+            for (pk_ctx *sub : ctx->subs) CUDA_CHECK(cudaStreamSynchronize(sub->stream));
+        } else {
+            CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        }
+    })
+}
+
 uint32_t pk_ctx_device_count(const pk_ctx *ctx) { return ctx ? (ctx->subs.empty() ? 1u : (uint32_t)ctx->subs.size()) : 0u; }
 
 void pk_ctx_destroy(pk_ctx *ctx)

@@ -111,6 +111,20 @@ def gather_terms(key: torch.Tensor, mag: torch.Tensor, sign: torch.Tensor, count
     return gather_segments(send, recv, counts, limbs, workspace, group)
 
 
+def _order_ctx_before_torch(ctx):
+    """Work queued on the context's stream must be complete before torch-side work (symmetric-memory barrier, NCCL
+    collective, tensor views) that depends on it.  Nothing to do when the context was created on torch's current
+    stream; a context on a private stream is synchronised."""
+    if ctx.stream is None or ctx.stream != torch.cuda.current_stream().cuda_stream:
+        ctx.synchronize()
+
+
+def _order_torch_before_ctx(ctx):
+    """The reverse: torch-side work (the barrier) must be complete before the context's next kernel."""
+    if ctx.stream is None or ctx.stream != torch.cuda.current_stream().cuda_stream:
+        torch.cuda.current_stream().synchronize()
+
+
 def export_local(dpoly, device) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Copy a device polynomial into torch tensors on the same GPU (device-to-device, no host round trip)."""
     n, limbs = len(dpoly), max(1, dpoly.limbs)
@@ -171,10 +185,13 @@ class PeerExchange:
             par = self.parity
             self.parity ^= 1
             part.publish_size(self._slots(par))
+            _order_ctx_before_torch(part.ctx)  # the size stores precede the barrier
             self.hdl.barrier()
+            _order_torch_before_ctx(part.ctx)  # the push kernel reads a complete size table
             sizes_ptr = self.base[self.rank] + par * w * 16
             part.export_peers(self.rank, sizes_ptr, [b + self.key_off for b in self.base], [b + self.mag_off for b in self.base],
                               [b + self.sign_off for b in self.base], self.cap, self.cap_limbs)
+            _order_ctx_before_torch(part.ctx)  # the term stores precede the barrier that completes the exchange
             self.hdl.barrier()
             sizes = self.buf[par * w * 16:(par + 1) * w * 16].view(torch.int64).cpu().view(w, 2)  # the host round trip
             counts = [int(x) for x in sizes[:, 0]]
@@ -227,6 +244,7 @@ def multiply_partitioned(ctx, da, db, device, group=None, gather: bool = True, w
     if counts[rank]:  # this rank's terms go straight into its segment of the exchange buffer
         base = send.data_ptr()
         part.export_to(base, base + mag_off, base + sign_off, mag_limbs=limbs)
+        _order_ctx_before_torch(ctx)  # the segment is complete before NCCL reads it
     mark()
     out = gather_segments(send, recv, counts, limbs, workspace, group)
     mark()

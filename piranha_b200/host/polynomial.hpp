@@ -18,6 +18,7 @@
 #ifndef PB200_POLYNOMIAL_HPP
 #define PB200_POLYNOMIAL_HPP
 
+#include <atomic>
 #include <algorithm>
 #include <cstddef>
 #include <cstdint>
@@ -57,6 +58,20 @@ struct term {
     Key m_key{};
 };
 
+// std::atomic<bool> that copies by value (series are copyable; a copy starts from the source's current state)
+struct copyable_atomic_bool {
+    std::atomic<bool> v;
+    copyable_atomic_bool(bool b = true) : v(b) {}
+    copyable_atomic_bool(const copyable_atomic_bool &o) : v(o.v.load(std::memory_order_acquire)) {}
+    copyable_atomic_bool &operator=(const copyable_atomic_bool &o)
+    {
+        v.store(o.v.load(std::memory_order_acquire), std::memory_order_release);
+        return *this;
+    }
+    bool load(std::memory_order m = std::memory_order_seq_cst) const { return v.load(m); }
+    void store(bool b, std::memory_order m = std::memory_order_seq_cst) { v.store(b, m); }
+};
+
 struct term_hasher {
     template <typename Term>
     std::size_t operator()(const Term &t) const
@@ -65,20 +80,41 @@ struct term_hasher {
     }
 };
 
-// One pk_ctx per host thread: multipliers are built and consumed on one thread, and operator* may be called
-// concurrently from different threads on different operands (base_series_multiplier.hpp:404-408).
+// ONE pk_ctx per process, shared and reference-counted: every device-resident series keeps the context that owns its
+// terms alive (so a static / global polynomial can be destroyed after main() returns), and calls into the context are
+// serialised by its mutex -- operator* may be called concurrently from different threads on shared const operands
+// (base_series_multiplier.hpp:404-408), a pk_ctx is used by one thread at a time.  The context spreads every product over
+// settings::get_n_gpus() devices (pk_ctx_create_multi; environment PB200_DEVICES = "0,1,2,3" or PB200_N_GPUS = 4), the
+// analogue of settings::set_n_threads() sizing the reference's thread pool.
 class gpu
 {
 public:
-    static pk_ctx *context()
-    {
-        thread_local holder h;
-        if (!h.ctx) {
-            const char *dev = std::getenv("PB200_DEVICE");
-            const int rc = pk_ctx_create(dev ? std::atoi(dev) : 0, nullptr, &h.ctx);
-            if (rc != PK_OK) throw std::runtime_error("piranha_b200: no usable sm_100 GPU (pk_ctx_create failed); there is no CPU fallback");
+    struct holder {
+        pk_ctx *ctx = nullptr;
+        std::recursive_mutex mx;
+        unsigned n_gpus = 1;
+        ~holder()
+        {
+            if (ctx) pk_ctx_destroy(ctx);
         }
-        return h.ctx;
+    };
+    using handle = std::shared_ptr<holder>;
+    // the current context (created on first use, re-created when settings::set_n_gpus() changed the device count)
+    static handle shared()
+    {
+        std::lock_guard<std::mutex> lk(slot_mutex());
+        handle &cur = slot();
+        const unsigned want = settings::get_n_gpus();
+        if (cur && cur->n_gpus == want) return cur;
+        auto h = std::make_shared<holder>();
+        std::vector<int> ids = device_list(want);
+        int rc;
+        if (ids.size() == 1) rc = pk_ctx_create(ids[0], nullptr, &h->ctx);
+        else rc = pk_ctx_create_multi(static_cast<std::uint32_t>(ids.size()), ids.data(), &h->ctx);
+        if (rc != PK_OK) throw std::runtime_error("piranha_b200: no usable sm_100 GPU (pk_ctx_create failed); there is no CPU fallback");
+        h->n_gpus = want;
+        cur = h;
+        return cur;
     }
     // status code -> the exception the reference throws (include/piranha_b200.h)
     static void check(pk_ctx *ctx, int rc)
@@ -96,13 +132,41 @@ public:
     }
 
 private:
-    struct holder {
-        pk_ctx *ctx = nullptr;
-        ~holder()
-        {
-            if (ctx) pk_ctx_destroy(ctx);
+    static std::mutex &slot_mutex()
+    {
+        static std::mutex m;
+        return m;
+    }
+    static handle &slot()
+    {
+        static handle h;
+        return h;
+    }
+    static std::vector<int> device_list(unsigned want)
+    {
+        std::vector<int> ids;
+        if (const char *list = std::getenv("PB200_DEVICES")) {
+            const char *p = list;
+            while (*p) {
+                char *end = nullptr;
+                const long v = std::strtol(p, &end, 10);
+                if (end == p) break;
+                ids.push_back(static_cast<int>(v));
+                p = (*end == ',') ? end + 1 : end;
+            }
         }
-    };
+        if (ids.empty()) { // devices first, first + 1, ...; more parts than the box has GPUs share the devices round-robin
+            const char *dev = std::getenv("PB200_DEVICE");
+            const int first = dev ? std::atoi(dev) : 0;
+            const int have = std::max(1, pk_device_count());
+            for (unsigned i = 0; i < want; ++i) ids.push_back((first + static_cast<int>(i)) % have);
+        } else {
+            const std::size_t listed = ids.size();
+            for (std::size_t i = listed; i < want; ++i) ids.push_back(ids[i % listed]);
+            ids.resize(std::max<std::size_t>(1, want));
+        }
+        return ids;
+    }
 };
 
 template <typename Cf, typename Key>
@@ -126,7 +190,12 @@ public:
     }
 
     // number of terms; a device-resident product answers without touching the host
-    size_type size() const { return m_host_valid ? m_container.size() : static_cast<size_type>(pk_dpoly_size(m_dev->p)); }
+    size_type size() const
+    {
+        if (m_host_valid.load(std::memory_order_acquire)) return m_container.size();
+        std::lock_guard<std::recursive_mutex> lk(m_lazy.mx);
+        return m_host_valid.load(std::memory_order_relaxed) ? m_container.size() : static_cast<size_type>(pk_dpoly_size(m_dev->p));
+    }
     bool empty() const { return size() == 0; }
     const symbol_fset &get_symbol_set() const { return m_symbol_set; }
     void set_symbol_set(const symbol_fset &s)
@@ -141,8 +210,12 @@ public:
     // ---- device residency: a product stays in HBM until its terms are asked for, and
     // an operand keeps the device copy made for its first product, so chains like f *= tmp (series.hpp:799-805) and pow
     // never re-upload f nor download intermediate results
-    bool is_device_resident() const { return static_cast<bool>(m_dev); }
-    bool is_host_resident() const { return m_host_valid; }
+    bool is_device_resident() const
+    {
+        std::lock_guard<std::recursive_mutex> lk(m_lazy.mx);
+        return static_cast<bool>(m_dev);
+    }
+    bool is_host_resident() const { return m_host_valid.load(std::memory_order_acquire); }
     void materialise() const { (void)host(); }
 
     // series::insert: add to an existing term or create it, drop zeros (series.hpp:2190)
@@ -403,27 +476,39 @@ private:
     }
 
     // ---- host / device state
-    struct device_terms { // owns one pk_dpoly (immutable once created, so copies of the series share it)
+    struct device_terms { // owns one pk_dpoly (immutable once created, so copies of the series share it) and keeps the
+                          // context that created it alive; freed through that context, whichever thread drops the last copy
+        gpu::handle h;
         pk_dpoly *p = nullptr;
         ~device_terms()
         {
-            if (p) {
-                try {
-                    pk_dpoly_free(gpu::context(), p);
-                } catch (...) {
-                }
+            if (p && h) {
+                std::lock_guard<std::recursive_mutex> lk(h->mx);
+                pk_dpoly_free(h->ctx, p);
             }
         }
+    };
+    // The host container and the device copy are two lazily filled caches of the same terms, filled from const member
+    // functions.  The reference allows concurrent const use of a series, so both fills are serialised per series.
+    struct lazy_state {
+        mutable std::recursive_mutex mx;
+        lazy_state() = default;
+        lazy_state(const lazy_state &) {}
+        lazy_state &operator=(const lazy_state &) { return *this; }
     };
     static constexpr bool gpu_type = std::is_same<Cf, integer>::value && std::is_same<Key, kronecker_monomial<std::int64_t>>::value;
     const container_type &host() const
     {
-        if (!m_host_valid) download();
+        if (!m_host_valid.load(std::memory_order_acquire)) {
+            std::lock_guard<std::recursive_mutex> lk(m_lazy.mx);
+            if (!m_host_valid.load(std::memory_order_relaxed)) download();
+        }
         return m_container;
     }
     container_type &host_mut()
     {
-        if (!m_host_valid) download();
+        host();
+        std::lock_guard<std::recursive_mutex> lk(m_lazy.mx);
         m_dev.reset();
         return m_container;
     }
@@ -431,8 +516,10 @@ private:
     // result (polynomial.hpp:1666-1667, :1750-1754, base_series_multiplier.hpp:934)
     void download() const
     {
-        if constexpr (gpu_type) {
-            pk_ctx *ctx = gpu::context();
+        if constexpr (gpu_type) { // (called with m_lazy.mx held)
+            const gpu::handle h = m_dev->h;
+            std::unique_lock<std::recursive_mutex> ctx_lock(h->mx);
+            pk_ctx *ctx = h->ctx;
             pk_result r{};
             gpu::check(ctx, pk_download(ctx, m_dev->p, &r));
             try {
@@ -443,7 +530,7 @@ private:
                         r.n, [&r](std::size_t i) { return term_type(integer::from_limbs(r.sign[i], r.mag + i * r.limbs, r.limbs), Key::from_int(r.key[i])); },
                         [&r](std::size_t i) { return static_cast<std::size_t>(r.key[i]); }, nt);
                     pk_result_free(ctx, &r);
-                    m_host_valid = true;
+                    m_host_valid.store(true, std::memory_order_release);
                     return;
                 }
                 m_container.rehash(std::max<std::size_t>(1, r.n));
@@ -459,7 +546,7 @@ private:
                 throw;
             }
             pk_result_free(ctx, &r);
-            m_host_valid = true;
+            m_host_valid.store(true, std::memory_order_release);
         }
     }
     template <typename, typename>
@@ -467,8 +554,9 @@ private:
 
     symbol_fset m_symbol_set;
     mutable container_type m_container;
-    mutable bool m_host_valid = true;
+    mutable copyable_atomic_bool m_host_valid{true};
     mutable std::shared_ptr<device_terms> m_dev;
+    lazy_state m_lazy;
 };
 
 namespace math
@@ -504,8 +592,9 @@ public:
         m_s2 = &s2;
         if (m_s1->size() < m_s2->size()) std::swap(m_s1, m_s2); // larger series first
         if (m_s1->empty() || m_s2->empty()) return;
-        pk_ctx *ctx = gpu::context();
-        gpu::check(ctx, pk_check_bounds(ctx, device(*m_s1), device(*m_s2)));
+        m_h = gpu::shared();
+        std::lock_guard<std::recursive_mutex> lk(m_h->mx);
+        gpu::check(m_h->ctx, pk_check_bounds(m_h->ctx, device(*m_s1, m_h), device(*m_s2, m_h)));
     }
     series_multiplier(const series_multiplier &) = delete;
     series_multiplier &operator=(const series_multiplier &) = delete;
@@ -550,11 +639,13 @@ public:
         o.degree_mask = mask.data();
         return run(o);
     }
-    // statistics of the last product on this thread's context (benchmarks)
+    // statistics of the last product on the process' context (benchmarks)
     static pk_stats last_stats()
     {
         pk_stats st{};
-        pk_get_stats(gpu::context(), &st);
+        const gpu::handle h = gpu::shared();
+        std::lock_guard<std::recursive_mutex> lk(h->mx);
+        pk_get_stats(h->ctx, &st);
         return st;
     }
 
@@ -567,9 +658,11 @@ private:
     }
     // The series' terms in HBM: uploaded on first use (the role of fill_term_pointers, base_series_multiplier.hpp:89-154:
     // walk the container once, here into the structure-of-arrays form of the C ABI) and kept with the series.
-    static pk_dpoly *device(const series_type &s)
+    static pk_dpoly *device(const series_type &s, const gpu::handle &h)
     {
-        if (s.m_dev) return s.m_dev->p;
+        std::lock_guard<std::recursive_mutex> lazy(s.m_lazy.mx);
+        if (s.m_dev && s.m_dev->h == h) return s.m_dev->p;
+        // (a device copy that belongs to an earlier context -- settings::set_n_gpus() changed -- is read back first)
         const auto &c = s.host();
         const std::size_t n = c.size();
         std::size_t L = 1;
@@ -585,11 +678,12 @@ private:
             sign[i] = static_cast<std::int8_t>(t.m_cf.sign());
             ++i;
         }
-        pk_ctx *ctx = gpu::context();
         const pk_poly hp{n, static_cast<std::uint32_t>(s.get_symbol_set().size()), static_cast<std::uint32_t>(L), key.data(),
                          mag.data(), sign.data()};
         auto dev = std::make_shared<series_type::device_terms>();
-        gpu::check(ctx, pk_upload(ctx, &hp, &dev->p));
+        dev->h = h;
+        std::lock_guard<std::recursive_mutex> lk(h->mx);
+        gpu::check(h->ctx, pk_upload(h->ctx, &hp, &dev->p));
         s.m_dev = std::move(dev);
         return s.m_dev->p;
     }
@@ -598,17 +692,21 @@ private:
         series_type retval;
         retval.set_symbol_set(m_ss); // polynomial.hpp:1651-1652
         if (m_s1->empty() || m_s2->empty()) return retval; // :1654-1656
-        pk_ctx *ctx = gpu::context();
         auto dev = std::make_shared<series_type::device_terms>();
-        gpu::check(ctx, pk_mul_dev(ctx, device(*m_s1), device(*m_s2), &o, &dev->p));
+        dev->h = m_h;
+        {
+            std::lock_guard<std::recursive_mutex> lk(m_h->mx);
+            gpu::check(m_h->ctx, pk_mul_dev(m_h->ctx, device(*m_s1, m_h), device(*m_s2, m_h), &o, &dev->p));
+        }
         // the result stays in HBM; reading its terms (or _container()) downloads it once into the hash_set
         retval.m_dev = std::move(dev);
-        retval.m_host_valid = false;
+        retval.m_host_valid.store(false, std::memory_order_release);
         return retval;
     }
 
     symbol_fset m_ss;
     const series_type *m_s1 = nullptr, *m_s2 = nullptr;
+    gpu::handle m_h;
 };
 
 } // namespace pb200

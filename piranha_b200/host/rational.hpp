@@ -187,8 +187,10 @@ private:
         series_type r;
         r.set_symbol_set(m_ss);
         auto &c = r._container();
-        if (!p.m_host_valid) { // product still in HBM: fill the rational container straight from the downloaded terms
-            pk_ctx *ctx = gpu::context();
+        if (!p.m_host_valid.load(std::memory_order_acquire)) { // product still in HBM: fill the rational container straight from the downloaded terms
+            const gpu::handle h = p.m_dev->h;
+            std::lock_guard<std::recursive_mutex> ctx_lock(h->mx);
+            pk_ctx *ctx = h->ctx;
             pk_result res{};
             gpu::check(ctx, pk_download(ctx, p.m_dev->p, &res));
             try {

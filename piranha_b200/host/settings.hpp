@@ -5,6 +5,7 @@
 #define PB200_SETTINGS_HPP
 
 #include <atomic>
+#include <cstdlib>
 #include <stdexcept>
 #include <thread>
 
@@ -24,7 +25,33 @@ class settings
         return c ? c : 1u;
     }
 
+    static std::atomic<unsigned> &gpus()
+    {
+        static std::atomic<unsigned> v{env_gpus()};
+        return v;
+    }
+    static unsigned env_gpus()
+    {
+        if (const char *list = std::getenv("PB200_DEVICES")) { // "0,1,2,3": as many devices as the list names
+            unsigned n = 1;
+            for (const char *p = list; *p; ++p) n += (*p == ',');
+            return n;
+        }
+        const char *e = std::getenv("PB200_N_GPUS");
+        const int n = e ? std::atoi(e) : 1;
+        return n > 0 ? static_cast<unsigned>(n) : 1u;
+    }
+
 public:
+    // Number of GPUs one product is spread over (pk_ctx_create_multi): the multiplier's own parallelism, the role
+    // set_n_threads plays for the reference's thread pool (settings.hpp:102-128).  Takes effect at the next product.
+    static unsigned get_n_gpus() { return gpus().load(std::memory_order_relaxed); }
+    static void set_n_gpus(unsigned n)
+    {
+        if (n == 0u || n > 16u) throw std::invalid_argument("the number of GPUs must be in [1, 16]");
+        gpus().store(n, std::memory_order_relaxed);
+    }
+    static void reset_n_gpus() { gpus().store(env_gpus(), std::memory_order_relaxed); }
     static unsigned get_n_threads() { return value().load(std::memory_order_relaxed); }
     static void set_n_threads(unsigned n)
     {

@@ -209,6 +209,52 @@ static void threads_test()
     }
 }
 
+static void shared_operands_test()
+{
+    // concurrent const use of the SAME operands from several threads (the reference allows it): the lazy device upload
+    // and the lazy host download of a series are serialised per series, every thread sees the same product
+    pt x{"x"}, y{"y"}, z{"z"};
+    const pt f = (1 + x + y + z).pow(9), g = (1 + x - y + z).pow(9);
+    const pt shared_product = f * g; // device-resident; the threads below read (download) it concurrently
+    std::vector<std::size_t> sizes(6, 0), reads(6, 0);
+    std::vector<std::thread> th;
+    for (int k = 0; k < 6; ++k)
+        th.emplace_back([k, &sizes, &reads, &f, &g, &shared_product]() {
+            sizes[k] = (f * g).size();
+            reads[k] = shared_product._container().size();
+        });
+    for (auto &t : th) t.join();
+    const pt want = plain_product(f, g);
+    for (int k = 0; k < 6; ++k) {
+        CHECK_EQUAL(sizes[k], want.size());
+        CHECK_EQUAL(reads[k], want.size());
+    }
+    CHECK_EQUAL(shared_product, want);
+    // a series created and destroyed on another thread frees its device terms through the context that owns them
+    pt moved;
+    std::thread([&moved, &f]() { moved = f * f; }).join();
+    CHECK_EQUAL(moved.size(), (18u + 1) * (18u + 2) * (18u + 3) / 6);
+}
+
+static void multi_gpu_test()
+{
+    // settings::set_n_gpus(n): one product spread over n devices behind the same operator* (pk_ctx_create_multi); with
+    // fewer physical GPUs the parts share a device (PB200_DEVICES names them), the code path is the same
+    pt x{"x"}, y{"y"}, z{"z"}, t{"t"};
+    const pt f = (1 + x + y + z + t).pow(10), g = (1 - x + y + z + t).pow(10);
+    const pt one = f * g;
+    CHECK_EQUAL(one.size(), 5786u); // polynomial_multiplier_01.cpp:218-231
+    one.materialise();
+    settings::set_n_gpus(3);
+    const pt three = f * g; // operands re-uploaded to the new context
+    CHECK_EQUAL(three.size(), 5786u);
+    CHECK_EQUAL(three, one);
+    const pt chained = three * f; // a partitioned product as an operand: replicated device-to-device
+    settings::reset_n_gpus();
+    CHECK_EQUAL(chained, one * f);
+    CHECK_THROW(settings::set_n_gpus(0), std::invalid_argument);
+}
+
 static void residency_test()
 {
     // a product stays on the device until its terms are read; operands keep the device copy of their first product, so
@@ -338,5 +384,7 @@ int main()
     RUN_TEST(pearce_test);
     RUN_TEST(truncation_test);
     RUN_TEST(threads_test);
+    RUN_TEST(shared_operands_test);
+    RUN_TEST(multi_gpu_test);
     return test_summary();
 }

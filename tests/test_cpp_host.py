@@ -97,7 +97,8 @@ def test_host_integer_and_rational_against_python():
 @pytest.mark.gpu
 def test_reference_multiplier_tests_through_operator_star():
     out = _run("multiplier_test", 900)
-    for t in ("residency_test", "rational_test", "unpacked_test", "bounds_test", "multiplication_test", "pearce_test", "truncation_test", "threads_test"):
+    for t in ("residency_test", "rational_test", "unpacked_test", "bounds_test", "multiplication_test", "pearce_test", "truncation_test", "threads_test",
+              "shared_operands_test", "multi_gpu_test"):
         assert f"[  OK  ] {t}" in out
 
 
