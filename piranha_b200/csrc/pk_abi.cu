@@ -289,6 +289,7 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
     ctx->call_launches = 0;
     memset(&ctx->stats, 0, sizeof(ctx->stats));
     ctx->ev_valid = false;
+    ctx->aux_valid = false;
     // larger series first, base_series_multiplier.hpp:368-372
     pk_dpoly *A = a, *B = b;
     if (A->n < B->n) std::swap(A, B);
@@ -348,12 +349,25 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
                   slbuf->as<u32>(), ctx->d_ctr);
     };
 
-    // ---- output partition [lo, hi) in tight-code space
-    // a partitioned product uses the block geometry only when every part gets many whole blocks (else the rounding
-    // of the cuts would unbalance the parts); a function of the operands and P only, so all ranks agree
+    // ---- strategy
+    // a partitioned product uses the block geometry only when every part gets many whole blocks; a function of the operands
+    // and P only, so all ranks agree
     if (bp.ok && P > 1 && pl.range / bp.S < 256ull * P) bp.ok = false;
+    const unsigned __int128 w_bound = (unsigned __int128)nA * nB;
+    const bool filter = trunc || P > 1;
+    u32 algo = o.algo;
+    pk_dpoly *result = nullptr;
+    if ((algo == PK_ALGO_AUTO && w_bound >= (1u << 16) && bp.ok) || algo == PK_ALGO_BLOCK) {
+        // the block path cuts the output partition itself, on the device, from its per-unit product counts
+        if (bp.ok)
+            result = block_multiply(ctx, pl, bp, A, B, keyA.as<u64>(), keyB.as<u64>(), o.part_index, P, nv, trunc ? degA.as<i64>() : nullptr,
+                                    trunc ? degB.as<i64>() : nullptr, o.max_degree, prepack ? packA.as<uint4>() : nullptr,
+                                    prepack ? packB.as<uint4>() : nullptr);
+        algo = result ? PK_ALGO_BLOCK : PK_ALGO_ZONE; // no block geometry for these operands (or tiny groups): generic zones
+    }
+    // ---- output partition [lo, hi) in tight-code space for the generic paths
     u64 lo = 0, hi = pl.range;
-    if (P > 1) {
+    if (!result && P > 1) {
         // stratified sample of pair sums: 512 x 512 pairs resolve the cuts to ~0.2 % of the work for any P <= 64
         const u32 SA = (u32)std::min<u64>(nA, 512), SB = (u32)std::min<u64>(nB, 512);
         const u64 S = (u64)SA * SB;
@@ -370,39 +384,19 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         cuts[0] = 0;
         cuts[P] = pl.range;
-        // whole blocks per rank when the operands have a block geometry (a function of the operands only, so every
-        // rank rounds the same way and the partitions stay disjoint and exhaustive)
-        if (bp.ok)
-            for (u32 p = 1; p < P; ++p) cuts[p] -= cuts[p] % bp.S;
         for (u32 p = 1; p <= P; ++p) cuts[p] = std::max(cuts[p], cuts[p - 1]);
         lo = cuts[o.part_index];
         hi = cuts[o.part_index + 1];
     }
-    const bool filter = trunc || P > 1;
     const u64 sub_range = hi - lo;
-
-    // ---- strategy
-    const unsigned __int128 w_bound = (unsigned __int128)nA * nB;
-    u32 algo = o.algo;
-    if (algo == PK_ALGO_AUTO) {
-        if (w_bound >= (1u << 16) && bp.ok && sub_range) algo = PK_ALGO_BLOCK;
-        else algo = choose_algo(ctx, pl, nA, nB, sub_range, trunc);
-    }
-    pk_dpoly *result = nullptr;
-    if (algo == PK_ALGO_BLOCK) {
-        if (bp.ok && sub_range)
-            result = block_multiply(ctx, pl, bp, A, B, keyA.as<u64>(), keyB.as<u64>(), lo, hi, nv, trunc ? degA.as<i64>() : nullptr,
-                                    trunc ? degB.as<i64>() : nullptr, o.max_degree, prepack ? packA.as<uint4>() : nullptr,
-                                    prepack ? packB.as<uint4>() : nullptr, P);
-        if (!result) algo = PK_ALGO_ZONE; // no block geometry for these operands (or tiny groups): generic zones
-    }
+    if (!result && algo == PK_ALGO_AUTO) algo = choose_algo(ctx, pl, nA, nB, sub_range, trunc);
     if (trunc && !result) prepare_degree_sorted();
-    if (algo == PK_ALGO_ZONE) {
+    if (!result && algo == PK_ALGO_ZONE) {
         result = zone_multiply(ctx, pl, A, B, keyA.as<u64>(), kB, mB, strideB, trunc ? slbuf->as<u32>() : nullptr, lo, hi,
                                trunc, nv);
         if (!result) algo = PK_ALGO_AUTO_FALLBACK; // zone path declined (configuration outside its envelope)
     }
-    if (algo == PK_ALGO_AUTO_FALLBACK) {
+    if (!result && algo == PK_ALGO_AUTO_FALLBACK) {
         const unsigned __int128 dense_bytes = (unsigned __int128)sub_range * pl.nl * 8;
         algo = (sub_range <= 8 * w_bound && dense_bytes <= ((unsigned __int128)16 << 30)) ? PK_ALGO_DENSE : PK_ALGO_HASH;
     }
@@ -600,6 +594,7 @@ int pk_ctx_create(int device, void *stream, pk_ctx **out)
     }
     ok = ok && cudaEventCreate(&c->ev_begin) == cudaSuccess && cudaEventCreate(&c->ev_mul0) == cudaSuccess
          && cudaEventCreate(&c->ev_mul1) == cudaSuccess && cudaEventCreate(&c->ev_end) == cudaSuccess
+         && cudaEventCreate(&c->ev_aux0) == cudaSuccess && cudaEventCreate(&c->ev_aux1) == cudaSuccess
          && cudaHostAlloc(&c->h_scratch, kScratchBytes, cudaHostAllocPortable) == cudaSuccess
          && cudaMalloc((void **)&c->d_ctr, sizeof(MulCounters)) == cudaSuccess
          && cudaMalloc((void **)&c->d_meta, sizeof(MetaDev)) == cudaSuccess
@@ -718,6 +713,10 @@ void pk_ctx_destroy(pk_ctx *ctx)
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_mul0) cudaEventDestroy(ctx->ev_mul0);
     if (ctx->ev_mul1) cudaEventDestroy(ctx->ev_mul1);
+    if (ctx->ev_aux0) cudaEventDestroy(ctx->ev_aux0);
+    if (ctx->ev_aux1) cudaEventDestroy(ctx->ev_aux1);
+    if (ctx->tiles_buf) cudaFreeAsync(ctx->tiles_buf, ctx->stream);
+    if (ctx->bitmap_buf) cudaFreeAsync(ctx->bitmap_buf, ctx->stream);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->ev_part) cudaEventDestroy(ctx->ev_part);
@@ -755,6 +754,16 @@ int pk_ctx_trim(pk_ctx *ctx)
             delete ctx->staging;
             ctx->staging = nullptr;
             ctx->staging_cap = 0;
+        }
+        if (ctx->tiles_buf) {
+            cudaFreeAsync(ctx->tiles_buf, ctx->stream);
+            ctx->tiles_buf = nullptr;
+            ctx->tiles_cap = 0;
+        }
+        if (ctx->bitmap_buf) {
+            cudaFreeAsync(ctx->bitmap_buf, ctx->stream);
+            ctx->bitmap_buf = nullptr;
+            ctx->bitmap_bytes = 0;
         }
         for (auto &b : ctx->pinned)
             if (!b.in_use && b.ptr) {
@@ -844,6 +853,9 @@ int pk_ctx_set_tuning(pk_ctx *ctx, const char *key, uint64_t value)
     else if (k == "block_permute") ctx->block_tuning.permute = (u32)value;
     else if (k == "block_smem") ctx->block_tuning.smem_limit = (u32)value;
     else if (k == "block_radix0") ctx->block_tuning.radix0_residue = std::min<u32>(32, (u32)value);
+    else if (k == "block_unit_codes") ctx->block_tuning.unit_codes = std::max<u32>(32, (u32)value);
+    else if (k == "block_merge") ctx->block_tuning.merge = (u32)value;
+    else if (k == "block_ctas") ctx->block_tuning.ctas = (u32)value;
     else return PK_E_ARGS;
     return PK_OK;
 }
@@ -859,6 +871,7 @@ int pk_get_stats(pk_ctx *ctx, pk_stats *out)
         float ms = 0.f;
         cudaEventSynchronize(ctx->ev_end); // the last copy of a product may still be running
         if (cudaEventElapsedTime(&ms, ctx->ev_mul0, ctx->ev_mul1) == cudaSuccess) ctx->stats.mul_kernel_ms = ms;
+        if (ctx->aux_valid && cudaEventElapsedTime(&ms, ctx->ev_aux0, ctx->ev_aux1) == cudaSuccess) ctx->stats.mul_kernel_ms += ms;
         if (cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end) == cudaSuccess) ctx->stats.device_ms = ms;
     }
     ctx->stats.total_launches = ctx->total_launches;
@@ -1068,6 +1081,7 @@ void collect_part_stats(pk_ctx *ctx, pk_stats &acc)
     if (ctx->ev_valid) {
         cudaEventSynchronize(ctx->ev_end);
         if (cudaEventElapsedTime(&ms, ctx->ev_mul0, ctx->ev_mul1) == cudaSuccess) acc.mul_kernel_ms += ms;
+        if (ctx->aux_valid && cudaEventElapsedTime(&ms, ctx->ev_aux0, ctx->ev_aux1) == cudaSuccess) acc.mul_kernel_ms += ms;
         if (cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end) == cudaSuccess) acc.device_ms += ms;
     }
     const pk_stats &s = ctx->stats;

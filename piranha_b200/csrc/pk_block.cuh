@@ -6,22 +6,28 @@
 // two operand codes never carries from one digit into the next.  Cut the digits at a split index s:
 //     code = hi * S + lo,   S = tradix_0 * ... * tradix_{s-1},   and   (a + b).hi = a.hi + b.hi,  (a + b).lo = a.lo + b.lo.
 // Terms with equal `hi` are contiguous in the sorted operands (a "group").  Every product of group ga of A with group
-// gb of B lands in output block h = hi(ga) + hi(gb), which owns the S consecutive codes [h*S, (h+1)*S).  So
-//   * a zone = Hz consecutive blocks, accumulated in ONE thread block's shared memory exactly as in pk_zone.cuh
-//     (dense slots, or bitmap + popcount-rank slots for sparse ranges; 32-bit word planes; ATOMS with carry chain);
-//   * the work of a zone is a list of tiles (rows [a0, a0+an) of A) x (group gb of B): no binary search, no cursor,
-//     no range test per product, and every lane of a warp does useful work (wide tiles: lane = term of gb, loop over
-//     the rows; narrow tiles: the an x bn products are flattened over the lanes);
-//   * the tile list is built on the device for the whole product at once: count per block -> exclusive scan ->
-//     scatter (a counting sort by h), together with the exact work of every zone, which orders the zones
-//     heaviest-first (LPT) for the dynamic zone claiming.
-// Tile-level range pruning (this call's output partition [lo, hi), rounded to whole blocks) happens when the list is
-// built: pairs of groups outside the partition never become tiles.
+// gb of B lands in output block h = hi(ga) + hi(gb), which owns the S consecutive codes [h*S, (h+1)*S).
+//
+//   * A ZONE UNIT is Hu consecutive blocks.  The work of a unit is a list of tiles (rows [a0, a0+an) of A) x (a chunk
+//     of group gb of B): no binary search, no cursor, no range test per product.  The rows of a tile may span several
+//     groups of A -- all the groups whose products with gb land in the same unit are consecutive in A -- so tiles stay
+//     large where groups are small.  The tile list is built on the device for the whole product at once: count per
+//     unit -> scan -> scatter (a counting sort by unit).
+//   * The output partition of this call (one of P ordered code ranges, for the ranks / devices of a multi-GPU
+//     product) is cut ON THE DEVICE at the quantiles of the per-unit product counts: a deterministic function of the
+//     operands, so every rank derives the same cuts, and no sampling, sorting or host round trip is needed.
+//   * DENSE ranges (about one product per three codes or more): a zone = one unit, accumulated in ONE thread block's
+//     shared memory with slot = code - zone start (k_block); zones claimed heaviest first; terms go to a staging area
+//     and one gather lays them out in code order.
+//   * SPARSE ranges: k_mark walks the tiles once with the codes only and marks a bitmap per unit (shared memory, then
+//     stored to HBM: range / 8 bytes) and counts the codes that occur.  A scan over the unit counts cuts the range into
+//     zones whose entries fit one pass of shared-memory accumulators AND fixes the final position of every zone's
+//     terms.  k_acc then loads a zone's bitmap back (bulk copy), turns it into a perfect order-preserving hash
+//     (popcount rank), walks the tiles with the coefficients, and emits the terms straight to their final positions:
+//     no staging area, no gather (unless coefficients cancelled to zero, which leaves holes to close).
 #pragma once
 
 #include <chrono>
-
-#include <cub/device/device_scan.cuh>
 
 #include "pk_zone.cuh"
 
@@ -30,20 +36,25 @@ namespace pk
 
 struct TruncDev;
 
-struct BlockArgs {
-    ZoneArgs z;           // operands, accumulator geometry, output staging (shared with the zone path)
-    const uint4 *tiles;   // {a0, b0, an | bn << 10, block index relative to h_base}, grouped by block
-    const u32 *tstart;    // n_h + 1 entries: first tile of every block
-    const u32 *order;     // zones, heaviest first (nullptr = natural order)
-    const u32 *n_active;  // zones with at least one tile (device value)
-    u32 h_base, n_h;      // blocks [h_base, h_base + n_h) belong to this call's partition
-    const u32 *zstart;    // first block of every zone (n_zones + 1 entries, ascending)
-    u32 S;                // codes per block
-    const TruncDev *trunc; // degree truncation (nullptr = none)
-    u32 off_keys;          // MODE 1: byte offset of the hash keys (cap words) in dynamic shared memory
-    u32 hash;              // MODE 1: 1 = try the one-walk hash accumulation first
-    u32 pair_walk;         // one-limb operands: 1 = the accumulating walk takes two products at a time
+// Geometry and counters that only the device knows until the host reads them back.
+struct BlockGeo {
+    u32 zu_lo, zu_hi;   // this call's partition: zone units [zu_lo, zu_hi)
+    u32 n_tiles;        // tiles of the partition (may exceed the buffer: then nothing is written and kGeoTileOverflow is set)
+    u32 n_zones;        // zones of the partition
+    u32 n_active;       // zones with work
+    u32 flags;
+    u32 max_entries;    // most marked codes in one zone unit
+    u32 claim_mark;     // dynamic claim counters
+    u32 claim_acc;
+    u32 pad;
+    u64 products_all;   // pair count of the whole product (before degree tests)
+    u64 products_part;  // pair count of this partition (before degree tests)
+    u64 entries_total;  // marked codes of the partition: the result size unless coefficients cancel
+    u64 zeros;          // marked codes whose coefficient cancelled to zero
 };
+constexpr u32 kGeoDecline = 1u;      // groups too small: the tile list would be as long as the product itself
+constexpr u32 kGeoTileOverflow = 2u; // the tile buffer is too small (the host grows it and repeats)
+
 
 // Degree truncation in the block path (polynomial.hpp:1402-1531 restated per tile).  Records carry the term's degree as
 // an offset from its operand's smallest degree; a pair (i, j) is multiplied iff off_a + off_b <= dlim, where
@@ -114,13 +125,17 @@ __global__ void k_pack_operand_deg(const u64 *__restrict__ key, const u64 *__res
 // code / S for 32-bit codes with magic = floor(2^64 / S) + 1
 __device__ __forceinline__ u32 div_magic(u32 x, u64 magic) { return (u32)__umul64hi((u64)x, magic); }
 
-// Group table of one operand: tab[hi] = {first term, one past the last term}; glist = the hi values that occur.
+
+// Group table of one operand: tab[hi] = {first term, one past the last term}; glist = the hi values that occur (any
+// order); codes = the 32-bit codes alone (what the marking walk loads).
 __global__ void k_block_groups(const uint4 *__restrict__ rec, u32 n, u64 magicS, uint2 *__restrict__ tab,
-                               u32 *__restrict__ glist, u32 *__restrict__ gcount, uint2 *__restrict__ gdeg)
+                               u32 *__restrict__ glist, u32 *__restrict__ gcount, u32 *__restrict__ codes, uint2 *__restrict__ gdeg)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const u32 hi = div_magic(__ldg(&rec[i].x), magicS);
+    const u32 code = __ldg(&rec[i].x);
+    codes[i] = code;
+    const u32 hi = div_magic(code, magicS);
     if (gdeg) { // truncation: {smallest, ~largest} degree offset of the group (both by atomicMin from an all-ones fill)
         const u32 off = __ldg(&rec[i].y) >> 1;
         atomicMin(&gdeg[hi].x, off);
@@ -135,217 +150,257 @@ __global__ void k_block_groups(const uint4 *__restrict__ rec, u32 n, u64 magicS,
     if (hi != next) tab[hi].y = i + 1;
 }
 
-// Bank-conflict-free lanes.  In a 32- or 64-term tile lane j holds term j of a chunk of gb and every lane adds into slot
-// lo_a + lo_b(j), so the bank of an ATOMS is (const + code_b(j)) mod 32: distinct banks for the 32 lanes iff their codes are
-// distinct mod 32.  Terms of a group in code order put 2-3 short rows of the lowest digit on a warp, which overlap by a
-// few banks (measured: 2.4 wavefronts per ATOMS).  The order of the terms INSIDE a group is free (a tile is any set of
-// terms of gb), so every group of B can be re-ordered by (rank within its residue class, residue class): positions
-// 32k .. 32k+31 then hold one term of each class as long as every class has more than k terms.  One warp per group.
-// Measured effect on the pairing kernel: -3 % (fateman1), -2 % (fateman2): the shared-memory atomic unit retires about
-// 11.4 lane-atomics per clock whether or not the lanes conflict (tools/microbench.cu), so the extra wavefronts that ncu
-// counts are not the bound.  Optional (tuning key "block_permute").
-__global__ void __launch_bounds__(256) k_block_permute(const uint4 *__restrict__ rec, const uint2 *__restrict__ hi_limb,
-                                                       const uint2 *__restrict__ tab, const u32 *__restrict__ glist,
-                                                       const u32 *__restrict__ gcount, u32 *__restrict__ rank_tmp,
-                                                       uint4 *__restrict__ out, uint2 *__restrict__ out_hi)
+// first[h] = first term whose hi is >= h, i.e. whose code is >= h * S, for every h in [0, HR]: one binary search per h
+// over the sorted records (the operand is a few 10^4 terms, L1/L2 resident).
+__global__ void k_block_first(const uint4 *__restrict__ rec, u32 n, u32 S, u32 HR, u32 *__restrict__ first)
 {
-    __shared__ u32 s_cnt[8][32];
-    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const u32 G = __ldg(gcount);
-    for (u32 g = blockIdx.x * 8u + warp; g < G; g += gridDim.x * 8u) {
-        const uint2 r = __ldg(&tab[__ldg(&glist[g])]);
-        const u32 s = r.x, n = r.y - r.x;
-        s_cnt[warp][lane] = 0;
-        __syncwarp();
-        for (u32 i = lane; i < n; i += 32u) rank_tmp[s + i] = atomicAdd(&s_cnt[warp][__ldg(&rec[s + i].x) & 31u], 1u);
-        __syncwarp();
-        for (u32 i = lane; i < n; i += 32u) {
-            const u32 c = __ldg(&rec[s + i].x) & 31u, rk = rank_tmp[s + i];
-            u32 pos = 0; // terms before (rk, c) in (rank, class) order
-            for (u32 q = 0; q < 32u; ++q) {
-                const u32 cq = s_cnt[warp][q];
-                pos += min(cq, rk) + ((q < c && cq > rk) ? 1u : 0u);
-            }
-            out[s + pos] = __ldg(&rec[s + i]);
-            if (hi_limb) out_hi[s + pos] = __ldg(&hi_limb[s + i]);
-        }
-        __syncwarp();
+    const u32 h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h > HR) return;
+    const u64 want = (u64)h * S;
+    u32 lo = 0, hi = n;
+    while (lo < hi) {
+        const u32 mid = (lo + hi) >> 1;
+        if ((u64)__ldg(&rec[mid].x) < want) lo = mid + 1;
+        else hi = mid;
     }
+    first[h] = lo;
 }
-
-constexpr u32 kTileCols = 32; // a full tile holds exactly one term of gb per lane
 
 struct TileArgs {
     const u32 *glistA, *glistB;
     const uint2 *tabA, *tabB;
-    u32 GA, GB;
-    u32 h_base, n_h; // partition, in blocks
-    u32 target;      // products per tile
-    u32 wide;        // 1 = use 64-term chunks of gb (two terms per lane)
+    const u32 *firstA;       // first row of A whose hi is >= h
+    const u32 *gcount;       // {GA, GB} (device values)
+    u32 Hu;                  // blocks per zone unit
+    u32 HR;                  // hi values are < HR
+    u32 n_zu;                // zone units of the whole range
+    u32 merge;               // 1 = a tile's rows span every group of A that lands in the unit (untruncated products)
+    u32 target;              // products per tile
+    u32 wide;                // 1 = use 64-term chunks of gb (two terms per lane)
     const uint2 *gdegA, *gdegB; // truncation: degree offset extremes per group (nullptr = untruncated)
     const TruncDev *trunc;
-    u32 *cnt;        // tiles per block (count pass) / cursor per block (scatter pass)
-    const u32 *tstart;
+    u32 *cnt;                // PASS 0: tiles per unit; PASS 1: cursor per unit of the partition
+    u64 *prod;               // PASS 0: products per unit
+    const u32 *tstart;       // PASS 1: first tile of every unit of the partition
     uint4 *tiles;
-    u32 max_tiles;
-    MulCounters *ctr;
+    u32 tiles_cap;
+    BlockGeo *geo;
 };
 
-// One thread per pair of groups (ga, gb).  PASS 0: count the tiles of block h = hi(ga) + hi(gb) and add the pair's
-// products to its zone.  PASS 1: write the tiles at the block's scanned offset.
-// Tile shapes: gb is cut into chunks of exactly 32 terms (FULL tiles: lane = term of gb, held in registers over the
-// rows of the tile) plus one ragged chunk of nb mod 32 terms (FLAT tiles: rows x terms flattened over the lanes); rows
-// are cut so that a tile has about `target` products.
+constexpr u32 kTileCols = 32; // a full tile holds exactly one term of gb per lane
+
+// One thread per pair of groups (ga, gb), grid-stride (the group counts are device values).  PASS 0: count the tiles and
+// products of the zone unit that block h = hi(ga) + hi(gb) belongs to.  PASS 1: write the tiles of the units of this
+// call's partition at the unit's scanned offset.
+// With `merge`, only the FIRST group of A that lands in the unit with gb makes tiles, and their rows run over all such
+// groups (they are consecutive rows of A: hi(ga) in [unit_first_block - hb, unit_end_block - hb)).
+// Tile shapes: gb is cut into chunks of 64 / exactly 32 terms (FULL tiles: lane = term(s) of gb, held in registers over
+// the rows of the tile) plus one ragged chunk (FLAT tiles: rows x terms flattened over the lanes); rows are cut so that a
+// tile has about `target` products.
 template <int PASS>
 __global__ void k_block_tiles(const TileArgs t)
 {
-    const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= (u64)t.GA * t.GB) return;
-    const u32 ia = (u32)(p / t.GB), ib = (u32)(p - (u64)ia * t.GB);
-    const u32 ha = __ldg(&t.glistA[ia]), hb = __ldg(&t.glistB[ib]);
-    const u32 h = ha + hb;
-    if (h < t.h_base || h - t.h_base >= t.n_h) return; // range pruning at tile level
-    const u32 hr = h - t.h_base;
-    const uint2 ra = __ldg(&t.tabA[ha]), rb = __ldg(&t.tabB[hb]);
-    const u32 na = ra.y - ra.x, nb = rb.y - rb.x;
-    u32 filt = 0; // bit 31 of the tile word: products of the tile need the degree test
-    if (t.trunc) {
-        if (t.trunc->none) return;
-        const uint2 da = __ldg(&t.gdegA[ha]), db = __ldg(&t.gdegB[hb]);
-        const u32 dlim = t.trunc->dlim;
-        if ((u64)da.x + db.x > dlim) return; // degree pruning at tile level: not even the smallest degrees fit
-        if ((u64)(~da.y) + (~db.y) > dlim) filt = 0x80000000u;
+    const u32 GA = __ldg(&t.gcount[0]), GB = __ldg(&t.gcount[1]);
+    const u64 pairs = (u64)GA * GB;
+    u32 zu_lo = 0, zu_hi = t.n_zu;
+    if (PASS == 1) {
+        if (t.geo->flags) return; // declined or no room: nothing is written
+        zu_lo = t.geo->zu_lo;
+        zu_hi = t.geo->zu_hi;
     }
-    // gb = n64 chunks of 64 terms (two per lane) + at most one chunk of 32 (one per lane) + a ragged rest (flat)
-    const u32 n64 = t.wide ? nb / 64u : 0u;
-    const u32 n32 = (nb - n64 * 64u) / kTileCols, rem = nb - n64 * 64u - n32 * kTileCols;
-    const u32 rpt_w = min(1023u, max(1u, t.target / 64u));
-    const u32 rpt_f = min(1023u, max(1u, t.target / kTileCols));
-    const u32 rpt_r = rem ? min(1023u, max(1u, t.target / rem)) : 1u;
-    const u32 nrow_w = (na + rpt_w - 1) / rpt_w, nrow_f = (na + rpt_f - 1) / rpt_f, nrow_r = rem ? (na + rpt_r - 1) / rpt_r : 0u;
-    const u32 nt = n64 * nrow_w + n32 * nrow_f + nrow_r;
-    if (PASS == 0) {
-        atomicAdd(&t.cnt[hr], nt);
-    } else {
-        const u32 pos = __ldg(&t.tstart[hr]) + atomicAdd(&t.cnt[hr], nt);
-        if (pos + nt > t.max_tiles) { // cannot happen: max_tiles is a proven bound
-            atomicOr(&t.ctr->flags, kFlagTableFull);
-            return;
+    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < pairs; p += (u64)gridDim.x * blockDim.x) {
+        const u32 ia = (u32)(p / GB), ib = (u32)(p - (u64)ia * GB);
+        const u32 ha = __ldg(&t.glistA[ia]), hb = __ldg(&t.glistB[ib]);
+        const u32 h = ha + hb;
+        const u32 zu = h / t.Hu;
+        if (PASS == 1 && (zu < zu_lo || zu >= zu_hi)) continue; // range pruning at tile level
+        const uint2 ra = __ldg(&t.tabA[ha]), rb = __ldg(&t.tabB[hb]);
+        u32 a0 = ra.x, na = ra.y - ra.x;
+        const u32 nb = rb.y - rb.x;
+        u32 filt = 0; // bit 31 of the tile word: products of the tile need the degree test
+        if (t.merge) {
+            const u32 u0 = zu * t.Hu, u1 = u0 + t.Hu; // blocks of the unit
+            const u32 h_first = u0 > hb ? u0 - hb : 0u, h_end = min(t.HR, u1 - hb);
+            const u32 first = __ldg(&t.firstA[h_first]);
+            if (first != ra.x) continue; // another group of A leads this unit's tiles with gb
+            a0 = first;
+            na = __ldg(&t.firstA[h_end]) - first;
+        } else if (t.trunc) {
+            if (t.trunc->none) continue;
+            const uint2 da = __ldg(&t.gdegA[ha]), db = __ldg(&t.gdegB[hb]);
+            const u32 dlim = t.trunc->dlim;
+            if ((u64)da.x + db.x > dlim) continue; // degree pruning at tile level: not even the smallest degrees fit
+            if ((u64)(~da.y) + (~db.y) > dlim) filt = 0x80000000u;
         }
-        u32 k = pos, c0 = rb.x;
-        for (u32 c = 0; c < n64; ++c, c0 += 64u)
-            for (u32 r = 0; r < nrow_w; ++r, ++k)
-                t.tiles[k] = make_uint4(ra.x + r * rpt_w, c0, min(rpt_w, na - r * rpt_w) | (64u << 10) | filt, hr);
-        for (u32 c = 0; c < n32; ++c, c0 += kTileCols)
-            for (u32 r = 0; r < nrow_f; ++r, ++k)
-                t.tiles[k] = make_uint4(ra.x + r * rpt_f, c0, min(rpt_f, na - r * rpt_f) | (kTileCols << 10) | filt, hr);
-        for (u32 r = 0; r < nrow_r; ++r, ++k)
-            t.tiles[k] = make_uint4(ra.x + r * rpt_r, c0, min(rpt_r, na - r * rpt_r) | (rem << 10) | filt, hr);
+        // gb = n64 chunks of 64 terms (two per lane) + at most one chunk of 32 (one per lane) + a ragged rest (flat)
+        const u32 n64 = t.wide ? nb / 64u : 0u;
+        const u32 n32 = (nb - n64 * 64u) / kTileCols, rem = nb - n64 * 64u - n32 * kTileCols;
+        const u32 rpt_w = min(1023u, max(1u, t.target / 64u));
+        const u32 rpt_f = min(1023u, max(1u, t.target / kTileCols));
+        const u32 rpt_r = rem ? min(1023u, max(1u, t.target / rem)) : 1u;
+        const u32 nrow_w = (na + rpt_w - 1) / rpt_w, nrow_f = (na + rpt_f - 1) / rpt_f, nrow_r = rem ? (na + rpt_r - 1) / rpt_r : 0u;
+        const u32 nt = n64 * nrow_w + n32 * nrow_f + nrow_r;
+        if (PASS == 0) {
+            atomicAdd(&t.cnt[zu], nt);
+            atomicAdd(&t.prod[zu], (u64)na * nb);
+        } else {
+            const u32 zr = zu - zu_lo;
+            const u32 pos = __ldg(&t.tstart[zr]) + atomicAdd(&t.cnt[zr], nt);
+            if (pos + nt > t.tiles_cap) { // cannot happen: the plan kernel checked the total
+                atomicOr(&t.geo->flags, kGeoTileOverflow);
+                continue;
+            }
+            u32 k = pos, c0 = rb.x;
+            for (u32 c = 0; c < n64; ++c, c0 += 64u)
+                for (u32 r = 0; r < nrow_w; ++r, ++k)
+                    t.tiles[k] = make_uint4(a0 + r * rpt_w, c0, min(rpt_w, na - r * rpt_w) | (64u << 10) | filt, zr);
+            for (u32 c = 0; c < n32; ++c, c0 += kTileCols)
+                for (u32 r = 0; r < nrow_f; ++r, ++k)
+                    t.tiles[k] = make_uint4(a0 + r * rpt_f, c0, min(rpt_f, na - r * rpt_f) | (kTileCols << 10) | filt, zr);
+            for (u32 r = 0; r < nrow_r; ++r, ++k)
+                t.tiles[k] = make_uint4(a0 + r * rpt_r, c0, min(rpt_r, na - r * rpt_r) | (rem << 10) | filt, zr);
+        }
     }
 }
 
-// Zones of Hz consecutive blocks each (dense zones: the slots of Hz blocks are what shared memory holds).
-__global__ void k_block_uniform_zones(u32 n_h, u32 Hz, u32 nz, u32 *__restrict__ zstart, u32 *__restrict__ n_zones)
+// ---- single-block scans (1024 threads) over arrays of a few 10^4 .. 10^6 entries ----------------------------------
+
+__device__ __forceinline__ u64 warp_incl_scan64(u64 v)
 {
-    const u32 z = blockIdx.x * blockDim.x + threadIdx.x;
-    if (z <= nz) zstart[z] = min(n_h, z * Hz);
-    if (z == 0) *n_zones = nz;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u64 t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane_id() >= (u32)o) v += t;
+    }
+    return v;
 }
 
-// Zones of about equal work (bitmap zones): the blocks are cut at the quantiles of the tile count (nq of them), and a
-// quantile longer than span_max blocks (the bitmap of a zone covers span_max blocks) is cut into equal pieces.  Where
-// blocks are heavy a zone is a few blocks, in the sparse tail it is span_max blocks -- every zone costs a thread block
-// about the same time, whatever part of the code range (or which output partition) it comes from.  One block.
-__global__ void __launch_bounds__(1024) k_block_equal_zones(const u32 *__restrict__ tstart, u32 n_h, u32 span_max, u32 nq,
-                                                            u32 max_zones, u32 *__restrict__ zstart, u32 *__restrict__ n_zones)
+// exclusive scan of one u64 per thread over the block; returns the block total in `total`.  ws: >= 33 u64 of smem.
+__device__ __forceinline__ u64 block_excl_scan64(u64 v, u64 *ws, u64 &total)
 {
-    __shared__ u32 s_ws[40];
-    __shared__ u32 s_run;
-    const u32 total = tstart[n_h];
-    const u32 per = max(1u, (total + nq - 1) / nq);
-    auto bound = [&](u32 q) -> u32 { // first block whose tiles start at or after tile q * per
-        if (q == 0) return 0u;
-        if (q >= nq) return n_h;
-        const u64 want = (u64)q * per;
-        u32 lo = 0, hi = n_h;
-        while (lo < hi) {
-            const u32 mid = (lo + hi) >> 1;
-            if (tstart[mid] < want) lo = mid + 1;
-            else hi = mid;
-        }
-        return lo;
-    };
-    if (threadIdx.x == 0) s_run = 0;
+    const u64 incl = warp_incl_scan64(v);
+    const u32 w = threadIdx.x >> 5;
+    if (lane_id() == 31) ws[w] = incl;
     __syncthreads();
-    for (u32 base = 0; base < nq; base += blockDim.x) {
-        const u32 q = base + threadIdx.x;
-        u32 b0 = 0, len = 0, pieces = 0;
-        if (q < nq) {
-            b0 = bound(q);
-            len = bound(q + 1) - b0;
-            pieces = (len + span_max - 1) / span_max;
-        }
-        u32 tot;
-        const u32 excl = block_excl_scan(pieces, s_ws, tot);
-        const u32 run = s_run;
-        if (pieces) {
-            const u32 step = (len + pieces - 1) / pieces;
-            for (u32 j = 0; j < pieces; ++j)
-                if (run + excl + j < max_zones) zstart[run + excl + j] = b0 + j * step;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) s_run = run + tot;
-        __syncthreads();
+    if (w == 0) {
+        const u32 nw = (blockDim.x + 31) >> 5;
+        const u64 s = lane_id() < nw ? ws[lane_id()] : 0;
+        const u64 si = warp_incl_scan64(s);
+        ws[lane_id()] = si - s;
+        if (lane_id() == 31) ws[32] = si;
     }
-    if (threadIdx.x == 0) {
-        const u32 nz = min(s_run, max_zones); // (max_zones is a proven bound: nq + n_h / span_max + 1)
-        zstart[nz] = n_h;
-        *n_zones = nz;
-    }
+    __syncthreads();
+    total = ws[32];
+    const u64 r = ws[w] + incl - v;
+    __syncthreads();
+    return r;
 }
 
-// Zone order for the dynamic claiming: heaviest first (LPT), by a counting sort over 256 logarithmic work classes.
-// One block.  Zones without work sort last and are never claimed (n_active).
-// uniform_hz != 0: the zones are uniform_nz zones of uniform_hz blocks each and this kernel writes zstart / n_zones itself
-// (saves the launch of k_block_uniform_zones).
-__global__ void __launch_bounds__(1024) k_block_order(const u32 *__restrict__ tstart, u32 *__restrict__ zstart,
-                                                      u32 *__restrict__ n_zones, u32 *__restrict__ order,
-                                                      u32 *__restrict__ n_active, u32 n_h, u32 uniform_hz, u32 uniform_nz)
-{
-    if (uniform_hz) {
-        for (u32 z = threadIdx.x; z <= uniform_nz; z += blockDim.x) zstart[z] = min(n_h, z * uniform_hz);
-        if (threadIdx.x == 0) *n_zones = uniform_nz;
-        __syncthreads();
-    }
-    const u32 nz = *n_zones;
-    // work of a zone = its number of tiles (every tile holds about the same number of products)
-    auto zwork_of = [&](u32 z) -> u64 { return (u64)(tstart[zstart[z + 1]] - tstart[zstart[z]]); };
-    __shared__ u32 s_hist[256], s_start[256];
-    for (u32 i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
-    __syncthreads();
-    auto cls = [](u64 w) -> u32 {
-        if (w == 0) return 0u;
-        const u32 e = 63u - (u32)__clzll((long long)w);
-        const u32 m = e >= 2 ? (u32)(w >> (e - 2)) & 3u : 0u;
-        return min(255u, 4u * e + m + 1u);
-    };
-    for (u32 z = threadIdx.x; z < nz; z += blockDim.x) atomicAdd(&s_hist[cls(zwork_of(z))], 1u);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        u32 run = 0;
-        for (int c = 255; c >= 0; --c) {
-            s_start[c] = run;
-            run += s_hist[c];
-        }
-        *n_active = nz - s_hist[0];
-    }
-    __syncthreads();
-    for (u32 z = threadIdx.x; z < nz; z += blockDim.x) order[atomicAdd(&s_start[cls(zwork_of(z))], 1u)] = z;
-}
+struct PlanArgs {
+    const u32 *cnt;    // tiles per zone unit (whole range)
+    const u64 *prod;   // products per zone unit (whole range)
+    u32 n_zu;
+    u32 parts, part;   // this call computes part `part` of `parts`
+    u32 *tstart;       // out: first tile of every unit of the partition (+ one past the last)
+    u64 *pprefix;      // out: exclusive prefix of the products over the units of the partition (+ total)
+    u32 tiles_cap;
+    const u32 *gcount; // {GA, GB}
+    u64 W;             // nA * nB
+    u32 min_tile;
+    BlockGeo *geo;
+};
 
-__global__ void k_block_natural_order(const u32 *__restrict__ n_zones, u32 *__restrict__ n_active)
+// The plan of one call, decided on the device (one block): the output partition [zu_lo, zu_hi) -- cut at the quantiles
+// part / parts and (part + 1) / parts of the per-unit product counts, so every rank of a partitioned product derives
+// the same cuts and every product is done by exactly one rank --, the exclusive scan of the tile counts over the
+// partition, and the checks that make the host repeat or decline (tile buffer too small, groups too small).
+// The arrays are walked in chunks of 4096 units, four consecutive units per thread (coalesced), one block scan per chunk.
+__global__ void __launch_bounds__(1024) k_block_plan(const PlanArgs a)
 {
-    *n_active = *n_zones;
+    __shared__ u64 s_ws[40];
+    __shared__ u32 s_cut[2];
+    const u32 tid = threadIdx.x;
+    if (tid == 0) {
+        s_cut[0] = 0;
+        s_cut[1] = a.n_zu;
+    }
+    // products of the whole range
+    u64 local = 0;
+    for (u32 i = tid; i < a.n_zu; i += 1024u) local += a.prod[i];
+    u64 W_all;
+    block_excl_scan64(local, s_ws, W_all);
+    if (a.parts > 1) {
+        // boundary p = the unit whose product interval [exclusive prefix, inclusive prefix) holds floor(W_all * p / parts)
+        const u64 T0 = (u64)(((unsigned __int128)W_all * a.part) / a.parts);
+        const u64 T1 = (u64)(((unsigned __int128)W_all * (a.part + 1)) / a.parts);
+        u64 run = 0;
+        for (u32 base = 0; base < a.n_zu; base += 4096u) {
+            const u32 i = base + tid * 4u;
+            u64 v[4], sum = 0;
+#pragma unroll
+            for (u32 k = 0; k < 4; ++k) {
+                v[k] = (i + k < a.n_zu) ? a.prod[i + k] : 0ull;
+                sum += v[k];
+            }
+            u64 total;
+            u64 ex = run + block_excl_scan64(sum, s_ws, total);
+#pragma unroll
+            for (u32 k = 0; k < 4; ++k) {
+                if (v[k]) {
+                    if (a.part > 0 && ex <= T0 && T0 < ex + v[k]) s_cut[0] = i + k;
+                    if (a.part + 1 < a.parts && ex <= T1 && T1 < ex + v[k]) s_cut[1] = i + k;
+                }
+                ex += v[k];
+            }
+            run += total;
+        }
+    }
+    __syncthreads();
+    const u32 zu_lo = s_cut[0], zu_hi = max(s_cut[0], s_cut[1]);
+    // tiles and products of the partition: exclusive scans
+    const u32 n = zu_hi - zu_lo;
+    u64 crun = 0, prun = 0;
+    for (u32 base = 0; base < n; base += 4096u) {
+        const u32 j = base + tid * 4u;
+        u64 c[4], v[4], csum = 0, vsum = 0;
+#pragma unroll
+        for (u32 k = 0; k < 4; ++k) {
+            c[k] = (j + k < n) ? (u64)a.cnt[zu_lo + j + k] : 0ull;
+            v[k] = (j + k < n) ? a.prod[zu_lo + j + k] : 0ull;
+            csum += c[k];
+            vsum += v[k];
+        }
+        u64 ctot, vtot;
+        u64 cex = crun + block_excl_scan64(csum, s_ws, ctot);
+        u64 vex = prun + block_excl_scan64(vsum, s_ws, vtot);
+#pragma unroll
+        for (u32 k = 0; k < 4; ++k) {
+            if (j + k < n) {
+                a.tstart[j + k] = (u32)min(cex, (u64)0xFFFFFFFFull);
+                a.pprefix[j + k] = vex;
+            }
+            cex += c[k];
+            vex += v[k];
+        }
+        crun += ctot;
+        prun += vtot;
+    }
+    if (tid == 0) {
+        const bool fits = crun <= (u64)a.tiles_cap && crun <= 0x7FFFFFFFull;
+        a.tstart[n] = (u32)min(crun, (u64)0xFFFFFFFFull);
+        a.pprefix[n] = prun;
+        BlockGeo &g = *a.geo;
+        g.zu_lo = zu_lo;
+        g.zu_hi = zu_hi;
+        g.n_tiles = (u32)min(crun, (u64)0xFFFFFFFFull);
+        g.products_all = W_all;
+        g.products_part = prun;
+        const u64 pairs = (u64)a.gcount[0] * a.gcount[1];
+        u32 flags = 0;
+        if ((unsigned __int128)pairs * a.min_tile > (unsigned __int128)a.W || pairs >= (1ull << 31)) flags |= kGeoDecline;
+        if (!fits) flags |= kGeoTileOverflow;
+        g.flags = flags;
+    }
 }
 
 // LOAD 0: the code only (bitmap marking), 1: code + sign/degree word (marking with the degree test), 2: whole record
@@ -570,273 +625,422 @@ __device__ __forceinline__ void block_accumulate(u32 saddr0, u32 wstride, const 
     }
 }
 
-// Open-addressing insert into the zone's shared-memory key table (linear probing; key = slot + 1, 0 = empty).  Returns the
-// table index of the slot's accumulator, or 0xFFFFFFFF when the probe limit is hit (the zone then falls back to the
-// two-walk bitmap scheme, which handles any number of entries in passes).
-constexpr u32 kHashProbeLimit = 32;
-__device__ __forceinline__ u32 block_hash_slot(u32 keys_s, u32 cap, u32 slot)
+// Walk the tiles [t0, t1) with the warps of a block: a warp claims `TB` consecutive tiles with ONE shared-memory atomic
+// (lanes 0..TB-1 load one descriptor each, a shuffle hands them round), so the claim and the descriptors' L2 latency are
+// paid once per TB tiles.  *s_next must hold t0 before the block-wide barrier that precedes the walk.
+template <int TB, typename F>
+__device__ __forceinline__ void block_walk_tiles(const uint4 *__restrict__ tiles, u32 s_next_addr, u32 tend, u32 lane, F &&body)
 {
-    const u32 key = slot + 1u;
-    u32 h = __umulhi(slot * 0x9E3779B1u, cap);
-    for (u32 probes = 0; probes < kHashProbeLimit; ++probes) {
-        u32 cur;
-        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(cur) : "r"(keys_s + h * 4u) : "memory");
-        if (cur == key) return h;
-        if (cur == 0u) {
-            u32 old;
-            asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(keys_s + h * 4u), "r"(0u), "r"(key) : "memory");
-            if (old == 0u || old == key) return h;
-        }
-        if (++h == cap) h = 0;
-    }
-    return 0xFFFFFFFFu;
-}
-
-// Dynamic tile claiming for one walk over the tiles [*, tend) of a zone: a warp claims its next tile (shared-memory
-// counter) and loads that tile's record BEFORE it processes the current one, so the claim and the record's L2 latency
-// hide behind useful work.  The counter must have been set to the first tile before the block-wide barrier.
-template <typename F>
-__device__ __forceinline__ void block_for_each_tile(const uint4 *__restrict__ tiles, u32 *s_next, u32 tend, u32 lane, F &&body)
-{
-    u32 k = 0;
-    if (lane == 0) k = atomicAdd(s_next, 1u);
-    k = __shfl_sync(0xffffffffu, k, 0);
-    if (k >= tend) return;
-    uint4 t = __ldg(&tiles[k]);
     for (;;) {
-        u32 kn = 0;
-        if (lane == 0) kn = atomicAdd(s_next, 1u);
-        kn = __shfl_sync(0xffffffffu, kn, 0);
-        uint4 tn = make_uint4(0u, 0u, 0u, 0u);
-        if (kn < tend) tn = __ldg(&tiles[kn]);
-        body(t);
-        if (kn >= tend) return;
-        t = tn;
+        u32 k0 = 0;
+        if (lane == 0) k0 = atoms_add(s_next_addr, (u32)TB);
+        k0 = __shfl_sync(0xffffffffu, k0, 0);
+        if (k0 >= tend) return;
+        uint4 mine = make_uint4(0u, 0u, 0u, 0u);
+        if (lane < (u32)TB && k0 + lane < tend) mine = __ldg(&tiles[k0 + lane]);
+#pragma unroll
+        for (int j = 0; j < TB; ++j) {
+            uint4 t;
+            t.x = __shfl_sync(0xffffffffu, mine.x, j);
+            t.y = __shfl_sync(0xffffffffu, mine.y, j);
+            t.z = __shfl_sync(0xffffffffu, mine.z, j);
+            t.w = __shfl_sync(0xffffffffu, mine.w, j);
+            if (k0 + (u32)j < tend) body(t);
+        }
     }
 }
 
-// MODE 0: dense zones (slot = code - zlo; the plan guarantees Hz * S <= cap, so one pass).
-// MODE 1: bitmap zones (slot = rank of the code among the codes that occur; passes of at most cap entries).  The
-//         bitmap is an array of {bits, rank of the word's first bit} pairs, so a rank is one 8-byte shared load, one
-//         mask and one popcount.
-template <int NW, int PW, int MODE, bool SIGNED, int LW>
-__global__ void __launch_bounds__(1024, 1) k_block(const BlockArgs ba)
+// Visit the products of one tile with the 32-bit codes only: f(code_a, code_b).
+template <typename F>
+__device__ __forceinline__ void block_tile_codes(const u32 *__restrict__ A, const u32 *__restrict__ B, const uint4 t, u32 lane, F &&f)
 {
-    constexpr u32 kThreads = 1024;
-    const ZoneArgs &a = ba.z;
+    const u32 a0 = t.x, b0 = t.y, an = t.z & 1023u, bn = (t.z >> 10) & 127u;
+    if (bn == 64u) {
+        const u32 b0v = __ldg(&B[b0 + lane]), b1v = __ldg(&B[b0 + 32u + lane]);
+        for (u32 i = 0; i < an; ++i) {
+            const u32 av = __ldg(&A[a0 + i]);
+            f(av, b0v);
+            f(av, b1v);
+        }
+    } else if (bn == kTileCols) {
+        const u32 bv = __ldg(&B[b0 + lane]);
+        for (u32 i = 0; i < an; ++i) f(__ldg(&A[a0 + i]), bv);
+    } else {
+        const u32 total = an * bn;
+        const float rbn = __frcp_rn((float)bn);
+        const u32 q = (u32)(32.5f * rbn), r = 32u - q * bn;
+        u32 i = (u32)(((float)lane + 0.5f) * rbn), j = lane - i * bn;
+        for (u32 idx = lane; idx < total; idx += 32u) {
+            f(__ldg(&A[a0 + i]), __ldg(&B[b0 + j]));
+            i += q;
+            j += r;
+            if (j >= bn) {
+                j -= bn;
+                ++i;
+            }
+        }
+    }
+}
+
+struct MarkArgs {
+    const uint4 *A, *B;     // packed records (degree-tested tiles read the degree offsets from them)
+    const u32 *codeA, *codeB;
+    const uint4 *tiles;
+    const u32 *tstart;      // per unit of the partition
+    u32 U;                  // codes per zone unit (Hu * S)
+    u32 range;              // number of tight codes of the whole product
+    u32 *gbm;               // out: bitmap of the partition, bit (code - first code of the partition); zeroed by the host
+    u32 *entries;           // out: marked codes per unit
+    const TruncDev *trunc;
+    BlockGeo *geo;
+};
+
+// SPARSE ranges, first walk: mark the codes that occur.  One block of 128 threads per zone unit (claimed dynamically);
+// the unit's bitmap lives in shared memory while the warps walk its tiles with the 32-bit codes alone, then its words go
+// to the partition's bitmap in HBM (the two words a unit shares with its neighbours by atomic OR) and its popcount to
+// entries[].  No accumulators here: several blocks per SM, their barrier phases overlap.
+__global__ void __launch_bounds__(128) k_block_mark(const MarkArgs m)
+{
+    extern __shared__ __align__(16) u32 mbm[];
+    __shared__ u32 s_claim, s_red[4];
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (m.geo->flags) return;
+    const u32 zu_lo = m.geo->zu_lo, n_units = m.geo->zu_hi - zu_lo;
+    const u64 code_lo = (u64)zu_lo * m.U;
+    const u32 dlim = m.trunc ? __ldg(&m.trunc->dlim) : 0xFFFFFFFFu;
+    const u32 bm_s = smem_u32(mbm);
+    u32 my_max = 0;
+    for (;;) {
+        if (tid == 0) s_claim = atomicAdd(&m.geo->claim_mark, 1u);
+        __syncthreads();
+        const u32 zr = s_claim;
+        __syncthreads();
+        if (zr >= n_units) break;
+        const u32 t0 = __ldg(&m.tstart[zr]), t1 = __ldg(&m.tstart[zr + 1]);
+        if (t0 == t1) {
+            if (tid == 0) m.entries[zr] = 0;
+            continue;
+        }
+        const u64 c0 = code_lo + (u64)zr * m.U, c1 = min((u64)m.range, c0 + m.U);
+        const u32 bit0 = (u32)(c0 - code_lo), bit1 = (u32)(c1 - code_lo);
+        const u32 w_first = bit0 >> 5, nwords = ((bit1 + 31u) >> 5) - w_first;
+        const u32 slot_base = (u32)code_lo + w_first * 32u; // slot = code - slot_base
+        for (u32 w = tid; w < nwords; w += 128u) mbm[w] = 0;
+        __syncthreads();
+        for (u32 k = t0 + warp; k < t1; k += 4u) { // (static round robin: no claim traffic; tiles are at most ~512 products)
+            const uint4 t = __ldg(&m.tiles[k]);
+            if (t.z >> 31) { // truncation: some products of this tile exceed the degree limit
+                block_tile_loop<1, 1>(m.A, m.B, nullptr, nullptr, t, lane, [&](const uint4 &av, const uint4 &bv, const uint2 &, const uint2 &) {
+                    if ((av.y >> 1) + (bv.y >> 1) > dlim) return;
+                    const u32 slot = av.x + bv.x - slot_base;
+                    reds_or(bm_s + (slot >> 5) * 4u, 1u << (slot & 31u));
+                });
+            } else {
+                block_tile_codes(m.codeA, m.codeB, t, lane, [&](u32 ca, u32 cb) {
+                    const u32 slot = ca + cb - slot_base;
+                    reds_or(bm_s + (slot >> 5) * 4u, 1u << (slot & 31u));
+                });
+            }
+        }
+        __syncthreads();
+        u32 cnt = 0;
+        for (u32 w = tid; w < nwords; w += 128u) {
+            const u32 v = mbm[w];
+            if (v) {
+                cnt += __popc(v);
+                if (w == 0 || w + 1 == nwords) atomicOr(&m.gbm[w_first + w], v);
+                else m.gbm[w_first + w] = v;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) s_red[warp] = cnt;
+        __syncthreads();
+        if (tid == 0) {
+            const u32 e = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+            m.entries[zr] = e;
+            my_max = max(my_max, e);
+        }
+    }
+    if (tid == 0 && my_max) atomicMax(&m.geo->max_entries, my_max);
+}
+
+struct ZonesArgs {
+    const u32 *entries;   // sparse: marked codes per unit of the partition (nullptr = dense: one zone per unit)
+    const u32 *tstart;    // per unit of the partition
+    const u64 *pprefix;   // exclusive product prefix per unit of the partition
+    u32 cap;              // sparse: accumulator entries one zone pass holds
+    u32 zmax;             // sparse: most units one zone may span (the bitmap of a zone lives in shared memory)
+    u64 zone_products;    // sparse: products per zone aimed at
+    u32 *zstart;          // out: first unit of every zone (+ one past the last)
+    u64 *zone_off;        // out (sparse): position of the zone's first term in the result (+ total)
+    u32 *order;           // out: zones, heaviest first
+    u32 max_zones;
+    BlockGeo *geo;
+};
+
+// Zones of the partition and their order (one block).
+// DENSE: one zone per unit.  SPARSE: consecutive units are packed into zones by a running weight -- a unit weighs
+// entries / cap' + 1 / zmax + products / zone_products, a zone ends where the prefix of the weights passes the next
+// integer -- so no zone holds more entries than one pass of accumulators takes (cap' = cap minus the largest unit),
+// spans more units than its bitmap covers, or carries much more work than the others; the prefix of the entry counts at
+// a zone's first unit is where its terms go in the result.  Order: heaviest first (LPT) by a counting sort over 256
+// logarithmic classes of the zone's product count; zones without tiles sort last and are never claimed.
+__global__ void __launch_bounds__(1024) k_block_zones(const ZonesArgs a)
+{
+    __shared__ u64 s_ws[40];
+    __shared__ u32 s_ws32[40];
+    __shared__ u32 s_hist[256], s_start[256];
+    const u32 tid = threadIdx.x;
+    BlockGeo &g = *a.geo;
+    if (g.flags) {
+        if (tid == 0) g.n_zones = g.n_active = 0;
+        return;
+    }
+    const u32 n = g.zu_hi - g.zu_lo;
+    u32 nz = 0;
+    if (!a.entries) {
+        nz = min(n, a.max_zones);
+        for (u32 z = tid; z <= nz; z += 1024u) a.zstart[z] = z;
+        __syncthreads();
+    } else {
+        const u32 max_e = g.max_entries;
+        const u64 cap_eff = max((u64)a.cap / 2u, (u64)a.cap - min((u64)a.cap, (u64)max_e)); // entries a zone may collect before its last unit
+        const double ONE = 1048576.0;
+        const double w_entry = ONE / (double)cap_eff, w_unit = ONE / (double)a.zmax, w_prod = ONE / (double)max(a.zone_products, (u64)1);
+        auto weight = [&](u32 i) -> u64 { // (floating point, but the same expression everywhere it is used: cuts are consistent)
+            const double w = ceil((double)a.entries[i] * w_entry) + ceil(w_unit) + floor((double)(a.pprefix[i + 1] - a.pprefix[i]) * w_prod);
+            return (u64)fmin(w, ONE); // (a unit heavier than a zone is a zone of its own)
+        };
+        // chunks of 4096 units, four consecutive units per thread; zone id of a unit = floor(exclusive weight prefix): the
+        // weights of a zone's units except the last sum to < 1
+        u64 wrun = 0, erun = 0;
+        u32 zrun = 0;
+        for (u32 base = 0; base < n; base += 4096u) {
+            const u32 i = base + tid * 4u;
+            u64 w[4], e[4], wsum = 0, esum = 0;
+#pragma unroll
+            for (u32 k = 0; k < 4; ++k) {
+                w[k] = (i + k < n) ? weight(i + k) : 0ull;
+                e[k] = (i + k < n) ? (u64)a.entries[i + k] : 0ull;
+                wsum += w[k];
+                esum += e[k];
+            }
+            u64 wtot, etot;
+            u64 wex = wrun + block_excl_scan64(wsum, s_ws, wtot);
+            u64 eex = erun + block_excl_scan64(esum, s_ws, etot);
+            u32 prev_id = (i > 0 && i < n) ? (u32)((wex - weight(i - 1)) >> 20) : 0xFFFFFFFFu;
+            u32 start[4], starts = 0;
+            {
+                u64 x = wex;
+#pragma unroll
+                for (u32 k = 0; k < 4; ++k) {
+                    const u32 id = (u32)(x >> 20);
+                    start[k] = (i + k < n && id != prev_id) ? 1u : 0u;
+                    starts += start[k];
+                    prev_id = id;
+                    x += w[k];
+                }
+            }
+            u32 stot;
+            u32 zidx = zrun + block_excl_scan(starts, s_ws32, stot);
+#pragma unroll
+            for (u32 k = 0; k < 4; ++k) {
+                if (start[k]) {
+                    if (zidx < a.max_zones) {
+                        a.zstart[zidx] = i + k;
+                        a.zone_off[zidx] = eex;
+                    }
+                    ++zidx;
+                }
+                eex += e[k];
+            }
+            wrun += wtot;
+            erun += etot;
+            zrun += stot;
+        }
+        nz = min(zrun, a.max_zones);
+        if (tid == 0) {
+            a.zstart[nz] = n;
+            a.zone_off[nz] = erun;
+            g.entries_total = erun;
+        }
+        __syncthreads();
+    }
+    // heaviest first
+    auto zwork_of = [&](u32 z) -> u64 {
+        const u32 u0 = a.zstart[z], u1 = a.zstart[z + 1];
+        if (a.tstart[u0] == a.tstart[u1]) return 0ull; // no tiles
+        return max((u64)1, a.pprefix[u1] - a.pprefix[u0]);
+    };
+    for (u32 i = tid; i < 256; i += 1024u) s_hist[i] = 0;
+    __syncthreads();
+    auto cls = [](u64 w) -> u32 {
+        if (w == 0) return 0u;
+        const u32 e = 63u - (u32)__clzll((long long)w);
+        const u32 m = e >= 2 ? (u32)(w >> (e - 2)) & 3u : 0u;
+        return min(255u, 4u * e + m + 1u);
+    };
+    for (u32 z = tid; z < nz; z += 1024u) atomicAdd(&s_hist[cls(zwork_of(z))], 1u);
+    __syncthreads();
+    if (tid == 0) {
+        u32 run = 0;
+        for (int c = 255; c >= 0; --c) {
+            s_start[c] = run;
+            run += s_hist[c];
+        }
+        g.n_zones = nz;
+        g.n_active = nz - s_hist[0];
+    }
+    __syncthreads();
+    for (u32 z = tid; z < nz; z += 1024u) a.order[atomicAdd(&s_start[cls(zwork_of(z))], 1u)] = z;
+}
+
+
+
+// Product of two operand records -> 32-bit words of the magnitude (pw[0..8))
+template <int LW>
+__device__ __forceinline__ void block_product_words(const uint4 &av, const uint4 &bv, const uint2 &ah, const uint2 &bh, u32 (&pw)[8])
+{
+    const u64 ma = (u64)av.z | ((u64)av.w << 32), mb = (u64)bv.z | ((u64)bv.w << 32);
+    if (LW == 1) {
+        const u64 plo = ma * mb, phi = __umul64hi(ma, mb);
+        pw[0] = (u32)plo, pw[1] = (u32)(plo >> 32), pw[2] = (u32)phi, pw[3] = (u32)(phi >> 32);
+        pw[4] = pw[5] = pw[6] = pw[7] = 0u;
+    } else {
+        const u64 xa[2] = {ma, (u64)ah.x | ((u64)ah.y << 32)}, xb[2] = {mb, (u64)bh.x | ((u64)bh.y << 32)};
+        u64 pr[4];
+        mag_mul<2, 2>(xa, xb, pr);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pw[2 * q] = (u32)pr[q], pw[2 * q + 1] = (u32)(pr[q] >> 32);
+    }
+}
+
+struct AccArgs {
+    ZoneArgs z;            // operands, accumulator geometry (cap, off_acc, off_bm), codec, result arrays, counters
+    const uint4 *tiles;
+    const u32 *tstart;     // per unit of the partition
+    const u32 *zstart;     // first unit of every zone (+ one past the last)
+    const u64 *zone_off;   // position of the zone's first term in the result arrays (+ total)
+    const u32 *order;      // zones, heaviest first
+    const u32 *gbm;        // bitmap of the partition (k_block_mark)
+    u32 *zone_count;       // out: non-zero terms the zone wrote (its marked codes minus the cancellations)
+    u32 U;                 // codes per zone unit
+    u32 range;
+    u32 raw_off;           // byte offset in dynamic shared memory of the landing area of the raw bitmap words
+    const TruncDev *trunc;
+    BlockGeo *geo;
+};
+
+// SPARSE ranges, second walk: accumulate and emit.  One thread block (1024 threads, one per SM) per zone:
+//   1. the zone's bitmap words arrive from HBM by one bulk copy (cp.async.bulk + mbarrier) into shared memory and become
+//      {bits, exclusive popcount prefix} pairs: rank(code) = prefix + popc(bits below) is a perfect order-preserving hash
+//      of the zone's codes into [0, entries);
+//   2. the warps walk the zone's tiles: key add -> rank -> 64x64 (or 128x128) product -> shared-memory atomics with the
+//      carry chain (block_accumulate);
+//   3. every thread emits a run of consecutive ranks -- it finds its first code by a binary search over the prefixes
+//      and then steps through the set bits -- at the zone's FINAL position in the result (zone_off + rank): the scan in
+//      k_block_zones fixed it, so the terms of all zones land in code order without staging or gather.  Zero
+//      coefficients are dropped (sanitise_series); they leave a gap at the zone's end that one gather pass closes later.
+// A zone with more entries than one pass of accumulators holds (a single unit denser than cap) runs in several passes
+// over consecutive code ranges.
+template <int NW, int PW, bool SIGNED, int LW>
+__global__ void __launch_bounds__(1024, 1) k_block_acc(const AccArgs aa)
+{
+    const u32 kThreads = blockDim.x; // 1024 (one block per SM) or 512 (two per SM: one walks while the other emits)
+    const ZoneArgs &a = aa.z;
     extern __shared__ __align__(16) unsigned char zsmem[];
     u32 *acc = reinterpret_cast<u32 *>(zsmem + a.off_acc);
-    uint2 *bm = reinterpret_cast<uint2 *>(zsmem + a.off_bm); // MODE 1: {bits, prefix}
-    u32 *list = reinterpret_cast<u32 *>(zsmem + a.off_list);
-    u32 *hkeys = reinterpret_cast<u32 *>(zsmem + ba.off_keys); // MODE 1: keys of the hash attempt
+    uint2 *bm = reinterpret_cast<uint2 *>(zsmem + a.off_bm); // {bits, prefix}
+    u32 *raw = reinterpret_cast<u32 *>(zsmem + aa.raw_off);  // landing area of the bulk copy (the upper half of bm)
     __shared__ u32 s_ws[40];
-    __shared__ u64 s_b64[2];
     __shared__ u32 s_b32[4];
-    __shared__ u32 s_next; // dynamic tile counter
-    __shared__ u32 s_ovf;  // the hash attempt ran out of probes
+    __shared__ u32 s_next;
+    __shared__ __align__(8) u64 s_bar;
 
     const u32 tid = threadIdx.x, lane = tid & 31u;
-    const u32 acc_s = smem_u32(acc), bm_s = smem_u32(bm);
+    const u32 acc_s = smem_u32(acc);
+    const u32 next_s = smem_u32(&s_next);
     const u32 wstride = a.cap * 4u;
     u64 my_pairs = 0;
     u32 my_maxbits = 0, my_flags = 0;
-    const u32 n_active = __ldg(ba.n_active);
-    const u32 dlim = ba.trunc ? __ldg(&ba.trunc->dlim) : 0xFFFFFFFFu;
+    if (aa.geo->flags) return;
+    const u32 n_active = aa.geo->n_active;
+    const u32 zu_lo = aa.geo->zu_lo;
+    const u64 code_lo = (u64)zu_lo * aa.U;
+    const u32 dlim = aa.trunc ? __ldg(&aa.trunc->dlim) : 0xFFFFFFFFu;
 
     for (u32 i = tid; i < a.cap * NW; i += kThreads) acc[i] = 0;
-    if (MODE == 1) {
-        for (u32 i = tid; i < a.bm_words; i += kThreads) bm[i] = make_uint2(0u, 0u);
-        if (ba.hash)
-            for (u32 i = tid; i < a.cap; i += kThreads) hkeys[i] = 0;
-    }
+    if (tid == 0) mbar_init(&s_bar, 1);
     __syncthreads();
+    u32 bar_parity = 0;
 
     for (;;) {
-        if (tid == 0) s_b32[0] = atomicAdd(a.chunk_counter, 1u);
+        if (tid == 0) s_b32[0] = atomicAdd(&aa.geo->claim_acc, 1u);
         __syncthreads();
         const u32 claimed = s_b32[0];
         __syncthreads();
         if (claimed >= n_active) break;
-        const u32 z = ba.order ? __ldg(&ba.order[claimed]) : claimed;
-        const u32 hr0 = __ldg(&ba.zstart[z]), hr1 = __ldg(&ba.zstart[z + 1]);
-        const u32 zlo = (ba.h_base + hr0) * ba.S, zhi = (ba.h_base + hr1) * ba.S;
-        const u32 t0 = __ldg(&ba.tstart[hr0]), t1 = __ldg(&ba.tstart[hr1]);
-        if (t0 == t1) continue; // (only in natural order: a zone without tiles)
-        const u32 zwords = (MODE == 1) ? min(a.bm_words, (zhi - zlo + 31u) >> 5) : 0u; // bitmap words in use
+        const u32 z = __ldg(&aa.order[claimed]);
+        const u32 u0 = __ldg(&aa.zstart[z]), u1 = __ldg(&aa.zstart[z + 1]);
+        const u64 zoff = __ldg(&aa.zone_off[z]);
+        const u32 n_entries = (u32)(__ldg(&aa.zone_off[z + 1]) - zoff);
+        const u32 t0 = __ldg(&aa.tstart[u0]), t1 = __ldg(&aa.tstart[u1]);
+        if (n_entries == 0 || t0 == t1) continue;
+        const u64 zc0 = code_lo + (u64)u0 * aa.U, zc1 = min((u64)aa.range, code_lo + (u64)u1 * aa.U);
+        const u32 bit0 = (u32)(zc0 - code_lo), bit1 = (u32)(zc1 - code_lo);
+        const u32 w_first = bit0 >> 5, zwords = ((bit1 + 31u) >> 5) - w_first;
+        const u32 slot_base = (u32)code_lo + w_first * 32u; // slot = code - slot_base; word = slot >> 5
 
-        // ---------------- sparse zones, experiment (tuning key "block_hash", off): ONE walk that accumulates into a
-        // shared-memory hash table keyed by the code (the bitmap is then built from the ENTRIES, not from the products, and
-        // only orders the emission).  A zone whose entries do not fit (probe limit) is cleared and redone by the two-walk
-        // scheme below.  Measured on pearce1: 0.60 ms against 0.39 ms for the two-walk scheme -- the probe loop leaves the
-        // lanes of a warp diverged for the multiply-accumulate that follows (9 of 32 lanes active in the ncu source view),
-        // and the heaviest 9 % of the zones overflow the table and pay for both schemes.
-        if (MODE == 1 && ba.hash) {
-            const u32 keys_s = smem_u32(hkeys);
-            if (tid == 0) {
-                s_next = t0;
-                s_ovf = 0;
-            }
-            __syncthreads();
-            u64 zone_pairs = 0;
-            auto hash_accumulate = [&](const uint4 &av, const uint4 &bv, const uint2 &ah, const uint2 &bh) {
-                const u32 h = block_hash_slot(keys_s, a.cap, av.x + bv.x - zlo);
-                if (h == 0xFFFFFFFFu) {
-                    s_ovf = 1;
-                    return;
-                }
-                const u64 ma = (u64)av.z | ((u64)av.w << 32), mb = (u64)bv.z | ((u64)bv.w << 32);
-                u32 pw[8];
-                if (LW == 1) {
-                    const u64 plo = ma * mb, phi = __umul64hi(ma, mb);
-                    pw[0] = (u32)plo, pw[1] = (u32)(plo >> 32), pw[2] = (u32)phi, pw[3] = (u32)(phi >> 32);
-                    pw[4] = pw[5] = pw[6] = pw[7] = 0u;
-                } else {
-                    const u64 xa[2] = {ma, (u64)ah.x | ((u64)ah.y << 32)}, xb[2] = {mb, (u64)bh.x | ((u64)bh.y << 32)};
-                    u64 pr[4];
-                    mag_mul<2, 2>(xa, xb, pr);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) pw[2 * q] = (u32)pr[q], pw[2 * q + 1] = (u32)(pr[q] >> 32);
-                }
-                block_accumulate<NW, PW, SIGNED>(acc_s + h * 4u, wstride, pw, SIGNED && (((av.y ^ bv.y) & 1u) != 0));
-            };
-            block_for_each_tile(ba.tiles, &s_next, t1, lane, [&](const uint4 &t) {
-                if (*((volatile u32 *)&s_ovf)) return; // the attempt is lost: drain the tile list quickly
-                if (t.z >> 31) {
-                    block_tile_loop<2, LW>(a.A, a.B, a.A1, a.B1, t, lane, [&](const uint4 &av, const uint4 &bv, const uint2 &ah, const uint2 &bh) {
-                        if ((av.y >> 1) + (bv.y >> 1) > dlim) return;
-                        ++zone_pairs;
-                        hash_accumulate(av, bv, ah, bh);
-                    });
-                } else {
-                    if (lane == 0) zone_pairs += (u64)(t.z & 1023u) * ((t.z >> 10) & 127u);
-                    block_tile_loop<2, LW>(a.A, a.B, a.A1, a.B1, t, lane, hash_accumulate);
-                }
-            });
-            __syncthreads();
-            if (s_ovf == 0) {
-                my_pairs += zone_pairs;
-                // entries -> bitmap -> ranks -> list of table indices in ascending code order
-                for (u32 h = tid; h < a.cap; h += kThreads) {
-                    const u32 k = hkeys[h];
-                    if (k) reds_or(bm_s + ((k - 1u) >> 5) * 8u, 1u << ((k - 1u) & 31u));
-                }
-                __syncthreads();
-                const u32 wpt = (zwords + kThreads - 1) / kThreads;
-                const u32 w0 = min(zwords, tid * wpt), w1 = min(zwords, w0 + wpt);
-                u32 local = 0;
-                for (u32 w = w0; w < w1; ++w) local += __popc(bm[w].x);
-                u32 n_ent;
-                u32 run = block_excl_scan(local, s_ws, n_ent);
-                for (u32 w = w0; w < w1; ++w) {
-                    bm[w].y = run;
-                    run += __popc(bm[w].x);
-                }
-                __syncthreads();
-                for (u32 h = tid; h < a.cap; h += kThreads) {
-                    const u32 k = hkeys[h];
-                    if (k) {
-                        const uint2 bw = bm[(k - 1u) >> 5];
-                        list[bw.y + __popc(bw.x & ((1u << ((k - 1u) & 31u)) - 1u))] = h;
-                    }
-                }
-                __syncthreads();
-                // emission in rank order (one run of consecutive ranks per thread), zeros dropped, table cleared on the way
-                const u32 per = ((n_ent + kThreads - 1) / kThreads) | 1u;
-                const u32 e0 = min(n_ent, tid * per), e1 = min(n_ent, e0 + per);
-                u32 nzc = 0;
-                for (u32 e = e0; e < e1; ++e) {
-                    const u32 h = list[e];
-                    u32 any = 0;
-#pragma unroll
-                    for (int q = 0; q < NW; ++q) any |= acc[q * a.cap + h];
-                    nzc += any != 0;
-                }
-                u32 total;
-                const u32 excl = block_excl_scan(nzc, s_ws, total);
-                if (tid == 0) s_b64[1] = atomicAdd(a.bump, (u64)total);
-                __syncthreads();
-                const u64 zone_base = s_b64[1];
-                u64 pos = zone_base + excl;
-                for (u32 e = e0; e < e1; ++e) {
-                    const u32 h = list[e];
-                    u32 wd[NW], any = 0;
-#pragma unroll
-                    for (int q = 0; q < NW; ++q) {
-                        wd[q] = acc[q * a.cap + h];
-                        acc[q * a.cap + h] = 0;
-                        any |= wd[q];
-                    }
-                    const u32 slot = hkeys[h] - 1u;
-                    hkeys[h] = 0;
-                    if (any) {
-                        zone_emit<NW>(a, pos, zlo + slot, wd, my_maxbits, my_flags);
-                        ++pos;
-                    }
-                }
-                if (tid == 0) {
-                    a.zone_count[z] = total;
-                    a.zone_off[z] = zone_base;
-                }
-                for (u32 i = tid; i < zwords; i += kThreads) bm[i].x = 0;
-                __syncthreads();
-                continue;
-            }
-            // lost: clear what the attempt left behind, then the two-walk scheme
-            if (tid == 0) atomicAdd(&a.ctr->aux, 1ull); // (statistics: zones that fell back)
-            for (u32 i = tid; i < a.cap; i += kThreads) hkeys[i] = 0;
-            for (u32 i = tid; i < a.cap * NW; i += kThreads) acc[i] = 0;
-            __syncthreads();
+        // ---- 1. bitmap: bulk copy HBM -> shared, then {bits, prefix}
+        // (the copy wants 16-byte aligned addresses and sizes: it starts at the aligned word at or before w_first)
+        const u32 w_al = w_first & ~3u, lead = w_first - w_al;
+        const u32 copy_words = (lead + zwords + 3u) & ~3u;
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic-proxy accesses to the landing area precede the bulk copy
+            mbar_expect_tx(&s_bar, copy_words * 4u);
+            tma_load_1d(raw, aa.gbm + w_al, copy_words * 4u, &s_bar);
         }
-
-        // ---------------- walk 1 (bitmap zones): mark the codes that occur
-        u32 zone_count = 0;
-        if (MODE == 1) {
-            if (tid == 0) s_next = t0;
-            __syncthreads();
-            block_for_each_tile(ba.tiles, &s_next, t1, lane, [&](const uint4 &t) {
-                if (t.z >> 31) { // truncation: some products of this tile exceed the degree limit
-                    block_tile_loop<1, LW>(a.A, a.B, a.A1, a.B1, t, lane, [&](const uint4 &av, const uint4 &bv, const uint2 &, const uint2 &) {
-                        if ((av.y >> 1) + (bv.y >> 1) > dlim) return;
-                        ++my_pairs;
-                        const u32 slot = av.x + bv.x - zlo;
-                        reds_or(bm_s + (slot >> 5) * 8u, 1u << (slot & 31u));
-                    });
-                } else {
-                    if (lane == 0) my_pairs += (u64)(t.z & 1023u) * ((t.z >> 10) & 127u);
-                    block_tile_loop<0, LW>(a.A, a.B, a.A1, a.B1, t, lane, [&](const uint4 &av, const uint4 &bv, const uint2 &, const uint2 &) {
-                        const u32 slot = av.x + bv.x - zlo;
-                        reds_or(bm_s + (slot >> 5) * 8u, 1u << (slot & 31u));
-                    });
-                }
-            });
-            __syncthreads();
-            // exclusive popcount prefix per bitmap word
-            const u32 wpt = (zwords + kThreads - 1) / kThreads;
-            const u32 w0 = min(zwords, tid * wpt), w1 = min(zwords, w0 + wpt);
-            u32 local = 0;
-            for (u32 w = w0; w < w1; ++w) local += __popc(bm[w].x);
-            u32 total;
-            u32 run = block_excl_scan(local, s_ws, total);
-            for (u32 w = w0; w < w1; ++w) {
-                bm[w].y = run;
-                run += __popc(bm[w].x);
-            }
-            zone_count = total;
-            __syncthreads();
+        mbar_wait(&s_bar, bar_parity);
+        bar_parity ^= 1u;
+        const u32 wpt = (zwords + kThreads - 1) / kThreads;
+        const u32 w0 = min(zwords, tid * wpt), w1 = min(zwords, w0 + wpt);
+        const u32 first_mask = 0xFFFFFFFFu << (bit0 & 31u);
+        const u32 last_mask = (bit1 & 31u) ? ((1u << (bit1 & 31u)) - 1u) : 0xFFFFFFFFu;
+        u32 local = 0;
+        for (u32 w = w0; w < w1; ++w) {
+            u32 v = raw[lead + w];
+            if (w == 0) v &= first_mask; // bits below the zone belong to its neighbour
+            if (w + 1 == zwords) v &= last_mask;
+            local += __popc(v);
         }
+        u32 total;
+        u32 run = block_excl_scan(local, s_ws, total);
+        // (pairs overwrite the landing area from below: every thread has read its raw words before the scan's barriers)
+        u32 keep[8]; // (the plan keeps zwords <= 8 * blockDim.x)
+        for (u32 w = w0, k = 0; w < w1 && k < 8; ++w, ++k) {
+            u32 v = raw[lead + w];
+            if (w == 0) v &= first_mask;
+            if (w + 1 == zwords) v &= last_mask;
+            keep[k] = v;
+        }
+        __syncthreads();
+        for (u32 w = w0, k = 0; w < w1 && k < 8; ++w, ++k) {
+            bm[w] = make_uint2(keep[k], run);
+            run += __popc(keep[k]);
+        }
+        if (total != n_entries) my_flags |= kFlagTableFull; // (cannot happen: the same bits were counted by k_block_mark)
+        __syncthreads();
 
-        // ---------------- accumulate + emit, in passes of at most `cap` entries
-        const u32 n_entries = (MODE == 1) ? zone_count : (zhi - zlo);
-        const bool single = (MODE == 0) || n_entries <= a.cap;
-        u64 zone_base = 0, zone_written = 0;
-        bool have_base = false;
-        u32 r0 = 0;   // first rank (bitmap) / slot (dense) of this pass
-        u32 c0 = zlo; // first code of this pass
+        // ---- 2 + 3. accumulate and emit, in passes of at most `cap` entries
+        const bool single = n_entries <= a.cap;
+        u32 zone_written = 0;
+        u32 r0 = 0;          // first rank of this pass
+        u32 c0 = (u32)zc0;   // first code of this pass
         do {
             const u32 r1 = min(n_entries, r0 + a.cap);
-            u32 c1 = zhi;
+            u32 c1 = (u32)zc1;
             u32 tp0 = t0, tp1 = t1; // tiles of this pass
-            if (MODE == 1) {
+            if (!single) {
                 if (r1 < n_entries) { // the code of rank r1 bounds this pass
                     if (tid == 0) {
                         u32 lo_w = 0, hi_w = zwords; // last word with prefix <= r1
@@ -850,109 +1054,51 @@ __global__ void __launch_bounds__(1024, 1) k_block(const BlockArgs ba)
                             rem -= __popc(bm[w].x);
                             ++w;
                         }
-                        s_b32[1] = zlo + w * 32u + __fns(bm[w].x, 0, (int)rem + 1);
+                        s_b32[1] = slot_base + w * 32u + __fns(bm[w].x, 0, (int)rem + 1);
                     }
                     __syncthreads();
                     c1 = s_b32[1];
                 }
-                if (!single) { // the codes of a pass are consecutive, so only the tiles of its blocks are walked
-                    tp0 = __ldg(&ba.tstart[hr0 + (c0 - zlo) / ba.S]);
-                    tp1 = __ldg(&ba.tstart[hr0 + (c1 - 1u - zlo) / ba.S + 1u]);
-                }
-                // rank -> slot list of this pass, so that emission runs with full warps
-                const u32 wpt = (zwords + kThreads - 1) / kThreads;
-                const u32 w0 = min(zwords, tid * wpt), w1 = min(zwords, w0 + wpt);
-                for (u32 w = w0; w < w1; ++w) {
-                    const uint2 bw = bm[w];
-                    u32 rank = bw.y, bits = bw.x;
-                    if (rank >= r1 || rank + (u32)__popc(bits) <= r0) continue;
-                    while (bits) {
-                        const u32 b = __ffs(bits) - 1;
-                        bits &= bits - 1;
-                        if (rank >= r0 && rank < r1) list[rank - r0] = w * 32u + b;
-                        ++rank;
-                    }
-                }
+                // the codes of a pass are consecutive, so only the tiles of the units it covers are walked
+                tp0 = __ldg(&aa.tstart[u0 + (u32)((c0 - zc0) / aa.U)]);
+                tp1 = __ldg(&aa.tstart[u0 + (u32)((c1 - 1u - zc0) / aa.U) + 1u]);
             }
             if (tid == 0) s_next = tp0;
             __syncthreads();
             auto accumulate = [&](const uint4 &av, const uint4 &bv, const uint2 &ah, const uint2 &bh) {
                 const u32 code = av.x + bv.x;
-                if (MODE == 1 && !single && (code < c0 || code >= c1)) return;
-                const u32 slot = code - zlo;
-                u32 e;
-                if (MODE == 1) {
-                    const uint2 bw = bm[slot >> 5];
-                    e = bw.y + __popc(bw.x & ((1u << (slot & 31u)) - 1u)) - r0;
-                } else {
-                    e = slot;
-                }
-                const u64 ma = (u64)av.z | ((u64)av.w << 32), mb = (u64)bv.z | ((u64)bv.w << 32);
+                if (!single && (code < c0 || code >= c1)) return;
+                const u32 slot = code - slot_base;
+                const uint2 bw = bm[slot >> 5];
+                const u32 e = bw.y + __popc(bw.x & ((1u << (slot & 31u)) - 1u)) - r0;
                 u32 pw[8];
-                if (LW == 1) {
-                    const u64 plo = ma * mb, phi = __umul64hi(ma, mb);
-                    pw[0] = (u32)plo, pw[1] = (u32)(plo >> 32), pw[2] = (u32)phi, pw[3] = (u32)(phi >> 32);
-                    pw[4] = pw[5] = pw[6] = pw[7] = 0u;
-                } else {
-                    const u64 xa[2] = {ma, (u64)ah.x | ((u64)ah.y << 32)}, xb[2] = {mb, (u64)bh.x | ((u64)bh.y << 32)};
-                    u64 pr[4];
-                    mag_mul<2, 2>(xa, xb, pr);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) pw[2 * q] = (u32)pr[q], pw[2 * q + 1] = (u32)(pr[q] >> 32);
-                }
+                block_product_words<LW>(av, bv, ah, bh, pw);
                 block_accumulate<NW, PW, SIGNED>(acc_s + e * 4u, wstride, pw, SIGNED && (((av.y ^ bv.y) & 1u) != 0));
             };
-            // the same for two products at a time (one-limb operands): slots and products of both first, then the two
-            // accumulation chains interleaved word by word
-            auto accumulate2 = [&](const uint4 &av0, const uint4 &bv0, bool on0, const uint4 &av1, const uint4 &bv1, bool on1) {
-                const u32 code0 = av0.x + bv0.x, code1 = av1.x + bv1.x;
-                if (MODE == 1 && !single) {
-                    on0 = on0 && code0 >= c0 && code0 < c1;
-                    on1 = on1 && code1 >= c0 && code1 < c1;
-                }
-                const u32 slot0 = on0 ? code0 - zlo : 0u, slot1 = on1 ? code1 - zlo : 0u;
-                u32 e0 = slot0, e1 = slot1;
-                if (MODE == 1) {
-                    const uint2 bw0 = bm[slot0 >> 5], bw1 = bm[slot1 >> 5];
-                    e0 = on0 ? bw0.y + __popc(bw0.x & ((1u << (slot0 & 31u)) - 1u)) - r0 : 0u;
-                    e1 = on1 ? bw1.y + __popc(bw1.x & ((1u << (slot1 & 31u)) - 1u)) - r0 : 0u;
-                }
-                const u64 ma0 = (u64)av0.z | ((u64)av0.w << 32), mb0 = (u64)bv0.z | ((u64)bv0.w << 32);
-                const u64 ma1 = (u64)av1.z | ((u64)av1.w << 32), mb1 = (u64)bv1.z | ((u64)bv1.w << 32);
-                const u64 lo0 = ma0 * mb0, hi0 = __umul64hi(ma0, mb0), lo1 = ma1 * mb1, hi1 = __umul64hi(ma1, mb1);
-                const u32 p0[4] = {(u32)lo0, (u32)(lo0 >> 32), (u32)hi0, (u32)(hi0 >> 32)};
-                const u32 p1[4] = {(u32)lo1, (u32)(lo1 >> 32), (u32)hi1, (u32)(hi1 >> 32)};
-                block_accumulate2<NW, (PW < 4 ? PW : 4), SIGNED>(acc_s + e0 * 4u, p0, SIGNED && (((av0.y ^ bv0.y) & 1u) != 0), on0,
-                                                                 acc_s + e1 * 4u, p1, SIGNED && (((av1.y ^ bv1.y) & 1u) != 0), on1, wstride);
-            };
-            block_for_each_tile(ba.tiles, &s_next, tp1, lane, [&](const uint4 &t) {
-                // (measured: fateman2, five-word chains, 3.63 -> 3.43 ms; fateman1 unchanged; bitmap zones 5 % SLOWER --
-                // their rank look-ups and range tests double too -- and degree-tested tiles 30 % slower, so only the
-                // untested tiles of dense zones take the pair walk)
-                if (LW == 1 && MODE == 0 && ba.pair_walk && !(t.z >> 31)) {
-                    if (lane == 0) my_pairs += (u64)(t.z & 1023u) * ((t.z >> 10) & 127u);
-                    block_tile_loop2(a.A, a.B, t, lane, [&](const uint4 &av0, const uint4 &bv0, const uint4 &av1, const uint4 &bv1, bool on1) {
-                        accumulate2(av0, bv0, true, av1, bv1, on1);
-                    });
-                    return;
-                }
+            block_walk_tiles<1>(aa.tiles, next_s, tp1, lane, [&](const uint4 &t) {
                 if (t.z >> 31) { // truncation: test the degree of every product of this tile
                     block_tile_loop<2, LW>(a.A, a.B, a.A1, a.B1, t, lane, [&](const uint4 &av, const uint4 &bv, const uint2 &ah, const uint2 &bh) {
                         if ((av.y >> 1) + (bv.y >> 1) > dlim) return;
-                        if (MODE == 0) ++my_pairs;
+                        if (single || (av.x + bv.x >= c0 && av.x + bv.x < c1)) ++my_pairs;
                         accumulate(av, bv, ah, bh);
                     });
                 } else {
-                    if (MODE == 0 && lane == 0) my_pairs += (u64)(t.z & 1023u) * ((t.z >> 10) & 127u);
-                    block_tile_loop<2, LW>(a.A, a.B, a.A1, a.B1, t, lane, accumulate);
+                    if (single && lane == 0) my_pairs += (u64)(t.z & 1023u) * ((t.z >> 10) & 127u);
+                    if (!single) {
+                        block_tile_loop<2, LW>(a.A, a.B, a.A1, a.B1, t, lane, [&](const uint4 &av, const uint4 &bv, const uint2 &ah, const uint2 &bh) {
+                            if (av.x + bv.x >= c0 && av.x + bv.x < c1) ++my_pairs;
+                            accumulate(av, bv, ah, bh);
+                        });
+                    } else {
+                        block_tile_loop<2, LW>(a.A, a.B, a.A1, a.B1, t, lane, accumulate);
+                    }
                 }
             });
             __syncthreads();
 
-            // ---- emit the entries [0, n_pass) of this pass in ascending code order: every thread owns a run of
-            // consecutive entries (odd length: conflict-free strided reads), counts its non-zero ones, ONE block scan
-            // gives its first output position; staging space is claimed with one atomicAdd per zone (the exact count
-            // of a single-pass zone, else the entry count)
+            // ---- emit the entries [0, n_pass) of this pass in ascending code order: every thread owns a run of consecutive
+            // ranks (odd length: conflict-free strided reads), counts its non-zero ones, ONE block scan gives its first
+            // output position inside the zone
             const u32 n_pass = r1 - r0;
             const u32 per = ((n_pass + kThreads - 1) / kThreads) | 1u;
             const u32 e0 = min(n_pass, tid * per), e1 = min(n_pass, e0 + per);
@@ -963,40 +1109,208 @@ __global__ void __launch_bounds__(1024, 1) k_block(const BlockArgs ba)
                 for (int q = 0; q < NW; ++q) any |= acc[q * a.cap + e];
                 nzc += any != 0;
             }
-            u32 total;
-            const u32 excl = block_excl_scan(nzc, s_ws, total);
-            if (!have_base) {
-                if (tid == 0) s_b64[1] = atomicAdd(a.bump, single ? (u64)total : (u64)n_entries);
-                __syncthreads();
-                zone_base = s_b64[1];
-                have_base = true;
-            }
-            u64 pos = zone_base + zone_written + excl;
-            for (u32 e = e0; e < e1; ++e) {
-                u32 wd[NW], any = 0;
+            u32 ptotal;
+            const u32 excl = block_excl_scan(nzc, s_ws, ptotal);
+            if (e0 < e1) {
+                // the code of rank r0 + e0: first word whose inclusive prefix exceeds it, then the set bits in order
+                const u32 target = r0 + e0;
+                u32 lo_w = 0, hi_w = zwords; // invariant: prefix(lo_w) <= target, and the answer is in [lo_w, hi_w)
+                while (hi_w - lo_w > 1) {
+                    const u32 mid = (lo_w + hi_w) >> 1;
+                    if (bm[mid].y <= target) lo_w = mid;
+                    else hi_w = mid;
+                }
+                // (words with equal prefixes are empty: the last word with prefix <= target is the one that holds the rank)
+                u32 w = lo_w;
+                u32 bits = bm[w].x;
+                for (u32 k = target - bm[w].y; k > 0; --k) bits &= bits - 1u;
+                u64 pos = zoff + zone_written + excl;
+                for (u32 e = e0; e < e1; ++e) {
+                    if (bits == 0u) {
+                        // the next set bit: usually in one of the next words; a long run of empty words (sparse codes) is
+                        // jumped over by a search for the last word whose prefix is <= the rank (the words between are empty)
+                        bits = bm[++w].x;
+                        if (bits == 0u) bits = bm[++w].x;
+                        if (bits == 0u) {
+                            const u32 rank = r0 + e;
+                            u32 lw = w, hw = zwords;
+                            while (hw - lw > 1) {
+                                const u32 mid = (lw + hw) >> 1;
+                                if (bm[mid].y <= rank) lw = mid;
+                                else hw = mid;
+                            }
+                            w = lw;
+                            bits = bm[w].x;
+                        }
+                    }
+                    const u32 b = __ffs(bits) - 1u;
+                    bits &= bits - 1u;
+                    u32 wd[NW], any = 0;
 #pragma unroll
-                for (int q = 0; q < NW; ++q) {
-                    wd[q] = acc[q * a.cap + e];
-                    acc[q * a.cap + e] = 0;
-                    any |= wd[q];
-                }
-                if (any) {
-                    const u32 slot = (MODE == 1) ? list[e] : e;
-                    zone_emit<NW>(a, pos, zlo + slot, wd, my_maxbits, my_flags);
-                    ++pos;
+                    for (int q = 0; q < NW; ++q) {
+                        wd[q] = acc[q * a.cap + e];
+                        acc[q * a.cap + e] = 0;
+                        any |= wd[q];
+                    }
+                    if (any) {
+                        zone_emit<NW>(a, pos, slot_base + w * 32u + b, wd, my_maxbits, my_flags);
+                        ++pos;
+                    }
                 }
             }
-            zone_written += total;
+            zone_written += ptotal;
             r0 = r1;
             c0 = c1;
             __syncthreads();
         } while (r0 < n_entries);
         if (tid == 0) {
-            a.zone_count[z] = (u32)zone_written;
-            a.zone_off[z] = zone_base;
+            aa.zone_count[z] = zone_written;
+            if (zone_written != n_entries) atomicAdd(&aa.geo->zeros, (u64)(n_entries - zone_written));
         }
-        if (MODE == 1) {
-            for (u32 i = tid; i < zwords; i += kThreads) bm[i].x = 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, o);
+        my_maxbits = max(my_maxbits, __shfl_xor_sync(0xffffffffu, my_maxbits, o));
+        my_flags |= __shfl_xor_sync(0xffffffffu, my_flags, o);
+    }
+    if (lane == 0) {
+        if (my_pairs) atomicAdd(&a.ctr->pairs, my_pairs);
+        if (my_maxbits) atomicMax(&a.ctr->max_bits, my_maxbits);
+        if (my_flags) atomicOr(&a.ctr->flags, my_flags);
+    }
+}
+
+
+
+struct DenseArgs {
+    ZoneArgs z;            // operands, accumulator geometry, output staging, counters
+    const uint4 *tiles;
+    const u32 *tstart;     // per unit of the partition (zone = unit)
+    const u32 *order;      // zones, heaviest first
+    u32 U;                 // codes per zone (unit)
+    u32 range;
+    u32 pair_walk;         // one-limb operands: 1 = the accumulating walk takes two products at a time
+    const TruncDev *trunc;
+    BlockGeo *geo;
+};
+
+// DENSE ranges: one thread block (1024 threads, one per SM) per zone, slot = code - first code of the zone; the plan
+// guarantees U <= cap, so one pass.  Warps claim tiles dynamically; 32/64-term tiles keep the b terms in registers and
+// broadcast-load the a rows; ragged tiles are flattened over the lanes.  Emission drops zeros (sanitise_series), decodes
+// keys, appends the zone's terms to a staging area (one atomicAdd per zone); k_zone_scan + k_zone_gather lay the zones
+// out in code order afterwards.
+template <int NW, int PW, bool SIGNED, int LW>
+__global__ void __launch_bounds__(1024, 1) k_block_dense(const DenseArgs da)
+{
+    constexpr u32 kThreads = 1024;
+    const ZoneArgs &a = da.z;
+    extern __shared__ __align__(16) unsigned char zsmem[];
+    u32 *acc = reinterpret_cast<u32 *>(zsmem + a.off_acc);
+    __shared__ u32 s_ws[40];
+    __shared__ u64 s_b64[2];
+    __shared__ u32 s_b32[4];
+    __shared__ u32 s_next;
+
+    const u32 tid = threadIdx.x, lane = tid & 31u;
+    const u32 acc_s = smem_u32(acc);
+    const u32 next_s = smem_u32(&s_next);
+    const u32 wstride = a.cap * 4u;
+    u64 my_pairs = 0;
+    u32 my_maxbits = 0, my_flags = 0;
+    if (da.geo->flags) return;
+    const u32 n_active = da.geo->n_active;
+    const u64 code_lo = (u64)da.geo->zu_lo * da.U;
+    const u32 dlim = da.trunc ? __ldg(&da.trunc->dlim) : 0xFFFFFFFFu;
+
+    for (u32 i = tid; i < a.cap * NW; i += kThreads) acc[i] = 0;
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) s_b32[0] = atomicAdd(&da.geo->claim_acc, 1u);
+        __syncthreads();
+        const u32 claimed = s_b32[0];
+        __syncthreads();
+        if (claimed >= n_active) break;
+        const u32 z = __ldg(&da.order[claimed]);
+        const u32 zlo = (u32)(code_lo + (u64)z * da.U), zhi = (u32)min((u64)da.range, code_lo + (u64)(z + 1) * da.U);
+        const u32 t0 = __ldg(&da.tstart[z]), t1 = __ldg(&da.tstart[z + 1]);
+        if (t0 == t1) continue;
+        if (tid == 0) s_next = t0;
+        __syncthreads();
+        auto accumulate = [&](const uint4 &av, const uint4 &bv, const uint2 &ah, const uint2 &bh) {
+            const u32 e = av.x + bv.x - zlo;
+            u32 pw[8];
+            block_product_words<LW>(av, bv, ah, bh, pw);
+            block_accumulate<NW, PW, SIGNED>(acc_s + e * 4u, wstride, pw, SIGNED && (((av.y ^ bv.y) & 1u) != 0));
+        };
+        // the same for two products at a time (one-limb operands): slots and products of both first, then the two
+        // accumulation chains interleaved word by word
+        auto accumulate2 = [&](const uint4 &av0, const uint4 &bv0, const uint4 &av1, const uint4 &bv1, bool on1) {
+            const u32 e0 = av0.x + bv0.x - zlo, e1 = on1 ? av1.x + bv1.x - zlo : 0u;
+            const u64 ma0 = (u64)av0.z | ((u64)av0.w << 32), mb0 = (u64)bv0.z | ((u64)bv0.w << 32);
+            const u64 ma1 = (u64)av1.z | ((u64)av1.w << 32), mb1 = (u64)bv1.z | ((u64)bv1.w << 32);
+            const u64 lo0 = ma0 * mb0, hi0 = __umul64hi(ma0, mb0), lo1 = ma1 * mb1, hi1 = __umul64hi(ma1, mb1);
+            const u32 p0[4] = {(u32)lo0, (u32)(lo0 >> 32), (u32)hi0, (u32)(hi0 >> 32)};
+            const u32 p1[4] = {(u32)lo1, (u32)(lo1 >> 32), (u32)hi1, (u32)(hi1 >> 32)};
+            block_accumulate2<NW, (PW < 4 ? PW : 4), SIGNED>(acc_s + e0 * 4u, p0, SIGNED && (((av0.y ^ bv0.y) & 1u) != 0), true,
+                                                             acc_s + e1 * 4u, p1, SIGNED && (((av1.y ^ bv1.y) & 1u) != 0), on1, wstride);
+        };
+        block_walk_tiles<2>(da.tiles, next_s, t1, lane, [&](const uint4 &t) {
+            // (measured: fateman2, five-word chains, 3.63 -> 3.43 ms; fateman1 unchanged; degree-tested tiles 30 % slower,
+            // so only the untested tiles take the pair walk)
+            if (LW == 1 && da.pair_walk && !(t.z >> 31)) {
+                if (lane == 0) my_pairs += (u64)(t.z & 1023u) * ((t.z >> 10) & 127u);
+                block_tile_loop2(a.A, a.B, t, lane, accumulate2);
+                return;
+            }
+            if (t.z >> 31) { // truncation: test the degree of every product of this tile
+                block_tile_loop<2, LW>(a.A, a.B, a.A1, a.B1, t, lane, [&](const uint4 &av, const uint4 &bv, const uint2 &ah, const uint2 &bh) {
+                    if ((av.y >> 1) + (bv.y >> 1) > dlim) return;
+                    ++my_pairs;
+                    accumulate(av, bv, ah, bh);
+                });
+            } else {
+                if (lane == 0) my_pairs += (u64)(t.z & 1023u) * ((t.z >> 10) & 127u);
+                block_tile_loop<2, LW>(a.A, a.B, a.A1, a.B1, t, lane, accumulate);
+            }
+        });
+        __syncthreads();
+
+        // ---- emit the slots of the zone in ascending code order: every thread owns a run of consecutive slots (odd
+        // length: conflict-free strided reads), counts its non-zero ones, ONE block scan gives its first output position;
+        // staging space is claimed with one atomicAdd per zone
+        const u32 n_slots = zhi - zlo;
+        const u32 per = ((n_slots + kThreads - 1) / kThreads) | 1u;
+        const u32 e0 = min(n_slots, tid * per), e1 = min(n_slots, e0 + per);
+        u32 nzc = 0;
+        for (u32 e = e0; e < e1; ++e) {
+            u32 any = 0;
+#pragma unroll
+            for (int q = 0; q < NW; ++q) any |= acc[q * a.cap + e];
+            nzc += any != 0;
+        }
+        u32 total;
+        const u32 excl = block_excl_scan(nzc, s_ws, total);
+        if (tid == 0) s_b64[1] = atomicAdd(a.bump, (u64)total);
+        __syncthreads();
+        const u64 zone_base = s_b64[1];
+        u64 pos = zone_base + excl;
+        for (u32 e = e0; e < e1; ++e) {
+            u32 wd[NW], any = 0;
+#pragma unroll
+            for (int q = 0; q < NW; ++q) {
+                wd[q] = acc[q * a.cap + e];
+                acc[q * a.cap + e] = 0;
+                any |= wd[q];
+            }
+            if (any) {
+                zone_emit<NW>(a, pos, zlo + e, wd, my_maxbits, my_flags);
+                ++pos;
+            }
+        }
+        if (tid == 0) {
+            a.zone_count[z] = total;
+            a.zone_off[z] = zone_base;
         }
         __syncthreads();
     }
@@ -1012,61 +1326,38 @@ __global__ void __launch_bounds__(1024, 1) k_block(const BlockArgs ba)
     }
 }
 
-// ------------------------------------------------------------------------------------------------ host side
 
-template <int NW, int PW, int MODE, bool SIGNED, int LW>
-struct BlockKernel {
-    static void set_smem(size_t bytes)
-    {
-        cudaFuncSetAttribute(k_block<NW, PW, MODE, SIGNED, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    }
-    static void launch(pk_ctx *ctx, const BlockArgs &ba, u32 grid, size_t smem)
-    {
-        PK_LAUNCH(ctx, (k_block<NW, PW, MODE, SIGNED, LW>), grid, 1024, smem, ba);
-    }
-};
+
+// ------------------------------------------------------------------------------------------------ host side
 
 // One-limb operands: the (accumulator words, product words) pairs the width bound can ask for:
 // NW = ceil((prod_bits + cnt_bits + 1) / 32) with cnt_bits <= 31, PW = min(4, ceil(prod_bits / 32)).
+#ifdef PK_DEV_WIDTHS // (development builds: the widths of fateman1 / pearce1 only)
+#define PK_BLOCK_WIDTHS(X) X(3, 3)
+#define PK_BLOCK_WIDTHS2(X) X(5, 4)
+#else
 #define PK_BLOCK_WIDTHS(X) X(2, 1) X(2, 2) X(3, 2) X(3, 3) X(4, 3) X(4, 4) X(5, 4) X(6, 4)
 // Two-limb operands (products of 65 .. 256 bits): PW = ceil(prod_bits / 32) and always one more accumulator word (the
 // count bits fit in it), signed accumulation for every sign mix -- fewer instances for the rarer case.
 #define PK_BLOCK_WIDTHS2(X) X(4, 3) X(5, 4) X(6, 5) X(7, 6) X(8, 7) X(9, 8)
+#endif
 
-template <int NW, int PW>
-void block_set_smem_w(size_t b)
-{
-    BlockKernel<NW, PW, 0, false, 1>::set_smem(b);
-    BlockKernel<NW, PW, 0, true, 1>::set_smem(b);
-    BlockKernel<NW, PW, 1, false, 1>::set_smem(b);
-    BlockKernel<NW, PW, 1, true, 1>::set_smem(b);
-}
-
-template <int NW, int PW>
-void block_set_smem_w2(size_t b)
-{
-    BlockKernel<NW, PW, 0, true, 2>::set_smem(b);
-    BlockKernel<NW, PW, 1, true, 2>::set_smem(b);
-}
-
-template <int NW, int PW>
-void block_launch_w(pk_ctx *ctx, const BlockArgs &ba, u32 grid, size_t smem, u32 mode, bool is_signed)
-{
-    if (mode == 0) {
-        if (is_signed) BlockKernel<NW, PW, 0, true, 1>::launch(ctx, ba, grid, smem);
-        else BlockKernel<NW, PW, 0, false, 1>::launch(ctx, ba, grid, smem);
-    } else {
-        if (is_signed) BlockKernel<NW, PW, 1, true, 1>::launch(ctx, ba, grid, smem);
-        else BlockKernel<NW, PW, 1, false, 1>::launch(ctx, ba, grid, smem);
+template <int NW, int PW, bool SIGNED, int LW>
+struct BlockKernels {
+    static void set_smem(size_t bytes)
+    {
+        cudaFuncSetAttribute(k_block_dense<NW, PW, SIGNED, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaFuncSetAttribute(k_block_acc<NW, PW, SIGNED, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     }
-}
-
-template <int NW, int PW>
-void block_launch_w2(pk_ctx *ctx, const BlockArgs &ba, u32 grid, size_t smem, u32 mode)
-{
-    if (mode == 0) BlockKernel<NW, PW, 0, true, 2>::launch(ctx, ba, grid, smem);
-    else BlockKernel<NW, PW, 1, true, 2>::launch(ctx, ba, grid, smem);
-}
+    static void launch_dense(pk_ctx *ctx, const DenseArgs &da, u32 grid, size_t smem)
+    {
+        PK_LAUNCH(ctx, (k_block_dense<NW, PW, SIGNED, LW>), grid, 1024, smem, da);
+    }
+    static void launch_acc(pk_ctx *ctx, const AccArgs &aa, u32 grid, u32 threads, size_t smem)
+    {
+        PK_LAUNCH(ctx, (k_block_acc<NW, PW, SIGNED, LW>), grid, threads, smem, aa);
+    }
+};
 
 inline bool block_width_supported(u32 NW, u32 PW, u32 LW)
 {
@@ -1086,20 +1377,24 @@ inline void block_configure(pk_ctx *ctx)
     t.tile_target = std::max<u32>(32, env_u32("PK_BLOCK_TARGET", t.tile_target));
     t.zone_work = std::max<u32>(1, env_u32("PK_BLOCK_ZONE_WORK", t.zone_work));
     t.force_mode = env_u32("PK_BLOCK_MODE", t.force_mode);
-    t.natural = env_u32("PK_BLOCK_NATURAL", t.natural);
     t.pair_walk = env_u32("PK_BLOCK_PAIR_WALK", t.pair_walk);
     t.wide = env_u32("PK_BLOCK_WIDE", t.wide);
-    t.permute = env_u32("PK_BLOCK_PERMUTE", t.permute);
-    t.hash = env_u32("PK_BLOCK_HASH", t.hash);
     t.smem_limit = env_u32("PK_BLOCK_SMEM", t.smem_limit);
     t.radix0_residue = env_u32("PK_BLOCK_RADIX0", t.radix0_residue);
+    t.unit_codes = env_u32("PK_BLOCK_UNIT_CODES", t.unit_codes);
+    t.zone_products = env_u32("PK_BLOCK_ZONE_PRODUCTS", t.zone_products);
+    t.merge = env_u32("PK_BLOCK_MERGE", t.merge);
+    t.ctas = env_u32("PK_BLOCK_CTAS", t.ctas);
     const size_t dyn = ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0;
-#define X(nw, pw) block_set_smem_w<nw, pw>(dyn);
+#define X(nw, pw)                                 \
+    BlockKernels<nw, pw, false, 1>::set_smem(dyn); \
+    BlockKernels<nw, pw, true, 1>::set_smem(dyn);
     PK_BLOCK_WIDTHS(X)
 #undef X
-#define X(nw, pw) block_set_smem_w2<nw, pw>(dyn);
+#define X(nw, pw) BlockKernels<nw, pw, true, 2>::set_smem(dyn);
     PK_BLOCK_WIDTHS2(X)
 #undef X
+    cudaFuncSetAttribute(k_block_mark, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 << 10);
 }
 
 struct BlockPlan {
@@ -1108,22 +1403,26 @@ struct BlockPlan {
     u32 split = 0; // digits [0, split) form `lo`
     u32 S = 0;     // codes per block
     u32 Hz_max = 1;
+    u32 Hu = 1;    // blocks per zone unit
     u32 cap = 0, bm_words = 0;
-    u32 off_acc = 0, off_bm = 0, off_list = 0, off_keys = 0;
+    u32 off_acc = 0, off_bm = 0, raw_off = 0;
+    u32 ctas = 1;  // sparse: thread blocks per SM of the accumulating kernel (1024 / ctas threads each)
     size_t smem = 0;
 };
 
-inline size_t block_smem_budget(pk_ctx *ctx)
+inline size_t block_smem_budget(pk_ctx *ctx, u32 ctas = 1)
 {
-    size_t budget = ctx->smem_per_sm > 1024 ? ctx->smem_per_sm - 1024 : 0;
+    size_t budget = ctx->smem_per_sm > 1024 * ctas ? (ctx->smem_per_sm - 1024 * ctas) / ctas : 0; // (1 KB per block is the system's)
     budget = std::min(budget, ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0);
     if (ctx->block_tuning.smem_limit) budget = std::min<size_t>(budget, ctx->block_tuning.smem_limit);
     return budget > 1024 ? (budget - 512) & ~255ull : 0; // static shared memory + alignment slack
 }
 
+constexpr u32 kAccBitmapWords = 8192; // sparse zones: at most 2^18 codes per SM (64 KB of {bits, prefix} pairs; 8 words per thread)
+
 // The geometry of the block path for a pair of operands.  A function of the operands (tight radices, widths) and of
-// the device only -- NOT of the output partition -- so every rank of a partitioned product derives the same S and
-// the partition cuts can be rounded to whole blocks consistently.
+// the device only -- NOT of the output partition -- so every rank of a partitioned product derives the same blocks and
+// units and the partition cuts (whole units, decided on the device) agree.
 inline BlockPlan block_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB)
 {
     const BlockTuning &t = ctx->block_tuning;
@@ -1139,34 +1438,34 @@ inline BlockPlan block_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB)
         NW = PW + 1;
     }
     if (!block_width_supported(NW, PW, LW)) return bp;
+    const u32 ctas = t.ctas == 2 ? 2u : 1u;
     const size_t budget = block_smem_budget(ctx);
-    if (budget < (16u << 10)) return bp;
+    if (budget < (96u << 10)) return bp;
     const double W = (double)nA * (double)nB;
     // dense zones when there is at least about one product per three codes, else bitmap zones
     u32 mode = (double)pl.range <= 3.0 * W ? 0u : 1u;
     if (t.force_mode == 1) mode = 0;
     if (t.force_mode == 2) mode = 1;
     const u64 cap_dense = (budget / (NW * 4)) & ~31ull;
-    // bitmap zones: 8 bytes of {bits, prefix} per 32 codes, and room for at least 2048 entries
-    u64 span_bitmap = 1ull << ctx->zone_tuning.span_log2_max;
-    while (span_bitmap > 1024 && span_bitmap / 4 + (size_t)(NW + 1) * 4 * 2048 > budget) span_bitmap >>= 1;
-    const u64 limit = mode == 0 ? cap_dense : span_bitmap;
+    // sparse zones: the bitmap pairs take 64 KB, the accumulators the rest
+    const u64 bm_bytes = (u64)(kAccBitmapWords / ctas) * 8;
+    const u64 cap_sparse = ((block_smem_budget(ctx, ctas) - bm_bytes - 64) / (NW * 4)) & ~31ull;
+    const u64 span_sparse = (u64)(kAccBitmapWords / ctas) * 32 - 256;
     // the largest split whose block still fits; at least one digit must stay in `hi`
-    // (bitmap zones: a block should also hold its entries in one pass -- the products and the codes of a block bound them --
-    // because only multi-block zones can restrict a pass to the tiles of the blocks it covers)
-    const u64 cap_bitmap = (budget / 2 / ((NW + 1) * 4)) & ~31ull;
+    // (sparse zones: a block should also hold its entries in one pass -- the products and the codes of a block bound them)
+    const u64 limit = mode == 0 ? cap_dense : span_sparse / 2;
     u64 S = 1;
     u32 split = 0;
     for (u32 v = 0; v + 1 < pl.n_vars; ++v) {
         const u64 next = S * pl.cpR.tradix[v];
         if (next > limit) break;
-        if (mode == 1 && split >= 1 && std::min(W / ((double)pl.range / (double)next), (double)next) > (double)cap_bitmap) break;
+        if (mode == 1 && split >= 1 && std::min(W / ((double)pl.range / (double)next), (double)next) > (double)cap_sparse / 2) break;
         S = next;
         split = v + 1;
     }
     if (split == 0 || S < 32) return bp;                       // blocks too small to be worth a tile list
     if (pl.range / S > (8u << 20)) return bp;                  // group tables are indexed by hi
-    if (pl.range + 2 * S >= 0xFFFFFFFFull) return bp;          // zone bounds are 32-bit
+    if (pl.range + 2 * S >= 0xFFFFFFFFull) return bp;          // codes are 32-bit
     bp.NW = NW;
     bp.PW = PW;
     bp.LW = LW;
@@ -1175,39 +1474,30 @@ inline BlockPlan block_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB)
     bp.S = (u32)S;
     bp.Hz_max = (u32)std::max<u64>(1, limit / S);
     bp.grid = (u32)ctx->sm_count;
+    bp.ctas = mode == 1 ? ctas : 1u;
     bp.ok = true;
     return bp;
 }
 
-// Shared-memory layout once Hz is known.  Returns false when the zone does not fit.
-inline bool block_layout(pk_ctx *ctx, BlockPlan &bp, u32 Hz)
+// Shared-memory layout of the accumulating kernels.
+inline bool block_layout(pk_ctx *ctx, BlockPlan &bp, u64 unit_codes)
 {
-    const size_t budget = block_smem_budget(ctx);
-    const u64 span = (u64)Hz * bp.S;
+    const size_t budget = block_smem_budget(ctx, bp.ctas);
     const u32 NW = bp.NW;
     size_t off = 0;
     if (bp.mode == 0) {
-        bp.cap = (u32)((span + 31) & ~31ull);
+        bp.cap = (u32)((unit_codes + 31) & ~31ull);
         bp.off_acc = 0;
         off = (size_t)bp.cap * NW * 4;
         bp.bm_words = 0;
     } else {
-        const u64 words = (span + 31) / 32;
-        const size_t bm_bytes = (words * 8 + 15) & ~15ull;
-        if (bm_bytes + (size_t)(NW + 1) * 4 * 64 + 64 > budget) return false;
-        bp.bm_words = (u32)words;
+        bp.bm_words = kAccBitmapWords / bp.ctas;
         bp.off_bm = 0;
-        off = bm_bytes;
-        // per entry: NW accumulator words + one list word (+ one key word of the hash attempt)
-        const u32 per_entry = (NW + 1 + (ctx->block_tuning.hash ? 1u : 0u)) * 4;
-        u64 cap = ((budget - off - 48) / per_entry) & ~31ull;
-        if (!ctx->block_tuning.hash) cap = std::min<u64>(cap, (span + 31) & ~31ull);
-        if (ctx->zone_tuning.force_cap) cap = std::max<u64>(1, std::min<u64>(cap, ctx->zone_tuning.force_cap));
+        bp.raw_off = bp.bm_words * 4; // the upper half of the pair array receives the raw words
+        off = (size_t)bp.bm_words * 8;
+        u64 cap = ((budget - off - 64) / (NW * 4)) & ~31ull;
+        if (ctx->zone_tuning.force_cap) cap = std::max<u64>(32, std::min<u64>(cap, ctx->zone_tuning.force_cap & ~31u));
         bp.cap = (u32)cap;
-        bp.off_list = (u32)off;
-        off += ((size_t)bp.cap * 4 + 15) & ~15ull;
-        bp.off_keys = (u32)off;
-        if (ctx->block_tuning.hash) off += ((size_t)bp.cap * 4 + 15) & ~15ull;
         bp.off_acc = (u32)off;
         off += (size_t)bp.cap * NW * 4;
     }
@@ -1215,12 +1505,60 @@ inline bool block_layout(pk_ctx *ctx, BlockPlan &bp, u32 Hz)
     return off <= budget;
 }
 
-// Returns the product restricted to [lo, hi) (both multiples of S), or nullptr when the operands do not suit the
-// block path (tiny groups); the caller then uses the generic zone path.  parts = number of output partitions the
-// whole product is cut into (this call computes one of them).
+struct BlockDispatch {
+    u32 NW, PW, LW;
+    bool is_signed;
+};
+
+inline void block_launch_dense(pk_ctx *ctx, const BlockDispatch &d, const DenseArgs &da, u32 grid, size_t smem)
+{
+#define X(nw, pw)                                                                       \
+    if (d.LW == 1 && d.NW == nw && d.PW == pw) {                                        \
+        if (d.is_signed) BlockKernels<nw, pw, true, 1>::launch_dense(ctx, da, grid, smem); \
+        else BlockKernels<nw, pw, false, 1>::launch_dense(ctx, da, grid, smem);         \
+    }
+    PK_BLOCK_WIDTHS(X)
+#undef X
+#define X(nw, pw) \
+    if (d.LW == 2 && d.NW == nw && d.PW == pw) BlockKernels<nw, pw, true, 2>::launch_dense(ctx, da, grid, smem);
+    PK_BLOCK_WIDTHS2(X)
+#undef X
+}
+
+inline void block_launch_acc(pk_ctx *ctx, const BlockDispatch &d, const AccArgs &aa, u32 grid, u32 threads, size_t smem)
+{
+#define X(nw, pw)                                                                              \
+    if (d.LW == 1 && d.NW == nw && d.PW == pw) {                                               \
+        if (d.is_signed) BlockKernels<nw, pw, true, 1>::launch_acc(ctx, aa, grid, threads, smem); \
+        else BlockKernels<nw, pw, false, 1>::launch_acc(ctx, aa, grid, threads, smem);         \
+    }
+    PK_BLOCK_WIDTHS(X)
+#undef X
+#define X(nw, pw) \
+    if (d.LW == 2 && d.NW == nw && d.PW == pw) BlockKernels<nw, pw, true, 2>::launch_acc(ctx, aa, grid, threads, smem);
+    PK_BLOCK_WIDTHS2(X)
+#undef X
+}
+
+// grow-only device buffer kept in the context across products (tile list)
+inline void *ctx_tiles_acquire(pk_ctx *ctx, u64 n_tiles)
+{
+    if (ctx->tiles_buf && ctx->tiles_cap >= n_tiles) return ctx->tiles_buf;
+    if (ctx->tiles_buf) cudaFreeAsync(ctx->tiles_buf, ctx->stream);
+    ctx->tiles_buf = nullptr;
+    ctx->tiles_cap = 0;
+    const u64 cap = n_tiles + n_tiles / 4 + 4096;
+    CUDA_CHECK(cudaMallocFromPoolAsync(&ctx->tiles_buf, cap * 16, ctx->pool, ctx->stream));
+    ctx->tiles_cap = cap;
+    return ctx->tiles_buf;
+}
+
+// Returns part `part` of `parts` of the product (ordered ranges of whole zone units, cut on the device at the quantiles
+// of the work), or nullptr when the operands do not suit the block path (tiny groups); the caller then uses the generic
+// zone path.
 inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const pk_dpoly *A, const pk_dpoly *B,
-                                const u64 *keyA, const u64 *keyB, u64 lo, u64 hi, u32 nv, const i64 *degA, const i64 *degB,
-                                i64 max_degree, const uint4 *prepackA, const uint4 *prepackB, u32 parts)
+                                const u64 *keyA, const u64 *keyB, u32 part, u32 parts, u32 nv, const i64 *degA, const i64 *degB,
+                                i64 max_degree, const uint4 *prepackA, const uint4 *prepackB)
 {
     const u64 nA = A->n, nB = B->n;
     const bool trunc = degA != nullptr;
@@ -1243,56 +1581,67 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     }
     const BlockTuning &bt = ctx->block_tuning;
     const u32 S = bp.S;
-    if (lo % S != 0 || (hi % S != 0 && hi != pl.range) || hi <= lo) return nullptr;
-    const u32 h_base = (u32)(lo / S);
-    const u32 n_h = (u32)((hi - lo + S - 1) / S);
     const unsigned __int128 w_bound = (unsigned __int128)nA * nB;
-    const u64 out_cap = (u64)std::min<unsigned __int128>(w_bound, hi - lo);
-    if ((unsigned __int128)out_cap * (9 + 8 * pl.out_limbs) > (unsigned __int128)ctx->total_mem / 2) return nullptr;
+    const u64 HR = pl.range / S + 2; // hi values of the operands and of the result are < HR
 
-    const u64 HR = pl.range / S + 2;
-    // ---- zone geometry: about zone_work products per zone, at least 4 zones per thread block when possible
-    // (an output partition holds about 1 / parts of the products: the cuts are quantiles of sampled pair sums)
-    const double avg_h = (double)w_bound / (double)std::max<u32>(1, parts) / (double)n_h;
-    u64 Hz = (u64)std::max(1.0, (double)bt.zone_work / std::max(1.0, avg_h));
-    Hz = std::min<u64>(Hz, std::max<u64>(1, n_h / (4ull * bp.grid)));
-    if (bp.mode == 1) { // bitmap zones: keep the products of a zone near what one pass of entries holds (measured: pearce1)
-        const double cap_est = (double)(block_smem_budget(ctx) / ((bp.NW + 1) * 4));
-        Hz = std::min<u64>(Hz, (u64)std::max(1.0, cap_est / std::max(1.0, avg_h)));
+    // ---- zone units
+    u64 Hu;
+    if (bp.mode == 0) {
+        // dense: about zone_work products per zone, at least 4 zones per thread block when possible, at most what the
+        // accumulators hold (an output partition holds about 1 / parts of the products)
+        const u64 n_h = (pl.range + S - 1) / S;
+        const double avg_h = (double)w_bound / (double)n_h;
+        Hu = (u64)std::max(1.0, (double)bt.zone_work / std::max(1.0, avg_h));
+        Hu = std::min<u64>(Hu, std::max<u64>(1, n_h / std::max<u32>(1, parts) / (4ull * bp.grid)));
+        Hu = std::max<u64>(1, std::min<u64>(Hu, bp.Hz_max));
+        if (bt.force_hz) Hu = std::max<u64>(1, std::min<u64>(bt.force_hz, bp.Hz_max));
+    } else {
+        // sparse: units of about unit_codes codes -- small next to a zone, so that zones can be cut finely by entries
+        // and work, large enough that a tile's rows span the neighbouring groups of A
+        Hu = std::max<u64>(1, (u64)(bt.unit_codes / bp.ctas) / S);
+        if (bt.force_hz) Hu = bt.force_hz;
+        Hu = std::max<u64>(1, std::min<u64>(Hu, bp.Hz_max));
     }
-    Hz = std::max<u64>(1, std::min<u64>(Hz, bp.Hz_max));
-    if (bt.force_hz) Hz = std::max<u64>(1, std::min<u64>(bt.force_hz, bp.Hz_max));
-    while (!block_layout(ctx, bp, (u32)Hz)) {
-        if (Hz == 1) return nullptr;
-        Hz = (Hz + 1) / 2;
-    }
-    // bitmap zones are cut at equal work (k_block_equal_zones): nq quantiles of at most zone_work products each, at least
-    // 4 per thread block, no zone longer than Hz blocks; dense zones are Hz blocks each.  nz = bound on the zone count.
-    // (measured on pearce1: zones of ~one pass of entries (14 k products) are 20 % SLOWER than zones of 65 k -- a walk
-    // hands out one 512-product tile per warp and round, so a zone needs several rounds to keep 32 warps busy.)
-    // By default only the output partitions of a multi-GPU product use them: a partition starts or ends in the dense
-    // middle of the code range, where zones of Hz blocks are several times heavier than the average zone and the
-    // heaviest-first schedule cannot balance them (pearce1, halves: 0.228 / 0.314 ms with zones of Hz blocks,
-    // 0.210 / 0.232 ms cut at equal work; whole products are within 1 % (pearce1) or 5 % slower (pearce2) and keep Hz).
-    const bool equal_zones = bp.mode == 1 && (bt.equal_zones == 2 || (bt.equal_zones == 1 && parts > 1));
-    u32 nq = 0;
-    if (equal_zones) {
-        const double per_zone = bt.zone_products ? (double)bt.zone_products : (double)bt.zone_work;
-        const double want = (double)w_bound / (double)std::max<u32>(1, parts) / std::max(1.0, per_zone);
-        nq = (u32)std::min<double>(1u << 16, std::max<double>(4.0 * bp.grid, want));
-    }
-    const u32 nz = equal_zones ? nq + (u32)(n_h / Hz) + 2 : (u32)((n_h + Hz - 1) / Hz);
-    // every array that must start at zero lives in ONE allocation cleared by ONE memset: group tables, group counters,
-    // zone bookkeeping, the tile counters of the count pass and the tile cursors of the scatter pass
-    const size_t z_tab = (size_t)HR * 8, z_book = (size_t)nz * 36 + 160, z_cnt = (((size_t)n_h + 1) * 4 + 15) & ~15ull;
-    const size_t zo_tabA = 0, zo_tabB = z_tab, zo_gcnt = 2 * z_tab, zo_book = zo_gcnt + 16, zo_cnt = zo_book + z_book,
-                 zo_cur = zo_cnt + z_cnt, z_total = zo_cur + z_cnt;
+    const u64 U = Hu * S;
+    if (!block_layout(ctx, bp, U)) return nullptr;
+    bp.Hu = (u32)Hu;
+    const u32 n_zu = (u32)((pl.range + U - 1) / U);
+    const u32 zmax = bp.mode == 1 ? (u32)std::max<u64>(1, ((u64)bp.bm_words * 32 - 256) / U) : 1u;
+
+    // every array that must start at zero lives in ONE allocation cleared by ONE memset
+    const size_t z_tab = ((size_t)HR * 8 + 15) & ~15ull, z_geo = 256, z_gcnt = 16, z_cnt = (((size_t)n_zu + 2) * 4 + 15) & ~15ull,
+                 z_prod = ((size_t)n_zu + 2) * 8, z_zc = (((size_t)n_zu + 2) * 4 + 15) & ~15ull;
+    const size_t zo_tabA = 0, zo_tabB = z_tab, zo_geo = 2 * z_tab, zo_gcnt = zo_geo + z_geo, zo_cnt = zo_gcnt + z_gcnt,
+                 zo_cur = zo_cnt + z_cnt, zo_prod = zo_cur + z_cnt, zo_zc = zo_prod + z_prod, zo_bump = zo_zc + z_zc, z_total = zo_bump + 16;
     DevBuf zeroed(ctx, z_total);
     CUDA_CHECK(cudaMemsetAsync(zeroed.p, 0, z_total, ctx->stream));
     char *const zbase = zeroed.as<char>();
     uint2 *const tabA_p = reinterpret_cast<uint2 *>(zbase + zo_tabA), *const tabB_p = reinterpret_cast<uint2 *>(zbase + zo_tabB);
+    BlockGeo *const geo = reinterpret_cast<BlockGeo *>(zbase + zo_geo);
     u32 *const gcnt_p = reinterpret_cast<u32 *>(zbase + zo_gcnt);
     u32 *const cnt_p = reinterpret_cast<u32 *>(zbase + zo_cnt), *const cur_p = reinterpret_cast<u32 *>(zbase + zo_cur);
+    u64 *const prod_p = reinterpret_cast<u64 *>(zbase + zo_prod);
+    u32 *const zone_count = reinterpret_cast<u32 *>(zbase + zo_zc);
+    u64 *const bump = reinterpret_cast<u64 *>(zbase + zo_bump);
+    // not zeroed: written before they are read
+    DevBuf work(ctx, ((size_t)HR + 2) * 8 + (nA + nB) * 8 + ((size_t)n_zu + 2) * (4 + 8 + 4 + 8 + 8 + 4 + 4) + 1024);
+    char *wp = work.as<char>();
+    auto carve = [&](size_t bytes) {
+        char *r = wp;
+        wp += (bytes + 15) & ~15ull;
+        return r;
+    };
+    u32 *const firstA = reinterpret_cast<u32 *>(carve(((size_t)HR + 1) * 4));
+    u32 *const glA = reinterpret_cast<u32 *>(carve(nA * 4)), *const glB = reinterpret_cast<u32 *>(carve(nB * 4));
+    u32 *const codeA = reinterpret_cast<u32 *>(carve(nA * 4)), *const codeB = reinterpret_cast<u32 *>(carve(nB * 4));
+    u32 *const tstart = reinterpret_cast<u32 *>(carve(((size_t)n_zu + 2) * 4));
+    u64 *const pprefix = reinterpret_cast<u64 *>(carve(((size_t)n_zu + 2) * 8));
+    u32 *const entries = reinterpret_cast<u32 *>(carve(((size_t)n_zu + 2) * 4));
+    u32 *const zstart = reinterpret_cast<u32 *>(carve(((size_t)n_zu + 2) * 4));
+    u64 *const zone_off = reinterpret_cast<u64 *>(carve(((size_t)n_zu + 2) * 8));
+    u64 *const zone_prefix = reinterpret_cast<u64 *>(carve(((size_t)n_zu + 2) * 8));
+    u32 *const order = reinterpret_cast<u32 *>(carve(((size_t)n_zu + 2) * 4));
+
     const bool packed = prepackA && prepackB && !trunc;
     DevBuf pa_own(ctx, packed ? 0 : (nA + 1) * 16), pb_own(ctx, packed ? 0 : (nB + 1) * 16), tdev(ctx, trunc ? sizeof(TruncDev) : 0);
     uint4 *const pa_p = packed ? const_cast<uint4 *>(prepackA) : pa_own.as<uint4>();
@@ -1313,18 +1662,16 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
         PK_LAUNCH(ctx, k_pack_operand, grid_for(nA, 256), 256, 0, keyA, A->planes, pa_p, nA);
         PK_LAUNCH(ctx, k_pack_operand, grid_for(nB, 256), 256, 0, keyB, B->planes, pb_p, nB);
     }
-
     phase("pack");
+
     // ---- groups of equal hi
     const u64 magicS = (u64)((((unsigned __int128)1) << 64) / S) + 1;
-    DevBuf glA(ctx, nA * 4), glB(ctx, nB * 4);
-    PK_LAUNCH(ctx, k_block_groups, grid_for(nA, 256), 256, 0, pa_p, (u32)nA, magicS, tabA_p, glA.as<u32>(),
-              gcnt_p, trunc ? gdegA.as<uint2>() : nullptr);
-    PK_LAUNCH(ctx, k_block_groups, grid_for(nB, 256), 256, 0, pb_p, (u32)nB, magicS, tabB_p, glB.as<u32>(),
-              gcnt_p + 1, trunc ? gdegB.as<uint2>() : nullptr);
-    // lanes of a tile on distinct banks: re-order the terms inside every group of B (k_block_permute)
-    const bool permute = bt.permute != 0;
-    DevBuf pb_perm(ctx, permute ? (nB + 1) * 16 : 0), hi_perm(ctx, permute && bp.LW == 2 ? (nB + 1) * 8 : 0), rank_tmp(ctx, permute ? nB * 4 : 0);
+    PK_LAUNCH(ctx, k_block_groups, grid_for(nA, 256), 256, 0, pa_p, (u32)nA, magicS, tabA_p, glA, gcnt_p, codeA,
+              trunc ? gdegA.as<uint2>() : nullptr);
+    PK_LAUNCH(ctx, k_block_groups, grid_for(nB, 256), 256, 0, pb_p, (u32)nB, magicS, tabB_p, glB, gcnt_p + 1, codeB,
+              trunc ? gdegB.as<uint2>() : nullptr);
+    const bool merge = !trunc && bt.merge;
+    if (merge) PK_LAUNCH(ctx, k_block_first, grid_for(HR + 1, 256), 256, 0, pa_p, (u32)nA, S, (u32)HR, firstA);
     DevBuf zero1(ctx, bp.LW == 2 ? std::max(nA, nB) * 8 + 16 : 0);
     const uint2 *hiA = nullptr, *hiB = nullptr;
     if (bp.LW == 2) {
@@ -1334,56 +1681,23 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
         hiA = (pl.LA == 2 && A->limbs >= 2) ? reinterpret_cast<const uint2 *>(A->planes + A->stride) : zero1.as<uint2>();
         hiB = (pl.LB == 2 && B->limbs >= 2) ? reinterpret_cast<const uint2 *>(B->planes + B->stride) : zero1.as<uint2>();
     }
-    const uint4 *pb_use = pb_p;
-    if (permute) {
-        const u32 pgrid = std::min<u32>(grid_for(nB, 64), (u32)ctx->sm_count * 8);
-        PK_LAUNCH(ctx, k_block_permute, pgrid, 256, 0, pb_p, hiB, tabB_p, glB.as<u32>(), gcnt_p + 1,
-                  rank_tmp.as<u32>(), pb_perm.as<uint4>(), hi_perm.as<uint2>());
-        pb_use = pb_perm.as<uint4>();
-        if (bp.LW == 2) hiB = hi_perm.as<uint2>();
-    }
-    u32 *hg = reinterpret_cast<u32 *>(static_cast<char *>(ctx->h_scratch) + 2048);
-    readback(ctx, hg, gcnt_p, 8);
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    const u32 GA = hg[0], GB = hg[1];
     phase("groups");
-    const u64 pairs = (u64)GA * GB;
-    // tiny groups: the tile list would be as long as the product itself
-    if ((unsigned __int128)pairs * bt.min_tile > w_bound || pairs >= (1ull << 31)) return nullptr;
 
-    if (getenv("PK_BLOCK_DEBUG"))
-        fprintf(stderr, "block path: S=%u split=%u n_h=%u Hz=%llu (max %u) zones<=%u mode=%u NW=%u PW=%u cap=%u bm_words=%u smem=%zu GA=%u GB=%u\n",
-                S, bp.split, n_h, (unsigned long long)Hz, bp.Hz_max, nz, bp.mode, bp.NW, bp.PW, bp.cap, bp.bm_words, bp.smem, GA, GB);
-
-    // ---- tile list: count -> scan -> scatter
-    // every chunk of gb (at most nb / 32 + 2 per pair) gives at most 2 * na * width / target + 1 tiles (+ na / 1023 when the
-    // row count per tile hits its 10-bit cap)
-    const u64 max_tiles64 = 2 * (u64)(w_bound / std::min<u32>(bt.tile_target, 512)) + ((u64)GA * nB) / kTileCols + 2 * pairs
-                            + (nB / kTileCols + 2 * (u64)GB) * (nA / 1023 + 1) + 64;
-    if (max_tiles64 >= (1ull << 31)) return nullptr;
-    const u32 max_tiles = (u32)max_tiles64;
-    DevBuf tstart(ctx, ((size_t)n_h + 1) * 4), tiles(ctx, (size_t)max_tiles * 16);
-    // bookkeeping: (spare u64), offsets (u64), prefix (u64) per zone; bump; counters; zone count + order (u32)
-    u64 *zwork = reinterpret_cast<u64 *>(zbase + zo_book);
-    u64 *zone_off = zwork + nz;
-    u64 *zone_prefix = zone_off + nz;
-    u64 *bump = zone_prefix + nz;
-    u32 *chunk_counter = reinterpret_cast<u32 *>(bump + 1);
-    u32 *n_zones_dev = chunk_counter + 1;
-    u32 *n_active_dev = chunk_counter + 2;
-    u32 *zone_count = chunk_counter + 4;
-    u32 *order = zone_count + nz;
-    u32 *zstart = order + nz; // nz + 1 entries
+    // ---- tile list: count -> plan (partition cuts + scan) -> scatter.  The tile buffer lives in the context and grows
+    // when the device reports that the list does not fit (first product of a new size); then the list is built again.
+    if (!ctx->tiles_buf) ctx_tiles_acquire(ctx, (u64)std::min<unsigned __int128>(w_bound / 128 + 65536, 1u << 26));
     TileArgs ta{};
-    ta.glistA = glA.as<u32>();
-    ta.glistB = glB.as<u32>();
+    ta.glistA = glA;
+    ta.glistB = glB;
     ta.tabA = tabA_p;
     ta.tabB = tabB_p;
-    ta.GA = GA;
-    ta.GB = GB;
-    ta.h_base = h_base;
-    ta.n_h = n_h;
-    // (measured: dense zones like 1024-2048 products per tile, bitmap zones 512 -- their tiles are walked twice and the
+    ta.firstA = firstA;
+    ta.gcount = gcnt_p;
+    ta.Hu = (u32)Hu;
+    ta.HR = (u32)HR;
+    ta.n_zu = n_zu;
+    ta.merge = merge ? 1u : 0u;
+    // (measured: dense zones like 1024-2048 products per tile, sparse zones 512 -- their tiles are walked twice and the
     // zones are smaller, so finer tiles balance the warps better)
     ta.target = bp.mode == 1 ? std::min<u32>(bt.tile_target, 512) : bt.tile_target;
     ta.wide = bt.wide;
@@ -1391,101 +1705,264 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     ta.gdegB = trunc ? gdegB.as<uint2>() : nullptr;
     ta.trunc = trunc ? td : nullptr;
     ta.cnt = cnt_p;
-    ta.tstart = tstart.as<u32>();
-    ta.tiles = tiles.as<uint4>();
-    ta.max_tiles = max_tiles;
-    ta.ctr = ctx->d_ctr;
-    const u32 pgrid = grid_for(pairs, 256);
+    ta.prod = prod_p;
+    ta.tstart = tstart;
+    ta.geo = geo;
+    const u32 pgrid = (u32)ctx->sm_count * 8;
     PK_LAUNCH(ctx, (k_block_tiles<0>), pgrid, 256, 0, ta);
-    {
-        size_t tmp_bytes = 0;
-        CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt_p, tstart.as<u32>(), (int)(n_h + 1), ctx->stream));
-        DevBuf tmp(ctx, tmp_bytes);
-        CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, cnt_p, tstart.as<u32>(), (int)(n_h + 1), ctx->stream));
-    }
-    ta.cnt = cur_p; // the scatter pass counts again, into its own zeroed cursors
-    PK_LAUNCH(ctx, (k_block_tiles<1>), pgrid, 256, 0, ta);
-    const bool lpt = !bt.natural && nz <= (1u << 17);
-    if (equal_zones) PK_LAUNCH(ctx, k_block_equal_zones, 1, 1024, 0, tstart.as<u32>(), n_h, (u32)Hz, nq, nz, zstart, n_zones_dev);
-    else if (!lpt) PK_LAUNCH(ctx, k_block_uniform_zones, grid_for((u64)nz + 1, 256), 256, 0, n_h, (u32)Hz, nz, zstart, n_zones_dev);
-    if (lpt)
-        PK_LAUNCH(ctx, k_block_order, 1, 1024, 0, tstart.as<u32>(), zstart, n_zones_dev, order, n_active_dev, n_h,
-                  equal_zones ? 0u : (u32)Hz, equal_zones ? 0u : nz);
-    else PK_LAUNCH(ctx, k_block_natural_order, 1, 1, 0, n_zones_dev, n_active_dev);
 
-    phase("tile list");
-    const StagingView g = staging_acquire(ctx, out_cap, nv, pl.out_limbs);
-    phase("staging");
-    BlockArgs ba{};
-    ZoneArgs &za = ba.z;
-    za.A1 = hiA;
-    za.B1 = hiB;
-    za.A = pa_p;
-    za.nA = (u32)nA;
-    za.B = pb_use;
-    za.nB = (u32)nB;
-    za.lo = (u32)lo;
-    za.hi = (u32)hi;
-    za.cap = bp.cap;
-    za.pw = std::min<u32>(4, (pl.prod_bits + 31) / 32);
-    za.bm_words = bp.bm_words;
-    za.off_acc = bp.off_acc;
-    za.off_bm = bp.off_bm;
-    za.off_list = bp.off_list;
-    za.okey = g.p->key;
-    za.oplanes = g.p->planes;
-    za.ostride = g.p->stride;
-    za.osign = g.p->sign;
-    za.out_limbs = pl.out_limbs;
-    za.out_cap = out_cap;
-    zone_fill_codec(pl, za.cd);
-    za.chunk_counter = chunk_counter;
-    za.zone_count = zone_count;
-    za.zone_off = zone_off;
-    za.bump = bump;
-    za.ctr = ctx->d_ctr;
-    ba.tiles = tiles.as<uint4>();
-    ba.tstart = tstart.as<u32>();
-    ba.order = lpt ? order : nullptr;
-    ba.n_active = n_active_dev;
-    ba.h_base = h_base;
-    ba.n_h = n_h;
-    ba.zstart = zstart;
-    ba.S = S;
-    ba.trunc = trunc ? td : nullptr;
-    ba.off_keys = bp.off_keys;
-    ba.hash = (bp.mode == 1 && bt.hash) ? 1u : 0u;
-    ba.pair_walk = bt.pair_walk;
-    const bool is_signed = A->any_neg || B->any_neg;
-    const u32 grid = std::min<u32>(bp.grid, nz);
-    CUDA_CHECK(cudaEventRecord(ctx->ev_mul0, ctx->stream));
-#define X(nw, pw) \
-    if (bp.LW == 1 && bp.NW == nw && bp.PW == pw) block_launch_w<nw, pw>(ctx, ba, grid, bp.smem, bp.mode, is_signed);
-    PK_BLOCK_WIDTHS(X)
-#undef X
-#define X(nw, pw) \
-    if (bp.LW == 2 && bp.NW == nw && bp.PW == pw) block_launch_w2<nw, pw>(ctx, ba, grid, bp.smem, bp.mode);
-    PK_BLOCK_WIDTHS2(X)
-#undef X
-    CUDA_CHECK(cudaEventRecord(ctx->ev_mul1, ctx->stream));
-    phase("k_block");
-    PK_LAUNCH(ctx, k_zone_scan, 1, 1024, 0, zone_count, zone_prefix, n_zones_dev, &ctx->d_ctr->n_out);
+    BlockGeo *hgeo = reinterpret_cast<BlockGeo *>(static_cast<char *>(ctx->h_scratch) + 2048);
     MulCounters *hc = static_cast<MulCounters *>(ctx->h_scratch);
-    readback(ctx, hc, ctx->d_ctr, sizeof(MulCounters));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    const u64 n_out = hc->n_out;
-    if (getenv("PK_BLOCK_DEBUG")) fprintf(stderr, "block path: %llu of %u zones fell back from the hash attempt\n", (unsigned long long)hc->aux, nz);
-    if (n_out > out_cap || (hc->flags & kFlagTableFull)) fail(PK_E_CUDA, "block path: a count exceeds its bound (internal error)");
+    const bool is_signed = A->any_neg || B->any_neg;
+    const BlockDispatch disp{bp.NW, bp.PW, bp.LW, is_signed || bp.LW == 2};
+    void *gbm_p = nullptr;
+    size_t gbm_bytes = 0;
+    if (bp.mode == 1) { // the bitmap of the code range (range / 8 bytes) lives in the context across products (grow-only)
+        gbm_bytes = ((size_t)(pl.range / 32 + 2 * (U / 32) + 64) * 4 + 255) & ~255ull;
+        if (ctx->bitmap_bytes < gbm_bytes) {
+            if (ctx->bitmap_buf) cudaFreeAsync(ctx->bitmap_buf, ctx->stream);
+            ctx->bitmap_buf = nullptr;
+            ctx->bitmap_bytes = 0;
+            CUDA_CHECK(cudaMallocFromPoolAsync(&ctx->bitmap_buf, gbm_bytes + gbm_bytes / 8, ctx->pool, ctx->stream));
+            ctx->bitmap_bytes = gbm_bytes + gbm_bytes / 8;
+        }
+        gbm_p = ctx->bitmap_buf;
+    }
+
+    StagingView stage{nullptr};
+    for (int attempt = 0;; ++attempt) {
+        PlanArgs pa{};
+        pa.cnt = cnt_p;
+        pa.prod = prod_p;
+        pa.n_zu = n_zu;
+        pa.parts = std::max<u32>(1, parts);
+        pa.part = part;
+        pa.tstart = tstart;
+        pa.pprefix = pprefix;
+        pa.tiles_cap = (u32)std::min<u64>(ctx->tiles_cap, 0x7FFFFFFFull);
+        pa.gcount = gcnt_p;
+        pa.W = (u64)w_bound;
+        pa.min_tile = bt.min_tile;
+        pa.geo = geo;
+        PK_LAUNCH(ctx, k_block_plan, 1, 1024, 0, pa);
+        ta.cnt = cur_p; // the scatter pass counts again, into its own zeroed cursors
+        ta.tiles = static_cast<uint4 *>(ctx->tiles_buf);
+        ta.tiles_cap = pa.tiles_cap;
+        PK_LAUNCH(ctx, (k_block_tiles<1>), pgrid, 256, 0, ta);
+        phase("tile list");
+
+        ZonesArgs za{};
+        za.tstart = tstart;
+        za.pprefix = pprefix;
+        za.zstart = zstart;
+        za.zone_off = zone_off;
+        za.order = order;
+        za.max_zones = n_zu;
+        za.geo = geo;
+        if (bp.mode == 1) {
+            // ---- sparse: mark, then zones by entries and work
+            CUDA_CHECK(cudaMemsetAsync(gbm_p, 0, gbm_bytes, ctx->stream));
+            MarkArgs ma{};
+            ma.A = pa_p;
+            ma.B = pb_p;
+            ma.codeA = codeA;
+            ma.codeB = codeB;
+            ma.tiles = ta.tiles;
+            ma.tstart = tstart;
+            ma.U = (u32)U;
+            ma.range = (u32)pl.range;
+            ma.gbm = static_cast<u32 *>(gbm_p);
+            ma.entries = entries;
+            ma.trunc = trunc ? td : nullptr;
+            ma.geo = geo;
+            const size_t msmem = ((size_t)(U / 32 + 4) * 4 + 15) & ~15ull;
+            const u32 per_sm = (u32)std::max<size_t>(1, std::min<size_t>(16, (ctx->smem_per_sm - 2048) / (msmem + 256)));
+            CUDA_CHECK(cudaEventRecord(ctx->ev_aux0, ctx->stream)); // (the marking walk is pairing work: its time is added to mul_kernel_ms)
+            PK_LAUNCH(ctx, k_block_mark, (u32)ctx->sm_count * per_sm, 128, msmem, ma);
+            CUDA_CHECK(cudaEventRecord(ctx->ev_aux1, ctx->stream));
+            ctx->aux_valid = true;
+            za.entries = entries;
+            za.cap = bp.cap;
+            za.zmax = zmax;
+            const u64 part_products = (u64)(w_bound / std::max<u32>(1, parts));
+            za.zone_products = bt.zone_products ? bt.zone_products : std::max<u64>(1u << 16, part_products / ((u64)bp.grid * bp.ctas * 4));
+            PK_LAUNCH(ctx, k_block_zones, 1, 1024, 0, za);
+            phase("mark + zones");
+        } else {
+            za.entries = nullptr;
+            PK_LAUNCH(ctx, k_block_zones, 1, 1024, 0, za);
+            stage = staging_acquire(ctx, (u64)std::min<unsigned __int128>(w_bound, pl.range), nv, pl.out_limbs);
+        }
+        if (bp.mode == 1) {
+            // the result size (marked codes) decides the allocation of the result: one read-back
+            readback(ctx, hgeo, geo, sizeof(BlockGeo));
+            CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            phase("size read-back");
+        } else {
+            break; // dense: flags are read together with the counters after the pairing kernel
+        }
+        if (hgeo->flags & kGeoDecline) return nullptr;
+        if (!(hgeo->flags & kGeoTileOverflow)) break;
+        if (attempt) fail(PK_E_CUDA, "block path: the tile list does not fit after growing (internal error)");
+        ctx_tiles_acquire(ctx, hgeo->n_tiles);
+        CUDA_CHECK(cudaMemsetAsync(cur_p, 0, z_cnt, ctx->stream));
+        CUDA_CHECK(cudaMemsetAsync(geo, 0, sizeof(BlockGeo), ctx->stream));
+    }
+
+    ZoneArgs zargs{};
+    zargs.A1 = hiA;
+    zargs.B1 = hiB;
+    zargs.A = pa_p;
+    zargs.nA = (u32)nA;
+    zargs.B = pb_p;
+    zargs.nB = (u32)nB;
+    zargs.cap = bp.cap;
+    zargs.pw = std::min<u32>(4, (pl.prod_bits + 31) / 32);
+    zargs.bm_words = bp.bm_words;
+    zargs.off_acc = bp.off_acc;
+    zargs.off_bm = bp.off_bm;
+    zargs.out_limbs = pl.out_limbs;
+    zone_fill_codec(pl, zargs.cd);
+    zargs.zone_count = zone_count;
+    zargs.zone_off = zone_off;
+    zargs.bump = bump;
+    zargs.ctr = ctx->d_ctr;
     ctx->stats.table_slots = (u64)bp.cap;
     ctx->stats.acc_lanes = bp.NW;
     ctx->stats.chunk_bits = bp.PW; // (block path: 32-bit words of a product = unconditional ATOMS per term product)
     ctx->stats.retries = bp.mode | (1024u << 8);
-    phase("scan + count");
+
+    if (bp.mode == 1) {
+        // ---- sparse: accumulate and emit straight into the result
+        const u64 n_entries = hgeo->entries_total;
+        if (getenv("PK_BLOCK_DEBUG"))
+            fprintf(stderr, "block path (sparse): S=%u split=%u Hu=%llu U=%llu units=%u part units [%u, %u) tiles=%u zones=%u active=%u max_e=%u cap=%u entries=%llu NW=%u PW=%u\n",
+                    S, bp.split, (unsigned long long)Hu, (unsigned long long)U, n_zu, hgeo->zu_lo, hgeo->zu_hi, hgeo->n_tiles, hgeo->n_zones,
+                    hgeo->n_active, hgeo->max_entries, bp.cap, (unsigned long long)n_entries, bp.NW, bp.PW);
+        DPolyGuard res{ctx, new_dpoly(ctx, n_entries, nv, pl.out_limbs)};
+        phase("result alloc");
+        AccArgs aa{};
+        aa.z = zargs;
+        aa.z.okey = res.p->key;
+        aa.z.oplanes = res.p->planes;
+        aa.z.ostride = res.p->stride;
+        aa.z.osign = res.p->sign;
+        aa.z.out_cap = n_entries;
+        aa.tiles = static_cast<uint4 *>(ctx->tiles_buf);
+        aa.tstart = tstart;
+        aa.zstart = zstart;
+        aa.zone_off = zone_off;
+        aa.order = order;
+        aa.gbm = static_cast<u32 *>(gbm_p);
+        aa.zone_count = zone_count;
+        aa.U = (u32)U;
+        aa.range = (u32)pl.range;
+        aa.raw_off = bp.raw_off;
+        aa.trunc = trunc ? td : nullptr;
+        aa.geo = geo;
+        CUDA_CHECK(cudaEventRecord(ctx->ev_mul0, ctx->stream));
+        if (n_entries) {
+            const u32 grid = std::max<u32>(1, std::min<u32>(bp.grid * bp.ctas, hgeo->n_active));
+            block_launch_acc(ctx, disp, aa, grid, 1024u / bp.ctas, bp.smem);
+        }
+        CUDA_CHECK(cudaEventRecord(ctx->ev_mul1, ctx->stream));
+        phase("k_block_acc");
+        // counters + cancellations: one read-back
+        readback(ctx, hc, ctx->d_ctr, sizeof(MulCounters));
+        readback(ctx, hgeo, geo, sizeof(BlockGeo));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        if (hc->flags & kFlagTableFull) fail(PK_E_CUDA, "block path: a count exceeds its bound (internal error)");
+        const u64 zeros = hgeo->zeros;
+        if (zeros == 0) {
+            hc->n_out = n_entries;
+            return res.release();
+        }
+        // coefficients cancelled: the zones are compact but end in gaps; close them (zone order = code order)
+        const u64 n_out = n_entries - zeros;
+        DPolyGuard fin{ctx, new_dpoly(ctx, n_out, nv, pl.out_limbs)};
+        if (n_out) {
+            PK_LAUNCH(ctx, k_zone_scan, 1, 1024, 0, zone_count, zone_prefix, &geo->n_zones, &ctx->d_ctr->n_out);
+            PK_LAUNCH(ctx, k_zone_gather, grid_for(n_out, kGatherPerBlock), 256, 0, zone_count, zone_off, zone_prefix, &geo->n_zones,
+                      res.p->key, res.p->planes, res.p->stride, res.p->sign, fin.p->key, fin.p->planes, fin.p->stride, fin.p->sign,
+                      pl.out_limbs, n_out);
+        }
+        hc->n_out = n_out;
+        phase("compaction");
+        return fin.release();
+    }
+
+    // ---- dense: accumulate into the staging area, then scan + gather
+    DenseArgs da{};
+    da.z = zargs;
+    da.z.okey = stage.p->key;
+    da.z.oplanes = stage.p->planes;
+    da.z.ostride = stage.p->stride;
+    da.z.osign = stage.p->sign;
+    da.z.out_cap = (u64)std::min<unsigned __int128>(w_bound, pl.range);
+    da.tiles = static_cast<uint4 *>(ctx->tiles_buf);
+    da.tstart = tstart;
+    da.order = order;
+    da.U = (u32)U;
+    da.range = (u32)pl.range;
+    da.pair_walk = bt.pair_walk;
+    da.trunc = trunc ? td : nullptr;
+    da.geo = geo;
+    for (int attempt = 0;; ++attempt) {
+        CUDA_CHECK(cudaEventRecord(ctx->ev_mul0, ctx->stream));
+        block_launch_dense(ctx, disp, da, std::min<u32>(bp.grid, n_zu), bp.smem);
+        CUDA_CHECK(cudaEventRecord(ctx->ev_mul1, ctx->stream));
+        phase("k_block_dense");
+        PK_LAUNCH(ctx, k_zone_scan, 1, 1024, 0, zone_count, zone_prefix, &geo->n_zones, &ctx->d_ctr->n_out);
+        readback(ctx, hc, ctx->d_ctr, sizeof(MulCounters));
+        readback(ctx, hgeo, geo, sizeof(BlockGeo));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        if (hgeo->flags & kGeoDecline) return nullptr;
+        if (!(hgeo->flags & kGeoTileOverflow)) break;
+        if (attempt) fail(PK_E_CUDA, "block path: the tile list does not fit after growing (internal error)");
+        // the tile buffer was too small: nothing ran.  Grow it, build the list again, run again.
+        ctx_tiles_acquire(ctx, hgeo->n_tiles);
+        CUDA_CHECK(cudaMemsetAsync(cur_p, 0, z_cnt, ctx->stream));
+        CUDA_CHECK(cudaMemsetAsync(geo, 0, sizeof(BlockGeo), ctx->stream));
+        PlanArgs pa{};
+        pa.cnt = cnt_p;
+        pa.prod = prod_p;
+        pa.n_zu = n_zu;
+        pa.parts = std::max<u32>(1, parts);
+        pa.part = part;
+        pa.tstart = tstart;
+        pa.pprefix = pprefix;
+        pa.tiles_cap = (u32)std::min<u64>(ctx->tiles_cap, 0x7FFFFFFFull);
+        pa.gcount = gcnt_p;
+        pa.W = (u64)w_bound;
+        pa.min_tile = bt.min_tile;
+        pa.geo = geo;
+        PK_LAUNCH(ctx, k_block_plan, 1, 1024, 0, pa);
+        ta.cnt = cur_p;
+        ta.tiles = static_cast<uint4 *>(ctx->tiles_buf);
+        ta.tiles_cap = pa.tiles_cap;
+        PK_LAUNCH(ctx, (k_block_tiles<1>), pgrid, 256, 0, ta);
+        ZonesArgs za{};
+        za.tstart = tstart;
+        za.pprefix = pprefix;
+        za.zstart = zstart;
+        za.zone_off = zone_off;
+        za.order = order;
+        za.max_zones = n_zu;
+        za.geo = geo;
+        PK_LAUNCH(ctx, k_block_zones, 1, 1024, 0, za);
+        da.tiles = static_cast<uint4 *>(ctx->tiles_buf);
+    }
+    const u64 n_out = hc->n_out;
+    if (getenv("PK_BLOCK_DEBUG"))
+        fprintf(stderr, "block path (dense): S=%u split=%u Hu=%llu units=%u part units [%u, %u) tiles=%u zones=%u active=%u cap=%u n_out=%llu NW=%u PW=%u\n",
+                S, bp.split, (unsigned long long)Hu, n_zu, hgeo->zu_lo, hgeo->zu_hi, hgeo->n_tiles, hgeo->n_zones, hgeo->n_active, bp.cap,
+                (unsigned long long)n_out, bp.NW, bp.PW);
+    if (n_out > da.z.out_cap || (hc->flags & kFlagTableFull)) fail(PK_E_CUDA, "block path: a count exceeds its bound (internal error)");
     DPolyGuard e{ctx, new_dpoly(ctx, n_out, nv, pl.out_limbs)};
-    phase("result alloc");
     if (n_out) {
-        PK_LAUNCH(ctx, k_zone_gather, grid_for(n_out, kGatherPerBlock), 256, 0, zone_count, zone_off, zone_prefix, n_zones_dev,
-                  g.p->key, g.p->planes, g.p->stride, g.p->sign, e.p->key, e.p->planes, e.p->stride, e.p->sign, pl.out_limbs, n_out);
+        PK_LAUNCH(ctx, k_zone_gather, grid_for(n_out, kGatherPerBlock), 256, 0, zone_count, zone_off, zone_prefix, &geo->n_zones,
+                  stage.p->key, stage.p->planes, stage.p->stride, stage.p->sign, e.p->key, e.p->planes, e.p->stride, e.p->sign, pl.out_limbs,
+                  n_out);
     }
     phase("gather");
     return e.release();

@@ -51,6 +51,9 @@ struct BlockTuning {
                                   // bitmap scheme (measured slower on pearce1: 0.60 vs 0.39 ms; experiment, off)
     uint32_t smem_limit = 0;      // bytes of shared memory a zone may use (0 = all): what is left over serves as L1
     uint32_t radix0_residue = 0;  // experiment: pad the radix of digit 0 so that radix mod 32 == this (1..32); 0 = off
+    uint32_t unit_codes = 1u << 14; // sparse ranges: codes per zone unit aimed at (a unit is a whole number of blocks)
+    uint32_t ctas = 1;            // sparse ranges: thread blocks per SM of the accumulating kernel (1 x 1024 or 2 x 512 threads)
+    uint32_t merge = 1;           // 1 = a tile's rows span all the groups of A that land in the same zone unit with its group of B
 };
 
 } // namespace pk
@@ -79,7 +82,12 @@ struct pk_ctx {
     uint64_t total_launches = 0;
     uint32_t call_launches = 0;
     cudaEvent_t ev_begin = nullptr, ev_mul0 = nullptr, ev_mul1 = nullptr, ev_end = nullptr;
-    bool ev_valid = false;
+    cudaEvent_t ev_aux0 = nullptr, ev_aux1 = nullptr; // the marking walk of the sparse block path
+    bool ev_valid = false, aux_valid = false;
+    void *tiles_buf = nullptr;  // tile list of the block path, kept across products (grow-only)
+    uint64_t tiles_cap = 0;     // in tiles
+    void *bitmap_buf = nullptr; // sparse block path: bitmap of the code range (k_block_mark -> k_block_acc), grow-only
+    size_t bitmap_bytes = 0;
     void *h_scratch = nullptr; // small pinned read-back area
     pk::MulCounters *d_ctr = nullptr;
     pk::MetaDev *d_meta = nullptr;

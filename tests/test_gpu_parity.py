@@ -295,6 +295,12 @@ def _variant_case(case):
     dict(block_mode=2, block_hash=0, block_hz=3, zone_cap=37),
     dict(block_mode=2, block_hash=1, zone_cap=64),         # hash attempts that run out of probes and fall back
     dict(block_mode=2, block_hash=1, block_hz=1000000),
+    dict(block_mode=2, block_ctas=2),                      # two accumulating blocks of 512 threads per SM
+    dict(block_mode=2, block_ctas=2, block_hz=3, zone_cap=37),
+    dict(block_mode=2, block_merge=0),                     # one tile per pair of groups (no row ranges across groups)
+    dict(block_mode=1, block_merge=0, block_hz=2),
+    dict(block_mode=2, block_unit_codes=64, block_zone_products=100),   # tiny zone units, tiny zones
+    dict(block_mode=2, block_unit_codes=1000000, block_zone_products=1000000000),
 ])
 @pytest.mark.parametrize("case", ["pearce", "cancel", "signed"])
 def test_block_variants(tuning, case):

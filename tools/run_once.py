@@ -36,6 +36,8 @@ def main():
               f"NW={st['acc_lanes']} cap={st['table_slots']} R={st['result_terms']} launches={st['kernel_launches']} "
               f"kernel_ms min {min(ks):.4f} med {statistics.median(ks):.4f}  device_ms min {min(ds):.4f} med {statistics.median(ds):.4f}  "
               f"-> {W / min(ks) / 1e6:.1f} G products/s (kernel)  digest {r.digest():016x}", flush=True)
+        if os.environ.get("PK_ONCE_ALL"):
+            print("   device_ms:", " ".join(f"{x:.3f}" for x in ds), flush=True)
         ctx.close()
 
 if __name__ == "__main__":
