@@ -67,7 +67,8 @@ void compute_meta(pk_ctx *ctx, pk_dpoly *p, const i64 *key, const u64 *mag, cons
         p->egcd[v] = m->egcd[v];
     }
     p->max_bits = m->max_bits;
-    p->any_neg = m->any_neg != 0;
+    p->any_neg = (m->any_neg & 1u) != 0;
+    p->any_zero = (m->any_neg & 2u) != 0;
     p->has_meta = true;
 }
 

@@ -29,6 +29,8 @@
 
 #include <chrono>
 
+#include <cooperative_groups.h>
+
 #include "pk_zone.cuh"
 
 namespace pk
@@ -310,95 +312,142 @@ struct PlanArgs {
     BlockGeo *geo;
 };
 
-// The plan of one call, decided on the device (one block): the output partition [zu_lo, zu_hi) -- cut at the quantiles
-// part / parts and (part + 1) / parts of the per-unit product counts, so every rank of a partitioned product derives
-// the same cuts and every product is done by exactly one rank --, the exclusive scan of the tile counts over the
-// partition, and the checks that make the host repeat or decline (tile buffer too small, groups too small).
-// The arrays are walked in chunks of 4096 units, four consecutive units per thread (coalesced), one block scan per chunk.
-__global__ void __launch_bounds__(1024) k_block_plan(const PlanArgs a)
+constexpr u32 kPlanThreads = 256;
+constexpr u32 kPlanMaxBlocks = 1024;
+
+// sum of one value per thread over the block (256 threads); every thread gets the total.  ws: >= 33 u64 of smem.
+__device__ __forceinline__ u64 block_sum64(u64 v, u64 *ws)
 {
+    u64 total;
+    block_excl_scan64(v, ws, total);
+    return total;
+}
+
+// The plan of one call, decided on the device by ONE cooperative launch over all SMs (a single block took 60 us for the
+// 45 k zone units of pearce1): the output partition [zu_lo, zu_hi) -- cut at the quantiles part / parts and (part + 1) /
+// parts of the per-unit product counts, so every rank of a partitioned product derives the same cuts and every product is
+// done by exactly one rank --, the exclusive scans of the tile and product counts over the partition, and the checks that
+// make the host repeat or decline (tile buffer too small, groups too small).
+// Block b owns the units [b * chunk, (b + 1) * chunk).  Phase 1: chunk sums.  Phase 2: the block whose chunk holds a cut
+// finds the unit.  Phase 3: every block writes the prefixes of its units relative to the partition's first unit.
+struct PlanScratch {
+    u64 chunk_prod[kPlanMaxBlocks];
+    u64 chunk_cnt[kPlanMaxBlocks];
+    u32 cut[2];        // zu_lo, zu_hi
+    u32 pad[2];
+    u64 base_prod[2];  // product prefix at the cuts
+    u64 base_cnt[2];   // tile prefix at the cuts
+};
+
+__global__ void __launch_bounds__(kPlanThreads) k_block_plan(const PlanArgs a, PlanScratch *sc)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
     __shared__ u64 s_ws[40];
-    __shared__ u32 s_cut[2];
-    const u32 tid = threadIdx.x;
-    if (tid == 0) {
-        s_cut[0] = 0;
-        s_cut[1] = a.n_zu;
+    const u32 tid = threadIdx.x, G = gridDim.x, b = blockIdx.x;
+    const u32 chunk = (a.n_zu + G - 1) / G;
+    const u32 u0 = min(a.n_zu, b * chunk), u1 = min(a.n_zu, u0 + chunk);
+    // ---- phase 1: chunk sums
+    {
+        u64 ps = 0, cs = 0;
+        for (u32 u = u0 + tid; u < u1; u += kPlanThreads) {
+            ps += a.prod[u];
+            cs += a.cnt[u];
+        }
+        ps = block_sum64(ps, s_ws);
+        cs = block_sum64(cs, s_ws);
+        if (tid == 0) {
+            sc->chunk_prod[b] = ps;
+            sc->chunk_cnt[b] = cs;
+            if (b == 0) {
+                sc->cut[0] = 0;
+                sc->cut[1] = a.n_zu;
+                sc->base_prod[0] = sc->base_cnt[0] = 0;
+            }
+        }
     }
-    // products of the whole range
-    u64 local = 0;
-    for (u32 i = tid; i < a.n_zu; i += 1024u) local += a.prod[i];
-    u64 W_all;
-    block_excl_scan64(local, s_ws, W_all);
+    grid.sync();
+    // prefix of the chunk sums at this block, and the totals
+    u64 my_pp = 0, my_cp = 0, W_all = 0, C_all = 0;
+    {
+        u64 pp = 0, cp = 0, pa = 0, ca = 0;
+        for (u32 j = tid; j < G; j += kPlanThreads) {
+            const u64 pv = sc->chunk_prod[j], cv = sc->chunk_cnt[j];
+            pa += pv;
+            ca += cv;
+            if (j < b) {
+                pp += pv;
+                cp += cv;
+            }
+        }
+        my_pp = block_sum64(pp, s_ws);
+        my_cp = block_sum64(cp, s_ws);
+        W_all = block_sum64(pa, s_ws);
+        C_all = block_sum64(ca, s_ws);
+    }
+    // ---- phase 2: cuts.  Boundary p = the unit whose product interval [exclusive prefix, inclusive prefix) holds
+    // floor(W_all * p / parts); the block whose chunk holds it scans its chunk for the unit.
     if (a.parts > 1) {
-        // boundary p = the unit whose product interval [exclusive prefix, inclusive prefix) holds floor(W_all * p / parts)
-        const u64 T0 = (u64)(((unsigned __int128)W_all * a.part) / a.parts);
-        const u64 T1 = (u64)(((unsigned __int128)W_all * (a.part + 1)) / a.parts);
-        u64 run = 0;
-        for (u32 base = 0; base < a.n_zu; base += 4096u) {
-            const u32 i = base + tid * 4u;
-            u64 v[4], sum = 0;
-#pragma unroll
-            for (u32 k = 0; k < 4; ++k) {
-                v[k] = (i + k < a.n_zu) ? a.prod[i + k] : 0ull;
-                sum += v[k];
-            }
-            u64 total;
-            u64 ex = run + block_excl_scan64(sum, s_ws, total);
-#pragma unroll
-            for (u32 k = 0; k < 4; ++k) {
-                if (v[k]) {
-                    if (a.part > 0 && ex <= T0 && T0 < ex + v[k]) s_cut[0] = i + k;
-                    if (a.part + 1 < a.parts && ex <= T1 && T1 < ex + v[k]) s_cut[1] = i + k;
+        const u64 T[2] = {(u64)(((unsigned __int128)W_all * a.part) / a.parts), (u64)(((unsigned __int128)W_all * (a.part + 1)) / a.parts)};
+        const bool want[2] = {a.part > 0, a.part + 1 < a.parts};
+        const u64 my_end = my_pp + sc->chunk_prod[b];
+        u64 prun = my_pp, crun = my_cp;
+        for (u32 base = u0; base < u1; base += kPlanThreads) {
+            const u32 u = base + tid;
+            const u64 pv = u < u1 ? a.prod[u] : 0, cv = u < u1 ? (u64)a.cnt[u] : 0;
+            u64 ptot, ctot;
+            const u64 pex = prun + block_excl_scan64(pv, s_ws, ptot);
+            const u64 cex = crun + block_excl_scan64(cv, s_ws, ctot);
+            for (int q = 0; q < 2; ++q)
+                if (want[q] && pv && pex <= T[q] && T[q] < pex + pv) {
+                    sc->cut[q] = u;
+                    sc->base_prod[q] = pex;
+                    sc->base_cnt[q] = cex;
                 }
-                ex += v[k];
+            prun += ptot;
+            crun += ctot;
+        }
+        (void)my_end;
+    }
+    if (b == 0 && tid == 0 && !(a.parts > 1 && a.part + 1 < a.parts)) { // the partition runs to the end of the range
+        sc->base_prod[1] = W_all;
+        sc->base_cnt[1] = C_all;
+    }
+    grid.sync();
+    // ---- phase 3: prefixes relative to the partition
+    const u32 zu_lo = sc->cut[0], zu_hi = max(sc->cut[0], sc->cut[1]);
+    const u64 bp0 = sc->base_prod[0], bc0 = sc->base_cnt[0];
+    const u64 n_tiles = (zu_hi > zu_lo) ? sc->base_cnt[1] - bc0 : 0ull, p_part = (zu_hi > zu_lo) ? sc->base_prod[1] - bp0 : 0ull;
+    {
+        u64 prun = my_pp, crun = my_cp;
+        for (u32 base = u0; base < u1; base += kPlanThreads) {
+            const u32 u = base + tid;
+            const u64 pv = u < u1 ? a.prod[u] : 0, cv = u < u1 ? (u64)a.cnt[u] : 0;
+            u64 ptot, ctot;
+            const u64 pex = prun + block_excl_scan64(pv, s_ws, ptot);
+            const u64 cex = crun + block_excl_scan64(cv, s_ws, ctot);
+            if (u < u1 && u >= zu_lo && u < zu_hi) {
+                a.tstart[u - zu_lo] = (u32)min(cex - bc0, (u64)0xFFFFFFFFull);
+                a.pprefix[u - zu_lo] = pex - bp0;
             }
-            run += total;
+            prun += ptot;
+            crun += ctot;
         }
     }
-    __syncthreads();
-    const u32 zu_lo = s_cut[0], zu_hi = max(s_cut[0], s_cut[1]);
-    // tiles and products of the partition: exclusive scans
-    const u32 n = zu_hi - zu_lo;
-    u64 crun = 0, prun = 0;
-    for (u32 base = 0; base < n; base += 4096u) {
-        const u32 j = base + tid * 4u;
-        u64 c[4], v[4], csum = 0, vsum = 0;
-#pragma unroll
-        for (u32 k = 0; k < 4; ++k) {
-            c[k] = (j + k < n) ? (u64)a.cnt[zu_lo + j + k] : 0ull;
-            v[k] = (j + k < n) ? a.prod[zu_lo + j + k] : 0ull;
-            csum += c[k];
-            vsum += v[k];
-        }
-        u64 ctot, vtot;
-        u64 cex = crun + block_excl_scan64(csum, s_ws, ctot);
-        u64 vex = prun + block_excl_scan64(vsum, s_ws, vtot);
-#pragma unroll
-        for (u32 k = 0; k < 4; ++k) {
-            if (j + k < n) {
-                a.tstart[j + k] = (u32)min(cex, (u64)0xFFFFFFFFull);
-                a.pprefix[j + k] = vex;
-            }
-            cex += c[k];
-            vex += v[k];
-        }
-        crun += ctot;
-        prun += vtot;
-    }
-    if (tid == 0) {
-        const bool fits = crun <= (u64)a.tiles_cap && crun <= 0x7FFFFFFFull;
-        a.tstart[n] = (u32)min(crun, (u64)0xFFFFFFFFull);
-        a.pprefix[n] = prun;
+    if (b == 0 && tid == 0) {
+        const u32 n = zu_hi - zu_lo;
+        a.tstart[n] = (u32)min(n_tiles, (u64)0xFFFFFFFFull);
+        a.pprefix[n] = p_part;
         BlockGeo &g = *a.geo;
         g.zu_lo = zu_lo;
         g.zu_hi = zu_hi;
-        g.n_tiles = (u32)min(crun, (u64)0xFFFFFFFFull);
+        g.n_tiles = (u32)min(n_tiles, (u64)0xFFFFFFFFull);
         g.products_all = W_all;
-        g.products_part = prun;
+        g.products_part = p_part;
         const u64 pairs = (u64)a.gcount[0] * a.gcount[1];
         u32 flags = 0;
         if ((unsigned __int128)pairs * a.min_tile > (unsigned __int128)a.W || pairs >= (1ull << 31)) flags |= kGeoDecline;
-        if (!fits) flags |= kGeoTileOverflow;
+        if (n_tiles > (u64)a.tiles_cap || n_tiles > 0x7FFFFFFFull) flags |= kGeoTileOverflow;
         g.flags = flags;
     }
 }
@@ -625,28 +674,26 @@ __device__ __forceinline__ void block_accumulate(u32 saddr0, u32 wstride, const 
     }
 }
 
-// Walk the tiles [t0, t1) with the warps of a block: a warp claims `TB` consecutive tiles with ONE shared-memory atomic
-// (lanes 0..TB-1 load one descriptor each, a shuffle hands them round), so the claim and the descriptors' L2 latency are
-// paid once per TB tiles.  *s_next must hold t0 before the block-wide barrier that precedes the walk.
-template <int TB, typename F>
+// Walk the tiles [*s_next, tend) with the warps of a block: a warp claims its next tile (one shared-memory atomic) and
+// loads that tile's descriptor BEFORE it processes the current one, so the claim and the descriptor's L2 latency hide
+// behind useful work.  *s_next must hold the first tile before the block-wide barrier that precedes the walk.
+template <typename F>
 __device__ __forceinline__ void block_walk_tiles(const uint4 *__restrict__ tiles, u32 s_next_addr, u32 tend, u32 lane, F &&body)
 {
+    u32 k = 0;
+    if (lane == 0) k = atoms_add(s_next_addr, 1u);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    if (k >= tend) return;
+    uint4 t = __ldg(&tiles[k]);
     for (;;) {
-        u32 k0 = 0;
-        if (lane == 0) k0 = atoms_add(s_next_addr, (u32)TB);
-        k0 = __shfl_sync(0xffffffffu, k0, 0);
-        if (k0 >= tend) return;
-        uint4 mine = make_uint4(0u, 0u, 0u, 0u);
-        if (lane < (u32)TB && k0 + lane < tend) mine = __ldg(&tiles[k0 + lane]);
-#pragma unroll
-        for (int j = 0; j < TB; ++j) {
-            uint4 t;
-            t.x = __shfl_sync(0xffffffffu, mine.x, j);
-            t.y = __shfl_sync(0xffffffffu, mine.y, j);
-            t.z = __shfl_sync(0xffffffffu, mine.z, j);
-            t.w = __shfl_sync(0xffffffffu, mine.w, j);
-            if (k0 + (u32)j < tend) body(t);
-        }
+        u32 kn = 0;
+        if (lane == 0) kn = atoms_add(s_next_addr, 1u);
+        kn = __shfl_sync(0xffffffffu, kn, 0);
+        uint4 tn = make_uint4(0u, 0u, 0u, 0u);
+        if (kn < tend) tn = __ldg(&tiles[kn]);
+        body(t);
+        if (kn >= tend) return;
+        t = tn;
     }
 }
 
@@ -666,18 +713,13 @@ __device__ __forceinline__ void block_tile_codes(const u32 *__restrict__ A, cons
         const u32 bv = __ldg(&B[b0 + lane]);
         for (u32 i = 0; i < an; ++i) f(__ldg(&A[a0 + i]), bv);
     } else {
-        const u32 total = an * bn;
-        const float rbn = __frcp_rn((float)bn);
-        const u32 q = (u32)(32.5f * rbn), r = 32u - q * bn;
-        u32 i = (u32)(((float)lane + 0.5f) * rbn), j = lane - i * bn;
-        for (u32 idx = lane; idx < total; idx += 32u) {
-            f(__ldg(&A[a0 + i]), __ldg(&B[b0 + j]));
-            i += q;
-            j += r;
-            if (j >= bn) {
-                j -= bn;
-                ++i;
-            }
+        // ragged chunk (bn < 32 terms): lane l keeps column l % bn in a register and takes rows l / bn, l / bn + R, ...
+        // with R = 32 / bn rows per step -- one load and no index arithmetic per product; lanes beyond R * bn idle
+        const u32 R = 32u / bn;
+        const u32 r = (u32)(((float)lane + 0.5f) * __frcp_rn((float)bn)), j = lane - r * bn;
+        if (r < R) {
+            const u32 bv = __ldg(&B[b0 + j]);
+            for (u32 i = r; i < an; i += R) f(__ldg(&A[a0 + i]), bv);
         }
     }
 }
@@ -702,7 +744,7 @@ struct MarkArgs {
 __global__ void __launch_bounds__(128) k_block_mark(const MarkArgs m)
 {
     extern __shared__ __align__(16) u32 mbm[];
-    __shared__ u32 s_claim, s_red[4];
+    __shared__ u32 s_red[4];
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (m.geo->flags) return;
     const u32 zu_lo = m.geo->zu_lo, n_units = m.geo->zu_hi - zu_lo;
@@ -710,12 +752,9 @@ __global__ void __launch_bounds__(128) k_block_mark(const MarkArgs m)
     const u32 dlim = m.trunc ? __ldg(&m.trunc->dlim) : 0xFFFFFFFFu;
     const u32 bm_s = smem_u32(mbm);
     u32 my_max = 0;
-    for (;;) {
-        if (tid == 0) s_claim = atomicAdd(&m.geo->claim_mark, 1u);
-        __syncthreads();
-        const u32 zr = s_claim;
-        __syncthreads();
-        if (zr >= n_units) break;
+    // units are dealt round robin over the blocks (no claim traffic: the heavy units of the dense middle of the range
+    // are consecutive, so every block gets its share of them)
+    for (u32 zr = blockIdx.x; zr < n_units; zr += gridDim.x) {
         const u32 t0 = __ldg(&m.tstart[zr]), t1 = __ldg(&m.tstart[zr + 1]);
         if (t0 == t1) {
             if (tid == 0) m.entries[zr] = 0;
@@ -727,8 +766,10 @@ __global__ void __launch_bounds__(128) k_block_mark(const MarkArgs m)
         const u32 slot_base = (u32)code_lo + w_first * 32u; // slot = code - slot_base
         for (u32 w = tid; w < nwords; w += 128u) mbm[w] = 0;
         __syncthreads();
-        for (u32 k = t0 + warp; k < t1; k += 4u) { // (static round robin: no claim traffic; tiles are at most ~512 products)
-            const uint4 t = __ldg(&m.tiles[k]);
+        uint4 tnext = (t0 + warp < t1) ? __ldg(&m.tiles[t0 + warp]) : make_uint4(0u, 0u, 0u, 0u);
+        for (u32 k = t0 + warp; k < t1; k += 4u) { // (static round robin over the warps; the next descriptor is loaded ahead)
+            const uint4 t = tnext;
+            if (k + 4u < t1) tnext = __ldg(&m.tiles[k + 4u]);
             if (t.z >> 31) { // truncation: some products of this tile exceed the degree limit
                 block_tile_loop<1, 1>(m.A, m.B, nullptr, nullptr, t, lane, [&](const uint4 &av, const uint4 &bv, const uint2 &, const uint2 &) {
                     if ((av.y >> 1) + (bv.y >> 1) > dlim) return;
@@ -760,6 +801,7 @@ __global__ void __launch_bounds__(128) k_block_mark(const MarkArgs m)
             m.entries[zr] = e;
             my_max = max(my_max, e);
         }
+        __syncthreads();
     }
     if (tid == 0 && my_max) atomicMax(&m.geo->max_entries, my_max);
 }
@@ -778,109 +820,154 @@ struct ZonesArgs {
     BlockGeo *geo;
 };
 
-// Zones of the partition and their order (one block).
+struct ZonesScratch {
+    u64 chunk_w[kPlanMaxBlocks];
+    u64 chunk_e[kPlanMaxBlocks];
+    u32 chunk_s[kPlanMaxBlocks];
+    u32 hist[256], cursor[256]; // counting sort of the zones by work class
+};
+
+// Zones of the partition and their order: ONE cooperative launch over all SMs (block b owns a chunk of consecutive units).
 // DENSE: one zone per unit.  SPARSE: consecutive units are packed into zones by a running weight -- a unit weighs
 // entries / cap' + 1 / zmax + products / zone_products, a zone ends where the prefix of the weights passes the next
 // integer -- so no zone holds more entries than one pass of accumulators takes (cap' = cap minus the largest unit),
 // spans more units than its bitmap covers, or carries much more work than the others; the prefix of the entry counts at
 // a zone's first unit is where its terms go in the result.  Order: heaviest first (LPT) by a counting sort over 256
 // logarithmic classes of the zone's product count; zones without tiles sort last and are never claimed.
-__global__ void __launch_bounds__(1024) k_block_zones(const ZonesArgs a)
+__global__ void __launch_bounds__(kPlanThreads) k_block_zones(const ZonesArgs a, ZonesScratch *sc)
 {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
     __shared__ u64 s_ws[40];
     __shared__ u32 s_ws32[40];
     __shared__ u32 s_hist[256], s_start[256];
-    const u32 tid = threadIdx.x;
+    const u32 tid = threadIdx.x, G = gridDim.x, b = blockIdx.x;
     BlockGeo &g = *a.geo;
-    if (g.flags) {
-        if (tid == 0) g.n_zones = g.n_active = 0;
+    if (g.flags) { // (uniform over the grid: no block reaches a grid barrier)
+        if (b == 0 && tid == 0) g.n_zones = g.n_active = 0;
         return;
     }
     const u32 n = g.zu_hi - g.zu_lo;
     u32 nz = 0;
+    if (b == 0)
+        for (u32 i = tid; i < 256; i += kPlanThreads) sc->hist[i] = sc->cursor[i] = 0; // (read after the grid barriers below)
     if (!a.entries) {
         nz = min(n, a.max_zones);
-        for (u32 z = tid; z <= nz; z += 1024u) a.zstart[z] = z;
-        __syncthreads();
+        for (u32 z = b * kPlanThreads + tid; z <= nz; z += G * kPlanThreads) a.zstart[z] = z;
     } else {
         const u32 max_e = g.max_entries;
         const u64 cap_eff = max((u64)a.cap / 2u, (u64)a.cap - min((u64)a.cap, (u64)max_e)); // entries a zone may collect before its last unit
-        const double ONE = 1048576.0;
-        const double w_entry = ONE / (double)cap_eff, w_unit = ONE / (double)a.zmax, w_prod = ONE / (double)max(a.zone_products, (u64)1);
-        auto weight = [&](u32 i) -> u64 { // (floating point, but the same expression everywhere it is used: cuts are consistent)
-            const double w = ceil((double)a.entries[i] * w_entry) + ceil(w_unit) + floor((double)(a.pprefix[i + 1] - a.pprefix[i]) * w_prod);
-            return (u64)fmin(w, ONE); // (a unit heavier than a zone is a zone of its own)
+        const u64 ONE = 1ull << 20;
+        const u64 fx_e = (ONE << 32) / cap_eff, fx_p = (ONE << 32) / max(a.zone_products, (u64)1), w_unit = (ONE + a.zmax - 1) / a.zmax;
+        auto weight = [&](u32 i) -> u64 { // (fixed point; the same expression in every phase, so the cuts are consistent)
+            const u64 e = a.entries[i], p = min(a.pprefix[i + 1] - a.pprefix[i], (u64)0xFFFFFFFFull);
+            const u64 w = __umul64hi(e << 32, fx_e) + (e ? 1u : 0u) + w_unit + __umul64hi(p << 32, fx_p);
+            return min(w, ONE); // (a unit heavier than a zone is a zone of its own)
         };
-        // chunks of 4096 units, four consecutive units per thread; zone id of a unit = floor(exclusive weight prefix): the
-        // weights of a zone's units except the last sum to < 1
-        u64 wrun = 0, erun = 0;
-        u32 zrun = 0;
-        for (u32 base = 0; base < n; base += 4096u) {
-            const u32 i = base + tid * 4u;
-            u64 w[4], e[4], wsum = 0, esum = 0;
-#pragma unroll
-            for (u32 k = 0; k < 4; ++k) {
-                w[k] = (i + k < n) ? weight(i + k) : 0ull;
-                e[k] = (i + k < n) ? (u64)a.entries[i + k] : 0ull;
-                wsum += w[k];
-                esum += e[k];
+        const u32 chunk = (n + G - 1) / G;
+        const u32 i0 = min(n, b * chunk), i1 = min(n, i0 + chunk);
+        // ---- phase A: chunk sums of the weights and the entries
+        {
+            u64 ws = 0, es = 0;
+            for (u32 i = i0 + tid; i < i1; i += kPlanThreads) {
+                ws += weight(i);
+                es += a.entries[i];
             }
-            u64 wtot, etot;
-            u64 wex = wrun + block_excl_scan64(wsum, s_ws, wtot);
-            u64 eex = erun + block_excl_scan64(esum, s_ws, etot);
-            u32 prev_id = (i > 0 && i < n) ? (u32)((wex - weight(i - 1)) >> 20) : 0xFFFFFFFFu;
-            u32 start[4], starts = 0;
-            {
-                u64 x = wex;
-#pragma unroll
-                for (u32 k = 0; k < 4; ++k) {
-                    const u32 id = (u32)(x >> 20);
-                    start[k] = (i + k < n && id != prev_id) ? 1u : 0u;
-                    starts += start[k];
-                    prev_id = id;
-                    x += w[k];
-                }
+            ws = block_sum64(ws, s_ws);
+            es = block_sum64(es, s_ws);
+            if (tid == 0) {
+                sc->chunk_w[b] = ws;
+                sc->chunk_e[b] = es;
             }
-            u32 stot;
-            u32 zidx = zrun + block_excl_scan(starts, s_ws32, stot);
-#pragma unroll
-            for (u32 k = 0; k < 4; ++k) {
-                if (start[k]) {
-                    if (zidx < a.max_zones) {
-                        a.zstart[zidx] = i + k;
-                        a.zone_off[zidx] = eex;
-                    }
-                    ++zidx;
-                }
-                eex += e[k];
-            }
-            wrun += wtot;
-            erun += etot;
-            zrun += stot;
         }
-        nz = min(zrun, a.max_zones);
-        if (tid == 0) {
+        grid.sync();
+        u64 my_w = 0, my_e = 0, e_all = 0;
+        {
+            u64 wp = 0, ep = 0, ea = 0;
+            for (u32 j = tid; j < G; j += kPlanThreads) {
+                const u64 wv = sc->chunk_w[j], ev = sc->chunk_e[j];
+                ea += ev;
+                if (j < b) {
+                    wp += wv;
+                    ep += ev;
+                }
+            }
+            my_w = block_sum64(wp, s_ws);
+            my_e = block_sum64(ep, s_ws);
+            e_all = block_sum64(ea, s_ws);
+        }
+        // ---- phase B: zone id of a unit = floor(exclusive weight prefix): the weights of a zone's units except the last
+        // sum to < 1.  A unit starts a zone when its id differs from its predecessor's.  Count the starts of the chunk.
+        auto walk = [&](u32 zbase, bool write) -> u32 {
+            u64 wrun = my_w, erun = my_e;
+            u32 zrun = zbase;
+            for (u32 base = i0; base < i1; base += kPlanThreads) {
+                const u32 i = base + tid;
+                const u64 w = i < i1 ? weight(i) : 0ull, e = i < i1 ? (u64)a.entries[i] : 0ull;
+                u64 wtot, etot;
+                const u64 wex = wrun + block_excl_scan64(w, s_ws, wtot);
+                const u64 eex = erun + block_excl_scan64(e, s_ws, etot);
+                u32 start = 0;
+                if (i < i1) {
+                    const u32 id = (u32)(wex >> 20);
+                    const u32 prev_id = i > 0 ? (u32)((wex - weight(i - 1)) >> 20) : 0xFFFFFFFFu;
+                    start = id != prev_id ? 1u : 0u;
+                }
+                u32 stot;
+                const u32 zidx = zrun + block_excl_scan(start, s_ws32, stot);
+                if (write && start && zidx < a.max_zones) {
+                    a.zstart[zidx] = i;
+                    a.zone_off[zidx] = eex;
+                }
+                wrun += wtot;
+                erun += etot;
+                zrun += stot;
+            }
+            return zrun - zbase;
+        };
+        const u32 my_starts = walk(0u, false);
+        if (tid == 0) sc->chunk_s[b] = my_starts;
+        grid.sync();
+        // ---- phase C: zone indices from the prefix of the chunks' start counts; write the zone table
+        u32 zbase = 0, z_all = 0;
+        {
+            u32 sp = 0, sa = 0;
+            for (u32 j = tid; j < G; j += kPlanThreads) {
+                const u32 sv = sc->chunk_s[j];
+                sa += sv;
+                if (j < b) sp += sv;
+            }
+            u32 tot;
+            block_excl_scan(sp, s_ws32, tot);
+            zbase = tot;
+            block_excl_scan(sa, s_ws32, tot);
+            z_all = tot;
+        }
+        walk(zbase, true);
+        nz = min(z_all, a.max_zones);
+        if (b == 0 && tid == 0) {
             a.zstart[nz] = n;
-            a.zone_off[nz] = erun;
-            g.entries_total = erun;
+            a.zone_off[nz] = e_all;
+            g.entries_total = e_all;
         }
-        __syncthreads();
     }
-    // heaviest first
+    grid.sync();
+    // ---- heaviest first: a counting sort over the work classes, all blocks (one zone per thread and round)
     auto zwork_of = [&](u32 z) -> u64 {
         const u32 u0 = a.zstart[z], u1 = a.zstart[z + 1];
         if (a.tstart[u0] == a.tstart[u1]) return 0ull; // no tiles
         return max((u64)1, a.pprefix[u1] - a.pprefix[u0]);
     };
-    for (u32 i = tid; i < 256; i += 1024u) s_hist[i] = 0;
-    __syncthreads();
     auto cls = [](u64 w) -> u32 {
         if (w == 0) return 0u;
         const u32 e = 63u - (u32)__clzll((long long)w);
         const u32 m = e >= 2 ? (u32)(w >> (e - 2)) & 3u : 0u;
         return min(255u, 4u * e + m + 1u);
     };
-    for (u32 z = tid; z < nz; z += 1024u) atomicAdd(&s_hist[cls(zwork_of(z))], 1u);
+    const u32 stride = G * kPlanThreads;
+    for (u32 z = b * kPlanThreads + tid; z < nz; z += stride) atomicAdd(&sc->hist[cls(zwork_of(z))], 1u);
+    grid.sync();
+    for (u32 i = tid; i < 256; i += kPlanThreads) s_hist[i] = sc->hist[i];
     __syncthreads();
     if (tid == 0) {
         u32 run = 0;
@@ -888,14 +975,17 @@ __global__ void __launch_bounds__(1024) k_block_zones(const ZonesArgs a)
             s_start[c] = run;
             run += s_hist[c];
         }
-        g.n_zones = nz;
-        g.n_active = nz - s_hist[0];
+        if (b == 0) {
+            g.n_zones = nz;
+            g.n_active = nz - s_hist[0];
+        }
     }
     __syncthreads();
-    for (u32 z = tid; z < nz; z += 1024u) a.order[atomicAdd(&s_start[cls(zwork_of(z))], 1u)] = z;
+    for (u32 z = b * kPlanThreads + tid; z < nz; z += stride) {
+        const u32 c = cls(zwork_of(z));
+        a.order[s_start[c] + atomicAdd(&sc->cursor[c], 1u)] = z;
+    }
 }
-
-
 
 // Product of two operand records -> 32-bit words of the magnitude (pw[0..8))
 template <int LW>
@@ -927,6 +1017,7 @@ struct AccArgs {
     u32 U;                 // codes per zone unit
     u32 range;
     u32 raw_off;           // byte offset in dynamic shared memory of the landing area of the raw bitmap words
+    u32 nozero;            // 1 = no coefficient can be zero (no negative and no zero operand coefficients): every marked code is a term
     const TruncDev *trunc;
     BlockGeo *geo;
 };
@@ -963,6 +1054,9 @@ __global__ void __launch_bounds__(1024, 1) k_block_acc(const AccArgs aa)
     const u32 wstride = a.cap * 4u;
     u64 my_pairs = 0;
     u32 my_maxbits = 0, my_flags = 0;
+    u32 my_orw[NW];
+#pragma unroll
+    for (int q = 0; q < NW; ++q) my_orw[q] = 0;
     if (aa.geo->flags) return;
     const u32 n_active = aa.geo->n_active;
     const u32 zu_lo = aa.geo->zu_lo;
@@ -1075,7 +1169,7 @@ __global__ void __launch_bounds__(1024, 1) k_block_acc(const AccArgs aa)
                 block_product_words<LW>(av, bv, ah, bh, pw);
                 block_accumulate<NW, PW, SIGNED>(acc_s + e * 4u, wstride, pw, SIGNED && (((av.y ^ bv.y) & 1u) != 0));
             };
-            block_walk_tiles<1>(aa.tiles, next_s, tp1, lane, [&](const uint4 &t) {
+            block_walk_tiles(aa.tiles, next_s, tp1, lane, [&](const uint4 &t) {
                 if (t.z >> 31) { // truncation: test the degree of every product of this tile
                     block_tile_loop<2, LW>(a.A, a.B, a.A1, a.B1, t, lane, [&](const uint4 &av, const uint4 &bv, const uint2 &ah, const uint2 &bh) {
                         if ((av.y >> 1) + (bv.y >> 1) > dlim) return;
@@ -1102,15 +1196,17 @@ __global__ void __launch_bounds__(1024, 1) k_block_acc(const AccArgs aa)
             const u32 n_pass = r1 - r0;
             const u32 per = ((n_pass + kThreads - 1) / kThreads) | 1u;
             const u32 e0 = min(n_pass, tid * per), e1 = min(n_pass, e0 + per);
-            u32 nzc = 0;
-            for (u32 e = e0; e < e1; ++e) {
-                u32 any = 0;
+            u32 ptotal = n_pass, excl = e0;
+            if (!aa.nozero) { // coefficients may cancel: positions follow from the count of the non-zero ones
+                u32 nzc = 0;
+                for (u32 e = e0; e < e1; ++e) {
+                    u32 any = 0;
 #pragma unroll
-                for (int q = 0; q < NW; ++q) any |= acc[q * a.cap + e];
-                nzc += any != 0;
+                    for (int q = 0; q < NW; ++q) any |= acc[q * a.cap + e];
+                    nzc += any != 0;
+                }
+                excl = block_excl_scan(nzc, s_ws, ptotal);
             }
-            u32 ptotal;
-            const u32 excl = block_excl_scan(nzc, s_ws, ptotal);
             if (e0 < e1) {
                 // the code of rank r0 + e0: first word whose inclusive prefix exceeds it, then the set bits in order
                 const u32 target = r0 + e0;
@@ -1153,7 +1249,10 @@ __global__ void __launch_bounds__(1024, 1) k_block_acc(const AccArgs aa)
                         any |= wd[q];
                     }
                     if (any) {
-                        zone_emit<NW>(a, pos, slot_base + w * 32u + b, wd, my_maxbits, my_flags);
+                        // (measured: stepping the key from the previous code of the run -- KeyWalker -- saves instructions but
+                        // splits the warp between the lanes that carry out of digit 0 and those that do not; a full decode per
+                        // term keeps the lanes together and is as fast)
+                        zone_emit_key<NW, SIGNED>(a, pos, zone_code_to_piranha(slot_base + w * 32u + b, a.cd), wd, my_orw, my_flags);
                         ++pos;
                     }
                 }
@@ -1168,6 +1267,7 @@ __global__ void __launch_bounds__(1024, 1) k_block_acc(const AccArgs aa)
             if (zone_written != n_entries) atomicAdd(&aa.geo->zeros, (u64)(n_entries - zone_written));
         }
     }
+    my_maxbits = zone_maxbits<NW>(my_orw);
     for (int o = 16; o > 0; o >>= 1) {
         my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, o);
         my_maxbits = max(my_maxbits, __shfl_xor_sync(0xffffffffu, my_maxbits, o));
@@ -1255,7 +1355,7 @@ __global__ void __launch_bounds__(1024, 1) k_block_dense(const DenseArgs da)
             block_accumulate2<NW, (PW < 4 ? PW : 4), SIGNED>(acc_s + e0 * 4u, p0, SIGNED && (((av0.y ^ bv0.y) & 1u) != 0), true,
                                                              acc_s + e1 * 4u, p1, SIGNED && (((av1.y ^ bv1.y) & 1u) != 0), on1, wstride);
         };
-        block_walk_tiles<2>(da.tiles, next_s, t1, lane, [&](const uint4 &t) {
+        block_walk_tiles(da.tiles, next_s, t1, lane, [&](const uint4 &t) {
             // (measured: fateman2, five-word chains, 3.63 -> 3.43 ms; fateman1 unchanged; degree-tested tiles 30 % slower,
             // so only the untested tiles take the pair walk)
             if (LW == 1 && da.pair_walk && !(t.z >> 31)) {
@@ -1304,7 +1404,7 @@ __global__ void __launch_bounds__(1024, 1) k_block_dense(const DenseArgs da)
                 any |= wd[q];
             }
             if (any) {
-                zone_emit<NW>(a, pos, zlo + e, wd, my_maxbits, my_flags);
+                zone_emit<NW, SIGNED>(a, pos, zlo + e, wd, my_maxbits, my_flags);
                 ++pos;
             }
         }
@@ -1438,7 +1538,6 @@ inline BlockPlan block_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB)
         NW = PW + 1;
     }
     if (!block_width_supported(NW, PW, LW)) return bp;
-    const u32 ctas = t.ctas == 2 ? 2u : 1u;
     const size_t budget = block_smem_budget(ctx);
     if (budget < (96u << 10)) return bp;
     const double W = (double)nA * (double)nB;
@@ -1447,22 +1546,41 @@ inline BlockPlan block_plan(pk_ctx *ctx, const Plan &pl, u64 nA, u64 nB)
     if (t.force_mode == 1) mode = 0;
     if (t.force_mode == 2) mode = 1;
     const u64 cap_dense = (budget / (NW * 4)) & ~31ull;
-    // sparse zones: the bitmap pairs take 64 KB, the accumulators the rest
-    const u64 bm_bytes = (u64)(kAccBitmapWords / ctas) * 8;
-    const u64 cap_sparse = ((block_smem_budget(ctx, ctas) - bm_bytes - 64) / (NW * 4)) & ~31ull;
-    const u64 span_sparse = (u64)(kAccBitmapWords / ctas) * 32 - 256;
     // the largest split whose block still fits; at least one digit must stay in `hi`
-    // (sparse zones: a block should also hold its entries in one pass -- the products and the codes of a block bound them)
-    const u64 limit = mode == 0 ? cap_dense : span_sparse / 2;
+    // (sparse zones: the bitmap pairs take 64 KB per SM, the accumulators the rest, shared by `ctas` thread blocks; a block
+    // of codes should also hold its entries in one pass -- the products and the codes of a block bound them)
+    auto split_for = [&](u32 ctas, u64 &S_out) -> u32 {
+        const u64 bm_bytes = (u64)(kAccBitmapWords / ctas) * 8;
+        const u64 cap_sparse = ((block_smem_budget(ctx, ctas) - bm_bytes - 64) / (NW * 4)) & ~31ull;
+        const u64 span_sparse = (u64)(kAccBitmapWords / ctas) * 32 - 256;
+        const u64 limit = mode == 0 ? cap_dense : span_sparse / 2;
+        u64 S = 1;
+        u32 split = 0;
+        for (u32 v = 0; v + 1 < pl.n_vars; ++v) {
+            const u64 next = S * pl.cpR.tradix[v];
+            if (next > limit) break;
+            if (mode == 1 && split >= 1 && std::min(W / ((double)pl.range / (double)next), (double)next) > (double)cap_sparse / 2) break;
+            S = next;
+            split = v + 1;
+        }
+        S_out = S;
+        return split;
+    };
+    // several accumulating thread blocks per SM overlap each other's barrier phases, but each gets a smaller share of the
+    // shared memory: take the most blocks per SM that still allow the split one block per SM would get
     u64 S = 1;
-    u32 split = 0;
-    for (u32 v = 0; v + 1 < pl.n_vars; ++v) {
-        const u64 next = S * pl.cpR.tradix[v];
-        if (next > limit) break;
-        if (mode == 1 && split >= 1 && std::min(W / ((double)pl.range / (double)next), (double)next) > (double)cap_sparse / 2) break;
-        S = next;
-        split = v + 1;
+    u32 split = split_for(1u, S), ctas = 1u;
+    if (mode == 1) {
+        for (u32 c = (t.ctas == 4 ? 4u : (t.ctas == 2 ? 2u : 1u)); c > 1u; c >>= 1) {
+            u64 Sc = 1;
+            if (split_for(c, Sc) == split) {
+                ctas = c;
+                S = Sc;
+                break;
+            }
+        }
     }
+    const u64 limit = mode == 0 ? cap_dense : ((u64)(kAccBitmapWords / ctas) * 32 - 256) / 2;
     if (split == 0 || S < 32) return bp;                       // blocks too small to be worth a tile list
     if (pl.range / S > (8u << 20)) return bp;                  // group tables are indexed by hi
     if (pl.range + 2 * S >= 0xFFFFFFFFull) return bp;          // codes are 32-bit
@@ -1538,6 +1656,17 @@ inline void block_launch_acc(pk_ctx *ctx, const BlockDispatch &d, const AccArgs 
     if (d.LW == 2 && d.NW == nw && d.PW == pw) BlockKernels<nw, pw, true, 2>::launch_acc(ctx, aa, grid, threads, smem);
     PK_BLOCK_WIDTHS2(X)
 #undef X
+}
+
+// cooperative launch (grid-wide barriers inside the kernel): every block must be resident, so the grid is at most one
+// block per SM
+template <typename... KArgs, typename... Args>
+inline void launch_coop(pk_ctx *ctx, void (*kernel)(KArgs...), u32 grid, u32 block, Args... args)
+{
+    void *argv[] = {(void *)&args...};
+    CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)kernel, dim3(grid), dim3(block), argv, 0, ctx->stream));
+    ++ctx->call_launches;
+    ++ctx->total_launches;
 }
 
 // grow-only device buffer kept in the context across products (tile list)
@@ -1624,7 +1753,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     u32 *const zone_count = reinterpret_cast<u32 *>(zbase + zo_zc);
     u64 *const bump = reinterpret_cast<u64 *>(zbase + zo_bump);
     // not zeroed: written before they are read
-    DevBuf work(ctx, ((size_t)HR + 2) * 8 + (nA + nB) * 8 + ((size_t)n_zu + 2) * (4 + 8 + 4 + 8 + 8 + 4 + 4) + 1024);
+    DevBuf work(ctx, ((size_t)HR + 2) * 8 + (nA + nB) * 8 + ((size_t)n_zu + 2) * (4 + 8 + 4 + 8 + 8 + 4 + 4) + sizeof(PlanScratch) + sizeof(ZonesScratch) + 1024);
     char *wp = work.as<char>();
     auto carve = [&](size_t bytes) {
         char *r = wp;
@@ -1641,6 +1770,9 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     u64 *const zone_off = reinterpret_cast<u64 *>(carve(((size_t)n_zu + 2) * 8));
     u64 *const zone_prefix = reinterpret_cast<u64 *>(carve(((size_t)n_zu + 2) * 8));
     u32 *const order = reinterpret_cast<u32 *>(carve(((size_t)n_zu + 2) * 4));
+    PlanScratch *const plan_sc = reinterpret_cast<PlanScratch *>(carve(sizeof(PlanScratch)));
+    ZonesScratch *const zones_sc = reinterpret_cast<ZonesScratch *>(carve(sizeof(ZonesScratch)));
+    const u32 coop_grid = std::max<u32>(1, std::min<u32>({(u32)ctx->sm_count, kPlanMaxBlocks, (n_zu + kPlanThreads - 1) / kPlanThreads}));
 
     const bool packed = prepackA && prepackB && !trunc;
     DevBuf pa_own(ctx, packed ? 0 : (nA + 1) * 16), pb_own(ctx, packed ? 0 : (nB + 1) * 16), tdev(ctx, trunc ? sizeof(TruncDev) : 0);
@@ -1744,7 +1876,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
         pa.W = (u64)w_bound;
         pa.min_tile = bt.min_tile;
         pa.geo = geo;
-        PK_LAUNCH(ctx, k_block_plan, 1, 1024, 0, pa);
+        launch_coop(ctx, k_block_plan, coop_grid, kPlanThreads, pa, plan_sc);
         ta.cnt = cur_p; // the scatter pass counts again, into its own zeroed cursors
         ta.tiles = static_cast<uint4 *>(ctx->tiles_buf);
         ta.tiles_cap = pa.tiles_cap;
@@ -1786,11 +1918,11 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
             za.zmax = zmax;
             const u64 part_products = (u64)(w_bound / std::max<u32>(1, parts));
             za.zone_products = bt.zone_products ? bt.zone_products : std::max<u64>(1u << 16, part_products / ((u64)bp.grid * bp.ctas * 4));
-            PK_LAUNCH(ctx, k_block_zones, 1, 1024, 0, za);
+            launch_coop(ctx, k_block_zones, coop_grid, kPlanThreads, za, zones_sc);
             phase("mark + zones");
         } else {
             za.entries = nullptr;
-            PK_LAUNCH(ctx, k_block_zones, 1, 1024, 0, za);
+            launch_coop(ctx, k_block_zones, coop_grid, kPlanThreads, za, zones_sc);
             stage = staging_acquire(ctx, (u64)std::min<unsigned __int128>(w_bound, pl.range), nv, pl.out_limbs);
         }
         if (bp.mode == 1) {
@@ -1858,6 +1990,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
         aa.U = (u32)U;
         aa.range = (u32)pl.range;
         aa.raw_off = bp.raw_off;
+        aa.nozero = (!disp.is_signed && !A->any_zero && !B->any_zero) ? 1u : 0u;
         aa.trunc = trunc ? td : nullptr;
         aa.geo = geo;
         CUDA_CHECK(cudaEventRecord(ctx->ev_mul0, ctx->stream));
@@ -1936,7 +2069,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
         pa.W = (u64)w_bound;
         pa.min_tile = bt.min_tile;
         pa.geo = geo;
-        PK_LAUNCH(ctx, k_block_plan, 1, 1024, 0, pa);
+        launch_coop(ctx, k_block_plan, coop_grid, kPlanThreads, pa, plan_sc);
         ta.cnt = cur_p;
         ta.tiles = static_cast<uint4 *>(ctx->tiles_buf);
         ta.tiles_cap = pa.tiles_cap;
@@ -1949,7 +2082,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
         za.order = order;
         za.max_zones = n_zu;
         za.geo = geo;
-        PK_LAUNCH(ctx, k_block_zones, 1, 1024, 0, za);
+        launch_coop(ctx, k_block_zones, coop_grid, kPlanThreads, za, zones_sc);
         da.tiles = static_cast<uint4 *>(ctx->tiles_buf);
     }
     const u64 n_out = hc->n_out;

@@ -51,8 +51,9 @@ struct BlockTuning {
                                   // bitmap scheme (measured slower on pearce1: 0.60 vs 0.39 ms; experiment, off)
     uint32_t smem_limit = 0;      // bytes of shared memory a zone may use (0 = all): what is left over serves as L1
     uint32_t radix0_residue = 0;  // experiment: pad the radix of digit 0 so that radix mod 32 == this (1..32); 0 = off
-    uint32_t unit_codes = 1u << 14; // sparse ranges: codes per zone unit aimed at (a unit is a whole number of blocks)
-    uint32_t ctas = 1;            // sparse ranges: thread blocks per SM of the accumulating kernel (1 x 1024 or 2 x 512 threads)
+    uint32_t unit_codes = 1u << 15; // sparse ranges: codes per zone unit aimed at, times the blocks per SM (a unit is a whole number of blocks)
+    uint32_t ctas = 4;            // sparse ranges: thread blocks per SM of the accumulating kernel (1 x 1024, 2 x 512 or 4 x 256 threads;
+                                  // measured on pearce1: 0.42 / 0.34 / 0.32 ms -- while one block emits or waits at a barrier the others walk)
     uint32_t merge = 1;           // 1 = a tile's rows span all the groups of A that land in the same zone unit with its group of B
 };
 
@@ -120,6 +121,7 @@ struct pk_dpoly {
     std::vector<uint64_t> egcd;
     uint32_t max_bits = 0;
     bool any_neg = false;
+    bool any_zero = false;      // some coefficient is zero (accepted on upload, contributes nothing; results never hold one)
     std::mutex meta_mutex; // has_meta and the fields above are filled lazily (results of pk_mul_dev): guarded
     // multi-device polynomial (created through a multi-device context): rep[d] = full replica on device d (nullptr = not
     // materialised), part[r] = the ordered parts of a partitioned product (part r lives on device r); n = total terms

@@ -154,7 +154,9 @@ __global__ void k_meta(const i64 *__restrict__ key, const u64 *__restrict__ plan
             if (m) bits = 64u * l + bitlen64(m);
         }
         if (bits > s_bits) atomicMax(&s_bits, bits);
-        if (sign[i] < 0 && bits && !*((volatile u32 *)&meta->any_neg)) atomicOr(&meta->any_neg, 1u);
+        // bit 0: some coefficient is negative; bit 1: some coefficient is zero (sign 0 or zero magnitude)
+        const u32 flag = (bits == 0u || sign[i] == 0) ? 2u : (sign[i] < 0 ? 1u : 0u);
+        if (flag && (*((volatile u32 *)&meta->any_neg) & flag) == 0u) atomicOr(&meta->any_neg, flag);
     }
     __syncthreads();
     for (u32 v = threadIdx.x; v < cp.n_vars; v += blockDim.x) {

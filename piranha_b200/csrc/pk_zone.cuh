@@ -155,12 +155,13 @@ __device__ __forceinline__ i64 zone_code_to_piranha(u32 code, const ZoneCodec &c
     return out;
 }
 
-// Two's complement NW words -> sign, magnitude; writes the term at `pos`.
-template <int NW>
-__device__ __forceinline__ void zone_emit(const ZoneArgs &a, u64 pos, u32 code, const u32 (&wd)[NW], u32 &maxbits, u32 &flags)
+// Two's complement NW words -> sign, magnitude; writes the term with Kronecker code `key` at `pos`.  SIGNED = false: the
+// accumulator cannot be negative (operands without negative coefficients).
+template <int NW, bool SIGNED = true>
+__device__ __forceinline__ void zone_emit_key(const ZoneArgs &a, u64 pos, i64 key, const u32 (&wd)[NW], u32 (&orw)[NW], u32 &flags)
 {
     u32 m[NW];
-    const bool neg = (wd[NW - 1] >> 31) != 0;
+    const bool neg = SIGNED && (wd[NW - 1] >> 31) != 0;
     if (neg) {
         u32 carry = 1;
 #pragma unroll
@@ -177,19 +178,91 @@ __device__ __forceinline__ void zone_emit(const ZoneArgs &a, u64 pos, u32 code, 
         flags |= kFlagTableFull;
         return;
     }
-    u32 bits = 0;
 #pragma unroll
     for (int l = 0; l < (NW + 1) / 2; ++l) {
         const u64 limb = (u64)m[2 * l] | ((2 * l + 1 < NW) ? ((u64)m[(2 * l + 1 < NW) ? 2 * l + 1 : 0] << 32) : 0ull);
         if ((u32)l < a.out_limbs) a.oplanes[(u64)l * a.ostride + pos] = limb;
         else if (limb) flags |= kFlagWidth;
-        if (limb) bits = 64u * l + bitlen64(limb);
     }
     for (u32 l = (NW + 1) / 2; l < a.out_limbs; ++l) a.oplanes[(u64)l * a.ostride + pos] = 0;
-    a.okey[pos] = zone_code_to_piranha(code, a.cd);
+    a.okey[pos] = key;
     a.osign[pos] = neg ? (signed char)-1 : (signed char)1;
-    maxbits = max(maxbits, bits);
+    // the largest bit length over all terms = the position of the highest bit set in ANY magnitude: OR the words per
+    // position (orw), the caller turns the ORs into a bit length once at the end (zone_maxbits)
+#pragma unroll
+    for (int w = 0; w < NW; ++w) orw[w] |= m[w];
 }
+
+template <int NW>
+__device__ __forceinline__ u32 zone_maxbits(const u32 (&orw)[NW])
+{
+    u32 bits = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+        if (orw[w]) bits = 32u * (u32)w + (32u - (u32)__clz((int)orw[w]));
+    return bits;
+}
+
+template <int NW, bool SIGNED = true>
+__device__ __forceinline__ void zone_emit(const ZoneArgs &a, u64 pos, u32 code, const u32 (&wd)[NW], u32 &maxbits, u32 &flags)
+{
+    u32 orw[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) orw[w] = 0;
+    zone_emit_key<NW, SIGNED>(a, pos, zone_code_to_piranha(code, a.cd), wd, orw, flags);
+    maxbits = max(maxbits, zone_maxbits<NW>(orw));
+}
+
+// Tight code -> Kronecker code for ASCENDING codes: the digits of the previous code are kept (first kKeyWalkVars digits in
+// registers, the rest folded into a base) and a step adds the difference to digit 0 and carries on; most steps touch
+// one or two digits instead of all of them.
+constexpr int kKeyWalkVars = 8;
+struct KeyWalker {
+    u32 d[kKeyWalkVars];
+    u32 code;
+    i64 key;
+    __device__ __forceinline__ void init(u32 c0, const ZoneCodec &cd)
+    {
+        code = c0;
+        key = cd.base_code;
+        u32 c = c0;
+#pragma unroll
+        for (int v = 0; v < kKeyWalkVars; ++v) {
+            d[v] = 0;
+            if ((u32)v < cd.n_vars) {
+                const u32 r = cd.tradix[v];
+                if (r > 1) {
+                    const u32 q = (u32)__umul64hi((u64)c, cd.magic[v]);
+                    d[v] = c - q * r;
+                    c = q;
+                    key += (i64)d[v] * cd.spstride[v];
+                }
+            }
+        }
+        for (u32 v = kKeyWalkVars; v < cd.n_vars; ++v) { // (more variables than the walker keeps: their digits never change within its reach)
+            const u32 r = cd.tradix[v];
+            if (r > 1) {
+                const u32 q = (u32)__umul64hi((u64)c, cd.magic[v]);
+                key += (i64)(c - q * r) * cd.spstride[v];
+                c = q;
+            }
+        }
+    }
+    // advance to c1 >= code: most steps stay inside digit 0 (one add, one 32 x 64 multiply); a step that carries out of it
+    // decodes from scratch
+    __device__ __forceinline__ void step(u32 c1, const ZoneCodec &cd)
+    {
+        const u32 delta = c1 - code;
+        const u32 x = d[0] + delta;
+        if (cd.tradix[0] > 1u && delta < cd.tradix[0] && x < cd.tradix[0]) {
+            key += (i64)delta * cd.spstride[0];
+            d[0] = x;
+            code = c1;
+        } else {
+            init(c1, cd);
+        }
+    }
+};
 
 // MODE 0: dense zones (slot = code - zlo).  MODE 1: bitmap zones (slot = rank of the code among the codes that occur).
 // TPB threads per block, 1024 / TPB blocks per SM: while one block sits in a barrier phase (prefix, emit, walk tail)
