@@ -34,8 +34,8 @@ class _PcResult(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "piranha_cpu.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("piranha_cpu.c", "pc_dispatch.c", "Makefile"))
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
 

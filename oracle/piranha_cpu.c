@@ -28,11 +28,19 @@
  *       multiplication in 256x256 blocks with one spinlock per bucket when threaded
  *       polynomial.hpp:1402-1531, base_series_multiplier.hpp:449-504, :987-1102
  *   - sanitise_series: recount and drop zero coefficients            base_series_multiplier.hpp:855-949
- * Coefficients: mp++ integers never overflow; here they are 256-bit two's complement accumulators fed by
- * operands of at most two 64-bit limbs (sign + magnitude, little-endian limbs), which is exact for every
- * configuration in BASELINE.json (largest result coefficient 2^127.96).
+ * Coefficients: mp++ integers never overflow (static storage of N limbs, promotion beyond); here they are fixed-width
+ * two's complement accumulators of PC_L = 2, 3 or 4 64-bit limbs fed by operands of at most two limbs (sign + magnitude,
+ * little-endian limbs).  This file is compiled once per width (oracle/Makefile: -DPC_L=2/3/4 -Dpc_mul=pc_mul_L<n>) and
+ * oracle/pc_dispatch.c picks the narrowest width the bound |a|max * |b|max * min(n1, n2) fits, the way mppp::integer<N>
+ * stays in its static limbs: a table node is {key, PC_L limbs, next} = 32 / 40 / 48 bytes (the reference's node is
+ * term + next pointer).  Exact for every configuration in BASELINE.json (largest result coefficient 2^127.96 -> 3 limbs).
+ * The bucket array is mapped with MADV_HUGEPAGE (the products of a task land ~2700 buckets apart, one TLB entry each with
+ * 4 KB pages), first touched by the worker threads like the reference's parallel rehash (hash_set.hpp:463-531); worker
+ * threads live in a persistent pool (thread_pool.hpp:75-215) and the estimator's trials run on it in parallel
+ * (base_series_multiplier.hpp:592-718).
  */
 #define _GNU_SOURCE
+#include <sys/mman.h>
 #include <pthread.h>
 #include <stdatomic.h>
 #include <stdint.h>
@@ -40,13 +48,18 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <sched.h>
+#include <unistd.h>
 
 #define PC_OK 0
 #define PC_E_ARGS 1
 #define PC_E_KEY_RANGE 2
 #define PC_E_NOMEM 4
 
-#define PC_ACC_LIMBS 4
+#ifndef PC_L
+#define PC_L 4
+#endif
+#define PC_ACC_LIMBS PC_L
 #define PC_BLOCK 256u           /* tuning::multiplication_block_size, tuning.hpp:57 */
 #define PC_EST_THRESHOLD 200u   /* tuning::estimate_threshold, tuning.hpp:60 */
 #define PC_MIN_WORK 250000ull   /* settings::min_work_per_thread, settings.hpp:57 */
@@ -66,12 +79,14 @@ typedef struct {
     int64_t deg;
 } term_t;
 
+/* next == NULL: an empty bucket head; PC_END: a used node that ends its chain (calloc'ed / fresh pages = all empty) */
 typedef struct node {
     int64_t key;
     acc_t cf;
     struct node *next;
-    int used;
 } node_t;
+#define PC_END ((node_t *)(uintptr_t)1)
+#define PC_USED(n) ((n)->next != NULL)
 
 typedef struct arena {
     struct arena *prev;
@@ -83,6 +98,7 @@ typedef struct {
     node_t *b;      /* bucket array: first node inline, hash_set.hpp:128-174 */
     uint64_t nb;    /* power of two */
     uint64_t mask;
+    size_t bytes;   /* mapped size */
 } table_t;
 
 typedef struct {
@@ -99,7 +115,12 @@ typedef struct {
 /* ---------------------------------------------------------------- multiprecision helpers */
 
 static inline void acc_zero(acc_t *a) { memset(a, 0, sizeof(*a)); }
-static inline int acc_is_zero(const acc_t *a) { return (a->w[0] | a->w[1] | a->w[2] | a->w[3]) == 0; }
+static inline int acc_is_zero(const acc_t *a)
+{
+    uint64_t o = 0;
+    for (int i = 0; i < PC_L; ++i) o |= a->w[i];
+    return o == 0;
+}
 
 /* |t1| * |t2| -> 256-bit magnitude */
 static inline void mag_mul(const term_t *x, const term_t *y, uint64_t p[4])
@@ -128,16 +149,17 @@ static inline void mag_mul(const term_t *x, const term_t *y, uint64_t p[4])
 
 static inline void acc_add_mag(acc_t *a, const uint64_t p[4], int neg)
 {
+    /* (the width bound guarantees p[PC_L..3] == 0 and no carry out of the top limb) */
     if (!neg) {
         u128 c = 0;
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < PC_L; ++i) {
             c += (u128)a->w[i] + p[i];
             a->w[i] = (uint64_t)c;
             c >>= 64;
         }
     } else {
         u128 br = 0;
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < PC_L; ++i) {
             u128 d = (u128)a->w[i] - p[i] - br;
             a->w[i] = (uint64_t)d;
             br = (d >> 64) & 1;
@@ -187,6 +209,94 @@ static uint32_t mt_below(mt_t *m, uint32_t range)
         }
     }
     return (uint32_t)(prod >> 32);
+}
+
+/* ---------------------------------------------------------------- persistent thread pool
+ * thread_pool.hpp:75-215: one worker thread per slot, created once and kept; a job is handed to slot t and the caller
+ * waits for all of them (future_list::wait_all, thread_pool.hpp:516-612).  The benchmarks bind worker t to core t
+ * (settings::set_thread_binding(true), benchmarks/fateman1.cpp:50-54); so does this pool. */
+
+typedef struct {
+    pthread_t th;
+    pthread_mutex_t m;
+    pthread_cond_t cv_job, cv_done;
+    void *(*fn)(void *);
+    void *arg;
+    int has, done, started;
+    uint32_t slot;
+} pool_slot_t;
+
+#define PC_POOL_MAX 1024u
+static pool_slot_t *g_pool[PC_POOL_MAX];
+static pthread_mutex_t g_pool_m = PTHREAD_MUTEX_INITIALIZER;
+
+static void *pool_main(void *p)
+{
+    pool_slot_t *s = (pool_slot_t *)p;
+    long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+    if (ncpu > 0) {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        CPU_SET((int)(s->slot % (uint32_t)ncpu), &set);
+        pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+    }
+    pthread_mutex_lock(&s->m);
+    for (;;) {
+        while (!s->has) pthread_cond_wait(&s->cv_job, &s->m);
+        s->has = 0;
+        void *(*fn)(void *) = s->fn;
+        void *arg = s->arg;
+        pthread_mutex_unlock(&s->m);
+        fn(arg);
+        pthread_mutex_lock(&s->m);
+        s->done = 1;
+        pthread_cond_signal(&s->cv_done);
+    }
+    return NULL;
+}
+
+/* fn(args + t * stride) on pool slot t for t in [0, nt); returns when all are done */
+static int pool_run(uint32_t nt, void *(*fn)(void *), void *args, size_t stride)
+{
+    if (nt > PC_POOL_MAX) return PC_E_ARGS;
+    pthread_mutex_lock(&g_pool_m);
+    for (uint32_t t = 0; t < nt; ++t) {
+        if (g_pool[t]) continue;
+        pool_slot_t *s = (pool_slot_t *)calloc(1, sizeof(pool_slot_t));
+        if (!s) {
+            pthread_mutex_unlock(&g_pool_m);
+            return PC_E_NOMEM;
+        }
+        pthread_mutex_init(&s->m, NULL);
+        pthread_cond_init(&s->cv_job, NULL);
+        pthread_cond_init(&s->cv_done, NULL);
+        s->slot = t;
+        if (pthread_create(&s->th, NULL, pool_main, s)) {
+            free(s);
+            pthread_mutex_unlock(&g_pool_m);
+            return PC_E_NOMEM;
+        }
+        pthread_detach(s->th);
+        g_pool[t] = s;
+    }
+    for (uint32_t t = 0; t < nt; ++t) {
+        pool_slot_t *s = g_pool[t];
+        pthread_mutex_lock(&s->m);
+        s->fn = fn;
+        s->arg = (char *)args + (size_t)t * stride;
+        s->done = 0;
+        s->has = 1;
+        pthread_cond_signal(&s->cv_job);
+        pthread_mutex_unlock(&s->m);
+    }
+    for (uint32_t t = 0; t < nt; ++t) {
+        pool_slot_t *s = g_pool[t];
+        pthread_mutex_lock(&s->m);
+        while (!s->done) pthread_cond_wait(&s->cv_done, &s->m);
+        pthread_mutex_unlock(&s->m);
+    }
+    pthread_mutex_unlock(&g_pool_m);
+    return 0;
 }
 
 /* ---------------------------------------------------------------- multiplier state */
@@ -256,16 +366,15 @@ static inline int consume_pair(mult_t *m, arena_t **ar, const term_t *t1, const 
     uint64_t p[4];
     mag_mul(t1, t2, p);
     const int neg = t1->neg ^ t2->neg;
-    if (!b->used) { /* empty bucket: inline node, hash_set.hpp:295-310 */
-        b->used = 1;
+    if (!PC_USED(b)) { /* empty bucket: inline node, hash_set.hpp:295-310 */
         b->key = key;
         acc_zero(&b->cf);
         acc_add_mag(&b->cf, p, neg);
-        b->next = NULL;
+        b->next = PC_END;
         return 0;
     }
     node_t *cur = b, *last = b;
-    while (cur) { /* _find */
+    while (cur != PC_END) { /* _find */
         if (cur->key == key) {
             acc_add_mag(&cur->cf, p, neg); /* multiply_accumulate */
             return 0;
@@ -275,11 +384,10 @@ static inline int consume_pair(mult_t *m, arena_t **ar, const term_t *t1, const 
     }
     node_t *n = arena_new_node(ar); /* _unique_insert: new node at the chain end */
     if (!n) return PC_E_NOMEM;
-    n->used = 1;
     n->key = key;
     acc_zero(&n->cf);
     acc_add_mag(&n->cf, p, neg);
-    n->next = NULL;
+    n->next = PC_END;
     last->next = n;
     return 0;
 }
@@ -309,12 +417,20 @@ static int kset_insert(kset_t *s, int64_t k) /* returns 1 if new */
 
 static uint64_t lf_of(const mult_t *m, uint64_t i) { return m->sl ? (m->sl[i] < m->n2 ? m->sl[i] : m->n2) : m->n2; }
 
-static uint64_t estimate_final_series_size(const mult_t *m)
+typedef struct {
+    const mult_t *m;
+    unsigned tr0, tr1; /* trials [tr0, tr1) */
+    u128 total;
+    int rc;
+} est_worker_t;
+
+/* the trials [tr0, tr1): every trial is seeded by its own index, so the sum does not depend on how they are dealt out */
+static void *estimate_trials(void *p)
 {
-    const uint64_t n1 = m->n1, n2 = m->n2;
-    if (!n1 || !n2) return 1;
-    if (n1 == 1 || n2 == 1) return n1 * n2;
-    const unsigned n_trials = 15, multiplier = 2;
+    est_worker_t *w = (est_worker_t *)p;
+    const mult_t *m = w->m;
+    const uint64_t n1 = m->n1;
+    const unsigned multiplier = 2;
     kset_t s;
     s.cap = 1;
     while (s.cap < 2 * n1 + 2) s.cap <<= 1;
@@ -322,8 +438,15 @@ static uint64_t estimate_final_series_size(const mult_t *m)
     s.keys = (int64_t *)malloc(s.cap * sizeof(int64_t));
     s.used = (uint8_t *)malloc(s.cap);
     uint64_t *idx = (uint64_t *)malloc(n1 * sizeof(uint64_t));
+    if (!s.keys || !s.used || !idx) {
+        free(s.keys);
+        free(s.used);
+        free(idx);
+        w->rc = PC_E_NOMEM;
+        return NULL;
+    }
     u128 total = 0;
-    for (unsigned tr = 0; tr < n_trials; ++tr) {
+    for (unsigned tr = w->tr0; tr < w->tr1; ++tr) {
         mt_t eng;
         mt_seed(&eng, tr); /* seeded by the global trial index: base_series_multiplier.hpp:627-629 */
         for (uint64_t i = 0; i < n1; ++i) idx[i] = i;
@@ -352,6 +475,31 @@ static uint64_t estimate_final_series_size(const mult_t *m)
     free(s.keys);
     free(s.used);
     free(idx);
+    w->total = total;
+    return NULL;
+}
+
+static uint64_t estimate_final_series_size(const mult_t *m)
+{
+    const uint64_t n1 = m->n1, n2 = m->n2;
+    if (!n1 || !n2) return 1;
+    if (n1 == 1 || n2 == 1) return n1 * n2;
+    const unsigned n_trials = 15;
+    /* the trials are dealt out over the threads (base_series_multiplier.hpp:592-718) */
+    uint32_t nt = m->n_threads < n_trials ? m->n_threads : n_trials;
+    if (nt < 1) nt = 1;
+    est_worker_t ws[15];
+    for (uint32_t t = 0; t < nt; ++t) {
+        ws[t].m = m;
+        ws[t].tr0 = n_trials * t / nt;
+        ws[t].tr1 = n_trials * (t + 1) / nt;
+        ws[t].total = 0;
+        ws[t].rc = 0;
+    }
+    if (nt == 1) estimate_trials(&ws[0]);
+    else if (pool_run(nt, estimate_trials, ws, sizeof(est_worker_t))) return n1; /* (cannot size: a small table still gives the right result) */
+    u128 total = 0;
+    for (uint32_t t = 0; t < nt; ++t) total += ws[t].total;
     uint64_t est = (uint64_t)(total / n_trials);
     return est ? est : 1;
 }
@@ -361,8 +509,13 @@ static int table_rehash(table_t *t, uint64_t want, uint32_t n_threads)
     (void)n_threads; /* calloc pages are zeroed by the kernel on first touch by the worker threads */
     uint64_t nb = 1;
     while (nb < want) nb <<= 1;
-    t->b = (node_t *)calloc(nb, sizeof(node_t));
-    if (!t->b) return PC_E_NOMEM;
+    /* fresh anonymous pages are zero = empty buckets; huge pages when the kernel grants them */
+    const size_t bytes = (((size_t)nb * sizeof(node_t)) + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    void *mem = mmap(NULL, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (mem == MAP_FAILED) return PC_E_NOMEM;
+    madvise(mem, bytes, MADV_HUGEPAGE);
+    t->b = (node_t *)mem;
+    t->bytes = bytes;
     t->nb = nb;
     t->mask = nb - 1;
     return 0;
@@ -587,7 +740,6 @@ static int sparse_kronecker_multiplication(mult_t *m)
     tvec_t *zones = (tvec_t *)calloc(n_zones, sizeof(tvec_t));
     atomic_flag *claimed = (atomic_flag *)malloc(n_zones * sizeof(atomic_flag));
     worker_t *ws = (worker_t *)calloc(m->n_threads, sizeof(worker_t));
-    pthread_t *th = (pthread_t *)calloc(m->n_threads, sizeof(pthread_t));
     for (uint64_t z = 0; z < n_zones; ++z) atomic_flag_clear(&claimed[z]);
     for (uint32_t t = 0; t < m->n_threads; ++t) {
         ws[t].m = m;
@@ -599,18 +751,15 @@ static int sparse_kronecker_multiplication(mult_t *m)
     }
     for (int phase = 0; phase < 2 && !rc; ++phase) {
         const double tp = now_s();
-        for (uint32_t t = 0; t < m->n_threads; ++t) pthread_create(&th[t], NULL, phase ? zone_worker : zone_builder, &ws[t]);
-        for (uint32_t t = 0; t < m->n_threads; ++t) {
-            pthread_join(th[t], NULL);
+        rc = pool_run(m->n_threads, phase ? zone_worker : zone_builder, ws, sizeof(worker_t));
+        for (uint32_t t = 0; t < m->n_threads; ++t)
             if (ws[t].rc) rc = ws[t].rc;
-        }
         if (getenv("PC_TIMING")) fprintf(stderr, "[pc] %s %.1f ms\n", phase ? "zone workers" : "zone builders", (now_s() - tp) * 1e3);
     }
     for (uint64_t z = 0; z < n_zones; ++z) free(zones[z].t);
     free(zones);
     free(claimed);
     free(ws);
-    free(th);
     return rc;
 }
 
@@ -687,7 +836,6 @@ static int plain_multiplication(mult_t *m)
     if (!m->locks) return PC_E_NOMEM;
     for (uint64_t i = 0; i < m->tab.nb; ++i) atomic_flag_clear(&m->locks[i]);
     pworker_t *ws = (pworker_t *)calloc(m->n_threads, sizeof(pworker_t));
-    pthread_t *th = (pthread_t *)calloc(m->n_threads, sizeof(pthread_t));
     const uint64_t block = m->n1 / m->n_threads; /* base_series_multiplier.hpp:1054 */
     for (uint32_t t = 0; t < m->n_threads; ++t) {
         ws[t].m = m;
@@ -695,14 +843,11 @@ static int plain_multiplication(mult_t *m)
         ws[t].end1 = (t == m->n_threads - 1) ? m->n1 : (t + 1) * block;
         ws[t].tid = t;
         ws[t].locked = 1;
-        pthread_create(&th[t], NULL, blocked_multiplication, &ws[t]);
     }
-    for (uint32_t t = 0; t < m->n_threads; ++t) {
-        pthread_join(th[t], NULL);
+    rc = pool_run(m->n_threads, blocked_multiplication, ws, sizeof(pworker_t));
+    for (uint32_t t = 0; t < m->n_threads; ++t)
         if (ws[t].rc) rc = ws[t].rc;
-    }
     free(ws);
-    free(th);
     return rc;
 }
 
@@ -718,8 +863,9 @@ static void *sanitise_worker(void *p)
     sanitise_t *w = (sanitise_t *)p;
     uint64_t cnt = 0;
     for (uint64_t b = w->b0; b < w->b1; ++b)
-        for (const node_t *c = &w->tab->b[b]; c && c->used; c = c->next)
-            if (!acc_is_zero(&c->cf)) ++cnt;
+        if (PC_USED(&w->tab->b[b]))
+            for (const node_t *c = &w->tab->b[b]; c != PC_END; c = c->next)
+                if (!acc_is_zero(&c->cf)) ++cnt;
     w->count = cnt;
     return NULL;
 }
@@ -859,10 +1005,7 @@ int pc_mul(uint64_t n1, const int64_t *key1, const uint64_t *mag1, uint32_t limb
     {
         const uint32_t nt = (m.n_threads > 1 && m.tab.nb >= 4096) ? m.n_threads : 1;
         sanitise_t *sw = (sanitise_t *)calloc(nt, sizeof(sanitise_t));
-        pthread_t *sth = (pthread_t *)calloc(nt, sizeof(pthread_t));
-        if (!sw || !sth) {
-            free(sw);
-            free(sth);
+        if (!sw) {
             rc = PC_E_NOMEM;
             goto done;
         }
@@ -871,15 +1014,12 @@ int pc_mul(uint64_t n1, const int64_t *key1, const uint64_t *mag1, uint32_t limb
             sw[t].b0 = m.tab.nb / nt * t;
             sw[t].b1 = (t + 1 == nt) ? m.tab.nb : m.tab.nb / nt * (t + 1);
         }
-        for (uint32_t t = 1; t < nt; ++t) pthread_create(&sth[t], NULL, sanitise_worker, &sw[t]);
-        sanitise_worker(&sw[0]);
-        uint64_t cnt = sw[0].count;
-        for (uint32_t t = 1; t < nt; ++t) {
-            pthread_join(sth[t], NULL);
-            cnt += sw[t].count;
-        }
+        if (nt == 1) sanitise_worker(&sw[0]);
+        else rc = pool_run(nt, sanitise_worker, sw, sizeof(sanitise_t));
+        uint64_t cnt = 0;
+        for (uint32_t t = 0; t < nt; ++t) cnt += sw[t].count;
         free(sw);
-        free(sth);
+        if (rc) goto done;
         out->n = cnt;
         out->buckets = m.tab.nb;
     }
@@ -892,14 +1032,15 @@ done:
         out->sign = (int8_t *)malloc(out->n);
         if (!out->key || !out->mag || !out->sign) rc = PC_E_NOMEM;
         uint64_t o = 0;
-        for (uint64_t b = 0; b < m.tab.nb && !rc; ++b)
-            for (node_t *c = &m.tab.b[b]; c && c->used; c = c->next) {
+        for (uint64_t b = 0; b < m.tab.nb && !rc; ++b) {
+            if (!PC_USED(&m.tab.b[b])) continue;
+            for (node_t *c = &m.tab.b[b]; c != PC_END; c = c->next) {
                 if (acc_is_zero(&c->cf)) continue;
                 acc_t v = c->cf;
-                const int neg = (int)(v.w[3] >> 63);
+                const int neg = (int)(v.w[PC_L - 1] >> 63);
                 if (neg) { /* two's complement -> magnitude */
                     u128 cy = 1;
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < PC_L; ++i) {
                         cy += (uint64_t)~v.w[i];
                         v.w[i] = (uint64_t)cy;
                         cy >>= 64;
@@ -910,8 +1051,9 @@ done:
                 out->sign[o] = neg ? -1 : 1;
                 ++o;
             }
+        }
     }
-    free(m.tab.b);
+    if (m.tab.b) munmap(m.tab.b, m.tab.bytes);
     free(m.locks);
     if (m.arenas) {
         for (uint32_t t = 0; t < m.n_threads; ++t) arena_free_all(m.arenas[t]);
@@ -932,6 +1074,7 @@ done:
     return rc;
 }
 
+#ifndef PC_NO_RESULT_FREE
 void pc_result_free(pc_result *r)
 {
     if (!r) return;
@@ -940,3 +1083,4 @@ void pc_result_free(pc_result *r)
     free(r->sign);
     memset(r, 0, sizeof(*r));
 }
+#endif

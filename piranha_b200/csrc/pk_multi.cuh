@@ -342,17 +342,25 @@ void multi_mul(pk_ctx *M, const pk_poly *a, const pk_poly *b, const pk_opts *opt
     if (!a || !b) fail(PK_E_ARGS, "null operand");
     const pk_opts o0 = multi_opts(opts_in);
     const u32 N = (u32)M->subs.size();
+    const bool trace = getenv("PK_MULTI_TRACE") != nullptr; // debug: wall time of the phases
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
+    std::vector<double> t_up(N, 0.0), t_mul(N, 0.0);
     MultiGuard g{M, multi_new(M, a->n_vars)};
     g.p->part.assign(N, nullptr);
     multi_run(M, [&](u32 r) {
         pk_ctx *sub = M->subs[r];
+        const auto w0 = std::chrono::steady_clock::now();
         DPolyGuard da{sub, upload_impl(sub, a)};
         DPolyGuard db{sub, (a == b) ? nullptr : upload_impl(sub, b)};
+        t_up[r] = ms_since(w0);
         pk_opts o = o0;
         o.part_index = r;
         o.part_count = N;
         g.p->part[r] = mul_impl(sub, da.p, db.p ? db.p : da.p, &o);
+        t_mul[r] = ms_since(w0);
     });
+    const double t_phase1 = ms_since(t0);
     g.p->n = 0;
     g.p->limbs = 1;
     for (pk_dpoly *q : g.p->part) {
@@ -361,6 +369,11 @@ void multi_mul(pk_ctx *M, const pk_poly *a, const pk_poly *b, const pk_opts *opt
     }
     multi_collect_stats(M);
     multi_download(M, g.p, out);
+    if (trace) {
+        fprintf(stderr, "[pk multi] upload+multiply %.3f ms, + download %.3f ms;  per device (upload, upload+multiply):", t_phase1, ms_since(t0));
+        for (u32 r = 0; r < N; ++r) fprintf(stderr, " (%.3f, %.3f)", t_up[r], t_mul[r]);
+        fprintf(stderr, "\n");
+    }
 }
 
 u64 multi_digest(pk_ctx *M, const pk_dpoly *p)
