@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <exception>
 #include <functional>
 #include <iterator>
@@ -21,6 +22,10 @@
 #include <utility>
 #include <vector>
 
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
+
 namespace pb200
 {
 
@@ -29,6 +34,60 @@ namespace detail
 // Contiguous pool of constructed nodes over raw storage: what hash_set needs from std::vector, plus the one thing
 // std::vector cannot do -- hand out uninitialised storage for n nodes so that several threads construct (and first-touch
 // the pages of) disjoint ranges at once.
+// Large arrays (node pools and bucket heads of results with millions of terms) are 2 MB aligned and advised to use huge
+// pages: a bulk fill touches the bucket heads in random order, one TLB entry per element with 4 KB pages.
+inline void *big_alloc(std::size_t bytes)
+{
+    constexpr std::size_t huge = std::size_t(2) << 20;
+    if (bytes >= 2 * huge) {
+        void *p = nullptr;
+        const std::size_t rounded = (bytes + huge - 1) & ~(huge - 1);
+        if (::posix_memalign(&p, huge, rounded) != 0 || !p) throw std::bad_alloc();
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+        ::madvise(p, rounded, MADV_HUGEPAGE);
+#endif
+        return p;
+    }
+    void *p = std::malloc(bytes ? bytes : 1);
+    if (!p) throw std::bad_alloc();
+    return p;
+}
+inline void big_free(void *p) { std::free(p); }
+
+// std::allocator that leaves trivially constructible elements uninitialised on resize() (the caller fills them, possibly
+// from several threads) and allocates through big_alloc
+template <typename T>
+struct raw_big_allocator {
+    using value_type = T;
+    raw_big_allocator() = default;
+    template <typename U>
+    raw_big_allocator(const raw_big_allocator<U> &) noexcept
+    {
+    }
+    T *allocate(std::size_t n) { return static_cast<T *>(big_alloc(n * sizeof(T))); }
+    void deallocate(T *p, std::size_t) noexcept { big_free(p); }
+    template <typename U>
+    void construct(U *p) noexcept(std::is_nothrow_default_constructible<U>::value)
+    {
+        ::new (static_cast<void *>(p)) U; // default-initialisation: no zero fill
+    }
+    template <typename U, typename... Args>
+    void construct(U *p, Args &&...args)
+    {
+        ::new (static_cast<void *>(p)) U(std::forward<Args>(args)...);
+    }
+    template <typename U>
+    bool operator==(const raw_big_allocator<U> &) const noexcept
+    {
+        return true;
+    }
+    template <typename U>
+    bool operator!=(const raw_big_allocator<U> &) const noexcept
+    {
+        return false;
+    }
+};
+
 template <typename Node>
 class node_pool
 {
@@ -59,12 +118,12 @@ public:
     void reserve(std::size_t n)
     {
         if (n <= m_cap) return;
-        Node *np = static_cast<Node *>(::operator new(n * sizeof(Node)));
+        Node *np = static_cast<Node *>(big_alloc(n * sizeof(Node)));
         for (std::size_t i = 0; i < m_size; ++i) {
             ::new (static_cast<void *>(np + i)) Node(std::move(m_p[i]));
             m_p[i].~Node();
         }
-        ::operator delete(m_p);
+        big_free(m_p);
         m_p = np;
         m_cap = n;
     }
@@ -89,7 +148,7 @@ private:
     void release()
     {
         for (std::size_t i = 0; i < m_size; ++i) m_p[i].~Node();
-        ::operator delete(m_p);
+        big_free(m_p);
         m_p = nullptr;
         m_size = m_cap = 0;
     }
@@ -288,7 +347,7 @@ public:
         while (nb < n) nb <<= 1;
         n_threads = static_cast<unsigned>(std::max<size_type>(1, std::min<size_type>(n_threads, n / 4096 + 1)));
         node *pool = m_nodes.raw(n);
-        m_heads.resize(nb); // value-initialised once; the slices are set to npos by the threads below
+        m_heads.resize(nb); // (left uninitialised by the allocator: the slices are set to npos by the threads below)
         std::uint32_t *heads = m_heads.data();
         std::vector<size_type> built(n_threads, 0);
         std::vector<std::exception_ptr> err(n_threads);
@@ -337,7 +396,7 @@ public:
 
 private:
     detail::node_pool<node> m_nodes;
-    std::vector<std::uint32_t> m_heads;
+    std::vector<std::uint32_t, detail::raw_big_allocator<std::uint32_t>> m_heads;
     std::uint32_t m_free = npos;
     size_type m_n_elements = 0;
 };

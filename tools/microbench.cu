@@ -3,6 +3,8 @@
 //   - global RED.ADD.64 on L2-resident and HBM-resident tables (random / run-clustered addresses)
 //   - CAS-claim + RED (open addressing probe)
 //   - random 16-byte LDG gathers (operand fetch)
+//   - the INT32 multiply pipe: IMAD (32 x 32 + 32), IMAD.WIDE (32 x 32 + 64 -> 64) and the 64 x 64 -> 128 coefficient
+//     product the pairing kernels issue (4 IMAD.WIDE-class operations), as independent chains per thread
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tools/microbench tools/microbench.cu
 // Output: one line per experiment, ops/s over the whole chip.  Numbers feed DESIGN.md's roofline section.
 #include <cstdint>
@@ -140,6 +142,42 @@ float time_ms(F f, int reps = 5)
     return best;
 }
 
+// MODE 0: IMAD (mad.lo.u32), MODE 1: IMAD.WIDE (mad.wide.u32), MODE 2: 64 x 64 -> 128 product (mul.lo.u64 + mul.hi.u64), with
+// CHAINS independent dependency chains per thread so that the pipe, not the latency, is measured.
+template <int MODE, int CHAINS>
+__global__ void k_imad(u64 *out, int iters, u32 seed0)
+{
+    u32 a[CHAINS], b[CHAINS];
+    u64 w[CHAINS], h[CHAINS];
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) {
+        a[c] = seed0 * (2u * c + 3u) + t;
+        b[c] = (seed0 ^ 0x9E3779B9u) + 7u * c + t * 5u;
+        w[c] = ((u64)a[c] << 32) | b[c];
+        h[c] = 0;
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int c = 0; c < CHAINS; ++c) {
+            if (MODE == 0) {
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[c]) : "r"(b[c]), "r"(a[c]));
+            } else if (MODE == 1) {
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"(a[c]), "r"(b[c]));
+            } else {
+                u64 lo, hi;
+                asm volatile("mul.lo.u64 %0, %2, %3;\n\tmul.hi.u64 %1, %2, %3;" : "=l"(lo), "=l"(hi) : "l"(w[c]), "l"(w[c] | 1ull));
+                w[c] = lo ^ hi;
+                h[c] += hi;
+            }
+        }
+    }
+    u64 sink = 0;
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) sink += a[c] + w[c] + h[c];
+    if (sink == 0x1234567ull) out[0] = sink; // (keeps the chains alive)
+}
+
 int main()
 {
     cudaDeviceProp prop;
@@ -227,6 +265,26 @@ int main()
             printf("gather16 table=%zuMB: %.3f ms, %.2f Gload/s\n", bytes >> 20, t, n / t * 1e-6);
         }
         CK(cudaFree(tab));
+    }
+    // ---- INT32 multiply pipe
+    {
+        u64 *d_sink;
+        CK(cudaMalloc(&d_sink, 64));
+        const int iters = 4096, threads = 1024, chains = 8;
+        const char *names[3] = {"IMAD 32x32+32", "IMAD.WIDE 32x32+64", "64x64->128 product (mul.lo.u64 + mul.hi.u64)"};
+        for (int mode = 0; mode < 3; ++mode) {
+            auto launch = [&]() {
+                if (mode == 0) k_imad<0, chains><<<sms, threads>>>(d_sink, iters, 12345u);
+                else if (mode == 1) k_imad<1, chains><<<sms, threads>>>(d_sink, iters, 12345u);
+                else k_imad<2, chains><<<sms, threads>>>(d_sink, iters, 12345u);
+            };
+            const float ms = time_ms(launch);
+            CK(cudaGetLastError());
+            const double ops = (double)sms * threads * iters * chains;
+            printf("int_pipe %s: %.3f ms, %.1f Gop/s chip, %.2f lane-op/clk/SM @%.0f MHz\n", names[mode], ms, ops / ms * 1e-6,
+                   ops / ms * 1e-6 / (double)sms / (prop.clockRate * 1e-6), prop.clockRate * 1e-3);
+        }
+        CK(cudaFree(d_sink));
     }
     printf("done\n");
     return 0;
