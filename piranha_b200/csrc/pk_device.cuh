@@ -228,6 +228,13 @@ __global__ void k_readback(u32 *__restrict__ host_dst, const u32 *__restrict__ d
     __threadfence_system();
 }
 
+__global__ void k_readback2(u32 *__restrict__ h1, const u32 *__restrict__ d1, u32 n1, u32 *__restrict__ h2, const u32 *__restrict__ d2, u32 n2)
+{
+    for (u32 i = threadIdx.x; i < n1; i += blockDim.x) h1[i] = d1[i];
+    for (u32 i = threadIdx.x; i < n2; i += blockDim.x) h2[i] = d2[i];
+    __threadfence_system();
+}
+
 // ---- warp scans ---------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ u32 warp_incl_scan(u32 v)

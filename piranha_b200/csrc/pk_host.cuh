@@ -52,12 +52,29 @@ struct BlockTuning {
     uint32_t smem_limit = 0;      // bytes of shared memory a zone may use (0 = all): what is left over serves as L1
     uint32_t radix0_residue = 0;  // experiment: pad the radix of digit 0 so that radix mod 32 == this (1..32); 0 = off
     uint32_t unit_codes = 1u << 15; // sparse ranges: codes per zone unit aimed at, times the blocks per SM (a unit is a whole number of blocks)
+    uint32_t size_hint = 1;       // sparse ranges: size the result from the last product of the same operands and options (skips the
+                                  // mid-product read-back; verified on the device, repeated the long way on a miss)
     uint32_t ctas = 4;            // sparse ranges: thread blocks per SM of the accumulating kernel (1 x 1024, 2 x 512 or 4 x 256 threads;
                                   // measured on pearce1: 0.42 / 0.34 / 0.32 ms -- while one block emits or waits at a barrier the others walk)
     uint32_t merge = 1;           // 1 = a tile's rows span all the groups of A that land in the same zone unit with its group of B
 };
 
 } // namespace pk
+
+// What the sparse block path remembers of its last product on a context (see block_multiply).
+struct SizeHint {
+    const void *a = nullptr, *b = nullptr;
+    uint64_t nA = 0, nB = 0, range = 0, U = 0;
+    uint32_t part = 0, parts = 0, trunc = 0;
+    int64_t max_degree = 0;
+    uint64_t entries = 0;
+    bool valid = false;
+    bool same_key(const SizeHint &o) const
+    {
+        return a == o.a && b == o.b && nA == o.nA && nB == o.nB && range == o.range && U == o.U && part == o.part && parts == o.parts
+               && trunc == o.trunc && max_degree == o.max_degree;
+    }
+};
 
 struct PinnedBuf {
     void *ptr = nullptr;
@@ -87,6 +104,7 @@ struct pk_ctx {
     bool ev_valid = false, aux_valid = false;
     void *tiles_buf = nullptr;  // tile list of the block path, kept across products (grow-only)
     uint64_t tiles_cap = 0;     // in tiles
+    SizeHint size_hint;
     void *bitmap_buf = nullptr; // sparse block path: bitmap of the code range (k_block_mark -> k_block_acc), grow-only
     size_t bitmap_bytes = 0;
     void *h_scratch = nullptr; // small pinned read-back area
@@ -190,6 +208,15 @@ inline void readback(pk_ctx *ctx, void *host_pinned, const void *dev, size_t byt
     --ctx->total_launches;
 }
 
+// two read-backs in one launch
+inline void readback2(pk_ctx *ctx, void *h1, const void *d1, size_t b1, void *h2, const void *d2, size_t b2)
+{
+    PK_LAUNCH(ctx, k_readback2, 1, 64, 0, static_cast<u32 *>(h1), static_cast<const u32 *>(d1), (u32)(b1 / 4), static_cast<u32 *>(h2),
+              static_cast<const u32 *>(d2), (u32)(b2 / 4));
+    --ctx->call_launches;
+    --ctx->total_launches;
+}
+
 inline u32 grid_for(u64 n, u32 block) { return (u32)std::max<u64>(1, (n + block - 1) / block); }
 
 inline u32 bit_length(unsigned __int128 x)
@@ -249,6 +276,14 @@ struct DPolyGuard {
         pk_dpoly *r = p;
         p = nullptr;
         return r;
+    }
+    void release_now() // free what the guard holds, now
+    {
+        if (p) {
+            free_dpoly_arrays(ctx, p);
+            delete p;
+            p = nullptr;
+        }
     }
 };
 
