@@ -19,6 +19,7 @@ void fill_piranha_codec(const pk_ctx *ctx, u32 n_vars, CodecParams &cp)
     memset(&cp, 0, sizeof(cp));
     cp.n_vars = n_vars;
     cp.h_min = n_vars ? ctx->h_min[n_vars] : 0;
+    cp.h_max = n_vars ? ctx->h_max[n_vars] : 0;
     i64 ps = 1;
     for (u32 v = 0; v < n_vars; ++v) {
         const i64 M = ctx->limits[n_vars][v];
@@ -67,8 +68,10 @@ void compute_meta(pk_ctx *ctx, pk_dpoly *p, const i64 *key, const u64 *mag, cons
         p->egcd[v] = m->egcd[v];
     }
     p->max_bits = m->max_bits;
-    p->any_neg = (m->any_neg & 1u) != 0;
-    p->any_zero = (m->any_neg & 2u) != 0;
+    if (m->any_neg & kMetaKeyRange) fail(PK_E_ARGS, "a key is not a Kronecker code of this many variables (outside [h_min, h_max])");
+    if (m->any_neg & kMetaBadSign) fail(PK_E_ARGS, "a sign is not -1, 0 or +1");
+    p->any_neg = (m->any_neg & kMetaNeg) != 0;
+    p->any_zero = (m->any_neg & kMetaZero) != 0;
     p->has_meta = true;
 }
 
@@ -139,9 +142,13 @@ pk_dpoly *upload_impl(pk_ctx *ctx, const pk_poly *p)
               (i64 *)nullptr, (const u64 *)nullptr, (uint4 *)nullptr);
     PK_LAUNCH(ctx, k_iota32, grid_for(n, 256), 256, 0, idx.as<u32>(), n);
     radix_sort_pairs(ctx, fk.as<u64>(), fk2.as<u64>(), idx.as<u32>(), idx2.as<u32>(), n, (int)std::max<u32>(1, bit_length(range)));
+    CUDA_CHECK(cudaMemsetAsync(&ctx->d_meta->any_neg, 0, 4, ctx->stream));
     PK_LAUNCH(ctx, k_gather_terms, grid_for(n, 256), 256, 0, idx2.as<u32>(), raw_key.as<i64>(), raw_mag.as<u64>(),
-              raw_sign.as<signed char>(), g.p->key, g.p->planes, g.p->sign, n, p->limbs, g.p->stride);
-    ensure_meta(ctx, g.p);
+              raw_sign.as<signed char>(), g.p->key, g.p->planes, g.p->sign, n, p->limbs, g.p->stride, &ctx->d_meta->any_neg);
+    // the upload returns with the polynomial complete (other contexts / streams may use it) and its keys checked
+    readback(ctx, ctx->h_scratch, &ctx->d_meta->any_neg, 4);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (*static_cast<const u32 *>(ctx->h_scratch) & kMetaDuplicate) fail(PK_E_ARGS, "two terms with the same key");
     return g.release();
 }
 

@@ -25,7 +25,7 @@ constexpr int kMaxAccLimbs = 6; // widest normalised accumulator (64-bit limbs)
 struct CodecParams {
     u32 n_vars;
     u32 trunc_mode;
-    i64 h_min;
+    i64 h_min, h_max;        // smallest / largest Kronecker code of the codification
     i64 radix[PK_MAX_VARS];  // piranha radix 2*M_k+1
     i64 M[PK_MAX_VARS];      // piranha limit M_k
     i64 emin[PK_MAX_VARS];   // operand (or result) minimum exponent
@@ -42,8 +42,10 @@ struct MetaDev {
     i64 emax[PK_MAX_VARS];
     u64 egcd[PK_MAX_VARS]; // gcd over terms of (e - e_first)
     u32 max_bits;          // bit length of the largest coefficient magnitude
-    u32 any_neg;           // some coefficient is negative
+    u32 any_neg;           // bit 0: some coefficient is negative; 1: some coefficient is zero; 2: a key outside [h_min, h_max];
+                           // 3: a sign outside {-1, 0, +1}; 4: two terms with the same key
 };
+constexpr u32 kMetaNeg = 1u, kMetaZero = 2u, kMetaKeyRange = 4u, kMetaBadSign = 8u, kMetaDuplicate = 16u;
 
 // Device-side counters of one multiplication (read back once at the end).
 struct MulCounters {

@@ -92,12 +92,15 @@ __global__ void k_iota32(u32 *out, u64 n)
 // gather terms through a permutation (after sorting by key)
 __global__ void k_gather_terms(const u32 *__restrict__ perm, const i64 *__restrict__ raw_key,
                                const u64 *__restrict__ mag_aos, const signed char *__restrict__ sign, i64 *__restrict__ okey,
-                               u64 *__restrict__ oplanes, signed char *__restrict__ osign, u64 n, u32 limbs, u64 stride)
+                               u64 *__restrict__ oplanes, signed char *__restrict__ osign, u64 n, u32 limbs, u64 stride, u32 *flags)
 {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const u32 s = perm[i];
     okey[i] = raw_key[s];
+    // the terms are in key order now: equal neighbours are duplicate keys (a series holds every key once, series.hpp:1312-1320;
+    // the width proof "at most min(n1, n2) products per code" relies on it)
+    if (i && raw_key[perm[i - 1]] == raw_key[s]) atomicOr(flags, kMetaDuplicate);
     for (u32 l = 0; l < limbs; ++l) oplanes[l * stride + i] = mag_aos[(u64)s * limbs + l];
     osign[i] = sign[s];
 }
@@ -155,8 +158,10 @@ __global__ void k_meta(const i64 *__restrict__ key, const u64 *__restrict__ plan
         }
         if (bits > s_bits) atomicMax(&s_bits, bits);
         // bit 0: some coefficient is negative; bit 1: some coefficient is zero (sign 0 or zero magnitude)
-        const u32 flag = (bits == 0u || sign[i] == 0) ? 2u : (sign[i] < 0 ? 1u : 0u);
-        if (flag && (*((volatile u32 *)&meta->any_neg) & flag) == 0u) atomicOr(&meta->any_neg, flag);
+        u32 flag = (bits == 0u || sign[i] == 0) ? kMetaZero : (sign[i] < 0 ? kMetaNeg : 0u);
+        if (key[i] < cp.h_min || key[i] > cp.h_max) flag |= kMetaKeyRange; // (the reference's decode throws for such a code)
+        if (sign[i] < -1 || sign[i] > 1) flag |= kMetaBadSign;
+        if (flag && (*((volatile u32 *)&meta->any_neg) & flag) != flag) atomicOr(&meta->any_neg, flag);
     }
     __syncthreads();
     for (u32 v = threadIdx.x; v < cp.n_vars; v += blockDim.x) {

@@ -857,3 +857,33 @@ def test_multi_ctx_argument_errors(ctx):
         assert_terms_equal(m.mul_dev(da_multi, db_multi).download(), ctx.mul(a, b, nv))
     finally:
         m.close()
+
+
+def test_upload_rejects_invalid_terms(ctx):
+    """pk_upload checks what the reference's containers guarantee: keys inside the codification's range (decode throws
+    std::invalid_argument otherwise, kronecker_array.hpp:329-365), signs in {-1, 0, +1}, every key once (series.hpp:1312-1320)."""
+    lim, hmin, hmax = ctx.limits(2)
+    ok = terms({(1, 2): 3, (0, 1): -5}, 2)
+    for bad_key in (hmax + 1, hmin - 1):
+        k = ok[0].copy()
+        k[0] = bad_key
+        with pytest.raises(ValueError):
+            ctx.upload((k, ok[1], ok[2]), 2)
+    s = ok[2].copy()
+    s[1] = 2
+    with pytest.raises(ValueError):
+        ctx.upload((ok[0], ok[1], s), 2)
+    k = ok[0].copy()
+    k[1] = k[0]
+    with pytest.raises(ValueError):
+        ctx.upload((k, ok[1], ok[2]), 2)
+    with pytest.raises(ValueError):
+        ctx.mul((k, ok[1], ok[2]), ok, 2)
+    # a zero coefficient is accepted and contributes nothing
+    z, zm = ok[2].copy(), ok[1].copy()
+    z[0] = 0
+    zm[0] = 0
+    r = ctx.mul((ok[0], zm, z), ok, 2)
+    full = {(1, 2): 3, (0, 1): -5}
+    keep = {e: c for e, c in full.items() if po.kron_encode(e) != int(ok[0][0])}
+    assert_terms_equal(r, oracle_terms(po.p_mul(keep, full), 2))
