@@ -526,12 +526,38 @@ __device__ __forceinline__ void block_tile_loop(const uint4 *__restrict__ A, con
 // independent, so their shared-memory atomics (whose returned values feed the carries) are in flight together; one
 // product at a time leaves a warp waiting on the ATOMS round trip of every word (the `memory` clobber of the atomics
 // also keeps the next product's operand loads behind them).  Used by the dense zones only (see the walk).
+__device__ __forceinline__ uint4 lds128(u32 saddr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+
+// rows_s != 0: the tile's rows of A were staged in shared memory (bulk copy, see block_walk_tiles_staged): a row is one
+// broadcast LDS.128 (one LSU wavefront) instead of a broadcast LDG.128 (four).  Full tiles (32 / 64 columns) only.
 template <typename F2>
 __device__ __forceinline__ void block_tile_loop2(const uint4 *__restrict__ A, const uint4 *__restrict__ B, const uint4 t, u32 lane,
-                                                 F2 &&f2)
+                                                 F2 &&f2, u32 rows_s = 0u)
 {
     const u32 a0 = t.x, b0 = t.y, an = t.z & 1023u, bn = (t.z >> 10) & 127u;
-    if (bn == 64u) {
+    if (rows_s != 0u && bn == 64u) {
+        const uint4 bv0 = __ldg(&B[b0 + lane]), bv1 = __ldg(&B[b0 + 32u + lane]);
+        for (u32 i = 0; i < an; ++i) {
+            const uint4 av = lds128(rows_s + i * 16u);
+            f2(av, bv0, av, bv1, true);
+        }
+    } else if (rows_s != 0u && bn == kTileCols) {
+        const uint4 bv = __ldg(&B[b0 + lane]);
+        u32 i = 0;
+        for (; i + 1 < an; i += 2) {
+            const uint4 av0 = lds128(rows_s + i * 16u), av1 = lds128(rows_s + i * 16u + 16u);
+            f2(av0, bv, av1, bv, true);
+        }
+        if (i < an) {
+            const uint4 av = lds128(rows_s + i * 16u);
+            f2(av, bv, av, bv, false);
+        }
+    } else if (bn == 64u) {
         const uint4 bv0 = __ldg(&B[b0 + lane]), bv1 = __ldg(&B[b0 + 32u + lane]);
         for (u32 i = 0; i < an; ++i) {
             const uint4 av = __ldg(&A[a0 + i]);
@@ -694,6 +720,66 @@ __device__ __forceinline__ void block_walk_tiles(const uint4 *__restrict__ tiles
         body(t);
         if (kn >= tend) return;
         t = tn;
+    }
+}
+
+// The same walk with the rows of A of every FULL tile (32 / 64 columns, at most kStageRows rows) staged in shared memory by
+// a bulk copy (cp.async.bulk + mbarrier, one elected lane): the copy for the NEXT tile is issued before the current tile is
+// processed, into the other half of the warp's double buffer, so it lands behind useful work.  body(t, rows_s): rows_s is
+// the shared-memory address of the tile's rows, or 0 when the tile was not staged (ragged or too many rows).
+constexpr u32 kStageRows = 32;
+__device__ __forceinline__ bool block_tile_stageable(const uint4 &t)
+{
+    const u32 an = t.z & 1023u, bn = (t.z >> 10) & 127u;
+    return (bn == 64u || bn == kTileCols) && an <= kStageRows && !(t.z >> 31);
+}
+template <typename F>
+__device__ __forceinline__ void block_walk_tiles_staged(const uint4 *__restrict__ tiles, const uint4 *__restrict__ A, u32 s_next_addr,
+                                                        u32 tend, u32 lane, u32 buf_s /* 2 x kStageRows x 16 B of this warp */,
+                                                        u64 *bars /* 2 mbarriers of this warp */, u32 &phases, F &&body)
+{
+    auto issue = [&](const uint4 &t, u32 which) {
+        if (lane == 0) {
+            const u32 bytes = (t.z & 1023u) * 16u;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the warp's earlier reads of this buffer precede the copy
+            mbar_expect_tx(&bars[which], bytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             buf_s + which * kStageRows * 16u),
+                         "l"(A + t.x), "r"(bytes), "r"(smem_u32(&bars[which]))
+                         : "memory");
+        }
+    };
+    u32 k = 0;
+    if (lane == 0) k = atoms_add(s_next_addr, 1u);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    if (k >= tend) return;
+    uint4 t = __ldg(&tiles[k]);
+    u32 cur = 0;
+    bool staged = block_tile_stageable(t);
+    if (staged) issue(t, cur);
+    for (;;) {
+        u32 kn = 0;
+        if (lane == 0) kn = atoms_add(s_next_addr, 1u);
+        kn = __shfl_sync(0xffffffffu, kn, 0);
+        uint4 tn = make_uint4(0u, 0u, 0u, 0u);
+        bool staged_n = false;
+        if (kn < tend) {
+            tn = __ldg(&tiles[kn]);
+            staged_n = block_tile_stageable(tn);
+            if (staged_n) issue(tn, cur ^ 1u);
+        }
+        if (staged) {
+            mbar_wait(&bars[cur], (phases >> cur) & 1u);
+            phases ^= 1u << cur;
+            body(t, buf_s + cur * kStageRows * 16u);
+        } else {
+            body(t, 0u);
+        }
+        __syncwarp(); // all lanes are done with the buffer before lane 0 may overwrite it two tiles on
+        if (kn >= tend) return;
+        t = tn;
+        staged = staged_n;
+        cur ^= 1u;
     }
 }
 
@@ -987,12 +1073,29 @@ __global__ void __launch_bounds__(kPlanThreads) k_block_zones(const ZonesArgs a,
     }
 }
 
-// Product of two operand records -> 32-bit words of the magnitude (pw[0..8))
-template <int LW>
+// One-limb magnitudes whose product is known to fit 96 bits (PW <= 3 words): three IMAD.WIDE and one IMAD instead of the
+// full 64 x 64 -> 128 product (mul.lo.u64 + mul.hi.u64, about ten multiply-pipe instructions).  With a = a1:a0, b = b1:b0:
+//   w0 = a0 b0;  mid = a0 b1 + a1 b0 + hi32(w0)  (< 2^64 because the whole product is < 2^96);  word 2 = a1 b1 + hi32(mid).
+__device__ __forceinline__ void mul96(u32 a0, u32 a1, u32 b0, u32 b1, u32 &p0, u32 &p1, u32 &p2)
+{
+    u64 w0, mid;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(w0) : "r"(a0), "r"(b0));
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(mid) : "r"(a0), "r"(b1), "l"(w0 >> 32));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(mid) : "r"(a1), "r"(b0));
+    p0 = (u32)w0;
+    p1 = (u32)mid;
+    p2 = a1 * b1 + (u32)(mid >> 32);
+}
+
+// Product of two operand records -> 32-bit words of the magnitude (pw[0..8)); PW = words the product is known to fit
+template <int LW, int PW = 4>
 __device__ __forceinline__ void block_product_words(const uint4 &av, const uint4 &bv, const uint2 &ah, const uint2 &bh, u32 (&pw)[8])
 {
     const u64 ma = (u64)av.z | ((u64)av.w << 32), mb = (u64)bv.z | ((u64)bv.w << 32);
-    if (LW == 1) {
+    if (LW == 1 && PW <= 3) {
+        mul96(av.z, av.w, bv.z, bv.w, pw[0], pw[1], pw[2]);
+        pw[3] = pw[4] = pw[5] = pw[6] = pw[7] = 0u;
+    } else if (LW == 1) {
         const u64 plo = ma * mb, phi = __umul64hi(ma, mb);
         pw[0] = (u32)plo, pw[1] = (u32)(plo >> 32), pw[2] = (u32)phi, pw[3] = (u32)(phi >> 32);
         pw[4] = pw[5] = pw[6] = pw[7] = 0u;
@@ -1167,7 +1270,7 @@ __global__ void __launch_bounds__(1024, 1) k_block_acc(const AccArgs aa)
                 const uint2 bw = bm[slot >> 5];
                 const u32 e = bw.y + __popc(bw.x & ((1u << (slot & 31u)) - 1u)) - r0;
                 u32 pw[8];
-                block_product_words<LW>(av, bv, ah, bh, pw);
+                block_product_words<LW, PW>(av, bv, ah, bh, pw);
                 block_accumulate<NW, PW, SIGNED>(acc_s + e * 4u, wstride, pw, SIGNED && (((av.y ^ bv.y) & 1u) != 0));
             };
             block_walk_tiles(aa.tiles, next_s, tp1, lane, [&](const uint4 &t) {
@@ -1291,6 +1394,8 @@ struct DenseArgs {
     u32 U;                 // codes per zone (unit)
     u32 range;
     u32 pair_walk;         // one-limb operands: 1 = the accumulating walk takes two products at a time
+    u32 stage_off;         // byte offset in dynamic shared memory of the per-warp row buffers (32 x {2 x kStageRows x 16 B}) followed by
+                           // 64 mbarriers, or 0xFFFFFFFF when the rows of A are not staged
     const TruncDev *trunc;
     BlockGeo *geo;
 };
@@ -1324,6 +1429,15 @@ __global__ void __launch_bounds__(1024, 1) k_block_dense(const DenseArgs da)
     const u32 dlim = da.trunc ? __ldg(&da.trunc->dlim) : 0xFFFFFFFFu;
 
     for (u32 i = tid; i < a.cap * NW; i += kThreads) acc[i] = 0;
+    const bool staging = LW == 1 && da.pair_walk && da.stage_off != 0xFFFFFFFFu;
+    const u32 warp = tid >> 5;
+    u64 *bars = reinterpret_cast<u64 *>(zsmem + (staging ? da.stage_off : 0u) + 32u * 2u * kStageRows * 16u) + 2u * warp;
+    const u32 buf_s = smem_u32(zsmem + (staging ? da.stage_off : 0u)) + warp * 2u * kStageRows * 16u;
+    u32 phases = 0;
+    if (staging && lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+    }
     __syncthreads();
 
     for (;;) {
@@ -1341,27 +1455,34 @@ __global__ void __launch_bounds__(1024, 1) k_block_dense(const DenseArgs da)
         auto accumulate = [&](const uint4 &av, const uint4 &bv, const uint2 &ah, const uint2 &bh) {
             const u32 e = av.x + bv.x - zlo;
             u32 pw[8];
-            block_product_words<LW>(av, bv, ah, bh, pw);
+            block_product_words<LW, PW>(av, bv, ah, bh, pw);
             block_accumulate<NW, PW, SIGNED>(acc_s + e * 4u, wstride, pw, SIGNED && (((av.y ^ bv.y) & 1u) != 0));
         };
         // the same for two products at a time (one-limb operands): slots and products of both first, then the two
         // accumulation chains interleaved word by word
         auto accumulate2 = [&](const uint4 &av0, const uint4 &bv0, const uint4 &av1, const uint4 &bv1, bool on1) {
             const u32 e0 = av0.x + bv0.x - zlo, e1 = on1 ? av1.x + bv1.x - zlo : 0u;
-            const u64 ma0 = (u64)av0.z | ((u64)av0.w << 32), mb0 = (u64)bv0.z | ((u64)bv0.w << 32);
-            const u64 ma1 = (u64)av1.z | ((u64)av1.w << 32), mb1 = (u64)bv1.z | ((u64)bv1.w << 32);
-            const u64 lo0 = ma0 * mb0, hi0 = __umul64hi(ma0, mb0), lo1 = ma1 * mb1, hi1 = __umul64hi(ma1, mb1);
-            const u32 p0[4] = {(u32)lo0, (u32)(lo0 >> 32), (u32)hi0, (u32)(hi0 >> 32)};
-            const u32 p1[4] = {(u32)lo1, (u32)(lo1 >> 32), (u32)hi1, (u32)(hi1 >> 32)};
+            u32 p0[4], p1[4];
+            if (PW <= 3) { // products of at most 96 bits: the short multiply
+                mul96(av0.z, av0.w, bv0.z, bv0.w, p0[0], p0[1], p0[2]);
+                mul96(av1.z, av1.w, bv1.z, bv1.w, p1[0], p1[1], p1[2]);
+                p0[3] = p1[3] = 0u;
+            } else {
+                const u64 ma0 = (u64)av0.z | ((u64)av0.w << 32), mb0 = (u64)bv0.z | ((u64)bv0.w << 32);
+                const u64 ma1 = (u64)av1.z | ((u64)av1.w << 32), mb1 = (u64)bv1.z | ((u64)bv1.w << 32);
+                const u64 lo0 = ma0 * mb0, hi0 = __umul64hi(ma0, mb0), lo1 = ma1 * mb1, hi1 = __umul64hi(ma1, mb1);
+                p0[0] = (u32)lo0, p0[1] = (u32)(lo0 >> 32), p0[2] = (u32)hi0, p0[3] = (u32)(hi0 >> 32);
+                p1[0] = (u32)lo1, p1[1] = (u32)(lo1 >> 32), p1[2] = (u32)hi1, p1[3] = (u32)(hi1 >> 32);
+            }
             block_accumulate2<NW, (PW < 4 ? PW : 4), SIGNED>(acc_s + e0 * 4u, p0, SIGNED && (((av0.y ^ bv0.y) & 1u) != 0), true,
                                                              acc_s + e1 * 4u, p1, SIGNED && (((av1.y ^ bv1.y) & 1u) != 0), on1, wstride);
         };
-        block_walk_tiles(da.tiles, next_s, t1, lane, [&](const uint4 &t) {
+        auto tile_body = [&](const uint4 &t, u32 rows_s) {
             // (measured: fateman2, five-word chains, 3.63 -> 3.43 ms; fateman1 unchanged; degree-tested tiles 30 % slower,
             // so only the untested tiles take the pair walk)
             if (LW == 1 && da.pair_walk && !(t.z >> 31)) {
                 if (lane == 0) my_pairs += (u64)(t.z & 1023u) * ((t.z >> 10) & 127u);
-                block_tile_loop2(a.A, a.B, t, lane, accumulate2);
+                block_tile_loop2(a.A, a.B, t, lane, accumulate2, rows_s);
                 return;
             }
             if (t.z >> 31) { // truncation: test the degree of every product of this tile
@@ -1374,7 +1495,9 @@ __global__ void __launch_bounds__(1024, 1) k_block_dense(const DenseArgs da)
                 if (lane == 0) my_pairs += (u64)(t.z & 1023u) * ((t.z >> 10) & 127u);
                 block_tile_loop<2, LW>(a.A, a.B, a.A1, a.B1, t, lane, accumulate);
             }
-        });
+        };
+        if (staging) block_walk_tiles_staged(da.tiles, a.A, next_s, t1, lane, buf_s, bars, phases, tile_body);
+        else block_walk_tiles(da.tiles, next_s, t1, lane, [&](const uint4 &t) { tile_body(t, 0u); });
         __syncthreads();
 
         // ---- emit the slots of the zone in ascending code order: every thread owns a run of consecutive slots (odd
@@ -1487,6 +1610,7 @@ inline void block_configure(pk_ctx *ctx)
     t.merge = env_u32("PK_BLOCK_MERGE", t.merge);
     t.ctas = env_u32("PK_BLOCK_CTAS", t.ctas);
     t.size_hint = env_u32("PK_BLOCK_SIZE_HINT", t.size_hint);
+    t.stage_rows = env_u32("PK_BLOCK_STAGE_ROWS", t.stage_rows);
     const size_t dyn = ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0;
 #define X(nw, pw)                                 \
     BlockKernels<nw, pw, false, 1>::set_smem(dyn); \
@@ -1509,6 +1633,7 @@ struct BlockPlan {
     u32 cap = 0, bm_words = 0;
     u32 off_acc = 0, off_bm = 0, raw_off = 0;
     u32 ctas = 1;  // sparse: thread blocks per SM of the accumulating kernel (1024 / ctas threads each)
+    u32 stage_off = 0xFFFFFFFFu; // dense: offset of the staged-walk row buffers in dynamic shared memory
     size_t smem = 0;
 };
 
@@ -1610,6 +1735,14 @@ inline bool block_layout(pk_ctx *ctx, BlockPlan &bp, u64 unit_codes)
         bp.off_acc = 0;
         off = (size_t)bp.cap * NW * 4;
         bp.bm_words = 0;
+        // per-warp row buffers of the staged walk, when the accumulators leave room for them
+        const size_t stage_bytes = 32u * 2u * kStageRows * 16u + 64u * 8u;
+        bp.stage_off = 0xFFFFFFFFu;
+        if (ctx->block_tuning.stage_rows && ((off + 15) & ~15ull) + stage_bytes <= budget) {
+            off = (off + 15) & ~15ull;
+            bp.stage_off = (u32)off;
+            off += stage_bytes;
+        }
     } else {
         bp.bm_words = kAccBitmapWords / bp.ctas;
         bp.off_bm = 0;
@@ -2066,6 +2199,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     da.U = (u32)U;
     da.range = (u32)pl.range;
     da.pair_walk = bt.pair_walk;
+    da.stage_off = bp.stage_off;
     da.trunc = trunc ? td : nullptr;
     da.geo = geo;
     for (int attempt = 0;; ++attempt) {

@@ -142,6 +142,32 @@ float time_ms(F f, int reps = 5)
     return best;
 }
 
+// 64-bit shared-memory atomics: MODE 0 fire-and-forget, MODE 1 two-word (128-bit) accumulator with the carry taken from the
+// returned value -- the alternative to three / four 32-bit words per accumulator.
+template <int MODE>
+__global__ void k_smem_atomics64(u32 *out, int iters, u32 words_mask)
+{
+    extern __shared__ u64 s64[];
+    for (u32 i = threadIdx.x; i <= words_mask; i += blockDim.x) s64[i] = 0;
+    __syncthreads();
+    u32 seed = blockIdx.x * 9781u + threadIdx.x * 7u + 1u;
+    u64 sink = 0;
+    for (int it = 0; it < iters; ++it) {
+        const u32 r = lcg(seed);
+        const u32 base = r >> 8;
+        const u64 v = ((u64)r << 24) | 1ull;
+        if (MODE == 0) {
+            atomicAdd(&s64[base & words_mask], v);
+        } else {
+            const u64 old = atomicAdd(&s64[base & words_mask], v);
+            const u64 carry = (old + v < v) ? 1ull : 0ull;
+            atomicAdd(&s64[(base + 1u) & words_mask], (u64)(r & 0xFFFu) + carry);
+            sink += old;
+        }
+    }
+    if (sink == 0x1234567ull) out[0] = (u32)sink;
+}
+
 // MODE 0: IMAD (mad.lo.u32), MODE 1: IMAD.WIDE (mad.wide.u32), MODE 2: 64 x 64 -> 128 product (mul.lo.u64 + mul.hi.u64), with
 // CHAINS independent dependency chains per thread so that the pipe, not the latency, is measured.
 template <int MODE, int CHAINS>
@@ -265,6 +291,26 @@ int main()
             printf("gather16 table=%zuMB: %.3f ms, %.2f Gload/s\n", bytes >> 20, t, n / t * 1e-6);
         }
         CK(cudaFree(tab));
+    }
+    // ---- 64-bit shared atomics
+    {
+        const int iters = 4096, threads = 1024;
+        const u32 mask = (1u << 13) - 1;
+        const size_t smem = (size_t)(mask + 1) * 8;
+        CK(cudaFuncSetAttribute(k_smem_atomics64<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(k_smem_atomics64<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        for (int mode = 0; mode < 2; ++mode) {
+            auto launch = [&]() {
+                if (mode == 0) k_smem_atomics64<0><<<sms, threads, smem>>>(d_out, iters, mask);
+                else k_smem_atomics64<1><<<sms, threads, smem>>>(d_out, iters, mask);
+            };
+            const float ms = time_ms(launch);
+            CK(cudaGetLastError());
+            const double ops = (double)sms * threads * iters * (mode ? 2.0 : 1.0);
+            printf("smem_atomics64 mode=%d (%s): %.3f ms, %.1f Gatom/s chip, %.2f atom/clk/SM @%.0f MHz\n", mode,
+                   mode ? "random, 2-word carry chain" : "random, fire-and-forget", ms, ops / ms * 1e-6,
+                   ops / ms * 1e-6 / (double)sms / (prop.clockRate * 1e-6), prop.clockRate * 1e-3);
+        }
     }
     // ---- INT32 multiply pipe
     {
