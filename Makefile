@@ -5,7 +5,7 @@ CXXFLAGS ?= -std=c++17 -O2 -Wall -Wextra -pthread
 LIB := piranha_b200/lib/libpiranha_b200.so
 HOST_HDRS := $(wildcard piranha_b200/host/*.hpp) include/piranha_b200.h
 BIN := build/bin
-PROGS := $(BIN)/host_logic_test $(BIN)/multiplier_test $(BIN)/fateman1 $(BIN)/fateman2 $(BIN)/pearce1 $(BIN)/fateman1_rational $(BIN)/pearce1_rational
+PROGS := $(BIN)/host_logic_test $(BIN)/multiplier_test $(BIN)/fateman1 $(BIN)/fateman2 $(BIN)/pearce1 $(BIN)/fateman1_rational $(BIN)/pearce1_rational $(BIN)/fateman1_dynamic
 LINK := -Lpiranha_b200/lib -lpiranha_b200 -Wl,-rpath,'$$ORIGIN/../../piranha_b200/lib'
 
 all: $(LIB) oracle host

@@ -42,8 +42,11 @@ extern "C" {
 #define PK_E_ARGS 1      /* std::invalid_argument: mismatched n_vars, bad sizes, bad options */
 #define PK_E_KEY_RANGE 2 /* std::overflow_error "Kronecker monomial components are out of bounds"
                             (check_bounds, polynomial.hpp:1118-1194) */
-#define PK_E_CF_WIDTH 3  /* coefficient bound exceeds the supported fixed accumulator width; never a silent wrap
-                            (the reference promotes to heap mpz instead, integer.hpp:67-85) */
+#define PK_E_CF_WIDTH 3  /* coefficient wider than the library computes: operands of more than 4 limbs (256 bits) or a result
+                            bound of more than 9 limbs.  Never a silent wrap and never a CPU computation (the reference promotes
+                            to heap mpz instead, integer.hpp:67-85).  Width protocol: operands of 1-2 limbs run on the pairing
+                            kernels (results up to 5 limbs); operands of 3-4 limbs are multiplied as 128-bit halves through the
+                            same kernels and summed with shifts on the device (benchmarks/fateman1_dynamic.cpp chains) */
 #define PK_E_NOMEM 4     /* std::bad_alloc */
 #define PK_E_CUDA 5      /* std::runtime_error: CUDA failure, or no sm_100 device present */
 #define PK_E_DEGREE 6    /* std::overflow_error from the checked degree subtraction of the truncation logic
@@ -67,7 +70,7 @@ typedef struct pk_dpoly pk_dpoly; /* a polynomial resident in HBM (sorted by key
 typedef struct pk_poly {
     uint64_t n;          /* number of terms (series::size()) */
     uint32_t n_vars;     /* size of the symbol set (m_ss.size()) */
-    uint32_t limbs;      /* 64-bit limbs per coefficient magnitude, 1..2 for operands (results: up to 5) */
+    uint32_t limbs;      /* 64-bit limbs per coefficient magnitude, 1..4 for operands (results: up to 9) */
     const int64_t *key;  /* n Kronecker codes, any order (hash_set order is unspecified) */
     const uint64_t *mag; /* n * limbs */
     const int8_t *sign;  /* n */

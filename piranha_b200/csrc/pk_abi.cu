@@ -2,12 +2,14 @@
 // orchestration, result download.  The CUDA kernels live in pk_kernels.cuh (HBM/L2 accumulators) and
 // pk_zone.cuh (shared-memory zones).  There is no CPU fallback: every product is computed by the kernels.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "../host/kronecker_array.hpp"
 #include "pk_host.cuh"
 #include "pk_kernels.cuh"
 #include "pk_zone.cuh"
 #include "pk_block.cuh"
+#include "pk_wide.cuh"
 
 using namespace pk;
 
@@ -105,7 +107,7 @@ pk_dpoly *upload_impl(pk_ctx *ctx, const pk_poly *p)
 {
     if (!p) fail(PK_E_ARGS, "null polynomial");
     if (p->n_vars >= ctx->limits.size()) fail(PK_E_ARGS, "too many variables for the Kronecker codification");
-    if (p->limbs < 1 || p->limbs > 2) fail(PK_E_CF_WIDTH, "operand coefficients must have 1 or 2 limbs");
+    if (p->limbs < 1 || p->limbs > 4) fail(PK_E_CF_WIDTH, "operand coefficients must have 1 to 4 limbs");
     if (p->n >= (1ull << 32)) fail(PK_E_ARGS, "operand too large");
     if (p->n && (!p->key || !p->mag || !p->sign)) fail(PK_E_ARGS, "null term arrays");
     const u64 n = p->n;
@@ -278,6 +280,8 @@ void launch_mul_global(pk_ctx *ctx, const Plan &pl, const MulArgs &args)
     else PK_LAUNCH(ctx, (k_mul_global<MODE, 2, 2, FILTER>), grid, kMulThreads, 0, args);
 }
 
+pk_dpoly *wide_multiply(pk_ctx *ctx, pk_dpoly *A, pk_dpoly *B, const pk_opts *opts_in);
+
 pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in)
 {
     pk_opts o{};
@@ -313,6 +317,8 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
     }
     ensure_meta(ctx, A);
     ensure_meta(ctx, B);
+    // operands of three or four limbs: 128-bit halves through the same kernels, summed with shifts (pk_wide.cuh)
+    if (A->max_bits > 128 || B->max_bits > 128) return wide_multiply(ctx, A, B, opts_in);
     Plan pl = make_plan(ctx, A, B, o);
     const bool trunc = o.trunc_mode != 0;
     const u64 nA = A->n, nB = B->n;
@@ -539,6 +545,143 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
     ctx->stats.result_limbs = rg.p->limbs;
     ctx->stats.kernel_launches = ctx->call_launches;
     return rg.release();
+}
+
+// a * b for operands of up to four limbs (see pk_wide.cuh)
+pk_dpoly *wide_multiply(pk_ctx *ctx, pk_dpoly *A, pk_dpoly *B, const pk_opts *opts_in)
+{
+    if (A->max_bits > 256 || B->max_bits > 256) fail(PK_E_CF_WIDTH, "operand coefficient wider than 4 limbs");
+    const u32 nv = A->n_vars;
+    // 128-bit halves as views of the operand's arrays (a half that is all zero contributes nothing and is skipped)
+    struct Half {
+        pk_dpoly v;
+        u32 shift = 0;
+        bool used = false;
+    };
+    Half hA[2], hB[2];
+    auto make_views = [&](pk_dpoly *P, Half (&h)[2]) {
+        for (u32 k = 0; k < 2; ++k) {
+            if (P->limbs <= 2 * k) continue;
+            pk_dpoly &v = h[k].v;
+            v.n = P->n;
+            v.stride = P->stride;
+            v.n_vars = P->n_vars;
+            v.limbs = std::min<u32>(2, P->limbs - 2 * k);
+            v.alloc_limbs = v.limbs;
+            v.key = P->key;
+            v.planes = P->planes + (u64)2 * k * P->stride;
+            v.sign = P->sign;
+            v.has_meta = false;
+            ensure_meta(ctx, &v);
+            h[k].shift = 2 * k;
+            h[k].used = v.max_bits != 0;
+        }
+    };
+    make_views(A, hA);
+    make_views(B, hB);
+    std::vector<pk_dpoly *> parts;
+    std::vector<u32> shifts;
+    struct PartsGuard {
+        pk_ctx *ctx;
+        std::vector<pk_dpoly *> &v;
+        ~PartsGuard()
+        {
+            for (pk_dpoly *p : v)
+                if (p) {
+                    free_dpoly_arrays(ctx, p);
+                    delete p;
+                }
+        }
+    } guard{ctx, parts};
+    pk_stats first{};
+    float kernel_ms = 0.f;
+    for (u32 i = 0; i < 2; ++i)
+        for (u32 j = 0; j < 2; ++j) {
+            if (!hA[i].used || !hB[j].used) continue;
+            parts.push_back(mul_impl(ctx, &hA[i].v, &hB[j].v, opts_in));
+            shifts.push_back(hA[i].shift + hB[j].shift);
+            pk_stats st{};
+            ctx->stats.total_launches = ctx->total_launches;
+            if (parts.size() == 1) first = ctx->stats;
+            float ms = 0.f;
+            if (ctx->ev_valid && cudaEventSynchronize(ctx->ev_end) == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev_mul0, ctx->ev_mul1) == cudaSuccess)
+                kernel_ms += ms;
+            (void)st;
+        }
+    // restore the views' borrowed pointers before they go out of scope (they own nothing)
+    u64 total = 0;
+    for (pk_dpoly *p : parts) total += p->n;
+    const u32 cnt_bits = bit_length(std::min(A->n, B->n));
+    const u32 out_limbs = std::max<u32>(1, (A->max_bits + B->max_bits + cnt_bits + 63) / 64);
+    if (out_limbs + 1 > kWideLimbs) fail(PK_E_CF_WIDTH, "coefficient bound exceeds the accumulator width");
+    if (total >= (1ull << 30)) fail(PK_E_NOMEM, "wide product too large for the reduce pass");
+    if (total == 0) {
+        pk_dpoly *r = new_dpoly(ctx, 0, nv, 1);
+        r->has_meta = true;
+        r->emin.assign(nv, 0);
+        r->emax.assign(nv, 0);
+        r->egcd.assign(nv, 0);
+        return r;
+    }
+    WideSrc w{};
+    w.n_parts = (u32)parts.size();
+    w.h_min = nv ? ctx->h_min[nv] : 0;
+    u64 off = 0;
+    for (u32 s = 0; s < w.n_parts; ++s) {
+        w.key[s] = parts[s]->key;
+        w.planes[s] = parts[s]->planes;
+        w.sign[s] = parts[s]->sign;
+        w.stride[s] = parts[s]->stride;
+        w.limbs[s] = parts[s]->limbs;
+        w.shift[s] = shifts[s];
+        w.off[s] = off;
+        off += parts[s]->n;
+    }
+    for (u32 s = w.n_parts; s <= kWideMaxParts; ++s) w.off[s] = off;
+    DevBuf k0(ctx, total * 8), k1(ctx, total * 8), s0(ctx, total * 4), s1(ctx, total * 4), head(ctx, total * 4), upos(ctx, total * 4);
+    PK_LAUNCH(ctx, k_wide_collect, grid_for(total, 256), 256, 0, w, k0.as<u64>(), s0.as<u32>());
+    const unsigned __int128 span = nv ? (unsigned __int128)((__int128)ctx->h_max[nv] - ctx->h_min[nv]) : 0;
+    radix_sort_pairs(ctx, k0.as<u64>(), k1.as<u64>(), s0.as<u32>(), s1.as<u32>(), total, (int)std::max<u32>(1, bit_length(span)));
+    PK_LAUNCH(ctx, k_wide_heads, grid_for(total, 256), 256, 0, k1.as<u64>(), total, head.as<u32>());
+    auto exclusive_sum = [&](const u32 *in, u32 *out, u64 n) {
+        size_t tmp_bytes = 0;
+        CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (int)n, ctx->stream));
+        DevBuf tmp(ctx, tmp_bytes);
+        CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, in, out, (int)n, ctx->stream));
+    };
+    exclusive_sum(head.as<u32>(), upos.as<u32>(), total);
+    u32 *h2 = reinterpret_cast<u32 *>(static_cast<char *>(ctx->h_scratch) + 3072);
+    auto last_plus = [&](const u32 *scan, const u32 *flag, u64 n) -> u64 { // exclusive scan value + flag of the last element
+        readback(ctx, h2, scan + (n - 1), 4);
+        readback(ctx, h2 + 1, flag + (n - 1), 4);
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        return (u64)h2[0] + h2[1];
+    };
+    const u64 n_unique = last_plus(upos.as<u32>(), head.as<u32>(), total);
+    DevBuf tkey(ctx, n_unique * 8), tmag(ctx, n_unique * kWideLimbs * 8), tsign(ctx, n_unique), tnz(ctx, n_unique * 4), pos(ctx, n_unique * 4);
+    CUDA_CHECK(cudaMemsetAsync(&ctx->d_ctr->max_bits, 0, 4, ctx->stream));
+    PK_LAUNCH(ctx, k_wide_reduce, grid_for(total, 256), 256, 0, w, k1.as<u64>(), s1.as<u32>(), head.as<u32>(), upos.as<u32>(), total,
+              tkey.as<u64>(), tmag.as<u64>(), tsign.as<signed char>(), tnz.as<u32>(), &ctx->d_ctr->max_bits);
+    exclusive_sum(tnz.as<u32>(), pos.as<u32>(), n_unique);
+    const u64 n_out = last_plus(pos.as<u32>(), tnz.as<u32>(), n_unique);
+    DPolyGuard res{ctx, new_dpoly(ctx, n_out, nv, out_limbs)};
+    if (n_out)
+        PK_LAUNCH(ctx, k_wide_compact, grid_for(n_unique, 256), 256, 0, tkey.as<u64>(), tmag.as<u64>(), tsign.as<signed char>(), tnz.as<u32>(),
+                  pos.as<u32>(), n_unique, w.h_min, res.p->key, res.p->planes, res.p->stride, res.p->sign, out_limbs);
+    readback(ctx, h2, &ctx->d_ctr->max_bits, 4);
+    CUDA_CHECK(cudaEventRecord(ctx->ev_end, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    res.p->max_bits = h2[0];
+    res.p->limbs = std::max<u32>(1, std::min<u32>(out_limbs, (h2[0] + 63) / 64));
+    // statistics of the whole product: the pair count of one half product (all have the same pairs), times of all
+    ctx->stats = first;
+    ctx->stats.result_terms = n_out;
+    ctx->stats.result_limbs = res.p->limbs;
+    ctx->stats.kernel_launches = ctx->call_launches;
+    ctx->stats.retries = (u32)parts.size() << 16 | (first.retries & 0xFFFFu);
+    ctx->ev_valid = false;
+    ctx->stats.mul_kernel_ms = kernel_ms;
+    return res.release();
 }
 
 } // namespace

@@ -104,7 +104,7 @@ def test_reference_multiplier_tests_through_operator_star():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("prog,size", [("fateman1", 135751), ("pearce1", 5821335), ("fateman2", 635376),
-                                       ("fateman1_rational", 135751), ("pearce1_rational", 5821335)])
+                                       ("fateman1_rational", 135751), ("pearce1_rational", 5821335), ("fateman1_dynamic", 135751)])
 def test_cpp_benchmarks(prog, size):
     """benchmarks/*.cpp: operands built by repeated operator*=, the final product timed, the result size checked
     against the reference's known answer (benchmarks/fateman1.cpp:55, pearce1.cpp:56, fateman2.cpp:55,

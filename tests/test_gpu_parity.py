@@ -887,3 +887,65 @@ def test_upload_rejects_invalid_terms(ctx):
     full = {(1, 2): 3, (0, 1): -5}
     keep = {e: c for e, c in full.items() if po.kron_encode(e) != int(ok[0][0])}
     assert_terms_equal(r, oracle_terms(po.p_mul(keep, full), 2))
+
+
+def _random_wide_poly(rs, n, bits, nv=3, signed=True):
+    p = {}
+    while len(p) < n:
+        e = tuple(int(x) for x in rs.randint(0, 7, size=nv))
+        c = int.from_bytes(rs.bytes((bits + 7) // 8), "little") >> ((8 - bits % 8) % 8) or 1
+        p[e] = -c if (signed and rs.randint(2)) else c
+    return p
+
+
+@pytest.mark.parametrize("bits_a,bits_b", [(200, 60), (256, 256), (130, 129), (129, 1), (192, 190)])
+def test_wide_operands(ctx, bits_a, bits_b):
+    """Operands of three and four limbs (the width protocol of the C ABI: 128-bit halves through the pairing kernels, summed
+    with shifts on the device), against the exact Python oracle; also as an output partition and truncated."""
+    rs = np.random.RandomState(bits_a * 1000 + bits_b)
+    nv = 3
+    f, g = _random_wide_poly(rs, 300, bits_a), _random_wide_poly(rs, 250, bits_b)
+    a, b = terms(f, nv, 1), terms(g, nv, 2)
+    assert a[1].shape[1] == (bits_a + 63) // 64
+    want = oracle_terms(po.p_mul(f, g), nv)
+    got = ctx.mul(a, b, nv)
+    assert_sorted_unique(got[0])
+    assert_terms_equal(got, want)
+    parts = [ctx.mul(a, b, nv, part_index=r, part_count=3) for r in range(3)]
+    L = max(p[1].shape[1] for p in parts)
+    cat = (np.concatenate([p[0] for p in parts]), np.concatenate([np.pad(p[1], ((0, 0), (0, L - p[1].shape[1]))) for p in parts]),
+           np.concatenate([p[2] for p in parts]))
+    assert_sorted_unique(cat[0])
+    assert_terms_equal(cat, want)
+    got_t = ctx.mul(a, b, nv, trunc_mode=1, max_degree=9)
+    assert_terms_equal(got_t, oracle_terms(po.p_mul(f, g, max_degree=9), nv))
+
+
+def test_wide_chain_and_limit(ctx):
+    """benchmarks/fateman1_dynamic.cpp: operands scaled by 2^64 - 1; the product (4 limbs) is multiplied on, device resident;
+    beyond four operand limbs the library reports PK_E_CF_WIDTH (std::overflow_error), it never wraps."""
+    nv = 4
+    f, _ = po.fateman_operands(4)
+    k = 2 ** 64 - 1
+    f = {e: c * k for e, c in f.items()}
+    g = dict(f)
+    g[(0, 0, 0, 0)] = g.get((0, 0, 0, 0), 0) + 1
+    df, dg = ctx.upload(terms(f, nv, 1), nv), ctx.upload(terms(g, nv, 2), nv)
+    p1 = ctx.mul_dev(df, dg)           # two-limb operands: the pairing kernels
+    p2 = ctx.mul_dev(p1, df)           # three-limb operand x two-limb operand: halves
+    ref1 = po.p_mul(f, g)
+    ref2 = po.p_mul(ref1, f)
+    assert_terms_equal(p1.download(), oracle_terms(ref1, nv))
+    assert_terms_equal(p2.download(), oracle_terms(ref2, nv))
+    p3 = ctx.mul_dev(p2, p1)           # four-limb x three-limb operands: still inside the protocol (result of six limbs)
+    assert_terms_equal(p3.download(), oracle_terms(po.p_mul(ref2, ref1), nv))
+    assert p1.limbs == 3 and p2.limbs == 4 and p3.limbs > 4
+    with pytest.raises(OverflowError):
+        ctx.mul_dev(p3, p3)            # operands of more than four limbs: reported, never wrapped
+    m = pb.Context.multi(_multi_devices(2))
+    try:
+        rs = np.random.RandomState(3)
+        fa, fb = _random_wide_poly(rs, 200, 250), _random_wide_poly(rs, 200, 250)
+        assert_terms_equal(m.mul(terms(fa, 3, 1), terms(fb, 3, 2), 3), oracle_terms(po.p_mul(fa, fb), 3))
+    finally:
+        m.close()
