@@ -146,11 +146,42 @@ void multi_require(const pk_ctx *M, const pk_dpoly *p)
     if (!p->is_multi || (p->rep.size() != M->subs.size())) fail(PK_E_ARGS, "polynomial does not belong to this multi-device context");
 }
 
+// a copy of `src` (complete, on device src_dev) on sub's device: peer-to-peer over NVLink, metadata from the host struct
+pk_dpoly *replicate_single(pk_ctx *sub, const pk_dpoly *src, int src_dev)
+{
+    DPolyGuard d{sub, new_dpoly(sub, src->n, src->n_vars, src->limbs)};
+    if (src->n) {
+        CUDA_CHECK(cudaMemcpyPeerAsync(d.p->key, sub->device, src->key, src_dev, src->n * 8, sub->stream));
+        for (u32 l = 0; l < src->limbs; ++l)
+            CUDA_CHECK(cudaMemcpyPeerAsync(d.p->planes + (u64)l * d.p->stride, sub->device, src->planes + (u64)l * src->stride, src_dev,
+                                           src->n * 8, sub->stream));
+        CUDA_CHECK(cudaMemcpyPeerAsync(d.p->sign, sub->device, src->sign, src_dev, src->n, sub->stream));
+    }
+    d.p->has_meta = src->has_meta;
+    d.p->emin = src->emin;
+    d.p->emax = src->emax;
+    d.p->egcd = src->egcd;
+    d.p->max_bits = src->max_bits;
+    d.p->any_neg = src->any_neg;
+    d.p->any_zero = src->any_zero;
+    return d.release();
+}
+
+// Host polynomial -> every device: ONE upload (device 0: host-to-device copy, exponent bounds, sort), then peer copies.
+// (Measured on 8 GPUs: eight concurrent uploads of the same pageable host arrays contend in the driver, 0.8 ms against
+// 0.35 ms for one.)
 pk_dpoly *multi_upload(pk_ctx *M, const pk_poly *p)
 {
     if (!p) fail(PK_E_ARGS, "null polynomial");
     MultiGuard g{M, multi_new(M, p->n_vars)};
-    multi_run(M, [&](u32 r) { g.p->rep[r] = upload_impl(M->subs[r], p); });
+    multi_run(M, [&](u32 r) {
+        if (r == 0) g.p->rep[0] = upload_impl(M->subs[0], p);
+    });
+    multi_run(M, [&](u32 r) {
+        if (r == 0) return;
+        g.p->rep[r] = replicate_single(M->subs[r], g.p->rep[0], M->subs[0]->device);
+        CUDA_CHECK(cudaStreamSynchronize(M->subs[r]->stream));
+    });
     g.p->n = g.p->rep[0]->n;
     g.p->limbs = g.p->rep[0]->limbs;
     return g.release();
@@ -348,17 +379,32 @@ void multi_mul(pk_ctx *M, const pk_poly *a, const pk_poly *b, const pk_opts *opt
     std::vector<double> t_up(N, 0.0), t_mul(N, 0.0);
     MultiGuard g{M, multi_new(M, a->n_vars)};
     g.p->part.assign(N, nullptr);
+    // the operands go to device 0 (and, when there are many devices, device 1 takes the second operand) and are
+    // replicated peer-to-peer; then every device multiplies its part
+    const u32 b_home = (N > 1 && a != b) ? 1u : 0u;
+    struct HomeGuard { // (freed with the owning device current, whichever thread unwinds)
+        pk_ctx *sub;
+        pk_dpoly *p = nullptr;
+        ~HomeGuard() { free_single(sub, p); }
+    } a0{M->subs[0]}, b0{M->subs[b_home]};
+    multi_run(M, [&](u32 r) {
+        const auto w0 = std::chrono::steady_clock::now();
+        if (r == 0) a0.p = upload_impl(M->subs[0], a);
+        if (r == b_home && a != b) b0.p = upload_impl(M->subs[b_home], b);
+        t_up[r] = ms_since(w0);
+    });
     multi_run(M, [&](u32 r) {
         pk_ctx *sub = M->subs[r];
         const auto w0 = std::chrono::steady_clock::now();
-        DPolyGuard da{sub, upload_impl(sub, a)};
-        DPolyGuard db{sub, (a == b) ? nullptr : upload_impl(sub, b)};
-        t_up[r] = ms_since(w0);
+        DPolyGuard da{sub, r == 0 ? nullptr : replicate_single(sub, a0.p, M->subs[0]->device)};
+        DPolyGuard db{sub, (a == b || r == b_home) ? nullptr : replicate_single(sub, b0.p, M->subs[b_home]->device)};
+        pk_dpoly *pa = r == 0 ? a0.p : da.p;
+        pk_dpoly *pb = (a == b) ? pa : (r == b_home ? b0.p : db.p);
         pk_opts o = o0;
         o.part_index = r;
         o.part_count = N;
-        g.p->part[r] = mul_impl(sub, da.p, db.p ? db.p : da.p, &o);
-        t_mul[r] = ms_since(w0);
+        g.p->part[r] = mul_impl(sub, pa, pb, &o);
+        t_mul[r] = t_up[r] + ms_since(w0);
     });
     const double t_phase1 = ms_since(t0);
     g.p->n = 0;
