@@ -52,6 +52,10 @@ extern "C" {
 #define PK_E_DEGREE 6    /* std::overflow_error from the checked degree subtraction of the truncation logic
                             (degree_sub -> safe_int_sub, polynomial.hpp:1243-1252, :1504) */
 
+#define PK_E_UNSUPPORTED 7 /* std::runtime_error: a product the reference would compute but this library does not handle -- exponent
+                            spans whose re-encoded code range reaches 2^62 (e.g. 1 + x + x^(2^62)), operands of 2^32 terms or
+                            more.  Distinct from PK_E_KEY_RANGE: the Kronecker bounds hold, nothing overflowed */
+
 #define PK_MAX_VARS 40u  /* kronecker_array<int64_t> supports < 40 components */
 
 /* Accumulation strategy (pk_opts.algo). */

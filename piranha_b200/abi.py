@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpiranha_b200.so")
 
-PK_OK, PK_E_ARGS, PK_E_KEY_RANGE, PK_E_CF_WIDTH, PK_E_NOMEM, PK_E_CUDA, PK_E_DEGREE = range(7)
+PK_OK, PK_E_ARGS, PK_E_KEY_RANGE, PK_E_CF_WIDTH, PK_E_NOMEM, PK_E_CUDA, PK_E_DEGREE, PK_E_UNSUPPORTED = range(8)
 PK_ALGO_AUTO, PK_ALGO_DENSE, PK_ALGO_HASH, PK_ALGO_ZONE, PK_ALGO_BLOCK = range(5)
 ALGO_NAMES = {0: "auto", 1: "dense", 2: "hash", 3: "zone", 4: "block"}
 

@@ -108,7 +108,7 @@ pk_dpoly *upload_impl(pk_ctx *ctx, const pk_poly *p)
     if (!p) fail(PK_E_ARGS, "null polynomial");
     if (p->n_vars >= ctx->limits.size()) fail(PK_E_ARGS, "too many variables for the Kronecker codification");
     if (p->limbs < 1 || p->limbs > 4) fail(PK_E_CF_WIDTH, "operand coefficients must have 1 to 4 limbs");
-    if (p->n >= (1ull << 32)) fail(PK_E_ARGS, "operand too large");
+    if (p->n >= (1ull << 32)) fail(PK_E_UNSUPPORTED, "operands of 2^32 terms or more are not supported");
     if (p->n && (!p->key || !p->mag || !p->sign)) fail(PK_E_ARGS, "null term arrays");
     const u64 n = p->n;
     DPolyGuard g{ctx, new_dpoly(ctx, n, p->n_vars, p->limbs)};
@@ -137,7 +137,7 @@ pk_dpoly *upload_impl(pk_ctx *ctx, const pk_poly *p)
         cp.step[v] = (i64)gs;
         cp.stride[v] = (u64)range;
         range *= (u64)(g.p->emax[v] - g.p->emin[v]) / gs + 1;
-        if (range >= ((unsigned __int128)1 << 62)) fail(PK_E_KEY_RANGE, "exponent spans too wide to re-encode");
+        if (range >= ((unsigned __int128)1 << 62)) fail(PK_E_UNSUPPORTED, "exponent spans too wide to re-encode (code range of 2^62 or more)");
     }
     DevBuf fk(ctx, n * 8), fk2(ctx, n * 8), idx(ctx, n * 4), idx2(ctx, n * 4);
     PK_LAUNCH(ctx, k_prepare, grid_for(n, 256), 256, 0, raw_key.as<i64>(), raw_sign.as<signed char>(), n, cp, fk.as<u64>(),
@@ -226,11 +226,13 @@ Plan make_plan(pk_ctx *ctx, const pk_dpoly *A, const pk_dpoly *B, const pk_opts 
     pl.cpA.trunc_mode = pl.cpB.trunc_mode = (u32)o.trunc_mode;
     unsigned __int128 range = 1;
     __int128 base = 0;
-    for (u32 v = 0; v < nv; ++v) {
+    for (u32 v = 0; v < nv; ++v) { // check_bounds first, for every variable (polynomial.hpp:1189-1193): its error wins
         const __int128 lo = (__int128)A->emin[v] + B->emin[v], hi = (__int128)A->emax[v] + B->emax[v];
         const i64 M = ctx->limits[nv][v];
-        // check_bounds, polynomial.hpp:1189-1193
         if (lo < -(__int128)M || hi > (__int128)M) fail(PK_E_KEY_RANGE, "Kronecker monomial components are out of bounds");
+    }
+    for (u32 v = 0; v < nv; ++v) {
+        const __int128 lo = (__int128)A->emin[v] + B->emin[v];
         u64 g = gcd64(A->egcd[v], B->egcd[v]);
         if (g == 0) g = 1;
         const u64 span = (u64)(A->emax[v] - A->emin[v]) + (u64)(B->emax[v] - B->emin[v]);
@@ -246,7 +248,7 @@ Plan make_plan(pk_ctx *ctx, const pk_dpoly *A, const pk_dpoly *B, const pk_opts 
         const bool counts = o.trunc_mode == 1 || (o.trunc_mode == 2 && o.degree_mask && o.degree_mask[v]);
         pl.cpA.mask[v] = pl.cpB.mask[v] = counts ? 1 : 0;
         range *= tr;
-        if (range >= ((unsigned __int128)1 << 62)) fail(PK_E_KEY_RANGE, "re-encoded code range overflow");
+        if (range >= ((unsigned __int128)1 << 62)) fail(PK_E_UNSUPPORTED, "exponent spans too wide to re-encode (code range of 2^62 or more)");
         base += lo * (__int128)pl.cpR.pstride[v];
     }
     pl.base_code = (i64)base;
@@ -258,7 +260,7 @@ Plan make_plan(pk_ctx *ctx, const pk_dpoly *A, const pk_dpoly *B, const pk_opts 
     if (pl.LA > 2 || pl.LB > 2) fail(PK_E_CF_WIDTH, "operand coefficient wider than 2 limbs");
     pl.prod_bits = std::max<u32>(1, A->max_bits + B->max_bits);
     pl.cnt_bits = bit_length(std::min(A->n, B->n));
-    if (pl.cnt_bits > 31) fail(PK_E_ARGS, "operands too large");
+    if (pl.cnt_bits > 31) fail(PK_E_UNSUPPORTED, "operands of 2^31 terms or more are not supported");
     pl.cbits = std::min<u32>(62, 63 - pl.cnt_bits);
     pl.nl = (pl.prod_bits + pl.cbits - 1) / pl.cbits;
     pl.out_limbs = (pl.prod_bits + pl.cnt_bits + 63) / 64;
@@ -272,7 +274,7 @@ void launch_mul_global(pk_ctx *ctx, const Plan &pl, const MulArgs &args)
     const u32 R = (pl.LA + pl.LB == 2) ? 8 : 4;
     const u32 TI = (kMulThreads / 32) * R;
     const u64 tiles = ((args.nA + TI - 1) / TI) * ((args.nB + kTileJ - 1) / kTileJ);
-    if (tiles >= (1ull << 31)) fail(PK_E_ARGS, "grid too large");
+    if (tiles >= (1ull << 31)) fail(PK_E_UNSUPPORTED, "product too large for the HBM-accumulator kernels (2^31 tiles or more)");
     const u32 grid = (u32)tiles;
     if (pl.LA == 1 && pl.LB == 1) PK_LAUNCH(ctx, (k_mul_global<MODE, 1, 1, FILTER>), grid, kMulThreads, 0, args);
     else if (pl.LA == 2 && pl.LB == 1) PK_LAUNCH(ctx, (k_mul_global<MODE, 2, 1, FILTER>), grid, kMulThreads, 0, args);

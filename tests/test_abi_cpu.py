@@ -48,7 +48,7 @@ def test_struct_layouts_match_the_header(tmp_path):
         for fname, _ in cls._fields_:
             assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
     src = open(HEADER).read()
-    for code, name in enumerate(["PK_OK", "PK_E_ARGS", "PK_E_KEY_RANGE", "PK_E_CF_WIDTH", "PK_E_NOMEM", "PK_E_CUDA", "PK_E_DEGREE"]):
+    for code, name in enumerate(["PK_OK", "PK_E_ARGS", "PK_E_KEY_RANGE", "PK_E_CF_WIDTH", "PK_E_NOMEM", "PK_E_CUDA", "PK_E_DEGREE", "PK_E_UNSUPPORTED"]):
         assert re.search(rf"#define {name} {code}\b", src), name
         assert getattr(abi, name) == code
     for code, name in enumerate(["PK_ALGO_AUTO", "PK_ALGO_DENSE", "PK_ALGO_HASH", "PK_ALGO_ZONE", "PK_ALGO_BLOCK"]):

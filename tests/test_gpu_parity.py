@@ -949,3 +949,17 @@ def test_wide_chain_and_limit(ctx):
         assert_terms_equal(m.mul(terms(fa, 3, 1), terms(fb, 3, 2), 3), oracle_terms(po.p_mul(fa, fb), 3))
     finally:
         m.close()
+
+
+def test_unsupported_sizes_have_their_own_status(ctx):
+    """A product the reference would compute but whose re-encoded code range reaches 2^62 is reported as PK_E_UNSUPPORTED (a
+    runtime error), not as the overflow_error of the bounds check: nothing overflowed."""
+    big = 12 * 10 ** 17  # the 1-variable Kronecker limit is 3.0e18: sums of two such exponents stay inside it
+    f = {(-big,): 1, (0,): 1, (1,): 1, (big,): 1}
+    with pytest.raises(pb.PkError) as ei:
+        ctx.mul(terms(f, 1), terms(f, 1), 1)  # code range 4.8e18 + 1 >= 2^62
+    assert ei.value.code == 7
+    # ... while exponents that leave the Kronecker limits still raise the reference's overflow_error
+    lim, _, _ = ctx.limits(1)
+    with pytest.raises(OverflowError):
+        ctx.mul(terms({(int(lim[0]),): 1, (0,): 1}, 1), terms(f, 1), 1)
