@@ -475,7 +475,7 @@ __device__ __forceinline__ uint2 block_load_hi(const uint2 *p, u32 idx)
 
 // Visit every product of one tile: f(a_record, b_record, a_high_limb, b_high_limb).  FULL selects how much of a record
 // is loaded (block_load); LW = limbs per operand magnitude (1 or 2).
-template <int FULL, int LW, typename F>
+template <int FULL, int LW, bool FLATCOL = false, typename F>
 __device__ __forceinline__ void block_tile_loop(const uint4 *__restrict__ A, const uint4 *__restrict__ B,
                                                 const uint2 *__restrict__ A1, const uint2 *__restrict__ B1, const uint4 t,
                                                 u32 lane, F &&f)
@@ -499,6 +499,17 @@ __device__ __forceinline__ void block_tile_loop(const uint4 *__restrict__ A, con
             const uint4 av = block_load<FULL>(&A[a0 + i]);
             const uint2 ah = block_load_hi<FULL, LW>(A1, a0 + i);
             f(av, bv, ah, bh);
+        }
+    } else if (FLATCOL) {
+        // ragged chunk (bn < 32 terms), fixed columns: lane l keeps term l % bn of gb in registers and takes the rows
+        // l / bn, l / bn + R, ... with R = 32 / bn rows per step -- one load and no index arithmetic per product; the
+        // lanes beyond R * bn idle (lane / bn through one float reciprocal; the +0.5 keeps the quotient off an integer boundary)
+        const u32 R = 32u / bn;
+        const u32 r = (u32)(((float)lane + 0.5f) * __frcp_rn((float)bn)), j = lane - r * bn;
+        if (r < R) {
+            const uint4 bv = block_load<FULL>(&B[b0 + j]);
+            const uint2 bh = block_load_hi<FULL, LW>(B1, b0 + j);
+            for (u32 i = r; i < an; i += R) f(block_load<FULL>(&A[a0 + i]), bv, block_load_hi<FULL, LW>(A1, a0 + i), bh);
         }
     } else {
         // flat tile: the an x bn products are flattened over the lanes; (i, j) advance by 32 without a division
@@ -1121,6 +1132,7 @@ struct AccArgs {
     u32 range;
     u32 raw_off;           // byte offset in dynamic shared memory of the landing area of the raw bitmap words
     u32 nozero;            // 1 = no coefficient can be zero (no negative and no zero operand coefficients): every marked code is a term
+    u32 flatcol;           // 1 = ragged chunks are walked with fixed columns per lane (tuning "block_flatcol")
     u64 expect_entries;    // the result arrays were sized for this many marked codes; the kernel does nothing if the device counted otherwise
     const TruncDev *trunc;
     BlockGeo *geo;
@@ -1287,6 +1299,8 @@ __global__ void __launch_bounds__(1024, 1) k_block_acc(const AccArgs aa)
                             if (av.x + bv.x >= c0 && av.x + bv.x < c1) ++my_pairs;
                             accumulate(av, bv, ah, bh);
                         });
+                    } else if (aa.flatcol) {
+                        block_tile_loop<2, LW, true>(a.A, a.B, a.A1, a.B1, t, lane, accumulate);
                     } else {
                         block_tile_loop<2, LW>(a.A, a.B, a.A1, a.B1, t, lane, accumulate);
                     }
@@ -1611,6 +1625,7 @@ inline void block_configure(pk_ctx *ctx)
     t.ctas = env_u32("PK_BLOCK_CTAS", t.ctas);
     t.size_hint = env_u32("PK_BLOCK_SIZE_HINT", t.size_hint);
     t.stage_rows = env_u32("PK_BLOCK_STAGE_ROWS", t.stage_rows);
+    t.flatcol = env_u32("PK_BLOCK_FLATCOL", t.flatcol);
     const size_t dyn = ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0;
 #define X(nw, pw)                                 \
     BlockKernels<nw, pw, false, 1>::set_smem(dyn); \
@@ -2010,7 +2025,8 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     key.parts = std::max<u32>(1, parts);
     key.trunc = trunc ? 1u : 0u;
     key.max_degree = trunc ? max_degree : 0;
-    const bool use_hint = bp.mode == 1 && bt.size_hint && ctx->size_hint.valid && ctx->size_hint.same_key(key);
+    const bool hint_ok = bt.size_hint && ctx->size_hint.valid && ctx->size_hint.same_key(key);
+    const bool use_hint = bp.mode == 1 && hint_ok;
     StagingView stage{nullptr};
     for (int attempt = 0;; ++attempt) {
         PlanArgs pa{};
@@ -2143,6 +2159,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
         aa.raw_off = bp.raw_off;
         aa.nozero = (!disp.is_signed && !A->any_zero && !B->any_zero) ? 1u : 0u;
         aa.expect_entries = n_entries;
+        aa.flatcol = bt.flatcol;
         aa.trunc = trunc ? td : nullptr;
         aa.geo = geo;
         CUDA_CHECK(cudaEventRecord(ctx->ev_mul0, ctx->stream));
@@ -2202,16 +2219,28 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     da.stage_off = bp.stage_off;
     da.trunc = trunc ? td : nullptr;
     da.geo = geo;
+    DPolyGuard e{ctx, nullptr};
     for (int attempt = 0;; ++attempt) {
         CUDA_CHECK(cudaEventRecord(ctx->ev_mul0, ctx->stream));
         block_launch_dense(ctx, disp, da, std::min<u32>(bp.grid, n_zu), bp.smem);
         CUDA_CHECK(cudaEventRecord(ctx->ev_mul1, ctx->stream));
         phase("k_block_dense");
         PK_LAUNCH(ctx, k_zone_scan, 1, 1024, 0, zone_count, zone_prefix, &geo->n_zones, &ctx->d_ctr->n_out);
+        if (hint_ok && attempt == 0) {
+            // the result is sized from the last product of the same shape and gathered right away; the kernel copies nothing
+            // when the device counted a different size (checked below), so no host round trip separates the two
+            const u64 n_hint = ctx->size_hint.entries;
+            e.p = new_dpoly(ctx, n_hint, nv, pl.out_limbs);
+            if (n_hint)
+                PK_LAUNCH(ctx, k_zone_gather, grid_for(n_hint, kGatherPerBlock), 256, 0, zone_count, zone_off, zone_prefix, &geo->n_zones,
+                          stage.p->key, stage.p->planes, stage.p->stride, stage.p->sign, e.p->key, e.p->planes, e.p->stride, e.p->sign,
+                          pl.out_limbs, n_hint, &ctx->d_ctr->n_out);
+        }
         readback2(ctx, hc, ctx->d_ctr, sizeof(MulCounters), hgeo, geo, sizeof(BlockGeo));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         if (hgeo->flags & kGeoDecline) return nullptr;
         if (!(hgeo->flags & kGeoTileOverflow)) break;
+        e.release_now();
         if (attempt) fail(PK_E_CUDA, "block path: the tile list does not fit after growing (internal error)");
         // the tile buffer was too small: nothing ran.  Grow it, build the list again, run again.
         ctx_tiles_acquire(ctx, hgeo->n_tiles);
@@ -2252,7 +2281,12 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
                 S, bp.split, (unsigned long long)Hu, n_zu, hgeo->zu_lo, hgeo->zu_hi, hgeo->n_tiles, hgeo->n_zones, hgeo->n_active, bp.cap,
                 (unsigned long long)n_out, bp.NW, bp.PW);
     if (n_out > da.z.out_cap || (hc->flags & kFlagTableFull)) fail(PK_E_CUDA, "block path: a count exceeds its bound (internal error)");
-    DPolyGuard e{ctx, new_dpoly(ctx, n_out, nv, pl.out_limbs)};
+    key.entries = n_out;
+    key.valid = true;
+    ctx->size_hint = key;
+    if (e.p && e.p->n == n_out) return e.release(); // the hint held: already gathered
+    e.release_now();
+    e.p = new_dpoly(ctx, n_out, nv, pl.out_limbs);
     if (n_out) {
         PK_LAUNCH(ctx, k_zone_gather, grid_for(n_out, kGatherPerBlock), 256, 0, zone_count, zone_off, zone_prefix, &geo->n_zones,
                   stage.p->key, stage.p->planes, stage.p->stride, stage.p->sign, e.p->key, e.p->planes, e.p->stride, e.p->sign, pl.out_limbs,

@@ -52,6 +52,7 @@ struct BlockTuning {
     uint32_t smem_limit = 0;      // bytes of shared memory a zone may use (0 = all): what is left over serves as L1
     uint32_t radix0_residue = 0;  // experiment: pad the radix of digit 0 so that radix mod 32 == this (1..32); 0 = off
     uint32_t unit_codes = 1u << 15; // sparse ranges: codes per zone unit aimed at, times the blocks per SM (a unit is a whole number of blocks)
+    uint32_t flatcol = 0;         // sparse ranges, accumulating walk: ragged chunks with fixed columns per lane instead of flattened products
     uint32_t stage_rows = 1;      // dense ranges: the rows of A of a full tile are staged in shared memory by a bulk copy (TMA), double
                                   // buffered per warp against the walk
     uint32_t size_hint = 1;       // sparse ranges: size the result from the last product of the same operands and options (skips the

@@ -605,25 +605,21 @@ __global__ void __launch_bounds__(1024) k_zone_cuts(const u32 *__restrict__ sort
 // Lay the zones out in zone order (= ascending code order).  One thread per OUTPUT term (so every write is coalesced
 // and the grid covers the whole result whatever the zone sizes): a block finds the zone of its first term by binary
 // search over the scanned zone offsets, then every thread walks forward from there.
-constexpr u32 kGatherPerBlock = 1024;
+constexpr u32 kGatherPerBlock = 256; // (one term per thread: a 135 k-term gather is 530 blocks; with 1024 per block it was 133 blocks and 39 us of latency chains)
 __global__ void __launch_bounds__(256) k_zone_gather(const u32 *__restrict__ zone_count, const u64 *__restrict__ zone_off,
                                                      const u64 *__restrict__ zone_prefix, const u32 *__restrict__ n_zones_dev,
                                                      const i64 *__restrict__ skey, const u64 *__restrict__ splanes,
                                                      u64 sstride, const signed char *__restrict__ ssign,
                                                      i64 *__restrict__ okey, u64 *__restrict__ oplanes, u64 ostride,
-                                                     signed char *__restrict__ osign, u32 limbs, u64 n_out)
+                                                     signed char *__restrict__ osign, u32 limbs, u64 n_out,
+                                                     const u64 *__restrict__ n_out_dev = nullptr)
 {
     (void)zone_count;
+    // (n_out_dev: the destination was sized from a hint; nothing is copied when the device counted a different size)
+    if (n_out_dev && *n_out_dev != n_out) return;
     const u32 n_zones = __ldg(n_zones_dev);
     const u64 base = (u64)blockIdx.x * kGatherPerBlock;
     if (base >= n_out || n_zones == 0) return;
-    u32 lo = 0, hi = n_zones; // last zone whose first output position is <= base
-    while (hi - lo > 1) {
-        const u32 mid = (lo + hi) >> 1;
-        if (__ldg(&zone_prefix[mid]) <= base) lo = mid;
-        else hi = mid;
-    }
-    u32 z = lo;
     constexpr u32 kPer = kGatherPerBlock / 256;
     u64 src[kPer];
 #pragma unroll
@@ -631,8 +627,16 @@ __global__ void __launch_bounds__(256) k_zone_gather(const u32 *__restrict__ zon
         const u64 i = base + k * 256u + threadIdx.x;
         src[k] = ~0ull;
         if (i < n_out) {
-            while (z + 1 < n_zones && __ldg(&zone_prefix[z + 1]) <= i) ++z;
-            src[k] = __ldg(&zone_off[z]) + (i - __ldg(&zone_prefix[z]));
+            // the zone of output i: the last zone whose first output position is <= i (a search per thread: the upper levels
+            // are the same addresses for the whole block and hit L1; walking zone by zone from the block's first zone was a
+            // chain of dependent L2 loads, most of the 39 us this kernel took for fateman1's 135 k terms)
+            u32 lo = 0, hi = n_zones;
+            while (hi - lo > 1) {
+                const u32 mid = (lo + hi) >> 1;
+                if (__ldg(&zone_prefix[mid]) <= i) lo = mid;
+                else hi = mid;
+            }
+            src[k] = __ldg(&zone_off[lo]) + (i - __ldg(&zone_prefix[lo]));
         }
     }
     i64 kk[kPer];
