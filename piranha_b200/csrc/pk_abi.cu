@@ -870,6 +870,7 @@ void pk_ctx_destroy(pk_ctx *ctx)
     if (ctx->ev_aux1) cudaEventDestroy(ctx->ev_aux1);
     if (ctx->tiles_buf) cudaFreeAsync(ctx->tiles_buf, ctx->stream);
     if (ctx->bitmap_buf) cudaFreeAsync(ctx->bitmap_buf, ctx->stream);
+    ctx_drop_idle(ctx);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->ev_part) cudaEventDestroy(ctx->ev_part);
@@ -918,6 +919,7 @@ int pk_ctx_trim(pk_ctx *ctx)
             ctx->bitmap_buf = nullptr;
             ctx->bitmap_bytes = 0;
         }
+        ctx_drop_idle(ctx);
         for (auto &b : ctx->pinned)
             if (!b.in_use && b.ptr) {
                 cudaFreeHost(b.ptr);

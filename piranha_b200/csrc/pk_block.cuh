@@ -849,6 +849,7 @@ __global__ void __launch_bounds__(128) k_block_mark(const MarkArgs m)
     const u32 dlim = m.trunc ? __ldg(&m.trunc->dlim) : 0xFFFFFFFFu;
     const u32 bm_s = smem_u32(mbm);
     u32 my_max = 0;
+    u64 my_sum = 0;
     // units are dealt round robin over the blocks (no claim traffic: the heavy units of the dense middle of the range
     // are consecutive, so every block gets its share of them)
     for (u32 zr = blockIdx.x; zr < n_units; zr += gridDim.x) {
@@ -897,10 +898,14 @@ __global__ void __launch_bounds__(128) k_block_mark(const MarkArgs m)
             const u32 e = s_red[0] + s_red[1] + s_red[2] + s_red[3];
             m.entries[zr] = e;
             my_max = max(my_max, e);
+            my_sum += e;
         }
         __syncthreads();
     }
-    if (tid == 0 && my_max) atomicMax(&m.geo->max_entries, my_max);
+    if (tid == 0 && my_max) {
+        atomicMax(&m.geo->max_entries, my_max);
+        atomicAdd(&m.geo->entries_total, my_sum); // (k_block_zones sizes its zones from the total and writes it again)
+    }
 }
 
 struct ZonesArgs {
@@ -910,6 +915,7 @@ struct ZonesArgs {
     u32 cap;              // sparse: accumulator entries one zone pass holds
     u32 zmax;             // sparse: most units one zone may span (the bitmap of a zone lives in shared memory)
     u64 zone_products;    // sparse: products per zone aimed at
+    u32 n_ctas;           // sparse: accumulating thread blocks on the device (0 = do not shrink zones for small products)
     u32 *zstart;          // out: first unit of every zone (+ one past the last)
     u64 *zone_off;        // out (sparse): position of the zone's first term in the result (+ total)
     u32 *order;           // out: zones, heaviest first
@@ -953,9 +959,16 @@ __global__ void __launch_bounds__(kPlanThreads) k_block_zones(const ZonesArgs a,
         for (u32 z = b * kPlanThreads + tid; z <= nz; z += G * kPlanThreads) a.zstart[z] = z;
     } else {
         const u32 max_e = g.max_entries;
-        const u64 cap_eff = max((u64)a.cap / 2u, (u64)a.cap - min((u64)a.cap, (u64)max_e)); // entries a zone may collect before its last unit
+        u64 cap_eff = max((u64)a.cap / 2u, (u64)a.cap - min((u64)a.cap, (u64)max_e)); // entries a zone may collect before its last unit
+        u64 zone_products = max(a.zone_products, (u64)1);
+        if (a.n_ctas) {
+            // a small product or partition: at least ~3 zones per accumulating block, so that every SM gets work and the
+            // heaviest-first order can balance it (pearce1 on 8 GPUs: 400 zones for 592 blocks otherwise)
+            cap_eff = min(cap_eff, max((u64)256, g.entries_total / ((u64)a.n_ctas * 3u)));
+            zone_products = min(zone_products, max((u64)2048, g.products_part / ((u64)a.n_ctas * 3u)));
+        }
         const u64 ONE = 1ull << 20;
-        const u64 fx_e = (ONE << 32) / cap_eff, fx_p = (ONE << 32) / max(a.zone_products, (u64)1), w_unit = (ONE + a.zmax - 1) / a.zmax;
+        const u64 fx_e = (ONE << 32) / cap_eff, fx_p = (ONE << 32) / zone_products, w_unit = (ONE + a.zmax - 1) / a.zmax;
         auto weight = [&](u32 i) -> u64 { // (fixed point; the same expression in every phase, so the cuts are consistent)
             const u64 e = a.entries[i], p = min(a.pprefix[i + 1] - a.pprefix[i], (u64)0xFFFFFFFFull);
             const u64 w = __umul64hi(e << 32, fx_e) + (e ? 1u : 0u) + w_unit + __umul64hi(p << 32, fx_p);
@@ -2083,6 +2096,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
             za.cap = bp.cap;
             za.zmax = zmax;
             const u64 part_products = (u64)(w_bound / std::max<u32>(1, parts));
+            za.n_ctas = bt.zone_products ? 0u : bp.grid * bp.ctas;
             za.zone_products = bt.zone_products ? bt.zone_products : std::max<u64>(1u << 16, part_products / ((u64)bp.grid * bp.ctas * 4));
             launch_coop(ctx, k_block_zones, coop_grid, kPlanThreads, za, zones_sc);
             phase("mark + zones");

@@ -108,6 +108,16 @@ struct pk_ctx {
     void *tiles_buf = nullptr;  // tile list of the block path, kept across products (grow-only)
     uint64_t tiles_cap = 0;     // in tiles
     SizeHint size_hint;
+    // Idle device blocks of this context (>= 256 KB), reused by size before the stream-ordered pool is asked.  The pool splits
+    // freed blocks for smaller requests, so a product whose result is tens of MB kept paying for fresh physical memory every
+    // few calls (measured: 1-5 ms stalls in the result allocation of partitioned pearce1 products, for a dozen products in a row);
+    // everything here lives on the context's one stream, so reuse is stream-ordered like the pool's own.
+    struct IdleBlock {
+        void *p;
+        size_t bytes;
+    };
+    std::vector<IdleBlock> idle_blocks;
+    size_t idle_bytes = 0;
     void *bitmap_buf = nullptr; // sparse block path: bitmap of the code range (k_block_mark -> k_block_acc), grow-only
     size_t bitmap_bytes = 0;
     void *h_scratch = nullptr; // small pinned read-back area
@@ -134,6 +144,7 @@ struct pk_dpoly {
     uint64_t n = 0, stride = 0;
     uint32_t n_vars = 0, limbs = 1;
     uint32_t alloc_limbs = 1;   // planes allocated (limbs may be trimmed below it)
+    size_t key_bytes = 0, planes_bytes = 0, sign_bytes = 0; // allocated sizes (blocks may come from the context's idle list)
     pk::i64 *key = nullptr;     // n (+2 padding) piranha codes, ascending
     pk::u64 *planes = nullptr;  // limbs planes of `stride` words
     signed char *sign = nullptr;
@@ -183,16 +194,61 @@ struct PkError {
         CUDA_CHECK(cudaGetLastError());                                  \
     } while (0)
 
+constexpr size_t kIdleMinBytes = 256u << 10;
+
+// device memory for this context's stream: an idle block of a fitting size (at most 25 % larger) or the pool
+inline void *ctx_alloc(pk_ctx *ctx, size_t &bytes)
+{
+    if (bytes >= kIdleMinBytes) {
+        size_t best = ctx->idle_blocks.size();
+        for (size_t i = 0; i < ctx->idle_blocks.size(); ++i) {
+            const size_t b = ctx->idle_blocks[i].bytes;
+            if (b >= bytes && b <= bytes + bytes / 4 && (best == ctx->idle_blocks.size() || b < ctx->idle_blocks[best].bytes)) best = i;
+        }
+        if (best != ctx->idle_blocks.size()) {
+            void *p = ctx->idle_blocks[best].p;
+            bytes = ctx->idle_blocks[best].bytes;
+            ctx->idle_bytes -= bytes;
+            ctx->idle_blocks[best] = ctx->idle_blocks.back();
+            ctx->idle_blocks.pop_back();
+            return p;
+        }
+    }
+    void *p = nullptr;
+    CUDA_CHECK(cudaMallocFromPoolAsync(&p, bytes, ctx->pool, ctx->stream));
+    return p;
+}
+
+inline void ctx_release(pk_ctx *ctx, void *p, size_t bytes)
+{
+    if (!p) return;
+    // (keep at most a quarter of the device's memory idle, and at most 64 blocks)
+    if (bytes >= kIdleMinBytes && ctx->idle_blocks.size() < 64 && ctx->idle_bytes + bytes <= ctx->total_mem / 4) {
+        ctx->idle_blocks.push_back({p, bytes});
+        ctx->idle_bytes += bytes;
+        return;
+    }
+    cudaFreeAsync(p, ctx->stream);
+}
+
+inline void ctx_drop_idle(pk_ctx *ctx)
+{
+    for (auto &b : ctx->idle_blocks) cudaFreeAsync(b.p, ctx->stream);
+    ctx->idle_blocks.clear();
+    ctx->idle_bytes = 0;
+}
+
 struct DevBuf { // stream-ordered allocation with scope lifetime
     pk_ctx *ctx;
     void *p = nullptr;
-    DevBuf(pk_ctx *c, size_t bytes) : ctx(c)
+    size_t bytes = 0;
+    DevBuf(pk_ctx *c, size_t b) : ctx(c), bytes(b)
     {
-        if (bytes) CUDA_CHECK(cudaMallocFromPoolAsync(&p, bytes, c->pool, c->stream));
+        if (bytes) p = ctx_alloc(c, bytes);
     }
     ~DevBuf()
     {
-        if (p) cudaFreeAsync(p, ctx->stream);
+        if (p) ctx_release(ctx, p, bytes);
     }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
@@ -256,9 +312,10 @@ struct Plan {
 
 inline void free_dpoly_arrays(pk_ctx *ctx, pk_dpoly *p)
 {
-    if (p->key) cudaFreeAsync(p->key, ctx->stream);
-    if (p->planes) cudaFreeAsync(p->planes, ctx->stream);
-    if (p->sign) cudaFreeAsync(p->sign, ctx->stream);
+    // (a polynomial is freed through the context whose stream last wrote it -- its own; views hold no sizes and free nothing)
+    if (p->key && p->key_bytes) ctx_release(ctx, p->key, p->key_bytes);
+    if (p->planes && p->planes_bytes) ctx_release(ctx, p->planes, p->planes_bytes);
+    if (p->sign && p->sign_bytes) ctx_release(ctx, p->sign, p->sign_bytes);
     p->key = nullptr;
     p->planes = nullptr;
     p->sign = nullptr;
@@ -299,9 +356,12 @@ inline pk_dpoly *new_dpoly(pk_ctx *ctx, u64 n, u32 n_vars, u32 limbs)
     p->alloc_limbs = limbs;
     p->stride = ((n + 1) & ~1ull) + 2; // even, with slack for the 16-byte TMA granularity
     DPolyGuard g{ctx, p.release()};
-    CUDA_CHECK(cudaMallocFromPoolAsync((void **)&g.p->key, (n + 2) * sizeof(int64_t), ctx->pool, ctx->stream));
-    CUDA_CHECK(cudaMallocFromPoolAsync((void **)&g.p->planes, g.p->stride * limbs * sizeof(uint64_t), ctx->pool, ctx->stream));
-    CUDA_CHECK(cudaMallocFromPoolAsync((void **)&g.p->sign, n + 2, ctx->pool, ctx->stream));
+    g.p->key_bytes = (n + 2) * sizeof(int64_t);
+    g.p->key = static_cast<pk::i64 *>(ctx_alloc(ctx, g.p->key_bytes));
+    g.p->planes_bytes = g.p->stride * limbs * sizeof(uint64_t);
+    g.p->planes = static_cast<pk::u64 *>(ctx_alloc(ctx, g.p->planes_bytes));
+    g.p->sign_bytes = n + 2;
+    g.p->sign = static_cast<signed char *>(ctx_alloc(ctx, g.p->sign_bytes));
     return g.release();
 }
 

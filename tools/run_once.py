@@ -38,6 +38,7 @@ def main():
               f"-> {W / min(ks) / 1e6:.1f} G products/s (kernel)  digest {r.digest():016x}", flush=True)
         if os.environ.get("PK_ONCE_ALL"):
             print("   device_ms:", " ".join(f"{x:.3f}" for x in ds), flush=True)
+            print("   kernel_ms:", " ".join(f"{x:.3f}" for x in ks), flush=True)
         ctx.close()
 
 if __name__ == "__main__":
