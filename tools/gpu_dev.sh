@@ -1,12 +1,13 @@
 #!/bin/bash
+# scratch: A/B of a tuning key on the GPU box (edit freely)
 cd "$(dirname "$0")/.."
-echo "--- part 0/2"
-PK_ONCE_ALL=1 timeout 120 python tools/run_once.py pearce1 --iters 12 --part 0/2 2>&1 | tail -2 | head -1
-echo "--- part 3/8"
-PK_ONCE_ALL=1 timeout 120 python tools/run_once.py pearce1 --iters 12 --part 3/8 2>&1 | tail -2 | head -1
-echo "--- whole"
-PK_ONCE_ALL=1 timeout 120 python tools/run_once.py pearce1 fateman1 --iters 10 2>&1 | grep device_ms:
-timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-timeout 300 python bench.py --steps 10 --no-cpu-baseline --also fateman1 2>/dev/null | python -c "
-import json,sys
-d=json.loads([x for x in sys.stdin if x.startswith('{')][-1]); print('bench ms', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], d['also']['fateman1']['ms_per_step'], d['step_ms_rank0'])"
+mkdir -p gpurun_out
+for ilp in 0 1 2 3; do
+  echo "== block_ilp=$ilp"
+  timeout 200 python tools/run_once.py pearce1 pearce2 monagan3 pearce1_dynamic --iters 8 block_ilp=$ilp 2>&1 | grep -v "^block path" | cut -c1-260
+done
+for ilp in 0 3; do
+  echo "== block_ilp=$ilp (dense family, must not change)"
+  timeout 200 python tools/run_once.py fateman1 --iters 6 block_ilp=$ilp 2>&1 | cut -c1-260
+done
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
