@@ -140,8 +140,10 @@ pk_dpoly *upload_impl(pk_ctx *ctx, const pk_poly *p)
         if (range >= ((unsigned __int128)1 << 62)) fail(PK_E_UNSUPPORTED, "exponent spans too wide to re-encode (code range of 2^62 or more)");
     }
     DevBuf fk(ctx, n * 8), fk2(ctx, n * 8), idx(ctx, n * 4), idx2(ctx, n * 4);
-    PK_LAUNCH(ctx, k_prepare, grid_for(n, 256), 256, 0, raw_key.as<i64>(), raw_sign.as<signed char>(), n, cp, fk.as<u64>(),
-              (i64 *)nullptr, (const u64 *)nullptr, (uint4 *)nullptr);
+    {
+        const PrepareArgs one{raw_key.as<i64>(), raw_sign.as<signed char>(), n, fk.as<u64>(), nullptr, nullptr, nullptr}, none{};
+        PK_LAUNCH(ctx, k_prepare, grid_for(n, 256), 256, 0, one, none, cp, cp, grid_for(n, 256));
+    }
     PK_LAUNCH(ctx, k_iota32, grid_for(n, 256), 256, 0, idx.as<u32>(), n);
     radix_sort_pairs(ctx, fk.as<u64>(), fk2.as<u64>(), idx.as<u32>(), idx2.as<u32>(), n, (int)std::max<u32>(1, bit_length(range)));
     CUDA_CHECK(cudaMemsetAsync(&ctx->d_meta->any_neg, 0, 4, ctx->stream));
@@ -336,10 +338,12 @@ pk_dpoly *mul_impl(pk_ctx *ctx, pk_dpoly *a, pk_dpoly *b, const pk_opts *opts_in
     BlockPlan bp = block_plan(ctx, pl, nA, nB);
     const bool prepack = bp.ok && !trunc && (o.algo == PK_ALGO_AUTO || o.algo == PK_ALGO_BLOCK);
     DevBuf packA(ctx, prepack ? (nA + 1) * 16 : 0), packB(ctx, prepack ? (nB + 1) * 16 : 0);
-    PK_LAUNCH(ctx, k_prepare, grid_for(nA, 256), 256, 0, A->key, A->sign, nA, pl.cpA, keyA.as<u64>(), degA.as<i64>(), A->planes,
-              packA.as<uint4>());
-    PK_LAUNCH(ctx, k_prepare, grid_for(nB, 256), 256, 0, B->key, B->sign, nB, pl.cpB, keyB.as<u64>(), degB.as<i64>(), B->planes,
-              packB.as<uint4>());
+    {
+        const PrepareArgs pa{A->key, A->sign, nA, keyA.as<u64>(), degA.as<i64>(), A->planes, packA.as<uint4>()};
+        const PrepareArgs pb{B->key, B->sign, nB, keyB.as<u64>(), degB.as<i64>(), B->planes, packB.as<uint4>()};
+        const u32 blocksA = grid_for(nA, 256);
+        PK_LAUNCH(ctx, k_prepare, blocksA + grid_for(nB, 256), 256, 0, pa, pb, pl.cpA, pl.cpB, blocksA);
+    }
     const u64 *kB = keyB.as<u64>();
     const u64 *mB = B->planes;
     u64 strideB = B->stride;

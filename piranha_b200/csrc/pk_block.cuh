@@ -48,7 +48,7 @@ struct BlockGeo {
     u32 max_entries;    // most marked codes in one zone unit
     u32 claim_mark;     // dynamic claim counters
     u32 claim_acc;
-    u32 pad;
+    u32 n_units_active; // units of the partition that have tiles (the marking walk visits only these)
     u64 products_all;   // pair count of the whole product (before degree tests)
     u64 products_part;  // pair count of this partition (before degree tests)
     u64 entries_total;  // marked codes of the partition: the result size unless coefficients cancel
@@ -130,42 +130,57 @@ __device__ __forceinline__ u32 div_magic(u32 x, u64 magic) { return (u32)__umul6
 
 // Group table of one operand: tab[hi] = {first term, one past the last term}; glist = the hi values that occur (any
 // order); codes = the 32-bit codes alone (what the marking walk loads).
-__global__ void k_block_groups(const uint4 *__restrict__ rec, u32 n, u64 magicS, uint2 *__restrict__ tab,
-                               u32 *__restrict__ glist, u32 *__restrict__ gcount, u32 *__restrict__ codes, uint2 *__restrict__ gdeg)
+struct GroupArgs {
+    const uint4 *rec;
+    u32 n;
+    uint2 *tab;
+    u32 *glist, *gcount, *codes;
+    uint2 *gdeg;
+};
+__device__ __forceinline__ void block_groups_of(const GroupArgs &g, u64 magicS, u32 i)
 {
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const u32 code = __ldg(&rec[i].x);
-    codes[i] = code;
+    if (i >= g.n) return;
+    const u32 code = __ldg(&g.rec[i].x);
+    g.codes[i] = code;
     const u32 hi = div_magic(code, magicS);
-    if (gdeg) { // truncation: {smallest, ~largest} degree offset of the group (both by atomicMin from an all-ones fill)
-        const u32 off = __ldg(&rec[i].y) >> 1;
-        atomicMin(&gdeg[hi].x, off);
-        atomicMin(&gdeg[hi].y, ~off);
+    if (g.gdeg) { // truncation: {smallest, ~largest} degree offset of the group (both by atomicMin from an all-ones fill)
+        const u32 off = __ldg(&g.rec[i].y) >> 1;
+        atomicMin(&g.gdeg[hi].x, off);
+        atomicMin(&g.gdeg[hi].y, ~off);
     }
-    const u32 prev = i ? div_magic(__ldg(&rec[i - 1].x), magicS) : 0xFFFFFFFFu;
-    const u32 next = (i + 1 < n) ? div_magic(__ldg(&rec[i + 1].x), magicS) : 0xFFFFFFFFu;
+    const u32 prev = i ? div_magic(__ldg(&g.rec[i - 1].x), magicS) : 0xFFFFFFFFu;
+    const u32 next = (i + 1 < g.n) ? div_magic(__ldg(&g.rec[i + 1].x), magicS) : 0xFFFFFFFFu;
     if (hi != prev) {
-        tab[hi].x = i;
-        glist[atomicAdd(gcount, 1u)] = hi;
+        g.tab[hi].x = i;
+        g.glist[atomicAdd(g.gcount, 1u)] = hi;
     }
-    if (hi != next) tab[hi].y = i + 1;
+    if (hi != next) g.tab[hi].y = i + 1;
 }
 
-// first[h] = first term whose hi is >= h, i.e. whose code is >= h * S, for every h in [0, HR]: one binary search per h
-// over the sorted records (the operand is a few 10^4 terms, L1/L2 resident).
-__global__ void k_block_first(const uint4 *__restrict__ rec, u32 n, u32 S, u32 HR, u32 *__restrict__ first)
+// ONE launch for the group tables of both operands and first[] (three launches of a few microseconds each before):
+// blocks [0, blocksA) take the terms of A, [blocksA, blocksA + blocksB) those of B, the rest compute
+// first[h] = first term of A whose hi is >= h, i.e. whose code is >= h * S, for every h in [0, HR] (one binary search per
+// h over the sorted records; the operand is a few 10^4 terms, L1/L2 resident).  n_first = 0: no first[].
+__global__ void k_block_groups(const GroupArgs ga, const GroupArgs gb, u64 magicS, u32 blocksA, u32 blocksB, u32 S, u32 n_first,
+                               u32 *__restrict__ first)
 {
-    const u32 h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h > HR) return;
-    const u64 want = (u64)h * S;
-    u32 lo = 0, hi = n;
-    while (lo < hi) {
-        const u32 mid = (lo + hi) >> 1;
-        if ((u64)__ldg(&rec[mid].x) < want) lo = mid + 1;
-        else hi = mid;
+    const u32 b = blockIdx.x;
+    if (b < blocksA) {
+        block_groups_of(ga, magicS, b * blockDim.x + threadIdx.x);
+    } else if (b < blocksA + blocksB) {
+        block_groups_of(gb, magicS, (b - blocksA) * blockDim.x + threadIdx.x);
+    } else {
+        const u32 h = (b - blocksA - blocksB) * blockDim.x + threadIdx.x;
+        if (h >= n_first) return;
+        const u64 want = (u64)h * S;
+        u32 lo = 0, hi = ga.n;
+        while (lo < hi) {
+            const u32 mid = (lo + hi) >> 1;
+            if ((u64)__ldg(&ga.rec[mid].x) < want) lo = mid + 1;
+            else hi = mid;
+        }
+        first[h] = lo;
     }
-    first[h] = lo;
 }
 
 struct TileArgs {
@@ -309,6 +324,8 @@ struct PlanArgs {
     const u32 *gcount; // {GA, GB}
     u64 W;             // nA * nB
     u32 min_tile;
+    u32 *entries;      // out (sparse ranges, else nullptr): zeroed for every unit of the partition (the marking walk writes the non-empty ones)
+    u32 *active;       // out (sparse ranges, else nullptr): the units of the partition that have tiles, relative to its first unit
     BlockGeo *geo;
 };
 
@@ -344,6 +361,8 @@ __global__ void __launch_bounds__(kPlanThreads) k_block_plan(const PlanArgs a, P
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     __shared__ u64 s_ws[40];
+    __shared__ u32 s_ws32[40];
+    __shared__ u32 s_abase;
     const u32 tid = threadIdx.x, G = gridDim.x, b = blockIdx.x;
     const u32 chunk = (a.n_zu + G - 1) / G;
     const u32 u0 = min(a.n_zu, b * chunk), u1 = min(a.n_zu, u0 + chunk);
@@ -426,9 +445,20 @@ __global__ void __launch_bounds__(kPlanThreads) k_block_plan(const PlanArgs a, P
             u64 ptot, ctot;
             const u64 pex = prun + block_excl_scan64(pv, s_ws, ptot);
             const u64 cex = crun + block_excl_scan64(cv, s_ws, ctot);
-            if (u < u1 && u >= zu_lo && u < zu_hi) {
+            const bool mine = u < u1 && u >= zu_lo && u < zu_hi;
+            if (mine) {
                 a.tstart[u - zu_lo] = (u32)min(cex - bc0, (u64)0xFFFFFFFFull);
                 a.pprefix[u - zu_lo] = pex - bp0;
+                if (a.entries) a.entries[u - zu_lo] = 0;
+            }
+            if (a.active) { // compact list of the units with tiles (one atomic per block and round; the order does not matter)
+                const u32 flag = (mine && cv != 0) ? 1u : 0u;
+                u32 ftot;
+                const u32 fex = block_excl_scan(flag, s_ws32, ftot);
+                if (tid == 0 && ftot) s_abase = atomicAdd(&a.geo->n_units_active, ftot);
+                __syncthreads();
+                if (flag) a.active[s_abase + fex] = u - zu_lo;
+                __syncthreads();
             }
             prun += ptot;
             crun += ctot;
@@ -829,7 +859,8 @@ struct MarkArgs {
     u32 U;                  // codes per zone unit (Hu * S)
     u32 range;              // number of tight codes of the whole product
     u32 *gbm;               // out: bitmap of the partition, bit (code - first code of the partition); zeroed by the host
-    u32 *entries;           // out: marked codes per unit
+    u32 *entries;           // out: marked codes per unit (zeroed by k_block_plan)
+    const u32 *active;      // units of the partition that have tiles
     const TruncDev *trunc;
     BlockGeo *geo;
 };
@@ -850,14 +881,14 @@ __global__ void __launch_bounds__(128) k_block_mark(const MarkArgs m)
     const u32 bm_s = smem_u32(mbm);
     u32 my_max = 0;
     u64 my_sum = 0;
-    // units are dealt round robin over the blocks (no claim traffic: the heavy units of the dense middle of the range
-    // are consecutive, so every block gets its share of them)
-    for (u32 zr = blockIdx.x; zr < n_units; zr += gridDim.x) {
+    // the units that have tiles (k_block_plan listed them; most units of a sparse range are empty and cost a quarter of this
+    // kernel's instructions when every block stepped over them) are dealt round robin over the blocks: no claim traffic,
+    // and the heavy units of the dense middle of the range are neighbours in the list, so every block gets its share
+    const u32 n_listed = m.geo->n_units_active;
+    for (u32 idx = blockIdx.x; idx < n_listed; idx += gridDim.x) {
+        const u32 zr = __ldg(&m.active[idx]);
         const u32 t0 = __ldg(&m.tstart[zr]), t1 = __ldg(&m.tstart[zr + 1]);
-        if (t0 == t1) {
-            if (tid == 0) m.entries[zr] = 0;
-            continue;
-        }
+        if (t0 == t1 || zr >= n_units) continue; // (cannot happen)
         const u64 c0 = code_lo + (u64)zr * m.U, c1 = min((u64)m.range, c0 + m.U);
         const u32 bit0 = (u32)(c0 - code_lo), bit1 = (u32)(c1 - code_lo);
         const u32 w_first = bit0 >> 5, nwords = ((bit1 + 31u) >> 5) - w_first;
@@ -927,7 +958,7 @@ struct ZonesScratch {
     u64 chunk_w[kPlanMaxBlocks];
     u64 chunk_e[kPlanMaxBlocks];
     u32 chunk_s[kPlanMaxBlocks];
-    u32 hist[256], cursor[256]; // counting sort of the zones by work class
+    u32 hist[256]; // counting sort of the zones by work class
 };
 
 // Zones of the partition and their order: ONE cooperative launch over all SMs (block b owns a chunk of consecutive units).
@@ -943,7 +974,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_block_zones(const ZonesArgs a,
     cg::grid_group grid = cg::this_grid();
     __shared__ u64 s_ws[40];
     __shared__ u32 s_ws32[40];
-    __shared__ u32 s_hist[256], s_start[256];
+    __shared__ u32 s_hist[256], s_start[256], s_base[256], s_cur[256];
     const u32 tid = threadIdx.x, G = gridDim.x, b = blockIdx.x;
     BlockGeo &g = *a.geo;
     if (g.flags) { // (uniform over the grid: no block reaches a grid barrier)
@@ -953,7 +984,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_block_zones(const ZonesArgs a,
     const u32 n = g.zu_hi - g.zu_lo;
     u32 nz = 0;
     if (b == 0)
-        for (u32 i = tid; i < 256; i += kPlanThreads) sc->hist[i] = sc->cursor[i] = 0; // (read after the grid barriers below)
+        for (u32 i = tid; i < 256; i += kPlanThreads) sc->hist[i] = 0; // (used after the grid barriers below)
     if (!a.entries) {
         nz = min(n, a.max_zones);
         for (u32 z = b * kPlanThreads + tid; z <= nz; z += G * kPlanThreads) a.zstart[z] = z;
@@ -1074,8 +1105,14 @@ __global__ void __launch_bounds__(kPlanThreads) k_block_zones(const ZonesArgs a,
         const u32 m = e >= 2 ? (u32)(w >> (e - 2)) & 3u : 0u;
         return min(255u, 4u * e + m + 1u);
     };
+    // (two levels: most zones fall into two or three classes, and thousands of atomics on one address of global memory
+    // took ~10 us of this kernel -- the block counts in shared memory and adds its counts once per class)
     const u32 stride = G * kPlanThreads;
-    for (u32 z = b * kPlanThreads + tid; z < nz; z += stride) atomicAdd(&sc->hist[cls(zwork_of(z))], 1u);
+    for (u32 i = tid; i < 256; i += kPlanThreads) s_hist[i] = s_cur[i] = 0;
+    __syncthreads();
+    for (u32 z = b * kPlanThreads + tid; z < nz; z += stride) atomicAdd(&s_hist[cls(zwork_of(z))], 1u);
+    __syncthreads();
+    for (u32 i = tid; i < 256; i += kPlanThreads) s_base[i] = s_hist[i] ? atomicAdd(&sc->hist[i], s_hist[i]) : 0u; // this block's offset inside the class
     grid.sync();
     for (u32 i = tid; i < 256; i += kPlanThreads) s_hist[i] = sc->hist[i];
     __syncthreads();
@@ -1093,7 +1130,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_block_zones(const ZonesArgs a,
     __syncthreads();
     for (u32 z = b * kPlanThreads + tid; z < nz; z += stride) {
         const u32 c = cls(zwork_of(z));
-        a.order[s_start[c] + atomicAdd(&sc->cursor[c], 1u)] = z;
+        a.order[s_start[c] + s_base[c] + atomicAdd(&s_cur[c], 1u)] = z;
     }
 }
 
@@ -1916,7 +1953,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     u32 *const zone_count = reinterpret_cast<u32 *>(zbase + zo_zc);
     u64 *const bump = reinterpret_cast<u64 *>(zbase + zo_bump);
     // not zeroed: written before they are read
-    DevBuf work(ctx, ((size_t)HR + 2) * 8 + (nA + nB) * 8 + ((size_t)n_zu + 2) * (4 + 8 + 4 + 8 + 8 + 4 + 4) + sizeof(PlanScratch) + sizeof(ZonesScratch) + 1024);
+    DevBuf work(ctx, ((size_t)HR + 2) * 8 + (nA + nB) * 8 + ((size_t)n_zu + 2) * (4 + 8 + 4 + 8 + 8 + 4 + 4 + 4 + 16) + sizeof(PlanScratch) + sizeof(ZonesScratch) + 1024);
     char *wp = work.as<char>();
     auto carve = [&](size_t bytes) {
         char *r = wp;
@@ -1933,6 +1970,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     u64 *const zone_off = reinterpret_cast<u64 *>(carve(((size_t)n_zu + 2) * 8));
     u64 *const zone_prefix = reinterpret_cast<u64 *>(carve(((size_t)n_zu + 2) * 8));
     u32 *const order = reinterpret_cast<u32 *>(carve(((size_t)n_zu + 2) * 4));
+    u32 *const active = reinterpret_cast<u32 *>(carve(((size_t)n_zu + 2) * 4));
     PlanScratch *const plan_sc = reinterpret_cast<PlanScratch *>(carve(sizeof(PlanScratch)));
     ZonesScratch *const zones_sc = reinterpret_cast<ZonesScratch *>(carve(sizeof(ZonesScratch)));
     const u32 coop_grid = std::max<u32>(1, std::min<u32>({(u32)ctx->sm_count, kPlanMaxBlocks, (n_zu + kPlanThreads - 1) / kPlanThreads}));
@@ -1961,12 +1999,14 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
 
     // ---- groups of equal hi
     const u64 magicS = (u64)((((unsigned __int128)1) << 64) / S) + 1;
-    PK_LAUNCH(ctx, k_block_groups, grid_for(nA, 256), 256, 0, pa_p, (u32)nA, magicS, tabA_p, glA, gcnt_p, codeA,
-              trunc ? gdegA.as<uint2>() : nullptr);
-    PK_LAUNCH(ctx, k_block_groups, grid_for(nB, 256), 256, 0, pb_p, (u32)nB, magicS, tabB_p, glB, gcnt_p + 1, codeB,
-              trunc ? gdegB.as<uint2>() : nullptr);
     const bool merge = !trunc && bt.merge;
-    if (merge) PK_LAUNCH(ctx, k_block_first, grid_for(HR + 1, 256), 256, 0, pa_p, (u32)nA, S, (u32)HR, firstA);
+    {
+        const GroupArgs ga{pa_p, (u32)nA, tabA_p, glA, gcnt_p, codeA, trunc ? gdegA.as<uint2>() : nullptr};
+        const GroupArgs gb{pb_p, (u32)nB, tabB_p, glB, gcnt_p + 1, codeB, trunc ? gdegB.as<uint2>() : nullptr};
+        const u32 blocksA = grid_for(nA, 256), blocksB = grid_for(nB, 256), n_first = merge ? (u32)HR + 1u : 0u;
+        PK_LAUNCH(ctx, k_block_groups, blocksA + blocksB + (n_first ? grid_for(n_first, 256) : 0u), 256, 0, ga, gb, magicS, blocksA, blocksB,
+                  S, n_first, firstA);
+    }
     DevBuf zero1(ctx, bp.LW == 2 ? std::max(nA, nB) * 8 + 16 : 0);
     const uint2 *hiA = nullptr, *hiB = nullptr;
     if (bp.LW == 2) {
@@ -2054,6 +2094,8 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
         pa.gcount = gcnt_p;
         pa.W = (u64)w_bound;
         pa.min_tile = bt.min_tile;
+        pa.entries = bp.mode == 1 ? entries : nullptr;
+        pa.active = bp.mode == 1 ? active : nullptr;
         pa.geo = geo;
         launch_coop(ctx, k_block_plan, coop_grid, kPlanThreads, pa, plan_sc);
         ta.cnt = cur_p; // the scatter pass counts again, into its own zeroed cursors
@@ -2084,6 +2126,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
             ma.range = (u32)pl.range;
             ma.gbm = static_cast<u32 *>(gbm_p);
             ma.entries = entries;
+            ma.active = active;
             ma.trunc = trunc ? td : nullptr;
             ma.geo = geo;
             const size_t msmem = ((size_t)(U / 32 + 4) * 4 + 15) & ~15ull;

@@ -174,12 +174,19 @@ __global__ void k_meta(const i64 *__restrict__ key, const u64 *__restrict__ plan
 
 // Per-multiplication operand preparation: tight code | sign bit, degree (total or partial), coefficient limbs
 // are read straight from the operand's planes by the multiply kernel.
-__global__ void k_prepare(const i64 *__restrict__ key, const signed char *__restrict__ sign, u64 n, CodecParams cp,
-                          u64 *__restrict__ okey, i64 *__restrict__ odeg, const u64 *__restrict__ m0, uint4 *__restrict__ opack)
+struct PrepareArgs {
+    const i64 *key;
+    const signed char *sign;
+    u64 n;
+    u64 *okey;
+    i64 *odeg;
+    const u64 *m0;
+    uint4 *opack;
+};
+__device__ __forceinline__ void prepare_term(const PrepareArgs &p, const CodecParams &cp, u64 i)
 {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    i64 code = key[i] - cp.h_min;
+    if (i >= p.n) return;
+    i64 code = p.key[i] - cp.h_min;
     u64 tight = 0;
     i64 deg = 0;
     for (u32 v = 0; v < cp.n_vars; ++v) {
@@ -189,14 +196,20 @@ __global__ void k_prepare(const i64 *__restrict__ key, const signed char *__rest
         tight += (u64)((e - cp.emin[v]) / cp.step[v]) * cp.stride[v];
         if (cp.mask[v]) deg += e;
     }
-    const signed char s = sign[i];
+    const signed char s = p.sign[i];
     // a zero coefficient contributes nothing: its magnitude limbs are zero, the sign bit is irrelevant
-    okey[i] = tight | (s < 0 ? kSignBit : 0ull);
-    if (odeg) odeg[i] = deg;
-    if (opack) { // packed 16-byte record of the shared-memory paths: {tight code (32 bit), sign, magnitude (one limb)}
-        const u64 m = m0[i];
-        opack[i] = make_uint4((u32)tight, s < 0 ? 1u : 0u, (u32)m, (u32)(m >> 32));
+    p.okey[i] = tight | (s < 0 ? kSignBit : 0ull);
+    if (p.odeg) p.odeg[i] = deg;
+    if (p.opack) { // packed 16-byte record of the shared-memory paths: {tight code (32 bit), sign, magnitude (one limb)}
+        const u64 m = p.m0[i];
+        p.opack[i] = make_uint4((u32)tight, s < 0 ? 1u : 0u, (u32)m, (u32)(m >> 32));
     }
+}
+// both operands in one launch: blocks [0, blocksA) take the terms of a, the rest those of b
+__global__ void k_prepare(const PrepareArgs a, const PrepareArgs b, const CodecParams cpa, const CodecParams cpb, u32 blocksA)
+{
+    if (blockIdx.x < blocksA) prepare_term(a, cpa, (u64)blockIdx.x * blockDim.x + threadIdx.x);
+    else prepare_term(b, cpb, (u64)(blockIdx.x - blocksA) * blockDim.x + threadIdx.x);
 }
 
 // permute prepared operand arrays (after sorting the second operand by degree, polynomial.hpp:1427-1442)
