@@ -1018,6 +1018,7 @@ int pk_ctx_set_tuning(pk_ctx *ctx, const char *key, uint64_t value)
     else if (k == "block_size_hint") ctx->block_tuning.size_hint = (u32)value;
     else if (k == "block_stage_rows") ctx->block_tuning.stage_rows = (u32)value;
     else if (k == "block_flatcol") ctx->block_tuning.flatcol = (u32)value;
+    else if (k == "block_self_clear") ctx->block_tuning.self_clear = (u32)value;
     else return PK_E_ARGS;
     return PK_OK;
 }

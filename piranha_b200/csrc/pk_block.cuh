@@ -957,7 +957,8 @@ struct ZonesArgs {
 struct ZonesScratch {
     u64 chunk_w[kPlanMaxBlocks];
     u64 chunk_e[kPlanMaxBlocks];
-    u32 chunk_s[kPlanMaxBlocks];
+    u32 n_zones;
+    u32 pad;
     u32 hist[256]; // counting sort of the zones by work class
 };
 
@@ -988,6 +989,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_block_zones(const ZonesArgs a,
     if (!a.entries) {
         nz = min(n, a.max_zones);
         for (u32 z = b * kPlanThreads + tid; z <= nz; z += G * kPlanThreads) a.zstart[z] = z;
+        grid.sync();
     } else {
         const u32 max_e = g.max_entries;
         u64 cap_eff = max((u64)a.cap / 2u, (u64)a.cap - min((u64)a.cap, (u64)max_e)); // entries a zone may collect before its last unit
@@ -1037,62 +1039,47 @@ __global__ void __launch_bounds__(kPlanThreads) k_block_zones(const ZonesArgs a,
             my_e = block_sum64(ep, s_ws);
             e_all = block_sum64(ea, s_ws);
         }
-        // ---- phase B: zone id of a unit = floor(exclusive weight prefix): the weights of a zone's units except the last
-        // sum to < 1.  A unit starts a zone when its id differs from its predecessor's.  Count the starts of the chunk.
-        auto walk = [&](u32 zbase, bool write) -> u32 {
+        // ---- phase B: zone of a unit = floor(exclusive weight prefix): the weights of a zone's units except the last sum
+        // to < 1.  A weight is at most 1, so the zone numbers of consecutive units differ by at most one: they ARE the
+        // zone indices, and a unit starts a zone when its number differs from its predecessor's.
+        {
             u64 wrun = my_w, erun = my_e;
-            u32 zrun = zbase;
             for (u32 base = i0; base < i1; base += kPlanThreads) {
                 const u32 i = base + tid;
                 const u64 w = i < i1 ? weight(i) : 0ull, e = i < i1 ? (u64)a.entries[i] : 0ull;
                 u64 wtot, etot;
                 const u64 wex = wrun + block_excl_scan64(w, s_ws, wtot);
                 const u64 eex = erun + block_excl_scan64(e, s_ws, etot);
-                u32 start = 0;
                 if (i < i1) {
                     const u32 id = (u32)(wex >> 20);
                     const u32 prev_id = i > 0 ? (u32)((wex - weight(i - 1)) >> 20) : 0xFFFFFFFFu;
-                    start = id != prev_id ? 1u : 0u;
-                }
-                u32 stot;
-                const u32 zidx = zrun + block_excl_scan(start, s_ws32, stot);
-                if (write && start && zidx < a.max_zones) {
-                    a.zstart[zidx] = i;
-                    a.zone_off[zidx] = eex;
+                    if (id != prev_id && id < a.max_zones) {
+                        a.zstart[id] = i;
+                        a.zone_off[id] = eex;
+                    }
+                    if (i + 1 == n) s_ws32[0] = id + 1u; // (the block that owns the last unit)
                 }
                 wrun += wtot;
                 erun += etot;
-                zrun += stot;
             }
-            return zrun - zbase;
-        };
-        const u32 my_starts = walk(0u, false);
-        if (tid == 0) sc->chunk_s[b] = my_starts;
+            __syncthreads();
+            if (n > 0 && i0 < n && i1 == n && tid == 0) {
+                const u32 z_all = min(s_ws32[0], a.max_zones);
+                a.zstart[z_all] = n;
+                a.zone_off[z_all] = e_all;
+                sc->n_zones = z_all;
+                g.entries_total = e_all;
+            }
+        }
+        if (n == 0 && b == 0 && tid == 0) {
+            a.zstart[0] = 0;
+            a.zone_off[0] = 0;
+            sc->n_zones = 0;
+            g.entries_total = 0;
+        }
         grid.sync();
-        // ---- phase C: zone indices from the prefix of the chunks' start counts; write the zone table
-        u32 zbase = 0, z_all = 0;
-        {
-            u32 sp = 0, sa = 0;
-            for (u32 j = tid; j < G; j += kPlanThreads) {
-                const u32 sv = sc->chunk_s[j];
-                sa += sv;
-                if (j < b) sp += sv;
-            }
-            u32 tot;
-            block_excl_scan(sp, s_ws32, tot);
-            zbase = tot;
-            block_excl_scan(sa, s_ws32, tot);
-            z_all = tot;
-        }
-        walk(zbase, true);
-        nz = min(z_all, a.max_zones);
-        if (b == 0 && tid == 0) {
-            a.zstart[nz] = n;
-            a.zone_off[nz] = e_all;
-            g.entries_total = e_all;
-        }
+        nz = sc->n_zones;
     }
-    grid.sync();
     // ---- heaviest first: a counting sort over the work classes, all blocks (one zone per thread and round)
     auto zwork_of = [&](u32 z) -> u64 {
         const u32 u0 = a.zstart[z], u1 = a.zstart[z + 1];
@@ -1176,13 +1163,14 @@ struct AccArgs {
     const u32 *zstart;     // first unit of every zone (+ one past the last)
     const u64 *zone_off;   // position of the zone's first term in the result arrays (+ total)
     const u32 *order;      // zones, heaviest first
-    const u32 *gbm;        // bitmap of the partition (k_block_mark)
+    u32 *gbm;        // bitmap of the partition (k_block_mark)
     u32 *zone_count;       // out: non-zero terms the zone wrote (its marked codes minus the cancellations)
     u32 U;                 // codes per zone unit
     u32 range;
     u32 raw_off;           // byte offset in dynamic shared memory of the landing area of the raw bitmap words
     u32 nozero;            // 1 = no coefficient can be zero (no negative and no zero operand coefficients): every marked code is a term
     u32 flatcol;           // 1 = ragged chunks are walked with fixed columns per lane (tuning "block_flatcol")
+    u32 self_clear;        // 1 = every zone clears its bits of the HBM bitmap after loading them
     u64 expect_entries;    // the result arrays were sized for this many marked codes; the kernel does nothing if the device counted otherwise
     const TruncDev *trunc;
     BlockGeo *geo;
@@ -1282,6 +1270,13 @@ __global__ void __launch_bounds__(1024, 1) k_block_acc(const AccArgs aa)
             if (w == 0) v &= first_mask;
             if (w + 1 == zwords) v &= last_mask;
             keep[k] = v;
+            // the zone's bits are consumed: clear them in HBM, so that the context's bitmap is all zero again when the
+            // product is complete and the next product needs no memset of the whole code range (the two words a zone
+            // shares with its neighbours lose only this zone's bits)
+            if (aa.self_clear && v) {
+                if (w == 0 || w + 1 == zwords) atomicAnd(&aa.gbm[w_first + w], ~v);
+                else aa.gbm[w_first + w] = 0u;
+            }
         }
         __syncthreads();
         for (u32 w = w0, k = 0; w < w1 && k < 8; ++w, ++k) {
@@ -1676,6 +1671,7 @@ inline void block_configure(pk_ctx *ctx)
     t.size_hint = env_u32("PK_BLOCK_SIZE_HINT", t.size_hint);
     t.stage_rows = env_u32("PK_BLOCK_STAGE_ROWS", t.stage_rows);
     t.flatcol = env_u32("PK_BLOCK_FLATCOL", t.flatcol);
+    t.self_clear = env_u32("PK_BLOCK_SELF_CLEAR", t.self_clear);
     const size_t dyn = ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0;
 #define X(nw, pw)                                 \
     BlockKernels<nw, pw, false, 1>::set_smem(dyn); \
@@ -2060,6 +2056,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
             ctx->bitmap_bytes = 0;
             CUDA_CHECK(cudaMallocFromPoolAsync(&ctx->bitmap_buf, gbm_bytes + gbm_bytes / 8, ctx->pool, ctx->stream));
             ctx->bitmap_bytes = gbm_bytes + gbm_bytes / 8;
+            ctx->bitmap_clean = false;
         }
         gbm_p = ctx->bitmap_buf;
     }
@@ -2114,7 +2111,10 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
         za.geo = geo;
         if (bp.mode == 1) {
             // ---- sparse: mark, then zones by entries and work
-            CUDA_CHECK(cudaMemsetAsync(gbm_p, 0, gbm_bytes, ctx->stream));
+            // the accumulating kernel clears the bits it consumes, so after a complete product the whole buffer is zero
+            // again; it is cleared here only when it is new or the last product on it did not run to its end
+            if (!ctx->bitmap_clean || !bt.self_clear) CUDA_CHECK(cudaMemsetAsync(gbm_p, 0, ctx->bitmap_bytes, ctx->stream));
+            ctx->bitmap_clean = false;
             MarkArgs ma{};
             ma.A = pa_p;
             ma.B = pb_p;
@@ -2217,6 +2217,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
         aa.nozero = (!disp.is_signed && !A->any_zero && !B->any_zero) ? 1u : 0u;
         aa.expect_entries = n_entries;
         aa.flatcol = bt.flatcol;
+        aa.self_clear = bt.self_clear;
         aa.trunc = trunc ? td : nullptr;
         aa.geo = geo;
         CUDA_CHECK(cudaEventRecord(ctx->ev_mul0, ctx->stream));
@@ -2239,6 +2240,8 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
         key.entries = n_entries;
         key.valid = true;
         ctx->size_hint = key;
+        // every marked bit was consumed and cleared by its zone (nothing was marked when there are no entries)
+        ctx->bitmap_clean = bt.self_clear && hgeo->flags == 0 && !(hc->flags & kFlagTableFull);
         if (hc->flags & kFlagTableFull) fail(PK_E_CUDA, "block path: a count exceeds its bound (internal error)");
         const u64 zeros = hgeo->zeros;
         if (zeros == 0) {

@@ -52,6 +52,7 @@ struct BlockTuning {
     uint32_t smem_limit = 0;      // bytes of shared memory a zone may use (0 = all): what is left over serves as L1
     uint32_t radix0_residue = 0;  // experiment: pad the radix of digit 0 so that radix mod 32 == this (1..32); 0 = off
     uint32_t unit_codes = 1u << 15; // sparse ranges: codes per zone unit aimed at, times the blocks per SM (a unit is a whole number of blocks)
+    uint32_t self_clear = 1;      // sparse ranges: zones clear their bits of the context's bitmap, so the next product skips the memset of the code range
     uint32_t flatcol = 0;         // sparse ranges, accumulating walk: ragged chunks with fixed columns per lane instead of flattened products
     uint32_t stage_rows = 1;      // dense ranges: the rows of A of a full tile are staged in shared memory by a bulk copy (TMA), double
                                   // buffered per warp against the walk
@@ -120,6 +121,7 @@ struct pk_ctx {
     size_t idle_bytes = 0;
     void *bitmap_buf = nullptr; // sparse block path: bitmap of the code range (k_block_mark -> k_block_acc), grow-only
     size_t bitmap_bytes = 0;
+    bool bitmap_clean = false;  // the whole buffer is zero (every zone of the last product cleared the bits it consumed)
     void *h_scratch = nullptr; // small pinned read-back area
     pk::MulCounters *d_ctr = nullptr;
     pk::MetaDev *d_meta = nullptr;
