@@ -53,7 +53,9 @@ struct BlockGeo {
     u64 products_part;  // pair count of this partition (before degree tests)
     u64 entries_total;  // marked codes of the partition: the result size unless coefficients cancel
     u64 zeros;          // marked codes whose coefficient cancelled to zero
+    u32 class_count[16]; // units with tiles per work class (class c: products in [2^(c-4), 2^(c-3)) times the average unit; 15 = the heaviest)
 };
+constexpr u32 kUnitClasses = 16;
 constexpr u32 kGeoDecline = 1u;      // groups too small: the tile list would be as long as the product itself
 constexpr u32 kGeoTileOverflow = 2u; // the tile buffer is too small (the host grows it and repeats)
 
@@ -325,7 +327,8 @@ struct PlanArgs {
     u64 W;             // nA * nB
     u32 min_tile;
     u32 *entries;      // out (sparse ranges, else nullptr): zeroed for every unit of the partition (the marking walk writes the non-empty ones)
-    u32 *active;       // out (sparse ranges, else nullptr): the units of the partition that have tiles, relative to its first unit
+    u32 *active;       // out (sparse ranges, else nullptr): the units of the partition that have tiles, relative to its first unit, one
+                       // list per work class (class c at active + c * n_zu; geo->class_count[c] entries)
     BlockGeo *geo;
 };
 
@@ -361,8 +364,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_block_plan(const PlanArgs a, P
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     __shared__ u64 s_ws[40];
-    __shared__ u32 s_ws32[40];
-    __shared__ u32 s_abase;
+    __shared__ u32 s_cls[kUnitClasses], s_cbase[kUnitClasses];
     const u32 tid = threadIdx.x, G = gridDim.x, b = blockIdx.x;
     const u32 chunk = (a.n_zu + G - 1) / G;
     const u32 u0 = min(a.n_zu, b * chunk), u1 = min(a.n_zu, u0 + chunk);
@@ -432,11 +434,16 @@ __global__ void __launch_bounds__(kPlanThreads) k_block_plan(const PlanArgs a, P
         sc->base_prod[1] = W_all;
         sc->base_cnt[1] = C_all;
     }
-    grid.sync();
-    // ---- phase 3: prefixes relative to the partition
-    const u32 zu_lo = sc->cut[0], zu_hi = max(sc->cut[0], sc->cut[1]);
-    const u64 bp0 = sc->base_prod[0], bc0 = sc->base_cnt[0];
-    const u64 n_tiles = (zu_hi > zu_lo) ? sc->base_cnt[1] - bc0 : 0ull, p_part = (zu_hi > zu_lo) ? sc->base_prod[1] - bp0 : 0ull;
+    // ---- phase 3: prefixes relative to the partition (an unpartitioned product knows its cuts without the second barrier:
+    // the whole range, and every block has the totals)
+    u32 zu_lo = 0, zu_hi = a.n_zu;
+    u64 bp0 = 0, bc0 = 0, n_tiles = C_all, p_part = W_all;
+    if (a.parts > 1) {
+        grid.sync();
+        zu_lo = sc->cut[0], zu_hi = max(sc->cut[0], sc->cut[1]);
+        bp0 = sc->base_prod[0], bc0 = sc->base_cnt[0];
+        n_tiles = (zu_hi > zu_lo) ? sc->base_cnt[1] - bc0 : 0ull, p_part = (zu_hi > zu_lo) ? sc->base_prod[1] - bp0 : 0ull;
+    }
     {
         u64 prun = my_pp, crun = my_cp;
         for (u32 base = u0; base < u1; base += kPlanThreads) {
@@ -451,14 +458,24 @@ __global__ void __launch_bounds__(kPlanThreads) k_block_plan(const PlanArgs a, P
                 a.pprefix[u - zu_lo] = pex - bp0;
                 if (a.entries) a.entries[u - zu_lo] = 0;
             }
-            if (a.active) { // compact list of the units with tiles (one atomic per block and round; the order does not matter)
-                const u32 flag = (mine && cv != 0) ? 1u : 0u;
-                u32 ftot;
-                const u32 fex = block_excl_scan(flag, s_ws32, ftot);
-                if (tid == 0 && ftot) s_abase = atomicAdd(&a.geo->n_units_active, ftot);
+            if (a.active) {
+                // lists of the units with tiles, one per work class (powers of two around the average unit of the
+                // partition), so that the marking walk can start with the heaviest units: the block counts per class in
+                // shared memory and reserves its places with one atomic per class
+                const bool listed = mine && cv != 0;
+                u32 c = 0, local = 0;
+                if (tid < kUnitClasses) s_cls[tid] = 0;
                 __syncthreads();
-                if (flag) a.active[s_abase + fex] = u - zu_lo;
+                if (listed) {
+                    const u64 avg = max((u64)1, p_part / max(1u, zu_hi - zu_lo));
+                    const int d = (64 - __clzll((long long)max(pv, (u64)1))) - (64 - __clzll((long long)avg)) + 4;
+                    c = (u32)min(max(d, 0), (int)kUnitClasses - 1);
+                    local = atomicAdd(&s_cls[c], 1u);
+                }
                 __syncthreads();
+                if (tid < kUnitClasses) s_cbase[tid] = s_cls[tid] ? atomicAdd(&a.geo->class_count[tid], s_cls[tid]) : 0u;
+                __syncthreads();
+                if (listed) a.active[(size_t)c * a.n_zu + s_cbase[c] + local] = u - zu_lo;
             }
             prun += ptot;
             crun += ctot;
@@ -860,7 +877,8 @@ struct MarkArgs {
     u32 range;              // number of tight codes of the whole product
     u32 *gbm;               // out: bitmap of the partition, bit (code - first code of the partition); zeroed by the host
     u32 *entries;           // out: marked codes per unit (zeroed by k_block_plan)
-    const u32 *active;      // units of the partition that have tiles
+    const u32 *active;      // units of the partition that have tiles, one list per work class (stride n_zu)
+    u32 n_zu;
     const TruncDev *trunc;
     BlockGeo *geo;
 };
@@ -881,14 +899,38 @@ __global__ void __launch_bounds__(128) k_block_mark(const MarkArgs m)
     const u32 bm_s = smem_u32(mbm);
     u32 my_max = 0;
     u64 my_sum = 0;
-    // the units that have tiles (k_block_plan listed them; most units of a sparse range are empty and cost a quarter of this
-    // kernel's instructions when every block stepped over them) are dealt round robin over the blocks: no claim traffic,
-    // and the heavy units of the dense middle of the range are neighbours in the list, so every block gets its share
-    const u32 n_listed = m.geo->n_units_active;
-    for (u32 idx = blockIdx.x; idx < n_listed; idx += gridDim.x) {
-        const u32 zr = __ldg(&m.active[idx]);
+    // the units that have tiles (k_block_plan listed them by work class; most units of a sparse range are empty) are
+    // claimed dynamically, HEAVIEST CLASS FIRST: dealt round robin, the SMs were busy for 105 k - 156 k cycles of the
+    // kernel's 163 k (ncu, pearce1) -- a block that met a heavy unit late finished long after the others.  The claim for
+    // the next unit is issued before the current one is walked, so its round trip hides behind the walk.
+    __shared__ u32 s_cstart[kUnitClasses + 1], s_claim;
+    if (tid == 0) {
+        u32 run = 0;
+        for (int c = (int)kUnitClasses - 1; c >= 0; --c) {
+            s_cstart[c] = run; // first claim number of class c (classes in descending order of work)
+            run += m.geo->class_count[c];
+        }
+        s_cstart[kUnitClasses] = run;
+        s_claim = blockIdx.x; // (the first claim of every block is its own number: no atomic storm at the start)
+    }
+    __syncthreads();
+    const u32 n_listed = s_cstart[kUnitClasses];
+    for (;;) {
+        const u32 kc = s_claim;
+        __syncthreads();
+        if (kc >= n_listed) break;
+        u32 k_next = 0;
+        // (consumed at the end of this unit; no claims at all when every listed unit is some block's first one)
+        if (tid == 0) k_next = n_listed > gridDim.x ? gridDim.x + atomicAdd(&m.geo->claim_mark, 1u) : n_listed;
+        u32 c = kUnitClasses - 1u;
+        while (c > 0u && kc >= s_cstart[c - 1u]) --c; // (class c holds the claims [s_cstart[c], s_cstart[c - 1]))
+        const u32 zr = __ldg(&m.active[(size_t)c * m.n_zu + (kc - s_cstart[c])]);
         const u32 t0 = __ldg(&m.tstart[zr]), t1 = __ldg(&m.tstart[zr + 1]);
-        if (t0 == t1 || zr >= n_units) continue; // (cannot happen)
+        if (t0 == t1 || zr >= n_units) { // (cannot happen)
+            if (tid == 0) s_claim = k_next;
+            __syncthreads();
+            continue;
+        }
         const u64 c0 = code_lo + (u64)zr * m.U, c1 = min((u64)m.range, c0 + m.U);
         const u32 bit0 = (u32)(c0 - code_lo), bit1 = (u32)(c1 - code_lo);
         const u32 w_first = bit0 >> 5, nwords = ((bit1 + 31u) >> 5) - w_first;
@@ -930,6 +972,7 @@ __global__ void __launch_bounds__(128) k_block_mark(const MarkArgs m)
             m.entries[zr] = e;
             my_max = max(my_max, e);
             my_sum += e;
+            s_claim = k_next;
         }
         __syncthreads();
     }
@@ -1949,7 +1992,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     u32 *const zone_count = reinterpret_cast<u32 *>(zbase + zo_zc);
     u64 *const bump = reinterpret_cast<u64 *>(zbase + zo_bump);
     // not zeroed: written before they are read
-    DevBuf work(ctx, ((size_t)HR + 2) * 8 + (nA + nB) * 8 + ((size_t)n_zu + 2) * (4 + 8 + 4 + 8 + 8 + 4 + 4 + 4 + 16) + sizeof(PlanScratch) + sizeof(ZonesScratch) + 1024);
+    DevBuf work(ctx, ((size_t)HR + 2) * 8 + (nA + nB) * 8 + ((size_t)n_zu + 2) * (4 + 8 + 4 + 8 + 8 + 4 + 4 + 16) + (size_t)kUnitClasses * n_zu * 4 + 64 + sizeof(PlanScratch) + sizeof(ZonesScratch) + 1024);
     char *wp = work.as<char>();
     auto carve = [&](size_t bytes) {
         char *r = wp;
@@ -1966,7 +2009,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     u64 *const zone_off = reinterpret_cast<u64 *>(carve(((size_t)n_zu + 2) * 8));
     u64 *const zone_prefix = reinterpret_cast<u64 *>(carve(((size_t)n_zu + 2) * 8));
     u32 *const order = reinterpret_cast<u32 *>(carve(((size_t)n_zu + 2) * 4));
-    u32 *const active = reinterpret_cast<u32 *>(carve(((size_t)n_zu + 2) * 4));
+    u32 *const active = reinterpret_cast<u32 *>(carve(bp.mode == 1 ? (size_t)kUnitClasses * n_zu * 4 + 16 : 16));
     PlanScratch *const plan_sc = reinterpret_cast<PlanScratch *>(carve(sizeof(PlanScratch)));
     ZonesScratch *const zones_sc = reinterpret_cast<ZonesScratch *>(carve(sizeof(ZonesScratch)));
     const u32 coop_grid = std::max<u32>(1, std::min<u32>({(u32)ctx->sm_count, kPlanMaxBlocks, (n_zu + kPlanThreads - 1) / kPlanThreads}));
@@ -2127,6 +2170,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
             ma.gbm = static_cast<u32 *>(gbm_p);
             ma.entries = entries;
             ma.active = active;
+            ma.n_zu = n_zu;
             ma.trunc = trunc ? td : nullptr;
             ma.geo = geo;
             const size_t msmem = ((size_t)(U / 32 + 4) * 4 + 15) & ~15ull;
