@@ -2279,6 +2279,7 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
             // or written; repeat the product the long way
             ctx->size_hint.valid = false;
             res.release_now();
+            if (getenv("PK_BLOCK_DEBUG")) fprintf(stderr, "block path (sparse): the size hint did not hold (%llu entries expected, %llu counted, flags %u): repeating\n", (unsigned long long)n_entries, (unsigned long long)hgeo->entries_total, hgeo->flags);
             return block_multiply(ctx, pl, bp, A, B, keyA, keyB, part, parts, nv, degA, degB, max_degree, prepackA, prepackB);
         }
         key.entries = n_entries;

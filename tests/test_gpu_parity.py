@@ -963,3 +963,61 @@ def test_unsupported_sizes_have_their_own_status(ctx):
     lim, _, _ = ctx.limits(1)
     with pytest.raises(OverflowError):
         ctx.mul(terms({(int(lim[0]),): 1, (0,): 1}, 1), terms(f, 1), 1)
+
+
+# ---------------------------------------------------------------------------------------------- state kept across products
+
+
+def _boxed_sparse_poly(seed, nv, n, side, negate=False):
+    """n distinct terms of the box [0, side)^nv, both corners included (every seed has the same exponent bounds, so the
+    same code range, unit size and term count: what the context's size hint compares)."""
+    rs = np.random.RandomState(seed)
+    codes = set(int(c) for c in rs.choice(side ** nv - 2, size=n - 2, replace=False) + 1) | {0, side ** nv - 1}
+    d = {}
+    for c in sorted(codes):
+        e = []
+        for _ in range(nv):
+            e.append(c % side)
+            c //= side
+        v = int(rs.randint(1, 1000))
+        d[tuple(e)] = -v if negate and (e[0] & 1) else v
+    return d
+
+
+@pytest.mark.parametrize("negate", [False, True])
+def test_repeated_interleaved_and_recycled_operands(negate):
+    """State a context keeps from one product to the next -- the size hint (a product of the same operand objects as the
+    last one sizes its result from it; the device verifies the count and the host repeats the long way on a miss), the
+    bitmap whose bits the accumulating kernel clears itself, the cache of idle device blocks -- never changes the bits:
+    repeated products, products of other shapes in between, and new operands that take the place (device blocks and
+    usually the handle address) of freed ones of the same shape."""
+    nv = 4
+    c2 = pb.Context(0)
+    try:
+        c2.set_tuning(block_min_tile=0)
+        b = terms(_boxed_sparse_poly(100, nv, 2200, 40, negate), nv, 2)
+        db = c2.upload(b, nv)
+        (pf, pg), pnv = po.pearce_operands(5), 5
+        pa, pb_ = terms(pf, pnv, 1), terms(pg, pnv, 2)
+        other = None
+        refs = {}
+        modes = set()
+        for round_ in range(3):
+            for seed in (1, 2, 3):
+                a = terms(_boxed_sparse_poly(seed, nv, 2500, 40, negate), nv, 1)
+                if seed not in refs:
+                    refs[seed] = cpu_ref(a, b, nv, n_threads=4)
+                da = c2.upload(a, nv)
+                for rep in range(3 if round_ == 0 else 2):  # the second and third time the hint holds
+                    r = c2.mul_dev(da, db, algo=pb.PK_ALGO_BLOCK)
+                    modes.add(c2.stats()["retries"] & 1)
+                    assert_terms_equal(r.download(), refs[seed])
+                    r.free()
+                if round_ == 1:  # a product of another shape (other code range, other bitmap extent) in between
+                    out = c2.mul(pa, pb_, pnv, algo=pb.PK_ALGO_BLOCK)
+                    other = other or cpu_ref(pa, pb_, pnv, n_threads=4)
+                    assert_terms_equal(out, other)
+                da.free()  # the next operand of the same shape takes its place
+        assert 1 in modes  # (the sparse, bitmap form of the block kernel is what ran)
+    finally:
+        c2.close()
