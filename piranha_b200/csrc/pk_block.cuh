@@ -2118,7 +2118,8 @@ inline pk_dpoly *block_multiply(pk_ctx *ctx, const Plan &pl, BlockPlan bp, const
     key.parts = std::max<u32>(1, parts);
     key.trunc = trunc ? 1u : 0u;
     key.max_degree = trunc ? max_degree : 0;
-    const bool hint_ok = bt.size_hint && ctx->size_hint.valid && ctx->size_hint.same_key(key);
+    // (tuning size_hint = 2, for tests: the last product's size is taken for ANY next product, so the miss path runs)
+    const bool hint_ok = bt.size_hint && ctx->size_hint.valid && (ctx->size_hint.same_key(key) || bt.size_hint == 2);
     const bool use_hint = bp.mode == 1 && hint_ok;
     StagingView stage{nullptr};
     for (int attempt = 0;; ++attempt) {

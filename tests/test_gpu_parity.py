@@ -1019,5 +1019,15 @@ def test_repeated_interleaved_and_recycled_operands(negate):
                     assert_terms_equal(out, other)
                 da.free()  # the next operand of the same shape takes its place
         assert 1 in modes  # (the sparse, bitmap form of the block kernel is what ran)
+        # the miss path, forced: every product is sized from the one before it, whatever its operands were
+        c2.set_tuning(block_size_hint=2)
+        (ff, fg), fnv = po.fateman_operands(6), 4
+        fa, fb = terms(ff, fnv, 1), terms(fg, fnv, 2)
+        dense_ref = cpu_ref(fa, fb, fnv, n_threads=4)
+        for seed in (1, 2, 3, 1):
+            a = terms(_boxed_sparse_poly(seed, nv, 2500, 40, negate), nv, 1)
+            assert_terms_equal(c2.mul(a, b, nv, algo=pb.PK_ALGO_BLOCK), refs[seed])
+            assert_terms_equal(c2.mul(fa, fb, fnv, algo=pb.PK_ALGO_BLOCK), dense_ref)  # (dense form: the gather is sized by the hint)
+            assert_terms_equal(c2.mul(pa, pb_, pnv, algo=pb.PK_ALGO_BLOCK), other)
     finally:
         c2.close()
