@@ -16,9 +16,11 @@
 #include <exception>
 #include <functional>
 #include <iterator>
+#include <mutex>
 #include <new>
 #include <stdexcept>
 #include <thread>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -36,23 +38,87 @@ namespace detail
 // the pages of) disjoint ranges at once.
 // Large arrays (node pools and bucket heads of results with millions of terms) are 2 MB aligned and advised to use huge
 // pages: a bulk fill touches the bucket heads in random order, one TLB entry per element with 4 KB pages.
+// Freed large blocks are kept (a few, up to PB200_HOST_CACHE_MB megabytes in total, default 1024; 0 = keep nothing) and
+// handed to the next request of about the same size: a benchmark loop or a chain of products builds results of the same
+// size over and over, and fresh pages cost a fault and a kernel zero-fill each (a quarter of the fill of a 5.8 M term
+// result).  glibc does the same below its mmap threshold; these blocks are above it.
+struct big_block_cache {
+    static constexpr std::size_t slots = 8;
+    struct block {
+        void *p;
+        std::size_t bytes;
+    };
+    std::mutex m;
+    block kept[slots] = {};
+    std::size_t total = 0, limit;
+    big_block_cache()
+    {
+        const char *e = std::getenv("PB200_HOST_CACHE_MB");
+        limit = (e ? std::strtoull(e, nullptr, 10) : 1024ull) << 20;
+    }
+    void *take(std::size_t bytes)
+    {
+        std::lock_guard<std::mutex> g(m);
+        block *best = nullptr;
+        for (auto &b : kept)
+            if (b.p && b.bytes >= bytes && b.bytes <= bytes + bytes / 4 && (!best || b.bytes < best->bytes)) best = &b;
+        if (!best) return nullptr;
+        void *p = best->p;
+        total -= best->bytes;
+        *best = block{nullptr, 0};
+        return p;
+    }
+    bool keep(void *p, std::size_t bytes)
+    {
+        std::lock_guard<std::mutex> g(m);
+        if (total + bytes > limit) return false;
+        for (auto &b : kept)
+            if (!b.p) {
+                b = block{p, bytes};
+                total += bytes;
+                return true;
+            }
+        return false;
+    }
+    static big_block_cache &get()
+    {
+        static big_block_cache *c = new big_block_cache; // (never destroyed: containers with static storage duration may free after main)
+        return *c;
+    }
+};
+constexpr std::size_t big_block_min = std::size_t(4) << 20;
 inline void *big_alloc(std::size_t bytes)
 {
     constexpr std::size_t huge = std::size_t(2) << 20;
-    if (bytes >= 2 * huge) {
-        void *p = nullptr;
+    if (bytes >= big_block_min) {
         const std::size_t rounded = (bytes + huge - 1) & ~(huge - 1);
-        if (::posix_memalign(&p, huge, rounded) != 0 || !p) throw std::bad_alloc();
+        if (void *p = big_block_cache::get().take(rounded)) return p;
+        // (the size is kept in front of the block: one huge page of slack keeps the block itself 2 MB aligned)
+        void *raw = nullptr;
+        if (::posix_memalign(&raw, huge, rounded + huge) != 0 || !raw) throw std::bad_alloc();
 #if defined(__linux__) && defined(MADV_HUGEPAGE)
-        ::madvise(p, rounded, MADV_HUGEPAGE);
+        ::madvise(raw, rounded + huge, MADV_HUGEPAGE);
 #endif
+        char *p = static_cast<char *>(raw) + huge;
+        reinterpret_cast<std::size_t *>(p)[-1] = rounded;
         return p;
     }
     void *p = std::malloc(bytes ? bytes : 1);
     if (!p) throw std::bad_alloc();
     return p;
 }
-inline void big_free(void *p) { std::free(p); }
+// bytes: the size the block was requested with
+inline void big_free(void *p, std::size_t bytes)
+{
+    if (!p) return;
+    if (bytes >= big_block_min) {
+        const std::size_t rounded = reinterpret_cast<std::size_t *>(p)[-1];
+        if (big_block_cache::get().keep(p, rounded)) return;
+        std::free(static_cast<char *>(p) - (std::size_t(2) << 20));
+        return;
+    }
+    std::free(p);
+}
 
 // std::allocator that leaves trivially constructible elements uninitialised on resize() (the caller fills them, possibly
 // from several threads) and allocates through big_alloc
@@ -65,7 +131,7 @@ struct raw_big_allocator {
     {
     }
     T *allocate(std::size_t n) { return static_cast<T *>(big_alloc(n * sizeof(T))); }
-    void deallocate(T *p, std::size_t) noexcept { big_free(p); }
+    void deallocate(T *p, std::size_t n) noexcept { big_free(p, n * sizeof(T)); }
     template <typename U>
     void construct(U *p) noexcept(std::is_nothrow_default_constructible<U>::value)
     {
@@ -123,7 +189,7 @@ public:
             ::new (static_cast<void *>(np + i)) Node(std::move(m_p[i]));
             m_p[i].~Node();
         }
-        big_free(m_p);
+        big_free(m_p, m_cap * sizeof(Node));
         m_p = np;
         m_cap = n;
     }
@@ -147,8 +213,26 @@ public:
 private:
     void release()
     {
-        for (std::size_t i = 0; i < m_size; ++i) m_p[i].~Node();
-        big_free(m_p);
+        if (!std::is_trivially_destructible<Node>::value && m_size) {
+            // (a coefficient may own heap storage: every node is visited, by several threads when the pool is large --
+            // 5.8 M nodes take 19 ms on one thread, the time of the fill itself)
+            const std::size_t hw = std::max(1u, std::thread::hardware_concurrency());
+            const std::size_t nt = m_size >= (std::size_t(1) << 20) ? std::min<std::size_t>({16, hw, m_size >> 18}) : 1;
+            Node *p = m_p;
+            const std::size_t n = m_size;
+            auto destroy = [p, n, nt](std::size_t t) {
+                for (std::size_t i = n * t / nt, hi = n * (t + 1) / nt; i < hi; ++i) p[i].~Node();
+            };
+            std::vector<std::thread> th;
+            try {
+                for (std::size_t t = 1; t < nt; ++t) th.emplace_back(destroy, t);
+            } catch (...) { // (no more threads: the rest is done here)
+                for (std::size_t t = th.size() + 1; t < nt; ++t) destroy(t);
+            }
+            destroy(0);
+            for (auto &x : th) x.join();
+        }
+        big_free(m_p, m_cap * sizeof(Node));
         m_p = nullptr;
         m_size = m_cap = 0;
     }

@@ -44,7 +44,36 @@ static void integer_test()
     CHECK_EQUAL(w4.to_string(), "115792089237316195398462578067141184799968521174335529155754622898352762650625");
     CHECK_EQUAL(w4.bits(), 256u);
     CHECK(integer(w4.to_string()) == w4);
-    CHECK_THROW(w4 * w4 * w4, std::overflow_error); // beyond the static capacity: reported, never wrapped
+    // beyond the static storage the value is promoted to the heap (mppp::integer), without limit
+    static_assert(sizeof(integer) == 24, "integer: two limbs in place + size, capacity and sign");
+    CHECK(integer(5).is_static() && w.is_static() && !w4.is_static());
+    const integer w12 = w4 * w4 * w4;
+    CHECK_EQUAL(w12.bits(), 768u);
+    CHECK_EQUAL(w12, w.pow(12));
+    CHECK_EQUAL(w12 / w4, w4 * w4);
+    CHECK((w12 % w4).is_zero());
+    CHECK_EQUAL(integer(w12.to_string()), w12);
+    {
+        integer a = w12, b = w4;      // copies and moves between static and promoted values
+        a = b;
+        CHECK_EQUAL(a, w4);
+        a = integer(7);
+        CHECK_EQUAL(a, integer(7));
+        b = std::move(a);
+        CHECK_EQUAL(b, integer(7));
+        CHECK(a.is_zero());
+        a = w12;
+        a -= w12;
+        CHECK(a.is_zero() && a.sign() == 0);
+        a += w12;
+        a += a;                       // aliased operand
+        CHECK_EQUAL(a, w12 * integer(2));
+        a -= w12;
+        a -= w12 - integer(1);
+        CHECK_EQUAL(a, integer(1));
+        CHECK_EQUAL(a.limb(0), 1u);
+        CHECK_EQUAL(a.limb(1), 0u);
+    }
     CHECK_EQUAL(integer(3).pow(40).to_string(), "12157665459056928801");
     CHECK_THROW(integer("12x"), std::invalid_argument);
 }
