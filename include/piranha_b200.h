@@ -207,6 +207,13 @@ int pk_mul_dev(pk_ctx *ctx, const pk_dpoly *a, const pk_dpoly *b, const pk_opts 
 int pk_check_bounds(pk_ctx *ctx, const pk_dpoly *a, const pk_dpoly *b);
 /* Copy a device polynomial back into library-owned pinned host memory. */
 int pk_download(pk_ctx *ctx, const pk_dpoly *p, pk_result *out);
+/* The same terms, grouped for a hash table: ordered by ((uint64_t)key >> shift) & (2^bits - 1), terms of equal group in
+ * ascending key order (a stable device-side sort, 1 <= bits <= 16).  With the identity hash of the reference's packed
+ * monomial (kronecker_monomial::hash, kronecker_monomial.hpp:441-444) and a power-of-two bucket count 2^b
+ * (hash_set.hpp:1298-1317: bucket = hash mod bucket count), shift = b - bits groups the terms by the TOP bits of their
+ * bucket, so a fill of the container (rehash + _unique_insert, polynomial.hpp:1666-1667) walks the bucket array window by
+ * window instead of at random.  PK_E_UNSUPPORTED on a multi-device context (use pk_download). */
+int pk_download_grouped(pk_ctx *ctx, const pk_dpoly *p, uint32_t shift, uint32_t bits, pk_result *out);
 void pk_dpoly_free(pk_ctx *ctx, pk_dpoly *p);
 uint64_t pk_dpoly_size(const pk_dpoly *p);
 uint32_t pk_dpoly_limbs(const pk_dpoly *p);

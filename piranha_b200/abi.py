@@ -21,7 +21,7 @@ ALGO_NAMES = {0: "auto", 1: "dense", 2: "hash", 3: "zone", 4: "block"}
 
 EXPORTED_SYMBOLS = [
     "pk_ctx_create", "pk_ctx_create_multi", "pk_ctx_device_count", "pk_device_count", "pk_ctx_synchronize", "pk_ctx_destroy", "pk_ctx_trim", "pk_last_error", "pk_ctx_set_limits", "pk_ctx_get_limits", "pk_get_stats", "pk_ctx_set_tuning",
-    "pk_mul", "pk_result_free", "pk_upload", "pk_mul_dev", "pk_check_bounds", "pk_download", "pk_dpoly_free", "pk_dpoly_size",
+    "pk_mul", "pk_result_free", "pk_upload", "pk_mul_dev", "pk_check_bounds", "pk_download", "pk_download_grouped", "pk_dpoly_free", "pk_dpoly_size",
     "pk_dpoly_limbs", "pk_dpoly_nvars", "pk_dpoly_export", "pk_dpoly_export_padded", "pk_dpoly_digest",
     "pk_dpoly_publish_size", "pk_dpoly_export_peers",
 ]
@@ -106,6 +106,7 @@ def load_library():
     lib.pk_mul_dev.argtypes = [vp, vp, vp, C.POINTER(PkOpts), C.POINTER(vp)]
     lib.pk_check_bounds.argtypes = [vp, vp, vp]
     lib.pk_download.argtypes = [vp, vp, C.POINTER(PkResult)]
+    lib.pk_download_grouped.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.POINTER(PkResult)]
     lib.pk_dpoly_free.argtypes = [vp, vp]
     lib.pk_dpoly_free.restype = None
     lib.pk_dpoly_size.argtypes = [vp]
@@ -330,6 +331,12 @@ class Context:
     def download(self, p: DevicePoly) -> Terms:
         r = PkResult()
         self._check(self.lib.pk_download(self.handle, p.handle, C.byref(r)))
+        return self._take_result(self.lib, self.handle, r)
+
+    def download_grouped(self, p: DevicePoly, shift: int, bits: int) -> Terms:
+        """The terms ordered by ((uint64)key >> shift) & (2**bits - 1), ascending keys inside a group (pk_download_grouped)."""
+        r = PkResult()
+        self._check(self.lib.pk_download_grouped(self.handle, p.handle, shift, bits, C.byref(r)))
         return self._take_result(self.lib, self.handle, r)
 
 

@@ -215,6 +215,42 @@ void download_impl(pk_ctx *ctx, const pk_dpoly *p, pk_result *out)
     }
 }
 
+// the terms grouped by ((u64)key >> shift) & (2^bits - 1), ascending keys inside a group (pk_download_grouped)
+void download_grouped_impl(pk_ctx *ctx, const pk_dpoly *p, u32 shift, u32 bits, pk_result *out)
+{
+    memset(out, 0, sizeof(*out));
+    out->n = p->n;
+    out->n_vars = p->n_vars;
+    out->limbs = p->limbs;
+    if (p->n == 0) return;
+    const u64 n = p->n;
+    if (n >= (1ull << 32)) fail(PK_E_UNSUPPORTED, "pk_download_grouped: 2^32 terms or more");
+    const u32 L = p->limbs;
+    DevBuf g0(ctx, n * 4), g1(ctx, n * 4), i0(ctx, n * 4), i1(ctx, n * 4);
+    PK_LAUNCH(ctx, k_group_of, grid_for(n, 256), 256, 0, p->key, n, shift, (1u << bits) - 1u, g0.as<u32>(), i0.as<u32>());
+    radix_sort_pairs(ctx, g0.as<u32>(), g1.as<u32>(), i0.as<u32>(), i1.as<u32>(), n, (int)bits); // (stable: keys stay ascending inside a group)
+    DevBuf dk(ctx, n * 8), dm(ctx, n * L * 8), dsg(ctx, n);
+    PK_LAUNCH(ctx, k_group_gather, grid_for(n, 256), 256, 0, i1.as<u32>(), p->key, p->planes, p->sign, n, L, p->stride, dk.as<i64>(),
+              dm.as<u64>(), dsg.as<signed char>());
+    const size_t key_b = (n * 8 + 63) & ~63ull, mag_b = (n * L * 8 + 63) & ~63ull, sign_b = (n + 63) & ~63ull;
+    PinnedBuf *pb = pinned_acquire(ctx, key_b + mag_b + sign_b);
+    char *base = static_cast<char *>(pb->ptr);
+    out->key = reinterpret_cast<int64_t *>(base);
+    out->mag = reinterpret_cast<uint64_t *>(base + key_b);
+    out->sign = reinterpret_cast<int8_t *>(base + key_b + mag_b);
+    out->owner = pb->ptr;
+    try {
+        CUDA_CHECK(cudaMemcpyAsync(out->key, dk.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(out->mag, dm.p, n * L * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(out->sign, dsg.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    } catch (...) {
+        pb->in_use = false;
+        memset(out, 0, sizeof(*out));
+        throw;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ multiply
 
 Plan make_plan(pk_ctx *ctx, const pk_dpoly *A, const pk_dpoly *B, const pk_opts &o)
@@ -1112,6 +1148,16 @@ int pk_download(pk_ctx *ctx, const pk_dpoly *p, pk_result *out)
             DeviceScope ds(ctx->device);
             download_impl(ctx, p, out);
         }
+    })
+}
+
+int pk_download_grouped(pk_ctx *ctx, const pk_dpoly *p, uint32_t shift, uint32_t bits, pk_result *out)
+{
+    if (!ctx || !p || !out || bits < 1 || bits > 16 || shift > 63) return PK_E_ARGS;
+    PK_TRY(ctx, {
+        if (!ctx->subs.empty() || p->is_multi) fail(PK_E_UNSUPPORTED, "pk_download_grouped: not on a multi-device context (use pk_download)");
+        DeviceScope ds(ctx->device);
+        download_grouped_impl(ctx, p, shift, bits, out);
     })
 }
 

@@ -26,6 +26,27 @@ __global__ void k_planes_to_aos(const u64 *__restrict__ planes, u64 *__restrict_
     for (u32 l = 0; l < out_limbs; ++l) aos[i * out_limbs + l] = l < limbs ? planes[l * stride + i] : 0ull;
 }
 
+// pk_download_grouped: group number of every term, then the terms gathered in the sorted order (magnitudes row-major, as
+// the host result holds them)
+__global__ void k_group_of(const i64 *__restrict__ key, u64 n, u32 shift, u32 mask, u32 *__restrict__ group, u32 *__restrict__ idx)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    group[i] = (u32)((u64)key[i] >> shift) & mask;
+    idx[i] = (u32)i;
+}
+__global__ void k_group_gather(const u32 *__restrict__ perm, const i64 *__restrict__ key, const u64 *__restrict__ planes,
+                               const signed char *__restrict__ sign, u64 n, u32 limbs, u64 stride, i64 *__restrict__ okey,
+                               u64 *__restrict__ oaos, signed char *__restrict__ osign)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 s = perm[i];
+    okey[i] = key[s];
+    for (u32 l = 0; l < limbs; ++l) oaos[i * limbs + l] = planes[l * stride + s];
+    osign[i] = sign[s];
+}
+
 // ---- multi-GPU term exchange over peer-mapped memory (NVLink / NVSwitch): every rank of a partitioned product pushes
 // its terms straight into the result arrays of ALL ranks with plain stores.
 constexpr u32 kMaxPeers = 16;

@@ -521,7 +521,17 @@ private:
             std::unique_lock<std::recursive_mutex> ctx_lock(h->mx);
             pk_ctx *ctx = h->ctx;
             pk_result r{};
-            gpu::check(ctx, pk_download(ctx, m_dev->p, &r));
+            // Large results arrive grouped by the top bits of their bucket in the table they are about to fill (power-of-two
+            // bucket count, bucket = hash mod count, hash = the packed key), so every fill thread walks the bucket heads
+            // window by window (128 KB each, cache resident) instead of at random over tens of megabytes.
+            const std::uint64_t n_dev = pk_dpoly_size(m_dev->p);
+            if (n_dev >= (1u << 20) && n_dev < (std::uint64_t(1) << 32) && pk_ctx_device_count(ctx) == 1u) {
+                unsigned b = 0;
+                while ((std::uint64_t(1) << b) < n_dev) ++b; // the bucket count _bulk_unique_fill will choose
+                gpu::check(ctx, pk_download_grouped(ctx, m_dev->p, b - 8u, 8u, &r));
+            } else {
+                gpu::check(ctx, pk_download(ctx, m_dev->p, &r));
+            }
             try {
                 m_container.clear();
                 const unsigned nt = settings::get_n_threads();

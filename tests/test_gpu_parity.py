@@ -1031,3 +1031,26 @@ def test_repeated_interleaved_and_recycled_operands(negate):
             assert_terms_equal(c2.mul(pa, pb_, pnv, algo=pb.PK_ALGO_BLOCK), other)
     finally:
         c2.close()
+
+
+@pytest.mark.parametrize("shift,bits", [(0, 1), (12, 8), (3, 16), (60, 4)])
+def test_download_grouped(ctx, shift, bits):
+    """pk_download_grouped: the same terms, ordered by ((uint64) key >> shift) & (2^bits - 1) and by key inside a group
+    (what a power-of-two hash table with the identity hash of kronecker_monomial wants to be filled from)."""
+    (f, g), nv = po.pearce_operands(5), 5
+    g = {k: (-v if sum(k) % 3 == 0 else v) for k, v in g.items()}
+    a, b = terms(f, nv, 1), terms(g, nv, 2)
+    r = ctx.mul_dev(ctx.upload(a, nv), ctx.upload(b, nv))
+    plain = r.download()
+    key, mag, sign = ctx.download_grouped(r, shift, bits)
+    group = (key.astype(np.uint64) >> np.uint64(shift)) & np.uint64((1 << bits) - 1)
+    order = np.lexsort((key, group))
+    assert np.array_equal(order, np.arange(len(key)))  # already in (group, key) order
+    back = np.argsort(key, kind="stable")
+    assert_terms_equal((key[back], mag[back], sign[back]), plain)
+    empty = ctx.mul_dev(ctx.upload(terms({}, nv), nv), ctx.upload(b, nv))
+    assert len(ctx.download_grouped(empty, shift, bits)[0]) == 0
+    with pytest.raises(ValueError):
+        ctx.download_grouped(r, 0, 0)
+    with pytest.raises(ValueError):
+        ctx.download_grouped(r, 64, 8)
