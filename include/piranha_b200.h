@@ -214,6 +214,13 @@ int pk_download(pk_ctx *ctx, const pk_dpoly *p, pk_result *out);
  * bucket, so a fill of the container (rehash + _unique_insert, polynomial.hpp:1666-1667) walks the bucket array window by
  * window instead of at random.  PK_E_UNSUPPORTED on a multi-device context (use pk_download). */
 int pk_download_grouped(pk_ctx *ctx, const pk_dpoly *p, uint32_t shift, uint32_t bits, pk_result *out);
+/* pk_download_grouped in n_chunks pieces (1 .. 256, in term order), so that the caller can consume the first terms while
+ * the rest is still crossing PCIe: after every piece fn(user, out, terms_ready) runs on the CALLING thread, and
+ * out->key / mag / sign [0, terms_ready) are final (n, n_vars, limbs and the array addresses are final from the first
+ * call on; a result of zero terms makes no call).  fn must not throw and must not call into this context. */
+typedef void (*pk_progress_fn)(void *user, const pk_result *out, uint64_t terms_ready);
+int pk_download_grouped_progress(pk_ctx *ctx, const pk_dpoly *p, uint32_t shift, uint32_t bits, uint32_t n_chunks,
+                                 pk_progress_fn fn, void *user, pk_result *out);
 void pk_dpoly_free(pk_ctx *ctx, pk_dpoly *p);
 uint64_t pk_dpoly_size(const pk_dpoly *p);
 uint32_t pk_dpoly_limbs(const pk_dpoly *p);

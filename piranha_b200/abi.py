@@ -21,7 +21,7 @@ ALGO_NAMES = {0: "auto", 1: "dense", 2: "hash", 3: "zone", 4: "block"}
 
 EXPORTED_SYMBOLS = [
     "pk_ctx_create", "pk_ctx_create_multi", "pk_ctx_device_count", "pk_device_count", "pk_ctx_synchronize", "pk_ctx_destroy", "pk_ctx_trim", "pk_last_error", "pk_ctx_set_limits", "pk_ctx_get_limits", "pk_get_stats", "pk_ctx_set_tuning",
-    "pk_mul", "pk_result_free", "pk_upload", "pk_mul_dev", "pk_check_bounds", "pk_download", "pk_download_grouped", "pk_dpoly_free", "pk_dpoly_size",
+    "pk_mul", "pk_result_free", "pk_upload", "pk_mul_dev", "pk_check_bounds", "pk_download", "pk_download_grouped", "pk_download_grouped_progress", "pk_dpoly_free", "pk_dpoly_size",
     "pk_dpoly_limbs", "pk_dpoly_nvars", "pk_dpoly_export", "pk_dpoly_export_padded", "pk_dpoly_digest",
     "pk_dpoly_publish_size", "pk_dpoly_export_peers",
 ]
@@ -35,6 +35,9 @@ class PkPoly(C.Structure):
 class PkResult(C.Structure):
     _fields_ = [("n", C.c_uint64), ("n_vars", C.c_uint32), ("limbs", C.c_uint32), ("key", C.POINTER(C.c_int64)),
                 ("mag", C.POINTER(C.c_uint64)), ("sign", C.POINTER(C.c_int8)), ("owner", C.c_void_p)]
+
+
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(PkResult), C.c_uint64)  # pk_progress_fn
 
 
 class PkOpts(C.Structure):
@@ -107,6 +110,7 @@ def load_library():
     lib.pk_check_bounds.argtypes = [vp, vp, vp]
     lib.pk_download.argtypes = [vp, vp, C.POINTER(PkResult)]
     lib.pk_download_grouped.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.POINTER(PkResult)]
+    lib.pk_download_grouped_progress.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, PROGRESS_FN, vp, C.POINTER(PkResult)]
     lib.pk_dpoly_free.argtypes = [vp, vp]
     lib.pk_dpoly_free.restype = None
     lib.pk_dpoly_size.argtypes = [vp]
@@ -333,10 +337,15 @@ class Context:
         self._check(self.lib.pk_download(self.handle, p.handle, C.byref(r)))
         return self._take_result(self.lib, self.handle, r)
 
-    def download_grouped(self, p: DevicePoly, shift: int, bits: int) -> Terms:
-        """The terms ordered by ((uint64)key >> shift) & (2**bits - 1), ascending keys inside a group (pk_download_grouped)."""
+    def download_grouped(self, p: DevicePoly, shift: int, bits: int, n_chunks: int = 0, progress=None) -> Terms:
+        """The terms ordered by ((uint64)key >> shift) & (2**bits - 1), ascending keys inside a group (pk_download_grouped).
+        n_chunks > 0: the copy runs in pieces and progress(terms_ready) is called after each (pk_download_grouped_progress)."""
         r = PkResult()
-        self._check(self.lib.pk_download_grouped(self.handle, p.handle, shift, bits, C.byref(r)))
+        if n_chunks:
+            fn = PROGRESS_FN((lambda user, out, ready: progress(int(ready))) if progress else (lambda user, out, ready: None))
+            self._check(self.lib.pk_download_grouped_progress(self.handle, p.handle, shift, bits, n_chunks, fn, None, C.byref(r)))
+        else:
+            self._check(self.lib.pk_download_grouped(self.handle, p.handle, shift, bits, C.byref(r)))
         return self._take_result(self.lib, self.handle, r)
 
 

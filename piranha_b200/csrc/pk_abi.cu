@@ -216,7 +216,7 @@ void download_impl(pk_ctx *ctx, const pk_dpoly *p, pk_result *out)
 }
 
 // the terms grouped by ((u64)key >> shift) & (2^bits - 1), ascending keys inside a group (pk_download_grouped)
-void download_grouped_impl(pk_ctx *ctx, const pk_dpoly *p, u32 shift, u32 bits, pk_result *out)
+void download_grouped_impl(pk_ctx *ctx, const pk_dpoly *p, u32 shift, u32 bits, pk_result *out, u32 n_chunks, pk_progress_fn fn, void *user)
 {
     memset(out, 0, sizeof(*out));
     out->n = p->n;
@@ -240,11 +240,27 @@ void download_grouped_impl(pk_ctx *ctx, const pk_dpoly *p, u32 shift, u32 bits, 
     out->sign = reinterpret_cast<int8_t *>(base + key_b + mag_b);
     out->owner = pb->ptr;
     try {
-        CUDA_CHECK(cudaMemcpyAsync(out->key, dk.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_CHECK(cudaMemcpyAsync(out->mag, dm.p, n * L * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_CHECK(cudaMemcpyAsync(out->sign, dsg.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+        n_chunks = (u32)std::min<u64>(std::max<u32>(1, n_chunks), n);
+        while (ctx->chunk_events.size() < n_chunks) {
+            cudaEvent_t e;
+            CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); // (not cudaEventBlockingSync: measured ~1.2 ms per wake-up on this platform)
+            ctx->chunk_events.push_back(e);
+        }
+        // all pieces are queued at once (the copies run back to back); the host then follows the events
+        for (u32 c = 0; c < n_chunks; ++c) {
+            const u64 lo = n * c / n_chunks, cnt = n * (c + 1) / n_chunks - lo;
+            CUDA_CHECK(cudaMemcpyAsync(out->key + lo, dk.as<i64>() + lo, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_CHECK(cudaMemcpyAsync(out->mag + lo * L, dm.as<u64>() + lo * L, cnt * L * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_CHECK(cudaMemcpyAsync(out->sign + lo, dsg.as<signed char>() + lo, cnt, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_CHECK(cudaEventRecord(ctx->chunk_events[c], ctx->stream));
+        }
+        for (u32 c = 0; c < n_chunks; ++c) {
+            CUDA_CHECK(cudaEventSynchronize(ctx->chunk_events[c]));
+            if (fn) fn(user, out, n * (c + 1) / n_chunks);
+        }
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     } catch (...) {
+        cudaStreamSynchronize(ctx->stream); // (no copy may still be writing into the buffer when it is handed back)
         pb->in_use = false;
         memset(out, 0, sizeof(*out));
         throw;
@@ -906,6 +922,7 @@ void pk_ctx_destroy(pk_ctx *ctx)
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_mul0) cudaEventDestroy(ctx->ev_mul0);
     if (ctx->ev_mul1) cudaEventDestroy(ctx->ev_mul1);
+    for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
     if (ctx->ev_aux0) cudaEventDestroy(ctx->ev_aux0);
     if (ctx->ev_aux1) cudaEventDestroy(ctx->ev_aux1);
     if (ctx->tiles_buf) cudaFreeAsync(ctx->tiles_buf, ctx->stream);
@@ -1151,14 +1168,20 @@ int pk_download(pk_ctx *ctx, const pk_dpoly *p, pk_result *out)
     })
 }
 
-int pk_download_grouped(pk_ctx *ctx, const pk_dpoly *p, uint32_t shift, uint32_t bits, pk_result *out)
+int pk_download_grouped_progress(pk_ctx *ctx, const pk_dpoly *p, uint32_t shift, uint32_t bits, uint32_t n_chunks, pk_progress_fn fn,
+                                 void *user, pk_result *out)
 {
-    if (!ctx || !p || !out || bits < 1 || bits > 16 || shift > 63) return PK_E_ARGS;
+    if (!ctx || !p || !out || bits < 1 || bits > 16 || shift > 63 || n_chunks < 1 || n_chunks > 256) return PK_E_ARGS;
     PK_TRY(ctx, {
         if (!ctx->subs.empty() || p->is_multi) fail(PK_E_UNSUPPORTED, "pk_download_grouped: not on a multi-device context (use pk_download)");
         DeviceScope ds(ctx->device);
-        download_grouped_impl(ctx, p, shift, bits, out);
+        download_grouped_impl(ctx, p, shift, bits, out, n_chunks, fn, user);
     })
+}
+
+int pk_download_grouped(pk_ctx *ctx, const pk_dpoly *p, uint32_t shift, uint32_t bits, pk_result *out)
+{
+    return pk_download_grouped_progress(ctx, p, shift, bits, 1, nullptr, nullptr, out);
 }
 
 void pk_dpoly_free(pk_ctx *ctx, pk_dpoly *p)

@@ -121,6 +121,7 @@ struct pk_ctx {
     size_t idle_bytes = 0;
     void *bitmap_buf = nullptr; // sparse block path: bitmap of the code range (k_block_mark -> k_block_acc), grow-only
     size_t bitmap_bytes = 0;
+    std::vector<cudaEvent_t> chunk_events; // pk_download_grouped_progress: one event per piece of the copy
     bool bitmap_clean = false;  // the whole buffer is zero (every zone of the last product cleared the bits it consumed)
     void *h_scratch = nullptr; // small pinned read-back area
     pk::MulCounters *d_ctr = nullptr;

@@ -10,6 +10,7 @@
 #define PB200_HASH_SET_HPP
 
 #include <algorithm>
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
 #include <cstdlib>
@@ -473,6 +474,77 @@ public:
         }
         m_nodes.commit(n);
         m_n_elements = n;
+    }
+    // _bulk_unique_fill for elements that are still ARRIVING (a result crossing PCIe in pieces): the index range is cut in
+    // n_chunks pieces dealt round robin over the threads, and a thread starts on a piece when ready_upto(hi) says that the
+    // elements [0, hi) are there (it blocks until then; false = the producer gave up, and the container is left empty).
+    // Returns false when it gave up.
+    template <typename Make, typename HashOf, typename Ready>
+    bool _bulk_unique_fill_streamed(size_type n, Make make, HashOf hash_of, unsigned n_threads, unsigned n_chunks, Ready ready_upto)
+    {
+        if (n >= npos) throw std::overflow_error("hash_set: too many elements");
+        clear();
+        if (!n) return true;
+        size_type nb = 1;
+        while (nb < n) nb <<= 1;
+        n_threads = static_cast<unsigned>(std::max<size_type>(1, std::min<size_type>(n_threads, n / 4096 + 1)));
+        n_chunks = static_cast<unsigned>(std::max<size_type>(n_threads, std::min<size_type>(n_chunks, n)));
+        node *pool = m_nodes.raw(n);
+        m_heads.resize(nb);
+        std::uint32_t *heads = m_heads.data();
+        std::vector<size_type> built(n_chunks, 0); // nodes constructed per piece
+        std::vector<std::exception_ptr> err(n_threads);
+        std::atomic<bool> stop{false};
+        auto clear_heads = [&](unsigned t) {
+            const size_type lo = nb * t / n_threads, hi = nb * (t + 1) / n_threads;
+            std::fill(heads + lo, heads + hi, npos);
+        };
+        auto build = [&](unsigned t) {
+            unsigned c = t;
+            size_type lo = 0, i = 0; // (the count of a piece is stored once, at its end: the counters of the pieces share cache lines)
+            try {
+                for (; c < n_chunks && !stop.load(std::memory_order_relaxed); c += n_threads) {
+                    lo = i = n * c / n_chunks;
+                    const size_type hi = n * (c + 1) / n_chunks;
+                    if (!ready_upto(hi)) {
+                        stop.store(true, std::memory_order_relaxed);
+                        return;
+                    }
+                    for (; i < hi; ++i) {
+                        if (i + 16 < hi) __builtin_prefetch(heads + (hash_of(i + 16) & (nb - 1)), 1, 1);
+                        ::new (static_cast<void *>(pool + i)) node{make(i), npos, true};
+                        pool[i].next = __atomic_exchange_n(heads + (hash_of(i) & (nb - 1)), static_cast<std::uint32_t>(i), __ATOMIC_RELAXED);
+                    }
+                    built[c] = hi - lo;
+                }
+            } catch (...) {
+                if (c < n_chunks) built[c] = i - lo;
+                err[t] = std::current_exception();
+                stop.store(true, std::memory_order_relaxed);
+            }
+        };
+        auto run = [&](auto &&f) {
+            std::vector<std::thread> th;
+            for (unsigned t = 1; t < n_threads; ++t) th.emplace_back(f, t);
+            f(0u);
+            for (auto &x : th) x.join();
+        };
+        run(clear_heads);
+        run(build);
+        if (stop.load()) {
+            for (unsigned c = 0; c < n_chunks; ++c) {
+                const size_type lo = n * c / n_chunks;
+                for (size_type i = lo; i < lo + built[c]; ++i) pool[i].~node();
+            }
+            m_nodes.abandon();
+            clear();
+            for (unsigned t = 0; t < n_threads; ++t)
+                if (err[t]) std::rethrow_exception(err[t]);
+            return false;
+        }
+        m_nodes.commit(n);
+        m_n_elements = n;
+        return true;
     }
     // hint that `bucket` is about to receive an element (bulk fills touch the buckets in random order: one cache miss
     // per element unless the bucket heads are requested a few elements ahead)

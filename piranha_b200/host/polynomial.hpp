@@ -19,6 +19,7 @@
 #define PB200_POLYNOMIAL_HPP
 
 #include <atomic>
+#include <condition_variable>
 #include <algorithm>
 #include <cstddef>
 #include <cstdint>
@@ -523,15 +524,68 @@ private:
             pk_result r{};
             // Large results arrive grouped by the top bits of their bucket in the table they are about to fill (power-of-two
             // bucket count, bucket = hash mod count, hash = the packed key), so every fill thread walks the bucket heads
-            // window by window (128 KB each, cache resident) instead of at random over tens of megabytes.
+            // window by window (128 KB each, cache resident) instead of at random over tens of megabytes -- and in pieces,
+            // so the fill threads work on the first pieces while the rest is still crossing PCIe.
             const std::uint64_t n_dev = pk_dpoly_size(m_dev->p);
-            if (n_dev >= (1u << 20) && n_dev < (std::uint64_t(1) << 32) && pk_ctx_device_count(ctx) == 1u) {
+            const unsigned nt_fill = settings::get_n_threads();
+            if (nt_fill > 1u && n_dev >= (1u << 20) && n_dev < (std::uint64_t(1) << 32) && pk_ctx_device_count(ctx) == 1u) {
                 unsigned b = 0;
-                while ((std::uint64_t(1) << b) < n_dev) ++b; // the bucket count _bulk_unique_fill will choose
-                gpu::check(ctx, pk_download_grouped(ctx, m_dev->p, b - 8u, 8u, &r));
-            } else {
-                gpu::check(ctx, pk_download(ctx, m_dev->p, &r));
+                while ((std::uint64_t(1) << b) < n_dev) ++b; // the bucket count the fill will choose
+                struct progress { // (the fill threads SLEEP while they wait: the thread that follows the copy needs a core to wake up on)
+                    std::mutex mx;
+                    std::condition_variable cv;
+                    std::uint64_t ready = 0;
+                    bool failed = false;
+                    const pk_result *r = nullptr;
+                } pg;
+                m_container.clear();
+                std::exception_ptr fill_err;
+                bool filled = false;
+                std::thread filler([&] {
+                    try {
+                        filled = m_container._bulk_unique_fill_streamed(
+                            n_dev,
+                            [&pg](std::size_t i) {
+                                const pk_result &q = *pg.r;
+                                return term_type(integer::from_limbs(q.sign[i], q.mag + i * q.limbs, q.limbs), Key::from_int(q.key[i]));
+                            },
+                            [&pg](std::size_t i) { return static_cast<std::size_t>(pg.r->key[i]); }, nt_fill, 4u * nt_fill,
+                            [&pg](std::size_t hi) {
+                                std::unique_lock<std::mutex> lk(pg.mx);
+                                pg.cv.wait(lk, [&] { return pg.ready >= hi || pg.failed; });
+                                return pg.ready >= hi;
+                            });
+                    } catch (...) {
+                        fill_err = std::current_exception();
+                    }
+                });
+                const int rc = pk_download_grouped_progress(
+                    ctx, m_dev->p, b - 8u, 8u, 4u * nt_fill,
+                    [](void *user, const pk_result *out, std::uint64_t ready) {
+                        auto *g = static_cast<progress *>(user);
+                        {
+                            std::lock_guard<std::mutex> lk(g->mx);
+                            g->r = out;
+                            g->ready = ready;
+                        }
+                        g->cv.notify_all();
+                    },
+                    &pg, &r);
+                {
+                    std::lock_guard<std::mutex> lk(pg.mx);
+                    if (rc != PK_OK || pg.ready < n_dev) pg.failed = true;
+                }
+                pg.cv.notify_all();
+                filler.join();
+                if (rc == PK_OK) pk_result_free(ctx, &r);
+                if (rc != PK_OK || fill_err || !filled) m_container.clear();
+                gpu::check(ctx, rc);
+                if (fill_err) std::rethrow_exception(fill_err);
+                if (!filled) throw std::runtime_error("polynomial: the fill of the result container was interrupted");
+                m_host_valid.store(true, std::memory_order_release);
+                return;
             }
+            gpu::check(ctx, pk_download(ctx, m_dev->p, &r));
             try {
                 m_container.clear();
                 const unsigned nt = settings::get_n_threads();
