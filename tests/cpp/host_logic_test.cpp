@@ -3,7 +3,9 @@
 // tests/kronecker_array.cpp:52-160 (limits structure, encode/decode round trips), tests/kronecker_monomial_01.cpp:404-461
 // (key multiply) and tests/hash_set_01.cpp (low-level interface).
 #include <cstdint>
+#include <atomic>
 #include <random>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -245,6 +247,51 @@ static void hash_set_test()
         CHECK(thrown);
         CHECK(b.empty());
         CHECK(b.insert(5).second);
+        // the same fill for elements that arrive in pieces (a result crossing PCIe): a producer thread announces them
+        for (unsigned n_chunks : {1u, 7u, 64u}) {
+            std::atomic<std::size_t> ready{0};
+            std::atomic<bool> failed{false};
+            auto wait = [&](std::size_t hi) {
+                while (ready.load(std::memory_order_acquire) < hi) {
+                    if (failed.load()) return false;
+                    std::this_thread::yield();
+                }
+                return true;
+            };
+            std::thread producer([&] {
+                for (std::size_t r = 0; r < nbulk; r += 777) ready.store(std::min<std::size_t>(nbulk, r + 777), std::memory_order_release);
+            });
+            hash_set<int, H> e;
+            e.insert(-1);
+            CHECK(e._bulk_unique_fill_streamed(nbulk, [](std::size_t i) { return static_cast<int>(i * 3); }, [](std::size_t i) { return i * 3; }, nt,
+                                               n_chunks, wait));
+            producer.join();
+            CHECK_EQUAL(e.size(), nbulk);
+            CHECK(e.find(-1) == e.end());
+            std::size_t hits = 0;
+            for (std::size_t i = 0; i < nbulk; ++i) hits += e.find(static_cast<int>(i * 3)) != e.end();
+            CHECK_EQUAL(hits, nbulk);
+            CHECK((std::vector<int>(e.begin(), e.end()) == order1)); // node order = element order, whatever the pieces
+            // a producer that gives up half way: false, and an empty, reusable set
+            ready.store(nbulk / 2);
+            failed.store(true);
+            CHECK(!e._bulk_unique_fill_streamed(nbulk, [](std::size_t i) { return static_cast<int>(i); }, [](std::size_t i) { return i; }, nt,
+                                                n_chunks, wait));
+            CHECK(e.empty());
+            CHECK(e.insert(5).second);
+            // an element constructor that throws
+            failed.store(false);
+            ready.store(nbulk);
+            bool thrown2 = false;
+            try {
+                e._bulk_unique_fill_streamed(nbulk, [](std::size_t i) { if (i == 31234) throw std::overflow_error("x"); return static_cast<int>(i); },
+                                             [](std::size_t i) { return i; }, nt, n_chunks, wait);
+            } catch (const std::overflow_error &) {
+                thrown2 = true;
+            }
+            CHECK(thrown2);
+            CHECK(e.empty());
+        }
     }
     CHECK(settings::get_n_threads() >= 1u);
     settings::set_n_threads(3u);
