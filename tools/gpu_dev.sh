@@ -1,8 +1,15 @@
 #!/bin/bash
-# scratch: timing of the headline workloads (edit freely)
+# scratch: launch list of one product (edit freely)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 300 python tools/run_once.py pearce1 pearce2 pearce1_dynamic --iters 8 2>&1 | grep -v "^block path" | cut -c1-260
-timeout 100 python tools/run_once.py pearce1 --iters 6 --part 3/8 2>&1 | cut -c1-260
-timeout 100 python tools/run_once.py pearce1 --iters 6 --part 0/2 2>&1 | cut -c1-260
-timeout 600 python -m pytest tests -x -q -m gpu -k "block or pearce or trunc or multi_ctx" 2>&1 | tail -2
+W=${1:-fateman1}
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/dev_launches.csv python tools/run_once.py $W --iters 3 > gpurun_out/dev_ncu.log 2>&1
+python - <<'PY'
+import csv
+rows=[r for r in csv.reader(open("gpurun_out/dev_launches.csv")) if len(r)>10]
+hdr=rows[0]; ki=hdr.index("Kernel Name"); vi=hdr.index("Metric Value")
+names=[(r[ki][:60], float(r[vi].replace(",",""))) for r in rows[1:]]
+last=max(i for i,(n,_) in enumerate(names) if "k_prepare" in n)
+for n,v in names[last:]: print(f"{v/1000:9.2f} us  {n}")
+print("sum", sum(v for _,v in names[last:])/1000)
+PY
