@@ -43,6 +43,10 @@ public:
     }
     integer(const integer &o) : integer()
     {
+        if (o.is_static()) { // (the common case: the whole object is its value)
+            std::memcpy(static_cast<void *>(this), static_cast<const void *>(&o), sizeof(integer));
+            return;
+        }
         assign(o.data(), o.m_size);
         m_neg = o.m_neg;
     }
@@ -50,6 +54,10 @@ public:
     integer &operator=(const integer &o)
     {
         if (this != &o) {
+            if (o.is_static() && is_static()) {
+                std::memcpy(static_cast<void *>(this), static_cast<const void *>(&o), sizeof(integer));
+                return *this;
+            }
             assign(o.data(), o.m_size);
             m_neg = o.m_neg;
         }
@@ -181,6 +189,16 @@ public:
             const bool qneg = a.m_neg != b.m_neg, rneg = a.m_neg;
             q = from_u128(x / y, qneg);
             r = from_u128(x % y, rneg);
+            return;
+        }
+        if (b.m_size == 1) { // one-limb divisor (the common denominators of the rational path): one pass of 128 / 64 divisions
+            integer quo(a);
+            const limb_t rm = quo.divmod_small(b.data()[0]);
+            quo.m_neg = quo.m_size && (a.m_neg != b.m_neg);
+            integer rem(rm);
+            rem.m_neg = rem.m_size && a.m_neg;
+            q = std::move(quo);
+            r = std::move(rem);
             return;
         }
         integer quo, rem;

@@ -132,6 +132,94 @@ public:
         }
     }
 
+    // Device terms -> host container: rehash + _unique_insert + _update_size, as sparse_kronecker_multiplication fills its
+    // result (polynomial.hpp:1666-1667, :1750-1754, base_series_multiplier.hpp:934).  make(result, i) builds term i.  The
+    // caller holds the context's lock.
+    // Large results arrive grouped by the top bits of their bucket in the table they are about to fill (power-of-two bucket
+    // count, bucket = hash mod count, hash = the packed key), so every fill thread walks the bucket heads window by window
+    // (128 KB each, cache resident) instead of at random over tens of megabytes -- and in pieces, so the fill threads work
+    // on the first pieces while the rest is still crossing PCIe.
+    template <typename Container, typename Make>
+    static void fill_from_device(pk_ctx *ctx, const pk_dpoly *p, Container &c, Make make)
+    {
+        pk_result r{};
+        const std::uint64_t n_dev = pk_dpoly_size(p);
+        const unsigned nt = settings::get_n_threads();
+        if (nt > 1u && n_dev >= (1u << 20) && n_dev < (std::uint64_t(1) << 32) && pk_ctx_device_count(ctx) == 1u) {
+            unsigned b = 0;
+            while ((std::uint64_t(1) << b) < n_dev) ++b; // the bucket count the fill will choose
+            struct progress { // (the fill threads SLEEP while they wait: the thread that follows the copy needs a core to wake up on)
+                std::mutex mx;
+                std::condition_variable cv;
+                std::uint64_t ready = 0;
+                bool failed = false;
+                const pk_result *r = nullptr;
+            } pg;
+            c.clear();
+            std::exception_ptr fill_err;
+            bool filled = false;
+            std::thread filler([&] {
+                try {
+                    filled = c._bulk_unique_fill_streamed(
+                        n_dev, [&pg, &make](std::size_t i) { return make(*pg.r, i); },
+                        [&pg](std::size_t i) { return static_cast<std::size_t>(pg.r->key[i]); }, nt, 4u * nt,
+                        [&pg](std::size_t hi) {
+                            std::unique_lock<std::mutex> lk(pg.mx);
+                            pg.cv.wait(lk, [&] { return pg.ready >= hi || pg.failed; });
+                            return pg.ready >= hi;
+                        });
+                } catch (...) {
+                    fill_err = std::current_exception();
+                }
+            });
+            const int rc = pk_download_grouped_progress(
+                ctx, p, b - 8u, 8u, 4u * nt,
+                [](void *user, const pk_result *out, std::uint64_t ready) {
+                    auto *g = static_cast<progress *>(user);
+                    {
+                        std::lock_guard<std::mutex> lk(g->mx);
+                        g->r = out;
+                        g->ready = ready;
+                    }
+                    g->cv.notify_all();
+                },
+                &pg, &r);
+            {
+                std::lock_guard<std::mutex> lk(pg.mx);
+                if (rc != PK_OK || pg.ready < n_dev) pg.failed = true;
+            }
+            pg.cv.notify_all();
+            filler.join();
+            if (rc == PK_OK) pk_result_free(ctx, &r);
+            if (rc != PK_OK || fill_err || !filled) c.clear();
+            check(ctx, rc);
+            if (fill_err) std::rethrow_exception(fill_err);
+            if (!filled) throw std::runtime_error("polynomial: the fill of the result container was interrupted");
+            return;
+        }
+        check(ctx, pk_download(ctx, p, &r));
+        try {
+            c.clear();
+            if (nt > 1u && r.n >= (1u << 16)) { // large results: thread-parallel fill
+                c._bulk_unique_fill(
+                    r.n, [&r, &make](std::size_t i) { return make(r, i); }, [&r](std::size_t i) { return static_cast<std::size_t>(r.key[i]); },
+                    nt);
+            } else {
+                c.rehash(std::max<std::size_t>(1, r.n));
+                for (std::uint64_t i = 0; i < r.n; ++i) {
+                    if (i + 24 < r.n) c._prefetch_bucket(c._bucket_from_hash(static_cast<std::size_t>(r.key[i + 24])));
+                    c._unique_insert(make(r, i), c._bucket_from_hash(static_cast<std::size_t>(r.key[i])));
+                }
+                c._update_size(r.n);
+            }
+        } catch (...) {
+            pk_result_free(ctx, &r);
+            c.clear();
+            throw;
+        }
+        pk_result_free(ctx, &r);
+    }
+
 private:
     static std::mutex &slot_mutex()
     {
@@ -521,95 +609,9 @@ private:
             const gpu::handle h = m_dev->h;
             std::unique_lock<std::recursive_mutex> ctx_lock(h->mx);
             pk_ctx *ctx = h->ctx;
-            pk_result r{};
-            // Large results arrive grouped by the top bits of their bucket in the table they are about to fill (power-of-two
-            // bucket count, bucket = hash mod count, hash = the packed key), so every fill thread walks the bucket heads
-            // window by window (128 KB each, cache resident) instead of at random over tens of megabytes -- and in pieces,
-            // so the fill threads work on the first pieces while the rest is still crossing PCIe.
-            const std::uint64_t n_dev = pk_dpoly_size(m_dev->p);
-            const unsigned nt_fill = settings::get_n_threads();
-            if (nt_fill > 1u && n_dev >= (1u << 20) && n_dev < (std::uint64_t(1) << 32) && pk_ctx_device_count(ctx) == 1u) {
-                unsigned b = 0;
-                while ((std::uint64_t(1) << b) < n_dev) ++b; // the bucket count the fill will choose
-                struct progress { // (the fill threads SLEEP while they wait: the thread that follows the copy needs a core to wake up on)
-                    std::mutex mx;
-                    std::condition_variable cv;
-                    std::uint64_t ready = 0;
-                    bool failed = false;
-                    const pk_result *r = nullptr;
-                } pg;
-                m_container.clear();
-                std::exception_ptr fill_err;
-                bool filled = false;
-                std::thread filler([&] {
-                    try {
-                        filled = m_container._bulk_unique_fill_streamed(
-                            n_dev,
-                            [&pg](std::size_t i) {
-                                const pk_result &q = *pg.r;
-                                return term_type(integer::from_limbs(q.sign[i], q.mag + i * q.limbs, q.limbs), Key::from_int(q.key[i]));
-                            },
-                            [&pg](std::size_t i) { return static_cast<std::size_t>(pg.r->key[i]); }, nt_fill, 4u * nt_fill,
-                            [&pg](std::size_t hi) {
-                                std::unique_lock<std::mutex> lk(pg.mx);
-                                pg.cv.wait(lk, [&] { return pg.ready >= hi || pg.failed; });
-                                return pg.ready >= hi;
-                            });
-                    } catch (...) {
-                        fill_err = std::current_exception();
-                    }
-                });
-                const int rc = pk_download_grouped_progress(
-                    ctx, m_dev->p, b - 8u, 8u, 4u * nt_fill,
-                    [](void *user, const pk_result *out, std::uint64_t ready) {
-                        auto *g = static_cast<progress *>(user);
-                        {
-                            std::lock_guard<std::mutex> lk(g->mx);
-                            g->r = out;
-                            g->ready = ready;
-                        }
-                        g->cv.notify_all();
-                    },
-                    &pg, &r);
-                {
-                    std::lock_guard<std::mutex> lk(pg.mx);
-                    if (rc != PK_OK || pg.ready < n_dev) pg.failed = true;
-                }
-                pg.cv.notify_all();
-                filler.join();
-                if (rc == PK_OK) pk_result_free(ctx, &r);
-                if (rc != PK_OK || fill_err || !filled) m_container.clear();
-                gpu::check(ctx, rc);
-                if (fill_err) std::rethrow_exception(fill_err);
-                if (!filled) throw std::runtime_error("polynomial: the fill of the result container was interrupted");
-                m_host_valid.store(true, std::memory_order_release);
-                return;
-            }
-            gpu::check(ctx, pk_download(ctx, m_dev->p, &r));
-            try {
-                m_container.clear();
-                const unsigned nt = settings::get_n_threads();
-                if (nt > 1u && r.n >= (1u << 16)) { // large results: thread-parallel fill
-                    m_container._bulk_unique_fill(
-                        r.n, [&r](std::size_t i) { return term_type(integer::from_limbs(r.sign[i], r.mag + i * r.limbs, r.limbs), Key::from_int(r.key[i])); },
-                        [&r](std::size_t i) { return static_cast<std::size_t>(r.key[i]); }, nt);
-                    pk_result_free(ctx, &r);
-                    m_host_valid.store(true, std::memory_order_release);
-                    return;
-                }
-                m_container.rehash(std::max<std::size_t>(1, r.n));
-                for (std::uint64_t i = 0; i < r.n; ++i) {
-                    if (i + 24 < r.n) m_container._prefetch_bucket(m_container._bucket_from_hash(static_cast<std::size_t>(r.key[i + 24])));
-                    term_type t(integer::from_limbs(r.sign[i], r.mag + i * r.limbs, r.limbs), Key::from_int(r.key[i]));
-                    m_container._unique_insert(std::move(t), m_container._bucket_from_hash(static_cast<std::size_t>(r.key[i])));
-                }
-                m_container._update_size(r.n);
-            } catch (...) {
-                pk_result_free(ctx, &r);
-                m_container.clear();
-                throw;
-            }
-            pk_result_free(ctx, &r);
+            gpu::fill_from_device(ctx, m_dev->p, m_container, [](const pk_result &q, std::size_t i) {
+                return term_type(integer::from_limbs(q.sign[i], q.mag + i * q.limbs, q.limbs), Key::from_int(q.key[i]));
+            });
             m_host_valid.store(true, std::memory_order_release);
         }
     }

@@ -7,6 +7,9 @@
 #ifndef PB200_RATIONAL_HPP
 #define PB200_RATIONAL_HPP
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <iostream>
 #include <stdexcept>
 #include <type_traits>
@@ -123,9 +126,13 @@ public:
     using degree_type = series_type::degree_type;
 
     explicit series_multiplier(const series_type &s1, const series_type &s2)
-        : m_ss(s1.get_symbol_set()), m_lcm1(lcm_of(s1)), m_lcm2(lcm_of(s2)), m_p1(scaled(s1, m_lcm1)), m_p2(scaled(s2, m_lcm2)),
-          m_mult(check(s1, s2, m_p1), m_p2)
+        : m_t0(std::chrono::steady_clock::now()), m_ss(s1.get_symbol_set()), m_lcm1(lcm_of(s1)), m_lcm2(lcm_of(s2)), m_p1(scaled(s1, m_lcm1)),
+          m_p2(scaled(s2, m_lcm2)), m_t1(std::chrono::steady_clock::now()), m_mult(check(s1, s2, m_p1), m_p2)
     {
+        if (std::getenv("PB200_TRACE"))
+            std::fprintf(stderr, "[pb200 rational] lcm + scaled operands %.3f ms, multiplier construction (bounds, uploads) %.3f ms\n",
+                         std::chrono::duration<double, std::milli>(m_t1 - m_t0).count(),
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - m_t1).count());
     }
     series_multiplier(const series_multiplier &) = delete;
     series_multiplier &operator=(const series_multiplier &) = delete;
@@ -143,7 +150,18 @@ public:
         }
         return _truncated_multiplication(std::get<1>(t), names, idx);
     }
-    series_type _untruncated_multiplication() const { return finalise(m_mult._untruncated_multiplication()); }
+    series_type _untruncated_multiplication() const
+    {
+        if (!std::getenv("PB200_TRACE")) return finalise(m_mult._untruncated_multiplication());
+        const auto t0 = std::chrono::steady_clock::now();
+        const int_series p = m_mult._untruncated_multiplication();
+        const auto t1 = std::chrono::steady_clock::now();
+        series_type r = finalise(p);
+        const auto t2 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[pb200 rational] integer product %.3f ms, result over the common denominator %.3f ms\n",
+                     std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
+        return r;
+    }
     series_type _truncated_multiplication(const degree_type &max_degree) const
     {
         return finalise(m_mult._truncated_multiplication(max_degree));
@@ -166,6 +184,7 @@ private:
         integer l(1);
         for (const auto &t : s._container()) {
             const integer &d = t.m_cf.den();
+            if (d.size() == 1 && d.limb(0) == 1) continue; // an integral coefficient leaves the lcm as it is
             l = l / integer::gcd(l, d) * d;
         }
         return l;
@@ -177,7 +196,18 @@ private:
         r.set_symbol_set(s.get_symbol_set());
         auto &c = r._container();
         c.rehash(std::max<std::size_t>(1, s.size()));
-        for (const auto &t : s._container()) c.insert(int_series::term_type(t.m_cf.num() * (lcm / t.m_cf.den()), t.m_key));
+        const bool lcm_is_one = lcm.size() == 1 && lcm.limb(0) == 1;
+        std::size_t n = 0;
+        for (const auto &t : s._container()) { // (the keys are those of s: unique, so the low-level insertion of the multipliers does)
+            const integer &d = t.m_cf.den();
+            const bool d_is_one = d.size() == 1 && d.limb(0) == 1;
+            integer v = lcm_is_one ? t.m_cf.num() : (d_is_one ? t.m_cf.num() * lcm : t.m_cf.num() * (lcm / d));
+            int_series::term_type it(std::move(v), t.m_key);
+            const auto b = c._bucket(it);
+            c._unique_insert(std::move(it), b);
+            ++n;
+        }
+        c._update_size(n);
         return r;
     }
     // den = lcm1 * lcm2, canonicalised (finalise_impl, base_series_multiplier.hpp:275-326)
@@ -190,22 +220,10 @@ private:
         if (!p.m_host_valid.load(std::memory_order_acquire)) { // product still in HBM: fill the rational container straight from the downloaded terms
             const gpu::handle h = p.m_dev->h;
             std::lock_guard<std::recursive_mutex> ctx_lock(h->mx);
-            pk_ctx *ctx = h->ctx;
-            pk_result res{};
-            gpu::check(ctx, pk_download(ctx, p.m_dev->p, &res));
-            try {
-                c._bulk_unique_fill(
-                    res.n,
-                    [&res, &den](std::size_t i) {
-                        return series_type::term_type(rational(integer::from_limbs(res.sign[i], res.mag + i * res.limbs, res.limbs), den),
-                                                      key_type::from_int(res.key[i]));
-                    },
-                    [&res](std::size_t i) { return static_cast<std::size_t>(res.key[i]); }, settings::get_n_threads());
-            } catch (...) {
-                pk_result_free(ctx, &res);
-                throw;
-            }
-            pk_result_free(ctx, &res);
+            gpu::fill_from_device(h->ctx, p.m_dev->p, c, [&den](const pk_result &res, std::size_t i) {
+                return series_type::term_type(rational(integer::from_limbs(res.sign[i], res.mag + i * res.limbs, res.limbs), den),
+                                              key_type::from_int(res.key[i]));
+            });
             return r;
         }
         c.rehash(std::max<std::size_t>(1, p.size()));
@@ -213,9 +231,11 @@ private:
         return r;
     }
 
+    std::chrono::steady_clock::time_point m_t0; // (PB200_TRACE=1 prints the phases)
     symbol_fset m_ss;
     integer m_lcm1, m_lcm2;
     int_series m_p1, m_p2;
+    std::chrono::steady_clock::time_point m_t1;
     series_multiplier<int_series> m_mult;
 };
 
