@@ -48,7 +48,7 @@ struct BlockGeo {
     u32 max_entries;    // most marked codes in one zone unit
     u32 claim_mark;     // dynamic claim counters
     u32 claim_acc;
-    u32 n_units_active; // units of the partition that have tiles (the marking walk visits only these)
+    u32 pad;
     u64 products_all;   // pair count of the whole product (before degree tests)
     u64 products_part;  // pair count of this partition (before degree tests)
     u64 entries_total;  // marked codes of the partition: the result size unless coefficients cancel

@@ -3,6 +3,7 @@
 // tests/kronecker_array.cpp:52-160 (limits structure, encode/decode round trips), tests/kronecker_monomial_01.cpp:404-461
 // (key multiply) and tests/hash_set_01.cpp (low-level interface).
 #include <cstdint>
+#include <cstring>
 #include <atomic>
 #include <random>
 #include <thread>
@@ -292,6 +293,33 @@ static void hash_set_test()
             CHECK(thrown2);
             CHECK(e.empty());
         }
+    }
+    // large arrays come from 2 MB aligned blocks that are recycled: the next block of about the same size is the freed one
+    {
+        using detail::big_alloc;
+        using detail::big_free;
+        const std::size_t bytes = (std::size_t(9) << 20) + 12345;
+        void *p1 = big_alloc(bytes);
+        CHECK((reinterpret_cast<std::uintptr_t>(p1) & ((std::size_t(2) << 20) - 1)) == 0u);
+        std::memset(p1, 0xAB, bytes);
+        big_free(p1, bytes);
+        void *p2 = big_alloc(bytes - 4096); // a little smaller: same block
+        CHECK(p2 == p1);
+        void *p3 = big_alloc(bytes); // the cache is empty now: a new block
+        CHECK(p3 != p2);
+        void *p4 = big_alloc(bytes * 4); // much larger than anything kept
+        big_free(p2, bytes - 4096);
+        big_free(p3, bytes);
+        big_free(p4, bytes * 4);
+        void *small = big_alloc(100); // small arrays go to malloc
+        big_free(small, 100);
+        big_free(nullptr, 0);
+        hash_set<int, H> big1;
+        big1._bulk_unique_fill(3u << 20, [](std::size_t i) { return static_cast<int>(i); }, [](std::size_t i) { return i; }, 4u);
+        CHECK_EQUAL(big1.size(), std::size_t(3u << 20));
+        big1.clear();
+        big1._bulk_unique_fill(3u << 20, [](std::size_t i) { return static_cast<int>(i) + 1; }, [](std::size_t i) { return i + 1; }, 4u);
+        CHECK(big1.find(3 << 20) != big1.end() && big1.find(0) == big1.end());
     }
     CHECK(settings::get_n_threads() >= 1u);
     settings::set_n_threads(3u);
