@@ -217,10 +217,13 @@ int pk_download_grouped(pk_ctx *ctx, const pk_dpoly *p, uint32_t shift, uint32_t
 /* pk_download_grouped in n_chunks pieces (1 .. 256, in term order), so that the caller can consume the first terms while
  * the rest is still crossing PCIe: after every piece fn(user, out, terms_ready) runs on the CALLING thread, and
  * out->key / mag / sign [0, terms_ready) are final (n, n_vars, limbs and the array addresses are final from the first
- * call on; a result of zero terms makes no call).  fn must not throw and must not call into this context. */
+ * call on; a result of zero terms makes no call).  fn must not throw and must not call into this context.
+ * group_offsets: NULL, or room for 2^bits + 1 entries, filled BEFORE the first call of fn: group g is the terms
+ * [group_offsets[g], group_offsets[g + 1]) -- with shift = b - bits as above, the terms of one group fall into a range of
+ * buckets that no other group touches, so a thread that fills whole groups needs no atomics on the bucket array. */
 typedef void (*pk_progress_fn)(void *user, const pk_result *out, uint64_t terms_ready);
 int pk_download_grouped_progress(pk_ctx *ctx, const pk_dpoly *p, uint32_t shift, uint32_t bits, uint32_t n_chunks,
-                                 pk_progress_fn fn, void *user, pk_result *out);
+                                 pk_progress_fn fn, void *user, uint64_t *group_offsets, pk_result *out);
 void pk_dpoly_free(pk_ctx *ctx, pk_dpoly *p);
 uint64_t pk_dpoly_size(const pk_dpoly *p);
 uint32_t pk_dpoly_limbs(const pk_dpoly *p);

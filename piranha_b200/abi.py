@@ -110,7 +110,7 @@ def load_library():
     lib.pk_check_bounds.argtypes = [vp, vp, vp]
     lib.pk_download.argtypes = [vp, vp, C.POINTER(PkResult)]
     lib.pk_download_grouped.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.POINTER(PkResult)]
-    lib.pk_download_grouped_progress.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, PROGRESS_FN, vp, C.POINTER(PkResult)]
+    lib.pk_download_grouped_progress.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, PROGRESS_FN, vp, vp, C.POINTER(PkResult)]
     lib.pk_dpoly_free.argtypes = [vp, vp]
     lib.pk_dpoly_free.restype = None
     lib.pk_dpoly_size.argtypes = [vp]
@@ -337,13 +337,17 @@ class Context:
         self._check(self.lib.pk_download(self.handle, p.handle, C.byref(r)))
         return self._take_result(self.lib, self.handle, r)
 
-    def download_grouped(self, p: DevicePoly, shift: int, bits: int, n_chunks: int = 0, progress=None) -> Terms:
+    def download_grouped(self, p: DevicePoly, shift: int, bits: int, n_chunks: int = 0, progress=None, offsets=None) -> Terms:
         """The terms ordered by ((uint64)key >> shift) & (2**bits - 1), ascending keys inside a group (pk_download_grouped).
-        n_chunks > 0: the copy runs in pieces and progress(terms_ready) is called after each (pk_download_grouped_progress)."""
+        n_chunks > 0: the copy runs in pieces and progress(terms_ready) is called after each (pk_download_grouped_progress);
+        offsets: a uint64 numpy array of 2**bits + 1 entries that receives the first term of every group."""
         r = PkResult()
         if n_chunks:
             fn = PROGRESS_FN((lambda user, out, ready: progress(int(ready))) if progress else (lambda user, out, ready: None))
-            self._check(self.lib.pk_download_grouped_progress(self.handle, p.handle, shift, bits, n_chunks, fn, None, C.byref(r)))
+            if offsets is not None:
+                assert offsets.dtype == np.uint64 and offsets.flags["C_CONTIGUOUS"] and len(offsets) == (1 << bits) + 1
+            optr = offsets.ctypes.data_as(C.c_void_p) if offsets is not None else None
+            self._check(self.lib.pk_download_grouped_progress(self.handle, p.handle, shift, bits, n_chunks, fn, None, optr, C.byref(r)))
         else:
             self._check(self.lib.pk_download_grouped(self.handle, p.handle, shift, bits, C.byref(r)))
         return self._take_result(self.lib, self.handle, r)

@@ -216,19 +216,25 @@ void download_impl(pk_ctx *ctx, const pk_dpoly *p, pk_result *out)
 }
 
 // the terms grouped by ((u64)key >> shift) & (2^bits - 1), ascending keys inside a group (pk_download_grouped)
-void download_grouped_impl(pk_ctx *ctx, const pk_dpoly *p, u32 shift, u32 bits, pk_result *out, u32 n_chunks, pk_progress_fn fn, void *user)
+void download_grouped_impl(pk_ctx *ctx, const pk_dpoly *p, u32 shift, u32 bits, pk_result *out, u32 n_chunks, pk_progress_fn fn, void *user,
+                           uint64_t *group_offsets)
 {
     memset(out, 0, sizeof(*out));
     out->n = p->n;
     out->n_vars = p->n_vars;
     out->limbs = p->limbs;
-    if (p->n == 0) return;
+    if (p->n == 0) {
+        if (group_offsets) std::fill(group_offsets, group_offsets + (1u << bits) + 1, 0ull);
+        return;
+    }
     const u64 n = p->n;
     if (n >= (1ull << 32)) fail(PK_E_UNSUPPORTED, "pk_download_grouped: 2^32 terms or more");
     const u32 L = p->limbs;
     DevBuf g0(ctx, n * 4), g1(ctx, n * 4), i0(ctx, n * 4), i1(ctx, n * 4);
     PK_LAUNCH(ctx, k_group_of, grid_for(n, 256), 256, 0, p->key, n, shift, (1u << bits) - 1u, g0.as<u32>(), i0.as<u32>());
     radix_sort_pairs(ctx, g0.as<u32>(), g1.as<u32>(), i0.as<u32>(), i1.as<u32>(), n, (int)bits); // (stable: keys stay ascending inside a group)
+    DevBuf goff(ctx, group_offsets ? ((size_t)(1u << bits) + 1) * 8 : 0);
+    if (group_offsets) PK_LAUNCH(ctx, k_group_offsets, grid_for((1u << bits) + 1, 256), 256, 0, g1.as<u32>(), n, 1u << bits, goff.as<u64>());
     DevBuf dk(ctx, n * 8), dm(ctx, n * L * 8), dsg(ctx, n);
     PK_LAUNCH(ctx, k_group_gather, grid_for(n, 256), 256, 0, i1.as<u32>(), p->key, p->planes, p->sign, n, L, p->stride, dk.as<i64>(),
               dm.as<u64>(), dsg.as<signed char>());
@@ -245,6 +251,10 @@ void download_grouped_impl(pk_ctx *ctx, const pk_dpoly *p, u32 shift, u32 bits, 
             cudaEvent_t e;
             CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); // (not cudaEventBlockingSync: measured ~1.2 ms per wake-up on this platform)
             ctx->chunk_events.push_back(e);
+        }
+        if (group_offsets) { // (a small copy into the caller's memory: complete when the call returns)
+            CUDA_CHECK(cudaMemcpyAsync(group_offsets, goff.p, ((size_t)(1u << bits) + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         }
         // all pieces are queued at once (the copies run back to back); the host then follows the events
         for (u32 c = 0; c < n_chunks; ++c) {
@@ -1169,19 +1179,19 @@ int pk_download(pk_ctx *ctx, const pk_dpoly *p, pk_result *out)
 }
 
 int pk_download_grouped_progress(pk_ctx *ctx, const pk_dpoly *p, uint32_t shift, uint32_t bits, uint32_t n_chunks, pk_progress_fn fn,
-                                 void *user, pk_result *out)
+                                 void *user, uint64_t *group_offsets, pk_result *out)
 {
     if (!ctx || !p || !out || bits < 1 || bits > 16 || shift > 63 || n_chunks < 1 || n_chunks > 256) return PK_E_ARGS;
     PK_TRY(ctx, {
         if (!ctx->subs.empty() || p->is_multi) fail(PK_E_UNSUPPORTED, "pk_download_grouped: not on a multi-device context (use pk_download)");
         DeviceScope ds(ctx->device);
-        download_grouped_impl(ctx, p, shift, bits, out, n_chunks, fn, user);
+        download_grouped_impl(ctx, p, shift, bits, out, n_chunks, fn, user, group_offsets);
     })
 }
 
 int pk_download_grouped(pk_ctx *ctx, const pk_dpoly *p, uint32_t shift, uint32_t bits, pk_result *out)
 {
-    return pk_download_grouped_progress(ctx, p, shift, bits, 1, nullptr, nullptr, out);
+    return pk_download_grouped_progress(ctx, p, shift, bits, 1, nullptr, nullptr, nullptr, out);
 }
 
 void pk_dpoly_free(pk_ctx *ctx, pk_dpoly *p)

@@ -35,6 +35,19 @@ __global__ void k_group_of(const i64 *__restrict__ key, u64 n, u32 shift, u32 ma
     group[i] = (u32)((u64)key[i] >> shift) & mask;
     idx[i] = (u32)i;
 }
+// first position of every group in the sorted group numbers (lower bound), and n for the entry past the last group
+__global__ void k_group_offsets(const u32 *__restrict__ sorted_group, u64 n, u32 n_groups, u64 *__restrict__ off)
+{
+    const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n_groups) return;
+    u64 lo = 0, hi = n;
+    while (lo < hi) {
+        const u64 mid = (lo + hi) >> 1;
+        if (sorted_group[mid] < g) lo = mid + 1;
+        else hi = mid;
+    }
+    off[g] = lo;
+}
 __global__ void k_group_gather(const u32 *__restrict__ perm, const i64 *__restrict__ key, const u64 *__restrict__ planes,
                                const signed char *__restrict__ sign, u64 n, u32 limbs, u64 stride, i64 *__restrict__ okey,
                                u64 *__restrict__ oaos, signed char *__restrict__ osign)

@@ -482,17 +482,30 @@ public:
     template <typename Make, typename HashOf, typename Ready>
     bool _bulk_unique_fill_streamed(size_type n, Make make, HashOf hash_of, unsigned n_threads, unsigned n_chunks, Ready ready_upto)
     {
+        n_threads = static_cast<unsigned>(std::max<size_type>(1, std::min<size_type>(n_threads, n / 4096 + 1)));
+        n_chunks = static_cast<unsigned>(std::max<size_type>(n_threads, std::min<size_type>(n_chunks, std::max<size_type>(n, 1))));
+        return _bulk_unique_fill_streamed(
+            n, make, hash_of, n_threads, n_chunks, ready_upto,
+            [n, n_chunks](unsigned c) { return std::make_pair(n * c / n_chunks, n * (c + 1) / n_chunks); }, false);
+    }
+    // The general form: piece c is the elements [range_of(c).first, range_of(c).second) -- the pieces tile [0, n), in
+    // order; range_of is first called after ready_upto(1) returned true (the producer may deliver the ranges with the
+    // first elements).  exclusive_buckets: the caller guarantees that no two pieces share a bucket (elements grouped by
+    // the top bits of their bucket, one piece per group): bucket heads are then updated with plain stores.
+    template <typename Make, typename HashOf, typename Ready, typename Range>
+    bool _bulk_unique_fill_streamed(size_type n, Make make, HashOf hash_of, unsigned n_threads, unsigned n_chunks, Ready ready_upto,
+                                    Range range_of, bool exclusive_buckets)
+    {
         if (n >= npos) throw std::overflow_error("hash_set: too many elements");
         clear();
         if (!n) return true;
         size_type nb = 1;
         while (nb < n) nb <<= 1;
-        n_threads = static_cast<unsigned>(std::max<size_type>(1, std::min<size_type>(n_threads, n / 4096 + 1)));
-        n_chunks = static_cast<unsigned>(std::max<size_type>(n_threads, std::min<size_type>(n_chunks, n)));
+        n_threads = std::max(1u, std::min(n_threads, n_chunks));
         node *pool = m_nodes.raw(n);
         m_heads.resize(nb);
         std::uint32_t *heads = m_heads.data();
-        std::vector<size_type> built(n_chunks, 0); // nodes constructed per piece
+        std::vector<std::pair<size_type, size_type>> built(n_chunks, {0, 0}); // {first node, nodes constructed} per piece
         std::vector<std::exception_ptr> err(n_threads);
         std::atomic<bool> stop{false};
         auto clear_heads = [&](unsigned t) {
@@ -503,22 +516,37 @@ public:
             unsigned c = t;
             size_type lo = 0, i = 0; // (the count of a piece is stored once, at its end: the counters of the pieces share cache lines)
             try {
+                if (!ready_upto(1)) {
+                    stop.store(true, std::memory_order_relaxed);
+                    return;
+                }
                 for (; c < n_chunks && !stop.load(std::memory_order_relaxed); c += n_threads) {
-                    lo = i = n * c / n_chunks;
-                    const size_type hi = n * (c + 1) / n_chunks;
-                    if (!ready_upto(hi)) {
+                    const auto range = range_of(c);
+                    lo = i = range.first;
+                    const size_type hi = range.second;
+                    if (hi <= lo) continue;
+                    if (hi > n || !ready_upto(hi)) {
                         stop.store(true, std::memory_order_relaxed);
                         return;
                     }
-                    for (; i < hi; ++i) {
-                        if (i + 16 < hi) __builtin_prefetch(heads + (hash_of(i + 16) & (nb - 1)), 1, 1);
-                        ::new (static_cast<void *>(pool + i)) node{make(i), npos, true};
-                        pool[i].next = __atomic_exchange_n(heads + (hash_of(i) & (nb - 1)), static_cast<std::uint32_t>(i), __ATOMIC_RELAXED);
+                    if (exclusive_buckets) {
+                        for (; i < hi; ++i) {
+                            if (i + 16 < hi) __builtin_prefetch(heads + (hash_of(i + 16) & (nb - 1)), 1, 1);
+                            std::uint32_t &head = heads[hash_of(i) & (nb - 1)];
+                            ::new (static_cast<void *>(pool + i)) node{make(i), head, true};
+                            head = static_cast<std::uint32_t>(i);
+                        }
+                    } else {
+                        for (; i < hi; ++i) {
+                            if (i + 16 < hi) __builtin_prefetch(heads + (hash_of(i + 16) & (nb - 1)), 1, 1);
+                            ::new (static_cast<void *>(pool + i)) node{make(i), npos, true};
+                            pool[i].next = __atomic_exchange_n(heads + (hash_of(i) & (nb - 1)), static_cast<std::uint32_t>(i), __ATOMIC_RELAXED);
+                        }
                     }
-                    built[c] = hi - lo;
+                    built[c] = {lo, hi - lo};
                 }
             } catch (...) {
-                if (c < n_chunks) built[c] = i - lo;
+                if (c < n_chunks) built[c] = {lo, i - lo};
                 err[t] = std::current_exception();
                 stop.store(true, std::memory_order_relaxed);
             }
@@ -531,11 +559,11 @@ public:
         };
         run(clear_heads);
         run(build);
-        if (stop.load()) {
-            for (unsigned c = 0; c < n_chunks; ++c) {
-                const size_type lo = n * c / n_chunks;
-                for (size_type i = lo; i < lo + built[c]; ++i) pool[i].~node();
-            }
+        size_type total = 0;
+        for (unsigned c = 0; c < n_chunks; ++c) total += built[c].second;
+        if (stop.load() || total != n) { // (total != n: the pieces did not tile [0, n))
+            for (unsigned c = 0; c < n_chunks; ++c)
+                for (size_type i = built[c].first; i < built[c].first + built[c].second; ++i) pool[i].~node();
             m_nodes.abandon();
             clear();
             for (unsigned t = 0; t < n_threads; ++t)

@@ -158,22 +158,27 @@ public:
             c.clear();
             std::exception_ptr fill_err;
             bool filled = false;
+            // one piece of the fill per group: the groups own disjoint ranges of buckets, so the bucket heads need no atomics
+            constexpr unsigned group_bits = 8u, n_groups = 1u << group_bits;
+            std::vector<std::uint64_t> goff(n_groups + 1u, 0); // (written by the library before the first progress call)
             std::thread filler([&] {
                 try {
                     filled = c._bulk_unique_fill_streamed(
                         n_dev, [&pg, &make](std::size_t i) { return make(*pg.r, i); },
-                        [&pg](std::size_t i) { return static_cast<std::size_t>(pg.r->key[i]); }, nt, 4u * nt,
+                        [&pg](std::size_t i) { return static_cast<std::size_t>(pg.r->key[i]); }, nt, n_groups,
                         [&pg](std::size_t hi) {
                             std::unique_lock<std::mutex> lk(pg.mx);
                             pg.cv.wait(lk, [&] { return pg.ready >= hi || pg.failed; });
                             return pg.ready >= hi;
-                        });
+                        },
+                        [&goff](unsigned g) { return std::make_pair(static_cast<std::size_t>(goff[g]), static_cast<std::size_t>(goff[g + 1u])); },
+                        true);
                 } catch (...) {
                     fill_err = std::current_exception();
                 }
             });
             const int rc = pk_download_grouped_progress(
-                ctx, p, b - 8u, 8u, 4u * nt,
+                ctx, p, b - group_bits, group_bits, 4u * nt,
                 [](void *user, const pk_result *out, std::uint64_t ready) {
                     auto *g = static_cast<progress *>(user);
                     {
@@ -183,7 +188,7 @@ public:
                     }
                     g->cv.notify_all();
                 },
-                &pg, &r);
+                &pg, goff.data(), &r);
             {
                 std::lock_guard<std::mutex> lk(pg.mx);
                 if (rc != PK_OK || pg.ready < n_dev) pg.failed = true;

@@ -273,6 +273,46 @@ static void hash_set_test()
             for (std::size_t i = 0; i < nbulk; ++i) hits += e.find(static_cast<int>(i * 3)) != e.end();
             CHECK_EQUAL(hits, nbulk);
             CHECK((std::vector<int>(e.begin(), e.end()) == order1)); // node order = element order, whatever the pieces
+            // pieces = groups of elements that own disjoint bucket ranges (grouped by the top bits of the bucket): plain
+            // stores on the bucket heads
+            {
+                const std::size_t nb = 65536, n_groups = 16;
+                std::vector<int> grouped;
+                std::vector<std::size_t> goff(n_groups + 1, 0);
+                for (std::size_t g = 0; g < n_groups; ++g) {
+                    goff[g] = grouped.size();
+                    for (std::size_t i = 0; i < nbulk; ++i)
+                        if (((i * 3) & (nb - 1)) >> 12 == g) grouped.push_back(static_cast<int>(i * 3));
+                }
+                goff[n_groups] = grouped.size();
+                CHECK_EQUAL(grouped.size(), nbulk);
+                std::atomic<std::size_t> ready2{0};
+                std::thread producer2([&] {
+                    for (std::size_t r = 0; r < nbulk; r += 1000) ready2.store(std::min<std::size_t>(nbulk, r + 1000), std::memory_order_release);
+                });
+                hash_set<int, H> x;
+                CHECK(x._bulk_unique_fill_streamed(
+                    nbulk, [&](std::size_t i) { return grouped[i]; }, [&](std::size_t i) { return static_cast<std::size_t>(grouped[i]); }, nt,
+                    static_cast<unsigned>(n_groups),
+                    [&](std::size_t hi) {
+                        while (ready2.load(std::memory_order_acquire) < hi) std::this_thread::yield();
+                        return true;
+                    },
+                    [&](unsigned g) { return std::make_pair(goff[g], goff[g + 1]); }, true));
+                producer2.join();
+                CHECK_EQUAL(x.size(), nbulk);
+                CHECK_EQUAL(x.bucket_count(), nb);
+                std::size_t hits2 = 0;
+                for (std::size_t i = 0; i < nbulk; ++i) hits2 += x.find(static_cast<int>(i * 3)) != x.end();
+                CHECK_EQUAL(hits2, nbulk);
+                CHECK(x.find(1) == x.end());
+                // ranges that do not tile [0, n): refused, empty set
+                CHECK(!x._bulk_unique_fill_streamed(
+                    nbulk, [&](std::size_t i) { return grouped[i]; }, [&](std::size_t i) { return static_cast<std::size_t>(grouped[i]); }, nt,
+                    static_cast<unsigned>(n_groups), [](std::size_t) { return true; },
+                    [&](unsigned g) { return std::make_pair(goff[g], g + 1 == n_groups ? goff[g + 1] - 1 : goff[g + 1]); }, true));
+                CHECK(x.empty());
+            }
             // a producer that gives up half way: false, and an empty, reusable set
             ready.store(nbulk / 2);
             failed.store(true);

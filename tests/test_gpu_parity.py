@@ -1050,9 +1050,11 @@ def test_download_grouped(ctx, shift, bits):
     assert_terms_equal((key[back], mag[back], sign[back]), plain)
     # the same in pieces, with the progress callback after each
     seen = []
-    k2, m2, s2 = ctx.download_grouped(r, shift, bits, n_chunks=7, progress=seen.append)
+    offsets = np.full((1 << bits) + 1, 12345, dtype=np.uint64)
+    k2, m2, s2 = ctx.download_grouped(r, shift, bits, n_chunks=7, progress=seen.append, offsets=offsets)
     assert seen == [len(key) * (c + 1) // 7 for c in range(7)]
     assert np.array_equal(k2, key) and np.array_equal(m2, mag) and np.array_equal(s2, sign)
+    assert np.array_equal(offsets, np.searchsorted(group, np.arange((1 << bits) + 1, dtype=np.uint64), side="left"))  # first term of every group
     empty = ctx.mul_dev(ctx.upload(terms({}, nv), nv), ctx.upload(b, nv))
     assert len(ctx.download_grouped(empty, shift, bits)[0]) == 0
     assert len(ctx.download_grouped(empty, shift, bits, n_chunks=3, progress=seen.append)[0]) == 0 and len(seen) == 7
